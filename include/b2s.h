@@ -1,0 +1,219 @@
+/* b2s.h -- C ABI of libb2s.so: the B200-native (sm_100a) audio-prompt forward / loss path.
+ *
+ * Drop-in boundary for wonjune-kang/llm-speech-summarization's one hot path. The reference
+ * is pure Python, so "the FFI a maintainer would bind" is ctypes; every entry point
+ * below names the reference code it replaces (REF/ = /root/reference, TF/ = transformers).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative b2s_status; b2s_last_error() gives the message
+ *     (thread-local); the Python shim turns a nonzero status into RuntimeError;
+ *   - all pointers are DEVICE pointers unless marked host; sizes are explicit; `stream` is a cudaStream_t
+ *     passed as void* (the caller's current stream); no function synchronises or allocates caller-visible
+ *     memory: outputs and workspaces are allocated by the caller (torch.empty) and passed in;
+ *   - bf16 tensors are `void*` to keep the header free of CUDA types; fp32 tensors are `float*`;
+ *   - no CPU fallback exists: without a CUDA device every compute entry point fails with B2S_ERR_CUDA.
+ */
+#ifndef B2S_H_
+#define B2S_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B2S_STATUS_OK = 0,
+  B2S_STATUS_INVALID = -1,
+  B2S_STATUS_CUDA = -2,
+  B2S_STATUS_UNSUPPORTED = -3
+} b2s_status;
+
+/* epilogue ids of b2s_gemm_bf16 */
+enum { B2S_EPI_BF16 = 0, B2S_EPI_RESID_F32 = 1, B2S_EPI_SWIGLU = 2, B2S_EPI_ROPE = 3, B2S_EPI_F32 = 4 };
+enum { B2S_ACT_NONE = 0, B2S_ACT_GELU = 1 };
+
+const char* b2s_last_error(void);
+int b2s_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long b2s_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense contraction: out = epi(A . W^T).  Replaces every nn.Linear / Conv1d(C_in >= 512) on the path
+ * (TF/models/hubert/modeling_hubert.py:45-92,127-151,216-231,262-369; REF/model/audio_encoder.py:87;
+ *  TF/models/llama/modeling_llama.py:171-289; REF/model/audio_llama.py:67).
+ * A is a bf16 3-D view (k contiguous | row stride | batch stride); see csrc/gemm_sm100.cuh for the meaning
+ * of taps / a_pad / groups (strided and grouped convolutions as implicit GEMM, zero padding by TMA). */
+typedef struct {
+  const void* A;
+  int32_t a_dim0;
+  int64_t a_row_stride;
+  int64_t a_batch_stride;
+  int32_t a_rows;
+  const void* W;
+  int32_t w_rows;
+  int32_t w_cols;
+  int32_t M, N, batches, groups, taps, k_per_tap, a_pad, a_group_off, w_group_off;
+  int32_t epi, act;
+  const float* bias;
+  void* out;
+  int64_t ldo;
+  int64_t out_batch_rows;
+  const float* resid;
+  const float* rope_cs;
+  const int32_t* positions;
+  int32_t rope_cols;
+  int32_t block_n;   /* 0 = auto, else 64/128/256 */
+  int32_t cta_group; /* 0 = auto, else 1/2 */
+} b2s_gemm_args;
+int b2s_gemm_bf16(const b2s_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused CE + logit-KD loss over packed response rows.  Replaces utils.soft_cross_entropy
+ * (REF/utils.py:167-178, call site REF/trainer.py:349-352) and the per-sample CrossEntropyLoss of
+ * AudioLlamaForCausalLM.forward (REF/model/audio_llama.py:72-101).
+ *   student/teacher: bf16 [rows, V] (leading dims lds/ldt); labels[row] = target id for the CE term or -1;
+ *   row_offsets: int32 [utterances+1] segment boundaries; outputs per utterance: loss_ld, loss_ntp (means);
+ *   lse_s/lse_t/coef_kd/coef_ce: fp32 [rows] saved for the backward (coef = scale / count). */
+size_t b2s_kd_ce_workspace_bytes(int32_t rows, int32_t V);
+int b2s_kd_ce_loss_fwd(const void* student, const void* teacher, int64_t lds, int64_t ldt, int32_t rows, int32_t V,
+                       const int32_t* labels, const int32_t* row_offsets, int32_t utterances, float scale_kd,
+                       float scale_ce, void* workspace, float* lse_s, float* lse_t, float* coef_kd, float* coef_ce,
+                       float* loss_ld, float* loss_ntp, void* stream);
+/* d(sum_u scale_kd*ld_u + scale_ce*ntp_u)/d student, bf16 [rows, V]; the teacher gets no gradient
+ * (.detach(), REF/trainer.py:351). */
+int b2s_kd_ce_loss_bwd(const void* student, const void* teacher, int64_t lds, int64_t ldt, int32_t rows, int32_t V,
+                       const int32_t* labels, const float* lse_s, const float* lse_t, const float* coef_kd,
+                       const float* coef_ce, void* d_student, int64_t ldd, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Normalisation family (TF/models/hubert/modeling_hubert.py:127-151,216-231,505-548,613;
+ * TF/models/llama/modeling_llama.py:53-67; REF/model/audio_encoder.py:59-63). */
+int b2s_layernorm_fwd(const void* x, int32_t in_bf16, const float* gamma, const float* beta, float eps,
+                      int32_t act_gelu, void* y_bf16, int64_t rows, int32_t C, void* stream);
+int b2s_rmsnorm_fwd(const float* x, const float* w, float eps, void* y_bf16, int64_t rows, int32_t C, void* stream);
+int b2s_rmsnorm_gather_fwd(const float* x, const int32_t* row_index, const float* w, float eps, void* y_bf16,
+                           int64_t rows, int32_t C, void* stream);
+int b2s_layernorm_avgpool_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y_bf16,
+                              int32_t batches, int32_t frames, int32_t C, int32_t kernel, int32_t stride,
+                              int32_t out_frames, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Remaining memory-bound ops. */
+/* HuBERT feature-extractor layer 0 (TF/models/hubert/modeling_hubert.py:127-151, layer_id 0) */
+int b2s_conv0_ln_gelu_fwd(const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, const float* w,
+                          const float* bias, const float* gamma, const float* beta, float eps, void* y_bf16,
+                          int32_t out_frames, void* stream);
+/* embedding gather + audio splice (REF/utils.py:27-46,49-73,85-164; REF/inference.py:113-134):
+ * h0[row] = row_src[row] >= 0 ? embed_tokens[row_src[row]] : audio_embeds[-(row_src[row]+1)] */
+int b2s_embed_splice_fwd(const void* embed_table_bf16, const float* audio_embeds, const int32_t* row_src, float* h0,
+                         int64_t rows, int32_t C, void* stream);
+/* per-row-pair sum of squared differences, the core of the FD MSE (REF/trainer.py:358-370) */
+int b2s_rowpair_sqdiff_fwd(const float* h, const int32_t* rows_a, const int32_t* rows_b, float* out, int32_t pairs,
+                           int32_t C, void* stream);
+/* weight-norm(dim=2) + K-major repack of the positional conv weight (TF/models/hubert/modeling_hubert.py:45-92) */
+int b2s_posconv_weight_pack(const float* g, const float* v, void* w_packed_bf16, int32_t cout, int32_t cin_g,
+                            int32_t k, void* stream);
+int b2s_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+int b2s_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
+
+/* Packed varlen attention forward (TF/models/hubert/modeling_hubert.py:262-345;
+ * TF/models/llama/modeling_llama.py:225-289). */
+int b2s_attention_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
+                      const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t Hq, int32_t Hkv,
+                      int32_t D, float scale, int32_t causal, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-model entry points (the layer loops run in C++, one call per forward). */
+typedef struct {
+  const float *ln1_g, *ln1_b;
+  const void* wqkv;  /* bf16 [3H, H]: q | k | v rows */
+  const float* bqkv; /* fp32 [3H] (k bias zero for Whisper) */
+  const void* wo;
+  const float* bo;
+  const float *ln2_g, *ln2_b;
+  const void* w1; /* bf16 [F, H] */
+  const float* b1;
+  const void* w2; /* bf16 [H, F] */
+  const float* b2;
+} b2s_encoder_layer;
+
+typedef struct {
+  /* conv feature extractor: layer 0 on CUDA cores, layers 1..6 as implicit GEMM */
+  const float *conv0_w, *conv0_b, *conv0_ln_g, *conv0_ln_b;
+  const void* conv_w[6]; /* bf16 [512, k*512], column = tap*512 + c_in */
+  const float* conv_b[6];
+  const float* conv_ln_g[6];
+  const float* conv_ln_b[6];
+  int32_t conv_k[6];
+  int32_t conv_stride[6];
+  /* feature projection */
+  const float *fp_ln_g, *fp_ln_b;
+  const void* fp_w; /* bf16 [H, 512] */
+  const float* fp_b;
+  /* positional conv (weight-normed, packed by b2s_posconv_weight_pack) */
+  const void* pos_w; /* bf16 [H][K=128][H/groups] */
+  const float* pos_b;
+  int32_t pos_k, pos_groups;
+  /* transformer */
+  const b2s_encoder_layer* layers; /* host array */
+  int32_t num_layers, hidden, heads, ffn;
+  const float *final_ln_g, *final_ln_b;
+  float ln_eps;
+  /* AudioEncoder pooling + projector (REF/model/audio_encoder.py:34-42,59-63,87) */
+  int32_t pool_kernel, pool_stride;
+  const void* proj_w; /* bf16 [llm_dim, H] */
+  const float* proj_b;
+  int32_t llm_dim;
+} b2s_hubert_weights;
+
+/* frames produced by the conv stack for `samples` input samples; pooled = AvgPool1d output length */
+int b2s_hubert_num_frames(const b2s_hubert_weights* w, int32_t samples, int32_t* frames, int32_t* pooled);
+size_t b2s_hubert_workspace_bytes(const b2s_hubert_weights* w, int32_t batches, int32_t samples);
+/* AudioEncoder.forward for the HuBERT + "pool" configuration (REF/model/audio_encoder.py:56-88 over
+ * TF/models/hubert/modeling_hubert.py:889-958), eval mode. wave: fp32 [batches, samples] (row stride
+ * wave_stride). audio_embeds: fp32 [batches*pooled, llm_dim]. last_hidden (optional, may be NULL):
+ * fp32 [batches*frames, hidden] pre-final-LN residual stream, for parity tests. */
+int b2s_hubert_forward(const b2s_hubert_weights* w, const float* wave, int64_t wave_stride, int32_t batches,
+                       int32_t samples, void* workspace, size_t workspace_bytes, float* audio_embeds,
+                       float* last_hidden, void* stream);
+
+typedef struct {
+  const float* ln1_w;
+  const void* wqkv; /* bf16 [(Hq+2Hkv)*D, H] */
+  const void* wo;   /* bf16 [H, Hq*D] */
+  const float* ln2_w;
+  const void* wgu;  /* bf16 [2F, H], 64 gate rows | 64 up rows interleaved */
+  const void* wd;   /* bf16 [H, F] */
+} b2s_llama_layer;
+
+typedef struct {
+  const b2s_llama_layer* layers; /* host array */
+  int32_t num_layers, hidden, heads, kv_heads, head_dim, ffn, vocab;
+  float rms_eps;
+  const float* final_norm_w;
+  const void* lm_head;   /* bf16 [vocab, H] */
+  const float* rope_cs;  /* fp32 [max_pos, head_dim]: cos[0:D/2] | sin[0:D/2] */
+  int32_t max_pos;
+} b2s_llama_weights;
+
+size_t b2s_llama_workspace_bytes(const b2s_llama_weights* w, int32_t rows, int32_t logit_rows);
+/* LlamaModel.forward + lm_head over a packed batch of sequences (REF/model/audio_llama.py:49-67 over
+ * TF/models/llama/modeling_llama.py:375-425), eval mode, causal per sequence.
+ *   h: fp32 [rows, hidden] in: inputs_embeds (spliced); out: last layer's residual stream (pre final norm);
+ *   cu_seqlens int32 [num_seqs+1]; positions int32 [rows];
+ *   logit_rows_index int32 [logit_rows]: rows whose logits are produced -> logits bf16 [logit_rows, vocab];
+ *   fd taps (optional): for each t < num_taps, before layer tap_layers[t] runs, out
+ *   fd_sq[t*pairs + i] = sum_c (h[tap_rows_a[i], c] - h[tap_rows_b[i], c])^2   (REF/trainer.py:358-370). */
+int b2s_llama_prefill(const b2s_llama_weights* w, float* h, int32_t rows, const int32_t* cu_seqlens,
+                      int32_t num_seqs, int32_t max_seqlen, const int32_t* positions,
+                      const int32_t* logit_rows_index, int32_t logit_rows, void* logits_bf16,
+                      const int32_t* tap_layers /*host*/, int32_t num_taps, const int32_t* tap_rows_a,
+                      const int32_t* tap_rows_b, int32_t pairs, float* fd_sq, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H_ */

@@ -1,0 +1,120 @@
+"""ctypes binding of libb2s.so (the C ABI in include/b2s.h).
+
+There is deliberately no fallback: if the library is missing it is built in-tree with nvcc; if that fails,
+or a compute entry point is called without a CUDA device, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2s.so")
+
+c_void_p, c_int, c_int64, c_float, c_size_t = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+P_int = C.c_void_p  # device int32*
+P_f32 = C.c_void_p  # device float*
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", c_void_p), ("a_dim0", c_int), ("a_row_stride", c_int64), ("a_batch_stride", c_int64),
+        ("a_rows", c_int), ("W", c_void_p), ("w_rows", c_int), ("w_cols", c_int),
+        ("M", c_int), ("N", c_int), ("batches", c_int), ("groups", c_int), ("taps", c_int),
+        ("k_per_tap", c_int), ("a_pad", c_int), ("a_group_off", c_int), ("w_group_off", c_int),
+        ("epi", c_int), ("act", c_int), ("bias", c_void_p), ("out", c_void_p), ("ldo", c_int64),
+        ("out_batch_rows", c_int64), ("resid", c_void_p), ("rope_cs", c_void_p), ("positions", c_void_p),
+        ("rope_cols", c_int), ("block_n", c_int), ("cta_group", c_int),
+    ]
+
+
+class EncoderLayer(C.Structure):
+    _fields_ = [(n, c_void_p) for n in
+                ("ln1_g", "ln1_b", "wqkv", "bqkv", "wo", "bo", "ln2_g", "ln2_b", "w1", "b1", "w2", "b2")]
+
+
+class HubertWeights(C.Structure):
+    _fields_ = [
+        ("conv0_w", c_void_p), ("conv0_b", c_void_p), ("conv0_ln_g", c_void_p), ("conv0_ln_b", c_void_p),
+        ("conv_w", c_void_p * 6), ("conv_b", c_void_p * 6), ("conv_ln_g", c_void_p * 6), ("conv_ln_b", c_void_p * 6),
+        ("conv_k", c_int * 6), ("conv_stride", c_int * 6),
+        ("fp_ln_g", c_void_p), ("fp_ln_b", c_void_p), ("fp_w", c_void_p), ("fp_b", c_void_p),
+        ("pos_w", c_void_p), ("pos_b", c_void_p), ("pos_k", c_int), ("pos_groups", c_int),
+        ("layers", C.POINTER(EncoderLayer)), ("num_layers", c_int), ("hidden", c_int), ("heads", c_int),
+        ("ffn", c_int), ("final_ln_g", c_void_p), ("final_ln_b", c_void_p), ("ln_eps", c_float),
+        ("pool_kernel", c_int), ("pool_stride", c_int), ("proj_w", c_void_p), ("proj_b", c_void_p),
+        ("llm_dim", c_int),
+    ]
+
+
+class LlamaLayer(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("ln1_w", "wqkv", "wo", "ln2_w", "wgu", "wd")]
+
+
+class LlamaWeights(C.Structure):
+    _fields_ = [
+        ("layers", C.POINTER(LlamaLayer)), ("num_layers", c_int), ("hidden", c_int), ("heads", c_int),
+        ("kv_heads", c_int), ("head_dim", c_int), ("ffn", c_int), ("vocab", c_int), ("rms_eps", c_float),
+        ("final_norm_w", c_void_p), ("lm_head", c_void_p), ("rope_cs", c_void_p), ("max_pos", c_int),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/b2s.h one to one (tests/test_abi.py checks the symbol list)
+PROTOTYPES = {
+    "b2s_last_error": (C.c_char_p, []),
+    "b2s_version": (c_int, []),
+    "b2s_launch_count": (C.c_longlong, []),
+    "b2s_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
+    "b2s_kd_ce_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "b2s_kd_ce_loss_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, P_int, P_int, c_int, c_float,
+                                   c_float, c_void_p, P_f32, P_f32, P_f32, P_f32, P_f32, P_f32, c_void_p]),
+    "b2s_kd_ce_loss_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, P_int, P_f32, P_f32, P_f32,
+                                   P_f32, c_void_p, c_int64, c_void_p]),
+    "b2s_layernorm_fwd": (c_int, [c_void_p, c_int, P_f32, P_f32, c_float, c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "b2s_rmsnorm_fwd": (c_int, [P_f32, P_f32, c_float, c_void_p, c_int64, c_int, c_void_p]),
+    "b2s_rmsnorm_gather_fwd": (c_int, [P_f32, P_int, P_f32, c_float, c_void_p, c_int64, c_int, c_void_p]),
+    "b2s_layernorm_avgpool_fwd": (c_int, [P_f32, P_f32, P_f32, c_float, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                          c_int, c_void_p]),
+    "b2s_conv0_ln_gelu_fwd": (c_int, [P_f32, c_int64, c_int, c_int, P_f32, P_f32, P_f32, P_f32, c_float, c_void_p,
+                                      c_int, c_void_p]),
+    "b2s_embed_splice_fwd": (c_int, [c_void_p, P_f32, P_int, P_f32, c_int64, c_int, c_void_p]),
+    "b2s_rowpair_sqdiff_fwd": (c_int, [P_f32, P_int, P_int, P_f32, c_int, c_int, c_void_p]),
+    "b2s_posconv_weight_pack": (c_int, [P_f32, P_f32, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b2s_cast_f32_to_bf16": (c_int, [P_f32, c_void_p, c_int64, c_void_p]),
+    "b2s_cast_bf16_to_f32": (c_int, [c_void_p, P_f32, c_int64, c_void_p]),
+    "b2s_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, P_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "b2s_hubert_num_frames": (c_int, [C.POINTER(HubertWeights), c_int, C.POINTER(c_int), C.POINTER(c_int)]),
+    "b2s_hubert_workspace_bytes": (c_size_t, [C.POINTER(HubertWeights), c_int, c_int]),
+    "b2s_hubert_forward": (c_int, [C.POINTER(HubertWeights), P_f32, c_int64, c_int, c_int, c_void_p, c_size_t, P_f32,
+                                   P_f32, c_void_p]),
+    "b2s_llama_workspace_bytes": (c_size_t, [C.POINTER(LlamaWeights), c_int, c_int]),
+    "b2s_llama_prefill": (c_int, [C.POINTER(LlamaWeights), P_f32, c_int, P_int, c_int, c_int, P_int, P_int, c_int,
+                                  c_void_p, C.POINTER(c_int), c_int, P_int, P_int, c_int, P_f32, c_void_p, c_size_t,
+                                  c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load (building first if necessary) libb2s.so and attach prototypes. Raises on any failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build(verbose=False)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().b2s_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libb2s {what} failed with status {status}: {msg}")

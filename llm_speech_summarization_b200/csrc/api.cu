@@ -1,0 +1,197 @@
+// api.cu -- the extern "C" surface declared in include/b2s.h, plus status/error plumbing.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/b2s.h"
+#include "b2s_common.cuh"
+#include "gemm_sm100.cuh"
+#include "ops.cuh"
+
+namespace b2s {
+
+namespace {
+thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+}  // namespace
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_last_error("CUDA error %d (%s) at %s:%d: %s", static_cast<int>(e), cudaGetErrorString(e), file, line, what);
+  return B2S_ERR_CUDA;
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+      sms = 148;
+    }
+  }
+  return sms;
+}
+
+// models.cu
+int hubert_num_frames(const b2s_hubert_weights* w, int samples, int* frames, int* pooled);
+size_t hubert_workspace_bytes(const b2s_hubert_weights* w, int batches, int samples);
+int hubert_forward(const b2s_hubert_weights* w, const float* wave, long long wave_stride, int batches, int samples,
+                   void* workspace, size_t workspace_bytes, float* audio_embeds, float* last_hidden,
+                   cudaStream_t stream);
+size_t llama_workspace_bytes(const b2s_llama_weights* w, int rows, int logit_rows);
+int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_seqlens, int num_seqs, int max_seqlen,
+                  const int* positions, const int* logit_rows_index, int logit_rows, void* logits_bf16,
+                  const int* tap_layers, int num_taps, const int* tap_rows_a, const int* tap_rows_b, int pairs,
+                  float* fd_sq, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace b2s
+
+using namespace b2s;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* b2s_last_error(void) { return g_err; }
+int b2s_version(void) { return 1; }
+long long b2s_launch_count(void) { return launch_count(); }
+
+int b2s_gemm_bf16(const b2s_gemm_args* a, void* stream) {
+  if (a == nullptr) {
+    set_last_error("b2s_gemm_bf16: null args");
+    return B2S_ERR_INVALID;
+  }
+  GemmArgs g{};
+  g.A = a->A;
+  g.a_dim0 = a->a_dim0;
+  g.a_row_stride = a->a_row_stride;
+  g.a_batch_stride = a->a_batch_stride;
+  g.a_rows = a->a_rows;
+  g.W = a->W;
+  g.w_rows = a->w_rows;
+  g.w_cols = a->w_cols;
+  g.M = a->M;
+  g.N = a->N;
+  g.batches = a->batches;
+  g.groups = a->groups;
+  g.taps = a->taps;
+  g.k_per_tap = a->k_per_tap;
+  g.a_pad = a->a_pad;
+  g.a_group_off = a->a_group_off;
+  g.w_group_off = a->w_group_off;
+  g.epi = a->epi;
+  g.act = a->act;
+  g.bias = a->bias;
+  g.out = a->out;
+  g.ldo = a->ldo;
+  g.out_batch_rows = a->out_batch_rows;
+  g.resid = a->resid;
+  g.rope_cs = a->rope_cs;
+  g.positions = a->positions;
+  g.rope_cols = a->rope_cols;
+  g.block_n = a->block_n;
+  g.cta_group = a->cta_group;
+  return gemm_bf16_launch(g, S(stream));
+}
+
+size_t b2s_kd_ce_workspace_bytes(int32_t rows, int32_t V) { return kd_ce_workspace_bytes(rows, V); }
+
+int b2s_kd_ce_loss_fwd(const void* student, const void* teacher, int64_t lds, int64_t ldt, int32_t rows, int32_t V,
+                       const int32_t* labels, const int32_t* row_offsets, int32_t utterances, float scale_kd,
+                       float scale_ce, void* workspace, float* lse_s, float* lse_t, float* coef_kd, float* coef_ce,
+                       float* loss_ld, float* loss_ntp, void* stream) {
+  return kd_ce_loss_fwd(student, teacher, lds, ldt, rows, V, labels, row_offsets, utterances, scale_kd, scale_ce,
+                        workspace, lse_s, lse_t, coef_kd, coef_ce, loss_ld, loss_ntp, S(stream));
+}
+
+int b2s_kd_ce_loss_bwd(const void* student, const void* teacher, int64_t lds, int64_t ldt, int32_t rows, int32_t V,
+                       const int32_t* labels, const float* lse_s, const float* lse_t, const float* coef_kd,
+                       const float* coef_ce, void* d_student, int64_t ldd, void* stream) {
+  return kd_ce_loss_bwd(student, teacher, lds, ldt, rows, V, labels, lse_s, lse_t, coef_kd, coef_ce, d_student, ldd,
+                        S(stream));
+}
+
+int b2s_layernorm_fwd(const void* x, int32_t in_bf16, const float* gamma, const float* beta, float eps,
+                      int32_t act_gelu, void* y_bf16, int64_t rows, int32_t C, void* stream) {
+  return layernorm_fwd(x, in_bf16, gamma, beta, eps, act_gelu, y_bf16, rows, C, S(stream));
+}
+int b2s_rmsnorm_fwd(const float* x, const float* w, float eps, void* y_bf16, int64_t rows, int32_t C, void* stream) {
+  return rmsnorm_fwd(x, w, eps, y_bf16, rows, C, S(stream));
+}
+int b2s_rmsnorm_gather_fwd(const float* x, const int32_t* row_index, const float* w, float eps, void* y_bf16,
+                           int64_t rows, int32_t C, void* stream) {
+  return rmsnorm_gather_fwd(x, row_index, w, eps, y_bf16, rows, C, S(stream));
+}
+int b2s_layernorm_avgpool_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y_bf16,
+                              int32_t batches, int32_t frames, int32_t C, int32_t kernel, int32_t stride,
+                              int32_t out_frames, void* stream) {
+  return layernorm_avgpool_fwd(x, gamma, beta, eps, y_bf16, batches, frames, C, kernel, stride, out_frames, S(stream));
+}
+int b2s_conv0_ln_gelu_fwd(const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, const float* w,
+                          const float* bias, const float* gamma, const float* beta, float eps, void* y_bf16,
+                          int32_t out_frames, void* stream) {
+  return conv0_ln_gelu_fwd(wave, wave_stride, batches, samples, w, bias, gamma, beta, eps, y_bf16, out_frames,
+                           S(stream));
+}
+int b2s_embed_splice_fwd(const void* embed_table_bf16, const float* audio_embeds, const int32_t* row_src, float* h0,
+                         int64_t rows, int32_t C, void* stream) {
+  return embed_splice_fwd(embed_table_bf16, audio_embeds, row_src, h0, rows, C, S(stream));
+}
+int b2s_rowpair_sqdiff_fwd(const float* h, const int32_t* rows_a, const int32_t* rows_b, float* out, int32_t pairs,
+                           int32_t C, void* stream) {
+  return rowpair_sqdiff_fwd(h, rows_a, rows_b, out, pairs, C, S(stream));
+}
+int b2s_posconv_weight_pack(const float* g, const float* v, void* w_packed_bf16, int32_t cout, int32_t cin_g,
+                            int32_t k, void* stream) {
+  return posconv_weight_pack(g, v, w_packed_bf16, cout, cin_g, k, S(stream));
+}
+int b2s_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
+  return cast_f32_to_bf16(x, y, n, S(stream));
+}
+int b2s_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
+  return cast_bf16_to_f32(x, y, n, S(stream));
+}
+int b2s_attention_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
+                      const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t Hq, int32_t Hkv,
+                      int32_t D, float scale, int32_t causal, void* stream) {
+  return attention_fwd(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, Hq, Hkv, D, scale, causal,
+                       S(stream));
+}
+
+int b2s_hubert_num_frames(const b2s_hubert_weights* w, int32_t samples, int32_t* frames, int32_t* pooled) {
+  return hubert_num_frames(w, samples, frames, pooled);
+}
+size_t b2s_hubert_workspace_bytes(const b2s_hubert_weights* w, int32_t batches, int32_t samples) {
+  return hubert_workspace_bytes(w, batches, samples);
+}
+int b2s_hubert_forward(const b2s_hubert_weights* w, const float* wave, int64_t wave_stride, int32_t batches,
+                       int32_t samples, void* workspace, size_t workspace_bytes, float* audio_embeds,
+                       float* last_hidden, void* stream) {
+  return hubert_forward(w, wave, wave_stride, batches, samples, workspace, workspace_bytes, audio_embeds, last_hidden,
+                        S(stream));
+}
+size_t b2s_llama_workspace_bytes(const b2s_llama_weights* w, int32_t rows, int32_t logit_rows) {
+  return llama_workspace_bytes(w, rows, logit_rows);
+}
+int b2s_llama_prefill(const b2s_llama_weights* w, float* h, int32_t rows, const int32_t* cu_seqlens,
+                      int32_t num_seqs, int32_t max_seqlen, const int32_t* positions,
+                      const int32_t* logit_rows_index, int32_t logit_rows, void* logits_bf16,
+                      const int32_t* tap_layers, int32_t num_taps, const int32_t* tap_rows_a,
+                      const int32_t* tap_rows_b, int32_t pairs, float* fd_sq, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return llama_prefill(w, h, rows, cu_seqlens, num_seqs, max_seqlen, positions, logit_rows_index, logit_rows,
+                       logits_bf16, tap_layers, num_taps, tap_rows_a, tap_rows_b, pairs, fd_sq, workspace,
+                       workspace_bytes, S(stream));
+}
+
+}  // extern "C"

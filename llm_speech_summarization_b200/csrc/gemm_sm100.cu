@@ -1,0 +1,536 @@
+// gemm_sm100.cu -- the one dense-contraction kernel of the hot path: a persistent, warp-specialised
+// tcgen05 GEMM for sm_100a.
+//
+//   * operands: bf16, both K-major (activations row-major, weights in nn.Linear [out, in] layout),
+//     staged into shared memory by TMA with the 128-byte swizzle, BLOCK_K = 64 (one swizzle atom);
+//   * math: tcgen05.mma kind::f16, fp32 accumulators in TMEM, UMMA 128 x BN x 16 (cta_group::1) or
+//     256 x BN x 16 across a CTA pair (cta_group::2, A split by rows, W split by columns);
+//   * pipeline: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+//     warps 4-7 = epilogue (TMEM -> registers -> fused epilogue -> global); smem ring of kStages
+//     full/empty mbarriers; TMEM accumulators double-buffered (2 x BN columns) so the epilogue of tile i
+//     overlaps the main loop of tile i+1; persistent CTAs walk a static, L2-friendly tile order.
+//   * fused epilogues: bias, erf-GELU, fp32 residual add, SwiGLU (gate|up packed), rotate-half RoPE.
+//
+// Replaces (reference path): every nn.Linear / Conv1d(k>1, C_in=512|1024) the reference executes through
+// transformers -- HubertAttention/FeedForward projections, the conv feature extractor layers 1-6 and the
+// positional conv (TF/models/hubert/modeling_hubert.py:45-92,127-151,262-369), AudioEncoder.embed_projection
+// (REF/model/audio_encoder.py:87), LlamaAttention/LlamaMLP projections and lm_head
+// (TF/models/llama/modeling_llama.py:171-289, REF/model/audio_llama.py:67).
+#include "gemm_sm100.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "b2s_common.cuh"
+#include "b2s_ptx.cuh"
+
+namespace b2s {
+
+namespace {
+
+constexpr int kBlockK = 64;           // bf16 elements = 128 bytes = one swizzle atom
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 256;
+constexpr int kATileBytes = 128 * kBlockK * 2;  // 16 KiB per CTA per stage
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int BN, int CG>
+struct Cfg {
+  static constexpr int kBRows = BN / CG;                    // W rows loaded per CTA per stage
+  static constexpr int kBTileBytes = kBRows * kBlockK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;  // power of two for BN in {64,128,256}
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
+};
+
+struct KParams {
+  int M, N;
+  int batches, groups;
+  int m_tiles, n_tiles;
+  int total_tiles;
+  int num_kb, kb_per_tap, k_per_tap;
+  int a_pad, a_group_off, w_group_off;
+  int epi, act;
+  const float* bias;
+  void* out;
+  long long ldo;
+  long long out_batch_rows;
+  const float* resid;
+  const float* rope_cs;
+  const int* positions;
+  int rope_cols;
+};
+
+struct TileCoord {
+  int b, g, m_t, n_t;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
+  constexpr int kGroupM = 8;
+  const int per_bg = p.m_tiles * p.n_tiles;
+  const int bg = t / per_bg;
+  const int r = t - bg * per_bg;
+  const int span = kGroupM * p.n_tiles;
+  const int gid = r / span;
+  const int first_m = gid * kGroupM;
+  const int gsz = min(p.m_tiles - first_m, kGroupM);
+  const int rr = r - gid * span;
+  TileCoord c;
+  c.m_t = first_m + rr % gsz;
+  c.n_t = rr / gsz;
+  c.b = bg / p.groups;
+  c.g = bg - c.b * p.groups;
+  return c;
+}
+
+// ---- epilogue helpers ------------------------------------------------------------------------
+__device__ __forceinline__ void add_bias_act(float (&v)[32], const float* bias, int act) {
+  if (bias != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + q);
+      v[4 * q + 0] += b4.x;
+      v[4 * q + 1] += b4.y;
+      v[4 * q + 2] += b4.z;
+      v[4 * q + 3] += b4.w;
+    }
+  }
+  if (act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  }
+}
+
+// store 32 consecutive fp32 values of one row as bf16 (ncols_valid multiple of 8)
+__device__ __forceinline__ void store_bf16_32(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (q * 8 < ncols_valid) {
+      uint4 u;
+      u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]);
+      u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+      u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]);
+      u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+      *reinterpret_cast<uint4*>(dst + 8 * q) = u;
+    }
+  }
+}
+
+template <int BN, int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                         const KParams p) {
+  using C = Cfg<BN, CG>;
+  constexpr int kStages = C::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment required by the 128B swizzle atoms
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(full_bar(s), CG);   // one arrive(+tx) per CTA producer, all on the leader's barrier
+      ptx::mbar_init(empty_bar(s), 1);   // one tcgen05.commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tfull_bar(s), 1);        // one tcgen05.commit
+      ptx::mbar_init(tempty_bar(s), 4 * CG);  // one arrive per epilogue warp (both CTAs -> leader)
+    }
+    ptx::fence_mbar_init();
+  }
+  if (CG == 2) ptx::cluster_sync_all();  // peer smem must be live before a 2-SM allocation
+  if (warp == 2) {
+    ptx::tmem_alloc<CG>(tmem_slot, C::kTmemCols);
+  }
+  ptx::tc_fence_before();
+  if (CG == 2) {
+    ptx::cluster_sync_all();
+  } else {
+    __syncthreads();
+  }
+  ptx::tc_fence_after();
+
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0 && lane == 0) {
+    // ============================== TMA producer ==============================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
+      const TileCoord tc = decode_tile(p, t);
+      const int m0 = tc.m_t * (128 * CG) + static_cast<int>(cta_rank) * 128;
+      const int n0 = tc.g * p.w_group_off + tc.n_t * BN + static_cast<int>(cta_rank) * C::kBRows;
+      const int a_c0_base = tc.g * p.a_group_off;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+        const int tap = kb / p.kb_per_tap;
+        const int kk = (kb - tap * p.kb_per_tap) * kBlockK;
+        const uint32_t sa = smem_base + stage * C::kStageBytes;
+        const uint32_t sb = sa + kATileBytes;
+        if (CG == 1) {
+          ptx::mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
+          ptx::tma_load_3d(&tmap_a, full_bar(stage), sa, a_c0_base + kk, m0 + tap - p.a_pad, tc.b);
+          ptx::tma_load_2d(&tmap_w, full_bar(stage), sb, tap * p.k_per_tap + kk, n0);
+        } else {
+          if (cta_rank == 0) {
+            ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+          } else {
+            ptx::mbar_arrive_cluster(full_bar(stage), 0);
+          }
+          ptx::tma_load_3d_2sm(&tmap_a, full_bar(stage), sa, a_c0_base + kk, m0 + tap - p.a_pad, tc.b);
+          ptx::tma_load_2d_2sm(&tmap_w, full_bar(stage), sb, tap * p.k_per_tap + kk, n0);
+        }
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+    // ============================== MMA issuer ==============================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128 * CG, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = cluster_id; t < p.total_tiles; t += num_clusters, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        ptx::mbar_wait(full_bar(stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = smem_base + stage * C::kStageBytes;
+        const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa);
+        const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sa + kATileBytes);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+          ptx::umma_bf16<CG>(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit<CG>(empty_bar(stage));  // frees this smem stage (both CTAs) when the MMAs retire
+        if (kb == p.num_kb - 1) ptx::umma_commit<CG>(tfull_bar(as));
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================== epilogue ==============================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the only ones this warp may read
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    int it = 0;
+    for (int t = cluster_id; t < p.total_tiles; t += num_clusters, ++it) {
+      const TileCoord tc = decode_tile(p, t);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m = tc.m_t * (128 * CG) + static_cast<int>(cta_rank) * 128 + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      const long long orow = static_cast<long long>(tc.b) * p.out_batch_rows + m;
+      const int ncol0 = tc.n_t * BN;  // column inside the group
+      const float* bias = p.bias ? p.bias + static_cast<long long>(tc.g) * p.N : nullptr;
+
+      ptx::mbar_wait(tfull_bar(as), aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_base + as * BN;
+
+      if (p.epi == EPI_BF16 || p.epi == EPI_F32 || p.epi == EPI_RESID_F32) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col = ncol0 + c * 32;
+          if (col >= p.N) break;
+          uint32_t raw[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, raw);
+          ptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          add_bias_act(v, bias ? bias + col : nullptr, p.act);
+          const int valid = min(32, p.N - col);
+          if (row_ok) {
+            const long long off = orow * p.ldo + static_cast<long long>(tc.g) * p.N + col;
+            if (p.epi == EPI_BF16) {
+              store_bf16_32(reinterpret_cast<__nv_bfloat16*>(p.out) + off, v, valid);
+            } else {
+              float* o = reinterpret_cast<float*>(p.out) + off;
+              const float* r = p.epi == EPI_RESID_F32 ? p.resid + off : nullptr;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (q * 4 < valid) {
+                  float4 x = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                  if (r != nullptr) {
+                    const float4 rr = *reinterpret_cast<const float4*>(r + 4 * q);
+                    x.x += rr.x;
+                    x.y += rr.y;
+                    x.z += rr.z;
+                    x.w += rr.w;
+                  }
+                  *reinterpret_cast<float4*>(o + 4 * q) = x;
+                }
+              }
+            }
+          }
+        }
+      } else {
+        // paired-chunk epilogues over 128-column blocks: chunk c pairs with chunk c+2
+        // (SwiGLU: 64 gate | 64 up ; RoPE: head_dim 128 = first half | second half)
+        int pos = 0;
+        if (p.epi == EPI_ROPE && row_ok) pos = __ldg(p.positions + orow);
+#pragma unroll 1
+        for (int blk = 0; blk < BN / 128; ++blk) {
+          const int bcol = ncol0 + blk * 128;
+          if (bcol >= p.N) break;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t raw_lo[32], raw_hi[32];
+            ptx::tmem_ld_32x32(taddr + blk * 128 + c * 32, raw_lo);
+            ptx::tmem_ld_32x32(taddr + blk * 128 + (c + 2) * 32, raw_hi);
+            ptx::tmem_ld_wait();
+            float lo[32], hi[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              lo[i] = __uint_as_float(raw_lo[i]);
+              hi[i] = __uint_as_float(raw_hi[i]);
+            }
+            add_bias_act(lo, bias ? bias + bcol + c * 32 : nullptr, ACT_NONE);
+            add_bias_act(hi, bias ? bias + bcol + (c + 2) * 32 : nullptr, ACT_NONE);
+            if (p.epi == EPI_SWIGLU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) lo[i] = silu(lo[i]) * hi[i];
+              if (row_ok) {
+                const long long off =
+                    orow * p.ldo + (static_cast<long long>(tc.g) * p.N + bcol) / 2 + c * 32;
+                store_bf16_32(reinterpret_cast<__nv_bfloat16*>(p.out) + off, lo, 32);
+              }
+            } else {  // EPI_ROPE
+              if (bcol < p.rope_cols && row_ok) {
+                const float* cs = p.rope_cs + static_cast<long long>(pos) * 128 + c * 32;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs) + q);
+                  const float4 s4 = __ldg(reinterpret_cast<const float4*>(cs + 64) + q);
+                  const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+                  const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float a = lo[4 * q + j], b = hi[4 * q + j];
+                    lo[4 * q + j] = a * cc[j] - b * ss[j];
+                    hi[4 * q + j] = b * cc[j] + a * ss[j];
+                  }
+                }
+              }
+              if (row_ok) {
+                const long long off = orow * p.ldo + static_cast<long long>(tc.g) * p.N + bcol + c * 32;
+                store_bf16_32(reinterpret_cast<__nv_bfloat16*>(p.out) + off, lo, 32);
+                store_bf16_32(reinterpret_cast<__nv_bfloat16*>(p.out) + off + 64, hi, 32);
+              }
+            }
+          }
+        }
+      }
+      // release this accumulator buffer back to the MMA issuer (leader CTA's barrier)
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 1) {
+          ptx::mbar_arrive(tempty_bar(as));
+        } else {
+          ptx::mbar_arrive_cluster(tempty_bar(as), 0);
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  if (CG == 2) {
+    ptx::cluster_sync_all();
+  } else {
+    __syncthreads();
+  }
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<CG>(tmem_base, C::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeFn>(sym);
+    }
+  });
+  return fn;
+}
+
+int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box) {
+  EncodeFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return B2S_ERR_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u)",
+                   static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                   (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)strides_bytes[0],
+                   (unsigned long long)(rank > 2 ? strides_bytes[1] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
+    return B2S_ERR_CUDA;
+  }
+  return B2S_OK;
+}
+
+template <int BN, int CG>
+int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const KParams& p, cudaStream_t stream) {
+  using C = Cfg<BN, CG>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, CG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2S_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  const int sms = num_sms();
+  int clusters = sms / CG;
+  if (clusters > p.total_tiles) clusters = p.total_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  count_launch();
+  B2S_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, p));
+  return B2S_OK;
+}
+
+}  // namespace
+
+int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
+  B2S_REQUIRE(a.A && a.W && a.out, "gemm: null pointer");
+  B2S_REQUIRE(a.M > 0 && a.N > 0 && a.k_per_tap > 0 && a.taps > 0 && a.batches > 0 && a.groups > 0,
+              "gemm: non-positive dimension");
+  B2S_REQUIRE(a.N % 8 == 0 && a.ldo % 8 == 0, "gemm: N and ldo must be multiples of 8");
+  B2S_REQUIRE(a.a_row_stride % 8 == 0 && a.a_batch_stride % 8 == 0 && a.w_cols % 8 == 0,
+              "gemm: strides must be multiples of 8 elements (16 bytes)");
+  B2S_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a.out) & 15) == 0,
+              "gemm: pointers must be 16-byte aligned");
+  B2S_REQUIRE(a.epi >= EPI_BF16 && a.epi <= EPI_F32, "gemm: bad epilogue id %d", a.epi);
+  if (a.epi == EPI_RESID_F32) B2S_REQUIRE(a.resid != nullptr, "gemm: residual epilogue needs resid");
+  if (a.epi == EPI_ROPE) {
+    B2S_REQUIRE(a.rope_cs && a.positions && a.N % 128 == 0 && a.rope_cols % 128 == 0,
+                "gemm: rope epilogue needs tables and 128-aligned heads");
+  }
+  if (a.epi == EPI_SWIGLU) B2S_REQUIRE(a.N % 128 == 0, "gemm: swiglu epilogue needs N %% 128 == 0");
+
+  int bn = a.block_n;
+  int cg = a.cta_group;
+  if (bn == 0) {
+    if (a.N <= 64) bn = 64;
+    else if (a.N % 256 != 0 && a.N % 128 == 0 && a.N < 1024) bn = 128;
+    else bn = 256;
+  }
+  if (cg == 0) cg = 1;
+  B2S_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: block_n must be 64/128/256");
+  B2S_REQUIRE(cg == 1 || cg == 2, "gemm: cta_group must be 1 or 2");
+  if (a.epi == EPI_ROPE || a.epi == EPI_SWIGLU) B2S_REQUIRE(bn >= 128, "gemm: paired epilogues need block_n >= 128");
+  if (a.groups > 1) B2S_REQUIRE(a.N % bn == 0 || a.N < bn, "gemm: grouped N must tile evenly");
+
+  KParams p{};
+  p.M = a.M;
+  p.N = a.N;
+  p.batches = a.batches;
+  p.groups = a.groups;
+  p.m_tiles = (a.M + 128 * cg - 1) / (128 * cg);
+  p.n_tiles = (a.N + bn - 1) / bn;
+  const long long total = 1LL * p.m_tiles * p.n_tiles * a.batches * a.groups;
+  B2S_REQUIRE(total < (1LL << 31), "gemm: too many tiles");
+  p.total_tiles = static_cast<int>(total);
+  p.kb_per_tap = (a.k_per_tap + kBlockK - 1) / kBlockK;
+  p.num_kb = p.kb_per_tap * a.taps;
+  p.k_per_tap = a.k_per_tap;
+  p.a_pad = a.a_pad;
+  p.a_group_off = a.a_group_off;
+  p.w_group_off = a.w_group_off;
+  p.epi = a.epi;
+  p.act = a.act;
+  p.bias = a.bias;
+  p.out = a.out;
+  p.ldo = a.ldo;
+  p.out_batch_rows = a.out_batch_rows;
+  p.resid = a.resid;
+  p.rope_cs = a.rope_cs;
+  p.positions = a.positions;
+  p.rope_cols = a.rope_cols;
+
+  CUtensorMap ta, tw;
+  {
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(a.a_dim0), static_cast<cuuint64_t>(a.a_rows),
+                          static_cast<cuuint64_t>(a.batches)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(a.a_row_stride) * 2,
+                             static_cast<cuuint64_t>(a.batches > 1 ? a.a_batch_stride : a.a_row_stride * a.a_rows) * 2};
+    if (strides[1] == 0) strides[1] = strides[0];
+    cuuint32_t box[3] = {kBlockK, 128, 1};
+    int rc = encode_map(&ta, a.A, 3, dims, strides, box);
+    if (rc != B2S_OK) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(a.w_cols), static_cast<cuuint64_t>(a.w_rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(a.w_cols) * 2};
+    cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(bn / cg)};
+    int rc = encode_map(&tw, a.W, 2, dims, strides, box);
+    if (rc != B2S_OK) return rc;
+  }
+
+  if (bn == 256 && cg == 1) return launch_cfg<256, 1>(ta, tw, p, stream);
+  if (bn == 128 && cg == 1) return launch_cfg<128, 1>(ta, tw, p, stream);
+  if (bn == 64 && cg == 1) return launch_cfg<64, 1>(ta, tw, p, stream);
+  if (bn == 256 && cg == 2) return launch_cfg<256, 2>(ta, tw, p, stream);
+  if (bn == 128 && cg == 2) return launch_cfg<128, 2>(ta, tw, p, stream);
+  set_last_error("gemm: unsupported (block_n=%d, cta_group=%d)", bn, cg);
+  return B2S_ERR_UNSUPPORTED;
+}
+
+}  // namespace b2s

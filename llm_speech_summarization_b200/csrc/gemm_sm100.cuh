@@ -1,0 +1,62 @@
+// gemm_sm100.cuh -- argument block of the tcgen05 GEMM (see gemm_sm100.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b2s {
+
+enum EpiMode : int {
+  EPI_BF16 = 0,       // out_bf16 = act(acc + bias)
+  EPI_RESID_F32 = 1,  // out_f32  = resid_f32 + act(acc + bias)          (out may alias resid)
+  EPI_SWIGLU = 2,     // out_bf16[:, j] = silu(acc[:, j]) * acc[:, j + BN/2] per BN-wide tile (gate|up packed)
+  EPI_ROPE = 3,       // out_bf16 = rotate-half RoPE over 128-wide heads for cols < rope_cols, else passthrough
+  EPI_F32 = 4,        // out_f32  = act(acc + bias)
+};
+
+enum ActMode : int { ACT_NONE = 0, ACT_GELU = 1 };
+
+// C[b, m, g*N + n] = epi( sum_k A[b, m (+tap), k] * W[g*w_group_off + n, k] )
+// A is any bf16 tensor addressable as a 3-D TMA view (k contiguous, row stride, batch stride): plain
+// row-major activations, the overlapping strided views that turn a strided Conv1d into a GEMM, or the
+// "tap" walk used by the grouped positional convolution (row coordinate advances with the k-block and
+// out-of-range rows are zero-filled by TMA = the conv's zero padding).
+struct GemmArgs {
+  // A view
+  const void* A;
+  int a_dim0;               // extent of the contiguous dim (elements)
+  long long a_row_stride;   // elements between consecutive rows  (multiple of 8)
+  long long a_batch_stride; // elements between batches           (multiple of 8)
+  int a_rows;               // rows per batch addressable in the view (TMA zero-fills beyond)
+  // W: row-major [w_rows, w_cols] bf16 (nn.Linear layout: out_features x in_features)
+  const void* W;
+  int w_rows;
+  int w_cols;
+  // problem
+  int M;           // output rows per batch
+  int N;           // output cols per group
+  int batches;
+  int groups;
+  int taps;        // 1 for a plain GEMM
+  int k_per_tap;   // reduction elements per tap (K for a plain GEMM)
+  int a_pad;       // row coordinate = m + tap - a_pad
+  int a_group_off; // A column offset per group
+  int w_group_off; // W row offset per group
+  // epilogue
+  int epi;
+  int act;
+  const float* bias;        // [groups*N] fp32 or null
+  void* out;
+  long long ldo;            // output leading dim (elements)
+  long long out_batch_rows; // output row = b*out_batch_rows + m
+  const float* resid;       // EPI_RESID_F32: fp32 [rows, ldo]
+  const float* rope_cs;     // EPI_ROPE: [npos, 128] fp32 = cos[0:64] | sin[0:64]
+  const int* positions;     // EPI_ROPE: [rows] position of each row inside its own sequence
+  int rope_cols;
+  // tuning (0 = auto)
+  int block_n;    // 64 / 128 / 256
+  int cta_group;  // 1 / 2
+};
+
+int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream);
+
+}  // namespace b2s

@@ -1,0 +1,417 @@
+// models.cu -- whole-model forward passes: the layer loops of the audio encoder and of the LLM prefill run
+// here in C++ (one C-ABI call per forward; every step is an asynchronous launch on the caller's stream).
+//
+//   hubert_forward : AudioEncoder.forward, HuBERT + "pool" branch  (REF/model/audio_encoder.py:56-88 over
+//                    HubertModel.forward TF/models/hubert/modeling_hubert.py:889-958, eval mode)
+//   llama_prefill  : LlamaModel.forward + lm_head over packed sequences (REF/model/audio_llama.py:49-67 over
+//                    TF/models/llama/modeling_llama.py:375-425), plus the FD-loss hidden-state taps
+//                    (REF/trainer.py:358-370)
+//
+// Numerics: bf16 GEMM operands, fp32 accumulation, fp32 residual streams, fp32 norm statistics, fp32
+// pre-norm conv activations; everything the reference computes in fp32 on CPU is within bf16 rounding.
+#include "../../include/b2s.h"
+#include "b2s_common.cuh"
+#include "gemm_sm100.cuh"
+#include "ops.cuh"
+
+namespace b2s {
+namespace {
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  size_t cap;
+  Carver(void* b, size_t c) : base(reinterpret_cast<uint8_t*>(b)), cap(c) {}
+  void* take(size_t bytes) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+  bool ok() const { return off <= cap; }
+};
+
+int conv_out_len(int in, int k, int s) { return in < k ? 0 : (in - k) / s + 1; }
+
+struct HubertPlan {
+  int t[8];  // t[0] = samples, t[i+1] = frames after conv layer i
+  int frames, pooled;
+  size_t bytes;
+  // workspace pieces
+  void *xa, *xb;   // bf16 ping-pong channels-last conv activations
+  float* pre;      // fp32 pre-norm conv output
+  float* h;        // fp32 residual stream [B*frames, H]
+  void* xn;        // bf16 normalised activations [B*frames, H]
+  void* qkv;       // bf16 [B*frames, 3H]
+  void* ao;        // bf16 [B*frames, H]
+  void* ff;        // bf16 [B*frames, F]
+  void* pooled_x;  // bf16 [B*pooled, H]
+  int* cu;         // int32 [B+1]
+};
+
+int plan_hubert(const b2s_hubert_weights* w, int batches, int samples, void* ws, size_t ws_bytes, HubertPlan* pl) {
+  pl->t[0] = samples;
+  pl->t[1] = conv_out_len(samples, 10, 5);
+  for (int i = 0; i < 6; ++i) pl->t[i + 2] = conv_out_len(pl->t[i + 1], w->conv_k[i], w->conv_stride[i]);
+  pl->frames = pl->t[7];
+  pl->pooled = pl->frames >= w->pool_kernel ? (pl->frames - w->pool_kernel) / w->pool_stride + 1 : 0;
+  const size_t B = batches;
+  const size_t rows = B * pl->frames;
+  Carver c(ws, ws_bytes);
+  pl->xa = c.take(B * pl->t[1] * 512 * 2 + 4096);
+  pl->xb = c.take(B * pl->t[2] * 512 * 2 + 4096);
+  pl->pre = reinterpret_cast<float*>(c.take(B * pl->t[2] * 512 * 4));
+  pl->h = reinterpret_cast<float*>(c.take(rows * w->hidden * 4));
+  pl->xn = c.take(rows * w->hidden * 2);
+  pl->qkv = c.take(rows * 3 * w->hidden * 2);
+  pl->ao = c.take(rows * w->hidden * 2);
+  pl->ff = c.take(rows * w->ffn * 2);
+  pl->pooled_x = c.take(B * (pl->pooled > 0 ? pl->pooled : 1) * w->hidden * 2);
+  pl->cu = reinterpret_cast<int*>(c.take((B + 1) * sizeof(int)));
+  pl->bytes = c.off + 256;
+  if (ws != nullptr && !c.ok()) {
+    set_last_error("hubert workspace too small: need %zu bytes, got %zu", pl->bytes, ws_bytes);
+    return B2S_ERR_INVALID;
+  }
+  return B2S_OK;
+}
+
+__global__ void iota_scaled_kernel(int* out, int n, int scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i * scale;
+}
+
+GemmArgs plain_gemm(const void* A, const void* W, long long M, int N, int K) {
+  GemmArgs g{};
+  g.A = A;
+  g.a_dim0 = K;
+  g.a_row_stride = K;
+  g.a_batch_stride = 0;
+  g.a_rows = static_cast<int>(M);
+  g.W = W;
+  g.w_rows = N;
+  g.w_cols = K;
+  g.M = static_cast<int>(M);
+  g.N = N;
+  g.batches = 1;
+  g.groups = 1;
+  g.taps = 1;
+  g.k_per_tap = K;
+  g.ldo = N;
+  g.out_batch_rows = 0;
+  return g;
+}
+
+}  // namespace
+
+int hubert_num_frames(const b2s_hubert_weights* w, int samples, int* frames, int* pooled) {
+  B2S_REQUIRE(w != nullptr, "hubert: null weights");
+  HubertPlan pl;
+  int rc = plan_hubert(w, 1, samples, nullptr, 0, &pl);
+  if (rc != B2S_OK) return rc;
+  if (frames) *frames = pl.frames;
+  if (pooled) *pooled = pl.pooled;
+  return B2S_OK;
+}
+
+size_t hubert_workspace_bytes(const b2s_hubert_weights* w, int batches, int samples) {
+  if (w == nullptr || batches <= 0 || samples <= 0) return 0;
+  HubertPlan pl;
+  plan_hubert(w, batches, samples, nullptr, 0, &pl);
+  return pl.bytes;
+}
+
+int hubert_forward(const b2s_hubert_weights* w, const float* wave, long long wave_stride, int batches, int samples,
+                   void* workspace, size_t workspace_bytes, float* audio_embeds, float* last_hidden,
+                   cudaStream_t stream) {
+  B2S_REQUIRE(w && wave && workspace && audio_embeds, "hubert_forward: null pointer");
+  B2S_REQUIRE(batches > 0 && samples > 0, "hubert_forward: empty batch");
+  B2S_REQUIRE(w->hidden % 256 == 0 && w->hidden % w->heads == 0 && w->hidden / w->heads == 64,
+              "hubert_forward: hidden/heads must give head_dim 64");
+  B2S_REQUIRE(w->pos_groups > 0 && w->hidden / w->pos_groups == 64, "hubert_forward: positional conv needs 64 ch/group");
+  HubertPlan pl;
+  int rc = plan_hubert(w, batches, samples, workspace, workspace_bytes, &pl);
+  if (rc != B2S_OK) return rc;
+  B2S_REQUIRE(pl.frames > 0 && pl.pooled > 0, "hubert_forward: audio too short (%d samples -> %d frames)", samples,
+              pl.frames);
+  const int B = batches, H = w->hidden, F = w->ffn;
+  const long long rows = static_cast<long long>(B) * pl.frames;
+  const float eps = w->ln_eps;
+
+  // ---- conv feature extractor
+  rc = conv0_ln_gelu_fwd(wave, wave_stride, B, samples, w->conv0_w, w->conv0_b, w->conv0_ln_g, w->conv0_ln_b, eps,
+                         pl.xa, pl.t[1], stream);
+  if (rc != B2S_OK) return rc;
+  void* cur = pl.xa;
+  void* nxt = pl.xb;
+  for (int i = 0; i < 6; ++i) {
+    const int tin = pl.t[i + 1], tout = pl.t[i + 2];
+    const int k = w->conv_k[i], s = w->conv_stride[i];
+    GemmArgs g{};
+    g.A = cur;
+    g.a_dim0 = k * 512;                                // overlapping window view: row t = x[s*t : s*t+k, :]
+    g.a_row_stride = static_cast<long long>(s) * 512;
+    g.a_batch_stride = static_cast<long long>(tin) * 512;
+    g.a_rows = tout;
+    g.W = w->conv_w[i];
+    g.w_rows = 512;
+    g.w_cols = k * 512;
+    g.M = tout;
+    g.N = 512;
+    g.batches = B;
+    g.groups = 1;
+    g.taps = 1;
+    g.k_per_tap = k * 512;
+    g.epi = EPI_F32;
+    g.act = ACT_NONE;
+    g.bias = w->conv_b[i];
+    g.out = pl.pre;
+    g.ldo = 512;
+    g.out_batch_rows = tout;
+    rc = gemm_bf16_launch(g, stream);
+    if (rc != B2S_OK) return rc;
+    rc = layernorm_fwd(pl.pre, 0, w->conv_ln_g[i], w->conv_ln_b[i], eps, 1, nxt, static_cast<long long>(B) * tout, 512,
+                       stream);
+    if (rc != B2S_OK) return rc;
+    void* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  // cur: bf16 [B, frames, 512]
+
+  // ---- feature projection: LN(512) -> Linear(512 -> H)
+  rc = layernorm_fwd(cur, 1, w->fp_ln_g, w->fp_ln_b, eps, 0, nxt, rows, 512, stream);
+  if (rc != B2S_OK) return rc;
+  {
+    GemmArgs g = plain_gemm(nxt, w->fp_w, rows, H, 512);
+    g.epi = EPI_F32;
+    g.bias = w->fp_b;
+    g.out = pl.h;
+    rc = gemm_bf16_launch(g, stream);
+    if (rc != B2S_OK) return rc;
+  }
+  // ---- positional conv embedding: h += gelu(grouped_conv(h) + b)
+  rc = cast_f32_to_bf16(pl.h, pl.xn, rows * H, stream);
+  if (rc != B2S_OK) return rc;
+  {
+    GemmArgs g{};
+    g.A = pl.xn;
+    g.a_dim0 = H;
+    g.a_row_stride = H;
+    g.a_batch_stride = static_cast<long long>(pl.frames) * H;
+    g.a_rows = pl.frames;
+    g.W = w->pos_w;
+    g.w_rows = H;
+    g.w_cols = w->pos_k * 64;
+    g.M = pl.frames;
+    g.N = 64;
+    g.batches = B;
+    g.groups = w->pos_groups;
+    g.taps = w->pos_k;
+    g.k_per_tap = 64;
+    g.a_pad = w->pos_k / 2;
+    g.a_group_off = 64;
+    g.w_group_off = 64;
+    g.epi = EPI_RESID_F32;
+    g.act = ACT_GELU;
+    g.bias = w->pos_b;
+    g.out = pl.h;
+    g.resid = pl.h;
+    g.ldo = H;
+    g.out_batch_rows = pl.frames;
+    rc = gemm_bf16_launch(g, stream);
+    if (rc != B2S_OK) return rc;
+  }
+  // ---- transformer layers (stable layer norm = pre-LN)
+  iota_scaled_kernel<<<(B + 1 + 255) / 256, 256, 0, stream>>>(pl.cu, B + 1, pl.frames);
+  B2S_LAUNCH_CHECK();
+  for (int l = 0; l < w->num_layers; ++l) {
+    const b2s_encoder_layer& L = w->layers[l];
+    rc = layernorm_fwd(pl.h, 0, L.ln1_g, L.ln1_b, eps, 0, pl.xn, rows, H, stream);
+    if (rc != B2S_OK) return rc;
+    {
+      GemmArgs g = plain_gemm(pl.xn, L.wqkv, rows, 3 * H, H);
+      g.epi = EPI_BF16;
+      g.bias = L.bqkv;
+      g.out = pl.qkv;
+      rc = gemm_bf16_launch(g, stream);
+      if (rc != B2S_OK) return rc;
+    }
+    {
+      const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(pl.qkv);
+      rc = attention_fwd(qkv, qkv + H, qkv + 2 * H, 3 * H, pl.ao, H, pl.cu, B, pl.frames, w->heads, w->heads, 64,
+                         0.125f, 0, stream);
+      if (rc != B2S_OK) return rc;
+    }
+    {
+      GemmArgs g = plain_gemm(pl.ao, L.wo, rows, H, H);
+      g.epi = EPI_RESID_F32;
+      g.bias = L.bo;
+      g.out = pl.h;
+      g.resid = pl.h;
+      rc = gemm_bf16_launch(g, stream);
+      if (rc != B2S_OK) return rc;
+    }
+    rc = layernorm_fwd(pl.h, 0, L.ln2_g, L.ln2_b, eps, 0, pl.xn, rows, H, stream);
+    if (rc != B2S_OK) return rc;
+    {
+      GemmArgs g = plain_gemm(pl.xn, L.w1, rows, F, H);
+      g.epi = EPI_BF16;
+      g.act = ACT_GELU;
+      g.bias = L.b1;
+      g.out = pl.ff;
+      rc = gemm_bf16_launch(g, stream);
+      if (rc != B2S_OK) return rc;
+    }
+    {
+      GemmArgs g = plain_gemm(pl.ff, L.w2, rows, H, F);
+      g.epi = EPI_RESID_F32;
+      g.bias = L.b2;
+      g.out = pl.h;
+      g.resid = pl.h;
+      rc = gemm_bf16_launch(g, stream);
+      if (rc != B2S_OK) return rc;
+    }
+  }
+  if (last_hidden != nullptr) {
+    B2S_CUDA_CHECK(cudaMemcpyAsync(last_hidden, pl.h, rows * H * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  }
+  // ---- final LN + AvgPool1d + projector
+  rc = layernorm_avgpool_fwd(pl.h, w->final_ln_g, w->final_ln_b, eps, pl.pooled_x, B, pl.frames, H, w->pool_kernel,
+                             w->pool_stride, pl.pooled, stream);
+  if (rc != B2S_OK) return rc;
+  {
+    GemmArgs g = plain_gemm(pl.pooled_x, w->proj_w, static_cast<long long>(B) * pl.pooled, w->llm_dim, H);
+    g.epi = EPI_F32;
+    g.bias = w->proj_b;
+    g.out = audio_embeds;
+    rc = gemm_bf16_launch(g, stream);
+    if (rc != B2S_OK) return rc;
+  }
+  return B2S_OK;
+}
+
+// --------------------------------------------------------------------------------------------- Llama
+namespace {
+struct LlamaPlan {
+  void* xn;   // bf16 [rows, H]
+  void* qkv;  // bf16 [rows, (Hq+2Hkv)*D]
+  void* ao;   // bf16 [rows, Hq*D]
+  void* act;  // bf16 [rows, F]
+  void* xf;   // bf16 [logit_rows, H]
+  size_t bytes;
+};
+int plan_llama(const b2s_llama_weights* w, long long rows, long long logit_rows, void* ws, size_t ws_bytes,
+               LlamaPlan* pl) {
+  const size_t qkv_cols = static_cast<size_t>(w->heads + 2 * w->kv_heads) * w->head_dim;
+  Carver c(ws, ws_bytes);
+  pl->xn = c.take(rows * w->hidden * 2);
+  pl->qkv = c.take(rows * qkv_cols * 2);
+  pl->ao = c.take(static_cast<size_t>(rows) * w->heads * w->head_dim * 2);
+  pl->act = c.take(static_cast<size_t>(rows) * w->ffn * 2);
+  pl->xf = c.take(static_cast<size_t>(logit_rows > 0 ? logit_rows : 1) * w->hidden * 2);
+  pl->bytes = c.off + 256;
+  if (ws != nullptr && !c.ok()) {
+    set_last_error("llama workspace too small: need %zu bytes, got %zu", pl->bytes, ws_bytes);
+    return B2S_ERR_INVALID;
+  }
+  return B2S_OK;
+}
+}  // namespace
+
+size_t llama_workspace_bytes(const b2s_llama_weights* w, int rows, int logit_rows) {
+  if (w == nullptr || rows <= 0) return 0;
+  LlamaPlan pl;
+  plan_llama(w, rows, logit_rows, nullptr, 0, &pl);
+  return pl.bytes;
+}
+
+int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_seqlens, int num_seqs, int max_seqlen,
+                  const int* positions, const int* logit_rows_index, int logit_rows, void* logits_bf16,
+                  const int* tap_layers, int num_taps, const int* tap_rows_a, const int* tap_rows_b, int pairs,
+                  float* fd_sq, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  B2S_REQUIRE(w && h && cu_seqlens && positions && workspace, "llama_prefill: null pointer");
+  B2S_REQUIRE(rows > 0 && num_seqs > 0 && max_seqlen > 0, "llama_prefill: empty batch");
+  B2S_REQUIRE(w->head_dim == 128, "llama_prefill: head_dim must be 128 (got %d)", w->head_dim);
+  B2S_REQUIRE(w->hidden % 256 == 0 && w->ffn % 64 == 0, "llama_prefill: hidden %% 256, ffn %% 64 required");
+  B2S_REQUIRE(logit_rows == 0 || (logit_rows_index && logits_bf16), "llama_prefill: logits requested without buffers");
+  B2S_REQUIRE(num_taps == 0 || (tap_layers && tap_rows_a && tap_rows_b && fd_sq), "llama_prefill: taps without buffers");
+  LlamaPlan pl;
+  int rc = plan_llama(w, rows, logit_rows, workspace, workspace_bytes, &pl);
+  if (rc != B2S_OK) return rc;
+  const int H = w->hidden, D = w->head_dim, Hq = w->heads, Hkv = w->kv_heads, F = w->ffn;
+  const int qkv_cols = (Hq + 2 * Hkv) * D;
+  const float scale = 1.0f / sqrtf(static_cast<float>(D));
+
+  for (int l = 0; l < w->num_layers; ++l) {
+    for (int t = 0; t < num_taps; ++t) {
+      if (tap_layers[t] == l && pairs > 0) {
+        rc = rowpair_sqdiff_fwd(h, tap_rows_a, tap_rows_b, fd_sq + static_cast<long long>(t) * pairs, pairs, H, stream);
+        if (rc != B2S_OK) return rc;
+      }
+    }
+    const b2s_llama_layer& L = w->layers[l];
+    rc = rmsnorm_fwd(h, L.ln1_w, w->rms_eps, pl.xn, rows, H, stream);
+    if (rc != B2S_OK) return rc;
+    {
+      GemmArgs g = plain_gemm(pl.xn, L.wqkv, rows, qkv_cols, H);
+      g.epi = EPI_ROPE;
+      g.out = pl.qkv;
+      g.rope_cs = w->rope_cs;
+      g.positions = positions;
+      g.rope_cols = (Hq + Hkv) * D;
+      rc = gemm_bf16_launch(g, stream);
+      if (rc != B2S_OK) return rc;
+    }
+    {
+      const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(pl.qkv);
+      rc = attention_fwd(qkv, qkv + Hq * D, qkv + (Hq + Hkv) * D, qkv_cols, pl.ao, Hq * D, cu_seqlens, num_seqs,
+                         max_seqlen, Hq, Hkv, D, scale, 1, stream);
+      if (rc != B2S_OK) return rc;
+    }
+    {
+      GemmArgs g = plain_gemm(pl.ao, L.wo, rows, H, Hq * D);
+      g.epi = EPI_RESID_F32;
+      g.out = h;
+      g.resid = h;
+      rc = gemm_bf16_launch(g, stream);
+      if (rc != B2S_OK) return rc;
+    }
+    rc = rmsnorm_fwd(h, L.ln2_w, w->rms_eps, pl.xn, rows, H, stream);
+    if (rc != B2S_OK) return rc;
+    {
+      GemmArgs g = plain_gemm(pl.xn, L.wgu, rows, 2 * F, H);
+      g.epi = EPI_SWIGLU;
+      g.out = pl.act;
+      g.ldo = F;
+      rc = gemm_bf16_launch(g, stream);
+      if (rc != B2S_OK) return rc;
+    }
+    {
+      GemmArgs g = plain_gemm(pl.act, L.wd, rows, H, F);
+      g.epi = EPI_RESID_F32;
+      g.out = h;
+      g.resid = h;
+      rc = gemm_bf16_launch(g, stream);
+      if (rc != B2S_OK) return rc;
+    }
+  }
+  for (int t = 0; t < num_taps; ++t) {
+    if (tap_layers[t] == w->num_layers && pairs > 0) {
+      set_last_error("llama_prefill: tap at the post-norm output (index num_layers) is not supported");
+      return B2S_ERR_UNSUPPORTED;
+    }
+  }
+  if (logit_rows > 0) {
+    rc = rmsnorm_gather_fwd(h, logit_rows_index, w->final_norm_w, w->rms_eps, pl.xf, logit_rows, H, stream);
+    if (rc != B2S_OK) return rc;
+    GemmArgs g = plain_gemm(pl.xf, w->lm_head, logit_rows, w->vocab, H);
+    g.epi = EPI_BF16;
+    g.out = logits_bf16;
+    rc = gemm_bf16_launch(g, stream);
+    if (rc != B2S_OK) return rc;
+  }
+  return B2S_OK;
+}
+
+}  // namespace b2s

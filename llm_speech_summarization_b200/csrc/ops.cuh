@@ -1,0 +1,60 @@
+// ops.cuh -- internal C++ launchers for the memory-bound kernels and attention (see include/b2s.h for the
+// C ABI that wraps them). All take raw device pointers + sizes + the stream to enqueue on; none synchronise.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b2s {
+
+// ---- loss.cu
+size_t kd_ce_workspace_bytes(int rows, int V);
+int kd_ce_loss_fwd(const void* S, const void* T, long long lds, long long ldt, int rows, int V, const int* labels,
+                   const int* row_offsets, int utterances, float scale_kd, float scale_ce, void* workspace,
+                   float* lse_s, float* lse_t, float* coef_kd, float* coef_ce, float* loss_ld, float* loss_ntp,
+                   cudaStream_t stream);
+int kd_ce_loss_bwd(const void* S, const void* T, long long lds, long long ldt, int rows, int V, const int* labels,
+                   const float* lse_s, const float* lse_t, const float* coef_kd, const float* coef_ce, void* dS,
+                   long long ldd, cudaStream_t stream);
+
+// ---- norm.cu
+// y_bf16[r, :] = act( (x[r,:] - mean) * rstd * gamma + beta ); x is fp32 (in_bf16 = 0) or bf16 (in_bf16 = 1)
+int layernorm_fwd(const void* x, int in_bf16, const float* gamma, const float* beta, float eps, int act_gelu,
+                  void* y_bf16, long long rows, int C, cudaStream_t stream);
+// y_bf16[r, :] = x[r,:] * rsqrt(mean(x^2) + eps) * w ; x fp32
+int rmsnorm_fwd(const float* x, const float* w, float eps, void* y_bf16, long long rows, int C, cudaStream_t stream);
+// rows gathered through an index list (final norm on the consumed rows only)
+int rmsnorm_gather_fwd(const float* x, const int* row_index, const float* w, float eps, void* y_bf16, long long rows,
+                       int C, cudaStream_t stream);
+// final LayerNorm of the encoder fused with AvgPool1d(kernel, stride) over time:
+// y[b, j, :] = mean_{r<kernel} LN(x[b, j*stride + r, :])   (REF/model/audio_encoder.py:59-63)
+int layernorm_avgpool_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y_bf16, int batches,
+                          int frames, int C, int kernel, int stride, int out_frames, cudaStream_t stream);
+
+// ---- misc.cu
+// HuBERT conv layer 0: Conv1d(1->512,k=10,s=5)+bias -> LayerNorm(512) -> GELU, channels-last bf16 out
+int conv0_ln_gelu_fwd(const float* wave, long long wave_stride, int batches, int samples, const float* w /*[512,10]*/,
+                      const float* bias, const float* gamma, const float* beta, float eps, void* y_bf16, int out_frames,
+                      cudaStream_t stream);
+// h0[row, :] = src >= 0 ? embed_table[src, :] : audio_embeds[-(src+1), :]
+int embed_splice_fwd(const void* embed_table_bf16, const float* audio_embeds, const int* row_src, float* h0,
+                     long long rows, int C, cudaStream_t stream);
+// sum over columns of (a[ra[i], :] - b[rb[i], :])^2 -> out[i]
+int rowpair_sqdiff_fwd(const float* h, const int* rows_a, const int* rows_b, float* out, int pairs, int C,
+                       cudaStream_t stream);
+// w[co, ci, k] = g[k] * v[co, ci, k] / ||v[:, :, k]||, repacked bf16 as [co][k][ci] (K-major per tap)
+int posconv_weight_pack(const float* g, const float* v, void* w_packed_bf16, int cout, int cin_g, int k,
+                        cudaStream_t stream);
+int cast_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t stream);
+int cast_bf16_to_f32(const void* x, float* y, long long n, cudaStream_t stream);
+// y_bf16 = gelu(x_f32 + residual) etc. are fused in GEMM epilogues; nothing else elementwise is needed.
+
+// ---- attention.cu
+// Packed variable-length attention. q/k/v are bf16 views into one [rows, ld] buffer (fused QKV output):
+// head h of row r lives at base + r*ld + h*D. Sequences are rows [cu[s], cu[s+1]).
+// GQA: query head h uses kv head h / (Hq / Hkv). Output o bf16 [rows, Hq*D].
+int attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
+                  const int* cu_seqlens, int num_seqs, int max_seqlen, int Hq, int Hkv, int D, float scale, int causal,
+                  cudaStream_t stream);
+
+}  // namespace b2s

@@ -1,0 +1,212 @@
+"""Tensor-level wrappers over the C ABI: torch supplies device memory and the current stream, nothing else.
+
+Every function requires CUDA tensors and raises otherwise (there is no CPU path in this package; the CPU
+restatement lives in oracle/ and is test infrastructure only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs
+
+EPI_BF16, EPI_RESID_F32, EPI_SWIGLU, EPI_ROPE, EPI_F32 = 0, 1, 2, 3, 4
+ACT_NONE, ACT_GELU = 0, 1
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("llm_speech_summarization_b200 ops need CUDA tensors (no CPU fallback exists)")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, epi: int = EPI_BF16,
+         act: int = ACT_NONE, resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         rope_cs: Optional[torch.Tensor] = None, positions: Optional[torch.Tensor] = None, rope_cols: int = 0,
+         block_n: int = 0, cta_group: int = 0) -> torch.Tensor:
+    """out = epi(a @ w.T) for row-major bf16 a [M, K] and w [N, K]."""
+    _need_cuda(a, w, bias, resid, out)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    n_out = N // 2 if epi == EPI_SWIGLU else N
+    if out is None:
+        dt = torch.float32 if epi in (EPI_RESID_F32, EPI_F32) else torch.bfloat16
+        out = torch.empty(M, n_out, device=a.device, dtype=dt)
+    g = GemmArgs()
+    g.A, g.a_dim0, g.a_row_stride, g.a_batch_stride, g.a_rows = a.data_ptr(), K, K, 0, M
+    g.W, g.w_rows, g.w_cols = w.data_ptr(), N, K
+    g.M, g.N, g.batches, g.groups, g.taps, g.k_per_tap = M, N, 1, 1, 1, K
+    g.epi, g.act = epi, act
+    g.bias = _ptr(bias)
+    g.out, g.ldo, g.out_batch_rows = out.data_ptr(), out.stride(0), 0
+    g.resid = _ptr(resid)
+    g.rope_cs, g.positions, g.rope_cols = _ptr(rope_cs), _ptr(positions), rope_cols
+    g.block_n, g.cta_group = block_n, cta_group
+    _lib.check(_lib.load().b2s_gemm_bf16(C.byref(g), _stream()), "gemm")
+    return out
+
+
+def gemm_raw(args: GemmArgs) -> None:
+    _lib.check(_lib.load().b2s_gemm_bf16(C.byref(args), _stream()), "gemm")
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, gelu: bool = False,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, gamma, beta)
+    assert x.is_contiguous() and x.dtype in (torch.float32, torch.bfloat16)
+    C_ = x.shape[-1]
+    rows = x.numel() // C_
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().b2s_layernorm_fwd(x.data_ptr(), int(x.dtype == torch.bfloat16), gamma.data_ptr(),
+                                             beta.data_ptr(), eps, int(gelu), out.data_ptr(), rows, C_, _stream()),
+               "layernorm")
+    return out
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, rows_index: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, w, rows_index)
+    assert x.is_contiguous() and x.dtype == torch.float32
+    C_ = x.shape[-1]
+    if rows_index is None:
+        rows = x.numel() // C_
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+        _lib.check(_lib.load().b2s_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), eps, out.data_ptr(), rows, C_, _stream()),
+                   "rmsnorm")
+    else:
+        assert rows_index.dtype == torch.int32
+        rows = rows_index.numel()
+        out = torch.empty(rows, C_, device=x.device, dtype=torch.bfloat16)
+        _lib.check(_lib.load().b2s_rmsnorm_gather_fwd(x.data_ptr(), rows_index.data_ptr(), w.data_ptr(), eps,
+                                                      out.data_ptr(), rows, C_, _stream()), "rmsnorm_gather")
+    return out
+
+
+def layernorm_avgpool(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, kernel: int,
+                      stride: int) -> torch.Tensor:
+    """x fp32 [B, T, C] -> bf16 [B, (T-kernel)//stride+1, C] = AvgPool1d(LN(x)) over time."""
+    _need_cuda(x, gamma, beta)
+    B, T, C_ = x.shape
+    To = (T - kernel) // stride + 1 if T >= kernel else 0
+    out = torch.empty(B, To, C_, device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().b2s_layernorm_avgpool_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps,
+                                                     out.data_ptr(), B, T, C_, kernel, stride, To, _stream()),
+               "layernorm_avgpool")
+    return out
+
+
+def conv0_ln_gelu(wave: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                  eps: float) -> torch.Tensor:
+    _need_cuda(wave, w, b, gamma, beta)
+    assert wave.dtype == torch.float32 and wave.dim() == 2 and wave.stride(1) == 1
+    B, T = wave.shape
+    To = (T - 10) // 5 + 1
+    out = torch.empty(B, To, 512, device=wave.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().b2s_conv0_ln_gelu_fwd(wave.data_ptr(), wave.stride(0), B, T, w.data_ptr(), b.data_ptr(),
+                                                 gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), To, _stream()),
+               "conv0_ln_gelu")
+    return out
+
+
+def embed_splice(table: torch.Tensor, audio: Optional[torch.Tensor], row_src: torch.Tensor) -> torch.Tensor:
+    _need_cuda(table, audio, row_src)
+    assert table.dtype == torch.bfloat16 and row_src.dtype == torch.int32
+    C_ = table.shape[1]
+    rows = row_src.numel()
+    out = torch.empty(rows, C_, device=table.device, dtype=torch.float32)
+    _lib.check(_lib.load().b2s_embed_splice_fwd(table.data_ptr(), _ptr(audio), row_src.data_ptr(), out.data_ptr(), rows,
+                                                C_, _stream()), "embed_splice")
+    return out
+
+
+def rowpair_sqdiff(h: torch.Tensor, rows_a: torch.Tensor, rows_b: torch.Tensor) -> torch.Tensor:
+    _need_cuda(h, rows_a, rows_b)
+    out = torch.empty(rows_a.numel(), device=h.device, dtype=torch.float32)
+    _lib.check(_lib.load().b2s_rowpair_sqdiff_fwd(h.data_ptr(), rows_a.data_ptr(), rows_b.data_ptr(), out.data_ptr(),
+                                                  rows_a.numel(), h.shape[-1], _stream()), "rowpair_sqdiff")
+    return out
+
+
+def posconv_weight_pack(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """weight-norm(dim=2) then repack [cout, cin_g, k] -> bf16 [cout, k*cin_g] (column = tap*cin_g + c_in)."""
+    _need_cuda(g, v)
+    cout, cin_g, k = v.shape
+    out = torch.empty(cout, k * cin_g, device=v.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().b2s_posconv_weight_pack(g.contiguous().data_ptr(), v.contiguous().data_ptr(),
+                                                   out.data_ptr(), cout, cin_g, k, _stream()), "posconv_weight_pack")
+    return out
+
+
+def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, Hq: int, Hkv: int, D: int, scale: float,
+              causal: bool) -> torch.Tensor:
+    """qkv bf16 [rows, (Hq+2Hkv)*D] (q | k | v) -> o bf16 [rows, Hq*D]."""
+    _need_cuda(qkv, cu_seqlens)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and cu_seqlens.dtype == torch.int32
+    rows, ld = qkv.shape
+    o = torch.empty(rows, Hq * D, device=qkv.device, dtype=torch.bfloat16)
+    base = qkv.data_ptr()
+    _lib.check(_lib.load().b2s_attention_fwd(base, base + 2 * Hq * D, base + 2 * (Hq + Hkv) * D, ld, o.data_ptr(),
+                                             Hq * D, cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, max_seqlen, Hq,
+                                             Hkv, D, scale, int(causal), _stream()), "attention")
+    return o
+
+
+class KdCeResult:
+    __slots__ = ("loss_ld", "loss_ntp", "lse_s", "lse_t", "coef_kd", "coef_ce")
+
+
+def kd_ce_loss(student: torch.Tensor, teacher: torch.Tensor, labels: torch.Tensor, row_offsets: torch.Tensor,
+               scale_kd: float = 1.0, scale_ce: float = 1.0) -> KdCeResult:
+    """Fused CE + KD over packed rows; returns per-utterance means and the statistics the backward needs."""
+    _need_cuda(student, teacher, labels, row_offsets)
+    assert student.dtype == torch.bfloat16 and teacher.dtype == torch.bfloat16
+    assert student.stride(1) == 1 and teacher.stride(1) == 1
+    assert labels.dtype == torch.int32 and row_offsets.dtype == torch.int32
+    rows, V = student.shape
+    U = row_offsets.numel() - 1
+    lib = _lib.load()
+    dev = student.device
+    ws = torch.empty(max(1, lib.b2s_kd_ce_workspace_bytes(rows, V)), device=dev, dtype=torch.uint8)
+    r = KdCeResult()
+    r.lse_s = torch.empty(rows, device=dev, dtype=torch.float32)
+    r.lse_t = torch.empty(rows, device=dev, dtype=torch.float32)
+    r.coef_kd = torch.empty(rows, device=dev, dtype=torch.float32)
+    r.coef_ce = torch.empty(rows, device=dev, dtype=torch.float32)
+    r.loss_ld = torch.empty(U, device=dev, dtype=torch.float32)
+    r.loss_ntp = torch.empty(U, device=dev, dtype=torch.float32)
+    _lib.check(lib.b2s_kd_ce_loss_fwd(student.data_ptr(), teacher.data_ptr(), student.stride(0), teacher.stride(0), rows,
+                                      V, labels.data_ptr(), row_offsets.data_ptr(), U, scale_kd, scale_ce,
+                                      ws.data_ptr(), r.lse_s.data_ptr(), r.lse_t.data_ptr(), r.coef_kd.data_ptr(),
+                                      r.coef_ce.data_ptr(), r.loss_ld.data_ptr(), r.loss_ntp.data_ptr(), _stream()),
+               "kd_ce_loss_fwd")
+    return r
+
+
+def kd_ce_loss_bwd(student: torch.Tensor, teacher: torch.Tensor, labels: torch.Tensor, res: KdCeResult,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(student, teacher, labels)
+    rows, V = student.shape
+    if out is None:
+        out = torch.empty(rows, V, device=student.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().b2s_kd_ce_loss_bwd(student.data_ptr(), teacher.data_ptr(), student.stride(0),
+                                              teacher.stride(0), rows, V, labels.data_ptr(), res.lse_s.data_ptr(),
+                                              res.lse_t.data_ptr(), res.coef_kd.data_ptr(), res.coef_ce.data_ptr(),
+                                              out.data_ptr(), out.stride(0), _stream()), "kd_ce_loss_bwd")
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.load().b2s_launch_count())

@@ -1,0 +1,155 @@
+"""GPU parity of the tcgen05 GEMM (through the C ABI) against a torch fp32 reference of the same op.
+
+Tolerances: operands are bf16-exact in both paths and accumulation is fp32, so fp32-output epilogues must agree
+to ~1e-5 relative L2; bf16-output epilogues to bf16 rounding (2^-9 ~ 2e-3 relative per element -> 3e-3 L2).
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 2e-5
+TOL_BF16 = 3e-3
+
+
+def _mk(M, N, K, dev, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    return a, w, b
+
+
+@pytest.mark.parametrize("bn,cg", [(256, 1), (128, 1), (64, 1), (256, 2), (128, 2)],
+                         ids=["bn256cg1", "bn128cg1", "bn64cg1", "bn256cg2", "bn128cg2"])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (499, 1024, 1024), (1000, 3072, 1024),
+                                   (130, 264, 200), (4096, 512, 1536), (317, 128256 // 4, 512)])
+def test_gemm_plain_f32(cuda, M, N, K, bn, cg):
+    from llm_speech_summarization_b200 import ops
+    a, w, b = _mk(M, N, K, cuda)
+    out = ops.gemm(a, w, bias=b, epi=ops.EPI_F32, block_n=bn, cta_group=cg)
+    ref = a.float() @ w.float().t() + b
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < TOL_F32
+
+
+@pytest.mark.parametrize("cg", [1, 2], ids=["cg1", "cg2"])
+def test_gemm_bf16_gelu(cuda, cg):
+    from llm_speech_summarization_b200 import ops
+    a, w, b = _mk(1497, 4096, 1024, cuda, seed=1)
+    out = ops.gemm(a, w, bias=b, epi=ops.EPI_BF16, act=ops.ACT_GELU, cta_group=cg)
+    ref = F.gelu(a.float() @ w.float().t() + b)
+    assert rel_l2(out.float(), ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("cg", [1, 2], ids=["cg1", "cg2"])
+def test_gemm_resid_inplace(cuda, cg):
+    from llm_speech_summarization_b200 import ops
+    a, w, b = _mk(777, 1024, 4096, cuda, seed=2)
+    h = torch.randn(777, 1024, device=cuda)
+    ref = h + (a.float() @ w.float().t() + b)
+    out = ops.gemm(a, w, bias=b, epi=ops.EPI_RESID_F32, resid=h, out=h, cta_group=cg)
+    assert out.data_ptr() == h.data_ptr()
+    assert rel_l2(out, ref) < TOL_F32
+
+
+@pytest.mark.parametrize("cg", [1, 2], ids=["cg1", "cg2"])
+def test_gemm_swiglu(cuda, cg):
+    from llm_speech_summarization_b200 import ops
+    from llm_speech_summarization_b200.packing import pack_gate_up
+    M, Hd, Fd = 333, 512, 1024
+    g = torch.Generator().manual_seed(3)
+    a = (torch.randn(M, Hd, generator=g) * 0.5).to(torch.bfloat16).to(cuda)
+    wg = (torch.randn(Fd, Hd, generator=g) * 0.05).to(torch.bfloat16).to(cuda)
+    wu = (torch.randn(Fd, Hd, generator=g) * 0.05).to(torch.bfloat16).to(cuda)
+    out = ops.gemm(a, pack_gate_up(wg, wu), epi=ops.EPI_SWIGLU, cta_group=cg)
+    ref = F.silu(a.float() @ wg.float().t()) * (a.float() @ wu.float().t())
+    assert out.shape == (M, Fd)
+    assert rel_l2(out.float(), ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("cg", [1, 2], ids=["cg1", "cg2"])
+def test_gemm_rope(cuda, cg):
+    from llm_speech_summarization_b200 import ops
+    M, Hd, Hq, Hkv, D = 300, 512, 4, 2, 128
+    g = torch.Generator().manual_seed(4)
+    a = (torch.randn(M, Hd, generator=g) * 0.5).to(torch.bfloat16).to(cuda)
+    w = (torch.randn((Hq + 2 * Hkv) * D, Hd, generator=g) * 0.05).to(torch.bfloat16).to(cuda)
+    pos = torch.randint(0, 400, (M,), generator=g).to(torch.int32).to(cuda)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2).float() / D))
+    ang = torch.arange(512).float()[:, None] * inv[None, :]
+    cs = torch.cat([ang.cos(), ang.sin()], dim=1).contiguous().to(cuda)
+    out = ops.gemm(a, w, epi=ops.EPI_ROPE, rope_cs=cs, positions=pos, rope_cols=(Hq + Hkv) * D, cta_group=cg)
+    y = (a.float() @ w.float().t()).view(M, Hq + 2 * Hkv, D)
+    cos = torch.cat([ang.cos(), ang.cos()], 1).to(cuda)[pos.long()][:, None, :]
+    sin = torch.cat([ang.sin(), ang.sin()], 1).to(cuda)[pos.long()][:, None, :]
+    rot = torch.cat([-y[..., D // 2:], y[..., :D // 2]], dim=-1)
+    yr = y * cos + rot * sin
+    ref = torch.cat([yr[:, :Hq + Hkv], y[:, Hq + Hkv:]], dim=1).reshape(M, -1)
+    assert rel_l2(out.float(), ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("k,s,T", [(3, 2, 1001), (2, 2, 640), (3, 2, 15999)])
+def test_gemm_strided_conv_view(cuda, k, s, T):
+    """Conv1d(512->512, k, stride s) as a GEMM over the overlapping window view."""
+    from llm_speech_summarization_b200 import ops
+    from llm_speech_summarization_b200._lib import GemmArgs
+    B, Cc = 3, 512
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(B, T, Cc, generator=g) * 0.5).to(torch.bfloat16).to(cuda)  # channels-last
+    w = (torch.randn(Cc, Cc, k, generator=g) * 0.03).to(torch.bfloat16).to(cuda)
+    b = torch.randn(Cc, generator=g).to(cuda)
+    To = (T - k) // s + 1
+    wp = w.permute(0, 2, 1).reshape(Cc, k * Cc).contiguous()
+    out = torch.empty(B, To, Cc, device=cuda, dtype=torch.float32)
+    a = GemmArgs()
+    a.A, a.a_dim0, a.a_row_stride, a.a_batch_stride, a.a_rows = x.data_ptr(), k * Cc, s * Cc, T * Cc, To
+    a.W, a.w_rows, a.w_cols = wp.data_ptr(), Cc, k * Cc
+    a.M, a.N, a.batches, a.groups, a.taps, a.k_per_tap = To, Cc, B, 1, 1, k * Cc
+    a.epi, a.bias, a.out, a.ldo, a.out_batch_rows = ops.EPI_F32, b.data_ptr(), out.data_ptr(), Cc, To
+    ops.gemm_raw(a)
+    ref = F.conv1d(x.float().transpose(1, 2), w.float(), b, stride=s).transpose(1, 2)
+    assert rel_l2(out, ref) < TOL_F32
+
+
+def test_gemm_grouped_posconv(cuda):
+    """Grouped Conv1d(1024,1024,k=128,pad=64,groups=16), last frame dropped, GELU, residual add."""
+    from llm_speech_summarization_b200 import ops
+    from llm_speech_summarization_b200._lib import GemmArgs
+    B, T, H, K, G = 2, 499, 1024, 128, 16
+    gen = torch.Generator().manual_seed(6)
+    h = torch.randn(B, T, H, generator=gen).to(cuda)
+    v = (torch.randn(H, H // G, K, generator=gen) * 0.02).to(cuda)
+    gg = (torch.rand(1, 1, K, generator=gen) + 0.5).to(cuda)
+    bias = torch.randn(H, generator=gen).to(cuda)
+    wp = ops.posconv_weight_pack(gg, v)
+    wn = gg * v / v.norm(dim=(0, 1), keepdim=True)
+    wp_ref = wn.permute(0, 2, 1).reshape(H, K * (H // G))
+    assert rel_l2(wp.float(), wp_ref) < 3e-3
+    x = h.to(torch.bfloat16)
+    out = h.clone()
+    a = GemmArgs()
+    a.A, a.a_dim0, a.a_row_stride, a.a_batch_stride, a.a_rows = x.data_ptr(), H, H, T * H, T
+    a.W, a.w_rows, a.w_cols = wp.data_ptr(), H, K * 64
+    a.M, a.N, a.batches, a.groups, a.taps, a.k_per_tap = T, 64, B, G, K, 64
+    a.a_pad, a.a_group_off, a.w_group_off = K // 2, 64, 64
+    a.epi, a.act, a.bias = ops.EPI_RESID_F32, ops.ACT_GELU, bias.data_ptr()
+    a.out, a.resid, a.ldo, a.out_batch_rows = out.data_ptr(), out.data_ptr(), H, T
+    ops.gemm_raw(a)
+    wq = wp.float().view(H, K, H // G).permute(0, 2, 1).contiguous()  # bf16-rounded normalised weight
+    y = F.conv1d(x.float().transpose(1, 2), wq, bias, padding=K // 2, groups=G)[:, :, :-1]
+    ref = h + F.gelu(y).transpose(1, 2)
+    assert rel_l2(out, ref) < TOL_F32
+
+
+def test_gemm_rejects_bad_args(cuda):
+    from llm_speech_summarization_b200 import ops
+    a = torch.zeros(8, 60, device=cuda, dtype=torch.bfloat16)  # K stride not a multiple of 8
+    w = torch.zeros(16, 60, device=cuda, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, w)

@@ -1,0 +1,165 @@
+"""GPU parity of the memory-bound kernels and attention (through the C ABI) against torch fp32 references."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _loss_ref(s, t, labels, offs):
+    """REF/utils.py:167-178 (soft_cross_entropy) and REF/model/audio_llama.py:84-98 restated per utterance."""
+    s, t = s.float(), t.float()
+    lds, ntps = [], []
+    for u in range(len(offs) - 1):
+        a, b = offs[u], offs[u + 1]
+        ls = F.log_softmax(s[a:b], -1)
+        pt = F.softmax(t[a:b], -1)
+        lds.append((-(pt * ls).sum(-1)).mean())
+        lab = labels[a:b]
+        m = lab >= 0
+        ntps.append(F.cross_entropy(s[a:b][m], lab[m].long()) if m.any() else s.new_zeros(()))
+    return torch.stack(lds), torch.stack(ntps)
+
+
+@pytest.mark.parametrize("V,R,U", [(128256, 64, 2), (49216, 33, 3), (512, 5, 1), (16384 + 8, 7, 2)])
+def test_kd_ce_loss_fwd_bwd(cuda, V, R, U):
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(V + R)
+    rows = R * U
+    s = (torch.randn(rows, V, generator=g) * 2.0).to(torch.bfloat16).to(cuda)
+    t = (torch.randn(rows, V, generator=g) * 2.0).to(torch.bfloat16).to(cuda)
+    labels = torch.randint(0, V, (rows,), generator=g).to(torch.int32)
+    offs = [u * R for u in range(U + 1)]
+    for u in range(U):
+        labels[offs[u + 1] - 1] = -1  # the last row of each utterance has no next-token target
+    labels = labels.to(cuda)
+    offs_t = torch.tensor(offs, dtype=torch.int32, device=cuda)
+    w_kd, w_ce = 0.5, 0.25
+    res = ops.kd_ce_loss(s, t, labels, offs_t, scale_kd=w_kd, scale_ce=w_ce)
+    s32 = s.float().requires_grad_(True)
+    ld_ref, ntp_ref = _loss_ref(s32, t, labels, offs)
+    # KD loss within 1e-3 relative is the north-star tolerance; same-input fp32 math should be far tighter
+    assert torch.allclose(res.loss_ld, ld_ref, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(res.loss_ntp, ntp_ref, rtol=1e-5, atol=1e-5)
+    (w_kd * ld_ref.sum() + w_ce * ntp_ref.sum()).backward()
+    ds = ops.kd_ce_loss_bwd(s, t, labels, res)
+    assert rel_l2(ds.float(), s32.grad) < 4e-3  # bf16 rounding of the stored gradient
+
+
+def test_kd_ce_loss_empty_rows(cuda):
+    from llm_speech_summarization_b200 import ops
+    s = torch.zeros(0, 512, device=cuda, dtype=torch.bfloat16)
+    labels = torch.zeros(0, dtype=torch.int32, device=cuda)
+    offs = torch.zeros(2, dtype=torch.int32, device=cuda)
+    res = ops.kd_ce_loss(s, s, labels, offs)
+    assert float(res.loss_ld[0]) == 0.0 and float(res.loss_ntp[0]) == 0.0
+
+
+@pytest.mark.parametrize("C_,dtype,gelu", [(512, torch.bfloat16, True), (512, torch.float32, True),
+                                           (1024, torch.float32, False), (3072, torch.float32, False)])
+def test_layernorm(cuda, C_, dtype, gelu):
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(C_)
+    x = (torch.randn(1237, C_, generator=g) * 3 + 0.7).to(dtype).to(cuda)
+    gm = torch.randn(C_, generator=g).to(cuda)
+    bt = torch.randn(C_, generator=g).to(cuda)
+    y = ops.layernorm(x, gm, bt, 1e-5, gelu=gelu)
+    ref = F.layer_norm(x.float(), (C_,), gm, bt, 1e-5)
+    if gelu:
+        ref = F.gelu(ref)
+    assert rel_l2(y.float(), ref) < 3e-3
+
+
+def test_rmsnorm_and_gather(cuda):
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(517, 3072, generator=g) * 2).to(cuda)
+    w = (torch.rand(3072, generator=g) + 0.5).to(cuda)
+    ref = w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5))
+    assert rel_l2(ops.rmsnorm(x, w, 1e-5).float(), ref) < 3e-3
+    idx = torch.tensor([5, 516, 0, 77], dtype=torch.int32, device=cuda)
+    assert rel_l2(ops.rmsnorm(x, w, 1e-5, rows_index=idx).float(), ref[idx.long()]) < 3e-3
+
+
+def test_layernorm_avgpool(cuda):
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(3, 499, 1024, generator=g).to(cuda)
+    gm = torch.randn(1024, generator=g).to(cuda)
+    bt = torch.randn(1024, generator=g).to(cuda)
+    y = ops.layernorm_avgpool(x, gm, bt, 1e-5, 8, 4)
+    ref = F.avg_pool1d(F.layer_norm(x, (1024,), gm, bt, 1e-5).transpose(1, 2), 8, 4).transpose(1, 2)
+    assert y.shape == (3, 123, 1024)
+    assert rel_l2(y.float(), ref) < 3e-3
+
+
+@pytest.mark.parametrize("T", [400, 16000, 12345])
+def test_conv0_ln_gelu(cuda, T):
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(T)
+    wave = (torch.randn(2, T, generator=g) * 0.1).to(cuda)
+    w = (torch.randn(512, 1, 10, generator=g) * 0.3).to(cuda)
+    b = torch.randn(512, generator=g).to(cuda)
+    gm = torch.randn(512, generator=g).to(cuda)
+    bt = torch.randn(512, generator=g).to(cuda)
+    y = ops.conv0_ln_gelu(wave, w.reshape(512, 10).contiguous(), b, gm, bt, 1e-5)
+    c = F.conv1d(wave[:, None, :], w, b, stride=5).transpose(1, 2)
+    ref = F.gelu(F.layer_norm(c, (512,), gm, bt, 1e-5))
+    assert y.shape == ref.shape
+    assert rel_l2(y.float(), ref) < 3e-3
+
+
+def test_embed_splice_and_sqdiff(cuda):
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    table = torch.randn(1000, 3072, generator=g).to(torch.bfloat16).to(cuda)
+    audio = torch.randn(50, 3072, generator=g).to(cuda)
+    src = torch.tensor([3, 999, -1, -50, 0, -7], dtype=torch.int32, device=cuda)
+    h = ops.embed_splice(table, audio, src)
+    ref = torch.stack([table[3].float(), table[999].float(), audio[0], audio[49], table[0].float(), audio[6]])
+    assert torch.equal(h, ref)
+    ra = torch.tensor([0, 2], dtype=torch.int32, device=cuda)
+    rb = torch.tensor([1, 3], dtype=torch.int32, device=cuda)
+    sq = ops.rowpair_sqdiff(h, ra, rb)
+    ref_sq = torch.stack([(ref[0] - ref[1]).pow(2).sum(), (ref[2] - ref[3]).pow(2).sum()])
+    assert torch.allclose(sq, ref_sq, rtol=1e-5)
+
+
+def _attn_ref(qkv, cu, Hq, Hkv, D, scale, causal):
+    rows = qkv.shape[0]
+    q, k, v = qkv.float().split([Hq * D, Hkv * D, Hkv * D], dim=1)
+    out = torch.zeros(rows, Hq * D, device=qkv.device)
+    for s in range(len(cu) - 1):
+        a, b = cu[s], cu[s + 1]
+        qs = q[a:b].view(b - a, Hq, D).transpose(0, 1)
+        ks = k[a:b].view(b - a, Hkv, D).transpose(0, 1).repeat_interleave(Hq // Hkv, 0)
+        vs = v[a:b].view(b - a, Hkv, D).transpose(0, 1).repeat_interleave(Hq // Hkv, 0)
+        o = F.scaled_dot_product_attention(qs, ks, vs, is_causal=causal, scale=scale)
+        out[a:b] = o.transpose(0, 1).reshape(b - a, Hq * D)
+    return out
+
+
+@pytest.mark.parametrize("Hq,Hkv,D,causal,lens", [
+    (16, 16, 64, False, [499, 499]),
+    (16, 16, 64, False, [1, 63, 64, 65, 130]),
+    (24, 8, 128, True, [200, 117, 1, 64, 129]),
+    (24, 24, 128, True, [136, 400]),
+    (4, 2, 128, False, [77]),
+])
+def test_attention(cuda, Hq, Hkv, D, causal, lens):
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(sum(lens) + D)
+    rows = sum(lens)
+    qkv = torch.randn(rows, (Hq + 2 * Hkv) * D, generator=g).to(torch.bfloat16).to(cuda)
+    cu = [0]
+    for L in lens:
+        cu.append(cu[-1] + L)
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=cuda)
+    scale = 1.0 / math.sqrt(D)
+    o = ops.attention(qkv, cu_t, max(lens), Hq, Hkv, D, scale, causal)
+    ref = _attn_ref(qkv, cu, Hq, Hkv, D, scale, causal)
+    assert rel_l2(o.float(), ref) < 6e-3  # P is rounded to bf16 before P.V, output rounded to bf16
