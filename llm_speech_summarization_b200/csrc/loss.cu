@@ -255,16 +255,15 @@ int kd_ce_loss_fwd(const void* S, const void* T, long long lds, long long ldt, i
                    const int* row_offsets, int utterances, float scale_kd, float scale_ce, void* workspace,
                    float* lse_s, float* lse_t, float* coef_kd, float* coef_ce, float* loss_ld, float* loss_ntp,
                    cudaStream_t stream) {
-  B2S_REQUIRE(S && T && labels && row_offsets && workspace && lse_s && lse_t && coef_kd && coef_ce && loss_ld &&
-                  loss_ntp,
-              "kd_ce_loss_fwd: null pointer");
-  B2S_REQUIRE(V > 0 && V % 8 == 0 && lds % 8 == 0 && ldt % 8 == 0, "kd_ce_loss_fwd: V/ld must be multiples of 8");
-  B2S_REQUIRE(utterances > 0 && rows >= 0, "kd_ce_loss_fwd: bad sizes");
-  if (rows == 0) {
+  B2S_REQUIRE(utterances > 0 && rows >= 0 && loss_ld && loss_ntp, "kd_ce_loss_fwd: bad sizes");
+  if (rows == 0) {  // no response rows at all: every utterance's mean over an empty set is reported as 0
     B2S_CUDA_CHECK(cudaMemsetAsync(loss_ld, 0, sizeof(float) * utterances, stream));
     B2S_CUDA_CHECK(cudaMemsetAsync(loss_ntp, 0, sizeof(float) * utterances, stream));
     return B2S_OK;
   }
+  B2S_REQUIRE(S && T && labels && row_offsets && workspace && lse_s && lse_t && coef_kd && coef_ce,
+              "kd_ce_loss_fwd: null pointer");
+  B2S_REQUIRE(V > 0 && V % 8 == 0 && lds % 8 == 0 && ldt % 8 == 0, "kd_ce_loss_fwd: V/ld must be multiples of 8");
   const int chunks = (V + kChunkCols - 1) / kChunkCols;
   dim3 grid(chunks, rows);
   kd_ce_partial_kernel<<<grid, kLossThreads, 0, stream>>>(
