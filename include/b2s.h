@@ -106,7 +106,8 @@ int b2s_conv0_ln_gelu_fwd(const float* wave, int64_t wave_stride, int32_t batche
                           const float* bias, const float* gamma, const float* beta, float eps, void* y_bf16,
                           int32_t out_frames, void* stream);
 /* embedding gather + audio splice (REF/utils.py:27-46,49-73,85-164; REF/inference.py:113-134):
- * h0[row] = row_src[row] >= 0 ? embed_tokens[row_src[row]] : audio_embeds[-(row_src[row]+1)] */
+ * h0[row] = row_src[row] >= 0 ? embed_tokens[row_src[row]] : audio_embeds[-(row_src[row]+1)];
+ * row_src[row] == INT32_MIN writes a zero row (the reference's left padding). */
 int b2s_embed_splice_fwd(const void* embed_table_bf16, const float* audio_embeds, const int32_t* row_src, float* h0,
                          int64_t rows, int32_t C, void* stream);
 /* per-row-pair sum of squared differences, the core of the FD MSE (REF/trainer.py:358-370) */
@@ -205,12 +206,14 @@ size_t b2s_llama_workspace_bytes(const b2s_llama_weights* w, int32_t rows, int32
  *   cu_seqlens int32 [num_seqs+1]; positions int32 [rows];
  *   logit_rows_index int32 [logit_rows]: rows whose logits are produced -> logits bf16 [logit_rows, vocab];
  *   fd taps (optional): for each t < num_taps, before layer tap_layers[t] runs, out
- *   fd_sq[t*pairs + i] = sum_c (h[tap_rows_a[i], c] - h[tap_rows_b[i], c])^2   (REF/trainer.py:358-370). */
+ *   fd_sq[t*pairs + i] = sum_c (h[tap_rows_a[i], c] - h[tap_rows_b[i], c])^2   (REF/trainer.py:358-370);
+ *   all_hidden (optional, may be NULL): fp32 [num_layers+1, rows, hidden], output_hidden_states=True layout
+ *   ([l] = input of layer l, [num_layers] = output of the final norm). */
 int b2s_llama_prefill(const b2s_llama_weights* w, float* h, int32_t rows, const int32_t* cu_seqlens,
                       int32_t num_seqs, int32_t max_seqlen, const int32_t* positions,
                       const int32_t* logit_rows_index, int32_t logit_rows, void* logits_bf16,
                       const int32_t* tap_layers /*host*/, int32_t num_taps, const int32_t* tap_rows_a,
-                      const int32_t* tap_rows_b, int32_t pairs, float* fd_sq, void* workspace,
+                      const int32_t* tap_rows_b, int32_t pairs, float* fd_sq, float* all_hidden, void* workspace,
                       size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

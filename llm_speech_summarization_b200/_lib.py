@@ -90,8 +90,8 @@ PROTOTYPES = {
                                    P_f32, c_void_p]),
     "b2s_llama_workspace_bytes": (c_size_t, [C.POINTER(LlamaWeights), c_int, c_int]),
     "b2s_llama_prefill": (c_int, [C.POINTER(LlamaWeights), P_f32, c_int, P_int, c_int, c_int, P_int, P_int, c_int,
-                                  c_void_p, C.POINTER(c_int), c_int, P_int, P_int, c_int, P_f32, c_void_p, c_size_t,
-                                  c_void_p]),
+                                  c_void_p, C.POINTER(c_int), c_int, P_int, P_int, c_int, P_f32, P_f32, c_void_p,
+                                  c_size_t, c_void_p]),
 }
 
 _lib = None

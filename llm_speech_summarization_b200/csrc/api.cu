@@ -52,7 +52,7 @@ size_t llama_workspace_bytes(const b2s_llama_weights* w, int rows, int logit_row
 int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_seqlens, int num_seqs, int max_seqlen,
                   const int* positions, const int* logit_rows_index, int logit_rows, void* logits_bf16,
                   const int* tap_layers, int num_taps, const int* tap_rows_a, const int* tap_rows_b, int pairs,
-                  float* fd_sq, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                  float* fd_sq, float* all_hidden, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 }  // namespace b2s
 
@@ -187,10 +187,10 @@ int b2s_llama_prefill(const b2s_llama_weights* w, float* h, int32_t rows, const 
                       int32_t num_seqs, int32_t max_seqlen, const int32_t* positions,
                       const int32_t* logit_rows_index, int32_t logit_rows, void* logits_bf16,
                       const int32_t* tap_layers, int32_t num_taps, const int32_t* tap_rows_a,
-                      const int32_t* tap_rows_b, int32_t pairs, float* fd_sq, void* workspace,
+                      const int32_t* tap_rows_b, int32_t pairs, float* fd_sq, float* all_hidden, void* workspace,
                       size_t workspace_bytes, void* stream) {
   return llama_prefill(w, h, rows, cu_seqlens, num_seqs, max_seqlen, positions, logit_rows_index, logit_rows,
-                       logits_bf16, tap_layers, num_taps, tap_rows_a, tap_rows_b, pairs, fd_sq, workspace,
+                       logits_bf16, tap_layers, num_taps, tap_rows_a, tap_rows_b, pairs, fd_sq, all_hidden, workspace,
                        workspace_bytes, S(stream));
 }
 

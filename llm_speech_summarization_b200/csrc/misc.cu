@@ -6,6 +6,8 @@
 //   * rowpair_sqdiff: per-row sum of squared differences for the feature-distillation MSE (REF/trainer.py:358-370).
 //   * posconv_weight_pack: weight-norm (dim=2) of the positional conv + repack to the K-major layout the
 //     tap-walk GEMM consumes (TF/models/hubert/modeling_hubert.py:45-92).
+#include <climits>
+
 #include "b2s_common.cuh"
 #include "ops.cuh"
 
@@ -99,7 +101,9 @@ embed_splice_kernel(const __nv_bfloat16* __restrict__ table, const float* __rest
   if (row >= rows) return;
   const int src = row_src[row];
   float* dst = h0 + row * C;
-  if (src >= 0) {
+  if (src == INT_MIN) {  // left-padding row of the reference's batched layout (REF/utils.py:136-146)
+    for (int i = lane; i < C / 4; i += 32) reinterpret_cast<float4*>(dst)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (src >= 0) {
     const uint4* s = reinterpret_cast<const uint4*>(table + static_cast<long long>(src) * C);
     for (int i = lane; i < C / 8; i += 32) {
       const uint4 u = __ldg(s + i);

@@ -329,7 +329,7 @@ size_t llama_workspace_bytes(const b2s_llama_weights* w, int rows, int logit_row
 int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_seqlens, int num_seqs, int max_seqlen,
                   const int* positions, const int* logit_rows_index, int logit_rows, void* logits_bf16,
                   const int* tap_layers, int num_taps, const int* tap_rows_a, const int* tap_rows_b, int pairs,
-                  float* fd_sq, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                  float* fd_sq, float* all_hidden, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   B2S_REQUIRE(w && h && cu_seqlens && positions && workspace, "llama_prefill: null pointer");
   B2S_REQUIRE(rows > 0 && num_seqs > 0 && max_seqlen > 0, "llama_prefill: empty batch");
   B2S_REQUIRE(w->head_dim == 128, "llama_prefill: head_dim must be 128 (got %d)", w->head_dim);
@@ -343,7 +343,12 @@ int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_
   const int qkv_cols = (Hq + 2 * Hkv) * D;
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
 
+  const size_t h_bytes = static_cast<size_t>(rows) * H * sizeof(float);
   for (int l = 0; l < w->num_layers; ++l) {
+    if (all_hidden != nullptr) {  // output_hidden_states: hidden_states[l] = input of layer l
+      B2S_CUDA_CHECK(cudaMemcpyAsync(all_hidden + static_cast<size_t>(l) * rows * H, h, h_bytes,
+                                     cudaMemcpyDeviceToDevice, stream));
+    }
     for (int t = 0; t < num_taps; ++t) {
       if (tap_layers[t] == l && pairs > 0) {
         rc = rowpair_sqdiff_fwd(h, tap_rows_a, tap_rows_b, fd_sq + static_cast<long long>(t) * pairs, pairs, H, stream);
@@ -401,6 +406,13 @@ int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_
       set_last_error("llama_prefill: tap at the post-norm output (index num_layers) is not supported");
       return B2S_ERR_UNSUPPORTED;
     }
+  }
+  if (all_hidden != nullptr) {  // hidden_states[-1] = output of the final norm (rounded through bf16)
+    rc = rmsnorm_fwd(h, w->final_norm_w, w->rms_eps, pl.xn, rows, H, stream);
+    if (rc != B2S_OK) return rc;
+    rc = cast_bf16_to_f32(pl.xn, all_hidden + static_cast<size_t>(w->num_layers) * rows * H,
+                          static_cast<long long>(rows) * H, stream);
+    if (rc != B2S_OK) return rc;
   }
   if (logit_rows > 0) {
     rc = rmsnorm_gather_fwd(h, logit_rows_index, w->final_norm_w, w->rms_eps, pl.xf, logit_rows, H, stream);

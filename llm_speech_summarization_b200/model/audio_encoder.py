@@ -1,0 +1,283 @@
+"""Drop-in for REF/model/audio_encoder.py: same constructor, same forward signature, same state_dict keys
+(SURVEY.md appendix B, 424 tensors for HuBERT-large + pool) -- but forward() is one call into the sm_100a
+library (b2s_hubert_forward): conv feature extractor, positional conv, transformer stack, final LayerNorm fused
+with AvgPool1d, projector.
+
+The module tree below exists only to own parameters under the reference's names so checkpoints written by the
+reference trainer (REF/trainer.py:516-528) and read by its inference script (REF/inference.py:24-26) load
+unchanged; both weight-norm spellings of the positional conv are accepted.
+There is no CPU path: forward() on a non-CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops, packing
+from ..config import EncoderArch, encoder_arch_from_config
+
+
+class _Params(nn.Module):
+    """A bag of named parameters (so state_dict keys read `<name>.weight` / `<name>.bias`)."""
+
+    def __init__(self, **shapes):
+        super().__init__()
+        for name, shape in shapes.items():
+            self.register_parameter(name, nn.Parameter(torch.zeros(*shape)))
+
+
+class _ConvLayer(nn.Module):
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.conv = _Params(weight=(cout, cin, k), bias=(cout,))
+        self.layer_norm = _Params(weight=(cout,), bias=(cout,))
+
+
+class _FeatureExtractor(nn.Module):
+    def __init__(self, arch: EncoderArch):
+        super().__init__()
+        cin = 1
+        layers = []
+        for co, k in zip(arch.conv_dim, arch.conv_kernel):
+            layers.append(_ConvLayer(cin, co, k))
+            cin = co
+        self.conv_layers = nn.ModuleList(layers)
+
+
+class _FeatureProjection(nn.Module):
+    def __init__(self, arch: EncoderArch):
+        super().__init__()
+        self.layer_norm = _Params(weight=(arch.conv_dim[-1],), bias=(arch.conv_dim[-1],))
+        self.projection = _Params(weight=(arch.hidden, arch.conv_dim[-1]), bias=(arch.hidden,))
+
+
+class _WeightNormParams(nn.Module):
+    def __init__(self, arch: EncoderArch):
+        super().__init__()
+        self.weight = _Params(original0=(1, 1, arch.pos_k), original1=(arch.hidden, arch.hidden // arch.pos_groups,
+                                                                     arch.pos_k))
+
+
+class _PosConvInner(nn.Module):
+    def __init__(self, arch: EncoderArch):
+        super().__init__()
+        self.register_parameter("bias", nn.Parameter(torch.zeros(arch.hidden)))
+        self.parametrizations = _WeightNormParams(arch)
+
+
+class _PosConv(nn.Module):
+    def __init__(self, arch: EncoderArch):
+        super().__init__()
+        self.conv = _PosConvInner(arch)
+
+
+class _Attention(nn.Module):
+    def __init__(self, H):
+        super().__init__()
+        for n in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            setattr(self, n, _Params(weight=(H, H), bias=(H,)))
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, H, Fd):
+        super().__init__()
+        self.intermediate_dense = _Params(weight=(Fd, H), bias=(Fd,))
+        self.output_dense = _Params(weight=(H, Fd), bias=(H,))
+
+
+class _EncoderLayer(nn.Module):
+    def __init__(self, H, Fd):
+        super().__init__()
+        self.attention = _Attention(H)
+        self.layer_norm = _Params(weight=(H,), bias=(H,))
+        self.feed_forward = _FeedForward(H, Fd)
+        self.final_layer_norm = _Params(weight=(H,), bias=(H,))
+
+
+class _Encoder(nn.Module):
+    def __init__(self, arch: EncoderArch):
+        super().__init__()
+        self.pos_conv_embed = _PosConv(arch)
+        self.layer_norm = _Params(weight=(arch.hidden,), bias=(arch.hidden,))
+        self.layers = nn.ModuleList([_EncoderLayer(arch.hidden, arch.ffn) for _ in range(arch.layers)])
+
+
+class _EncoderConfigView:
+    """`self.encoder.config.hidden_size` is read by the reference's constructor (REF/model/audio_encoder.py:40)."""
+
+    def __init__(self, arch: EncoderArch):
+        self.hidden_size = arch.hidden
+        self.num_hidden_layers = arch.layers
+        self.num_attention_heads = arch.heads
+        self.intermediate_size = arch.ffn
+
+
+class HubertBackbone(nn.Module):
+    """Parameter container with HF HubertModel's names (TF/models/hubert/modeling_hubert.py)."""
+
+    def __init__(self, arch: EncoderArch):
+        super().__init__()
+        self.arch = arch
+        self.config = _EncoderConfigView(arch)
+        self.register_parameter("masked_spec_embed", nn.Parameter(torch.zeros(arch.hidden)))
+        self.feature_extractor = _FeatureExtractor(arch)
+        self.feature_projection = _FeatureProjection(arch)
+        self.encoder = _Encoder(arch)
+
+
+def load_hubert_encoder(config):
+    """REF/model/audio_encoder.py:6-7 downloads facebook/hubert-large-ls960-ft; here the architecture comes from
+    the config (defaults = HuBERT-large) and the weights from the checkpoint the caller loads."""
+    return HubertBackbone(encoder_arch_from_config(config))
+
+
+class AudioEncoder(nn.Module):
+    def __init__(self, config, device):
+        super(AudioEncoder, self).__init__()
+        self.config = config
+        self.device = device
+
+        if self.config.model.audio_encoder.base == "hubert":
+            self.encoder_base = "hubert"
+            self.encoder = load_hubert_encoder(self.config)
+        elif self.config.model.audio_encoder.base == "whisper":
+            # SURVEY.md section 8 row a7 (config C4) -- scheduled after the HuBERT path meets its bar.
+            raise NotImplementedError("whisper audio encoder is not built yet in the B200 path (SURVEY.md 8/a7)")
+        else:
+            raise Exception("Unexpected encoder type in config.")
+
+        self.downsample_method = self.config.model.audio_encoder.downsample_method
+        self.downsample_factor = self.config.model.audio_encoder.downsample_factor
+        H = self.encoder.config.hidden_size
+        if self.downsample_method == "pool":
+            self.pool_kernel = int(self.config.model.audio_encoder.pooling.kernel_size)
+            self.pool_stride = int(self.config.model.audio_encoder.pooling.stride)
+            self.embed_projection = nn.Linear(H, self.config.model.llm_embedding_channels)
+        elif self.downsample_method in ("stack", "ctc_pool"):
+            # unused by every shipped yaml; kept out of the hot path on purpose
+            raise NotImplementedError(f"downsample_method={self.downsample_method!r} is outside the B200 hot path")
+        else:
+            raise Exception("Invalid downsampling method for audio encoder.")
+
+        self._packed = None
+        self._packed_key = None
+        self._register_load_state_dict_pre_hook(self._rename_legacy_weight_norm)
+
+    # -- checkpoints written by torch 2.0 spell the weight-norm parameters weight_g / weight_v
+    @staticmethod
+    def _rename_legacy_weight_norm(state_dict, prefix, *args):
+        base = prefix + "encoder.encoder.pos_conv_embed.conv."
+        for old, new in (("weight_g", "parametrizations.weight.original0"),
+                         ("weight_v", "parametrizations.weight.original1")):
+            if base + old in state_dict:
+                state_dict[base + new] = state_dict.pop(base + old)
+
+    # ---------------------------------------------------------------------------------------------
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def pack_weights(self, force: bool = False):
+        """bf16 / K-major copies of the parameters in the layouts the kernels consume, rebuilt whenever a
+        parameter changes (optimizer step, load_state_dict)."""
+        key = self._weights_key()
+        if not force and self._packed is not None and self._packed_key == key:
+            return self._packed
+        enc = self.encoder
+        arch: EncoderArch = enc.arch
+        dev = enc.masked_spec_embed.device
+        if dev.type != "cuda":
+            raise RuntimeError("AudioEncoder (B200 path) needs its parameters on a CUDA device; there is no CPU path")
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        keep: List[torch.Tensor] = []
+
+        def K(t):
+            keep.append(t)
+            return t.data_ptr()
+
+        w = _lib.HubertWeights()
+        c0 = enc.feature_extractor.conv_layers[0]
+        w.conv0_w = K(f32(c0.conv.weight).reshape(arch.conv_dim[0], arch.conv_kernel[0]).contiguous())
+        w.conv0_b, w.conv0_ln_g, w.conv0_ln_b = K(f32(c0.conv.bias)), K(f32(c0.layer_norm.weight)), K(
+            f32(c0.layer_norm.bias))
+        for i in range(6):
+            cl = enc.feature_extractor.conv_layers[i + 1]
+            w.conv_w[i] = K(bf(packing.pack_conv(cl.conv.weight.detach())))
+            w.conv_b[i], w.conv_ln_g[i], w.conv_ln_b[i] = K(f32(cl.conv.bias)), K(f32(cl.layer_norm.weight)), K(
+                f32(cl.layer_norm.bias))
+            w.conv_k[i], w.conv_stride[i] = arch.conv_kernel[i + 1], arch.conv_stride[i + 1]
+        fp = enc.feature_projection
+        w.fp_ln_g, w.fp_ln_b = K(f32(fp.layer_norm.weight)), K(f32(fp.layer_norm.bias))
+        w.fp_w, w.fp_b = K(bf(fp.projection.weight)), K(f32(fp.projection.bias))
+        pc = enc.encoder.pos_conv_embed.conv
+        w.pos_w = K(ops.posconv_weight_pack(f32(pc.parametrizations.weight.original0).reshape(-1),
+                                            f32(pc.parametrizations.weight.original1)))
+        w.pos_b, w.pos_k, w.pos_groups = K(f32(pc.bias)), arch.pos_k, arch.pos_groups
+        layers = (_lib.EncoderLayer * arch.layers)()
+        for l, lay in enumerate(enc.encoder.layers):
+            a = lay.attention
+            L = layers[l]
+            L.ln1_g, L.ln1_b = K(f32(lay.layer_norm.weight)), K(f32(lay.layer_norm.bias))
+            L.wqkv = K(bf(packing.pack_qkv(a.q_proj.weight.detach(), a.k_proj.weight.detach(),
+                                           a.v_proj.weight.detach())))
+            L.bqkv = K(f32(torch.cat([a.q_proj.bias.detach(), a.k_proj.bias.detach(), a.v_proj.bias.detach()])))
+            L.wo, L.bo = K(bf(a.out_proj.weight)), K(f32(a.out_proj.bias))
+            L.ln2_g, L.ln2_b = K(f32(lay.final_layer_norm.weight)), K(f32(lay.final_layer_norm.bias))
+            L.w1, L.b1 = K(bf(lay.feed_forward.intermediate_dense.weight)), K(
+                f32(lay.feed_forward.intermediate_dense.bias))
+            L.w2, L.b2 = K(bf(lay.feed_forward.output_dense.weight)), K(f32(lay.feed_forward.output_dense.bias))
+        w.layers = C.cast(layers, C.POINTER(_lib.EncoderLayer))
+        w.num_layers, w.hidden, w.heads, w.ffn = arch.layers, arch.hidden, arch.heads, arch.ffn
+        w.final_ln_g, w.final_ln_b = K(f32(enc.encoder.layer_norm.weight)), K(f32(enc.encoder.layer_norm.bias))
+        w.ln_eps = arch.ln_eps
+        w.pool_kernel, w.pool_stride = self.pool_kernel, self.pool_stride
+        w.proj_w, w.proj_b = K(bf(self.embed_projection.weight)), K(f32(self.embed_projection.bias))
+        w.llm_dim = self.embed_projection.out_features
+        self._packed = (w, layers, keep)
+        self._packed_key = key
+        return self._packed
+
+    def num_frames(self, samples: int):
+        w = self.pack_weights()[0]
+        frames, pooled = C.c_int32(), C.c_int32()
+        _lib.check(_lib.load().b2s_hubert_num_frames(C.byref(w), samples, C.byref(frames), C.byref(pooled)),
+                   "hubert_num_frames")
+        return frames.value, pooled.value
+
+    def forward_fp32(self, input: torch.Tensor, return_last_hidden: bool = False):
+        """(B, T0) waveform -> fp32 (B, A, llm_dim) projected audio embeddings (and optionally the fp32
+        pre-final-norm residual stream (B, N, H) for parity tests)."""
+        if not input.is_cuda:
+            raise RuntimeError("AudioEncoder.forward (B200 path) needs a CUDA input; there is no CPU path")
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "training-mode forward/backward of the audio encoder is not built yet (SURVEY.md 8/a13, K13); "
+                "call .eval() / torch.no_grad() for the forward path")
+        w = self.pack_weights()[0]
+        wave = input.to(torch.float32)
+        if wave.dim() != 2:
+            raise ValueError("expected a (B, T0) waveform batch")
+        if wave.stride(1) != 1:
+            wave = wave.contiguous()
+        B, T0 = wave.shape
+        frames, pooled = self.num_frames(T0)
+        lib = _lib.load()
+        nbytes = lib.b2s_hubert_workspace_bytes(C.byref(w), B, T0)
+        ws = torch.empty(nbytes, device=wave.device, dtype=torch.uint8)
+        out = torch.empty(B, pooled, w.llm_dim, device=wave.device, dtype=torch.float32)
+        last = torch.empty(B, frames, w.hidden, device=wave.device, dtype=torch.float32) if return_last_hidden else None
+        _lib.check(lib.b2s_hubert_forward(C.byref(w), wave.data_ptr(), wave.stride(0), B, T0, ws.data_ptr(), nbytes,
+                                          out.data_ptr(), None if last is None else last.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream), "hubert_forward")
+        return (out, last) if return_last_hidden else out
+
+    def forward(self, input, ctc_pool_ranges=None):
+        """Same contract as REF/model/audio_encoder.py:56-88 (`pool` branch): (B, T0) -> (B, A, llm_dim).
+        The result is returned in bf16, the activation dtype of the LLM it is spliced into (the reference returns
+        fp16 under autocast)."""
+        if self.downsample_method != "pool":
+            raise Exception("Invalid downsampling method for audio encoder.")
+        return self.forward_fp32(input).to(torch.bfloat16)

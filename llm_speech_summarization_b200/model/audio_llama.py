@@ -1,0 +1,322 @@
+"""Drop-in for REF/model/audio_llama.py: `AudioLlamaForCausalLM` with the reference's forward signature, output
+object (.loss / .logits / .hidden_states), `.model.embed_tokens` and a greedy `.generate(inputs_embeds=...)`,
+backed by the sm_100a prefill (b2s_llama_prefill) instead of transformers' LlamaModel.
+
+Parameters are held frozen in bf16 under HF's names (`model.embed_tokens.weight`, `model.layers.N.*`,
+`model.norm.weight`, `lm_head.weight`), so an HF Llama-3.2-3B / MiniChat-2-3B state_dict loads unchanged; the
+fused-QKV and gate|up-interleaved copies the kernels consume are built once (the LLM is frozen on this path,
+REF/trainer.py:62-64). No CPU path exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops, packing
+from ..config import LlmArch
+
+
+@dataclass
+class CausalLMOutputWithPast:
+    """Field-compatible with transformers.modeling_outputs.CausalLMOutputWithPast (REF/model/audio_llama.py:107-113)."""
+    loss: Optional[torch.Tensor] = None
+    logits: Optional[torch.Tensor] = None
+    past_key_values: Optional[object] = None
+    hidden_states: Optional[Tuple[torch.Tensor, ...]] = None
+    attentions: Optional[Tuple[torch.Tensor, ...]] = None
+
+    def __getitem__(self, i):
+        return tuple(v for v in (self.loss, self.logits, self.past_key_values, self.hidden_states, self.attentions)
+                     if v is not None)[i]
+
+
+class _W(nn.Module):
+    def __init__(self, *shape):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(*shape, dtype=torch.bfloat16), requires_grad=False)
+
+
+class EmbedTokens(nn.Module):
+    """`llm.model.embed_tokens(ids)` (REF/utils.py:33-35,61-62,117; REF/inference.py:121): gathers through the
+    splice kernel, returns bf16 (the LLM's activation dtype)."""
+
+    def __init__(self, vocab, hidden):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(vocab, hidden, dtype=torch.bfloat16), requires_grad=False)
+
+    def forward(self, input_ids: torch.Tensor) -> torch.Tensor:
+        ids = input_ids.to(device=self.weight.device, dtype=torch.int32).contiguous()
+        out = ops.embed_splice(self.weight, None, ids.reshape(-1))
+        return out.to(torch.bfloat16).reshape(*input_ids.shape, self.weight.shape[1])
+
+
+class _Attn(nn.Module):
+    def __init__(self, a: LlmArch):
+        super().__init__()
+        self.q_proj = _W(a.heads * a.head_dim, a.hidden)
+        self.k_proj = _W(a.kv_heads * a.head_dim, a.hidden)
+        self.v_proj = _W(a.kv_heads * a.head_dim, a.hidden)
+        self.o_proj = _W(a.hidden, a.heads * a.head_dim)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, a: LlmArch):
+        super().__init__()
+        self.gate_proj = _W(a.ffn, a.hidden)
+        self.up_proj = _W(a.ffn, a.hidden)
+        self.down_proj = _W(a.hidden, a.ffn)
+
+
+class _Layer(nn.Module):
+    def __init__(self, a: LlmArch):
+        super().__init__()
+        self.self_attn = _Attn(a)
+        self.mlp = _Mlp(a)
+        self.input_layernorm = _W(a.hidden)
+        self.post_attention_layernorm = _W(a.hidden)
+
+
+class _Model(nn.Module):
+    def __init__(self, a: LlmArch):
+        super().__init__()
+        self.embed_tokens = EmbedTokens(a.vocab, a.hidden)
+        self.layers = nn.ModuleList([_Layer(a) for _ in range(a.layers)])
+        self.norm = _W(a.hidden)
+
+
+class _ConfigView:
+    def __init__(self, a: LlmArch):
+        self.vocab_size = a.vocab
+        self.hidden_size = a.hidden
+        self.num_hidden_layers = a.layers
+        self.output_attentions = False
+        self.output_hidden_states = False
+        self.use_return_dict = True
+        self.tie_word_embeddings = a.tie_embeddings
+        self.eos_token_id = list(a.eos)
+        self.bos_token_id = a.bos
+
+
+class AudioLlamaForCausalLM(nn.Module):
+    def __init__(self, config: LlmArch):
+        super().__init__()
+        self.arch = config
+        self.config = _ConfigView(config)
+        self.model = _Model(config)
+        self.lm_head = _W(config.vocab, config.hidden)
+        if config.tie_embeddings:
+            self.lm_head.weight = self.model.embed_tokens.weight
+        self._packed = None
+
+    # ------------------------------------------------------------------------------------------ loading
+    @classmethod
+    def from_pretrained(cls, llm_type: str, use_cache: bool = True, torch_dtype=None, **kw):
+        """Same call as REF/trainer.py:58-62 / REF/inference.py:46-51. Reads the HF checkpoint's tensors through
+        transformers (needs local files or network) and re-homes them in this module."""
+        from ..config import KNOWN_LLMS
+        if llm_type not in KNOWN_LLMS:
+            raise Exception("Unknown LLM type.")
+        from transformers import AutoModelForCausalLM  # only to read the checkpoint
+        hf = AutoModelForCausalLM.from_pretrained(llm_type, torch_dtype=torch.bfloat16)
+        self = cls(KNOWN_LLMS[llm_type])
+        self.load_state_dict(hf.state_dict(), strict=False)
+        return self
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        sd = dict(state_dict)
+        if self.arch.tie_embeddings:
+            sd.setdefault("lm_head.weight", sd["model.embed_tokens.weight"])
+        sd = {k: v for k, v in sd.items() if not k.endswith("rotary_emb.inv_freq")}
+        self._packed = None
+        return super().load_state_dict(sd, strict=strict, assign=assign)
+
+    @property
+    def device(self):
+        return self.model.embed_tokens.weight.device
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        out = super()._apply(fn, *a, **k)
+        if self.arch.tie_embeddings:
+            self.lm_head.weight = self.model.embed_tokens.weight
+        return out
+
+    def packed(self):
+        """LlamaWeights struct (+ keep-alive list) in the kernels' layouts; built once (frozen LLM)."""
+        if self._packed is not None:
+            return self._packed
+        a = self.arch
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("AudioLlamaForCausalLM (B200 path) needs its weights on a CUDA device; no CPU path")
+        keep: List[torch.Tensor] = []
+
+        def K(t):
+            keep.append(t)
+            return t.data_ptr()
+
+        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        layers = (_lib.LlamaLayer * a.layers)()
+        for l, lay in enumerate(self.model.layers):
+            L = layers[l]
+            sa, mlp = lay.self_attn, lay.mlp
+            L.ln1_w = K(f32(lay.input_layernorm.weight))
+            L.wqkv = K(bf(packing.pack_qkv(sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight)))
+            L.wo = K(bf(sa.o_proj.weight))
+            L.ln2_w = K(f32(lay.post_attention_layernorm.weight))
+            L.wgu = K(bf(packing.pack_gate_up(mlp.gate_proj.weight.detach(), mlp.up_proj.weight.detach())))
+            L.wd = K(bf(mlp.down_proj.weight))
+        w = _lib.LlamaWeights()
+        w.layers = C.cast(layers, C.POINTER(_lib.LlamaLayer))
+        w.num_layers, w.hidden, w.heads, w.kv_heads = a.layers, a.hidden, a.heads, a.kv_heads
+        w.head_dim, w.ffn, w.vocab, w.rms_eps = a.head_dim, a.ffn, a.vocab, a.rms_eps
+        w.final_norm_w = K(f32(self.model.norm.weight))
+        w.lm_head = K(bf(self.lm_head.weight))
+        w.rope_cs = K(packing.rope_table(a.head_dim, a.max_pos, a.rope_theta, a.rope_scaling, device=dev))
+        w.max_pos = a.max_pos
+        self._packed = (w, layers, keep)
+        return self._packed
+
+    # ------------------------------------------------------------------------------------------ packed prefill
+    def prefill_packed(self, h: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, positions: torch.Tensor,
+                       logit_rows: Optional[torch.Tensor], *, tap_layers: Sequence[int] = (),
+                       tap_rows_a: Optional[torch.Tensor] = None, tap_rows_b: Optional[torch.Tensor] = None,
+                       all_hidden: bool = False, logits_out: Optional[torch.Tensor] = None):
+        """Run the LLM over packed sequences. h: fp32 [rows, H] (overwritten with the last residual stream).
+        Returns (logits bf16 [n_logit_rows, V] | None, fd_sq fp32 [taps, pairs] | None, all_hidden | None)."""
+        w = self.packed()[0]
+        a = self.arch
+        lib = _lib.load()
+        rows = h.shape[0]
+        assert h.dtype == torch.float32 and h.is_contiguous() and h.shape[1] == a.hidden
+        if int(max_seqlen) > a.max_pos:
+            raise ValueError(f"sequence of {max_seqlen} tokens exceeds the RoPE table ({a.max_pos})")
+        n_log = 0 if logit_rows is None else logit_rows.numel()
+        logits = None
+        if n_log:
+            logits = logits_out if logits_out is not None else torch.empty(n_log, a.vocab, device=h.device,
+                                                                           dtype=torch.bfloat16)
+        taps = [int(t) for t in tap_layers if 0 < int(t) < a.layers]  # tap 0 = identical embeddings -> 0 (skipped)
+        pairs = 0 if tap_rows_a is None else tap_rows_a.numel()
+        fd = torch.zeros(max(1, len(taps)), max(1, pairs), device=h.device, dtype=torch.float32)
+        tap_arr = (C.c_int32 * max(1, len(taps)))(*taps)
+        hid = torch.empty(a.layers + 1, rows, a.hidden, device=h.device, dtype=torch.float32) if all_hidden else None
+        nbytes = lib.b2s_llama_workspace_bytes(C.byref(w), rows, n_log)
+        ws = torch.empty(nbytes, device=h.device, dtype=torch.uint8)
+        _lib.check(lib.b2s_llama_prefill(
+            C.byref(w), h.data_ptr(), rows, cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, int(max_seqlen),
+            positions.data_ptr(), None if not n_log else logit_rows.data_ptr(), n_log,
+            None if logits is None else logits.data_ptr(), tap_arr, len(taps) if pairs else 0,
+            None if not pairs else tap_rows_a.data_ptr(), None if not pairs else tap_rows_b.data_ptr(), pairs,
+            fd.data_ptr(), None if hid is None else hid.data_ptr(), ws.data_ptr(), nbytes,
+            torch.cuda.current_stream().cuda_stream), "llama_prefill")
+        return logits, (fd if pairs and taps else None), hid
+
+    # ------------------------------------------------------------------------------------------ reference API
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
+                inputs_embeds=None, labels=None, use_cache=None, output_attentions=None,
+                output_hidden_states=None, return_dict=None, cache_position=None, num_logits_to_keep: int = 0,
+                **kwargs):
+        """REF/model/audio_llama.py:22-113. Batched inputs use the reference's left-padding + {0,1} mask
+        (REF/utils.py:136-146); internally the valid rows are packed and each sample gets its own causal mask."""
+        if output_attentions:
+            raise NotImplementedError("output_attentions is not available on the fused attention path")
+        if past_key_values is not None:
+            raise NotImplementedError("KV-cache continuation is the decode loop (SURVEY.md 8/f1), not built yet")
+        if inputs_embeds is None:
+            if input_ids is None:
+                raise ValueError("You must specify exactly one of input_ids or inputs_embeds")
+            inputs_embeds = self.model.embed_tokens(input_ids)
+        if not inputs_embeds.is_cuda:
+            raise RuntimeError("AudioLlamaForCausalLM.forward (B200 path) needs CUDA inputs; there is no CPU path")
+        dev = inputs_embeds.device
+        B, L, H = inputs_embeds.shape
+        if attention_mask is None:
+            lens = [L] * B
+        else:
+            lens = attention_mask.to("cpu").long().sum(dim=1).tolist()
+        # pack: sample b occupies padded columns [L - lens[b], L)
+        cu = [0]
+        for n in lens:
+            cu.append(cu[-1] + int(n))
+        rows = cu[-1]
+        if all(n == L for n in lens):
+            h = inputs_embeds.reshape(B * L, H).to(torch.float32).contiguous()
+        else:
+            h = torch.cat([inputs_embeds[b, L - lens[b]:, :] for b in range(B)], dim=0).to(torch.float32).contiguous()
+        cu_t = torch.tensor(cu, dtype=torch.int32, device=dev)
+        pos_t = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(dev)
+        keep = [n if num_logits_to_keep == 0 else min(int(num_logits_to_keep), n) for n in lens]
+        log_rows = torch.cat([torch.arange(cu[b + 1] - keep[b], cu[b + 1], dtype=torch.int32) for b in range(B)]).to(dev)
+        want_hidden = bool(output_hidden_states)
+        logits_p, _, hid = self.prefill_packed(h, cu_t, max(lens), pos_t, log_rows, all_hidden=want_hidden)
+
+        Lk = max(keep)
+        if all(k == Lk for k in keep):
+            logits = logits_p.view(B, Lk, -1)
+        else:
+            logits = logits_p.new_zeros(B, Lk, logits_p.shape[-1])
+            o = 0
+            for b in range(B):
+                logits[b, Lk - keep[b]:] = logits_p[o:o + keep[b]]
+                o += keep[b]
+
+        loss = None
+        if labels is not None:
+            # per-sample CE over logits[-R:-1] vs labels[1:], mean over samples (REF/model/audio_llama.py:72-101)
+            lab_rows, lab_vals, offs = [], [], [0]
+            o = 0
+            for b in range(B):
+                lb = labels[b].to(torch.int32).reshape(-1)
+                R = lb.numel()
+                start = o + keep[b] - R
+                lab_rows.append(torch.arange(start, start + R, dtype=torch.long))
+                lab_vals.append(torch.cat([lb[1:].cpu(), torch.tensor([-1], dtype=torch.int32)]))
+                offs.append(offs[-1] + R)
+                o += keep[b]
+            sel = logits_p[torch.cat(lab_rows).to(dev)]
+            res = ops.kd_ce_loss(sel, sel, torch.cat(lab_vals).to(dev), torch.tensor(offs, dtype=torch.int32, device=dev))
+            loss = res.loss_ntp.sum() / B
+
+        hidden_states = None
+        if want_hidden:
+            if all(n == L for n in lens):
+                hidden_states = tuple(hid[l].view(B, L, H) for l in range(hid.shape[0]))
+            else:
+                outs = []
+                for l in range(hid.shape[0]):
+                    t = hid.new_zeros(B, L, H)
+                    for b in range(B):
+                        t[b, L - lens[b]:] = hid[l, cu[b]:cu[b + 1]]
+                    outs.append(t)
+                hidden_states = tuple(outs)
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=hidden_states,
+                                      attentions=None)
+
+    @torch.no_grad()
+    def generate(self, input_ids=None, inputs_embeds=None, max_new_tokens: int = 256, **kwargs):
+        """Greedy decoding from a prompt given as embeddings (REF/inference.py:55-66, REF/trainer.py:530-545);
+        returns only the new token ids, like HF generate with inputs_embeds.
+        Round-1 note: the prompt prefill is the B200 path; each new token re-runs the prefill over the grown
+        sequence (no KV cache yet -- the cached decode loop is row f1 of SURVEY.md section 8)."""
+        if inputs_embeds is None:
+            inputs_embeds = self.model.embed_tokens(input_ids)
+        if inputs_embeds.shape[0] != 1:
+            raise NotImplementedError("generate() is batch-1 like the reference")
+        seq = inputs_embeds.to(torch.bfloat16)
+        eos = set(int(e) for e in self.arch.eos)
+        out: List[int] = []
+        for _ in range(int(max_new_tokens)):
+            logits = self.forward(inputs_embeds=seq, num_logits_to_keep=1).logits
+            nxt = int(logits[0, -1].float().argmax())
+            out.append(nxt)
+            if nxt in eos:
+                break
+            tok = torch.tensor([[nxt]], device=seq.device)
+            seq = torch.cat([seq, self.model.embed_tokens(tok)], dim=1)
+        return torch.tensor([out], dtype=torch.long, device=seq.device)

@@ -1,0 +1,182 @@
+"""The fused audio-prompt step: the body of the reference's training loop up to the losses
+(REF/trainer.py:270-370) for a whole micro-batch of utterances in a handful of launches.
+
+    encoder (b2s_hubert_forward, batched) -> one splice launch that builds EVERY student (audio-prompt) and teacher
+    (text-prompt) sequence packed back to back -> ONE LLM prefill over all of them (student and teacher share the
+    frozen weights; independent causal masks via cu_seqlens) with the FD taps fused in and the LM head computed
+    only on the consumed rows (last R of each sequence, REF/trainer.py:334,350-351) -> fused CE+KD loss.
+
+Per-utterance semantics are exactly the reference's batch-1 step: every utterance gets its own means
+(ntp over R-1 rows, ld over R rows, fd over R x hidden per tapped layer), and
+total_u = w_ntp*ntp_u + w_ld*ld_u + w_fd*fd_u (REF/trainer.py:325-370).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .utils import prompt_ids
+
+
+@dataclass
+class StepPlan:
+    """Host-built index arrays for one micro-batch (everything the kernels need besides the tensors)."""
+    row_src: torch.Tensor       # int32 [rows]   splice sources
+    cu_seqlens: torch.Tensor    # int32 [2B+1]
+    positions: torch.Tensor     # int32 [rows]
+    logit_rows: torch.Tensor    # int32 [2*sumR] student rows then teacher rows
+    labels: torch.Tensor        # int32 [sumR]
+    row_offsets: torch.Tensor   # int32 [B+1]
+    max_seqlen: int
+    rows: int
+    sum_r: int
+    resp_lens: List[int]
+    L_audio: List[int]
+    L_text: List[int]
+    seg: Optional[torch.Tensor] = None        # int64 [sumR] utterance index of each response row
+    resp_len_f: Optional[torch.Tensor] = None  # fp32 [B]
+
+
+def build_plan(prefix: Sequence[int], suffix: Sequence[int], n_audio: int, text_ids: Sequence[Sequence[int]],
+               resp_ids: Sequence[Sequence[int]], with_teacher: bool = True) -> Dict[str, object]:
+    """Pure-python index construction (no torch, unit-tested on CPU).
+    Sequence layout (REF/utils.py:27-46 + the double BOS strip):
+        student_i = prefix | audio rows of utterance i | suffix[1:] | response_i[1:]
+        teacher_i = prefix | transcript_i              | suffix[1:] | response_i[1:]
+    Packed order: student_0..student_{B-1}, teacher_0..teacher_{B-1}. Logits are produced for the last R_i rows of
+    each; CE labels for row j < R_i - 1 of utterance i are response_i[j+1], the last row has none (-1)."""
+    B = len(resp_ids)
+    row_src: List[int] = []
+    cu = [0]
+    positions: List[int] = []
+    L_audio, L_text = [], []
+    suf = list(suffix[1:])
+    for i in range(B):
+        resp = list(resp_ids[i])[1:]
+        seq = list(prefix) + [-(i * n_audio + r) - 1 for r in range(n_audio)] + suf + resp
+        row_src.extend(seq)
+        positions.extend(range(len(seq)))
+        cu.append(cu[-1] + len(seq))
+        L_audio.append(len(seq))
+    if with_teacher:
+        for i in range(B):
+            resp = list(resp_ids[i])[1:]
+            seq = list(prefix) + list(text_ids[i]) + suf + resp
+            row_src.extend(seq)
+            positions.extend(range(len(seq)))
+            cu.append(cu[-1] + len(seq))
+            L_text.append(len(seq))
+    resp_lens = [len(r) for r in resp_ids]
+    s_rows: List[int] = []
+    t_rows: List[int] = []
+    labels: List[int] = []
+    offs = [0]
+    for i in range(B):
+        R = resp_lens[i]
+        if R > L_audio[i]:
+            raise ValueError("response longer than its sequence")
+        s_rows.extend(range(cu[i + 1] - R, cu[i + 1]))
+        if with_teacher:
+            t_rows.extend(range(cu[B + i + 1] - R, cu[B + i + 1]))
+        labels.extend(list(resp_ids[i])[1:] + [-1])
+        offs.append(offs[-1] + R)
+    return dict(row_src=row_src, cu_seqlens=cu, positions=positions, student_rows=s_rows, teacher_rows=t_rows,
+                labels=labels, row_offsets=offs, max_seqlen=max(L_audio + L_text), rows=cu[-1], sum_r=offs[-1],
+                resp_lens=resp_lens, L_audio=L_audio, L_text=L_text)
+
+
+class AudioPromptStep:
+    def __init__(self, audio_encoder, llm, tokenizer, llm_type: str, *, use_ld_loss: bool = True,
+                 use_fd_loss: bool = True, ntp_loss_weight: float = 0.5, ld_loss_weight: float = 0.5,
+                 fd_loss_weight: float = 1.0, fd_loss_connector_layers: Sequence[int] = (0, 5, 11, 17, 23)):
+        self.audio_encoder = audio_encoder
+        self.llm = llm
+        self.prefix, self.suffix = prompt_ids(tokenizer, llm_type)
+        self.use_ld, self.use_fd = use_ld_loss, use_fd_loss
+        self.w_ntp, self.w_ld, self.w_fd = ntp_loss_weight, ld_loss_weight, fd_loss_weight
+        self.fd_layers = [int(l) for l in fd_loss_connector_layers]
+        for l in self.fd_layers:
+            if not 0 <= l < llm.arch.layers:
+                raise ValueError(f"fd_loss_connector_layers entry {l} outside the LLM's {llm.arch.layers} layers")
+
+    @classmethod
+    def from_config(cls, config, audio_encoder, llm, tokenizer):
+        t = config.train
+        return cls(audio_encoder, llm, tokenizer, config.model.llm_type, use_ld_loss=t.use_ld_loss,
+                   use_fd_loss=t.use_fd_loss, ntp_loss_weight=t.ntp_loss_weight, ld_loss_weight=t.ld_loss_weight,
+                   fd_loss_weight=t.fd_loss_weight, fd_loss_connector_layers=t.fd_loss_connector_layers)
+
+    def plan(self, n_audio: int, text_ids, resp_ids, device) -> StepPlan:
+        as_list = lambda xs: [x.tolist() if torch.is_tensor(x) else list(x) for x in xs]
+        d = build_plan(self.prefix, self.suffix, n_audio, as_list(text_ids), as_list(resp_ids),
+                       with_teacher=(self.use_ld or self.use_fd))
+        i32 = lambda x: torch.tensor(x, dtype=torch.int32).pin_memory().to(device, non_blocking=True)
+        return StepPlan(row_src=i32(d["row_src"]), cu_seqlens=i32(d["cu_seqlens"]), positions=i32(d["positions"]),
+                        logit_rows=i32(d["student_rows"] + d["teacher_rows"]), labels=i32(d["labels"]),
+                        row_offsets=i32(d["row_offsets"]), max_seqlen=d["max_seqlen"], rows=d["rows"],
+                        sum_r=d["sum_r"], resp_lens=d["resp_lens"], L_audio=d["L_audio"], L_text=d["L_text"],
+                        seg=torch.tensor([i for i, R in enumerate(d["resp_lens"]) for _ in range(R)],
+                                         dtype=torch.int64).pin_memory().to(device, non_blocking=True),
+                        resp_len_f=torch.tensor(d["resp_lens"], dtype=torch.float32).pin_memory().to(
+                            device, non_blocking=True))
+
+    @torch.no_grad()
+    def forward_losses(self, waves: torch.Tensor, text_ids, resp_ids, plan: Optional[StepPlan] = None,
+                       keep: bool = False) -> Dict[str, torch.Tensor]:
+        """waves: CUDA fp32 (B, T0), equal-length utterances (the reference's collate zero-pads a batch to one
+        length, REF/trainer.py:146-149; batch-1 has no padding). Returns per-utterance device tensors
+        ntp_loss / ld_loss / fd_loss / total_loss of shape (B,)."""
+        if not waves.is_cuda:
+            raise RuntimeError("AudioPromptStep needs CUDA inputs; there is no CPU path")
+        dev = waves.device
+        B = waves.shape[0]
+        audio = self.audio_encoder.forward_fp32(waves)  # (B, A, C) fp32
+        A, Cdim = audio.shape[1], audio.shape[2]
+        if plan is None:
+            plan = self.plan(A, text_ids, resp_ids, dev)
+        h = ops.embed_splice(self.llm.model.embed_tokens.weight, audio.view(B * A, Cdim), plan.row_src)
+        with_teacher = self.use_ld or self.use_fd
+        taps = [l for l in self.fd_layers if l > 0] if self.use_fd else []
+        s_rows = plan.logit_rows[:plan.sum_r]
+        t_rows = plan.logit_rows[plan.sum_r:] if with_teacher else None
+        logits, fd_sq, _ = self.llm.prefill_packed(
+            h, plan.cu_seqlens, plan.max_seqlen, plan.positions, plan.logit_rows, tap_layers=taps,
+            tap_rows_a=s_rows if taps else None, tap_rows_b=t_rows if taps else None)
+        s_log = logits[:plan.sum_r]
+        t_log = logits[plan.sum_r:] if with_teacher else s_log
+        res = ops.kd_ce_loss(s_log, t_log, plan.labels, plan.row_offsets, scale_kd=self.w_ld, scale_ce=self.w_ntp)
+        out = {"ntp_loss": res.loss_ntp}
+        total = self.w_ntp * res.loss_ntp
+        if self.use_ld:
+            out["ld_loss"] = res.loss_ld
+            total = total + self.w_ld * res.loss_ld
+        if self.use_fd:
+            # fd_u = sum over tapped layers of mean_{R_u x H}(diff^2); the layer-0 tap compares identical response
+            # embeddings and is exactly 0, so it is skipped.
+            fd = torch.zeros(B, device=dev, dtype=torch.float32)
+            if fd_sq is not None:
+                per_row = fd_sq.sum(dim=0)  # [sumR]
+                fd.index_add_(0, plan.seg, per_row)
+                fd = fd / (plan.resp_len_f * Cdim)
+            out["fd_loss"] = fd
+            total = total + self.w_fd * fd
+        out["total_loss"] = total
+        if keep:
+            out["audio_embeds"] = audio
+            out["student_logits"] = s_log
+            out["teacher_logits"] = t_log
+            out["kd_stats"] = res
+            out["plan"] = plan
+        return out
+
+    def __call__(self, waves_host: torch.Tensor, text_ids, resp_ids, device) -> Dict[str, float]:
+        """End-to-end call from HOST buffers: pinned H2D copy of the waveforms and ids, the fused step, and a D2H
+        read of the per-utterance losses (what bench.py's `e2e` times)."""
+        waves = waves_host.to(device, non_blocking=True)
+        out = self.forward_losses(waves, text_ids, resp_ids)
+        keys = [k for k in ("ntp_loss", "ld_loss", "fd_loss", "total_loss") if k in out]
+        stacked = torch.stack([out[k] for k in keys]).cpu()  # one D2H, synchronises
+        return {k: stacked[i] for i, k in enumerate(keys)}

@@ -1,0 +1,259 @@
+"""CPU suite (`-m "not gpu"`): the oracle against the golden vectors produced by the reference, the host logic
+(index plans, config, checkpoint layout), the C-ABI library's symbol table, and the world-size-2 gloo path."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import rel_l2
+from helpers import GOLDEN, ROOT, ns_config
+
+
+# --------------------------------------------------------------------------------------- oracle vs golden
+def _load_case(name):
+    from oracle import configs
+    g = torch.load(os.path.join(GOLDEN, f"{name}.pt"), weights_only=False)
+    enc_cfg = configs.EncoderCfg(**g["enc_cfg"])
+    llm_cfg = configs.LlmCfg(**g["llm_cfg"])
+    return g, enc_cfg, llm_cfg
+
+
+@pytest.mark.parametrize("name", ["tiny_llama_hubert", "tiny_minichat_hubert"])
+def test_oracle_matches_reference_golden(name):
+    """The restatement must reproduce what the reference's own modules produced (oracle/make_golden.py)."""
+    from oracle import configs, reference_math as rm
+    g, enc_cfg, llm_cfg = _load_case(name)
+    enc_sd = configs.make_encoder_state_dict(enc_cfg, seed=g["enc_seed"])
+    llm_sd = configs.make_llm_state_dict(llm_cfg, seed=g["llm_seed"])
+    tok = configs.stub_tokenizer(llm_cfg)
+    audio, text_ids, resp_ids = configs.synthetic_utterance(llm_cfg, 0, g["samples"], T=g["T"], R=g["R"])
+    with torch.no_grad():
+        o = rm.train_step_losses(enc_sd, llm_sd, enc_cfg, llm_cfg, tok, audio, text_ids, resp_ids,
+                                 fd_layers=g["fd_layers"], keep=True)
+        _, _, pre = rm.audio_prompt_prefill(enc_sd, llm_sd, enc_cfg, llm_cfg, tok, audio, g["extra_ids"])
+    assert o["L_audio"] == g["L_audio"] and o["L_text"] == g["L_text"]
+    assert rel_l2(o["audio_embeds"][0], g["audio_embeds"]) < 1e-4
+    assert rel_l2(o["student_logits"][0], g["student_logits"]) < 1e-4
+    assert rel_l2(o["teacher_logits"][0], g["teacher_logits"]) < 1e-4
+    assert rel_l2(pre[0], g["prefill_logits"]) < 1e-4
+    for k in ("ntp_loss", "ld_loss", "fd_loss"):
+        assert abs(float(o[k]) - g[k]) <= 1e-5 * abs(g[k]) + 1e-7
+    assert rm.compute_num_audio_embeds(g["samples"]) == g["num_audio_embeds"]
+
+
+def test_oracle_identities():
+    """D1/D2 (single-pass KD and CE from running statistics) and D5 (pool <-> projector)."""
+    from oracle import reference_math as rm
+    g = torch.Generator().manual_seed(0)
+    s = torch.randn(7, 1000, generator=g, dtype=torch.float64) * 3
+    t = torch.randn(7, 1000, generator=g, dtype=torch.float64) * 3
+    ref = rm.soft_cross_entropy(s, t)
+    lse = torch.logsumexp(s, -1)
+    dot = (torch.softmax(t, -1) * s).sum(-1)
+    assert abs(float((lse - dot).mean()) - float(ref)) < 1e-12
+    h = torch.randn(1, 499, 64, generator=g, dtype=torch.float64)
+    w = torch.randn(32, 64, generator=g, dtype=torch.float64)
+    pool = lambda x: torch.nn.functional.avg_pool1d(x.transpose(1, 2), 8, 4).transpose(1, 2)
+    assert rel_l2(pool(h) @ w.t(), pool(h @ w.t())) < 1e-12
+    assert pool(h).shape[1] == 123
+
+
+def test_compute_num_audio_embeds_matches_reference_values():
+    """REF/utils.py:13-24 on the benchmark lengths (160 000 -> 123, 480 000 -> 373)."""
+    from llm_speech_summarization_b200.utils import compute_num_audio_embeds
+    from oracle.reference_math import compute_num_audio_embeds as ref
+    for n, want in ((160000, 123), (480000, 373)):
+        assert compute_num_audio_embeds(n) == want == ref(n)
+    for n in (400, 8000, 16000, 123457):
+        assert compute_num_audio_embeds(n, sr=16000) == ref(n, sr=16000)
+
+
+# --------------------------------------------------------------------------------------- host logic
+def test_build_plan_matches_reference_layout():
+    """Packed index plan == the reference's sequence construction (double BOS strip, label alignment, lengths)."""
+    from oracle import configs, reference_math as rm
+    from llm_speech_summarization_b200.step import build_plan
+    llm_cfg = configs.TINY_LLAMA
+    tok = configs.stub_tokenizer(llm_cfg)
+    prefix, suffix = tok.prefix_ids, tok.suffix_ids
+    utts = [configs.synthetic_utterance(llm_cfg, i, 16, T=4 + i, R=3 + 2 * i) for i in range(3)]
+    A = 5
+    plan = build_plan(prefix, suffix, A, [u[1].tolist() for u in utts], [u[2].tolist() for u in utts])
+    table = torch.arange(llm_cfg.vocab, dtype=torch.float32)[:, None].repeat(1, 2)  # embedding = token id
+    embed = lambda ids: torch.nn.functional.embedding(ids, table)
+    audio = [-(torch.arange(i * A, (i + 1) * A, dtype=torch.float32) + 1)[:, None].repeat(1, 2) for i in range(3)]
+    a_seq, a_mask, t_seq, t_mask = rm.batch_full_embed_sequence(audio, [u[1] for u in utts], [u[2] for u in utts],
+                                                                tok, embed, llm_cfg.llm_type, process_text=True)
+    cu = plan["cu_seqlens"]
+    src = torch.tensor(plan["row_src"], dtype=torch.float32)
+    for i in range(3):
+        La, Lt = int(a_mask[i].sum()), int(t_mask[i].sum())
+        assert plan["L_audio"][i] == La and plan["L_text"][i] == Lt
+        assert torch.equal(src[cu[i]:cu[i + 1]], a_seq[i, a_seq.shape[1] - La:, 0])
+        assert torch.equal(src[cu[3 + i]:cu[3 + i + 1]], t_seq[i, t_seq.shape[1] - Lt:, 0])
+        assert plan["positions"][cu[i]:cu[i + 1]] == list(range(La))
+        R = len(utts[i][2])
+        rows = plan["student_rows"][plan["row_offsets"][i]:plan["row_offsets"][i + 1]]
+        assert rows == list(range(cu[i + 1] - R, cu[i + 1]))
+        labels = plan["labels"][plan["row_offsets"][i]:plan["row_offsets"][i + 1]]
+        assert labels == utts[i][2].tolist()[1:] + [-1]  # logits[-R:-1] vs labels[1:], REF/model/audio_llama.py:84-89
+    assert plan["rows"] == cu[-1] and plan["sum_r"] == sum(len(u[2]) for u in utts)
+    # P=9, A=123, S=6, R=64, T=40 -> 200 and 117
+    p = build_plan(list(range(9)), list(range(6)), 123, [list(range(40))], [list(range(64))])
+    assert p["L_audio"] == [200] and p["L_text"] == [117]
+
+
+def test_build_plan_edge_cases():
+    from llm_speech_summarization_b200.step import build_plan
+    p = build_plan([1, 2], [1, 3], 2, [[]], [[9]])  # empty transcript, 1-token response (no CE rows)
+    assert p["L_audio"] == [2 + 2 + 1 + 0] and p["L_text"] == [2 + 0 + 1 + 0]
+    assert p["labels"] == [-1] and p["sum_r"] == 1
+    p = build_plan([1], [1], 0, [[5, 6]], [[7, 8, 9]], with_teacher=False)  # no audio rows, no teacher
+    assert p["teacher_rows"] == [] and p["L_text"] == [] and p["L_audio"] == [1 + 0 + 0 + 2]
+    with pytest.raises(ValueError):
+        build_plan([], [1], 0, [[]], [[1, 2, 3, 4]])  # response longer than the sequence it must end
+
+
+def test_state_dict_layout_matches_reference_checkpoint():
+    """AudioEncoder.state_dict() == the reference's checkpoint layout (424 tensors for
+    HuBERT-large + pool), both weight-norm spellings load, and the trainer / inference checkpoint dicts round-trip."""
+    from oracle import configs
+    from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
+    cfg = ns_config(configs.TINY_ENCODER, configs.TINY_LLAMA)
+    enc = AudioEncoder(cfg, torch.device("cpu"))
+    sd = configs.make_encoder_state_dict(configs.TINY_ENCODER)
+    assert set(enc.state_dict().keys()) == set(sd.keys())
+    for k, v in enc.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    enc.load_state_dict(sd, strict=True)
+    legacy = dict(sd)
+    pc = "encoder.encoder.pos_conv_embed.conv."
+    legacy[pc + "weight_g"] = legacy.pop(pc + "parametrizations.weight.original0")
+    legacy[pc + "weight_v"] = legacy.pop(pc + "parametrizations.weight.original1")
+    enc2 = AudioEncoder(cfg, torch.device("cpu"))
+    enc2.load_state_dict(legacy, strict=True)
+    assert torch.equal(enc2.state_dict()[pc + "parametrizations.weight.original1"], sd[pc + "parametrizations.weight.original1"])
+    # full-size key count
+    from llm_speech_summarization_b200.config import EncoderArch
+    from llm_speech_summarization_b200.model.audio_encoder import HubertBackbone
+    n = len(HubertBackbone(EncoderArch(layers=24)).state_dict()) + 2  # + embed_projection.{weight,bias}
+    assert n == 424
+
+
+def test_config_loader_reads_reference_yaml_keys(tmp_path):
+    from llm_speech_summarization_b200.config import load_config, llm_arch_from_config, encoder_arch_from_config
+    y = tmp_path / "c.yaml"
+    y.write_text("""
+seed_everything: 1234
+model:
+  audio_encoder:
+    base: hubert
+    type: facebook/hubert-large-ls960-ft
+    downsample_method: pool
+    downsample_factor: 4
+    pooling:
+      kernel_size: 8
+      stride: 4
+  llm_type: "meta-llama/Llama-3.2-3B-Instruct"
+  llm_embedding_channels: 3072
+audio:
+  sampling_rate: 16000
+train:
+  grad_accum_interval: 16
+  use_ld_loss: True
+  fd_loss_connector_layers: [0, 5, 11, 17, 23]
+""")
+    c = load_config(str(y))
+    assert c.model.audio_encoder.pooling.kernel_size == 8 and c.train.fd_loss_connector_layers == [0, 5, 11, 17, 23]
+    a = llm_arch_from_config(c)
+    assert (a.layers, a.heads, a.kv_heads, a.vocab) == (28, 24, 8, 128256)
+    assert encoder_arch_from_config(c).hidden == 1024
+    c.model.llm_type = "nope"
+    with pytest.raises(Exception, match="Unknown LLM type."):
+        llm_arch_from_config(c)
+
+
+def test_reference_error_texts():
+    from oracle import configs
+    from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
+    from llm_speech_summarization_b200 import utils as U
+    cfg = ns_config(configs.TINY_ENCODER, configs.TINY_LLAMA)
+    cfg.model.audio_encoder.base = "wav2vec"
+    with pytest.raises(Exception, match="Unexpected encoder type in config."):
+        AudioEncoder(cfg, torch.device("cpu"))
+    with pytest.raises(Exception, match="Unknown LLM type."):
+        U.merge_prompt_tokens(None, None, None, "gpt2", "cpu")
+
+
+# --------------------------------------------------------------------------------------- C ABI
+def test_abi_exports_every_declared_symbol():
+    """libb2s.so loads without a GPU and exports exactly the functions include/b2s.h declares."""
+    from llm_speech_summarization_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "b2s.h")).read()
+    declared = set(re.findall(r"\b(b2s_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/b2s.h but not exported"
+    assert declared == set(_lib.PROTOTYPES.keys())
+    assert lib.b2s_version() == 1
+    assert lib.b2s_kd_ce_workspace_bytes(64, 128256) == 64 * 8 * 24
+
+
+def test_abi_fails_loudly_without_gpu():
+    """No CPU fallback: a compute call on a box without a CUDA device returns an error status + message."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from llm_speech_summarization_b200 import _lib
+    lib = _lib.load()
+    buf = (ctypes.c_float * 1024)()
+    rc = lib.b2s_cast_f32_to_bf16(ctypes.addressof(buf), ctypes.addressof(buf), 1024, None)
+    assert rc != 0 and len(lib.b2s_last_error()) > 0
+
+
+# --------------------------------------------------------------------------------------- world-size-2 (gloo)
+_DIST_SCRIPT = r"""
+import os, sys, torch
+sys.path.insert(0, os.environ["B2S_ROOT"])
+from llm_speech_summarization_b200 import dp
+rank, local_rank, world = dp.init_process_group("gloo")
+assert world == 2
+# sharding: disjoint, complete, balanced
+mine = dp.shard_indices(17, rank, world)
+cnt = torch.zeros(17); cnt[mine] = 1
+torch.distributed.all_reduce(cnt)
+assert torch.equal(cnt, torch.ones(17)) and abs(len(mine) - 17 / 2) <= 0.5
+# summed-gradient invariant: 16 utterances split over 2 ranks == 1 rank doing all 16 (REF/trainer.py:372-384)
+torch.manual_seed(0)
+w = torch.randn(5, 3, dtype=torch.float64)
+xs = torch.randn(16, 3, dtype=torch.float64)
+def grads(idx):
+    g1, g2 = torch.zeros(5, 3, dtype=torch.float64), torch.zeros(7, dtype=torch.float32)
+    for i in idx:
+        wi = w.clone().requires_grad_(True)
+        (torch.tanh(wi @ xs[i]).sum() * dp.local_accum_scale(16)).backward()
+        g1 += wi.grad; g2 += float(i)
+    return [g1, g2]
+local = grads(dp.shard_indices(16, rank, world))
+dp.allreduce_sum_(local, bucket_bytes=64)
+full = grads(range(16))
+assert torch.allclose(local[0], full[0], atol=1e-12) and torch.allclose(local[1], full[1])
+assert dp.max_over_ranks(float(rank), "cpu") == 1.0 and dp.sum_over_ranks(1.0, "cpu") == 2.0
+dp.barrier()
+print("OK", rank)
+"""
+
+
+def test_data_parallel_world_size_2_gloo(tmp_path):
+    script = tmp_path / "dist_check.py"
+    script.write_text(_DIST_SCRIPT)
+    env = dict(os.environ, B2S_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("OK") == 2

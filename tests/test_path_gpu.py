@@ -1,0 +1,165 @@
+"""End-to-end parity of the CUDA path (through the drop-in modules and the C ABI) against
+  (1) the golden vectors produced by the REFERENCE's own modules (tests/golden/*.pt, oracle/make_golden.py) and
+  (2) the CPU oracle (oracle/reference_math.py) on the same seeded inputs.
+
+Tolerances are the north star's: projected audio embeddings and logits within 2e-2 relative (bf16 vs the
+reference's fp32), KD loss within 1e-3 relative.
+"""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_l2
+from helpers import GOLDEN, bf16_round_sd, build_product
+
+pytestmark = pytest.mark.gpu
+
+TOL_EMBED = 2e-2
+TOL_LOGITS = 2e-2
+TOL_KD = 1e-3
+
+
+def _load_case(name):
+    from oracle import configs
+    g = torch.load(os.path.join(GOLDEN, f"{name}.pt"), weights_only=False)
+    enc_cfg = configs.EncoderCfg(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in g["enc_cfg"].items()})
+    llm_cfg = configs.LlmCfg(**g["llm_cfg"])
+    enc_sd = configs.make_encoder_state_dict(enc_cfg, seed=g["enc_seed"])
+    llm_sd = configs.make_llm_state_dict(llm_cfg, seed=g["llm_seed"])
+    return g, enc_cfg, llm_cfg, enc_sd, llm_sd
+
+
+@pytest.mark.parametrize("name", ["tiny_llama_hubert", "tiny_minichat_hubert"])
+def test_golden_step(cuda, name):
+    """Fused step (encoder -> splice -> packed student+teacher prefill -> CE/KD/FD) vs the reference's outputs."""
+    from oracle import configs
+    from llm_speech_summarization_b200.step import AudioPromptStep
+    g, enc_cfg, llm_cfg, enc_sd, llm_sd = _load_case(name)
+    cfg, enc, llm = build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, cuda)
+    tok = configs.stub_tokenizer(llm_cfg)
+    audio, text_ids, resp_ids = configs.synthetic_utterance(llm_cfg, 0, g["samples"], T=g["T"], R=g["R"])
+    step = AudioPromptStep(enc, llm, tok, llm_cfg.llm_type, fd_loss_connector_layers=g["fd_layers"])
+    out = step.forward_losses(audio[None, :].to(cuda), [text_ids], [resp_ids], keep=True)
+    plan = out["plan"]
+    assert plan.L_audio[0] == g["L_audio"] and plan.L_text[0] == g["L_text"]
+    assert out["audio_embeds"].shape[1] >= g["num_audio_embeds"]
+    assert rel_l2(out["audio_embeds"][0].cpu(), g["audio_embeds"]) < TOL_EMBED
+    assert rel_l2(out["student_logits"].float().cpu(), g["student_logits"]) < TOL_LOGITS
+    assert rel_l2(out["teacher_logits"].float().cpu(), g["teacher_logits"]) < TOL_LOGITS
+    assert abs(float(out["ld_loss"][0]) - g["ld_loss"]) / abs(g["ld_loss"]) < TOL_KD
+    assert abs(float(out["ntp_loss"][0]) - g["ntp_loss"]) / abs(g["ntp_loss"]) < 5e-3
+    assert abs(float(out["fd_loss"][0]) - g["fd_loss"]) / abs(g["fd_loss"]) < 3e-2
+    total = 0.5 * g["ntp_loss"] + 0.5 * g["ld_loss"] + 1.0 * g["fd_loss"]
+    assert abs(float(out["total_loss"][0]) - total) / abs(total) < 1e-2
+
+
+def test_dropin_modules_match_fused_and_oracle(cuda):
+    """The reference-signature calls (AudioEncoder.forward, utils.batch_full_embed_sequence,
+    AudioLlamaForCausalLM.forward with labels / hidden states, utils.soft_cross_entropy) reproduce the trainer's
+    step (REF/trainer.py:278-370) and agree with the oracle."""
+    from oracle import configs, reference_math as rm
+    from llm_speech_summarization_b200 import utils as U
+    g, enc_cfg, llm_cfg, enc_sd, llm_sd = _load_case("tiny_llama_hubert")
+    cfg, enc, llm = build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, cuda)
+    tok = configs.stub_tokenizer(llm_cfg)
+    audio, text_ids, resp_ids = configs.synthetic_utterance(llm_cfg, 0, g["samples"], T=g["T"], R=g["R"])
+    R = g["R"]
+    with torch.no_grad():
+        embeds = enc(audio[None, :].to(cuda))  # (1, A, C) bf16
+        a_seq, a_mask, t_seq, t_mask = U.batch_full_embed_sequence(
+            all_audio_embeds=embeds, all_text_input_ids=[text_ids], all_response_input_ids=[resp_ids], tokenizer=tok,
+            embed_tokens=llm.model.embed_tokens, llm_type=llm_cfg.llm_type, device=cuda, process_text=True)
+        assert a_seq.shape[1] == g["L_audio"] and t_seq.shape[1] == g["L_text"]
+        s_out = llm(inputs_embeds=a_seq, labels=[resp_ids.to(cuda)], output_hidden_states=True,
+                    attention_mask=a_mask.to(cuda))
+        t_out = llm(inputs_embeds=t_seq, labels=[resp_ids.to(cuda)], output_hidden_states=True,
+                    attention_mask=t_mask.to(cuda))
+        ld = U.soft_cross_entropy(s_out.logits[:, -R:, :], t_out.logits[:, -R:, :])
+        fd = sum(torch.nn.functional.mse_loss(s_out.hidden_states[l][:, -R:, :], t_out.hidden_states[l][:, -R:, :])
+                 for l in g["fd_layers"])
+    assert len(s_out.hidden_states) == llm_cfg.layers + 1
+    assert rel_l2(s_out.logits[0, -R:].float().cpu(), g["student_logits"]) < TOL_LOGITS
+    assert abs(float(s_out.loss) - g["ntp_loss"]) / abs(g["ntp_loss"]) < 5e-3
+    assert abs(float(ld) - g["ld_loss"]) / abs(g["ld_loss"]) < TOL_KD
+    assert abs(float(fd) - g["fd_loss"]) / abs(g["fd_loss"]) < 3e-2
+    # oracle with the same bf16-rounded LLM weights: tighter agreement on the hidden states
+    _, hs = rm.llama_model_forward(bf16_round_sd(llm_sd), a_seq.float().cpu(), a_mask, llm_cfg, output_hidden_states=True)
+    for l in (1, llm_cfg.layers):
+        assert rel_l2(s_out.hidden_states[l].float().cpu(), hs[l]) < 1e-2
+
+
+def test_prefill_inference_prompt(cuda):
+    """generate_audio_response's prompt assembly + prefill (REF/inference.py:95-135): additional text prompt before
+    the audio, merge_prompt_tokens, last-row logits; plus two greedy steps of generate()."""
+    from oracle import configs
+    from llm_speech_summarization_b200 import utils as U
+    g, enc_cfg, llm_cfg, enc_sd, llm_sd = _load_case("tiny_minichat_hubert")
+    cfg, enc, llm = build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, cuda)
+    tok = configs.stub_tokenizer(llm_cfg)
+    audio, _, _ = configs.synthetic_utterance(llm_cfg, 0, g["samples"], T=g["T"], R=g["R"])
+    with torch.no_grad():
+        embeds = enc(audio[None, :].to(cuda), ctc_pool_ranges=None)
+        text = llm.model.embed_tokens(g["extra_ids"][None, :].to(cuda))
+        combined = torch.cat([text, embeds], dim=1)
+        prompt = U.merge_prompt_tokens(inputs_embeds=combined, tokenizer=tok, embed_tokens=llm.model.embed_tokens,
+                                       llm_type=llm_cfg.llm_type, device=cuda)
+        logits = llm(inputs_embeds=prompt, num_logits_to_keep=1).logits[0, -1]
+        ids = llm.generate(input_ids=None, inputs_embeds=prompt, max_new_tokens=2)
+    assert rel_l2(logits.float().cpu(), g["prefill_logits"]) < TOL_LOGITS
+    assert ids.shape[0] == 1 and 1 <= ids.shape[1] <= 2
+    assert int(ids[0, 0]) == int(g["prefill_logits"].argmax()) or \
+        float(g["prefill_logits"].topk(2).values.diff().abs()) < 1e-2  # greedy token unless a near-tie
+
+
+def test_batched_step_equals_per_utterance(cuda):
+    """Packing B utterances into one launch must give each utterance the numbers it gets alone (batch-1 semantics)."""
+    from oracle import configs
+    from llm_speech_summarization_b200.step import AudioPromptStep
+    g, enc_cfg, llm_cfg, enc_sd, llm_sd = _load_case("tiny_llama_hubert")
+    cfg, enc, llm = build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, cuda)
+    tok = configs.stub_tokenizer(llm_cfg)
+    step = AudioPromptStep(enc, llm, tok, llm_cfg.llm_type, fd_loss_connector_layers=g["fd_layers"])
+    utts = [configs.synthetic_utterance(llm_cfg, i, 8000, T=5 + 3 * i, R=4 + 2 * i) for i in range(3)]
+    waves = torch.stack([u[0] for u in utts]).to(cuda)
+    both = step.forward_losses(waves, [u[1] for u in utts], [u[2] for u in utts])
+    for i, (a, t, r) in enumerate(utts):
+        one = step.forward_losses(a[None].to(cuda), [t], [r])
+        for k in ("ntp_loss", "ld_loss", "fd_loss", "total_loss"):
+            assert abs(float(both[k][i]) - float(one[k][0])) <= 2e-3 * abs(float(one[k][0])) + 1e-6, (k, i)
+
+
+def test_no_cpu_path():
+    """The product must fail loudly without CUDA tensors instead of falling back."""
+    from oracle import configs
+    from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
+    from helpers import ns_config
+    enc = AudioEncoder(ns_config(configs.TINY_ENCODER, configs.TINY_LLAMA), torch.device("cpu")).eval()
+    with pytest.raises(RuntimeError):
+        enc(torch.zeros(1, 4000))
+
+
+@pytest.mark.slow
+def test_full_size_vs_oracle(cuda):
+    """Full architectures (HuBERT-large + Llama-3.2-3B shapes, random init, 10 s audio): CUDA path vs the CPU
+    oracle run on this box's host cores. ~2-4 min of CPU time."""
+    from oracle import configs, reference_math as rm
+    from llm_speech_summarization_b200.step import AudioPromptStep
+    enc_cfg, llm_cfg = configs.HUBERT_LARGE, configs.LLAMA32_3B
+    enc_sd = configs.make_encoder_state_dict(enc_cfg, seed=1234)
+    llm_sd = configs.make_llm_state_dict(llm_cfg, seed=4321, dtype=torch.bfloat16)
+    tok = configs.stub_tokenizer(llm_cfg)
+    audio, text_ids, resp_ids = configs.synthetic_utterance(llm_cfg, 0, 160000, T=40, R=64)
+    cfg, enc, llm = build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, cuda)
+    step = AudioPromptStep(enc, llm, tok, llm_cfg.llm_type)
+    out = step.forward_losses(audio[None].to(cuda), [text_ids], [resp_ids], keep=True)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = rm.train_step_losses(enc_sd, {k: v.float() for k, v in llm_sd.items()}, enc_cfg, llm_cfg, tok, audio,
+                                   text_ids, resp_ids, keep=True)
+    assert out["plan"].L_audio[0] == 200 and out["plan"].L_text[0] == 117
+    assert rel_l2(out["audio_embeds"].cpu(), ref["audio_embeds"]) < TOL_EMBED
+    assert rel_l2(out["student_logits"].float().cpu(), ref["student_logits"][0]) < TOL_LOGITS
+    assert rel_l2(out["teacher_logits"].float().cpu(), ref["teacher_logits"][0]) < TOL_LOGITS
+    assert abs(float(out["ld_loss"][0]) - float(ref["ld_loss"])) / abs(float(ref["ld_loss"])) < TOL_KD
+    assert abs(float(out["ntp_loss"][0]) - float(ref["ntp_loss"])) / abs(float(ref["ntp_loss"])) < 5e-3
