@@ -68,6 +68,10 @@ typedef struct {
   int32_t cta_group; /* 0 = auto, else 1/2 */
 } b2s_gemm_args;
 int b2s_gemm_bf16(const b2s_gemm_args* args, void* stream);
+/* measurement hook (bench.py roofline leg): while enabled, every GEMM launch is bracketed by CUDA events on its
+ * stream; read() synchronises them and returns the summed device time (host pointers) and the launch count. */
+void b2s_gemm_timing_enable(int32_t on);
+int b2s_gemm_timing_read(double* total_ms, long long* launches);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused CE + logit-KD loss over packed response rows.  Replaces utils.soft_cross_entropy

@@ -104,6 +104,9 @@ int b2s_gemm_bf16(const b2s_gemm_args* a, void* stream) {
   return gemm_bf16_launch(g, S(stream));
 }
 
+void b2s_gemm_timing_enable(int32_t on) { gemm_timing_enable(on); }
+int b2s_gemm_timing_read(double* total_ms, long long* launches) { return gemm_timing_read(total_ms, launches); }
+
 size_t b2s_kd_ce_workspace_bytes(int32_t rows, int32_t V) { return kd_ce_workspace_bytes(rows, V); }
 
 int b2s_kd_ce_loss_fwd(const void* student, const void* teacher, int64_t lds, int64_t ldt, int32_t rows, int32_t V,

@@ -22,6 +22,8 @@
 #include <cudaTypedefs.h>
 
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "b2s_common.cuh"
 #include "b2s_ptx.cuh"
@@ -29,6 +31,9 @@
 namespace b2s {
 
 namespace {
+
+bool g_timing = false;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
 
 constexpr int kBlockK = 64;           // bf16 elements = 128 bytes = one swizzle atom
 constexpr int kUmmaK = 16;
@@ -441,11 +446,45 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const KParams& p, c
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   count_launch();
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (g_timing) {
+    B2S_CUDA_CHECK(cudaEventCreate(&ev0));
+    B2S_CUDA_CHECK(cudaEventCreate(&ev1));
+    B2S_CUDA_CHECK(cudaEventRecord(ev0, stream));
+  }
   B2S_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, p));
+  if (g_timing) {
+    B2S_CUDA_CHECK(cudaEventRecord(ev1, stream));
+    g_events.emplace_back(ev0, ev1);
+  }
   return B2S_OK;
 }
 
 }  // namespace
+
+// Optional per-launch timing of this kernel (bench.py's roofline leg): CUDA events on the launching stream
+// around every GEMM launch while enabled.
+void gemm_timing_enable(int on) {
+  for (auto& e : g_events) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  g_events.clear();
+  g_timing = on != 0;
+}
+
+int gemm_timing_read(double* total_ms, long long* launches) {
+  double ms = 0.0;
+  for (auto& e : g_events) {
+    B2S_CUDA_CHECK(cudaEventSynchronize(e.second));
+    float t = 0.f;
+    B2S_CUDA_CHECK(cudaEventElapsedTime(&t, e.first, e.second));
+    ms += t;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = static_cast<long long>(g_events.size());
+  return B2S_OK;
+}
 
 int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   B2S_REQUIRE(a.A && a.W && a.out, "gemm: null pointer");
@@ -469,10 +508,12 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   int cg = a.cta_group;
   if (bn == 0) {
     if (a.N <= 64) bn = 64;
-    else if (a.N % 256 != 0 && a.N % 128 == 0 && a.N < 1024) bn = 128;
+    else if (a.N <= 128) bn = 128;
     else bn = 256;
   }
-  if (cg == 0) cg = 1;
+  // measured on B200 (profiles/r01_trip1_kernel_microbench.jsonl): 256x256 tiles on a CTA pair win on every
+  // shape of the path (halved W smem traffic per SM); small-N grouped tiles stay single-CTA.
+  if (cg == 0) cg = (bn == 256 && a.M > 128) ? 2 : 1;
   B2S_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: block_n must be 64/128/256");
   B2S_REQUIRE(cg == 1 || cg == 2, "gemm: cta_group must be 1 or 2");
   if (a.epi == EPI_ROPE || a.epi == EPI_SWIGLU) B2S_REQUIRE(bn >= 128, "gemm: paired epilogues need block_n >= 128");

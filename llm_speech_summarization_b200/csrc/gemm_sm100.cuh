@@ -58,5 +58,7 @@ struct GemmArgs {
 };
 
 int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream);
+void gemm_timing_enable(int on);
+int gemm_timing_read(double* total_ms, long long* launches);
 
 }  // namespace b2s

@@ -118,8 +118,12 @@ def make_encoder_state_dict(cfg: EncoderCfg, seed: int = 1234) -> Dict[str, torc
     return sd
 
 
-def make_llm_state_dict(cfg: LlmCfg, seed: int = 4321, dtype: torch.dtype = torch.float32) -> Dict[str, torch.Tensor]:
-    """Synthetic LlamaForCausalLM weights, N(0, 0.02) like HF's default init; RMSNorm weights perturbed."""
+def make_llm_state_dict(cfg: LlmCfg, seed: int = 4321, dtype: torch.dtype = torch.float32,
+                        resid_scale: float = 1.0) -> Dict[str, torch.Tensor]:
+    """Synthetic LlamaForCausalLM weights, N(0, 0.02) like HF's default init; RMSNorm weights perturbed.
+    resid_scale multiplies the std of the residual-output projections (o_proj, down_proj): 1.0 = HF default init;
+    1/sqrt(2*layers) = the GPT-2 / Megatron depth-scaled init, which keeps the residual stream well conditioned
+    (HF-default init at hidden 3072 has per-branch gain > 1 and amplifies ANY rounding difference chaotically)."""
     g = torch.Generator().manual_seed(seed)
     H, D = cfg.hidden, cfg.head_dim
     sd: Dict[str, torch.Tensor] = {}
@@ -130,11 +134,11 @@ def make_llm_state_dict(cfg: LlmCfg, seed: int = 4321, dtype: torch.dtype = torc
         sd[p + "self_attn.q_proj.weight"] = _randn(g, cfg.heads * D, H, std=0.02).to(dtype)
         sd[p + "self_attn.k_proj.weight"] = _randn(g, cfg.kv_heads * D, H, std=0.02).to(dtype)
         sd[p + "self_attn.v_proj.weight"] = _randn(g, cfg.kv_heads * D, H, std=0.02).to(dtype)
-        sd[p + "self_attn.o_proj.weight"] = _randn(g, H, cfg.heads * D, std=0.02).to(dtype)
+        sd[p + "self_attn.o_proj.weight"] = _randn(g, H, cfg.heads * D, std=0.02 * resid_scale).to(dtype)
         sd[p + "post_attention_layernorm.weight"] = _randn(g, H, std=0.1, mean=1.0).to(dtype)
         sd[p + "mlp.gate_proj.weight"] = _randn(g, cfg.ffn, H, std=0.02).to(dtype)
         sd[p + "mlp.up_proj.weight"] = _randn(g, cfg.ffn, H, std=0.02).to(dtype)
-        sd[p + "mlp.down_proj.weight"] = _randn(g, H, cfg.ffn, std=0.02).to(dtype)
+        sd[p + "mlp.down_proj.weight"] = _randn(g, H, cfg.ffn, std=0.02 * resid_scale).to(dtype)
     sd["model.norm.weight"] = _randn(g, H, std=0.1, mean=1.0).to(dtype)
     if cfg.tie_embeddings:
         sd["lm_head.weight"] = sd["model.embed_tokens.weight"]
