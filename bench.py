@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts", type=int, default=3, help="utterances timed for the CPU baseline sample")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="only warm-up + timed steps (no e2e / roofline / CPU legs): for runs under ncu")
     return ap.parse_args()
 
 
@@ -308,6 +310,10 @@ def main():
     value = total_utts / (ms / 1e3)
     loss_check = float(out["total_loss"].mean())
 
+    if args.profile_mode:
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)}))
+        return
     # ---- e2e: host buffers -> H2D -> step -> D2H, through the public call
     for i in range(min(2, args.warmup)):
         step(host[i % n_pool][0], host[i % n_pool][1], host[i % n_pool][2], dev)

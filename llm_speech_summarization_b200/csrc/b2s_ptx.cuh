@@ -99,6 +99,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------- TMA
+// 1-D bulk async copy global -> shared (bytes multiple of 16, both addresses 16-byte aligned), completion on mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tmap(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
 }

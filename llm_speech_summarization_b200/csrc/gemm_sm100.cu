@@ -48,8 +48,11 @@ struct Cfg {
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;  // power of two for BN in {64,128,256}
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
+  static constexpr int kBarBytes = 256;                  // (2*kStages + 4) mbarriers + the TMEM base slot
+  static constexpr int kStagingBytes = 4 * 4096;         // one 32x128 B transpose tile per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kStagingBytes + 1024;  // +1024 align slack
+  static_assert((2 * kStages + 4) * 8 + 16 <= kBarBytes, "barrier region too small");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
 struct KParams {
@@ -110,19 +113,72 @@ __device__ __forceinline__ void add_bias_act(float (&v)[32], const float* bias, 
   }
 }
 
-// store 32 consecutive fp32 values of one row as bf16 (ncols_valid multiple of 8)
-__device__ __forceinline__ void store_bf16_32(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
+// ---- staged (transposing) stores ---------------------------------------------------------------
+// Staging tile: 32 rows x 128 B (32 fp32), 16-byte chunk q of row r stored at chunk position q ^ (r & 7):
+// the per-thread row writes and the per-row coalesced reads are both bank-conflict free.
+__device__ __forceinline__ void stage_write(uint32_t stg, const float (&v)[32], int lane) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    if (q * 8 < ncols_valid) {
-      uint4 u;
-      u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]);
-      u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
-      u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]);
-      u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
-      *reinterpret_cast<uint4*>(dst + 8 * q) = u;
+  for (int q = 0; q < 8; ++q) {
+    const uint32_t addr = stg + lane * 128 + ((q ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                 "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+                 : "memory");
+  }
+}
+__device__ __forceinline__ float4 stage_read(uint32_t stg, int row, int chunk) {
+  float4 x;
+  const uint32_t addr = stg + row * 128 + ((chunk ^ (row & 7)) << 4);
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
+  return x;
+}
+
+// v = this thread's row (lane) x 32 columns. out0 / resid0 point at element [warp's first row][first column].
+__device__ __forceinline__ void emit_f32(uint32_t stg, const float (&v)[32], int lane, float* out0,
+                                         const float* resid0, long long ld, int rows_valid, int cols_valid) {
+  stage_write(stg, v, lane);
+  __syncwarp();
+  const int chunk = lane & 7;
+  float4 x[8], r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    x[i] = stage_read(stg, row, chunk);
+    r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (resid0 != nullptr && row < rows_valid && chunk * 4 < cols_valid) {
+      r[i] = *reinterpret_cast<const float4*>(resid0 + row * ld + chunk * 4);
     }
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    if (row < rows_valid && chunk * 4 < cols_valid) {
+      *reinterpret_cast<float4*>(out0 + row * ld + chunk * 4) =
+          make_float4(x[i].x + r[i].x, x[i].y + r[i].y, x[i].z + r[i].z, x[i].w + r[i].w);
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void emit_bf16(uint32_t stg, const float (&v)[32], int lane, __nv_bfloat16* out0,
+                                          long long ld, int rows_valid, int cols_valid) {
+  stage_write(stg, v, lane);
+  __syncwarp();
+  const int j = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + (lane >> 2);
+    const float4 a = stage_read(stg, row, 2 * j);
+    const float4 b = stage_read(stg, row, 2 * j + 1);
+    if (row < rows_valid && j * 8 < cols_valid) {
+      uint4 u;
+      u.x = pack_bf16(a.x, a.y);
+      u.y = pack_bf16(a.z, a.w);
+      u.z = pack_bf16(b.x, b.y);
+      u.w = pack_bf16(b.z, b.w);
+      *reinterpret_cast<uint4*>(out0 + row * ld + j * 8) = u;
+    }
+  }
+  __syncwarp();
 }
 
 template <int BN, int CG>
@@ -141,6 +197,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t stage_base = bar_base + C::kBarBytes;  // epilogue transpose tiles (16-byte aligned)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -245,16 +302,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp >= 4) {
     // ============================== epilogue ==============================
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the only ones this warp may read
+    // Each warp owns TMEM lanes [32*quarter, +32) = 32 output rows. A thread reads ONE row x 32 columns from TMEM;
+    // writing that straight to global memory would touch 32 different cache lines per instruction, so every
+    // 32x32 chunk is transposed through a private, XOR-swizzled 4 KiB shared-memory tile and leaves the SM as
+    // fully coalesced 128-byte row segments (and the fp32 residual is read the same way).
+    const int quarter = warp & 3;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t stg = stage_base + static_cast<uint32_t>(quarter) * 4096u;
     int it = 0;
     for (int t = cluster_id; t < p.total_tiles; t += num_clusters, ++it) {
       const TileCoord tc = decode_tile(p, t);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m = tc.m_t * (128 * CG) + static_cast<int>(cta_rank) * 128 + quarter * 32 + lane;
-      const bool row_ok = m < p.M;
-      const long long orow = static_cast<long long>(tc.b) * p.out_batch_rows + m;
+      const int m0w = tc.m_t * (128 * CG) + static_cast<int>(cta_rank) * 128 + quarter * 32;  // warp's first row
+      const int rows_valid = max(0, min(32, p.M - m0w));
+      const bool row_ok = lane < rows_valid;
+      const long long orow0 = static_cast<long long>(tc.b) * p.out_batch_rows + m0w;
       const int ncol0 = tc.n_t * BN;  // column inside the group
       const float* bias = p.bias ? p.bias + static_cast<long long>(tc.g) * p.N : nullptr;
 
@@ -275,35 +338,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
           add_bias_act(v, bias ? bias + col : nullptr, p.act);
           const int valid = min(32, p.N - col);
-          if (row_ok) {
-            const long long off = orow * p.ldo + static_cast<long long>(tc.g) * p.N + col;
-            if (p.epi == EPI_BF16) {
-              store_bf16_32(reinterpret_cast<__nv_bfloat16*>(p.out) + off, v, valid);
-            } else {
-              float* o = reinterpret_cast<float*>(p.out) + off;
-              const float* r = p.epi == EPI_RESID_F32 ? p.resid + off : nullptr;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                if (q * 4 < valid) {
-                  float4 x = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                  if (r != nullptr) {
-                    const float4 rr = *reinterpret_cast<const float4*>(r + 4 * q);
-                    x.x += rr.x;
-                    x.y += rr.y;
-                    x.z += rr.z;
-                    x.w += rr.w;
-                  }
-                  *reinterpret_cast<float4*>(o + 4 * q) = x;
-                }
-              }
-            }
+          const long long off0 = orow0 * p.ldo + static_cast<long long>(tc.g) * p.N + col;
+          if (p.epi == EPI_BF16) {
+            emit_bf16(stg, v, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, valid);
+          } else {
+            emit_f32(stg, v, lane, reinterpret_cast<float*>(p.out) + off0,
+                     p.epi == EPI_RESID_F32 ? p.resid + off0 : nullptr, p.ldo, rows_valid, valid);
           }
         }
       } else {
         // paired-chunk epilogues over 128-column blocks: chunk c pairs with chunk c+2
         // (SwiGLU: 64 gate | 64 up ; RoPE: head_dim 128 = first half | second half)
         int pos = 0;
-        if (p.epi == EPI_ROPE && row_ok) pos = __ldg(p.positions + orow);
+        if (p.epi == EPI_ROPE && row_ok) pos = __ldg(p.positions + orow0 + lane);
 #pragma unroll 1
         for (int blk = 0; blk < BN / 128; ++blk) {
           const int bcol = ncol0 + blk * 128;
@@ -325,11 +372,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             if (p.epi == EPI_SWIGLU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) lo[i] = silu(lo[i]) * hi[i];
-              if (row_ok) {
-                const long long off =
-                    orow * p.ldo + (static_cast<long long>(tc.g) * p.N + bcol) / 2 + c * 32;
-                store_bf16_32(reinterpret_cast<__nv_bfloat16*>(p.out) + off, lo, 32);
-              }
+              const long long off0 = orow0 * p.ldo + (static_cast<long long>(tc.g) * p.N + bcol) / 2 + c * 32;
+              emit_bf16(stg, lo, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, 32);
             } else {  // EPI_ROPE
               if (bcol < p.rope_cols && row_ok) {
                 const float* cs = p.rope_cs + static_cast<long long>(pos) * 128 + c * 32;
@@ -347,11 +391,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                   }
                 }
               }
-              if (row_ok) {
-                const long long off = orow * p.ldo + static_cast<long long>(tc.g) * p.N + bcol + c * 32;
-                store_bf16_32(reinterpret_cast<__nv_bfloat16*>(p.out) + off, lo, 32);
-                store_bf16_32(reinterpret_cast<__nv_bfloat16*>(p.out) + off + 64, hi, 32);
-              }
+              const long long off0 = orow0 * p.ldo + static_cast<long long>(tc.g) * p.N + bcol + c * 32;
+              emit_bf16(stg, lo, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, 32);
+              emit_bf16(stg, hi, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0 + 64, p.ldo, rows_valid, 32);
             }
           }
         }

@@ -9,6 +9,7 @@
 // B_t = sum e^{t-m_t} s, so sum softmax(t) s = B_t / Z_t; probabilities are never materialised.
 // Backward writes only ds (6*N*V bytes total): ds = ck (softmax(s) - softmax(t)) + cc (softmax(s) - onehot).
 #include "b2s_common.cuh"
+#include "b2s_ptx.cuh"
 #include "ops.cuh"
 
 namespace b2s {
@@ -17,7 +18,17 @@ namespace {
 
 constexpr int kLossThreads = 256;
 constexpr int kChunkCols = 16384;  // vocabulary columns per CTA (32 KiB of each tensor)
+constexpr int kSub = 4;            // sub-blocks (one mbarrier each) per CTA slice
+constexpr int kSubCols = kChunkCols / kSub;
+constexpr int kSubBytes = kSubCols * 2;
+constexpr int kFwdSmemBytes = kSub * 2 * kSubBytes + kSub * 8 + 32;
 constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2(float x) {  // single MUFU.EX2; ex2(-inf) = +0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct Partial {
   float m_s, z_s, m_t, z_t, b_t, pad;
@@ -56,51 +67,63 @@ kd_ce_partial_kernel(const __nv_bfloat16* __restrict__ S, const __nv_bfloat16* _
 
   float m_s = -INFINITY, z_s = 0.f, m_t = -INFINITY, z_t = 0.f, b_t = 0.f;
 
-  constexpr int kUnroll = 4;
-  const int nvec = (c1 - c0) >> 3;  // V % 8 == 0 is required by the launcher
-  const uint4* sv = reinterpret_cast<const uint4*>(s + c0);
-  const uint4* tv = reinterpret_cast<const uint4*>(t + c0);
-  for (int base = threadIdx.x; base < nvec; base += kLossThreads * kUnroll) {
-    uint4 su[kUnroll], tu[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int i = base + u * kLossThreads;
-      if (i < nvec) {
-        su[u] = ld_stream_u4(sv + i);
-        tu[u] = ld_stream_u4(tv + i);
-      }
+  // Stage the CTA's 2 x 32 KiB slice through shared memory with bulk async copies (one elected thread, one
+  // mbarrier per 8 KiB sub-block): all 64 KiB are in flight at once, independent of register-level MLP, and the
+  // math on sub-block i overlaps the arrival of sub-blocks i+1.. (and of the other resident CTAs' slices).
+  extern __shared__ __align__(128) uint8_t loss_smem[];
+  const uint32_t smem0 = ptx::smem_u32(loss_smem);
+  const uint32_t bar0 = smem0 + kSub * 2 * kSubBytes;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSub; ++i) ptx::mbar_init(bar0 + 8 * i, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSub; ++i) {
+      const int cols = min(kSubCols, c1 - (c0 + i * kSubCols));
+      if (cols <= 0) break;
+      const uint32_t bytes = static_cast<uint32_t>(cols) * 2u;
+      ptx::mbar_arrive_expect_tx(bar0 + 8 * i, 2 * bytes);
+      ptx::bulk_g2s(smem0 + (2 * i) * kSubBytes, s + c0 + i * kSubCols, bytes, bar0 + 8 * i);
+      ptx::bulk_g2s(smem0 + (2 * i + 1) * kSubBytes, t + c0 + i * kSubCols, bytes, bar0 + 8 * i);
     }
+  }
+  for (int i = 0; i < kSub; ++i) {
+    const int cols = min(kSubCols, c1 - (c0 + i * kSubCols));
+    if (cols <= 0) break;
+    ptx::mbar_wait(bar0 + 8 * i, 0);
+    const int nvec = cols >> 3;  // V % 8 == 0 is required by the launcher
+    const uint4* sv = reinterpret_cast<const uint4*>(loss_smem + (2 * i) * kSubBytes);
+    const uint4* tv = reinterpret_cast<const uint4*>(loss_smem + (2 * i + 1) * kSubBytes);
+#pragma unroll 2
+    for (int v = threadIdx.x; v < nvec; v += kLossThreads) {
+      const uint4 su = sv[v], tu = tv[v];
+      float fs[8], ft[8];
+      unpack8(su, fs);
+      unpack8(tu, ft);
+      float vs = fs[0], vt = ft[0];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int i = base + u * kLossThreads;
-      if (i < nvec) {
-        float fs[8], ft[8];
-        unpack8(su[u], fs);
-        unpack8(tu[u], ft);
-        float vs = fs[0], vt = ft[0];
+      for (int j = 1; j < 8; ++j) {
+        vs = fmaxf(vs, fs[j]);
+        vt = fmaxf(vt, ft[j]);
+      }
+      if (vs > m_s) {
+        z_s *= ex2((m_s - vs) * kLog2e);
+        m_s = vs;
+      }
+      if (vt > m_t) {
+        const float f = ex2((m_t - vt) * kLog2e);
+        z_t *= f;
+        b_t *= f;
+        m_t = vt;
+      }
+      const float ms2 = m_s * kLog2e, mt2 = m_t * kLog2e;
 #pragma unroll
-        for (int j = 1; j < 8; ++j) {
-          vs = fmaxf(vs, fs[j]);
-          vt = fmaxf(vt, ft[j]);
-        }
-        if (vs > m_s) {
-          z_s *= exp2f((m_s - vs) * kLog2e);
-          m_s = vs;
-        }
-        if (vt > m_t) {
-          const float f = exp2f((m_t - vt) * kLog2e);
-          z_t *= f;
-          b_t *= f;
-          m_t = vt;
-        }
-        const float ms2 = m_s * kLog2e, mt2 = m_t * kLog2e;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          z_s += exp2f(fmaf(fs[j], kLog2e, -ms2));
-          const float e = exp2f(fmaf(ft[j], kLog2e, -mt2));
-          z_t += e;
-          b_t = fmaf(e, fs[j], b_t);
-        }
+      for (int j = 0; j < 8; ++j) {
+        z_s += ex2(fmaf(fs[j], kLog2e, -ms2));
+        const float e = ex2(fmaf(ft[j], kLog2e, -mt2));
+        z_t += e;
+        b_t = fmaf(e, fs[j], b_t);
       }
     }
   }
@@ -228,8 +251,8 @@ kd_ce_bwd_kernel(const __nv_bfloat16* __restrict__ S, const __nv_bfloat16* __res
         const int col = c0 + i * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float ps = exp2f(fmaf(fs[j], kLog2e, -ls2));
-          const float pt = exp2f(fmaf(ft[j], kLog2e, -lt2));
+          const float ps = ex2(fmaf(fs[j], kLog2e, -ls2));
+          const float pt = ex2(fmaf(ft[j], kLog2e, -lt2));
           g[j] = cs * ps - ck * pt;
           if (col + j == lab) g[j] -= cc;
         }
@@ -266,7 +289,13 @@ int kd_ce_loss_fwd(const void* S, const void* T, long long lds, long long ldt, i
   B2S_REQUIRE(V > 0 && V % 8 == 0 && lds % 8 == 0 && ldt % 8 == 0, "kd_ce_loss_fwd: V/ld must be multiples of 8");
   const int chunks = (V + kChunkCols - 1) / kChunkCols;
   dim3 grid(chunks, rows);
-  kd_ce_partial_kernel<<<grid, kLossThreads, 0, stream>>>(
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2S_CUDA_CHECK(cudaFuncSetAttribute(kd_ce_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kFwdSmemBytes));
+    attr_set = true;
+  }
+  kd_ce_partial_kernel<<<grid, kLossThreads, kFwdSmemBytes, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(S), reinterpret_cast<const __nv_bfloat16*>(T), lds, ldt, V,
       reinterpret_cast<Partial*>(workspace), chunks);
   B2S_LAUNCH_CHECK();
