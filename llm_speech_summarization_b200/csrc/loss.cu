@@ -8,6 +8,11 @@
 // one pass: per row an online softmax over s and t simultaneously keeps (m_s, Z_s, m_t, Z_t, B_t) with
 // B_t = sum e^{t-m_t} s, so sum softmax(t) s = B_t / Z_t; probabilities are never materialised.
 // Backward writes only ds (6*N*V bytes total): ds = ck (softmax(s) - softmax(t)) + cc (softmax(s) - onehot).
+//
+// Forward kernel design (HBM-bound, but 2 MUFU.EX2 per logit pair keeps the SFU pipe >60 % busy at full
+// bandwidth, so memory latency must be hidden completely): persistent CTAs, one producer warp feeding a
+// 6-stage shared-memory ring with 1-D bulk async copies (cp.async.bulk, 8 KiB of s + 8 KiB of t per stage,
+// mbarrier full/empty pairs), eight consumer warps doing the online-softmax math from shared memory.
 #include "b2s_common.cuh"
 #include "b2s_ptx.cuh"
 #include "ops.cuh"
@@ -16,12 +21,14 @@ namespace b2s {
 
 namespace {
 
-constexpr int kLossThreads = 256;
-constexpr int kChunkCols = 16384;  // vocabulary columns per CTA (32 KiB of each tensor)
-constexpr int kSub = 4;            // sub-blocks (one mbarrier each) per CTA slice
+constexpr int kLossThreads = 256;  // consumer threads (forward) / all threads (backward)
+constexpr int kChunkCols = 16384;  // vocabulary columns per work item (32 KiB of each tensor)
+constexpr int kSub = 4;            // sub-blocks (ring stages consumed) per work item
 constexpr int kSubCols = kChunkCols / kSub;
 constexpr int kSubBytes = kSubCols * 2;
-constexpr int kFwdSmemBytes = kSub * 2 * kSubBytes + kSub * 8 + 32;
+constexpr int kRing = 6;           // ring stages, each = one sub-block of s and of t
+constexpr int kFwdThreads = kLossThreads + 32;
+constexpr int kFwdSmemBytes = kRing * 2 * kSubBytes + 2 * kRing * 8 + 64;
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2(float x) {  // single MUFU.EX2; ex2(-inf) = +0
@@ -54,103 +61,143 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
 }
 
-// grid = (chunks, rows); each CTA streams kChunkCols columns of one (student,teacher) row pair.
-__global__ void __launch_bounds__(kLossThreads)
+// Work item = (row, chunk of kChunkCols columns); items are dealt round-robin to the persistent CTAs.
+__global__ void __launch_bounds__(kFwdThreads)
 kd_ce_partial_kernel(const __nv_bfloat16* __restrict__ S, const __nv_bfloat16* __restrict__ T, long long lds,
-                     long long ldt, int V, Partial* __restrict__ part, int chunks) {
-  const int row = blockIdx.y;
-  const int chunk = blockIdx.x;
-  const int c0 = chunk * kChunkCols;
-  const int c1 = min(V, c0 + kChunkCols);
-  const __nv_bfloat16* s = S + static_cast<long long>(row) * lds;
-  const __nv_bfloat16* t = T + static_cast<long long>(row) * ldt;
-
-  float m_s = -INFINITY, z_s = 0.f, m_t = -INFINITY, z_t = 0.f, b_t = 0.f;
-
-  // Stage the CTA's 2 x 32 KiB slice through shared memory with bulk async copies (one elected thread, one
-  // mbarrier per 8 KiB sub-block): all 64 KiB are in flight at once, independent of register-level MLP, and the
-  // math on sub-block i overlaps the arrival of sub-blocks i+1.. (and of the other resident CTAs' slices).
+                     long long ldt, int V, Partial* __restrict__ part, int chunks, int items) {
   extern __shared__ __align__(128) uint8_t loss_smem[];
   const uint32_t smem0 = ptx::smem_u32(loss_smem);
-  const uint32_t bar0 = smem0 + kSub * 2 * kSubBytes;
+  const uint32_t bar0 = smem0 + kRing * 2 * kSubBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kRing + s); };
+  __shared__ float sh[2][kLossThreads / 32][5];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kSub; ++i) ptx::mbar_init(bar0 + 8 * i, 1);
+    for (int s = 0; s < kRing; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), kLossThreads / 32);
+    }
     ptx::fence_mbar_init();
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kSub; ++i) {
-      const int cols = min(kSubCols, c1 - (c0 + i * kSubCols));
-      if (cols <= 0) break;
-      const uint32_t bytes = static_cast<uint32_t>(cols) * 2u;
-      ptx::mbar_arrive_expect_tx(bar0 + 8 * i, 2 * bytes);
-      ptx::bulk_g2s(smem0 + (2 * i) * kSubBytes, s + c0 + i * kSubCols, bytes, bar0 + 8 * i);
-      ptx::bulk_g2s(smem0 + (2 * i + 1) * kSubBytes, t + c0 + i * kSubCols, bytes, bar0 + 8 * i);
-    }
-  }
-  for (int i = 0; i < kSub; ++i) {
-    const int cols = min(kSubCols, c1 - (c0 + i * kSubCols));
-    if (cols <= 0) break;
-    ptx::mbar_wait(bar0 + 8 * i, 0);
-    const int nvec = cols >> 3;  // V % 8 == 0 is required by the launcher
-    const uint4* sv = reinterpret_cast<const uint4*>(loss_smem + (2 * i) * kSubBytes);
-    const uint4* tv = reinterpret_cast<const uint4*>(loss_smem + (2 * i + 1) * kSubBytes);
-#pragma unroll 2
-    for (int v = threadIdx.x; v < nvec; v += kLossThreads) {
-      const uint4 su = sv[v], tu = tv[v];
-      float fs[8], ft[8];
-      unpack8(su, fs);
-      unpack8(tu, ft);
-      float vs = fs[0], vt = ft[0];
-#pragma unroll
-      for (int j = 1; j < 8; ++j) {
-        vs = fmaxf(vs, fs[j]);
-        vt = fmaxf(vt, ft[j]);
-      }
-      if (vs > m_s) {
-        z_s *= ex2((m_s - vs) * kLog2e);
-        m_s = vs;
-      }
-      if (vt > m_t) {
-        const float f = ex2((m_t - vt) * kLog2e);
-        z_t *= f;
-        b_t *= f;
-        m_t = vt;
-      }
-      const float ms2 = m_s * kLog2e, mt2 = m_t * kLog2e;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        z_s += ex2(fmaf(fs[j], kLog2e, -ms2));
-        const float e = ex2(fmaf(ft[j], kLog2e, -mt2));
-        z_t += e;
-        b_t = fmaf(e, fs[j], b_t);
+
+  if (warp == kLossThreads / 32) {
+    // ================= producer warp (one elected lane) =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int row = item / chunks, chunk = item - row * chunks;
+        const int c0 = chunk * kChunkCols;
+        const int c1 = min(V, c0 + kChunkCols);
+        const __nv_bfloat16* s = S + static_cast<long long>(row) * lds + c0;
+        const __nv_bfloat16* t = T + static_cast<long long>(row) * ldt + c0;
+        for (int i = 0; i < kSub; ++i) {
+          const int cols = min(kSubCols, c1 - c0 - i * kSubCols);
+          if (cols <= 0) break;
+          const uint32_t bytes = static_cast<uint32_t>(cols) * 2u;
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * bytes);
+          ptx::bulk_g2s(smem0 + (2 * stage) * kSubBytes, s + i * kSubCols, bytes, full_bar(stage));
+          ptx::bulk_g2s(smem0 + (2 * stage + 1) * kSubBytes, t + i * kSubCols, bytes, full_bar(stage));
+          if (++stage == kRing) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
       }
     }
+    return;
   }
 
-  // warp then block merge
+  // ================= consumer warps =================
+  int stage = 0;
+  uint32_t phase = 0;
+  int parity = 0;
+  for (int item = blockIdx.x; item < items; item += gridDim.x, parity ^= 1) {
+    const int row = item / chunks, chunk = item - row * chunks;
+    const int c0 = chunk * kChunkCols;
+    const int c1 = min(V, c0 + kChunkCols);
+    float m_s = -INFINITY, z_s = 0.f, m_t = -INFINITY, z_t = 0.f, b_t = 0.f;
+    for (int i = 0; i < kSub; ++i) {
+      const int cols = min(kSubCols, c1 - c0 - i * kSubCols);
+      if (cols <= 0) break;
+      ptx::mbar_wait(full_bar(stage), phase);
+      const int nvec = cols >> 3;  // V % 8 == 0 is required by the launcher
+      const uint4* sv = reinterpret_cast<const uint4*>(loss_smem + (2 * stage) * kSubBytes);
+      const uint4* tv = reinterpret_cast<const uint4*>(loss_smem + (2 * stage + 1) * kSubBytes);
+#pragma unroll 2
+      for (int v = threadIdx.x; v < nvec; v += kLossThreads) {
+        const uint4 su = sv[v], tu = tv[v];
+        float fs[8], ft[8];
+        unpack8(su, fs);
+        unpack8(tu, ft);
+        float vs = fs[0], vt = ft[0];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float m2 = __shfl_xor_sync(0xffffffffu, m_s, o), z2 = __shfl_xor_sync(0xffffffffu, z_s, o);
-    const float n2 = __shfl_xor_sync(0xffffffffu, m_t, o), y2 = __shfl_xor_sync(0xffffffffu, z_t, o);
-    const float b2 = __shfl_xor_sync(0xffffffffu, b_t, o);
-    if (m2 > -INFINITY) merge_sz(m_s, z_s, m2, z2);
-    if (n2 > -INFINITY) merge_tzb(m_t, z_t, b_t, n2, y2, b2);
-  }
-  __shared__ float sh[kLossThreads / 32][5];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) {
-    sh[warp][0] = m_s; sh[warp][1] = z_s; sh[warp][2] = m_t; sh[warp][3] = z_t; sh[warp][4] = b_t;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < kLossThreads / 32; ++w) {
-      if (sh[w][0] > -INFINITY) merge_sz(m_s, z_s, sh[w][0], sh[w][1]);
-      if (sh[w][2] > -INFINITY) merge_tzb(m_t, z_t, b_t, sh[w][2], sh[w][3], sh[w][4]);
+        for (int j = 1; j < 8; ++j) {
+          vs = fmaxf(vs, fs[j]);
+          vt = fmaxf(vt, ft[j]);
+        }
+        if (vs > m_s) {
+          z_s *= ex2((m_s - vs) * kLog2e);
+          m_s = vs;
+        }
+        if (vt > m_t) {
+          const float f = ex2((m_t - vt) * kLog2e);
+          z_t *= f;
+          b_t *= f;
+          m_t = vt;
+        }
+        const float ms2 = m_s * kLog2e, mt2 = m_t * kLog2e;
+        float zs2 = 0.f, zt2 = 0.f, bt2 = 0.f;  // second accumulator set: halves the dependent-add chains
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          z_s += ex2(fmaf(fs[j], kLog2e, -ms2));
+          zs2 += ex2(fmaf(fs[j + 1], kLog2e, -ms2));
+          const float e0 = ex2(fmaf(ft[j], kLog2e, -mt2));
+          const float e1 = ex2(fmaf(ft[j + 1], kLog2e, -mt2));
+          z_t += e0;
+          zt2 += e1;
+          b_t = fmaf(e0, fs[j], b_t);
+          bt2 = fmaf(e1, fs[j + 1], bt2);
+        }
+        z_s += zs2;
+        z_t += zt2;
+        b_t += bt2;
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(empty_bar(stage));  // this warp is done reading the stage
+      if (++stage == kRing) {
+        stage = 0;
+        phase ^= 1u;
+      }
     }
-    Partial pr;
-    pr.m_s = m_s; pr.z_s = z_s; pr.m_t = m_t; pr.z_t = z_t; pr.b_t = b_t; pr.pad = 0.f;
-    part[static_cast<long long>(row) * chunks + chunk] = pr;
+
+    // warp then CTA merge of the running statistics (consumer threads only: named barrier 1)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m_s, o), z2 = __shfl_xor_sync(0xffffffffu, z_s, o);
+      const float n2 = __shfl_xor_sync(0xffffffffu, m_t, o), y2 = __shfl_xor_sync(0xffffffffu, z_t, o);
+      const float b2 = __shfl_xor_sync(0xffffffffu, b_t, o);
+      if (m2 > -INFINITY) merge_sz(m_s, z_s, m2, z2);
+      if (n2 > -INFINITY) merge_tzb(m_t, z_t, b_t, n2, y2, b2);
+    }
+    if (lane == 0) {
+      sh[parity][warp][0] = m_s; sh[parity][warp][1] = z_s; sh[parity][warp][2] = m_t;
+      sh[parity][warp][3] = z_t; sh[parity][warp][4] = b_t;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kLossThreads) : "memory");
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kLossThreads / 32; ++w) {
+        if (sh[parity][w][0] > -INFINITY) merge_sz(m_s, z_s, sh[parity][w][0], sh[parity][w][1]);
+        if (sh[parity][w][2] > -INFINITY) merge_tzb(m_t, z_t, b_t, sh[parity][w][2], sh[parity][w][3], sh[parity][w][4]);
+      }
+      Partial pr;
+      pr.m_s = m_s; pr.z_s = z_s; pr.m_t = m_t; pr.z_t = z_t; pr.b_t = b_t; pr.pad = 0.f;
+      part[item] = pr;  // item == row * chunks + chunk
+    }
+    // sh[] is double-buffered by item parity: the barrier of the NEXT item orders its reuse two items later
   }
 }
 
@@ -287,17 +334,23 @@ int kd_ce_loss_fwd(const void* S, const void* T, long long lds, long long ldt, i
   B2S_REQUIRE(S && T && labels && row_offsets && workspace && lse_s && lse_t && coef_kd && coef_ce,
               "kd_ce_loss_fwd: null pointer");
   B2S_REQUIRE(V > 0 && V % 8 == 0 && lds % 8 == 0 && ldt % 8 == 0, "kd_ce_loss_fwd: V/ld must be multiples of 8");
+  B2S_REQUIRE((reinterpret_cast<uintptr_t>(S) & 15) == 0 && (reinterpret_cast<uintptr_t>(T) & 15) == 0,
+              "kd_ce_loss_fwd: logits must be 16-byte aligned");
   const int chunks = (V + kChunkCols - 1) / kChunkCols;
-  dim3 grid(chunks, rows);
+  const long long items_ll = static_cast<long long>(rows) * chunks;
+  B2S_REQUIRE(items_ll < (1LL << 31), "kd_ce_loss_fwd: too many work items");
+  const int items = static_cast<int>(items_ll);
   static bool attr_set = false;
   if (!attr_set) {
     B2S_CUDA_CHECK(cudaFuncSetAttribute(kd_ce_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kFwdSmemBytes));
     attr_set = true;
   }
-  kd_ce_partial_kernel<<<grid, kLossThreads, kFwdSmemBytes, stream>>>(
+  int grid = 2 * num_sms();  // two 96 KiB rings per SM
+  if (grid > items) grid = items;
+  kd_ce_partial_kernel<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(S), reinterpret_cast<const __nv_bfloat16*>(T), lds, ldt, V,
-      reinterpret_cast<Partial*>(workspace), chunks);
+      reinterpret_cast<Partial*>(workspace), chunks, items);
   B2S_LAUNCH_CHECK();
   kd_ce_finalize_kernel<<<utterances, 256, 0, stream>>>(reinterpret_cast<const Partial*>(workspace), chunks,
                                                         reinterpret_cast<const __nv_bfloat16*>(S), lds, labels,
