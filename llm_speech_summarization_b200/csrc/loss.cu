@@ -9,10 +9,11 @@
 // B_t = sum e^{t-m_t} s, so sum softmax(t) s = B_t / Z_t; probabilities are never materialised.
 // Backward writes only ds (6*N*V bytes total): ds = ck (softmax(s) - softmax(t)) + cc (softmax(s) - onehot).
 //
-// Forward kernel design (HBM-bound, but 2 MUFU.EX2 per logit pair keeps the SFU pipe >60 % busy at full
-// bandwidth, so memory latency must be hidden completely): persistent CTAs, one producer warp feeding a
-// 6-stage shared-memory ring with 1-D bulk async copies (cp.async.bulk, 8 KiB of s + 8 KiB of t per stage,
-// mbarrier full/empty pairs), eight consumer warps doing the online-softmax math from shared memory.
+// Forward kernel: HBM-bound on paper, but 2 MUFU.EX2 per logit pair (16 lanes/clk/SM) keep the SFU pipe >55 % busy
+// at full bandwidth, so memory latency must be hidden completely and nothing may serialise the warps. Three
+// layouts were measured on B200 (profiles/r01_loss_kernel.md): register staging, whole-slice bulk-copy staging in
+// shared memory, and a persistent producer/consumer ring; the shared-memory variants lost to plain registers
+// because their CTA-wide mbarrier phases make the MUFU demand bursty. Kept: registers + 2-deep software pipeline.
 #include "b2s_common.cuh"
 #include "b2s_ptx.cuh"
 #include "ops.cuh"
@@ -21,14 +22,10 @@ namespace b2s {
 
 namespace {
 
-constexpr int kLossThreads = 256;  // consumer threads (forward) / all threads (backward)
-constexpr int kChunkCols = 16384;  // vocabulary columns per work item (32 KiB of each tensor)
-constexpr int kSub = 4;            // sub-blocks (ring stages consumed) per work item
-constexpr int kSubCols = kChunkCols / kSub;
-constexpr int kSubBytes = kSubCols * 2;
-constexpr int kRing = 6;           // ring stages, each = one sub-block of s and of t
-constexpr int kFwdThreads = kLossThreads + 32;
-constexpr int kFwdSmemBytes = kRing * 2 * kSubBytes + 2 * kRing * 8 + 64;
+constexpr int kLossThreads = 256;
+constexpr int kChunkCols = 16384;     // backward: vocabulary columns per CTA
+constexpr int kMaxFwdChunkCols = 65536;  // forward: largest slice per CTA (shrunk when there are few rows)
+constexpr int kMinFwdChunkCols = 8192;
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2(float x) {  // single MUFU.EX2; ex2(-inf) = +0
@@ -61,78 +58,48 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
 }
 
-// Work item = (row, chunk of kChunkCols columns); items are dealt round-robin to the persistent CTAs.
-__global__ void __launch_bounds__(kFwdThreads)
+// grid = (chunks, rows); each CTA streams `chunk_cols` columns of one (student, teacher) row pair straight from
+// HBM into registers with a 2-deep software pipeline (the loads of iteration i+1 are in flight while iteration i
+// is being reduced), 16-byte L1-bypassing loads, 4 CTAs (32 warps) per SM; no block-wide barrier until the end.
+__global__ void __launch_bounds__(kLossThreads, 4)
 kd_ce_partial_kernel(const __nv_bfloat16* __restrict__ S, const __nv_bfloat16* __restrict__ T, long long lds,
-                     long long ldt, int V, Partial* __restrict__ part, int chunks, int items) {
-  extern __shared__ __align__(128) uint8_t loss_smem[];
-  const uint32_t smem0 = ptx::smem_u32(loss_smem);
-  const uint32_t bar0 = smem0 + kRing * 2 * kSubBytes;
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (kRing + s); };
-  __shared__ float sh[2][kLossThreads / 32][5];
+                     long long ldt, int V, Partial* __restrict__ part, int chunks, int chunk_cols) {
+  const int row = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int c0 = chunk * chunk_cols;
+  const int c1 = min(V, c0 + chunk_cols);
+  const int nvec = (c1 - c0) >> 3;  // V % 8 == 0 is required by the launcher
+  const uint4* sv = reinterpret_cast<const uint4*>(S + static_cast<long long>(row) * lds + c0);
+  const uint4* tv = reinterpret_cast<const uint4*>(T + static_cast<long long>(row) * ldt + c0);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kRing; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), kLossThreads / 32);
+  float m_s = -INFINITY, z_s = 0.f, m_t = -INFINITY, z_t = 0.f, b_t = 0.f;
+  float zs2 = 0.f, zt2 = 0.f, bt2 = 0.f;  // second accumulator set: halves the dependent-add chains
+
+  constexpr int kPer = 2;  // vector pairs per thread per pipeline stage
+  uint4 cs[kPer], ct[kPer], ns[kPer], nt[kPer];
+#pragma unroll
+  for (int u = 0; u < kPer; ++u) {
+    const int i = threadIdx.x + u * kLossThreads;
+    if (i < nvec) {
+      cs[u] = ld_stream_u4(sv + i);
+      ct[u] = ld_stream_u4(tv + i);
     }
-    ptx::fence_mbar_init();
   }
-  __syncthreads();
-
-  if (warp == kLossThreads / 32) {
-    // ================= producer warp (one elected lane) =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int row = item / chunks, chunk = item - row * chunks;
-        const int c0 = chunk * kChunkCols;
-        const int c1 = min(V, c0 + kChunkCols);
-        const __nv_bfloat16* s = S + static_cast<long long>(row) * lds + c0;
-        const __nv_bfloat16* t = T + static_cast<long long>(row) * ldt + c0;
-        for (int i = 0; i < kSub; ++i) {
-          const int cols = min(kSubCols, c1 - c0 - i * kSubCols);
-          if (cols <= 0) break;
-          const uint32_t bytes = static_cast<uint32_t>(cols) * 2u;
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * bytes);
-          ptx::bulk_g2s(smem0 + (2 * stage) * kSubBytes, s + i * kSubCols, bytes, full_bar(stage));
-          ptx::bulk_g2s(smem0 + (2 * stage + 1) * kSubBytes, t + i * kSubCols, bytes, full_bar(stage));
-          if (++stage == kRing) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
+  for (int v = threadIdx.x; v < nvec; v += kPer * kLossThreads) {
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {  // prefetch the next stage
+      const int i = v + (kPer + u) * kLossThreads;
+      if (i < nvec) {
+        ns[u] = ld_stream_u4(sv + i);
+        nt[u] = ld_stream_u4(tv + i);
       }
     }
-    return;
-  }
-
-  // ================= consumer warps =================
-  int stage = 0;
-  uint32_t phase = 0;
-  int parity = 0;
-  for (int item = blockIdx.x; item < items; item += gridDim.x, parity ^= 1) {
-    const int row = item / chunks, chunk = item - row * chunks;
-    const int c0 = chunk * kChunkCols;
-    const int c1 = min(V, c0 + kChunkCols);
-    float m_s = -INFINITY, z_s = 0.f, m_t = -INFINITY, z_t = 0.f, b_t = 0.f;
-    for (int i = 0; i < kSub; ++i) {
-      const int cols = min(kSubCols, c1 - c0 - i * kSubCols);
-      if (cols <= 0) break;
-      ptx::mbar_wait(full_bar(stage), phase);
-      const int nvec = cols >> 3;  // V % 8 == 0 is required by the launcher
-      const uint4* sv = reinterpret_cast<const uint4*>(loss_smem + (2 * stage) * kSubBytes);
-      const uint4* tv = reinterpret_cast<const uint4*>(loss_smem + (2 * stage + 1) * kSubBytes);
-#pragma unroll 2
-      for (int v = threadIdx.x; v < nvec; v += kLossThreads) {
-        const uint4 su = sv[v], tu = tv[v];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      if (v + u * kLossThreads < nvec) {
         float fs[8], ft[8];
-        unpack8(su, fs);
-        unpack8(tu, ft);
+        unpack8(cs[u], fs);
+        unpack8(ct[u], ft);
         float vs = fs[0], vt = ft[0];
 #pragma unroll
         for (int j = 1; j < 8; ++j) {
@@ -140,17 +107,20 @@ kd_ce_partial_kernel(const __nv_bfloat16* __restrict__ S, const __nv_bfloat16* _
           vt = fmaxf(vt, ft[j]);
         }
         if (vs > m_s) {
-          z_s *= ex2((m_s - vs) * kLog2e);
+          const float f = ex2((m_s - vs) * kLog2e);
+          z_s *= f;
+          zs2 *= f;
           m_s = vs;
         }
         if (vt > m_t) {
           const float f = ex2((m_t - vt) * kLog2e);
           z_t *= f;
+          zt2 *= f;
           b_t *= f;
+          bt2 *= f;
           m_t = vt;
         }
         const float ms2 = m_s * kLog2e, mt2 = m_t * kLog2e;
-        float zs2 = 0.f, zt2 = 0.f, bt2 = 0.f;  // second accumulator set: halves the dependent-add chains
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
           z_s += ex2(fmaf(fs[j], kLog2e, -ms2));
@@ -162,42 +132,41 @@ kd_ce_partial_kernel(const __nv_bfloat16* __restrict__ S, const __nv_bfloat16* _
           b_t = fmaf(e0, fs[j], b_t);
           bt2 = fmaf(e1, fs[j + 1], bt2);
         }
-        z_s += zs2;
-        z_t += zt2;
-        b_t += bt2;
-      }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(empty_bar(stage));  // this warp is done reading the stage
-      if (++stage == kRing) {
-        stage = 0;
-        phase ^= 1u;
       }
     }
-
-    // warp then CTA merge of the running statistics (consumer threads only: named barrier 1)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float m2 = __shfl_xor_sync(0xffffffffu, m_s, o), z2 = __shfl_xor_sync(0xffffffffu, z_s, o);
-      const float n2 = __shfl_xor_sync(0xffffffffu, m_t, o), y2 = __shfl_xor_sync(0xffffffffu, z_t, o);
-      const float b2 = __shfl_xor_sync(0xffffffffu, b_t, o);
-      if (m2 > -INFINITY) merge_sz(m_s, z_s, m2, z2);
-      if (n2 > -INFINITY) merge_tzb(m_t, z_t, b_t, n2, y2, b2);
+    for (int u = 0; u < kPer; ++u) {
+      cs[u] = ns[u];
+      ct[u] = nt[u];
     }
-    if (lane == 0) {
-      sh[parity][warp][0] = m_s; sh[parity][warp][1] = z_s; sh[parity][warp][2] = m_t;
-      sh[parity][warp][3] = z_t; sh[parity][warp][4] = b_t;
+  }
+  z_s += zs2;
+  z_t += zt2;
+  b_t += bt2;
+
+  // warp then block merge
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m_s, o), z2 = __shfl_xor_sync(0xffffffffu, z_s, o);
+    const float n2 = __shfl_xor_sync(0xffffffffu, m_t, o), y2 = __shfl_xor_sync(0xffffffffu, z_t, o);
+    const float b2 = __shfl_xor_sync(0xffffffffu, b_t, o);
+    if (m2 > -INFINITY) merge_sz(m_s, z_s, m2, z2);
+    if (n2 > -INFINITY) merge_tzb(m_t, z_t, b_t, n2, y2, b2);
+  }
+  __shared__ float sh[kLossThreads / 32][5];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sh[warp][0] = m_s; sh[warp][1] = z_s; sh[warp][2] = m_t; sh[warp][3] = z_t; sh[warp][4] = b_t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kLossThreads / 32; ++w) {
+      if (sh[w][0] > -INFINITY) merge_sz(m_s, z_s, sh[w][0], sh[w][1]);
+      if (sh[w][2] > -INFINITY) merge_tzb(m_t, z_t, b_t, sh[w][2], sh[w][3], sh[w][4]);
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kLossThreads) : "memory");
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < kLossThreads / 32; ++w) {
-        if (sh[parity][w][0] > -INFINITY) merge_sz(m_s, z_s, sh[parity][w][0], sh[parity][w][1]);
-        if (sh[parity][w][2] > -INFINITY) merge_tzb(m_t, z_t, b_t, sh[parity][w][2], sh[parity][w][3], sh[parity][w][4]);
-      }
-      Partial pr;
-      pr.m_s = m_s; pr.z_s = z_s; pr.m_t = m_t; pr.z_t = z_t; pr.b_t = b_t; pr.pad = 0.f;
-      part[item] = pr;  // item == row * chunks + chunk
-    }
-    // sh[] is double-buffered by item parity: the barrier of the NEXT item orders its reuse two items later
+    Partial pr;
+    pr.m_s = m_s; pr.z_s = z_s; pr.m_t = m_t; pr.z_t = z_t; pr.b_t = b_t; pr.pad = 0.f;
+    part[static_cast<long long>(row) * chunks + chunk] = pr;
   }
 }
 
@@ -316,8 +285,17 @@ kd_ce_bwd_kernel(const __nv_bfloat16* __restrict__ S, const __nv_bfloat16* __res
 
 }  // namespace
 
+namespace {
+int fwd_chunk_cols(int rows, int V) {
+  int cols = kMaxFwdChunkCols;
+  const long long want = 4LL * num_sms();
+  while (cols > kMinFwdChunkCols && static_cast<long long>(rows) * ((V + cols - 1) / cols) < want) cols /= 2;
+  return cols;
+}
+}  // namespace
+
 size_t kd_ce_workspace_bytes(int rows, int V) {
-  const int chunks = (V + kChunkCols - 1) / kChunkCols;
+  const int chunks = (V + kMinFwdChunkCols - 1) / kMinFwdChunkCols;  // upper bound over every slice size
   return static_cast<size_t>(rows) * chunks * sizeof(Partial);
 }
 
@@ -336,21 +314,12 @@ int kd_ce_loss_fwd(const void* S, const void* T, long long lds, long long ldt, i
   B2S_REQUIRE(V > 0 && V % 8 == 0 && lds % 8 == 0 && ldt % 8 == 0, "kd_ce_loss_fwd: V/ld must be multiples of 8");
   B2S_REQUIRE((reinterpret_cast<uintptr_t>(S) & 15) == 0 && (reinterpret_cast<uintptr_t>(T) & 15) == 0,
               "kd_ce_loss_fwd: logits must be 16-byte aligned");
-  const int chunks = (V + kChunkCols - 1) / kChunkCols;
-  const long long items_ll = static_cast<long long>(rows) * chunks;
-  B2S_REQUIRE(items_ll < (1LL << 31), "kd_ce_loss_fwd: too many work items");
-  const int items = static_cast<int>(items_ll);
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2S_CUDA_CHECK(cudaFuncSetAttribute(kd_ce_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kFwdSmemBytes));
-    attr_set = true;
-  }
-  int grid = 2 * num_sms();  // two 96 KiB rings per SM
-  if (grid > items) grid = items;
-  kd_ce_partial_kernel<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(
+  const int chunk_cols = fwd_chunk_cols(rows, V);
+  const int chunks = (V + chunk_cols - 1) / chunk_cols;
+  dim3 grid(chunks, rows);
+  kd_ce_partial_kernel<<<grid, kLossThreads, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(S), reinterpret_cast<const __nv_bfloat16*>(T), lds, ldt, V,
-      reinterpret_cast<Partial*>(workspace), chunks, items);
+      reinterpret_cast<Partial*>(workspace), chunks, chunk_cols);
   B2S_LAUNCH_CHECK();
   kd_ce_finalize_kernel<<<utterances, 256, 0, stream>>>(reinterpret_cast<const Partial*>(workspace), chunks,
                                                         reinterpret_cast<const __nv_bfloat16*>(S), lds, labels,

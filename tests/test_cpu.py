@@ -201,7 +201,7 @@ def test_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/b2s.h but not exported"
     assert declared == set(_lib.PROTOTYPES.keys())
     assert lib.b2s_version() == 1
-    assert lib.b2s_kd_ce_workspace_bytes(64, 128256) == 64 * 8 * 24
+    assert lib.b2s_kd_ce_workspace_bytes(64, 128256) == 64 * 16 * 24  # rows x max slices x sizeof(Partial)
 
 
 def test_abi_fails_loudly_without_gpu():

@@ -52,7 +52,20 @@ def bench_loss(rows, V):
     labels = torch.randint(0, V, (rows,), device=dev, dtype=torch.int32)
     offs = torch.arange(0, rows + 1, 64, device=dev, dtype=torch.int32)
     res = ops.kd_ce_loss(s, t, labels, offs)
-    ms = time_fn(lambda: ops.kd_ce_loss(s, t, labels, offs))
+    # time the two launches alone (pre-allocated outputs, direct C-ABI call: no allocator / wrapper overhead)
+    from llm_speech_summarization_b200 import _lib
+    lib = _lib.load()
+    ws = torch.empty(lib.b2s_kd_ce_workspace_bytes(rows, V), device=dev, dtype=torch.uint8)
+    U = offs.numel() - 1
+    ld_o, ntp_o = torch.empty(U, device=dev), torch.empty(U, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def fwd():
+        _lib.check(lib.b2s_kd_ce_loss_fwd(s.data_ptr(), t.data_ptr(), V, V, rows, V, labels.data_ptr(), offs.data_ptr(),
+                                          U, 1.0, 1.0, ws.data_ptr(), res.lse_s.data_ptr(), res.lse_t.data_ptr(),
+                                          res.coef_kd.data_ptr(), res.coef_ce.data_ptr(), ld_o.data_ptr(),
+                                          ntp_o.data_ptr(), st))
+    ms = time_fn(fwd, iters=20)
     ds = torch.empty_like(s)
     msb = time_fn(lambda: ops.kd_ce_loss_bwd(s, t, labels, res, out=ds))
     print(json.dumps({"kernel": "kd_ce_loss", "rows": rows, "V": V, "fwd_ms": round(ms, 4),
@@ -62,6 +75,9 @@ def bench_loss(rows, V):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "loss"):  # before the GEMMs heat the part up (the loss kernel is SM-clock sensitive)
+        for rows in (64, 2048):
+            bench_loss(rows, 128256)
     if which in ("all", "gemm"):
         shapes = [
             (15968, 3072, 1024, ops.EPI_BF16, "hubert_qkv_b32"),
@@ -81,6 +97,6 @@ if __name__ == "__main__":
                 except Exception as e:  # keep going: one bad config must not hide the others
                     print(json.dumps({"kernel": "gemm", "label": label, "bn": bn, "cg": cg, "error": str(e)[:300]}),
                           flush=True)
-    if which in ("all", "loss"):
-        for rows in (64, 2048):
+    if which in ("all",):  # and again hot, right after sustained tensor-core load (power-capped clocks)
+        for rows in (2048,):
             bench_loss(rows, 128256)
