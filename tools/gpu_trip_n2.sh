@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+nvidia-smi -L
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+tail -5 gpurun_out/bench_n2.err; cat gpurun_out/bench_n2.json
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 --cpu-utts 1 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err
+tail -3 gpurun_out/bench_ref_n2.err; cat gpurun_out/bench_ref_n2.json
+python bench.py --steps 3 --warmup 3 --batch 64 --no-cpu-baseline 2>&1 | tail -1
