@@ -64,6 +64,7 @@ typedef struct {
   const float* rope_cs;
   const int32_t* positions;
   int32_t rope_cols;
+  int32_t resid_bcast; /* 1: resid is [M, ldo] shared by every batch (e.g. a positional table) */
   int32_t block_n;   /* 0 = auto, else 64/128/256 */
   int32_t cta_group; /* 0 = auto, else 1/2 */
 } b2s_gemm_args;
@@ -183,6 +184,32 @@ size_t b2s_hubert_workspace_bytes(const b2s_hubert_weights* w, int32_t batches, 
 int b2s_hubert_forward(const b2s_hubert_weights* w, const float* wave, int64_t wave_stride, int32_t batches,
                        int32_t samples, void* workspace, size_t workspace_bytes, float* audio_embeds,
                        float* last_hidden, void* stream);
+
+/* Whisper encoder variant of AudioEncoder.forward (REF/model/audio_encoder.py:10-13,56-88 over WhisperEncoder.forward,
+ * TF/models/whisper/modeling_whisper.py:593-647), eval mode. */
+typedef struct {
+  const void* conv1_w; /* bf16 [H, 3*mel], column = tap*mel + c_in */
+  const float* conv1_b;
+  const void* conv2_w; /* bf16 [H, 3*H] */
+  const float* conv2_b;
+  const float* pos_emb; /* fp32 [max_positions, H] (embed_positions.weight) */
+  const b2s_encoder_layer* layers; /* host array; k_proj has no bias -> zeros in bqkv */
+  int32_t num_layers, hidden, heads, ffn, mel_bins, max_positions;
+  const float *final_ln_g, *final_ln_b;
+  float ln_eps;
+  int32_t pool_kernel, pool_stride;
+  const void* proj_w;
+  const float* proj_b;
+  int32_t llm_dim;
+} b2s_whisper_weights;
+
+size_t b2s_whisper_workspace_bytes(const b2s_whisper_weights* w, int32_t batches);
+/* mel: fp32 [batches, mel_bins, frames_in] (frames_in must be 2*max_positions, like the reference);
+ * audio_embeds: fp32 [batches * pooled, llm_dim], pooled = (max_positions - pool_kernel)/pool_stride + 1;
+ * last_hidden (optional): fp32 [batches * max_positions, hidden] pre-final-LN residual stream. */
+int b2s_whisper_forward(const b2s_whisper_weights* w, const float* mel, int32_t batches, int32_t frames_in,
+                        void* workspace, size_t workspace_bytes, float* audio_embeds, float* last_hidden,
+                        void* stream);
 
 typedef struct {
   const float* ln1_w;

@@ -24,7 +24,7 @@ class GemmArgs(C.Structure):
         ("k_per_tap", c_int), ("a_pad", c_int), ("a_group_off", c_int), ("w_group_off", c_int),
         ("epi", c_int), ("act", c_int), ("bias", c_void_p), ("out", c_void_p), ("ldo", c_int64),
         ("out_batch_rows", c_int64), ("resid", c_void_p), ("rope_cs", c_void_p), ("positions", c_void_p),
-        ("rope_cols", c_int), ("block_n", c_int), ("cta_group", c_int),
+        ("rope_cols", c_int), ("resid_bcast", c_int), ("block_n", c_int), ("cta_group", c_int),
     ]
 
 
@@ -42,6 +42,17 @@ class HubertWeights(C.Structure):
         ("pos_w", c_void_p), ("pos_b", c_void_p), ("pos_k", c_int), ("pos_groups", c_int),
         ("layers", C.POINTER(EncoderLayer)), ("num_layers", c_int), ("hidden", c_int), ("heads", c_int),
         ("ffn", c_int), ("final_ln_g", c_void_p), ("final_ln_b", c_void_p), ("ln_eps", c_float),
+        ("pool_kernel", c_int), ("pool_stride", c_int), ("proj_w", c_void_p), ("proj_b", c_void_p),
+        ("llm_dim", c_int),
+    ]
+
+
+class WhisperWeights(C.Structure):
+    _fields_ = [
+        ("conv1_w", c_void_p), ("conv1_b", c_void_p), ("conv2_w", c_void_p), ("conv2_b", c_void_p),
+        ("pos_emb", c_void_p), ("layers", C.POINTER(EncoderLayer)), ("num_layers", c_int), ("hidden", c_int),
+        ("heads", c_int), ("ffn", c_int), ("mel_bins", c_int), ("max_positions", c_int),
+        ("final_ln_g", c_void_p), ("final_ln_b", c_void_p), ("ln_eps", c_float),
         ("pool_kernel", c_int), ("pool_stride", c_int), ("proj_w", c_void_p), ("proj_b", c_void_p),
         ("llm_dim", c_int),
     ]
@@ -90,6 +101,9 @@ PROTOTYPES = {
     "b2s_hubert_workspace_bytes": (c_size_t, [C.POINTER(HubertWeights), c_int, c_int]),
     "b2s_hubert_forward": (c_int, [C.POINTER(HubertWeights), P_f32, c_int64, c_int, c_int, c_void_p, c_size_t, P_f32,
                                    P_f32, c_void_p]),
+    "b2s_whisper_workspace_bytes": (c_size_t, [C.POINTER(WhisperWeights), c_int]),
+    "b2s_whisper_forward": (c_int, [C.POINTER(WhisperWeights), P_f32, c_int, c_int, c_void_p, c_size_t, P_f32, P_f32,
+                                    c_void_p]),
     "b2s_llama_workspace_bytes": (c_size_t, [C.POINTER(LlamaWeights), c_int, c_int]),
     "b2s_llama_prefill": (c_int, [C.POINTER(LlamaWeights), P_f32, c_int, P_int, c_int, c_int, P_int, P_int, c_int,
                                   c_void_p, C.POINTER(c_int), c_int, P_int, P_int, c_int, P_f32, P_f32, c_void_p,

@@ -52,6 +52,18 @@ class EncoderArch:
 
 
 @dataclass
+class WhisperArch:
+    """openai/whisper-medium encoder."""
+    hidden: int = 1024
+    layers: int = 24
+    heads: int = 16
+    ffn: int = 4096
+    mel_bins: int = 80
+    max_positions: int = 1500
+    ln_eps: float = 1e-5
+
+
+@dataclass
 class LlmArch:
     vocab: int = 128256
     hidden: int = 3072
@@ -97,6 +109,11 @@ def _override(arch, overrides):
 def encoder_arch_from_config(config) -> EncoderArch:
     ae = config.model.audio_encoder
     return _override(EncoderArch(), getattr(ae, "arch", None))
+
+
+def whisper_arch_from_config(config) -> WhisperArch:
+    ae = config.model.audio_encoder
+    return _override(WhisperArch(), getattr(ae, "arch", None))
 
 
 def llm_arch_from_config(config) -> LlmArch:

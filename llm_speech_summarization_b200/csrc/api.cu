@@ -48,6 +48,9 @@ size_t hubert_workspace_bytes(const b2s_hubert_weights* w, int batches, int samp
 int hubert_forward(const b2s_hubert_weights* w, const float* wave, long long wave_stride, int batches, int samples,
                    void* workspace, size_t workspace_bytes, float* audio_embeds, float* last_hidden,
                    cudaStream_t stream);
+size_t whisper_workspace_bytes(const b2s_whisper_weights* w, int batches);
+int whisper_forward(const b2s_whisper_weights* w, const float* mel, int batches, int frames_in, void* workspace,
+                    size_t workspace_bytes, float* audio_embeds, float* last_hidden, cudaStream_t stream);
 size_t llama_workspace_bytes(const b2s_llama_weights* w, int rows, int logit_rows);
 int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_seqlens, int num_seqs, int max_seqlen,
                   const int* positions, const int* logit_rows_index, int logit_rows, void* logits_bf16,
@@ -96,6 +99,7 @@ int b2s_gemm_bf16(const b2s_gemm_args* a, void* stream) {
   g.ldo = a->ldo;
   g.out_batch_rows = a->out_batch_rows;
   g.resid = a->resid;
+  g.resid_bcast = a->resid_bcast;
   g.rope_cs = a->rope_cs;
   g.positions = a->positions;
   g.rope_cols = a->rope_cols;
@@ -182,6 +186,14 @@ int b2s_hubert_forward(const b2s_hubert_weights* w, const float* wave, int64_t w
                        float* last_hidden, void* stream) {
   return hubert_forward(w, wave, wave_stride, batches, samples, workspace, workspace_bytes, audio_embeds, last_hidden,
                         S(stream));
+}
+size_t b2s_whisper_workspace_bytes(const b2s_whisper_weights* w, int32_t batches) {
+  return whisper_workspace_bytes(w, batches);
+}
+int b2s_whisper_forward(const b2s_whisper_weights* w, const float* mel, int32_t batches, int32_t frames_in,
+                        void* workspace, size_t workspace_bytes, float* audio_embeds, float* last_hidden,
+                        void* stream) {
+  return whisper_forward(w, mel, batches, frames_in, workspace, workspace_bytes, audio_embeds, last_hidden, S(stream));
 }
 size_t b2s_llama_workspace_bytes(const b2s_llama_weights* w, int32_t rows, int32_t logit_rows) {
   return llama_workspace_bytes(w, rows, logit_rows);

@@ -68,6 +68,7 @@ struct KParams {
   long long ldo;
   long long out_batch_rows;
   const float* resid;
+  int resid_bcast;
   const float* rope_cs;
   const int* positions;
   int rope_cols;
@@ -347,8 +348,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (p.epi == EPI_BF16) {
             emit_bf16(stg, v, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, valid);
           } else {
+            // resid_bcast: the residual is indexed by the row inside the batch only (e.g. a positional table)
+            const long long roff0 = p.resid_bcast
+                                        ? static_cast<long long>(m0w) * p.ldo + static_cast<long long>(tc.g) * p.N + col
+                                        : off0;
             emit_f32(stg, v, lane, reinterpret_cast<float*>(p.out) + off0,
-                     p.epi == EPI_RESID_F32 ? p.resid + off0 : nullptr, p.ldo, rows_valid, valid);
+                     p.epi == EPI_RESID_F32 ? p.resid + roff0 : nullptr, p.ldo, rows_valid, valid);
           }
         }
       } else {
@@ -589,6 +594,7 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   p.ldo = a.ldo;
   p.out_batch_rows = a.out_batch_rows;
   p.resid = a.resid;
+  p.resid_bcast = a.resid_bcast;
   p.rope_cs = a.rope_cs;
   p.positions = a.positions;
   p.rope_cols = a.rope_cols;

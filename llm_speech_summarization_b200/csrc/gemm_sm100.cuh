@@ -49,6 +49,7 @@ struct GemmArgs {
   long long ldo;            // output leading dim (elements)
   long long out_batch_rows; // output row = b*out_batch_rows + m
   const float* resid;       // EPI_RESID_F32: fp32 [rows, ldo]
+  int resid_bcast;          // 1: resid is [M, ldo], shared by every batch (row index = m, not b*out_batch_rows + m)
   const float* rope_cs;     // EPI_ROPE: [npos, 128] fp32 = cos[0:64] | sin[0:64]
   const int* positions;     // EPI_ROPE: [rows] position of each row inside its own sequence
   int rope_cols;

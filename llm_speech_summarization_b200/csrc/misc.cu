@@ -165,6 +165,22 @@ posconv_weight_pack_kernel(const float* __restrict__ g, const float* __restrict_
   }
 }
 
+// log-mel (B, C, T) fp32 -> channels-last bf16 (B, T + 2, C) with a zero row before and after each utterance
+// (the zero padding of Whisper's conv1/conv2, TF/models/whisper/modeling_whisper.py:566-567)
+__global__ void mel_to_padded_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C,
+                                        int T) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * (T + 2) * C;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const long long r = i / C;
+  const int tp = static_cast<int>(r % (T + 2));
+  const int b = static_cast<int>(r / (T + 2));
+  float v = 0.f;
+  if (tp >= 1 && tp <= T) v = x[(static_cast<long long>(b) * C + c) * T + (tp - 1)];
+  y[i] = __float2bfloat16(v);
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
@@ -224,6 +240,15 @@ int posconv_weight_pack(const float* g, const float* v, void* w_packed_bf16, int
   B2S_REQUIRE(g && v && w_packed_bf16 && cout > 0 && cin_g > 0 && k > 0, "posconv_weight_pack: bad arguments");
   posconv_weight_pack_kernel<<<k, 256, 0, stream>>>(g, v, reinterpret_cast<__nv_bfloat16*>(w_packed_bf16), cout, cin_g,
                                                     k);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+int mel_to_padded_cl(const float* x, void* y_bf16, int batches, int channels, int frames, cudaStream_t stream) {
+  B2S_REQUIRE(x && y_bf16 && batches > 0 && channels > 0 && frames > 0, "mel_to_padded_cl: bad arguments");
+  const long long total = static_cast<long long>(batches) * (frames + 2) * channels;
+  mel_to_padded_cl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(y_bf16), batches, channels, frames);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

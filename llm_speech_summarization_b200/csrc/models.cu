@@ -104,6 +104,63 @@ GemmArgs plain_gemm(const void* A, const void* W, long long M, int N, int K) {
 
 }  // namespace
 
+// The pre-LN transformer stack shared by HuBERT (stable-layer-norm variant) and the Whisper encoder:
+//   h += out_proj(attention(qkv(LN1(h))));  h += W2 gelu(W1 LN2(h))      (fp32 residual stream h, bf16 operands)
+int encoder_stack(const b2s_encoder_layer* layers, int num_layers, int H, int F, int heads, float eps, float* h,
+                  void* xn, void* qkv_buf, void* ao, void* ff, const int* cu, int B, int frames,
+                  cudaStream_t stream) {
+  const long long rows = static_cast<long long>(B) * frames;
+  int rc;
+  for (int l = 0; l < num_layers; ++l) {
+    const b2s_encoder_layer& L = layers[l];
+    rc = layernorm_fwd(h, 0, L.ln1_g, L.ln1_b, eps, 0, xn, rows, H, stream);
+    if (rc != B2S_OK) return rc;
+    {
+      GemmArgs g = plain_gemm(xn, L.wqkv, rows, 3 * H, H);
+      g.epi = EPI_BF16;
+      g.bias = L.bqkv;
+      g.out = qkv_buf;
+      rc = gemm_bf16_launch(g, stream);
+      if (rc != B2S_OK) return rc;
+    }
+    {
+      const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(qkv_buf);
+      rc = attention_fwd(qkv, qkv + H, qkv + 2 * H, 3 * H, ao, H, cu, B, frames, heads, heads, 64, 0.125f, 0, stream);
+      if (rc != B2S_OK) return rc;
+    }
+    {
+      GemmArgs g = plain_gemm(ao, L.wo, rows, H, H);
+      g.epi = EPI_RESID_F32;
+      g.bias = L.bo;
+      g.out = h;
+      g.resid = h;
+      rc = gemm_bf16_launch(g, stream);
+      if (rc != B2S_OK) return rc;
+    }
+    rc = layernorm_fwd(h, 0, L.ln2_g, L.ln2_b, eps, 0, xn, rows, H, stream);
+    if (rc != B2S_OK) return rc;
+    {
+      GemmArgs g = plain_gemm(xn, L.w1, rows, F, H);
+      g.epi = EPI_BF16;
+      g.act = ACT_GELU;
+      g.bias = L.b1;
+      g.out = ff;
+      rc = gemm_bf16_launch(g, stream);
+      if (rc != B2S_OK) return rc;
+    }
+    {
+      GemmArgs g = plain_gemm(ff, L.w2, rows, H, F);
+      g.epi = EPI_RESID_F32;
+      g.bias = L.b2;
+      g.out = h;
+      g.resid = h;
+      rc = gemm_bf16_launch(g, stream);
+      if (rc != B2S_OK) return rc;
+    }
+  }
+  return B2S_OK;
+}
+
 int hubert_num_frames(const b2s_hubert_weights* w, int samples, int* frames, int* pooled) {
   B2S_REQUIRE(w != nullptr, "hubert: null weights");
   HubertPlan pl;
@@ -225,60 +282,156 @@ int hubert_forward(const b2s_hubert_weights* w, const float* wave, long long wav
   // ---- transformer layers (stable layer norm = pre-LN)
   iota_scaled_kernel<<<(B + 1 + 255) / 256, 256, 0, stream>>>(pl.cu, B + 1, pl.frames);
   B2S_LAUNCH_CHECK();
-  for (int l = 0; l < w->num_layers; ++l) {
-    const b2s_encoder_layer& L = w->layers[l];
-    rc = layernorm_fwd(pl.h, 0, L.ln1_g, L.ln1_b, eps, 0, pl.xn, rows, H, stream);
-    if (rc != B2S_OK) return rc;
-    {
-      GemmArgs g = plain_gemm(pl.xn, L.wqkv, rows, 3 * H, H);
-      g.epi = EPI_BF16;
-      g.bias = L.bqkv;
-      g.out = pl.qkv;
-      rc = gemm_bf16_launch(g, stream);
-      if (rc != B2S_OK) return rc;
-    }
-    {
-      const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(pl.qkv);
-      rc = attention_fwd(qkv, qkv + H, qkv + 2 * H, 3 * H, pl.ao, H, pl.cu, B, pl.frames, w->heads, w->heads, 64,
-                         0.125f, 0, stream);
-      if (rc != B2S_OK) return rc;
-    }
-    {
-      GemmArgs g = plain_gemm(pl.ao, L.wo, rows, H, H);
-      g.epi = EPI_RESID_F32;
-      g.bias = L.bo;
-      g.out = pl.h;
-      g.resid = pl.h;
-      rc = gemm_bf16_launch(g, stream);
-      if (rc != B2S_OK) return rc;
-    }
-    rc = layernorm_fwd(pl.h, 0, L.ln2_g, L.ln2_b, eps, 0, pl.xn, rows, H, stream);
-    if (rc != B2S_OK) return rc;
-    {
-      GemmArgs g = plain_gemm(pl.xn, L.w1, rows, F, H);
-      g.epi = EPI_BF16;
-      g.act = ACT_GELU;
-      g.bias = L.b1;
-      g.out = pl.ff;
-      rc = gemm_bf16_launch(g, stream);
-      if (rc != B2S_OK) return rc;
-    }
-    {
-      GemmArgs g = plain_gemm(pl.ff, L.w2, rows, H, F);
-      g.epi = EPI_RESID_F32;
-      g.bias = L.b2;
-      g.out = pl.h;
-      g.resid = pl.h;
-      rc = gemm_bf16_launch(g, stream);
-      if (rc != B2S_OK) return rc;
-    }
-  }
+  rc = encoder_stack(w->layers, w->num_layers, H, F, w->heads, eps, pl.h, pl.xn, pl.qkv, pl.ao, pl.ff, pl.cu, B,
+                     pl.frames, stream);
+  if (rc != B2S_OK) return rc;
   if (last_hidden != nullptr) {
     B2S_CUDA_CHECK(cudaMemcpyAsync(last_hidden, pl.h, rows * H * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   }
   // ---- final LN + AvgPool1d + projector
   rc = layernorm_avgpool_fwd(pl.h, w->final_ln_g, w->final_ln_b, eps, pl.pooled_x, B, pl.frames, H, w->pool_kernel,
                              w->pool_stride, pl.pooled, stream);
+  if (rc != B2S_OK) return rc;
+  {
+    GemmArgs g = plain_gemm(pl.pooled_x, w->proj_w, static_cast<long long>(B) * pl.pooled, w->llm_dim, H);
+    g.epi = EPI_F32;
+    g.bias = w->proj_b;
+    g.out = audio_embeds;
+    rc = gemm_bf16_launch(g, stream);
+    if (rc != B2S_OK) return rc;
+  }
+  return B2S_OK;
+}
+
+// --------------------------------------------------------------------------------------------- Whisper
+namespace {
+struct WhisperPlan {
+  int frames_in, frames, pooled;
+  void* x0;   // bf16 [B, T+2, mel]   zero-padded channels-last log-mel
+  void* x1;   // bf16 [B, T+2, H]     zero-padded conv1 output
+  float* h;
+  void *xn, *qkv, *ao, *ff, *pooled_x;
+  int* cu;
+  size_t bytes;
+};
+int plan_whisper(const b2s_whisper_weights* w, int batches, void* ws, size_t ws_bytes, WhisperPlan* pl) {
+  pl->frames_in = 2 * w->max_positions;
+  pl->frames = w->max_positions;
+  pl->pooled = pl->frames >= w->pool_kernel ? (pl->frames - w->pool_kernel) / w->pool_stride + 1 : 0;
+  const size_t B = batches, H = w->hidden;
+  const size_t rows = B * pl->frames;
+  Carver c(ws, ws_bytes);
+  pl->x0 = c.take(B * (pl->frames_in + 2) * w->mel_bins * 2 + 4096);
+  pl->x1 = c.take(B * (pl->frames_in + 2) * H * 2 + 4096);
+  pl->h = reinterpret_cast<float*>(c.take(rows * H * 4));
+  pl->xn = c.take(rows * H * 2);
+  pl->qkv = c.take(rows * 3 * H * 2);
+  pl->ao = c.take(rows * H * 2);
+  pl->ff = c.take(rows * w->ffn * 2);
+  pl->pooled_x = c.take(B * (pl->pooled > 0 ? pl->pooled : 1) * H * 2);
+  pl->cu = reinterpret_cast<int*>(c.take((B + 1) * sizeof(int)));
+  pl->bytes = c.off + 256;
+  if (ws != nullptr && !c.ok()) {
+    set_last_error("whisper workspace too small: need %zu bytes, got %zu", pl->bytes, ws_bytes);
+    return B2S_ERR_INVALID;
+  }
+  return B2S_OK;
+}
+}  // namespace
+
+size_t whisper_workspace_bytes(const b2s_whisper_weights* w, int batches) {
+  if (w == nullptr || batches <= 0) return 0;
+  WhisperPlan pl;
+  plan_whisper(w, batches, nullptr, 0, &pl);
+  return pl.bytes;
+}
+
+int whisper_forward(const b2s_whisper_weights* w, const float* mel, int batches, int frames_in, void* workspace,
+                    size_t workspace_bytes, float* audio_embeds, float* last_hidden, cudaStream_t stream) {
+  B2S_REQUIRE(w && mel && workspace && audio_embeds, "whisper_forward: null pointer");
+  B2S_REQUIRE(batches > 0, "whisper_forward: empty batch");
+  // WhisperEncoder.forward raises unless the mel input has exactly max_source_positions * 2 frames
+  // (TF/models/whisper/modeling_whisper.py:613-617)
+  B2S_REQUIRE(frames_in == 2 * w->max_positions,
+              "Whisper expects the mel input features to be of length %d, but found %d", 2 * w->max_positions,
+              frames_in);
+  B2S_REQUIRE(w->hidden % 256 == 0 && w->hidden / w->heads == 64 && w->mel_bins % 8 == 0,
+              "whisper_forward: hidden %% 256, head_dim 64 and mel_bins %% 8 required");
+  WhisperPlan pl;
+  int rc = plan_whisper(w, batches, workspace, workspace_bytes, &pl);
+  if (rc != B2S_OK) return rc;
+  B2S_REQUIRE(pl.pooled > 0, "whisper_forward: too few frames to pool");
+  const int B = batches, H = w->hidden, F = w->ffn, C = w->mel_bins, T = frames_in;
+  const long long rows = static_cast<long long>(B) * pl.frames;
+
+  rc = mel_to_padded_cl(mel, pl.x0, B, C, T, stream);
+  if (rc != B2S_OK) return rc;
+  // conv1: Conv1d(mel -> H, k=3, pad=1) + GELU; output row t lands on padded row t+1 of x1, whose first and last
+  // rows stay zero (they are conv2's padding)
+  B2S_CUDA_CHECK(cudaMemsetAsync(pl.x1, 0, static_cast<size_t>(B) * (T + 2) * H * 2, stream));
+  {
+    GemmArgs g{};
+    g.A = pl.x0;
+    g.a_dim0 = 3 * C;  // window view over the padded input: row t = x[t : t+3, :]
+    g.a_row_stride = C;
+    g.a_batch_stride = static_cast<long long>(T + 2) * C;
+    g.a_rows = T;
+    g.W = w->conv1_w;
+    g.w_rows = H;
+    g.w_cols = 3 * C;
+    g.M = T;
+    g.N = H;
+    g.batches = B;
+    g.groups = 1;
+    g.taps = 1;
+    g.k_per_tap = 3 * C;
+    g.epi = EPI_BF16;
+    g.act = ACT_GELU;
+    g.bias = w->conv1_b;
+    g.out = reinterpret_cast<__nv_bfloat16*>(pl.x1) + H;  // skip the leading zero row
+    g.ldo = H;
+    g.out_batch_rows = T + 2;
+    rc = gemm_bf16_launch(g, stream);
+    if (rc != B2S_OK) return rc;
+  }
+  // conv2: Conv1d(H -> H, k=3, stride=2, pad=1) + GELU, + positional table -> fp32 residual stream
+  {
+    GemmArgs g{};
+    g.A = pl.x1;
+    g.a_dim0 = 3 * H;  // row t = x1_padded[2t : 2t+3, :]
+    g.a_row_stride = 2LL * H;
+    g.a_batch_stride = static_cast<long long>(T + 2) * H;
+    g.a_rows = pl.frames;
+    g.W = w->conv2_w;
+    g.w_rows = H;
+    g.w_cols = 3 * H;
+    g.M = pl.frames;
+    g.N = H;
+    g.batches = B;
+    g.groups = 1;
+    g.taps = 1;
+    g.k_per_tap = 3 * H;
+    g.epi = EPI_RESID_F32;
+    g.act = ACT_GELU;
+    g.bias = w->conv2_b;
+    g.out = pl.h;
+    g.resid = w->pos_emb;
+    g.resid_bcast = 1;
+    g.ldo = H;
+    g.out_batch_rows = pl.frames;
+    rc = gemm_bf16_launch(g, stream);
+    if (rc != B2S_OK) return rc;
+  }
+  iota_scaled_kernel<<<(B + 1 + 255) / 256, 256, 0, stream>>>(pl.cu, B + 1, pl.frames);
+  B2S_LAUNCH_CHECK();
+  rc = encoder_stack(w->layers, w->num_layers, H, F, w->heads, w->ln_eps, pl.h, pl.xn, pl.qkv, pl.ao, pl.ff, pl.cu, B,
+                     pl.frames, stream);
+  if (rc != B2S_OK) return rc;
+  if (last_hidden != nullptr) {
+    B2S_CUDA_CHECK(cudaMemcpyAsync(last_hidden, pl.h, rows * H * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  }
+  rc = layernorm_avgpool_fwd(pl.h, w->final_ln_g, w->final_ln_b, w->ln_eps, pl.pooled_x, B, pl.frames, H,
+                             w->pool_kernel, w->pool_stride, pl.pooled, stream);
   if (rc != B2S_OK) return rc;
   {
     GemmArgs g = plain_gemm(pl.pooled_x, w->proj_w, static_cast<long long>(B) * pl.pooled, w->llm_dim, H);

@@ -128,6 +128,54 @@ class HubertBackbone(nn.Module):
         self.encoder = _Encoder(arch)
 
 
+class _WhisperAttn(nn.Module):
+    def __init__(self, H):
+        super().__init__()
+        self.k_proj = _Params(weight=(H, H))  # no bias (TF/models/whisper/modeling_whisper.py:279)
+        self.v_proj = _Params(weight=(H, H), bias=(H,))
+        self.q_proj = _Params(weight=(H, H), bias=(H,))
+        self.out_proj = _Params(weight=(H, H), bias=(H,))
+
+
+class _WhisperLayer(nn.Module):
+    def __init__(self, H, Fd):
+        super().__init__()
+        self.self_attn = _WhisperAttn(H)
+        self.self_attn_layer_norm = _Params(weight=(H,), bias=(H,))
+        self.fc1 = _Params(weight=(Fd, H), bias=(Fd,))
+        self.fc2 = _Params(weight=(H, Fd), bias=(H,))
+        self.final_layer_norm = _Params(weight=(H,), bias=(H,))
+
+
+class WhisperBackbone(nn.Module):
+    """Parameter container with HF WhisperEncoder's names (TF/models/whisper/modeling_whisper.py:541-647)."""
+
+    def __init__(self, arch):
+        super().__init__()
+        self.arch = arch
+        self.config = _EncoderConfigView(arch)
+        self.conv1 = _Params(weight=(arch.hidden, arch.mel_bins, 3), bias=(arch.hidden,))
+        self.conv2 = _Params(weight=(arch.hidden, arch.hidden, 3), bias=(arch.hidden,))
+        self.embed_positions = _Params(weight=(arch.max_positions, arch.hidden))
+        self.embed_positions.weight.requires_grad_(False)
+        self.layers = nn.ModuleList([_WhisperLayer(arch.hidden, arch.ffn) for _ in range(arch.layers)])
+        self.layer_norm = _Params(weight=(arch.hidden,), bias=(arch.hidden,))
+
+
+def load_whisper_encoder(config):
+    """REF/model/audio_encoder.py:10-13 downloads openai/whisper-medium and its feature extractor; here the
+    architecture comes from the config (defaults = whisper-medium) and the log-mel extractor is transformers'
+    WhisperFeatureExtractor with its default (= whisper) parameters, which needs no download."""
+    from ..config import whisper_arch_from_config
+    feature_extractor = None
+    try:
+        from transformers import WhisperFeatureExtractor
+        feature_extractor = WhisperFeatureExtractor()
+    except Exception:  # transformers missing: the collate-side extractor is outside the hot path anyway
+        pass
+    return WhisperBackbone(whisper_arch_from_config(config)), feature_extractor
+
+
 def load_hubert_encoder(config):
     """REF/model/audio_encoder.py:6-7 downloads facebook/hubert-large-ls960-ft; here the architecture comes from
     the config (defaults = HuBERT-large) and the weights from the checkpoint the caller loads."""
@@ -144,8 +192,8 @@ class AudioEncoder(nn.Module):
             self.encoder_base = "hubert"
             self.encoder = load_hubert_encoder(self.config)
         elif self.config.model.audio_encoder.base == "whisper":
-            # SURVEY.md section 8 row a7 (config C4) -- scheduled after the HuBERT path meets its bar.
-            raise NotImplementedError("whisper audio encoder is not built yet in the B200 path (SURVEY.md 8/a7)")
+            self.encoder_base = "whisper"
+            self.encoder, self.feature_extractor = load_whisper_encoder(self.config)
         else:
             raise Exception("Unexpected encoder type in config.")
 
@@ -184,6 +232,10 @@ class AudioEncoder(nn.Module):
         parameter changes (optimizer step, load_state_dict)."""
         key = self._weights_key()
         if not force and self._packed is not None and self._packed_key == key:
+            return self._packed
+        if self.encoder_base == "whisper":
+            self._packed = self._pack_whisper()
+            self._packed_key = key
             return self._packed
         enc = self.encoder
         arch: EncoderArch = enc.arch
@@ -240,6 +292,67 @@ class AudioEncoder(nn.Module):
         self._packed_key = key
         return self._packed
 
+    def _pack_whisper(self):
+        enc = self.encoder
+        arch = enc.arch
+        dev = enc.conv1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("AudioEncoder (B200 path) needs its parameters on a CUDA device; there is no CPU path")
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        keep: List[torch.Tensor] = []
+
+        def K(t):
+            keep.append(t)
+            return t.data_ptr()
+
+        w = _lib.WhisperWeights()
+        w.conv1_w, w.conv1_b = K(bf(packing.pack_conv(enc.conv1.weight.detach()))), K(f32(enc.conv1.bias))
+        w.conv2_w, w.conv2_b = K(bf(packing.pack_conv(enc.conv2.weight.detach()))), K(f32(enc.conv2.bias))
+        w.pos_emb = K(f32(enc.embed_positions.weight))
+        layers = (_lib.EncoderLayer * arch.layers)()
+        for l, lay in enumerate(enc.layers):
+            a = lay.self_attn
+            L = layers[l]
+            L.ln1_g, L.ln1_b = K(f32(lay.self_attn_layer_norm.weight)), K(f32(lay.self_attn_layer_norm.bias))
+            L.wqkv = K(bf(packing.pack_qkv(a.q_proj.weight.detach(), a.k_proj.weight.detach(),
+                                           a.v_proj.weight.detach())))
+            L.bqkv = K(f32(torch.cat([a.q_proj.bias.detach(), torch.zeros_like(a.q_proj.bias), a.v_proj.bias.detach()])))
+            L.wo, L.bo = K(bf(a.out_proj.weight)), K(f32(a.out_proj.bias))
+            L.ln2_g, L.ln2_b = K(f32(lay.final_layer_norm.weight)), K(f32(lay.final_layer_norm.bias))
+            L.w1, L.b1 = K(bf(lay.fc1.weight)), K(f32(lay.fc1.bias))
+            L.w2, L.b2 = K(bf(lay.fc2.weight)), K(f32(lay.fc2.bias))
+        w.layers = C.cast(layers, C.POINTER(_lib.EncoderLayer))
+        w.num_layers, w.hidden, w.heads, w.ffn = arch.layers, arch.hidden, arch.heads, arch.ffn
+        w.mel_bins, w.max_positions = arch.mel_bins, arch.max_positions
+        w.final_ln_g, w.final_ln_b = K(f32(enc.layer_norm.weight)), K(f32(enc.layer_norm.bias))
+        w.ln_eps = arch.ln_eps
+        w.pool_kernel, w.pool_stride = self.pool_kernel, self.pool_stride
+        w.proj_w, w.proj_b = K(bf(self.embed_projection.weight)), K(f32(self.embed_projection.bias))
+        w.llm_dim = self.embed_projection.out_features
+        return (w, layers, keep)
+
+    def _whisper_forward_fp32(self, input: torch.Tensor, return_last_hidden: bool = False):
+        w = self.pack_weights()[0]
+        mel = input.to(torch.float32).contiguous()
+        if mel.dim() != 3 or mel.shape[1] != w.mel_bins:
+            raise ValueError(f"expected (B, {w.mel_bins}, T) log-mel features")
+        B, _, T = mel.shape
+        if T != 2 * w.max_positions:  # same check and message as WhisperEncoder.forward
+            raise ValueError(f"Whisper expects the mel input features to be of length {2 * w.max_positions}, but "
+                             f"found {T}. Make sure to pad the input mel features to {2 * w.max_positions}.")
+        pooled = (w.max_positions - w.pool_kernel) // w.pool_stride + 1
+        lib = _lib.load()
+        nbytes = lib.b2s_whisper_workspace_bytes(C.byref(w), B)
+        ws = torch.empty(nbytes, device=mel.device, dtype=torch.uint8)
+        out = torch.empty(B, pooled, w.llm_dim, device=mel.device, dtype=torch.float32)
+        last = (torch.empty(B, w.max_positions, w.hidden, device=mel.device, dtype=torch.float32)
+                if return_last_hidden else None)
+        _lib.check(lib.b2s_whisper_forward(C.byref(w), mel.data_ptr(), B, T, ws.data_ptr(), nbytes, out.data_ptr(),
+                                           None if last is None else last.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream), "whisper_forward")
+        return (out, last) if return_last_hidden else out
+
     def num_frames(self, samples: int):
         w = self.pack_weights()[0]
         frames, pooled = C.c_int32(), C.c_int32()
@@ -256,6 +369,8 @@ class AudioEncoder(nn.Module):
             raise NotImplementedError(
                 "training-mode forward/backward of the audio encoder is not built yet (SURVEY.md 8/a13, K13); "
                 "call .eval() / torch.no_grad() for the forward path")
+        if self.encoder_base == "whisper":
+            return self._whisper_forward_fp32(input, return_last_hidden)
         w = self.pack_weights()[0]
         wave = input.to(torch.float32)
         if wave.dim() != 2:

@@ -67,6 +67,62 @@ TINY_MINICHAT = LlmCfg(vocab=1000, hidden=256, ffn=512, layers=2, heads=2, kv_he
                        llm_type="GeneZC/MiniChat-2-3B")
 
 
+@dataclass
+class WhisperCfg:
+    hidden: int = 1024
+    layers: int = 24
+    heads: int = 16
+    ffn: int = 4096
+    mel_bins: int = 80
+    max_positions: int = 1500
+    ln_eps: float = 1e-5
+    pool_kernel: int = 8
+    pool_stride: int = 4
+    llm_dim: int = 3072
+
+
+WHISPER_MEDIUM = WhisperCfg()
+TINY_WHISPER = WhisperCfg(hidden=256, layers=2, heads=4, ffn=512, max_positions=100, llm_dim=256)
+
+
+def make_whisper_state_dict(cfg: WhisperCfg, seed: int = 2468) -> Dict[str, torch.Tensor]:
+    """Synthetic AudioEncoder(base=whisper) weights under the reference's checkpoint names (`encoder.` = HF
+    WhisperEncoder, TF/models/whisper/modeling_whisper.py:541-647; k_proj has no bias)."""
+    g = torch.Generator().manual_seed(seed)
+    H = cfg.hidden
+    sd: Dict[str, torch.Tensor] = {}
+    sd["encoder.conv1.weight"] = _randn(g, H, cfg.mel_bins, 3, std=math.sqrt(1.0 / (3 * cfg.mel_bins)))
+    sd["encoder.conv1.bias"] = _randn(g, H, std=0.05)
+    sd["encoder.conv2.weight"] = _randn(g, H, H, 3, std=math.sqrt(1.0 / (3 * H)))
+    sd["encoder.conv2.bias"] = _randn(g, H, std=0.05)
+    sd["encoder.embed_positions.weight"] = _randn(g, cfg.max_positions, H, std=0.3)
+    for l in range(cfg.layers):
+        p = f"encoder.layers.{l}."
+        sd[p + "self_attn.k_proj.weight"] = _randn(g, H, H, std=0.02)
+        for n in ("v_proj", "q_proj", "out_proj"):
+            sd[p + f"self_attn.{n}.weight"] = _randn(g, H, H, std=0.02)
+            sd[p + f"self_attn.{n}.bias"] = _randn(g, H, std=0.02)
+        sd[p + "self_attn_layer_norm.weight"] = _randn(g, H, std=0.1, mean=1.0)
+        sd[p + "self_attn_layer_norm.bias"] = _randn(g, H, std=0.1)
+        sd[p + "fc1.weight"] = _randn(g, cfg.ffn, H, std=0.02)
+        sd[p + "fc1.bias"] = _randn(g, cfg.ffn, std=0.02)
+        sd[p + "fc2.weight"] = _randn(g, H, cfg.ffn, std=0.02)
+        sd[p + "fc2.bias"] = _randn(g, H, std=0.02)
+        sd[p + "final_layer_norm.weight"] = _randn(g, H, std=0.1, mean=1.0)
+        sd[p + "final_layer_norm.bias"] = _randn(g, H, std=0.1)
+    sd["encoder.layer_norm.weight"] = _randn(g, H, std=0.1, mean=1.0)
+    sd["encoder.layer_norm.bias"] = _randn(g, H, std=0.1)
+    sd["embed_projection.weight"] = _randn(g, cfg.llm_dim, H, std=0.02)
+    sd["embed_projection.bias"] = _randn(g, cfg.llm_dim, std=0.02)
+    return sd
+
+
+def synthetic_log_mel(cfg: WhisperCfg, index: int, batch: int = 1) -> torch.Tensor:
+    """Synthetic log-mel in the extractor's output range: randn*0.5 clamped to [-1, 1.5]."""
+    g = torch.Generator().manual_seed(4321 + index)
+    return (torch.randn(batch, cfg.mel_bins, 2 * cfg.max_positions, generator=g) * 0.5).clamp(-1.0, 1.5)
+
+
 def _randn(gen: torch.Generator, *shape, std: float = 1.0, mean: float = 0.0) -> torch.Tensor:
     return torch.randn(*shape, generator=gen, dtype=torch.float32) * std + mean
 

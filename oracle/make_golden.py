@@ -175,6 +175,42 @@ def run_case(name, enc_cfg, llm_cfg, samples, T, R, fd_layers, extra_text=0, wri
     return errs
 
 
+def run_whisper_case(name, cfg, write=True):
+    """AudioEncoder(base="whisper") of the reference (REF/model/audio_encoder.py:10-13,25-27,56-88) on synthetic
+    log-mel features, plus the trainer's crop to compute_num_audio_embeds (REF/trainer.py:280-291)."""
+    from transformers import WhisperConfig, WhisperModel
+    from oracle import configs, reference_math as rm
+    ref_audio_encoder, _, ref_utils = import_reference()
+    wc = WhisperConfig(d_model=cfg.hidden, encoder_layers=cfg.layers, encoder_attention_heads=cfg.heads,
+                       encoder_ffn_dim=cfg.ffn, num_mel_bins=cfg.mel_bins, max_source_positions=cfg.max_positions,
+                       decoder_layers=1, decoder_attention_heads=cfg.heads, decoder_ffn_dim=cfg.ffn,
+                       activation_function="gelu", dropout=0.0, encoder_layerdrop=0.0, vocab_size=64,
+                       pad_token_id=0, bos_token_id=1, eos_token_id=2, decoder_start_token_id=1)
+    ref_audio_encoder.load_whisper_encoder = lambda config: (WhisperModel(wc).encoder, None)
+    config = ns(model=ns(audio_encoder=ns(base="whisper", type="openai/whisper-medium", downsample_method="pool",
+                                          downsample_factor=4,
+                                          pooling=ns(kernel_size=cfg.pool_kernel, stride=cfg.pool_stride)),
+                         llm_type="meta-llama/Llama-3.2-3B-Instruct", llm_embedding_channels=cfg.llm_dim))
+    enc = ref_audio_encoder.AudioEncoder(config, torch.device("cpu"))
+    sd = configs.make_whisper_state_dict(cfg)
+    enc.load_state_dict(sd, strict=True)
+    enc.eval()
+    mel = configs.synthetic_log_mel(cfg, 0, batch=2)
+    with torch.no_grad():
+        ref = enc(mel)
+        ora = rm.audio_encoder_forward_whisper(sd, mel, cfg)
+    # the trainer's un-padding for whisper: 20 ms frames -> samples covered by the mel input
+    samples = 2 * cfg.max_positions * 160
+    n = ref_utils.compute_num_audio_embeds(samples, sr=16000)
+    err = rel(ora, ref)
+    print(f"[{name}] oracle vs reference: audio_embeds {err:.2e}; shape {tuple(ref.shape)}, crop to {n}")
+    assert err < 2e-4 and n <= ref.shape[1]
+    if write:
+        os.makedirs(GOLD, exist_ok=True)
+        torch.save({"case": name, "cfg": configs.cfg_dict(cfg), "seed": 2468, "audio_embeds": ref.clone(),
+                    "num_audio_embeds": n, "torch": torch.__version__}, os.path.join(GOLD, f"{name}.pt"))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also check the full-size architectures (no fixture written)")
@@ -185,7 +221,9 @@ def main():
              fd_layers=(0, 1, 2))
     run_case("tiny_minichat_hubert", configs.TINY_ENCODER, configs.TINY_MINICHAT, samples=8000, T=5, R=4,
              fd_layers=(0, 1), extra_text=3)
+    run_whisper_case("tiny_whisper", configs.TINY_WHISPER)
     if args.full:
+        run_whisper_case("full_whisper_medium", configs.WHISPER_MEDIUM, write=False)
         run_case("full_llama32_hubert", configs.HUBERT_LARGE, configs.LLAMA32_3B, samples=160000, T=40, R=64,
                  fd_layers=(0, 5, 11, 17, 23), write=False)
 

@@ -118,6 +118,41 @@ def audio_encoder_forward(sd, wave: torch.Tensor, cfg: EncoderCfg) -> torch.Tens
     return F.linear(pooled, sd["embed_projection.weight"], sd["embed_projection.bias"])
 
 
+def whisper_last_hidden_state(sd, mel: torch.Tensor, cfg) -> torch.Tensor:
+    """WhisperEncoder.forward(...).last_hidden_state, eval mode (TF/models/whisper/modeling_whisper.py:593-647; layer
+    :361-414; attention :262-345 with q scaled by head_dim**-0.5 and a bias-free k_proj :279). (B, mel, 2*P) -> (B, P, H)."""
+    H, nh = cfg.hidden, cfg.heads
+    hd = H // nh
+    x = F.gelu(F.conv1d(mel, sd["encoder.conv1.weight"], sd["encoder.conv1.bias"], padding=1))
+    x = F.gelu(F.conv1d(x, sd["encoder.conv2.weight"], sd["encoder.conv2.bias"], stride=2, padding=1))
+    x = x.permute(0, 2, 1) + sd["encoder.embed_positions.weight"]
+    B, N, _ = x.shape
+    for l in range(cfg.layers):
+        p = f"encoder.layers.{l}."
+        y = F.layer_norm(x, (H,), sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"], cfg.ln_eps)
+        q = F.linear(y, sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.q_proj.bias"])
+        k = F.linear(y, sd[p + "self_attn.k_proj.weight"])
+        v = F.linear(y, sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.v_proj.bias"])
+        q = q.view(B, N, nh, hd).transpose(1, 2)
+        k = k.view(B, N, nh, hd).transpose(1, 2)
+        v = v.view(B, N, nh, hd).transpose(1, 2)
+        a = torch.softmax(torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5), dim=-1)
+        a = torch.matmul(a, v).transpose(1, 2).reshape(B, N, H)
+        x = x + F.linear(a, sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])
+        y = F.layer_norm(x, (H,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], cfg.ln_eps)
+        y = F.gelu(F.linear(y, sd[p + "fc1.weight"], sd[p + "fc1.bias"]))
+        x = x + F.linear(y, sd[p + "fc2.weight"], sd[p + "fc2.bias"])
+    return F.layer_norm(x, (H,), sd["encoder.layer_norm.weight"], sd["encoder.layer_norm.bias"], cfg.ln_eps)
+
+
+def audio_encoder_forward_whisper(sd, mel: torch.Tensor, cfg) -> torch.Tensor:
+    """REF/model/audio_encoder.py:56-88 with base == "whisper": encoder -> AvgPool1d -> embed_projection.
+    The crop to compute_num_audio_embeds happens in the trainer (REF/trainer.py:280-291), not here."""
+    enc = whisper_last_hidden_state(sd, mel, cfg)
+    pooled = F.avg_pool1d(enc.transpose(1, 2), kernel_size=cfg.pool_kernel, stride=cfg.pool_stride).transpose(1, 2)
+    return F.linear(pooled, sd["embed_projection.weight"], sd["embed_projection.bias"])
+
+
 def compute_num_audio_embeds(audio_samples, sr=16000):
     """REF/utils.py:13-24 (float floor-division, then int)."""
     num_embeds = (audio_samples - (sr * 0.01)) // (sr * 0.02)

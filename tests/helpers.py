@@ -51,3 +51,12 @@ def bf16_round_sd(sd):
     """The reference holds the frozen LLM in half precision (REF/trainer.py:58-62); round the synthetic fp32 weights
     the same way so both sides see identical parameters."""
     return {k: v.to(torch.bfloat16).to(torch.float32) for k, v in sd.items()}
+
+
+def ns_config_whisper(cfg, llm_type="meta-llama/Llama-3.2-3B-Instruct"):
+    return NS(model=NS(audio_encoder=NS(base="whisper", type="openai/whisper-medium", downsample_method="pool",
+                                        downsample_factor=4, pooling=NS(kernel_size=cfg.pool_kernel, stride=cfg.pool_stride),
+                                        arch=NS(hidden=cfg.hidden, layers=cfg.layers, heads=cfg.heads, ffn=cfg.ffn,
+                                                mel_bins=cfg.mel_bins, max_positions=cfg.max_positions)),
+                       llm_type=llm_type, llm_embedding_channels=cfg.llm_dim),
+              audio=NS(sampling_rate=16000))

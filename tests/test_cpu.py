@@ -257,3 +257,29 @@ def test_data_parallel_world_size_2_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("OK") == 2
+
+
+# --------------------------------------------------------------------------------------- whisper variant
+def test_whisper_oracle_matches_reference_golden():
+    from oracle import configs, reference_math as rm
+    g = torch.load(os.path.join(GOLDEN, "tiny_whisper.pt"), weights_only=False)
+    cfg = configs.WhisperCfg(**g["cfg"])
+    sd = configs.make_whisper_state_dict(cfg, seed=g["seed"])
+    with torch.no_grad():
+        out = rm.audio_encoder_forward_whisper(sd, configs.synthetic_log_mel(cfg, 0, batch=2), cfg)
+    assert out.shape == g["audio_embeds"].shape
+    assert rel_l2(out, g["audio_embeds"]) < 1e-4
+    assert rm.compute_num_audio_embeds(2 * cfg.max_positions * 160) == g["num_audio_embeds"]
+    assert rm.compute_num_audio_embeds(480000) == 373  # 30 s -> pooled 374 cropped to 373
+
+
+def test_whisper_state_dict_layout():
+    from oracle import configs
+    from helpers import ns_config_whisper
+    from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
+    cfg = configs.TINY_WHISPER
+    enc = AudioEncoder(ns_config_whisper(cfg), torch.device("cpu"))
+    sd = configs.make_whisper_state_dict(cfg)
+    assert set(enc.state_dict().keys()) == set(sd.keys())
+    enc.load_state_dict(sd, strict=True)
+    assert "encoder.layers.0.self_attn.k_proj.bias" not in enc.state_dict()

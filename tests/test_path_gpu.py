@@ -209,3 +209,46 @@ def _eager_bf16_teacher_logits(llm_sd, llm_cfg, tok, text_ids, resp_ids, dev):
     x = rms(x, sd["model.norm.weight"])
     R_ = resp_ids.shape[0]
     return F.linear(x[0, -R_:], sd["lm_head.weight"])
+
+
+def test_whisper_encoder_golden(cuda):
+    """AudioEncoder(base="whisper") on the CUDA path vs the reference module's output (tests/golden/tiny_whisper.pt),
+    plus the trainer's crop to compute_num_audio_embeds (REF/trainer.py:280-291) and the input-length check."""
+    from oracle import configs
+    from helpers import ns_config_whisper
+    from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
+    from llm_speech_summarization_b200.utils import compute_num_audio_embeds
+    g = torch.load(os.path.join(GOLDEN, "tiny_whisper.pt"), weights_only=False)
+    cfg = configs.WhisperCfg(**g["cfg"])
+    enc = AudioEncoder(ns_config_whisper(cfg), cuda)
+    enc.load_state_dict(configs.make_whisper_state_dict(cfg, seed=g["seed"]), strict=True)
+    enc.eval().to(cuda)
+    mel = configs.synthetic_log_mel(cfg, 0, batch=2)
+    with torch.no_grad():
+        out32 = enc.forward_fp32(mel.to(cuda))
+        out = enc(mel.to(cuda), None)
+    assert out.shape == g["audio_embeds"].shape and out.dtype == torch.bfloat16
+    assert rel_l2(out32.cpu(), g["audio_embeds"]) < TOL_EMBED
+    n = compute_num_audio_embeds(2 * cfg.max_positions * 160, sr=16000)
+    assert n == g["num_audio_embeds"] and out[0, :n].shape[0] == n
+    with pytest.raises(ValueError, match="Whisper expects the mel input features"):
+        enc(mel[:, :, :-2].to(cuda))
+
+
+@pytest.mark.slow
+def test_whisper_medium_full_size_vs_oracle(cuda):
+    """Whisper-medium encoder shapes (24 x 1024, 3000 mel frames -> 1500 -> 374 pooled), random init, vs the CPU oracle."""
+    from oracle import configs, reference_math as rm
+    from helpers import ns_config_whisper
+    from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
+    cfg = configs.WHISPER_MEDIUM
+    sd = configs.make_whisper_state_dict(cfg)
+    enc = AudioEncoder(ns_config_whisper(cfg), cuda)
+    enc.load_state_dict(sd, strict=True)
+    enc.eval().to(cuda)
+    mel = configs.synthetic_log_mel(cfg, 0, batch=2)
+    with torch.no_grad():
+        out = enc.forward_fp32(mel.to(cuda))
+        ref = rm.audio_encoder_forward_whisper(sd, mel, cfg)
+    assert out.shape == (2, 374, 3072)
+    assert rel_l2(out.cpu(), ref) < TOL_EMBED
