@@ -127,8 +127,11 @@ int b2s_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
 /* Packed varlen attention forward (TF/models/hubert/modeling_hubert.py:262-345;
  * TF/models/llama/modeling_llama.py:225-289). */
 int b2s_attention_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
-                      const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t Hq, int32_t Hkv,
-                      int32_t D, float scale, int32_t causal, void* stream);
+                      const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int64_t total_rows, int32_t Hq,
+                      int32_t Hkv, int32_t D, float scale, int32_t causal, void* stream);
+/* kernel selection for A/B tests: 1 = tcgen05/TMEM/TMA flash attention (default), 0 = legacy mma.sync kernel */
+void b2s_attention_set_impl(int32_t impl);
+int b2s_attention_get_impl(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Whole-model entry points (the layer loops run in C++, one call per forward). */

@@ -169,11 +169,13 @@ int b2s_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
   return cast_bf16_to_f32(x, y, n, S(stream));
 }
 int b2s_attention_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
-                      const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t Hq, int32_t Hkv,
-                      int32_t D, float scale, int32_t causal, void* stream) {
-  return attention_fwd(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, Hq, Hkv, D, scale, causal,
-                       S(stream));
+                      const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int64_t total_rows, int32_t Hq,
+                      int32_t Hkv, int32_t D, float scale, int32_t causal, void* stream) {
+  return attention_fwd(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, D, scale,
+                       causal, S(stream));
 }
+void b2s_attention_set_impl(int32_t impl) { attention_set_impl(impl); }
+int b2s_attention_get_impl(void) { return attention_get_impl(); }
 
 int b2s_hubert_num_frames(const b2s_hubert_weights* w, int32_t samples, int32_t* frames, int32_t* pooled) {
   return hubert_num_frames(w, samples, frames, pooled);

@@ -1,0 +1,350 @@
+// attention_tc.cu -- packed variable-length flash attention forward on tcgen05 / TMEM / TMA (sm_100a).
+//
+// One CTA per (sequence, query head, 128-query block); 5 warps:
+//   warps 0-3 : softmax. Thread r owns query row r (TMEM lane r): it reads its row of S straight from TMEM
+//               (no cross-thread reductions), applies scale / length / causal masks, keeps the online-softmax state
+//               (running reference max m, running sum l) in registers, writes P = exp2(S - m) as bf16 into a
+//               128B-swizzled K-major shared-memory tile, and rescales O in TMEM only when the row max grew by more
+//               than 2^8 since the last rescale (lazy rescale; the decision is warp-uniform).
+//   warp 4    : lane 0 issues TMA loads (Q once, K/V double-buffered) and all tcgen05.mma:
+//               S[128 x 128 keys] = Q K^T   (A = Q smem K-major, B = K smem K-major, fp32 accumulators in TMEM cols [0,128))
+//               O[128 x D]       += P V      (A = P smem K-major, B = V smem MN-major, accumulators in TMEM cols [128,128+D))
+// Hand-offs are mbarriers (tcgen05.commit -> softmax, softmax -> MMA issuer); every wait is bounded.
+//
+// Covers HuBERT / Whisper (non-causal, D=64) and Llama / MiniChat (causal GQA, D=128); same C entry point and
+// semantics as attention.cu (TF/models/hubert/modeling_hubert.py:262-345, TF/models/llama/modeling_llama.py:225-289).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "b2s_common.cuh"
+#include "b2s_ptx.cuh"
+#include "ops.cuh"
+
+namespace b2s {
+
+int encode_map_2d_bf16(CUtensorMap* map, const void* base, unsigned long long cols, unsigned long long rows,
+                       unsigned long long row_stride_bytes, unsigned box_cols, unsigned box_rows);  // gemm_sm100.cu
+
+namespace {
+
+constexpr int kBM = 128;   // queries per CTA
+constexpr int kBN = 128;   // keys per step
+constexpr int kThreadsTc = 160;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+template <int D>
+struct AttnCfg {
+  static constexpr int kQBytes = kBM * D * 2;
+  static constexpr int kKBytes = kBN * D * 2;
+  static constexpr int kVBytes = kBN * D * 2;
+  static constexpr int kPBytes = kBM * kBN * 2;
+  static constexpr int kSmemBytes = kQBytes + 2 * (kKBytes + kVBytes) + kPBytes + 256 + 1024;
+  static constexpr int kTmemCols = 256;  // S: [0,128), O: [128, 128 + D)
+  static constexpr int kOCol = 128;
+};
+
+struct AttnParams {
+  const int* cu;
+  __nv_bfloat16* o;
+  long long ldo;
+  int Hq, Hkv;
+  int q_col0, k_col0, v_col0;  // first column of head 0 inside each tensor map
+  float scale_log2;
+  int causal;
+};
+
+// MN-major, 128B-swizzled B operand (V tile: rows = keys at 128 B pitch, 64-element column atoms `lbo` bytes apart)
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((1024 >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreadsTc, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using C = AttnCfg<D>;
+  constexpr int kAtoms = D / 64;  // 64-element (128 B) column atoms per row
+
+  const int seq = blockIdx.z, h = blockIdx.y;
+  const int s0 = p.cu[seq];
+  const int L = p.cu[seq + 1] - s0;
+  const int q0 = blockIdx.x * kBM;
+  if (q0 >= L) return;  // uniform for the CTA
+  const int hk = h / (p.Hq / p.Hkv);
+  const int kv_len = p.causal ? min(L, q0 + kBM) : L;
+  const int nblk = (kv_len + kBN - 1) / kBN;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + C::kQBytes;               // 2 stages
+  const uint32_t sV = sK + 2 * C::kKBytes;           // 2 stages
+  const uint32_t sP = sV + 2 * C::kVBytes;
+  const uint32_t bars = sP + C::kPBytes;
+  const uint32_t bar_q = bars, bar_kv0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40;
+  const uint32_t tmem_slot = bars + 48;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar_q, 1);
+    ptx::mbar_init(bar_kv0, 1);
+    ptx::mbar_init(bar_kv0 + 8, 1);
+    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(bar_p, kBM);
+    ptx::mbar_init(bar_o, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4) ptx::tmem_alloc<1>(tmem_slot, C::kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---------------- TMA + MMA issuer ----------------
+      ptx::prefetch_tmap(&tmap_q);
+      ptx::prefetch_tmap(&tmap_k);
+      ptx::prefetch_tmap(&tmap_v);
+      ptx::mbar_arrive_expect_tx(bar_q, C::kQBytes);
+#pragma unroll
+      for (int a = 0; a < kAtoms; ++a)
+        ptx::tma_load_2d(&tmap_q, bar_q, sQ + a * (kBM * 128), p.q_col0 + h * D + a * 64, s0 + q0);
+      auto load_kv = [&](int j) {
+        const int st = j & 1;
+        ptx::mbar_arrive_expect_tx(bar_kv0 + 8 * st, C::kKBytes + C::kVBytes);
+#pragma unroll
+        for (int a = 0; a < kAtoms; ++a) {
+          ptx::tma_load_2d(&tmap_k, bar_kv0 + 8 * st, sK + st * C::kKBytes + a * (kBN * 128),
+                           p.k_col0 + hk * D + a * 64, s0 + j * kBN);
+          ptx::tma_load_2d(&tmap_v, bar_kv0 + 8 * st, sV + st * C::kVBytes + a * (kBN * 128),
+                           p.v_col0 + hk * D + a * 64, s0 + j * kBN);
+        }
+      };
+      load_kv(0);
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16_f32(kBM, kBN);
+      constexpr uint32_t idesc_o = ptx::make_idesc_bf16_f32(kBM, D) | (1u << 16);  // B (= V) is MN-major
+      ptx::mbar_wait(bar_q, 0);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        if (j + 1 < nblk) {
+          // stage st^1 was last read by PV(j-1): refill it only after that MMA has retired
+          if (j >= 1) ptx::mbar_wait(bar_o, (j - 1) & 1);
+          load_kv(j + 1);
+        }
+        ptx::mbar_wait(bar_kv0 + 8 * st, (j >> 1) & 1);
+        ptx::tc_fence_after();
+        // S = Q K^T
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 2) * (kBM * 128) + (k & 3) * 32;
+          ptx::umma_bf16<1>(tmem_base, ptx::make_kmajor_sw128_desc(sQ + off),
+                            ptx::make_kmajor_sw128_desc(sK + st * C::kKBytes + off), idesc_s, k > 0 ? 1u : 0u);
+        }
+        ptx::umma_commit<1>(bar_s);
+        // O += P V once the softmax warps have published P (and finished reading S / rescaling O)
+        ptx::mbar_wait(bar_p, j & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kBN / 16; ++k) {
+          const uint64_t pdesc = ptx::make_kmajor_sw128_desc(sP + (k >> 2) * (kBM * 128) + (k & 3) * 32);
+          const uint64_t vdesc = make_mnmajor_sw128_desc(sV + st * C::kVBytes + k * 2048, kBN * 128);
+          ptx::umma_bf16<1>(tmem_base + C::kOCol, pdesc, vdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit<1>(bar_o);
+        // S(j+1) may now overwrite S (the softmax warps are done with it); P's smem and O are protected because
+        // bar_s(j+1) -- a tcgen05.commit -- only fires after every earlier MMA of this thread, PV(j) included.
+      }
+    }
+  } else {
+    // ---------------- softmax warps: thread = query row ----------------
+    const int r = warp * 32 + lane;
+    const int qi = q0 + r;  // sequence-local query index
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t tS = tmem_base + lane_base;
+    const uint32_t tO = tmem_base + lane_base + C::kOCol;
+    float m_ref = -INFINITY;  // reference max (log2 domain) the accumulated O / l are expressed against
+    float l_run = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      ptx::mbar_wait(bar_s, j & 1);
+      ptx::tc_fence_after();
+      const int kbase = j * kBN;
+      // pass 1: row max of the masked, scaled scores
+      float bm = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(tS + c * 32, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int key = kbase + c * 32 + i;
+          const bool ok = key < L && (!p.causal || key <= qi);
+          bm = fmaxf(bm, ok ? __uint_as_float(raw[i]) * p.scale_log2 : -INFINITY);
+        }
+      }
+      // lazy rescale of the running state (warp-uniform decision; rows past L never matter)
+      const bool grow = bm > m_ref + kRescaleThreshold || (m_ref == -INFINITY && bm > -INFINITY);
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? bm : m_ref;
+        const float alpha = (m_ref == -INFINITY) ? 0.f : ex2f(m_ref - m_new);
+        if (j > 0) {  // O holds data only after the first PV
+#pragma unroll 1
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t raw[32];
+            ptx::tmem_ld_32x32(tO + c * 32, raw);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * (grow ? alpha : 1.0f));
+            tmem_st_32x32(tO + c * 32, raw);
+          }
+          tmem_st_wait();
+        }
+        if (grow) {
+          l_run *= alpha;
+          m_ref = m_new;
+        }
+      }
+      // pass 2: P = exp2(s - m_ref) -> bf16 -> swizzled K-major smem tile; row sum
+      const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(tS + c * 32, raw);
+        ptx::tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const int key = kbase + c * 32 + i;
+          const bool ok0 = key < L && (!p.causal || key <= qi);
+          const bool ok1 = key + 1 < L && (!p.causal || key + 1 <= qi);
+          const float p0 = ok0 ? ex2f(fmaf(__uint_as_float(raw[i]), p.scale_log2, -mr)) : 0.f;
+          const float p1 = ok1 ? ex2f(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2, -mr)) : 0.f;
+          rs += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
+        }
+        // chunk c covers keys [32c, 32c+32) = 64 bytes = four 16-byte chunks of atom (c >> 1)
+        const uint32_t atom = sP + (c >> 1) * (kBM * 128) + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (c & 1) * 4 + q;
+          const uint32_t addr = atom + ((chunk ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                       "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                       : "memory");
+        }
+      }
+      l_run += rs;
+      // publish P to the async proxy (UMMA reads smem) and hand S / O back to the MMA issuer
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_p);
+    }
+    // epilogue: O / l -> bf16 -> global (one row per thread)
+    ptx::mbar_wait(bar_o, (nblk - 1) & 1);
+    ptx::tc_fence_after();
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    __nv_bfloat16* orow = p.o + static_cast<long long>(s0 + qi) * p.ldo + h * D;
+#pragma unroll 1
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t raw[32];
+      ptx::tmem_ld_32x32(tO + c * 32, raw);
+      ptx::tmem_ld_wait();
+      if (qi < L) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(raw[8 * q + 0]) * inv, __uint_as_float(raw[8 * q + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(raw[8 * q + 2]) * inv, __uint_as_float(raw[8 * q + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(raw[8 * q + 4]) * inv, __uint_as_float(raw[8 * q + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(raw[8 * q + 6]) * inv, __uint_as_float(raw[8 * q + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = u;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, C::kTmemCols);
+  }
+}
+
+template <int D>
+int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, const int* cu,
+                   int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, float scale, int causal,
+                   cudaStream_t stream) {
+  using C = AttnCfg<D>;
+  auto kern = attn_fwd_tc_kernel<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2S_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap tq, tk, tv;
+  int rc = encode_map_2d_bf16(&tq, q, static_cast<unsigned long long>(Hq) * D, total_rows, ld * 2, 64, kBM);
+  if (rc != B2S_OK) return rc;
+  rc = encode_map_2d_bf16(&tk, k, static_cast<unsigned long long>(Hkv) * D, total_rows, ld * 2, 64, kBN);
+  if (rc != B2S_OK) return rc;
+  rc = encode_map_2d_bf16(&tv, v, static_cast<unsigned long long>(Hkv) * D, total_rows, ld * 2, 64, kBN);
+  if (rc != B2S_OK) return rc;
+  AttnParams p{};
+  p.cu = cu;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.ldo = ldo;
+  p.Hq = Hq;
+  p.Hkv = Hkv;
+  p.q_col0 = p.k_col0 = p.v_col0 = 0;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = causal;
+  dim3 grid((max_seqlen + kBM - 1) / kBM, Hq, num_seqs);
+  kern<<<grid, kThreadsTc, C::kSmemBytes, stream>>>(tq, tk, tv, p);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+}  // namespace
+
+int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
+                     const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
+                     float scale, int causal, cudaStream_t stream) {
+  if (D == 64)
+    return launch_attn_tc<64>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, scale,
+                              causal, stream);
+  if (D == 128)
+    return launch_attn_tc<128>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, scale,
+                               causal, stream);
+  set_last_error("attention_fwd_tc: head_dim %d unsupported (64 or 128)", D);
+  return B2S_ERR_UNSUPPORTED;
+}
+
+}  // namespace b2s

@@ -514,6 +514,15 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const KParams& p, c
 
 }  // namespace
 
+// 2-D bf16 tensor map with the 128-byte swizzle (shared with attention_tc.cu)
+int encode_map_2d_bf16(CUtensorMap* map, const void* base, unsigned long long cols, unsigned long long rows,
+                       unsigned long long row_stride_bytes, unsigned box_cols, unsigned box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  return encode_map(map, base, 2, dims, strides, box);
+}
+
 // Optional per-launch timing of this kernel (bench.py's roofline leg): CUDA events on the launching stream
 // around every GEMM launch while enabled.
 void gemm_timing_enable(int on) {

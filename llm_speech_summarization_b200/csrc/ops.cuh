@@ -55,8 +55,11 @@ int cast_bf16_to_f32(const void* x, float* y, long long n, cudaStream_t stream);
 // Packed variable-length attention. q/k/v are bf16 views into one [rows, ld] buffer (fused QKV output):
 // head h of row r lives at base + r*ld + h*D. Sequences are rows [cu[s], cu[s+1]).
 // GQA: query head h uses kv head h / (Hq / Hkv). Output o bf16 [rows, Hq*D].
+// total_rows = rows of the packed buffers (the TMA tensor maps zero-fill beyond it).
 int attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
-                  const int* cu_seqlens, int num_seqs, int max_seqlen, int Hq, int Hkv, int D, float scale, int causal,
-                  cudaStream_t stream);
+                  const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
+                  float scale, int causal, cudaStream_t stream);
+void attention_set_impl(int impl);  // 1 = tcgen05 kernel (default), 0 = legacy mma.sync kernel
+int attention_get_impl();
 
 }  // namespace b2s

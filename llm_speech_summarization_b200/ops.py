@@ -159,8 +159,8 @@ def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, Hq: 
     o = torch.empty(rows, Hq * D, device=qkv.device, dtype=torch.bfloat16)
     base = qkv.data_ptr()
     _lib.check(_lib.load().b2s_attention_fwd(base, base + 2 * Hq * D, base + 2 * (Hq + Hkv) * D, ld, o.data_ptr(),
-                                             Hq * D, cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, max_seqlen, Hq,
-                                             Hkv, D, scale, int(causal), _stream()), "attention")
+                                             Hq * D, cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, max_seqlen, rows,
+                                             Hq, Hkv, D, scale, int(causal), _stream()), "attention")
     return o
 
 
@@ -206,6 +206,11 @@ def kd_ce_loss_bwd(student: torch.Tensor, teacher: torch.Tensor, labels: torch.T
                                               res.lse_t.data_ptr(), res.coef_kd.data_ptr(), res.coef_ce.data_ptr(),
                                               out.data_ptr(), out.stride(0), _stream()), "kd_ce_loss_bwd")
     return out
+
+
+def attention_set_impl(impl: int) -> None:
+    """1 = tcgen05 kernel (default), 0 = legacy mma.sync kernel (A/B tests only)."""
+    _lib.load().b2s_attention_set_impl(int(impl))
 
 
 def launch_count() -> int:

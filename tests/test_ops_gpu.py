@@ -149,8 +149,21 @@ def _attn_ref(qkv, cu, Hq, Hkv, D, scale, causal):
     (24, 8, 128, True, [200, 117, 1, 64, 129]),
     (24, 24, 128, True, [136, 400]),
     (4, 2, 128, False, [77]),
+    (16, 16, 64, False, [1500]),
+    (2, 1, 128, True, [128, 256, 257, 383]),
+    (2, 2, 64, True, [300, 5]),
 ])
-def test_attention(cuda, Hq, Hkv, D, causal, lens):
+@pytest.mark.parametrize("impl", [1, 0], ids=["tcgen05", "mma_sync"])
+def test_attention(cuda, Hq, Hkv, D, causal, lens, impl):
+    from llm_speech_summarization_b200 import ops
+    ops.attention_set_impl(impl)
+    try:
+        _run_attention_case(cuda, Hq, Hkv, D, causal, lens)
+    finally:
+        ops.attention_set_impl(1)
+
+
+def _run_attention_case(cuda, Hq, Hkv, D, causal, lens):
     from llm_speech_summarization_b200 import ops
     g = torch.Generator().manual_seed(sum(lens) + D)
     rows = sum(lens)

@@ -73,8 +73,28 @@ def bench_loss(rows, V):
                       "bwd_gbs": round(6 * rows * V / msb / 1e6, 1)}), flush=True)
 
 
+def bench_attn(label, lens, Hq, Hkv, D, causal):
+    import math
+    dev = torch.device("cuda")
+    rows = sum(lens)
+    qkv = torch.randn(rows, (Hq + 2 * Hkv) * D, device=dev).to(torch.bfloat16)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
+    flops = sum(4 * L * L * Hq * D * (0.5 if causal else 1.0) for L in lens)
+    for impl, name in ((1, "tcgen05"), (0, "mma_sync")):
+        ops.attention_set_impl(impl)
+        ms = time_fn(lambda: ops.attention(qkv, cu, max(lens), Hq, Hkv, D, 1.0 / math.sqrt(D), causal), iters=20)
+        print(json.dumps({"kernel": "attention", "label": label, "impl": name, "ms": round(ms, 4),
+                          "tflops": round(flops / ms / 1e9, 1)}), flush=True)
+    ops.attention_set_impl(1)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "attn"):
+        bench_attn("hubert_b32", [499] * 32, 16, 16, 64, False)
+        bench_attn("whisper_b8", [1500] * 8, 16, 16, 64, False)
+        bench_attn("llama_b32_student+teacher", [200] * 32 + [117] * 32, 24, 8, 128, True)
+        bench_attn("minichat_b8_L400", [400] * 8, 24, 24, 128, True)
     if which in ("all", "loss"):  # before the GEMMs heat the part up (the loss kernel is SM-clock sensitive)
         for rows in (64, 2048):
             bench_loss(rows, 128256)
