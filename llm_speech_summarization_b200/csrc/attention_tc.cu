@@ -2,10 +2,10 @@
 //
 // One CTA per (sequence, query head, 128-query block); 5 warps:
 //   warps 0-3 : softmax. Thread r owns query row r (TMEM lane r): it reads its row of S straight from TMEM
-//               (no cross-thread reductions), applies scale / length / causal masks, keeps the online-softmax state
-//               (running reference max m, running sum l) in registers, writes P = exp2(S - m) as bf16 into a
-//               128B-swizzled K-major shared-memory tile, and rescales O in TMEM only when the row max grew by more
-//               than 2^8 since the last rescale (lazy rescale; the decision is warp-uniform).
+//               (no cross-thread reductions) ONCE per block, masks only in partial / diagonal blocks, keeps the
+//               online-softmax state (reference max m, running sum l) in registers, writes P = exp2(S - m) as bf16
+//               into a 128B-swizzled K-major shared-memory tile, and moves the reference (rescaling O in TMEM) only
+//               when the row max outgrew it by 2^16 (lazy, deferred, warp-uniform).
 //   warp 4    : lane 0 issues TMA loads (Q once, K/V double-buffered) and all tcgen05.mma:
 //               S[128 x 128 keys] = Q K^T   (A = Q smem K-major, B = K smem K-major, fp32 accumulators in TMEM cols [0,128))
 //               O[128 x D]       += P V      (A = P smem K-major, B = V smem MN-major, accumulators in TMEM cols [128,128+D))
@@ -30,7 +30,6 @@ namespace {
 constexpr int kBM = 128;   // queries per CTA
 constexpr int kBN = 128;   // keys per step
 constexpr int kThreadsTc = 160;
-constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 template <int D>
 struct AttnCfg {
@@ -38,7 +37,10 @@ struct AttnCfg {
   static constexpr int kKBytes = kBN * D * 2;
   static constexpr int kVBytes = kBN * D * 2;
   static constexpr int kPBytes = kBM * kBN * 2;
-  static constexpr int kSmemBytes = kQBytes + 2 * (kKBytes + kVBytes) + kPBytes + 256 + 1024;
+  // D = 64: single-buffered K/V keeps the CTA at ~81 KiB so two CTAs (2 x 256 TMEM columns) share an SM and overlap
+  // each other's TMA / MMA / softmax phases; D = 128: one CTA per SM, K/V double-buffered inside it.
+  static constexpr int kKvStages = (D == 64) ? 1 : 2;
+  static constexpr int kSmemBytes = kQBytes + kKvStages * (kKBytes + kVBytes) + kPBytes + 256 + 1024;
   static constexpr int kTmemCols = 256;  // S: [0,128), O: [128, 128 + D)
   static constexpr int kOCol = 128;
 };
@@ -102,9 +104,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
-  const uint32_t sK = sQ + C::kQBytes;               // 2 stages
-  const uint32_t sV = sK + 2 * C::kKBytes;           // 2 stages
-  const uint32_t sP = sV + 2 * C::kVBytes;
+  constexpr int kKvStages = C::kKvStages;
+  const uint32_t sK = sQ + C::kQBytes;
+  const uint32_t sV = sK + kKvStages * C::kKBytes;
+  const uint32_t sP = sV + kKvStages * C::kVBytes;
   const uint32_t bars = sP + C::kPBytes;
   const uint32_t bar_q = bars, bar_kv0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40;
   const uint32_t tmem_slot = bars + 48;
@@ -137,7 +140,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       for (int a = 0; a < kAtoms; ++a)
         ptx::tma_load_2d(&tmap_q, bar_q, sQ + a * (kBM * 128), p.q_col0 + h * D + a * 64, s0 + q0);
       auto load_kv = [&](int j) {
-        const int st = j & 1;
+        const int st = j % kKvStages;
         ptx::mbar_arrive_expect_tx(bar_kv0 + 8 * st, C::kKBytes + C::kVBytes);
 #pragma unroll
         for (int a = 0; a < kAtoms; ++a) {
@@ -152,13 +155,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       constexpr uint32_t idesc_o = ptx::make_idesc_bf16_f32(kBM, D) | (1u << 16);  // B (= V) is MN-major
       ptx::mbar_wait(bar_q, 0);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        if (j + 1 < nblk) {
+        const int st = j % kKvStages;
+        if (kKvStages == 2 && j + 1 < nblk) {
           // stage st^1 was last read by PV(j-1): refill it only after that MMA has retired
           if (j >= 1) ptx::mbar_wait(bar_o, (j - 1) & 1);
           load_kv(j + 1);
         }
-        ptx::mbar_wait(bar_kv0 + 8 * st, (j >> 1) & 1);
+        ptx::mbar_wait(bar_kv0 + 8 * st, (j / kKvStages) & 1);
         ptx::tc_fence_after();
         // S = Q K^T
 #pragma unroll
@@ -178,6 +181,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           ptx::umma_bf16<1>(tmem_base + C::kOCol, pdesc, vdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         }
         ptx::umma_commit<1>(bar_o);
+        if (kKvStages == 1 && j + 1 < nblk) {  // single buffer: refill once PV(j) has retired
+          ptx::mbar_wait(bar_o, j & 1);
+          load_kv(j + 1);
+        }
         // S(j+1) may now overwrite S (the softmax warps are done with it); P's smem and O are protected because
         // bar_s(j+1) -- a tcgen05.commit -- only fires after every earlier MMA of this thread, PV(j) included.
       }
@@ -189,79 +196,110 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     const uint32_t tS = tmem_base + lane_base;
     const uint32_t tO = tmem_base + lane_base + C::kOCol;
-    float m_ref = -INFINITY;  // reference max (log2 domain) the accumulated O / l are expressed against
+    const int row_limit = p.causal ? min(L, qi + 1) : L;  // this row sees keys [0, row_limit)
+    const float sc = p.scale_log2;                         // > 0
+    float m_ref = -INFINITY;  // log2-domain reference the accumulated O / l are expressed against
+    float pend = -INFINITY;   // larger reference to adopt at the next safe point (no PV in flight)
     float l_run = 0.f;
-    for (int j = 0; j < nblk; ++j) {
-      ptx::mbar_wait(bar_s, j & 1);
-      ptx::tc_fence_after();
-      const int kbase = j * kBN;
-      // pass 1: row max of the masked, scaled scores
-      float bm = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(tS + c * 32, raw);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int key = kbase + c * 32 + i;
-          const bool ok = key < L && (!p.causal || key <= qi);
-          bm = fmaxf(bm, ok ? __uint_as_float(raw[i]) * p.scale_log2 : -INFINITY);
-        }
-      }
-      // lazy rescale of the running state (warp-uniform decision; rows past L never matter)
-      const bool grow = bm > m_ref + kRescaleThreshold || (m_ref == -INFINITY && bm > -INFINITY);
-      if (__any_sync(0xffffffffu, grow)) {
-        const float m_new = grow ? bm : m_ref;
-        const float alpha = (m_ref == -INFINITY) ? 0.f : ex2f(m_ref - m_new);
-        if (j > 0) {  // O holds data only after the first PV
+
+    // adopt `pend` as the new reference where it is larger: rescale l (registers) and O (TMEM); warp-uniform
+    auto adopt = [&](bool o_valid) {
+      const bool need = pend > m_ref;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? ((m_ref == -INFINITY) ? 0.f : ex2f(m_ref - pend)) : 1.0f;
+        if (o_valid) {
 #pragma unroll 1
           for (int c = 0; c < D / 32; ++c) {
             uint32_t raw[32];
             ptx::tmem_ld_32x32(tO + c * 32, raw);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * (grow ? alpha : 1.0f));
+            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
             tmem_st_32x32(tO + c * 32, raw);
           }
           tmem_st_wait();
         }
-        if (grow) {
+        if (need) {
           l_run *= alpha;
-          m_ref = m_new;
+          m_ref = pend;
         }
       }
-      // pass 2: P = exp2(s - m_ref) -> bf16 -> swizzled K-major smem tile; row sum
-      const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;
-      float rs = 0.f;
+    };
+
+    for (int j = 0; j < nblk; ++j) {
+      ptx::mbar_wait(bar_s, j & 1);  // S(j) is in TMEM; every earlier MMA (PV(j-1) included) has retired
+      ptx::tc_fence_after();
+      const int nvis = row_limit - j * kBN;  // visible keys of this row inside this block (<= 0 .. >= 128)
+      const bool full_blk = __all_sync(0xffffffffu, nvis >= kBN);
+      if (j == 0) {
+        // first block: exact masked row max as the initial reference (nothing accumulated yet)
+        float bm = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(tS + c * 32, raw);
-        ptx::tmem_ld_wait();
-        uint32_t pk[16];
+        for (int c = 0; c < kBN / 32; ++c) {
+          uint32_t raw[32];
+          ptx::tmem_ld_32x32(tS + c * 32, raw);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const int key = kbase + c * 32 + i;
-          const bool ok0 = key < L && (!p.causal || key <= qi);
-          const bool ok1 = key + 1 < L && (!p.causal || key + 1 <= qi);
-          const float p0 = ok0 ? ex2f(fmaf(__uint_as_float(raw[i]), p.scale_log2, -mr)) : 0.f;
-          const float p1 = ok1 ? ex2f(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2, -mr)) : 0.f;
-          rs += p0 + p1;
-          pk[i >> 1] = pack_bf16(p0, p1);
+          for (int i = 0; i < 32; ++i) bm = fmaxf(bm, (c * 32 + i < nvis) ? __uint_as_float(raw[i]) : -INFINITY);
         }
-        // chunk c covers keys [32c, 32c+32) = 64 bytes = four 16-byte chunks of atom (c >> 1)
-        const uint32_t atom = sP + (c >> 1) * (kBM * 128) + r * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (c & 1) * 4 + q;
-          const uint32_t addr = atom + ((chunk ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
-                       "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                       : "memory");
-        }
+        pend = bm * sc;
       }
-      l_run += rs;
+      // Single pass per block against the (possibly stale) reference: P = exp2(s*sc - m_ref) may exceed 1, which
+      // fp32 / bf16 absorb; the reference is only moved when the block max outgrew it by 2^16 (deferred to the
+      // next block, when no PV is in flight) or, to rule out overflow, immediately by re-running the block (> 2^60).
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        adopt(j > 0);
+        const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;
+        float rs = 0.f, bmax = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < kBN / 32; ++c) {
+          uint32_t raw[32];
+          ptx::tmem_ld_32x32(tS + c * 32, raw);
+          ptx::tmem_ld_wait();
+          uint32_t pk[16];
+          if (full_blk) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float x0 = __uint_as_float(raw[i]), x1 = __uint_as_float(raw[i + 1]);
+              bmax = fmaxf(bmax, fmaxf(x0, x1));
+              const float p0 = ex2f(fmaf(x0, sc, -mr)), p1 = ex2f(fmaf(x1, sc, -mr));
+              rs += p0 + p1;
+              pk[i >> 1] = pack_bf16(p0, p1);
+            }
+          } else {
+            const int nv = nvis - c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float x0 = __uint_as_float(raw[i]), x1 = __uint_as_float(raw[i + 1]);
+              const bool ok0 = i < nv, ok1 = i + 1 < nv;
+              bmax = fmaxf(bmax, fmaxf(ok0 ? x0 : -INFINITY, ok1 ? x1 : -INFINITY));
+              const float p0 = ok0 ? ex2f(fmaf(x0, sc, -mr)) : 0.f;
+              const float p1 = ok1 ? ex2f(fmaf(x1, sc, -mr)) : 0.f;
+              rs += p0 + p1;
+              pk[i >> 1] = pack_bf16(p0, p1);
+            }
+          }
+          // chunk c covers keys [32c, 32c+32) = 64 bytes = four 16-byte chunks of atom (c >> 1)
+          const uint32_t atom = sP + (c >> 1) * (kBM * 128) + r * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = (c & 1) * 4 + q;
+            const uint32_t addr = atom + ((chunk ^ (r & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                         "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                         : "memory");
+          }
+        }
+        const float bm = bmax * sc;
+        const bool overflow_risk = bm > m_ref + 60.0f;
+        if (attempt == 0 && __any_sync(0xffffffffu, overflow_risk)) {
+          if (overflow_risk) pend = bm;
+          continue;  // adopt now and redo this block (P in smem is simply rewritten; nothing has consumed it)
+        }
+        l_run += rs;
+        if (bm > m_ref + 16.0f) pend = bm;
+        break;
+      }
       // publish P to the async proxy (UMMA reads smem) and hand S / O back to the MMA issuer
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
