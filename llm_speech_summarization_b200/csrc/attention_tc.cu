@@ -28,20 +28,20 @@ int encode_map_2d_bf16(CUtensorMap* map, const void* base, unsigned long long co
 namespace {
 
 constexpr int kBM = 128;   // queries per CTA
-constexpr int kBN = 128;   // keys per step
 constexpr int kThreadsTc = 160;
 
-template <int D>
+// BN = keys per step (128, or 64 for short sequences at D = 128 so that two CTAs fit on an SM)
+template <int D, int BN>
 struct AttnCfg {
   static constexpr int kQBytes = kBM * D * 2;
-  static constexpr int kKBytes = kBN * D * 2;
-  static constexpr int kVBytes = kBN * D * 2;
-  static constexpr int kPBytes = kBM * kBN * 2;
+  static constexpr int kKBytes = BN * D * 2;
+  static constexpr int kVBytes = BN * D * 2;
+  static constexpr int kPBytes = kBM * BN * 2;
   // D = 64: single-buffered K/V keeps the CTA at ~81 KiB so two CTAs (2 x 256 TMEM columns) share an SM and overlap
   // each other's TMA / MMA / softmax phases; D = 128: one CTA per SM, K/V double-buffered inside it.
-  static constexpr int kKvStages = (D == 64) ? 1 : 2;
+  static constexpr int kKvStages = (D == 64 || BN == 64) ? 1 : 2;
   static constexpr int kSmemBytes = kQBytes + kKvStages * (kKBytes + kVBytes) + kPBytes + 256 + 1024;
-  static constexpr int kTmemCols = 256;  // S: [0,128), O: [128, 128 + D)
+  static constexpr int kTmemCols = 256;  // S: [0, BN), O: [128, 128 + D)
   static constexpr int kOCol = 128;
 };
 
@@ -85,11 +85,12 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-template <int D>
+template <int D, int BN>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  using C = AttnCfg<D>;
+  using C = AttnCfg<D, BN>;
+  constexpr int kBN = BN;
   constexpr int kAtoms = D / 64;  // 64-element (128 B) column atoms per row
 
   const int seq = blockIdx.z, h = blockIdx.y;
@@ -166,9 +167,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         // S = Q K^T
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k >> 2) * (kBM * 128) + (k & 3) * 32;
-          ptx::umma_bf16<1>(tmem_base, ptx::make_kmajor_sw128_desc(sQ + off),
-                            ptx::make_kmajor_sw128_desc(sK + st * C::kKBytes + off), idesc_s, k > 0 ? 1u : 0u);
+          const uint32_t q_off = (k >> 2) * (kBM * 128) + (k & 3) * 32;  // 64-column atoms are kBM rows tall
+          const uint32_t k_off = (k >> 2) * (kBN * 128) + (k & 3) * 32;  // ... and kBN rows tall for K
+          ptx::umma_bf16<1>(tmem_base, ptx::make_kmajor_sw128_desc(sQ + q_off),
+                            ptx::make_kmajor_sw128_desc(sK + st * C::kKBytes + k_off), idesc_s, k > 0 ? 1u : 0u);
         }
         ptx::umma_commit<1>(bar_s);
         // O += P V once the softmax warps have published P (and finished reading S / rescaling O)
@@ -337,12 +339,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   }
 }
 
-template <int D>
+template <int D, int BN>
 int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, const int* cu,
                    int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, float scale, int causal,
                    cudaStream_t stream) {
-  using C = AttnCfg<D>;
-  auto kern = attn_fwd_tc_kernel<D>;
+  using C = AttnCfg<D, BN>;
+  constexpr int kBN = BN;
+  auto kern = attn_fwd_tc_kernel<D, BN>;
   static bool attr_set = false;
   if (!attr_set) {
     B2S_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -376,11 +379,14 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld_q
                      const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
                      float scale, int causal, cudaStream_t stream) {
   if (D == 64)
-    return launch_attn_tc<64>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, scale,
-                              causal, stream);
+    return launch_attn_tc<64, 128>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv,
+                                   scale, causal, stream);
+  if (D == 128 && max_seqlen <= 512)  // short prompts: per-CTA latency dominates -> two CTAs per SM
+    return launch_attn_tc<128, 64>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv,
+                                   scale, causal, stream);
   if (D == 128)
-    return launch_attn_tc<128>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, scale,
-                               causal, stream);
+    return launch_attn_tc<128, 128>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv,
+                                    scale, causal, stream);
   set_last_error("attention_fwd_tc: head_dim %d unsupported (64 or 128)", D);
   return B2S_ERR_UNSUPPORTED;
 }
