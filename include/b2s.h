@@ -128,7 +128,16 @@ int b2s_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
  * TF/models/llama/modeling_llama.py:225-289). */
 int b2s_attention_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
                       const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int64_t total_rows, int32_t Hq,
-                      int32_t Hkv, int32_t D, float scale, int32_t causal, void* stream);
+                      int32_t Hkv, int32_t D, float scale, int32_t causal, float* lse /* optional [rows, Hq] */,
+                      void* stream);
+/* Backward of b2s_attention_fwd (autograd through HubertAttention / LlamaAttention, REF/trainer.py:373-374).
+ * lse: the forward's saved log-sum-exp; delta_ws: fp32 [rows, Hq] scratch; dq/dk/dv: bf16, row stride ld_dqkv;
+ * rope_cs (optional): fuses the inverse rotary rotation into the dq / dk stores. */
+int b2s_attention_bwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const void* o, int64_t ld_o,
+                      const void* dout, int64_t ld_do, const float* lse, float* delta_ws, void* dq, void* dk, void* dv,
+                      int64_t ld_dqkv, const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen,
+                      int64_t total_rows, int32_t Hq, int32_t Hkv, int32_t D, float scale, int32_t causal,
+                      const float* rope_cs, void* stream);
 /* kernel selection for A/B tests: 1 = tcgen05/TMEM/TMA flash attention (default), 0 = legacy mma.sync kernel */
 void b2s_attention_set_impl(int32_t impl);
 int b2s_attention_get_impl(void);

@@ -96,7 +96,10 @@ PROTOTYPES = {
     "b2s_cast_f32_to_bf16": (c_int, [P_f32, c_void_p, c_int64, c_void_p]),
     "b2s_cast_bf16_to_f32": (c_int, [c_void_p, P_f32, c_int64, c_void_p]),
     "b2s_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, P_int, c_int, c_int,
-                                  c_int64, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+                                  c_int64, c_int, c_int, c_int, c_float, c_int, P_f32, c_void_p]),
+    "b2s_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, P_f32,
+                                  P_f32, c_void_p, c_void_p, c_void_p, c_int64, P_int, c_int, c_int, c_int64, c_int,
+                                  c_int, c_int, c_float, c_int, P_f32, c_void_p]),
     "b2s_attention_set_impl": (None, [c_int]),
     "b2s_attention_get_impl": (c_int, []),
     "b2s_hubert_num_frames": (c_int, [C.POINTER(HubertWeights), c_int, C.POINTER(c_int), C.POINTER(c_int)]),

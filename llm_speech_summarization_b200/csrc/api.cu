@@ -170,9 +170,17 @@ int b2s_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
 }
 int b2s_attention_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
                       const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int64_t total_rows, int32_t Hq,
-                      int32_t Hkv, int32_t D, float scale, int32_t causal, void* stream) {
+                      int32_t Hkv, int32_t D, float scale, int32_t causal, float* lse, void* stream) {
   return attention_fwd(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, D, scale,
-                       causal, S(stream));
+                       causal, lse, S(stream));
+}
+int b2s_attention_bwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const void* o, int64_t ld_o,
+                      const void* dout, int64_t ld_do, const float* lse, float* delta_ws, void* dq, void* dk, void* dv,
+                      int64_t ld_dqkv, const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen,
+                      int64_t total_rows, int32_t Hq, int32_t Hkv, int32_t D, float scale, int32_t causal,
+                      const float* rope_cs, void* stream) {
+  return attention_bwd(q, k, v, ld_qkv, o, ld_o, dout, ld_do, lse, delta_ws, dq, dk, dv, ld_dqkv, cu_seqlens, num_seqs,
+                       max_seqlen, total_rows, Hq, Hkv, D, scale, causal, rope_cs, S(stream));
 }
 void b2s_attention_set_impl(int32_t impl) { attention_set_impl(impl); }
 int b2s_attention_get_impl(void) { return attention_get_impl(); }

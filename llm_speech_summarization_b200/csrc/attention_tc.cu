@@ -53,6 +53,7 @@ struct AttnParams {
   int q_col0, k_col0, v_col0;  // first column of head 0 inside each tensor map
   float scale_log2;
   int causal;
+  float* lse;  // optional [rows, Hq]: log2-domain log-sum-exp of the scaled scores (saved for the backward)
 };
 
 // MN-major, 128B-swizzled B operand (V tile: rows = keys at 128 B pitch, 64-element column atoms `lbo` bytes apart)
@@ -311,6 +312,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     ptx::mbar_wait(bar_o, (nblk - 1) & 1);
     ptx::tc_fence_after();
     const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    if (p.lse != nullptr && qi < L) p.lse[static_cast<long long>(s0 + qi) * p.Hq + h] = m_ref + log2f(l_run);
     __nv_bfloat16* orow = p.o + static_cast<long long>(s0 + qi) * p.ldo + h * D;
 #pragma unroll 1
     for (int c = 0; c < D / 32; ++c) {
@@ -342,7 +344,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 template <int D, int BN>
 int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, const int* cu,
                    int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, float scale, int causal,
-                   cudaStream_t stream) {
+                   float* lse, cudaStream_t stream) {
   using C = AttnCfg<D, BN>;
   constexpr int kBN = BN;
   auto kern = attn_fwd_tc_kernel<D, BN>;
@@ -367,6 +369,7 @@ int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, vo
   p.q_col0 = p.k_col0 = p.v_col0 = 0;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
+  p.lse = lse;
   dim3 grid((max_seqlen + kBM - 1) / kBM, Hq, num_seqs);
   kern<<<grid, kThreadsTc, C::kSmemBytes, stream>>>(tq, tk, tv, p);
   B2S_LAUNCH_CHECK();
@@ -377,16 +380,16 @@ int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, vo
 
 int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
                      const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
-                     float scale, int causal, cudaStream_t stream) {
+                     float scale, int causal, float* lse, cudaStream_t stream) {
   if (D == 64)
     return launch_attn_tc<64, 128>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv,
-                                   scale, causal, stream);
+                                   scale, causal, lse, stream);
   if (D == 128 && max_seqlen <= 512)  // short prompts: per-CTA latency dominates -> two CTAs per SM
     return launch_attn_tc<128, 64>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv,
-                                   scale, causal, stream);
+                                   scale, causal, lse, stream);
   if (D == 128)
     return launch_attn_tc<128, 128>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv,
-                                    scale, causal, stream);
+                                    scale, causal, lse, stream);
   set_last_error("attention_fwd_tc: head_dim %d unsupported (64 or 128)", D);
   return B2S_ERR_UNSUPPORTED;
 }

@@ -126,7 +126,7 @@ int encoder_stack(const b2s_encoder_layer* layers, int num_layers, int H, int F,
     {
       const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(qkv_buf);
       rc = attention_fwd(qkv, qkv + H, qkv + 2 * H, 3 * H, ao, H, cu, B, frames, rows, heads, heads, 64, 0.125f, 0,
-                         stream);
+                         nullptr, stream);
       if (rc != B2S_OK) return rc;
     }
     {
@@ -525,7 +525,7 @@ int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_
     {
       const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(pl.qkv);
       rc = attention_fwd(qkv, qkv + Hq * D, qkv + (Hq + Hkv) * D, qkv_cols, pl.ao, Hq * D, cu_seqlens, num_seqs,
-                         max_seqlen, rows, Hq, Hkv, D, scale, 1, stream);
+                         max_seqlen, rows, Hq, Hkv, D, scale, 1, nullptr, stream);
       if (rc != B2S_OK) return rc;
     }
     {

@@ -58,7 +58,14 @@ int cast_bf16_to_f32(const void* x, float* y, long long n, cudaStream_t stream);
 // total_rows = rows of the packed buffers (the TMA tensor maps zero-fill beyond it).
 int attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
                   const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
-                  float scale, int causal, cudaStream_t stream);
+                  float scale, int causal, float* lse /* optional [rows, Hq] */, cudaStream_t stream);
+// Backward of attention_fwd. lse = the forward's saved log-sum-exp; delta_ws = fp32 [rows, Hq] scratch.
+// dq / dk / dv are bf16 views with row stride ld_dqkv (head h at column h*D). rope_cs (optional, [npos, D]) fuses
+// the inverse rotary rotation into the dq / dk stores (positions = row index inside its sequence).
+int attention_bwd(const void* q, const void* k, const void* v, long long ld_qkv, const void* o, long long ld_o,
+                  const void* dout, long long ld_do, const float* lse, float* delta_ws, void* dq, void* dk, void* dv,
+                  long long ld_dqkv, const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq,
+                  int Hkv, int D, float scale, int causal, const float* rope_cs, cudaStream_t stream);
 void attention_set_impl(int impl);  // 1 = tcgen05 kernel (default), 0 = legacy mma.sync kernel
 int attention_get_impl();
 

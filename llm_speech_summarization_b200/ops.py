@@ -151,17 +151,35 @@ def posconv_weight_pack(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
 
 
 def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, Hq: int, Hkv: int, D: int, scale: float,
-              causal: bool) -> torch.Tensor:
-    """qkv bf16 [rows, (Hq+2Hkv)*D] (q | k | v) -> o bf16 [rows, Hq*D]."""
+              causal: bool, return_lse: bool = False):
+    """qkv bf16 [rows, (Hq+2Hkv)*D] (q | k | v) -> o bf16 [rows, Hq*D] (and the fp32 [rows, Hq] log2-domain lse)."""
     _need_cuda(qkv, cu_seqlens)
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and cu_seqlens.dtype == torch.int32
     rows, ld = qkv.shape
     o = torch.empty(rows, Hq * D, device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(rows, Hq, device=qkv.device, dtype=torch.float32) if return_lse else None
     base = qkv.data_ptr()
     _lib.check(_lib.load().b2s_attention_fwd(base, base + 2 * Hq * D, base + 2 * (Hq + Hkv) * D, ld, o.data_ptr(),
                                              Hq * D, cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, max_seqlen, rows,
-                                             Hq, Hkv, D, scale, int(causal), _stream()), "attention")
-    return o
+                                             Hq, Hkv, D, scale, int(causal), _ptr(lse), _stream()), "attention")
+    return (o, lse) if return_lse else o
+
+
+def attention_bwd(qkv: torch.Tensor, o: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, cu_seqlens: torch.Tensor,
+                  max_seqlen: int, Hq: int, Hkv: int, D: int, scale: float, causal: bool,
+                  rope_cs: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Backward of attention(): returns dqkv bf16 [rows, (Hq+2Hkv)*D] in the same q | k | v column layout."""
+    _need_cuda(qkv, o, dout, lse, cu_seqlens, rope_cs)
+    rows, ld = qkv.shape
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(rows, Hq, device=qkv.device, dtype=torch.float32)
+    b, db = qkv.data_ptr(), dqkv.data_ptr()
+    _lib.check(_lib.load().b2s_attention_bwd(b, b + 2 * Hq * D, b + 2 * (Hq + Hkv) * D, ld, o.data_ptr(), o.stride(0),
+                                             dout.data_ptr(), dout.stride(0), lse.data_ptr(), delta.data_ptr(), db,
+                                             db + 2 * Hq * D, db + 2 * (Hq + Hkv) * D, ld, cu_seqlens.data_ptr(),
+                                             cu_seqlens.numel() - 1, max_seqlen, rows, Hq, Hkv, D, scale, int(causal),
+                                             _ptr(rope_cs), _stream()), "attention_bwd")
+    return dqkv
 
 
 class KdCeResult:

@@ -176,3 +176,39 @@ def _run_attention_case(cuda, Hq, Hkv, D, causal, lens):
     o = ops.attention(qkv, cu_t, max(lens), Hq, Hkv, D, scale, causal)
     ref = _attn_ref(qkv, cu, Hq, Hkv, D, scale, causal)
     assert rel_l2(o.float(), ref) < 6e-3  # P is rounded to bf16 before P.V, output rounded to bf16
+
+
+@pytest.mark.parametrize("Hq,Hkv,D,causal,lens", [
+    (16, 16, 64, False, [499, 130]),
+    (4, 4, 64, False, [1, 63, 64, 65]),
+    (24, 8, 128, True, [200, 117, 1, 64, 129]),
+    (6, 6, 128, True, [136, 300]),
+    (4, 2, 64, True, [77, 200]),
+])
+def test_attention_backward(cuda, Hq, Hkv, D, causal, lens):
+    """dQ / dK / dV of the packed attention vs autograd through fp32 SDPA on the same bf16 inputs."""
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(sum(lens) * D + Hq)
+    rows = sum(lens)
+    qkv = (torch.randn(rows, (Hq + 2 * Hkv) * D, generator=g) * 0.7).to(torch.bfloat16).to(cuda)
+    dout = torch.randn(rows, Hq * D, generator=g).to(torch.bfloat16).to(cuda)
+    cu = [0]
+    for L in lens:
+        cu.append(cu[-1] + L)
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=cuda)
+    scale = 1.0 / math.sqrt(D)
+    o, lse = ops.attention(qkv, cu_t, max(lens), Hq, Hkv, D, scale, causal, return_lse=True)
+    dqkv = ops.attention_bwd(qkv, o, dout, lse, cu_t, max(lens), Hq, Hkv, D, scale, causal)
+    x = qkv.float().requires_grad_(True)
+    ref = _attn_ref(x, cu, Hq, Hkv, D, scale, causal)
+    ref.backward(dout.float())
+    # lse sanity: natural-log lse of the scaled scores = lse2 * ln 2
+    q, k, _ = qkv.float().split([Hq * D, Hkv * D, Hkv * D], dim=1)
+    a, b = cu[0], cu[1]
+    s = (q[a:b].view(b - a, Hq, D).transpose(0, 1) @ k[a:b].view(b - a, Hkv, D).transpose(0, 1).repeat_interleave(
+        Hq // Hkv, 0).transpose(1, 2)) * scale
+    if causal:
+        s = s.masked_fill(~torch.ones(b - a, b - a, dtype=torch.bool, device=cuda).tril(), float("-inf"))
+    assert torch.allclose(lse[a:b].t() * math.log(2.0), torch.logsumexp(s, -1), atol=2e-3, rtol=2e-3)
+    for name, sl in (("dq", slice(0, Hq * D)), ("dk", slice(Hq * D, (Hq + Hkv) * D)), ("dv", slice((Hq + Hkv) * D, None))):
+        assert rel_l2(dqkv[:, sl].float(), x.grad[:, sl]) < 1.5e-2, name
