@@ -65,6 +65,8 @@ typedef struct {
   const int32_t* positions;
   int32_t rope_cols;
   int32_t resid_bcast; /* 1: resid is [M, ldo] shared by every batch (e.g. a positional table) */
+  void* out2;          /* optional bf16 [rows, ld2]: pre-activation copy (EPI_BF16+act) or raw gate|up (EPI_SWIGLU) */
+  int64_t ld2;
   int32_t block_n;   /* 0 = auto, else 64/128/256 */
   int32_t cta_group; /* 0 = auto, else 1/2 */
 } b2s_gemm_args;
@@ -258,6 +260,60 @@ int b2s_llama_prefill(const b2s_llama_weights* w, float* h, int32_t rows, const 
                       const int32_t* tap_layers /*host*/, int32_t num_taps, const int32_t* tap_rows_a,
                       const int32_t* tap_rows_b, int32_t pairs, float* fd_sq, float* all_hidden, void* workspace,
                       size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Training step (REF/trainer.py:270-384): forward with saved activations + backward of the frozen LLM
+ * (data gradients only: REF/trainer.py:62-64), memory-bound backward kernels, AdamW. */
+typedef struct {
+  const void* wqkv_t; /* bf16 [H, (Hq+2Hkv)*D]  = wqkv^T */
+  const void* wo_t;   /* bf16 [Hq*D, H]         = wo^T   */
+  const void* wgu_t;  /* bf16 [H, 2F]           = wgu^T (packed gate|up order) */
+  const void* wd_t;   /* bf16 [F, H]            = wd^T   */
+} b2s_llama_layer_t;
+typedef struct {
+  const b2s_llama_layer_t* layers; /* host array */
+  const void* lm_head_t;           /* bf16 [H, vocab] */
+} b2s_llama_weights_t;
+/* per-layer activations kept by the training forward (caller-allocated, rows = all packed rows):
+ *   h [L+1][rows][H] fp32 (h[0] = spliced input on entry, h[l] = input of layer l, h[L] = final stream),
+ *   h_mid [L][rows][H] fp32, qkv [L][rows][(Hq+2Hkv)D] bf16 (post-RoPE), ao [L][rows][Hq*D] bf16,
+ *   lse [L][rows][Hq] fp32, gu [L][rows][2F] bf16 (raw gate|up). */
+typedef struct {
+  float* h;
+  float* h_mid;
+  void* qkv;
+  void* ao;
+  float* lse;
+  void* gu;
+} b2s_llama_saved;
+size_t b2s_llama_train_workspace_bytes(const b2s_llama_weights* w, int32_t rows, int32_t logit_rows);
+size_t b2s_llama_backward_workspace_bytes(const b2s_llama_weights* w, int32_t rows_bwd, int32_t n_dl);
+int b2s_llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* saved, int32_t rows,
+                            const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, const int32_t* positions,
+                            const int32_t* logit_rows_index, int32_t logit_rows, void* logits_bf16,
+                            const int32_t* tap_layers /*host*/, int32_t num_taps, const int32_t* tap_rows_a,
+                            const int32_t* tap_rows_b, int32_t pairs, float* fd_sq, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* Gradient w.r.t. the LLM input rows [0, rows_bwd) (the student sequences, packed first):
+ *   d_logits bf16 [n_dl, vocab] for rows dl_rows_index; FD term: before layer l runs backward, rows tap_rows_a get
+ *   tap_coef[i] * (h[l+1][a_i] - h[l+1][b_i]) for every tap layer l+1; dh fp32 [rows_bwd, H] = dL/d h[0]. */
+int b2s_llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt, const b2s_llama_saved* saved,
+                       int32_t rows, int32_t rows_bwd, const int32_t* cu_seqlens, int32_t num_seqs_bwd,
+                       int32_t max_seqlen, const void* d_logits, const int32_t* dl_rows_index, int32_t n_dl,
+                       const int32_t* tap_layers /*host*/, int32_t num_taps, const int32_t* tap_rows_a,
+                       const int32_t* tap_rows_b, const float* tap_coef, int32_t pairs, float* dh, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int b2s_rmsnorm_bwd(const float* x, const int32_t* x_index, const float* w, float eps, const float* dy, float* dh,
+                    const int32_t* dh_index, void* dh_bf16, int64_t rows, int32_t C, void* stream);
+int b2s_layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int32_t dy_bf16, float* dh,
+                      int32_t accumulate, void* dh_bf16, float* dgamma, float* dbeta, int64_t rows, int32_t C,
+                      void* stream);
+int b2s_swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t rows, int32_t F, void* stream);
+int b2s_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, void* stream);
+int b2s_gather_rows_f32(const float* src, const int32_t* index, float* out, int64_t rows, int32_t C, void* stream);
+/* torch.optim.AdamW step on one flat fp32 tensor (REF/trainer.py:98-105,381); grad_scale multiplies the gradient. */
+int b2s_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

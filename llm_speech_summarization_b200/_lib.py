@@ -24,7 +24,8 @@ class GemmArgs(C.Structure):
         ("k_per_tap", c_int), ("a_pad", c_int), ("a_group_off", c_int), ("w_group_off", c_int),
         ("epi", c_int), ("act", c_int), ("bias", c_void_p), ("out", c_void_p), ("ldo", c_int64),
         ("out_batch_rows", c_int64), ("resid", c_void_p), ("rope_cs", c_void_p), ("positions", c_void_p),
-        ("rope_cols", c_int), ("resid_bcast", c_int), ("block_n", c_int), ("cta_group", c_int),
+        ("rope_cols", c_int), ("resid_bcast", c_int), ("out2", c_void_p), ("ld2", c_int64), ("block_n", c_int),
+        ("cta_group", c_int),
     ]
 
 
@@ -70,6 +71,18 @@ class LlamaWeights(C.Structure):
     ]
 
 
+class LlamaLayerT(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("wqkv_t", "wo_t", "wgu_t", "wd_t")]
+
+
+class LlamaWeightsT(C.Structure):
+    _fields_ = [("layers", C.POINTER(LlamaLayerT)), ("lm_head_t", c_void_p)]
+
+
+class LlamaSaved(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("h", "h_mid", "qkv", "ao", "lse", "gu")]
+
+
 # name -> (restype, argtypes); mirrors include/b2s.h one to one (tests/test_abi.py checks the symbol list)
 PROTOTYPES = {
     "b2s_last_error": (C.c_char_p, []),
@@ -113,6 +126,23 @@ PROTOTYPES = {
     "b2s_llama_prefill": (c_int, [C.POINTER(LlamaWeights), P_f32, c_int, P_int, c_int, c_int, P_int, P_int, c_int,
                                   c_void_p, C.POINTER(c_int), c_int, P_int, P_int, c_int, P_f32, P_f32, c_void_p,
                                   c_size_t, c_void_p]),
+    "b2s_llama_train_workspace_bytes": (c_size_t, [C.POINTER(LlamaWeights), c_int, c_int]),
+    "b2s_llama_backward_workspace_bytes": (c_size_t, [C.POINTER(LlamaWeights), c_int, c_int]),
+    "b2s_llama_forward_train": (c_int, [C.POINTER(LlamaWeights), C.POINTER(LlamaSaved), c_int, P_int, c_int, c_int,
+                                        P_int, P_int, c_int, c_void_p, C.POINTER(c_int), c_int, P_int, P_int, c_int,
+                                        P_f32, c_void_p, c_size_t, c_void_p]),
+    "b2s_llama_backward": (c_int, [C.POINTER(LlamaWeights), C.POINTER(LlamaWeightsT), C.POINTER(LlamaSaved), c_int,
+                                   c_int, P_int, c_int, c_int, c_void_p, P_int, c_int, C.POINTER(c_int), c_int, P_int,
+                                   P_int, P_f32, c_int, P_f32, c_void_p, c_size_t, c_void_p]),
+    "b2s_rmsnorm_bwd": (c_int, [P_f32, P_int, P_f32, c_float, P_f32, P_f32, P_int, c_void_p, c_int64, c_int,
+                                c_void_p]),
+    "b2s_layernorm_bwd": (c_int, [P_f32, P_f32, c_float, c_void_p, c_int, P_f32, c_int, c_void_p, P_f32, P_f32,
+                                  c_int64, c_int, c_void_p]),
+    "b2s_swiglu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "b2s_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "b2s_gather_rows_f32": (c_int, [P_f32, P_int, P_f32, c_int64, c_int, c_void_p]),
+    "b2s_adamw_step": (c_int, [P_f32, P_f32, P_f32, P_f32, c_int64, c_float, c_float, c_float, c_float, c_float,
+                               c_int, c_float, c_void_p]),
 }
 
 _lib = None

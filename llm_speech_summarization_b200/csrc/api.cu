@@ -57,6 +57,19 @@ int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_
                   const int* tap_layers, int num_taps, const int* tap_rows_a, const int* tap_rows_b, int pairs,
                   float* fd_sq, float* all_hidden, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+size_t llama_train_workspace_bytes(const b2s_llama_weights* w, int rows, int logit_rows);
+size_t llama_backward_workspace_bytes(const b2s_llama_weights* w, int rows_bwd, int n_dl);
+int llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* sv, int rows, const int* cu_seqlens,
+                        int num_seqs, int max_seqlen, const int* positions, const int* logit_rows_index,
+                        int logit_rows, void* logits_bf16, const int* tap_layers, int num_taps, const int* tap_rows_a,
+                        const int* tap_rows_b, int pairs, float* fd_sq, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream);
+int llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt, const b2s_llama_saved* sv, int rows,
+                   int rows_bwd, const int* cu_seqlens, int num_seqs_bwd, int max_seqlen, const void* d_logits,
+                   const int* dl_rows_index, int n_dl, const int* tap_layers, int num_taps, const int* tap_rows_a,
+                   const int* tap_rows_b, const float* tap_coef, int pairs, float* dh, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream);
+
 }  // namespace b2s
 
 using namespace b2s;
@@ -100,6 +113,8 @@ int b2s_gemm_bf16(const b2s_gemm_args* a, void* stream) {
   g.out_batch_rows = a->out_batch_rows;
   g.resid = a->resid;
   g.resid_bcast = a->resid_bcast;
+  g.out2 = a->out2;
+  g.ld2 = a->ld2;
   g.rope_cs = a->rope_cs;
   g.positions = a->positions;
   g.rope_cols = a->rope_cols;
@@ -217,6 +232,55 @@ int b2s_llama_prefill(const b2s_llama_weights* w, float* h, int32_t rows, const 
   return llama_prefill(w, h, rows, cu_seqlens, num_seqs, max_seqlen, positions, logit_rows_index, logit_rows,
                        logits_bf16, tap_layers, num_taps, tap_rows_a, tap_rows_b, pairs, fd_sq, all_hidden, workspace,
                        workspace_bytes, S(stream));
+}
+
+size_t b2s_llama_train_workspace_bytes(const b2s_llama_weights* w, int32_t rows, int32_t logit_rows) {
+  return llama_train_workspace_bytes(w, rows, logit_rows);
+}
+size_t b2s_llama_backward_workspace_bytes(const b2s_llama_weights* w, int32_t rows_bwd, int32_t n_dl) {
+  return llama_backward_workspace_bytes(w, rows_bwd, n_dl);
+}
+int b2s_llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* saved, int32_t rows,
+                            const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, const int32_t* positions,
+                            const int32_t* logit_rows_index, int32_t logit_rows, void* logits_bf16,
+                            const int32_t* tap_layers, int32_t num_taps, const int32_t* tap_rows_a,
+                            const int32_t* tap_rows_b, int32_t pairs, float* fd_sq, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  return llama_forward_train(w, saved, rows, cu_seqlens, num_seqs, max_seqlen, positions, logit_rows_index, logit_rows,
+                             logits_bf16, tap_layers, num_taps, tap_rows_a, tap_rows_b, pairs, fd_sq, workspace,
+                             workspace_bytes, S(stream));
+}
+int b2s_llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt, const b2s_llama_saved* saved,
+                       int32_t rows, int32_t rows_bwd, const int32_t* cu_seqlens, int32_t num_seqs_bwd,
+                       int32_t max_seqlen, const void* d_logits, const int32_t* dl_rows_index, int32_t n_dl,
+                       const int32_t* tap_layers, int32_t num_taps, const int32_t* tap_rows_a,
+                       const int32_t* tap_rows_b, const float* tap_coef, int32_t pairs, float* dh, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  return llama_backward(w, wt, saved, rows, rows_bwd, cu_seqlens, num_seqs_bwd, max_seqlen, d_logits, dl_rows_index,
+                        n_dl, tap_layers, num_taps, tap_rows_a, tap_rows_b, tap_coef, pairs, dh, workspace,
+                        workspace_bytes, S(stream));
+}
+int b2s_rmsnorm_bwd(const float* x, const int32_t* x_index, const float* w, float eps, const float* dy, float* dh,
+                    const int32_t* dh_index, void* dh_bf16, int64_t rows, int32_t C, void* stream) {
+  return rmsnorm_bwd(x, x_index, w, eps, dy, dh, dh_index, dh_bf16, rows, C, S(stream));
+}
+int b2s_layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int32_t dy_bf16, float* dh,
+                      int32_t accumulate, void* dh_bf16, float* dgamma, float* dbeta, int64_t rows, int32_t C,
+                      void* stream) {
+  return layernorm_bwd(x, gamma, eps, dy, dy_bf16, dh, accumulate, dh_bf16, dgamma, dbeta, rows, C, S(stream));
+}
+int b2s_swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t rows, int32_t F, void* stream) {
+  return swiglu_bwd(gu, dact, dgu, rows, F, S(stream));
+}
+int b2s_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, void* stream) {
+  return gelu_bwd(pre, dy, dpre, n, S(stream));
+}
+int b2s_gather_rows_f32(const float* src, const int32_t* index, float* out, int64_t rows, int32_t C, void* stream) {
+  return gather_rows_f32(src, index, out, rows, C, S(stream));
+}
+int b2s_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int32_t step, float grad_scale, void* stream) {
+  return adamw_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
 }
 
 }  // extern "C"

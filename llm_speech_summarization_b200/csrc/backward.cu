@@ -1,0 +1,354 @@
+// backward.cu -- the memory-bound pieces of the training step's backward pass and the optimizer
+// (REF/trainer.py:372-384: total_loss / grad_accum -> backward -> AdamW.step; autograd through the modules of
+// TF/models/llama/modeling_llama.py and TF/models/hubert/modeling_hubert.py). One warp per row for the norm
+// backwards (row in registers, fp32), vectorised elementwise kernels for the activation backwards.
+#include "b2s_common.cuh"
+#include "ops.cuh"
+
+namespace b2s {
+namespace {
+
+constexpr int kWarps = 8;
+
+__device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void st8f(float* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void st8bf(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void ld8bf(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+
+// RMSNorm backward (no weight gradient: the LLM is frozen, REF/trainer.py:63-64):
+//   y = w * x * rstd  =>  dx = rstd * (w dy) - x * rstd^3 / C * sum_k x_k w_k dy_k ;   dh[dst] += dx
+template <int GROUPS>
+__global__ void __launch_bounds__(kWarps * 32)
+rmsnorm_bwd_kernel(const float* __restrict__ x, const int* __restrict__ x_index, const float* __restrict__ w, float eps,
+                   const float* __restrict__ dy, float* dh, const int* __restrict__ dh_index,
+                   __nv_bfloat16* dh_bf16, long long rows) {
+  constexpr int C = GROUPS * 256;
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long xr = x_index ? x_index[row] : row;
+  const long long dr = dh_index ? dh_index[row] : row;
+  float xv[GROUPS][8], gv[GROUPS][8];
+  float ss = 0.f, dot = 0.f;
+#pragma unroll
+  for (int g = 0; g < GROUPS; ++g) {
+    const int c = (g * 32 + lane) * 8;
+    float wv[8], dv[8];
+    ld8f(x + xr * C + c, xv[g]);
+    ld8f(w + c, wv);
+    ld8f(dy + row * C + c, dv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gv[g][j] = wv[j] * dv[j];
+      ss = fmaf(xv[g][j], xv[g][j], ss);
+      dot = fmaf(xv[g][j], gv[g][j], dot);
+    }
+  }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float rstd = rsqrtf(ss * (1.0f / C) + eps);
+  const float coef = dot * rstd * rstd * rstd * (1.0f / C);
+#pragma unroll
+  for (int g = 0; g < GROUPS; ++g) {
+    const int c = (g * 32 + lane) * 8;
+    float acc[8];
+    ld8f(dh + dr * C + c, acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += rstd * gv[g][j] - coef * xv[g][j];
+    st8f(dh + dr * C + c, acc);
+    if (dh_bf16 != nullptr) st8bf(dh_bf16 + dr * C + c, acc);
+  }
+}
+
+// LayerNorm backward: xhat = (x - mean) rstd, y = gamma xhat + beta
+//   dx = rstd * (g - mean(g) - xhat * mean(g xhat)),  g = gamma dy ;  dgamma += dy xhat ; dbeta += dy
+// dx is ADDED to dh (residual stream gradient) or written (accumulate = 0).
+template <int GROUPS, bool DY_BF16>
+__global__ void __launch_bounds__(kWarps * 32)
+layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float eps, const void* __restrict__ dy,
+                     float* dh, int accumulate, __nv_bfloat16* dh_bf16, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, long long rows) {
+  constexpr int C = GROUPS * 256;
+  __shared__ float s_dg[C], s_db[C];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_dg[i] = s_db[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+  if (row < rows) {
+    float xv[GROUPS][8], dv[GROUPS][8];
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < GROUPS; ++g) {
+      const int c = (g * 32 + lane) * 8;
+      ld8f(x + row * C + c, xv[g]);
+      if constexpr (DY_BF16) ld8bf(reinterpret_cast<const __nv_bfloat16*>(dy) + row * C + c, dv[g]);
+      else ld8f(reinterpret_cast<const float*>(dy) + row * C + c, dv[g]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += xv[g][j];
+    }
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int g = 0; g < GROUPS; ++g)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xv[g][j] -= mean;
+        q = fmaf(xv[g][j], xv[g][j], q);
+      }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int g = 0; g < GROUPS; ++g) {
+      const int c = (g * 32 + lane) * 8;
+      float gm[8];
+      ld8f(gamma + c, gm);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = xv[g][j] * rstd;
+        atomicAdd(&s_dg[c + j], dv[g][j] * xh);
+        atomicAdd(&s_db[c + j], dv[g][j]);
+        xv[g][j] = xh;             // xhat
+        dv[g][j] *= gm[j];         // g = gamma dy
+        sg += dv[g][j];
+        sgx = fmaf(dv[g][j], xh, sgx);
+      }
+    }
+    sg = warp_sum(sg) * (1.0f / C);
+    sgx = warp_sum(sgx) * (1.0f / C);
+#pragma unroll
+    for (int g = 0; g < GROUPS; ++g) {
+      const int c = (g * 32 + lane) * 8;
+      float acc[8];
+      if (accumulate) ld8f(dh + row * C + c, acc);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += rstd * (dv[g][j] - sg - xv[g][j] * sgx);
+      st8f(dh + row * C + c, acc);
+      if (dh_bf16 != nullptr) st8bf(dh_bf16 + row * C + c, acc);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, s_dg[i]);
+    atomicAdd(dbeta + i, s_db[i]);
+  }
+}
+
+// SwiGLU backward on the packed layout (64 gate | 64 up per 128 columns):
+//   a = silu(g) u ; dg = da u sig(g) (1 + g (1 - sig(g))) ; du = da silu(g)
+__global__ void __launch_bounds__(256)
+swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __nv_bfloat16* __restrict__ dact,
+                  __nv_bfloat16* __restrict__ dgu, long long rows, int F) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // one 8-element vector of dact
+  const long long per_row = F / 8;
+  if (i >= rows * per_row) return;
+  const long long row = i / per_row;
+  const int v = static_cast<int>(i - row * per_row);
+  const int col = v * 8;                       // column in [0, F)
+  const int blk = col / 64, within = col % 64;  // 64-wide block
+  const long long gbase = row * 2 * F + blk * 128 + within;
+  float g[8], u[8], da[8], dg[8], du[8];
+  ld8bf(gu + gbase, g);
+  ld8bf(gu + gbase + 64, u);
+  ld8bf(dact + row * F + col, da);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float sg = 1.0f / (1.0f + __expf(-g[j]));
+    dg[j] = da[j] * u[j] * sg * (1.0f + g[j] * (1.0f - sg));
+    du[j] = da[j] * g[j] * sg;
+  }
+  st8bf(dgu + gbase, dg);
+  st8bf(dgu + gbase + 64, du);
+}
+
+// erf-GELU backward: dpre = dy * (Phi(x) + x phi(x))
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dy,
+                __nv_bfloat16* __restrict__ dpre, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float x[8], d[8];
+  ld8bf(pre + i * 8, x);
+  ld8bf(dy + i * 8, d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float cdf = 0.5f * (1.0f + erff(x[j] * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * x[j] * x[j]);
+    d[j] *= cdf + x[j] * pdf;
+  }
+  st8bf(dpre + i * 8, d);
+}
+
+// dh[rows_a[i]] += c * (h[rows_a[i]] - h[rows_b[i]])  (feature-distillation MSE backward, REF/trainer.py:358-370)
+__global__ void __launch_bounds__(256)
+add_rowdiff_kernel(const float* __restrict__ h, const int* __restrict__ rows_a, const int* __restrict__ rows_b,
+                   const float* __restrict__ coef, float* dh, __nv_bfloat16* dh_bf16, int pairs, int C) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= pairs) return;
+  const long long ra = rows_a[i], rb = rows_b[i];
+  const float c = coef[i];
+  for (int k = lane * 4; k < C; k += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(h + ra * C + k);
+    const float4 b = *reinterpret_cast<const float4*>(h + rb * C + k);
+    float4 d = *reinterpret_cast<float4*>(dh + ra * C + k);
+    d.x += c * (a.x - b.x); d.y += c * (a.y - b.y); d.z += c * (a.z - b.z); d.w += c * (a.w - b.w);
+    *reinterpret_cast<float4*>(dh + ra * C + k) = d;
+    if (dh_bf16 != nullptr) {
+      uint2 u;
+      u.x = pack_bf16(d.x, d.y);
+      u.y = pack_bf16(d.z, d.w);
+      *reinterpret_cast<uint2*>(dh_bf16 + ra * C + k) = u;
+    }
+  }
+}
+
+// out[i, :] = src[index[i], :]   (fp32 rows; index < 0 -> zeros)
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ index, float* __restrict__ out, long long rows,
+                   int C) {
+  const int lane = threadIdx.x & 31;
+  const long long i = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (i >= rows) return;
+  const long long s = index[i];
+  for (int k = lane * 4; k < C; k += 128) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s >= 0) v = *reinterpret_cast<const float4*>(src + s * C + k);
+    *reinterpret_cast<float4*>(out + i * C + k) = v;
+  }
+}
+
+// AdamW (torch.optim.AdamW semantics, REF/trainer.py:98-105): decoupled weight decay, bias-corrected moments.
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2,
+             float grad_scale) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gr = g[i] * grad_scale;
+  float pv = p[i] * (1.0f - lr * wd);
+  const float mv = beta1 * m[i] + (1.0f - beta1) * gr;
+  const float vv = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+  m[i] = mv;
+  v[i] = vv;
+  pv -= lr * (mv / bc1) / (sqrtf(vv / bc2) + eps);
+  p[i] = pv;
+}
+
+}  // namespace
+
+#define B2S_GROUPS_SWITCH(C, ...)                                  \
+  switch ((C) / 256) {                                             \
+    case 1: { constexpr int G = 1; __VA_ARGS__; break; }           \
+    case 2: { constexpr int G = 2; __VA_ARGS__; break; }           \
+    case 4: { constexpr int G = 4; __VA_ARGS__; break; }           \
+    case 12: { constexpr int G = 12; __VA_ARGS__; break; }         \
+    default:                                                       \
+      set_last_error("norm backward: unsupported width %d (256, 512, 1024, 3072)", (C)); \
+      return B2S_ERR_UNSUPPORTED;                                  \
+  }
+
+int rmsnorm_bwd(const float* x, const int* x_index, const float* w, float eps, const float* dy, float* dh,
+                const int* dh_index, void* dh_bf16, long long rows, int C, cudaStream_t stream) {
+  B2S_REQUIRE(x && w && dy && dh, "rmsnorm_bwd: null pointer");
+  B2S_REQUIRE(C % 256 == 0, "rmsnorm_bwd: C must be a multiple of 256");
+  if (rows <= 0) return B2S_OK;
+  const unsigned grid = static_cast<unsigned>((rows + kWarps - 1) / kWarps);
+  B2S_GROUPS_SWITCH(C, (rmsnorm_bwd_kernel<G><<<grid, kWarps * 32, 0, stream>>>(
+                           x, x_index, w, eps, dy, dh, dh_index, reinterpret_cast<__nv_bfloat16*>(dh_bf16), rows)));
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+int layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int dy_bf16, float* dh, int accumulate,
+                  void* dh_bf16, float* dgamma, float* dbeta, long long rows, int C, cudaStream_t stream) {
+  B2S_REQUIRE(x && gamma && dy && dh && dgamma && dbeta, "layernorm_bwd: null pointer");
+  B2S_REQUIRE(C % 256 == 0, "layernorm_bwd: C must be a multiple of 256");
+  if (rows <= 0) return B2S_OK;
+  const unsigned grid = static_cast<unsigned>((rows + kWarps - 1) / kWarps);
+  if (dy_bf16) {
+    B2S_GROUPS_SWITCH(C, (layernorm_bwd_kernel<G, true><<<grid, kWarps * 32, 0, stream>>>(
+                             x, gamma, eps, dy, dh, accumulate, reinterpret_cast<__nv_bfloat16*>(dh_bf16), dgamma, dbeta,
+                             rows)));
+  } else {
+    B2S_GROUPS_SWITCH(C, (layernorm_bwd_kernel<G, false><<<grid, kWarps * 32, 0, stream>>>(
+                             x, gamma, eps, dy, dh, accumulate, reinterpret_cast<__nv_bfloat16*>(dh_bf16), dgamma, dbeta,
+                             rows)));
+  }
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+int swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows, int F, cudaStream_t stream) {
+  B2S_REQUIRE(gu && dact && dgu, "swiglu_bwd: null pointer");
+  B2S_REQUIRE(F % 64 == 0, "swiglu_bwd: F must be a multiple of 64");
+  if (rows <= 0) return B2S_OK;
+  const long long n = rows * (F / 8);
+  swiglu_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(gu), reinterpret_cast<const __nv_bfloat16*>(dact),
+      reinterpret_cast<__nv_bfloat16*>(dgu), rows, F);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+int gelu_bwd(const void* pre, const void* dy, void* dpre, long long n, cudaStream_t stream) {
+  B2S_REQUIRE(pre && dy && dpre, "gelu_bwd: null pointer");
+  B2S_REQUIRE(n % 8 == 0, "gelu_bwd: element count must be a multiple of 8");
+  if (n <= 0) return B2S_OK;
+  gelu_bwd_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<const __nv_bfloat16*>(dy),
+      reinterpret_cast<__nv_bfloat16*>(dpre), n / 8);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+int add_rowdiff(const float* h, const int* rows_a, const int* rows_b, const float* coef, float* dh, void* dh_bf16,
+                int pairs, int C, cudaStream_t stream) {
+  B2S_REQUIRE(h && rows_a && rows_b && coef && dh, "add_rowdiff: null pointer");
+  B2S_REQUIRE(C % 4 == 0, "add_rowdiff: C must be a multiple of 4");
+  if (pairs <= 0) return B2S_OK;
+  add_rowdiff_kernel<<<(pairs + 7) / 8, 256, 0, stream>>>(h, rows_a, rows_b, coef, dh,
+                                                          reinterpret_cast<__nv_bfloat16*>(dh_bf16), pairs, C);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+int gather_rows_f32(const float* src, const int* index, float* out, long long rows, int C, cudaStream_t stream) {
+  B2S_REQUIRE(src && index && out, "gather_rows_f32: null pointer");
+  B2S_REQUIRE(C % 4 == 0, "gather_rows_f32: C must be a multiple of 4");
+  if (rows <= 0) return B2S_OK;
+  gather_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(src, index, out, rows, C);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+int adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+               float weight_decay, int step, float grad_scale, cudaStream_t stream) {
+  B2S_REQUIRE(p && g && m && v && step >= 1, "adamw_step: bad arguments");
+  if (n <= 0) return B2S_OK;
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  adamw_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps,
+                                                                           weight_decay, bc1, bc2, grad_scale);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+}  // namespace b2s

@@ -69,6 +69,8 @@ struct KParams {
   long long out_batch_rows;
   const float* resid;
   int resid_bcast;
+  void* out2;
+  long long ld2;
   const float* rope_cs;
   const int* positions;
   int rope_cols;
@@ -342,8 +344,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          add_bias_act(v, bias ? bias + col : nullptr, p.act);
           const int valid = min(32, p.N - col);
+          if (p.out2 != nullptr) {  // training: keep the pre-activation (acc + bias) for the backward
+            add_bias_act(v, bias ? bias + col : nullptr, ACT_NONE);
+            emit_bf16(stg, v, lane,
+                      reinterpret_cast<__nv_bfloat16*>(p.out2) + orow0 * p.ld2 + static_cast<long long>(tc.g) * p.N + col,
+                      p.ld2, rows_valid, valid);
+            add_bias_act(v, nullptr, p.act);
+          } else {
+            add_bias_act(v, bias ? bias + col : nullptr, p.act);
+          }
           const long long off0 = orow0 * p.ldo + static_cast<long long>(tc.g) * p.N + col;
           if (p.epi == EPI_BF16) {
             emit_bf16(stg, v, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, valid);
@@ -380,6 +390,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             add_bias_act(lo, bias ? bias + bcol + c * 32 : nullptr, ACT_NONE);
             add_bias_act(hi, bias ? bias + bcol + (c + 2) * 32 : nullptr, ACT_NONE);
             if (p.epi == EPI_SWIGLU) {
+              if (p.out2 != nullptr) {  // training: raw gate | up (the GEMM's natural [M, N] layout)
+                __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(p.out2) + orow0 * p.ld2 +
+                                     static_cast<long long>(tc.g) * p.N + bcol + c * 32;
+                emit_bf16(stg, lo, lane, raw, p.ld2, rows_valid, 32);
+                emit_bf16(stg, hi, lane, raw + 64, p.ld2, rows_valid, 32);
+              }
 #pragma unroll
               for (int i = 0; i < 32; ++i) lo[i] = silu(lo[i]) * hi[i];
               const long long off0 = orow0 * p.ldo + (static_cast<long long>(tc.g) * p.N + bcol) / 2 + c * 32;
@@ -604,6 +620,8 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   p.out_batch_rows = a.out_batch_rows;
   p.resid = a.resid;
   p.resid_bcast = a.resid_bcast;
+  p.out2 = a.out2;
+  p.ld2 = a.ld2;
   p.rope_cs = a.rope_cs;
   p.positions = a.positions;
   p.rope_cols = a.rope_cols;

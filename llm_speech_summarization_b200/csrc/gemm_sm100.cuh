@@ -50,6 +50,8 @@ struct GemmArgs {
   long long out_batch_rows; // output row = b*out_batch_rows + m
   const float* resid;       // EPI_RESID_F32: fp32 [rows, ldo]
   int resid_bcast;          // 1: resid is [M, ldo], shared by every batch (row index = m, not b*out_batch_rows + m)
+  void* out2;               // optional bf16 [rows, ld2]: (acc + bias) BEFORE the activation (EPI_BF16) / the raw
+  long long ld2;            //   gate|up columns (EPI_SWIGLU) -- what the backward pass needs
   const float* rope_cs;     // EPI_ROPE: [npos, 128] fp32 = cos[0:64] | sin[0:64]
   const int* positions;     // EPI_ROPE: [rows] position of each row inside its own sequence
   int rope_cols;

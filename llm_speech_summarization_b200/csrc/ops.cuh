@@ -51,6 +51,21 @@ int cast_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t stream);
 int cast_bf16_to_f32(const void* x, float* y, long long n, cudaStream_t stream);
 // y_bf16 = gelu(x_f32 + residual) etc. are fused in GEMM epilogues; nothing else elementwise is needed.
 
+// ---- backward.cu (training step: memory-bound backward kernels + optimizer)
+// dh[dst] += RMSNorm^T(dy) ; x / dst rows optionally gathered through index lists; optional bf16 copy of dh rows
+int rmsnorm_bwd(const float* x, const int* x_index, const float* w, float eps, const float* dy, float* dh,
+                const int* dh_index, void* dh_bf16, long long rows, int C, cudaStream_t stream);
+// dh (+)= LayerNorm^T(dy); dgamma / dbeta accumulated with atomics; dy fp32 or bf16
+int layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int dy_bf16, float* dh, int accumulate,
+                  void* dh_bf16, float* dgamma, float* dbeta, long long rows, int C, cudaStream_t stream);
+int swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows, int F, cudaStream_t stream);
+int gelu_bwd(const void* pre, const void* dy, void* dpre, long long n, cudaStream_t stream);
+int add_rowdiff(const float* h, const int* rows_a, const int* rows_b, const float* coef, float* dh, void* dh_bf16,
+                int pairs, int C, cudaStream_t stream);
+int gather_rows_f32(const float* src, const int* index, float* out, long long rows, int C, cudaStream_t stream);
+int adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+               float weight_decay, int step, float grad_scale, cudaStream_t stream);
+
 // ---- attention.cu
 // Packed variable-length attention. q/k/v are bf16 views into one [rows, ld] buffer (fused QKV output):
 // head h of row r lives at base + r*ld + h*D. Sequences are rows [cu[s], cu[s+1]).

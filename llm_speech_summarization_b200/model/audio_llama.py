@@ -111,6 +111,8 @@ class AudioLlamaForCausalLM(nn.Module):
         if config.tie_embeddings:
             self.lm_head.weight = self.model.embed_tokens.weight
         self._packed = None
+        self._packed_t = None
+        self._pw = None
 
     # ------------------------------------------------------------------------------------------ loading
     @classmethod
@@ -131,7 +133,7 @@ class AudioLlamaForCausalLM(nn.Module):
         if self.arch.tie_embeddings:
             sd.setdefault("lm_head.weight", sd["model.embed_tokens.weight"])
         sd = {k: v for k, v in sd.items() if not k.endswith("rotary_emb.inv_freq")}
-        self._packed = None
+        self._packed = self._packed_t = self._pw = None
         return super().load_state_dict(sd, strict=strict, assign=assign)
 
     @property
@@ -139,7 +141,7 @@ class AudioLlamaForCausalLM(nn.Module):
         return self.model.embed_tokens.weight.device
 
     def _apply(self, fn, *a, **k):
-        self._packed = None
+        self._packed = self._packed_t = self._pw = None
         out = super()._apply(fn, *a, **k)
         if self.arch.tie_embeddings:
             self.lm_head.weight = self.model.embed_tokens.weight
@@ -162,15 +164,21 @@ class AudioLlamaForCausalLM(nn.Module):
         bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
         f32 = lambda t: t.detach().to(torch.float32).contiguous()
         layers = (_lib.LlamaLayer * a.layers)()
+        self._pw = []
         for l, lay in enumerate(self.model.layers):
             L = layers[l]
             sa, mlp = lay.self_attn, lay.mlp
+            pw = dict(wqkv=bf(packing.pack_qkv(sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight)),
+                      wo=bf(sa.o_proj.weight),
+                      wgu=bf(packing.pack_gate_up(mlp.gate_proj.weight.detach(), mlp.up_proj.weight.detach())),
+                      wd=bf(mlp.down_proj.weight))
+            self._pw.append(pw)
             L.ln1_w = K(f32(lay.input_layernorm.weight))
-            L.wqkv = K(bf(packing.pack_qkv(sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight)))
-            L.wo = K(bf(sa.o_proj.weight))
+            L.wqkv = K(pw["wqkv"])
+            L.wo = K(pw["wo"])
             L.ln2_w = K(f32(lay.post_attention_layernorm.weight))
-            L.wgu = K(bf(packing.pack_gate_up(mlp.gate_proj.weight.detach(), mlp.up_proj.weight.detach())))
-            L.wd = K(bf(mlp.down_proj.weight))
+            L.wgu = K(pw["wgu"])
+            L.wd = K(pw["wd"])
         w = _lib.LlamaWeights()
         w.layers = C.cast(layers, C.POINTER(_lib.LlamaLayer))
         w.num_layers, w.hidden, w.heads, w.kv_heads = a.layers, a.hidden, a.heads, a.kv_heads
@@ -181,6 +189,94 @@ class AudioLlamaForCausalLM(nn.Module):
         w.max_pos = a.max_pos
         self._packed = (w, layers, keep)
         return self._packed
+
+    def packed_t(self):
+        """Transposed copies of the packed weights: the B operands of the dgrad GEMMs (dX = dY . W needs W^T in the
+        kernel's [N, K] K-major layout). Frozen LLM -> built once, only when a backward pass is requested."""
+        if self._packed_t is not None:
+            return self._packed_t
+        self.packed()
+        a = self.arch
+        keep: List[torch.Tensor] = []
+
+        def K(t):
+            keep.append(t)
+            return t.data_ptr()
+
+        layers = (_lib.LlamaLayerT * a.layers)()
+        for l, pw in enumerate(self._pw):
+            T = layers[l]
+            T.wqkv_t = K(pw["wqkv"].t().contiguous())
+            T.wo_t = K(pw["wo"].t().contiguous())
+            T.wgu_t = K(pw["wgu"].t().contiguous())
+            T.wd_t = K(pw["wd"].t().contiguous())
+        wt = _lib.LlamaWeightsT()
+        wt.layers = C.cast(layers, C.POINTER(_lib.LlamaLayerT))
+        wt.lm_head_t = K(self.lm_head.weight.detach().to(torch.bfloat16).t().contiguous())
+        self._packed_t = (wt, layers, keep)
+        return self._packed_t
+
+    def alloc_saved(self, rows: int, device):
+        """Per-layer activation buffers of the training forward (include/b2s.h: b2s_llama_saved)."""
+        a = self.arch
+        L, H, F_ = a.layers, a.hidden, a.ffn
+        qkv_cols = (a.heads + 2 * a.kv_heads) * a.head_dim
+        t = dict(h=torch.empty(L + 1, rows, H, device=device, dtype=torch.float32),
+                 h_mid=torch.empty(L, rows, H, device=device, dtype=torch.float32),
+                 qkv=torch.empty(L, rows, qkv_cols, device=device, dtype=torch.bfloat16),
+                 ao=torch.empty(L, rows, a.heads * a.head_dim, device=device, dtype=torch.bfloat16),
+                 lse=torch.empty(L, rows, a.heads, device=device, dtype=torch.float32),
+                 gu=torch.empty(L, rows, 2 * F_, device=device, dtype=torch.bfloat16))
+        sv = _lib.LlamaSaved()
+        for k, v in t.items():
+            setattr(sv, k, v.data_ptr())
+        return sv, t
+
+    def forward_train_packed(self, saved, saved_tensors, cu_seqlens, max_seqlen, positions, logit_rows,
+                             tap_layers: Sequence[int] = (), tap_rows_a=None, tap_rows_b=None):
+        """Training forward over packed sequences; saved_tensors["h"][0] must hold the spliced input."""
+        w = self.packed()[0]
+        a = self.arch
+        lib = _lib.load()
+        rows = saved_tensors["h"].shape[1]
+        dev = saved_tensors["h"].device
+        n_log = logit_rows.numel()
+        logits = torch.empty(n_log, a.vocab, device=dev, dtype=torch.bfloat16)
+        taps = [int(t) for t in tap_layers if 0 < int(t) < a.layers]
+        pairs = 0 if tap_rows_a is None else tap_rows_a.numel()
+        fd = torch.zeros(max(1, len(taps)), max(1, pairs), device=dev, dtype=torch.float32)
+        tap_arr = (C.c_int32 * max(1, len(taps)))(*taps)
+        nbytes = lib.b2s_llama_train_workspace_bytes(C.byref(w), rows, n_log)
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        _lib.check(lib.b2s_llama_forward_train(
+            C.byref(w), C.byref(saved), rows, cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, int(max_seqlen),
+            positions.data_ptr(), logit_rows.data_ptr(), n_log, logits.data_ptr(), tap_arr, len(taps) if pairs else 0,
+            None if not pairs else tap_rows_a.data_ptr(), None if not pairs else tap_rows_b.data_ptr(), pairs,
+            fd.data_ptr(), ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream), "llama_forward_train")
+        return logits, (fd if pairs and taps else None), taps
+
+    def backward_packed(self, saved, saved_tensors, rows_bwd: int, cu_seqlens, num_seqs_bwd: int, max_seqlen: int,
+                        d_logits, dl_rows, taps: Sequence[int], tap_rows_a, tap_rows_b, tap_coef):
+        """dL/d(input rows [0, rows_bwd)) given d_logits on rows dl_rows and the FD coefficients."""
+        w = self.packed()[0]
+        wt = self.packed_t()[0]
+        lib = _lib.load()
+        a = self.arch
+        rows = saved_tensors["h"].shape[1]
+        dev = d_logits.device
+        dh = torch.empty(rows_bwd, a.hidden, device=dev, dtype=torch.float32)
+        n_dl = dl_rows.numel()
+        pairs = 0 if tap_rows_a is None or not len(taps) else tap_rows_a.numel()
+        tap_arr = (C.c_int32 * max(1, len(taps)))(*[int(t) for t in taps])
+        nbytes = lib.b2s_llama_backward_workspace_bytes(C.byref(w), rows_bwd, n_dl)
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        _lib.check(lib.b2s_llama_backward(
+            C.byref(w), C.byref(wt), C.byref(saved), rows, rows_bwd, cu_seqlens.data_ptr(), num_seqs_bwd,
+            int(max_seqlen), d_logits.data_ptr(), dl_rows.data_ptr(), n_dl, tap_arr, len(taps) if pairs else 0,
+            None if not pairs else tap_rows_a.data_ptr(), None if not pairs else tap_rows_b.data_ptr(),
+            None if not pairs else tap_coef.data_ptr(), pairs, dh.data_ptr(), ws.data_ptr(), nbytes,
+            torch.cuda.current_stream().cuda_stream), "llama_backward")
+        return dh
 
     # ------------------------------------------------------------------------------------------ packed prefill
     def prefill_packed(self, h: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, positions: torch.Tensor,

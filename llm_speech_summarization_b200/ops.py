@@ -121,12 +121,15 @@ def conv0_ln_gelu(wave: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gamma: t
     return out
 
 
-def embed_splice(table: torch.Tensor, audio: Optional[torch.Tensor], row_src: torch.Tensor) -> torch.Tensor:
+def embed_splice(table: torch.Tensor, audio: Optional[torch.Tensor], row_src: torch.Tensor,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(table, audio, row_src)
     assert table.dtype == torch.bfloat16 and row_src.dtype == torch.int32
     C_ = table.shape[1]
     rows = row_src.numel()
-    out = torch.empty(rows, C_, device=table.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(rows, C_, device=table.device, dtype=torch.float32)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == (rows, C_)
     _lib.check(_lib.load().b2s_embed_splice_fwd(table.data_ptr(), _ptr(audio), row_src.data_ptr(), out.data_ptr(), rows,
                                                 C_, _stream()), "embed_splice")
     return out
@@ -223,6 +226,16 @@ def kd_ce_loss_bwd(student: torch.Tensor, teacher: torch.Tensor, labels: torch.T
                                               teacher.stride(0), rows, V, labels.data_ptr(), res.lse_s.data_ptr(),
                                               res.lse_t.data_ptr(), res.coef_kd.data_ptr(), res.coef_ce.data_ptr(),
                                               out.data_ptr(), out.stride(0), _stream()), "kd_ce_loss_bwd")
+    return out
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """out[i] = src[index[i]] for fp32 rows (index < 0 -> zeros)."""
+    _need_cuda(src, index)
+    assert src.dtype == torch.float32 and src.is_contiguous() and index.dtype == torch.int32
+    out = torch.empty(index.numel(), src.shape[1], device=src.device, dtype=torch.float32)
+    _lib.check(_lib.load().b2s_gather_rows_f32(src.data_ptr(), index.data_ptr(), out.data_ptr(), index.numel(),
+                                               src.shape[1], _stream()), "gather_rows")
     return out
 
 

@@ -38,6 +38,8 @@ class StepPlan:
     L_text: List[int]
     seg: Optional[torch.Tensor] = None        # int64 [sumR] utterance index of each response row
     resp_len_f: Optional[torch.Tensor] = None  # fp32 [B]
+    audio_rows: Optional[torch.Tensor] = None  # int32 [B*A] packed row of every audio embedding (student sequences)
+    student_rows_total: int = 0                # rows of all student sequences (they are packed first)
 
 
 def build_plan(prefix: Sequence[int], suffix: Sequence[int], n_audio: int, text_ids: Sequence[Sequence[int]],
@@ -83,9 +85,12 @@ def build_plan(prefix: Sequence[int], suffix: Sequence[int], n_audio: int, text_
             t_rows.extend(range(cu[B + i + 1] - R, cu[B + i + 1]))
         labels.extend(list(resp_ids[i])[1:] + [-1])
         offs.append(offs[-1] + R)
+    P = len(prefix)
+    audio_rows = [cu[i] + P + r for i in range(B) for r in range(n_audio)]
     return dict(row_src=row_src, cu_seqlens=cu, positions=positions, student_rows=s_rows, teacher_rows=t_rows,
                 labels=labels, row_offsets=offs, max_seqlen=max(L_audio + L_text), rows=cu[-1], sum_r=offs[-1],
-                resp_lens=resp_lens, L_audio=L_audio, L_text=L_text)
+                resp_lens=resp_lens, L_audio=L_audio, L_text=L_text, audio_rows=audio_rows,
+                student_rows_total=cu[B])
 
 
 class AudioPromptStep:
@@ -121,7 +126,8 @@ class AudioPromptStep:
                         seg=torch.tensor([i for i, R in enumerate(d["resp_lens"]) for _ in range(R)],
                                          dtype=torch.int64).pin_memory().to(device, non_blocking=True),
                         resp_len_f=torch.tensor(d["resp_lens"], dtype=torch.float32).pin_memory().to(
-                            device, non_blocking=True))
+                            device, non_blocking=True),
+                        audio_rows=i32(d["audio_rows"]), student_rows_total=d["student_rows_total"])
 
     @torch.no_grad()
     def forward_losses(self, waves: torch.Tensor, text_ids, resp_ids, plan: Optional[StepPlan] = None,
@@ -170,6 +176,57 @@ class AudioPromptStep:
             out["teacher_logits"] = t_log
             out["kd_stats"] = res
             out["plan"] = plan
+        return out
+
+    @torch.no_grad()
+    def llm_forward_backward(self, audio: torch.Tensor, text_ids, resp_ids, loss_scale: float = 1.0,
+                             plan: Optional[StepPlan] = None) -> Dict[str, torch.Tensor]:
+        """The LLM half of the TRAINING step for projected audio embeddings `audio` (B, A, C) fp32:
+        splice -> training forward (activations kept) -> losses -> backward through the frozen LLM
+        (REF/trainer.py:299-374). Returns the per-utterance losses and `d_audio_embeds` (B, A, C) fp32 =
+        d( sum_u loss_scale * total_u ) / d audio  -- loss_scale = 1 / grad_accum_interval in the reference."""
+        dev = audio.device
+        B, A, Cdim = audio.shape
+        if plan is None:
+            plan = self.plan(A, text_ids, resp_ids, dev)
+        with_teacher = self.use_ld or self.use_fd
+        saved, st = self.llm.alloc_saved(plan.rows, dev)
+        ops.embed_splice(self.llm.model.embed_tokens.weight, audio.reshape(B * A, Cdim).contiguous(), plan.row_src,
+                         out=st["h"][0])
+        s_rows = plan.logit_rows[:plan.sum_r]
+        t_rows = plan.logit_rows[plan.sum_r:] if with_teacher else None
+        fd_layers = [l for l in self.fd_layers if l > 0] if self.use_fd else []
+        logits, fd_sq, taps = self.llm.forward_train_packed(
+            saved, st, plan.cu_seqlens, plan.max_seqlen, plan.positions, plan.logit_rows, tap_layers=fd_layers,
+            tap_rows_a=s_rows if fd_layers else None, tap_rows_b=t_rows if fd_layers else None)
+        s_log = logits[:plan.sum_r]
+        t_log = logits[plan.sum_r:] if with_teacher else s_log
+        res = ops.kd_ce_loss(s_log, t_log, plan.labels, plan.row_offsets,
+                             scale_kd=(self.w_ld if self.use_ld else 0.0) * loss_scale, scale_ce=self.w_ntp * loss_scale)
+        out = {"ntp_loss": res.loss_ntp}
+        total = self.w_ntp * res.loss_ntp
+        if self.use_ld:
+            out["ld_loss"] = res.loss_ld
+            total = total + self.w_ld * res.loss_ld
+        tap_coef = None
+        if self.use_fd:
+            fd = torch.zeros(B, device=dev, dtype=torch.float32)
+            if fd_sq is not None:
+                fd.index_add_(0, plan.seg, fd_sq.sum(dim=0))
+                fd = fd / (plan.resp_len_f * Cdim)
+                # d fd_u / d h_s = 2 (h_s - h_t) / (R_u * C) per tapped layer
+                tap_coef = (2.0 * self.w_fd * loss_scale / (plan.resp_len_f * Cdim))[plan.seg].contiguous()
+            out["fd_loss"] = fd
+            total = total + self.w_fd * fd
+        out["total_loss"] = total
+        d_logits = ops.kd_ce_loss_bwd(s_log, t_log, plan.labels, res)
+        ns = len(plan.L_audio)
+        dh0 = self.llm.backward_packed(saved, st, plan.student_rows_total, plan.cu_seqlens, ns, max(plan.L_audio),
+                                       d_logits, s_rows, taps if tap_coef is not None else [],
+                                       s_rows if tap_coef is not None else None,
+                                       t_rows if tap_coef is not None else None, tap_coef)
+        out["d_audio_embeds"] = ops.gather_rows(dh0, plan.audio_rows).view(B, A, Cdim)
+        out["plan"] = plan
         return out
 
     def __call__(self, waves_host: torch.Tensor, text_ids, resp_ids, device) -> Dict[str, float]:

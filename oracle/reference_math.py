@@ -321,8 +321,16 @@ def train_step_losses(enc_sd, llm_sd, enc_cfg: EncoderCfg, llm_cfg: LlmCfg, toke
     teacher forward under no_grad (:337-344), KD on the last R rows (:349-352), FD MSE over the tapped hidden states
     (:358-370), total = w_ntp*ntp + w_ld*ld + w_fd*fd (:325-370). `text_ids` / `resp_ids` are the collate outputs
     (leading BOS already stripped once, REF/trainer.py:155-156)."""
-    embed = lambda ids: F.embedding(ids, llm_sd["model.embed_tokens.weight"])
     audio_embeds = audio_encoder_forward(enc_sd, audio[None, :], enc_cfg)  # (1, A, llm_dim)
+    return losses_from_audio_embeds(audio_embeds, llm_sd, llm_cfg, tokenizer, text_ids, resp_ids, use_ld=use_ld,
+                                    use_fd=use_fd, w_ntp=w_ntp, w_ld=w_ld, w_fd=w_fd, fd_layers=fd_layers, keep=keep)
+
+
+def losses_from_audio_embeds(audio_embeds, llm_sd, llm_cfg: LlmCfg, tokenizer, text_ids, resp_ids, *, use_ld=True,
+                             use_fd=True, w_ntp=0.5, w_ld=0.5, w_fd=1.0, fd_layers=(0, 5, 11, 17, 23), keep=False):
+    """The LLM half of the step (REF/trainer.py:299-370) as a differentiable function of the projected audio
+    embeddings (1, A, llm_dim): autograd through this is the oracle for the LLM backward."""
+    embed = lambda ids: F.embedding(ids, llm_sd["model.embed_tokens.weight"])
     a_seq, a_mask, t_seq, t_mask = batch_full_embed_sequence(
         audio_embeds, [text_ids], [resp_ids], tokenizer, embed, llm_cfg.llm_type, process_text=(use_ld or use_fd))
     out = {}
