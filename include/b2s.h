@@ -69,6 +69,16 @@ typedef struct {
   int64_t ld2;
   int32_t block_n;   /* 0 = auto, else 64/128/256 */
   int32_t cta_group; /* 0 = auto, else 1/2 */
+  /* backward GEMMs (no transposed copies): b_mn = W stored [K rows, N cols] (dgrad dX = dY . W with W in nn.Linear
+   * layout); a_mn = A stored [K rows, M cols], reduction also runs over k_batches batches of both operands
+   * (wgrad dW[m,n] = sum_{b,t} dY[b,t,m] X[b,t,n], k_per_tap = rows per batch); epi 5 = out_f32 += acc (atomic). */
+  int32_t a_mn, b_mn, k_batches;
+  int64_t w_row_stride;   /* MN-major W: elements between rows (0 = w_cols) */
+  int64_t w_batch_stride; /* MN-major W: elements between k-batches */
+  int32_t k_splits;       /* 0 = auto (epi 5 only), 1 = none */
+  int32_t b_tap_atoms;    /* grouped-conv wgrad: N atom j = W columns [g*w_group_off, +64) at rows k + j - a_pad */
+  int32_t out_group_rows; /* output row offset per group */
+  int32_t out_group_cols; /* output column offset per group (default N when out_group_rows == 0) */
 } b2s_gemm_args;
 int b2s_gemm_bf16(const b2s_gemm_args* args, void* stream);
 /* measurement hook (bench.py roofline leg): while enabled, every GEMM launch is bracketed by CUDA events on its

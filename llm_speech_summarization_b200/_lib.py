@@ -25,7 +25,9 @@ class GemmArgs(C.Structure):
         ("epi", c_int), ("act", c_int), ("bias", c_void_p), ("out", c_void_p), ("ldo", c_int64),
         ("out_batch_rows", c_int64), ("resid", c_void_p), ("rope_cs", c_void_p), ("positions", c_void_p),
         ("rope_cols", c_int), ("resid_bcast", c_int), ("out2", c_void_p), ("ld2", c_int64), ("block_n", c_int),
-        ("cta_group", c_int),
+        ("cta_group", c_int), ("a_mn", c_int), ("b_mn", c_int), ("k_batches", c_int), ("w_row_stride", c_int64),
+        ("w_batch_stride", c_int64), ("k_splits", c_int), ("b_tap_atoms", c_int), ("out_group_rows", c_int),
+        ("out_group_cols", c_int),
     ]
 
 

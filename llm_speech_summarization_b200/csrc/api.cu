@@ -120,6 +120,15 @@ int b2s_gemm_bf16(const b2s_gemm_args* a, void* stream) {
   g.rope_cols = a->rope_cols;
   g.block_n = a->block_n;
   g.cta_group = a->cta_group;
+  g.a_mn = a->a_mn;
+  g.b_mn = a->b_mn;
+  g.k_batches = a->k_batches;
+  g.w_row_stride = a->w_row_stride;
+  g.w_batch_stride = a->w_batch_stride;
+  g.k_splits = a->k_splits;
+  g.b_tap_atoms = a->b_tap_atoms;
+  g.out_group_rows = a->out_group_rows;
+  g.out_group_cols = a->out_group_cols;
   return gemm_bf16_launch(g, S(stream));
 }
 

@@ -56,17 +56,6 @@ struct AttnParams {
   float* lse;  // optional [rows, Hq]: log2-domain log-sum-exp of the scaled scores (saved for the backward)
 };
 
-// MN-major, 128B-swizzled B operand (V tile: rows = keys at 128 B pitch, 64-element column atoms `lbo` bytes apart)
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((1024 >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -180,7 +169,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
         for (int k = 0; k < kBN / 16; ++k) {
           const uint64_t pdesc = ptx::make_kmajor_sw128_desc(sP + (k >> 2) * (kBM * 128) + (k & 3) * 32);
-          const uint64_t vdesc = make_mnmajor_sw128_desc(sV + st * C::kVBytes + k * 2048, kBN * 128);
+          const uint64_t vdesc = ptx::make_mnmajor_sw128_desc(sV + st * C::kVBytes + k * 2048, kBN * 128);
           ptx::umma_bf16<1>(tmem_base + C::kOCol, pdesc, vdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         }
         ptx::umma_commit<1>(bar_o);

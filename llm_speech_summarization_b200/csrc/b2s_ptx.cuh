@@ -245,6 +245,18 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major, 128B-swizzled operand: each 64-element M/N atom is a block of rows (one per k) at 128 B pitch,
+// atoms `lbo_bytes` apart (LBO), 8-k groups 1024 B apart (SBO). K advances by 16 rows = 2048 bytes.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((1024 >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16: bf16 A/B (K-major both), fp32 accumulate, shape M x N.
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
   return (1u << 4)                              // c_format = F32

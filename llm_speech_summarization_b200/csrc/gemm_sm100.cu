@@ -74,14 +74,23 @@ struct KParams {
   const float* rope_cs;
   const int* positions;
   int rope_cols;
+  // MN-major operands / reduction over batches / split-K (backward GEMMs)
+  int a_mn, b_mn;         // operand stored [k rows, m|n cols] row-major instead of K-major
+  int kb_per_batch;       // k-blocks per reduction batch (num_kb = k_batches * kb_per_batch)
+  int k_splits, kb_per_split;
+  int tiles_per_split;
+  int b_tap_atoms;        // MN-major B: 64-column atom j of the N axis = the same columns shifted by j - a_pad rows
+  int og_rows, og_cols;   // output offset per group: rows += g * og_rows, cols += g * og_cols
 };
 
 struct TileCoord {
-  int b, g, m_t, n_t;
+  int b, g, m_t, n_t, split;
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
   constexpr int kGroupM = 8;
+  const int split = t / p.tiles_per_split;
+  t -= split * p.tiles_per_split;
   const int per_bg = p.m_tiles * p.n_tiles;
   const int bg = t / per_bg;
   const int r = t - bg * per_bg;
@@ -95,6 +104,7 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
   c.n_t = rr / gsz;
   c.b = bg / p.groups;
   c.g = bg - c.b * p.groups;
+  c.split = split;
   return c;
 }
 
@@ -157,6 +167,25 @@ __device__ __forceinline__ void emit_f32(uint32_t stg, const float (&v)[32], int
     if (row < rows_valid && chunk * 4 < cols_valid) {
       *reinterpret_cast<float4*>(out0 + row * ld + chunk * 4) =
           make_float4(x[i].x + r[i].x, x[i].y + r[i].y, x[i].z + r[i].z, x[i].w + r[i].w);
+    }
+  }
+  __syncwarp();
+}
+
+// out += v (fp32 reduction in L2: split-K partial sums and gradient accumulation across micro-batches)
+__device__ __forceinline__ void emit_accum_f32(uint32_t stg, const float (&v)[32], int lane, float* out0, long long ld,
+                                               int rows_valid, int cols_valid) {
+  stage_write(stg, v, lane);
+  __syncwarp();
+  const int chunk = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    const float4 x = stage_read(stg, row, chunk);
+    if (row < rows_valid && chunk * 4 < cols_valid) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out0 + row * ld + chunk * 4), "f"(x.x),
+                   "f"(x.y), "f"(x.z), "f"(x.w)
+                   : "memory");
     }
   }
   __syncwarp();
@@ -252,24 +281,57 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int m0 = tc.m_t * (128 * CG) + static_cast<int>(cta_rank) * 128;
       const int n0 = tc.g * p.w_group_off + tc.n_t * BN + static_cast<int>(cta_rank) * C::kBRows;
       const int a_c0_base = tc.g * p.a_group_off;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int kb_lo = tc.split * p.kb_per_split;
+      const int kb_hi = min(p.num_kb, kb_lo + p.kb_per_split);
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-        const int tap = kb / p.kb_per_tap;
-        const int kk = (kb - tap * p.kb_per_tap) * kBlockK;
         const uint32_t sa = smem_base + stage * C::kStageBytes;
         const uint32_t sb = sa + kATileBytes;
         if (CG == 1) {
           ptx::mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
-          ptx::tma_load_3d(&tmap_a, full_bar(stage), sa, a_c0_base + kk, m0 + tap - p.a_pad, tc.b);
-          ptx::tma_load_2d(&tmap_w, full_bar(stage), sb, tap * p.k_per_tap + kk, n0);
+        } else if (cta_rank == 0) {
+          ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::kStageBytes);
         } else {
-          if (cta_rank == 0) {
-            ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+          ptx::mbar_arrive_cluster(full_bar(stage), 0);
+        }
+        if ((p.a_mn | p.b_mn) == 0) {
+          const int tap = kb / p.kb_per_tap;
+          const int kk = (kb - tap * p.kb_per_tap) * kBlockK;
+          if (CG == 1) {
+            ptx::tma_load_3d(&tmap_a, full_bar(stage), sa, a_c0_base + kk, m0 + tap - p.a_pad, tc.b);
+            ptx::tma_load_2d(&tmap_w, full_bar(stage), sb, tap * p.k_per_tap + kk, n0);
           } else {
-            ptx::mbar_arrive_cluster(full_bar(stage), 0);
+            ptx::tma_load_3d_2sm(&tmap_a, full_bar(stage), sa, a_c0_base + kk, m0 + tap - p.a_pad, tc.b);
+            ptx::tma_load_2d_2sm(&tmap_w, full_bar(stage), sb, tap * p.k_per_tap + kk, n0);
           }
-          ptx::tma_load_3d_2sm(&tmap_a, full_bar(stage), sa, a_c0_base + kk, m0 + tap - p.a_pad, tc.b);
-          ptx::tma_load_2d_2sm(&tmap_w, full_bar(stage), sb, tap * p.k_per_tap + kk, n0);
+        } else {
+          // MN-major operands: the reduction index walks ROWS of the source (k-batch kbat, row kk); a tile is a
+          // set of [64 k-rows x 64 columns] boxes, one per 64-wide M / N atom, 8 KiB apart.
+          const int kbat = kb / p.kb_per_batch;
+          const int kk = (kb - kbat * p.kb_per_batch) * kBlockK;
+          if (p.a_mn) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+              if (CG == 1) ptx::tma_load_3d(&tmap_a, full_bar(stage), sa + a * 8192, a_c0_base + m0 + a * 64, kk, kbat);
+              else ptx::tma_load_3d_2sm(&tmap_a, full_bar(stage), sa + a * 8192, a_c0_base + m0 + a * 64, kk, kbat);
+            }
+          } else {
+            if (CG == 1) ptx::tma_load_3d(&tmap_a, full_bar(stage), sa, a_c0_base + kk, m0, tc.b);
+            else ptx::tma_load_3d_2sm(&tmap_a, full_bar(stage), sa, a_c0_base + kk, m0, tc.b);
+          }
+#pragma unroll
+          for (int a = 0; a < C::kBRows / 64; ++a) {
+            int col, row;
+            if (p.b_tap_atoms) {
+              col = tc.g * p.w_group_off;
+              row = kk + (tc.n_t * BN + static_cast<int>(cta_rank) * C::kBRows) / 64 + a - p.a_pad;
+            } else {
+              col = n0 + a * 64;
+              row = kk;
+            }
+            if (CG == 1) ptx::tma_load_3d(&tmap_w, full_bar(stage), sb + a * 8192, col, row, kbat);
+            else ptx::tma_load_3d_2sm(&tmap_w, full_bar(stage), sb + a * 8192, col, row, kbat);
+          }
         }
         if (++stage == kStages) {
           stage = 0;
@@ -279,7 +341,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp == 1 && lane == 0 && cta_rank == 0) {
     // ============================== MMA issuer ==============================
-    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128 * CG, BN);
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(128 * CG, BN) | (p.a_mn ? (1u << 15) : 0u) |
+                           (p.b_mn ? (1u << 16) : 0u);
+    // K step of 16 inside a stage: K-major = 32 bytes along the swizzled row; MN-major = 16 rows of 128 bytes
+    const uint32_t a_kstep = p.a_mn ? (2048u >> 4) : 2u;
+    const uint32_t b_kstep = p.b_mn ? (2048u >> 4) : 2u;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -289,19 +355,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int split = t / p.tiles_per_split;
+      const int kb_lo = split * p.kb_per_split;
+      const int kb_hi = min(p.num_kb, kb_lo + p.kb_per_split);
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
         const uint32_t sa = smem_base + stage * C::kStageBytes;
-        const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa);
-        const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sa + kATileBytes);
+        const uint64_t adesc = p.a_mn ? ptx::make_mnmajor_sw128_desc(sa, 8192) : ptx::make_kmajor_sw128_desc(sa);
+        const uint64_t bdesc = p.b_mn ? ptx::make_mnmajor_sw128_desc(sa + kATileBytes, 8192)
+                                      : ptx::make_kmajor_sw128_desc(sa + kATileBytes);
 #pragma unroll
         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-          ptx::umma_bf16<CG>(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_bf16<CG>(tmem_d, adesc + a_kstep * k, bdesc + b_kstep * k, idesc,
+                             ((kb - kb_lo) | k) != 0 ? 1u : 0u);
         }
         ptx::umma_commit<CG>(empty_bar(stage));  // frees this smem stage (both CTAs) when the MMAs retire
-        if (kb == p.num_kb - 1) ptx::umma_commit<CG>(tfull_bar(as));
+        if (kb == kb_hi - 1) ptx::umma_commit<CG>(tfull_bar(as));
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1u;
@@ -325,7 +395,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int m0w = tc.m_t * (128 * CG) + static_cast<int>(cta_rank) * 128 + quarter * 32;  // warp's first row
       const int rows_valid = max(0, min(32, p.M - m0w));
       const bool row_ok = lane < rows_valid;
-      const long long orow0 = static_cast<long long>(tc.b) * p.out_batch_rows + m0w;
+      const long long orow0 = static_cast<long long>(tc.b) * p.out_batch_rows +
+                              static_cast<long long>(tc.g) * p.og_rows + m0w;
       const int ncol0 = tc.n_t * BN;  // column inside the group
       const float* bias = p.bias ? p.bias + static_cast<long long>(tc.g) * p.N : nullptr;
 
@@ -333,7 +404,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + lane_base + as * BN;
 
-      if (p.epi == EPI_BF16 || p.epi == EPI_F32 || p.epi == EPI_RESID_F32) {
+      if (p.epi == EPI_BF16 || p.epi == EPI_F32 || p.epi == EPI_RESID_F32 || p.epi == EPI_ACCUM_F32) {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           const int col = ncol0 + c * 32;
@@ -348,19 +419,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (p.out2 != nullptr) {  // training: keep the pre-activation (acc + bias) for the backward
             add_bias_act(v, bias ? bias + col : nullptr, ACT_NONE);
             emit_bf16(stg, v, lane,
-                      reinterpret_cast<__nv_bfloat16*>(p.out2) + orow0 * p.ld2 + static_cast<long long>(tc.g) * p.N + col,
+                      reinterpret_cast<__nv_bfloat16*>(p.out2) + orow0 * p.ld2 + static_cast<long long>(tc.g) * p.og_cols + col,
                       p.ld2, rows_valid, valid);
             add_bias_act(v, nullptr, p.act);
           } else {
             add_bias_act(v, bias ? bias + col : nullptr, p.act);
           }
-          const long long off0 = orow0 * p.ldo + static_cast<long long>(tc.g) * p.N + col;
+          const long long off0 = orow0 * p.ldo + static_cast<long long>(tc.g) * p.og_cols + col;
           if (p.epi == EPI_BF16) {
             emit_bf16(stg, v, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, valid);
+          } else if (p.epi == EPI_ACCUM_F32) {
+            emit_accum_f32(stg, v, lane, reinterpret_cast<float*>(p.out) + off0, p.ldo, rows_valid, valid);
           } else {
             // resid_bcast: the residual is indexed by the row inside the batch only (e.g. a positional table)
             const long long roff0 = p.resid_bcast
-                                        ? static_cast<long long>(m0w) * p.ldo + static_cast<long long>(tc.g) * p.N + col
+                                        ? static_cast<long long>(m0w) * p.ldo + static_cast<long long>(tc.g) * p.og_cols + col
                                         : off0;
             emit_f32(stg, v, lane, reinterpret_cast<float*>(p.out) + off0,
                      p.epi == EPI_RESID_F32 ? p.resid + roff0 : nullptr, p.ldo, rows_valid, valid);
@@ -573,7 +646,18 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   B2S_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(a.out) & 15) == 0,
               "gemm: pointers must be 16-byte aligned");
-  B2S_REQUIRE(a.epi >= EPI_BF16 && a.epi <= EPI_F32, "gemm: bad epilogue id %d", a.epi);
+  B2S_REQUIRE(a.epi >= EPI_BF16 && a.epi <= EPI_ACCUM_F32, "gemm: bad epilogue id %d", a.epi);
+  const bool mn = a.a_mn || a.b_mn;
+  if (mn) {
+    B2S_REQUIRE(a.taps == 1 && (a.epi == EPI_BF16 || a.epi == EPI_F32 || a.epi == EPI_ACCUM_F32 || a.epi == EPI_RESID_F32),
+                "gemm: MN-major operands support plain epilogues and taps == 1 only");
+    B2S_REQUIRE(!a.a_mn || a.batches == 1, "gemm: MN-major A reduces over k_batches; tile batches must be 1");
+    B2S_REQUIRE(a.a_mn || a.k_batches <= 1, "gemm: k_batches needs MN-major A");
+  } else {
+    B2S_REQUIRE(a.k_batches <= 1 && !a.b_tap_atoms, "gemm: k_batches / b_tap_atoms need MN-major operands");
+  }
+  if (a.k_splits > 1) B2S_REQUIRE(a.epi == EPI_ACCUM_F32, "gemm: split-K needs the accumulate epilogue");
+  if (a.epi == EPI_ACCUM_F32) B2S_REQUIRE(a.bias == nullptr && a.act == ACT_NONE, "gemm: accumulate epilogue is plain");
   if (a.epi == EPI_RESID_F32) B2S_REQUIRE(a.resid != nullptr, "gemm: residual epilogue needs resid");
   if (a.epi == EPI_ROPE) {
     B2S_REQUIRE(a.rope_cs && a.positions && a.N % 128 == 0 && a.rope_cols % 128 == 0,
@@ -607,7 +691,29 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   B2S_REQUIRE(total < (1LL << 31), "gemm: too many tiles");
   p.total_tiles = static_cast<int>(total);
   p.kb_per_tap = (a.k_per_tap + kBlockK - 1) / kBlockK;
-  p.num_kb = p.kb_per_tap * a.taps;
+  const int k_batches = a.k_batches > 0 ? a.k_batches : 1;
+  p.kb_per_batch = p.kb_per_tap;
+  p.num_kb = p.kb_per_tap * a.taps * k_batches;
+  p.a_mn = a.a_mn ? 1 : 0;
+  p.b_mn = a.b_mn ? 1 : 0;
+  p.b_tap_atoms = a.b_tap_atoms ? 1 : 0;
+  p.og_rows = a.out_group_rows;
+  p.og_cols = a.out_group_cols > 0 || a.out_group_rows > 0 ? a.out_group_cols : a.N;
+  {
+    const int sms = num_sms();
+    int splits = a.k_splits;
+    if (splits == 0) {  // auto: only the accumulate epilogue can split
+      splits = 1;
+      if (a.epi == EPI_ACCUM_F32 && total > 0) splits = static_cast<int>((sms / cg) / total);
+    }
+    if (splits > p.num_kb / 4) splits = p.num_kb / 4;
+    if (splits < 1) splits = 1;
+    p.kb_per_split = (p.num_kb + splits - 1) / splits;
+    p.k_splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.tiles_per_split = p.total_tiles;
+    B2S_REQUIRE(total * p.k_splits < (1LL << 31), "gemm: too many tiles");
+    p.total_tiles = p.total_tiles * p.k_splits;
+  }
   p.k_per_tap = a.k_per_tap;
   p.a_pad = a.a_pad;
   p.a_group_off = a.a_group_off;
@@ -628,16 +734,29 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
 
   CUtensorMap ta, tw;
   {
+    const int nb = a.a_mn ? k_batches : a.batches;
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(a.a_dim0), static_cast<cuuint64_t>(a.a_rows),
-                          static_cast<cuuint64_t>(a.batches)};
+                          static_cast<cuuint64_t>(nb)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(a.a_row_stride) * 2,
-                             static_cast<cuuint64_t>(a.batches > 1 ? a.a_batch_stride : a.a_row_stride * a.a_rows) * 2};
+                             static_cast<cuuint64_t>(nb > 1 ? a.a_batch_stride : a.a_row_stride * a.a_rows) * 2};
     if (strides[1] == 0) strides[1] = strides[0];
-    cuuint32_t box[3] = {kBlockK, 128, 1};
+    cuuint32_t box[3] = {kBlockK, a.a_mn ? 64u : 128u, 1};
     int rc = encode_map(&ta, a.A, 3, dims, strides, box);
     if (rc != B2S_OK) return rc;
   }
-  {
+  if (a.b_mn) {
+    // MN-major W: [w_rows = reduction rows per k-batch, w_cols] with explicit row / batch strides
+    const long long rs = a.w_row_stride > 0 ? a.w_row_stride : a.w_cols;
+    B2S_REQUIRE(rs % 8 == 0 && a.w_batch_stride % 8 == 0, "gemm: W strides must be multiples of 8 elements");
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(a.w_cols), static_cast<cuuint64_t>(a.w_rows),
+                          static_cast<cuuint64_t>(k_batches)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(rs) * 2,
+                             static_cast<cuuint64_t>(k_batches > 1 ? a.w_batch_stride : rs * a.w_rows) * 2};
+    if (strides[1] == 0) strides[1] = strides[0];
+    cuuint32_t box[3] = {kBlockK, 64, 1};
+    int rc = encode_map(&tw, a.W, 3, dims, strides, box);
+    if (rc != B2S_OK) return rc;
+  } else {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(a.w_cols), static_cast<cuuint64_t>(a.w_rows)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(a.w_cols) * 2};
     cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(bn / cg)};

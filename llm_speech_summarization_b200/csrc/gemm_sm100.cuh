@@ -11,6 +11,7 @@ enum EpiMode : int {
   EPI_SWIGLU = 2,     // out_bf16[:, j] = silu(acc[:, j]) * acc[:, j + BN/2] per BN-wide tile (gate|up packed)
   EPI_ROPE = 3,       // out_bf16 = rotate-half RoPE over 128-wide heads for cols < rope_cols, else passthrough
   EPI_F32 = 4,        // out_f32  = act(acc + bias)
+  EPI_ACCUM_F32 = 5,  // out_f32 += acc + bias   (atomic fp32 adds: split-K partials, gradient accumulation)
 };
 
 enum ActMode : int { ACT_NONE = 0, ACT_GELU = 1 };
@@ -58,6 +59,19 @@ struct GemmArgs {
   // tuning (0 = auto)
   int block_n;    // 64 / 128 / 256
   int cta_group;  // 1 / 2
+  // ---- backward GEMMs: MN-major operands (no transposed copies), reduction over batches, split-K
+  //   b_mn: W is [w_rows = K, w_cols = N-extent] row-major (dgrad: dX = dY . W with W in nn.Linear layout)
+  //   a_mn: A is [a_rows = K, a_dim0 = M-extent] row-major; the reduction additionally runs over k_batches
+  //         batches of both operands (wgrad: dW[m, n] = sum_{b, t} dY[b, t, m] * X[b, t, n]); k_per_tap = rows per batch
+  int a_mn;
+  int b_mn;
+  int k_batches;            // 0/1 = none
+  long long w_row_stride;   // MN-major W: elements between rows (0 = w_cols) -- overlapping conv windows allowed
+  long long w_batch_stride; // MN-major W: elements between k-batches
+  int k_splits;             // 0 = auto (EPI_ACCUM_F32 only), 1 = none
+  int b_tap_atoms;          // grouped-conv wgrad: N atom j reads W columns [g*w_group_off, +64) at rows k + j - a_pad
+  int out_group_rows;       // output row offset per group   (default 0)
+  int out_group_cols;       // output column offset per group (default N when out_group_rows == 0)
 };
 
 int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream);

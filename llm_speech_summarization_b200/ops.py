@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import GemmArgs
 
-EPI_BF16, EPI_RESID_F32, EPI_SWIGLU, EPI_ROPE, EPI_F32 = 0, 1, 2, 3, 4
+EPI_BF16, EPI_RESID_F32, EPI_SWIGLU, EPI_ROPE, EPI_F32, EPI_ACCUM_F32 = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_GELU = 0, 1
 
 
@@ -56,6 +56,49 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     g.rope_cs, g.positions, g.rope_cols = _ptr(rope_cs), _ptr(positions), rope_cols
     g.block_n, g.cta_group = block_n, cta_group
     _lib.check(_lib.load().b2s_gemm_bf16(C.byref(g), _stream()), "gemm")
+    return out
+
+
+def gemm_dgrad(dy: torch.Tensor, w: torch.Tensor, *, out_f32: bool = False, block_n: int = 0,
+               cta_group: int = 0) -> torch.Tensor:
+    """dx[M, K] = dy[M, N] @ w[N, K] with w in its nn.Linear [out, in] layout (MN-major B operand, no transpose)."""
+    _need_cuda(dy, w)
+    assert dy.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and dy.is_contiguous() and w.is_contiguous()
+    M, N = dy.shape
+    K = w.shape[1]
+    assert w.shape[0] == N
+    out = torch.empty(M, K, device=dy.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    g = GemmArgs()
+    g.A, g.a_dim0, g.a_row_stride, g.a_batch_stride, g.a_rows = dy.data_ptr(), N, N, 0, M
+    g.W, g.w_rows, g.w_cols, g.b_mn = w.data_ptr(), N, K, 1
+    g.M, g.N, g.batches, g.groups, g.taps, g.k_per_tap = M, K, 1, 1, 1, N
+    g.epi = EPI_F32 if out_f32 else EPI_BF16
+    g.out, g.ldo = out.data_ptr(), K
+    g.block_n, g.cta_group = block_n, cta_group
+    _lib.check(_lib.load().b2s_gemm_bf16(C.byref(g), _stream()), "gemm_dgrad")
+    return out
+
+
+def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, *, k_splits: int = 0, block_n: int = 0,
+               cta_group: int = 0) -> torch.Tensor:
+    """out[N, K] += sum over rows of dy[.., N]^T x[.., K] (both operands MN-major, atomic fp32 accumulation).
+    dy / x: bf16 [rows, N] / [rows, K] or batched [B, T, N] / [B, T, K]."""
+    _need_cuda(dy, x, out)
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and dy.is_contiguous() and x.is_contiguous()
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    if dy.dim() == 2:
+        dy, x = dy[None], x[None]
+    B, T, N = dy.shape
+    K = x.shape[2]
+    assert out.shape == (N, K) and x.shape[:2] == (B, T)
+    g = GemmArgs()
+    g.A, g.a_dim0, g.a_row_stride, g.a_batch_stride, g.a_rows, g.a_mn = dy.data_ptr(), N, N, T * N, T, 1
+    g.W, g.w_rows, g.w_cols, g.b_mn, g.w_row_stride, g.w_batch_stride = x.data_ptr(), T, K, 1, K, T * K
+    g.M, g.N, g.batches, g.groups, g.taps, g.k_per_tap, g.k_batches = N, K, 1, 1, 1, T, B
+    g.epi = EPI_ACCUM_F32
+    g.out, g.ldo = out.data_ptr(), K
+    g.k_splits, g.block_n, g.cta_group = k_splits, block_n, cta_group
+    _lib.check(_lib.load().b2s_gemm_bf16(C.byref(g), _stream()), "gemm_wgrad")
     return out
 
 

@@ -153,3 +153,66 @@ def test_gemm_rejects_bad_args(cuda):
     w = torch.zeros(16, 60, device=cuda, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError):
         ops.gemm(a, w)
+
+
+# ------------------------------------------------------------------------------------------------ backward GEMMs
+@pytest.mark.parametrize("bn,cg", [(256, 1), (128, 1), (64, 1), (256, 2), (128, 2)],
+                         ids=["bn256cg1", "bn128cg1", "bn64cg1", "bn256cg2", "bn128cg2"])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 128), (499, 1024, 1024), (1000, 4096, 1024), (130, 200, 264),
+                                   (998, 512, 1536)])
+def test_gemm_dgrad_mn_major_w(cuda, M, N, K, bn, cg):
+    """dX = dY @ W with W in nn.Linear layout: the B operand is read MN-major (no transposed copy)."""
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    dy = (torch.randn(M, N, generator=g) * 0.5).to(torch.bfloat16).to(cuda)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(cuda)
+    out = ops.gemm_dgrad(dy, w, out_f32=True, block_n=bn, cta_group=cg)
+    ref = dy.float() @ w.float()
+    assert rel_l2(out, ref) < TOL_F32
+    out_bf = ops.gemm_dgrad(dy, w, block_n=bn, cta_group=cg)
+    assert rel_l2(out_bf.float(), ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("bn,cg", [(256, 1), (128, 1), (64, 1), (256, 2), (128, 2)],
+                         ids=["bn256cg1", "bn128cg1", "bn64cg1", "bn256cg2", "bn128cg2"])
+@pytest.mark.parametrize("B,T,N,K,splits", [(1, 128, 128, 64, 1), (1, 499, 1024, 1024, 0), (3, 333, 3072, 1024, 0),
+                                            (2, 1000, 264, 200, 3), (4, 499, 1024, 4096, 1)])
+def test_gemm_wgrad_mn_major_both(cuda, B, T, N, K, splits, bn, cg):
+    """dW += sum_{b,t} dY[b,t,:]^T X[b,t,:]: both operands MN-major, reduction over batches, split-K + atomic adds."""
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    dy = (torch.randn(B, T, N, generator=g) * 0.5).to(torch.bfloat16).to(cuda)
+    x = (torch.randn(B, T, K, generator=g) * 0.5).to(torch.bfloat16).to(cuda)
+    init = torch.randn(N, K, generator=g).to(cuda)
+    out = init.clone()
+    ops.gemm_wgrad(dy, x, out, k_splits=splits, block_n=bn, cta_group=cg)
+    ref = init + torch.einsum("btn,btk->nk", dy.float(), x.float())
+    assert rel_l2(out, ref) < TOL_F32
+    ops.gemm_wgrad(dy, x, out, k_splits=splits, block_n=bn, cta_group=cg)  # accumulates
+    assert rel_l2(out, 2 * ref - init) < TOL_F32
+
+
+@pytest.mark.parametrize("k,s,T", [(3, 2, 1001), (2, 2, 640)])
+def test_gemm_wgrad_strided_conv_view(cuda, k, s, T):
+    """Conv1d weight gradient: X operand = the overlapping window view [B, Tout, k*C] (row stride s*C) read MN-major."""
+    from llm_speech_summarization_b200 import ops
+    from llm_speech_summarization_b200._lib import GemmArgs
+    Cin, Cout, B = 512, 512, 2
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(B, T, Cin, generator=g) * 0.5).to(torch.bfloat16).to(cuda)
+    To = (T - k) // s + 1
+    dy = (torch.randn(B, To, Cout, generator=g) * 0.5).to(torch.bfloat16).to(cuda)
+    out = torch.zeros(Cout, k * Cin, device=cuda)
+    a = GemmArgs()
+    a.A, a.a_dim0, a.a_row_stride, a.a_batch_stride, a.a_rows, a.a_mn = dy.data_ptr(), Cout, Cout, To * Cout, To, 1
+    a.W, a.w_rows, a.w_cols, a.b_mn, a.w_row_stride, a.w_batch_stride = x.data_ptr(), To, k * Cin, 1, s * Cin, T * Cin
+    a.M, a.N, a.batches, a.groups, a.taps, a.k_per_tap, a.k_batches = Cout, k * Cin, 1, 1, 1, To, B
+    a.epi, a.out, a.ldo = ops.EPI_ACCUM_F32, out.data_ptr(), k * Cin
+    ops.gemm_raw(a)
+    # reference: conv1d weight gradient in torch's [Cout, Cin, k] layout -> packed [Cout, k*Cin]
+    xw = x.float().permute(0, 2, 1).requires_grad_(False)
+    w = torch.zeros(Cout, Cin, k, device=cuda, requires_grad=True)
+    y = F.conv1d(xw, w, stride=s)
+    (gw,) = torch.autograd.grad(y, w, dy.float().permute(0, 2, 1))
+    ref = gw.permute(0, 2, 1).reshape(Cout, k * Cin)
+    assert rel_l2(out, ref) < TOL_F32
