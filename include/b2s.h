@@ -313,6 +313,49 @@ int b2s_llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt
                        const int32_t* tap_layers /*host*/, int32_t num_taps, const int32_t* tap_rows_a,
                        const int32_t* tap_rows_b, const float* tap_coef, int32_t pairs, float* dh, void* workspace,
                        size_t workspace_bytes, void* stream);
+/* ---- trainable HuBERT audio encoder (REF/trainer.py:98-105: every AudioEncoder parameter is optimised).
+ * Gradient accumulators: fp32, zeroed by the caller, shaped like the packed tensors of b2s_hubert_weights
+ * (conv_w[i] [512, k*512], wqkv [3H, H], pos_w [H][k][H/groups] = gradient w.r.t. the weight-normed effective
+ * weight; the caller applies the weight-norm chain rule once per optimizer step). Accumulated with += so
+ * gradient accumulation over micro-batches (REF/trainer.py:372-380) needs no extra pass. */
+typedef struct {
+  float *ln1_g, *ln1_b, *wqkv, *bqkv, *wo, *bo, *ln2_g, *ln2_b, *w1, *b1, *w2, *b2;
+} b2s_encoder_layer_grads;
+typedef struct {
+  float *conv0_w, *conv0_b, *conv0_ln_g, *conv0_ln_b;
+  float* conv_w[6];
+  float* conv_b[6];
+  float* conv_ln_g[6];
+  float* conv_ln_b[6];
+  float *fp_ln_g, *fp_ln_b, *fp_w, *fp_b;
+  float *pos_w, *pos_b;
+  const b2s_encoder_layer_grads* layers; /* host array */
+  float *final_ln_g, *final_ln_b, *proj_w, *proj_b;
+} b2s_hubert_grads;
+size_t b2s_hubert_saved_bytes(const b2s_hubert_weights* w, int32_t batches, int32_t samples);
+size_t b2s_hubert_backward_workspace_bytes(const b2s_hubert_weights* w, int32_t batches, int32_t samples);
+/* b2s_hubert_forward keeping every activation the backward needs in `saved` (deterministic: no dropout / LayerDrop /
+ * SpecAugment, TF/models/hubert/modeling_hubert.py:596-599,842-886). */
+int b2s_hubert_forward_train(const b2s_hubert_weights* w, const float* wave, int64_t wave_stride, int32_t batches,
+                             int32_t samples, void* saved, size_t saved_bytes, float* audio_embeds, void* stream);
+/* d_audio_embeds fp32 [batches*pooled, llm_dim] -> grads (+=). pos_w_dgrad: bf16 [H][k][H/groups], the packed
+ * positional-conv weight with taps reversed and each (out, in) block transposed (the conv's transpose). */
+int b2s_hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* grads,
+                        const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, void* saved,
+                        size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
+                        void* stream);
+/* memory-bound backward kernels of the encoder (see csrc/backward_enc.cu) */
+int b2s_layernorm_bwd_ex(const void* x, int32_t x_bf16, const float* gamma, const float* beta, int32_t act_gelu,
+                         float eps, const void* dy, int32_t dy_bf16, float* dh, int32_t accumulate, void* dx_bf16,
+                         float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream);
+int b2s_colsum_accum(const void* x, int32_t x_bf16, float* out, int64_t rows, int32_t C, void* stream);
+int b2s_avgpool_bwd(const float* dpooled, float* dx, int32_t batches, int32_t frames, int32_t C, int32_t kernel,
+                    int32_t stride, int32_t pooled, void* stream);
+int b2s_col2im_add(const void* dcol_bf16, void* dx_bf16, int32_t batches, int32_t tin, int32_t tout, int32_t k,
+                   int32_t s, int32_t C, void* stream);
+int b2s_conv0_bwd(const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, const float* w,
+                  const float* bias, const float* gamma, const float* beta, float eps, const void* dy_bf16,
+                  int32_t frames, float* dW, float* db, float* dgamma, float* dbeta, void* stream);
 int b2s_rmsnorm_bwd(const float* x, const int32_t* x_index, const float* w, float eps, const float* dy, float* dh,
                     const int32_t* dh_index, void* dh_bf16, int64_t rows, int32_t C, void* stream);
 int b2s_layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int32_t dy_bf16, float* dh,

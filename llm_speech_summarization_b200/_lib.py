@@ -50,6 +50,21 @@ class HubertWeights(C.Structure):
     ]
 
 
+class EncoderLayerGrads(C.Structure):
+    _fields_ = [(n, c_void_p) for n in
+                ("ln1_g", "ln1_b", "wqkv", "bqkv", "wo", "bo", "ln2_g", "ln2_b", "w1", "b1", "w2", "b2")]
+
+
+class HubertGrads(C.Structure):
+    _fields_ = [
+        ("conv0_w", c_void_p), ("conv0_b", c_void_p), ("conv0_ln_g", c_void_p), ("conv0_ln_b", c_void_p),
+        ("conv_w", c_void_p * 6), ("conv_b", c_void_p * 6), ("conv_ln_g", c_void_p * 6), ("conv_ln_b", c_void_p * 6),
+        ("fp_ln_g", c_void_p), ("fp_ln_b", c_void_p), ("fp_w", c_void_p), ("fp_b", c_void_p),
+        ("pos_w", c_void_p), ("pos_b", c_void_p), ("layers", C.POINTER(EncoderLayerGrads)),
+        ("final_ln_g", c_void_p), ("final_ln_b", c_void_p), ("proj_w", c_void_p), ("proj_b", c_void_p),
+    ]
+
+
 class WhisperWeights(C.Structure):
     _fields_ = [
         ("conv1_w", c_void_p), ("conv1_b", c_void_p), ("conv2_w", c_void_p), ("conv2_b", c_void_p),
@@ -143,6 +158,19 @@ PROTOTYPES = {
     "b2s_swiglu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "b2s_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2s_gather_rows_f32": (c_int, [P_f32, P_int, P_f32, c_int64, c_int, c_void_p]),
+    "b2s_hubert_saved_bytes": (C.c_size_t, [C.POINTER(HubertWeights), c_int, c_int]),
+    "b2s_hubert_backward_workspace_bytes": (C.c_size_t, [C.POINTER(HubertWeights), c_int, c_int]),
+    "b2s_hubert_forward_train": (c_int, [C.POINTER(HubertWeights), c_void_p, c_int64, c_int, c_int, c_void_p,
+                                         C.c_size_t, c_void_p, c_void_p]),
+    "b2s_hubert_backward": (c_int, [C.POINTER(HubertWeights), c_void_p, C.POINTER(HubertGrads), c_void_p, c_int64,
+                                    c_int, c_int, c_void_p, C.c_size_t, c_void_p, c_void_p, C.c_size_t, c_void_p]),
+    "b2s_layernorm_bwd_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p,
+                                     c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "b2s_colsum_accum": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "b2s_avgpool_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b2s_col2im_add": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b2s_conv0_bwd": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                              c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2s_adamw_step": (c_int, [P_f32, P_f32, P_f32, P_f32, c_int64, c_float, c_float, c_float, c_float, c_float,
                                c_int, c_float, c_void_p]),
 }

@@ -58,6 +58,13 @@ int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_
                   float* fd_sq, float* all_hidden, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 size_t llama_train_workspace_bytes(const b2s_llama_weights* w, int rows, int logit_rows);
+size_t hubert_saved_bytes(const b2s_hubert_weights* w, int batches, int samples);
+size_t hubert_backward_workspace_bytes(const b2s_hubert_weights* w, int batches, int samples);
+int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long long wave_stride, int batches, int samples,
+                         void* saved, size_t saved_bytes, float* audio_embeds, cudaStream_t stream);
+int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* gr, const float* wave,
+                    long long wave_stride, int batches, int samples, void* saved, size_t saved_bytes,
+                    const float* d_audio_embeds, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t llama_backward_workspace_bytes(const b2s_llama_weights* w, int rows_bwd, int n_dl);
 int llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* sv, int rows, const int* cu_seqlens,
                         int num_seqs, int max_seqlen, const int* positions, const int* logit_rows_index,
@@ -290,6 +297,47 @@ int b2s_gather_rows_f32(const float* src, const int32_t* index, float* out, int6
 int b2s_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int32_t step, float grad_scale, void* stream) {
   return adamw_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
+}
+
+size_t b2s_hubert_saved_bytes(const b2s_hubert_weights* w, int32_t batches, int32_t samples) {
+  return hubert_saved_bytes(w, batches, samples);
+}
+size_t b2s_hubert_backward_workspace_bytes(const b2s_hubert_weights* w, int32_t batches, int32_t samples) {
+  return hubert_backward_workspace_bytes(w, batches, samples);
+}
+int b2s_hubert_forward_train(const b2s_hubert_weights* w, const float* wave, int64_t wave_stride, int32_t batches,
+                             int32_t samples, void* saved, size_t saved_bytes, float* audio_embeds, void* stream) {
+  return hubert_forward_train(w, wave, wave_stride, batches, samples, saved, saved_bytes, audio_embeds, S(stream));
+}
+int b2s_hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* grads,
+                        const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, void* saved,
+                        size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  return hubert_backward(w, pos_w_dgrad, grads, wave, wave_stride, batches, samples, saved, saved_bytes, d_audio_embeds,
+                         workspace, workspace_bytes, S(stream));
+}
+int b2s_layernorm_bwd_ex(const void* x, int32_t x_bf16, const float* gamma, const float* beta, int32_t act_gelu,
+                         float eps, const void* dy, int32_t dy_bf16, float* dh, int32_t accumulate, void* dx_bf16,
+                         float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream) {
+  return layernorm_bwd_ex(x, x_bf16, gamma, beta, act_gelu, eps, dy, dy_bf16, dh, accumulate, dx_bf16, dgamma, dbeta,
+                          rows, C, S(stream));
+}
+int b2s_colsum_accum(const void* x, int32_t x_bf16, float* out, int64_t rows, int32_t C, void* stream) {
+  return colsum_accum(x, x_bf16, out, rows, C, S(stream));
+}
+int b2s_avgpool_bwd(const float* dpooled, float* dx, int32_t batches, int32_t frames, int32_t C, int32_t kernel,
+                    int32_t stride, int32_t pooled, void* stream) {
+  return avgpool_bwd(dpooled, dx, batches, frames, C, kernel, stride, pooled, S(stream));
+}
+int b2s_col2im_add(const void* dcol_bf16, void* dx_bf16, int32_t batches, int32_t tin, int32_t tout, int32_t k,
+                   int32_t s, int32_t C, void* stream) {
+  return col2im_add(dcol_bf16, dx_bf16, batches, tin, tout, k, s, C, S(stream));
+}
+int b2s_conv0_bwd(const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, const float* w,
+                  const float* bias, const float* gamma, const float* beta, float eps, const void* dy_bf16,
+                  int32_t frames, float* dW, float* db, float* dgamma, float* dbeta, void* stream) {
+  return conv0_bwd(wave, wave_stride, batches, samples, w, bias, gamma, beta, eps, dy_bf16, frames, dW, db, dgamma,
+                   dbeta, S(stream));
 }
 
 }  // extern "C"

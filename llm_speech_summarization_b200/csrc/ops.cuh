@@ -66,6 +66,20 @@ int gather_rows_f32(const float* src, const int* index, float* out, long long ro
 int adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                float weight_decay, int step, float grad_scale, cudaStream_t stream);
 
+// ---- backward_enc.cu (trainable audio encoder)
+// LayerNorm (+ optional erf-GELU on its output) backward; x / dy fp32 or bf16; dh fp32 (+=) and/or bf16 dx outputs
+int layernorm_bwd_ex(const void* x, int x_bf16, const float* gamma, const float* beta, int act_gelu, float eps,
+                     const void* dy, int dy_bf16, float* dh, int accumulate, void* dx_bf16, float* dgamma, float* dbeta,
+                     long long rows, int C, cudaStream_t stream);
+int colsum_accum(const void* x, int x_bf16, float* out, long long rows, int C, cudaStream_t stream);
+int avgpool_bwd(const float* dpooled, float* dx, int batches, int frames, int C, int kernel, int stride, int pooled,
+                cudaStream_t stream);
+int col2im_add(const void* dcol_bf16, void* dx_bf16, int batches, int tin, int tout, int k, int s, int C,
+               cudaStream_t stream);
+int conv0_bwd(const float* wave, long long wave_stride, int batches, int samples, const float* w, const float* bias,
+              const float* gamma, const float* beta, float eps, const void* dy_bf16, int frames, float* dW, float* db,
+              float* dgamma, float* dbeta, cudaStream_t stream);
+
 // ---- attention.cu
 // Packed variable-length attention. q/k/v are bf16 views into one [rows, ld] buffer (fused QKV output):
 // head h of row r lives at base + r*ld + h*D. Sequences are rows [cu[s], cu[s+1]).

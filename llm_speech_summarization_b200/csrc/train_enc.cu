@@ -1,0 +1,541 @@
+// train_enc.cu -- training-mode forward (activations kept) and full backward of the trainable HuBERT audio encoder
+// (REF/trainer.py:98-105: every AudioEncoder parameter is optimised; REF/trainer.py:278,373-374: the loss gradient
+// comes back through the projected audio embeddings).
+//
+//   hubert_forward_train : hubert_forward (models.cu) with every activation the backward needs written into one
+//                          caller-owned "saved" region (no recomputation except the cheap LayerNorm outputs).
+//   hubert_backward      : d(audio_embeds) -> fp32 gradient accumulators for all 422 trainable tensors
+//                          (TF/models/hubert/modeling_hubert.py:127-231,45-92,505-624; REF/model/audio_encoder.py:59-87).
+//
+// Every dense contraction is the tcgen05 GEMM: dgrad reads the forward's bf16 weights MN-major (no transposed
+// copies, the weights change every optimizer step), wgrad reads dY and X MN-major and accumulates with fp32 atomics
+// (split-K fills the 148 SMs; accumulation across micro-batches = REF/trainer.py:372-380 comes for free).
+// Dropout / LayerDrop / SpecAugment (train-mode only, TF/.../modeling_hubert.py:596-599,842-886) are not applied:
+// the step is the deterministic one the oracle restates.
+#include "../../include/b2s.h"
+#include "b2s_common.cuh"
+#include "gemm_sm100.cuh"
+#include "ops.cuh"
+
+namespace b2s {
+namespace {
+
+struct Carve {
+  uint8_t* base;
+  size_t off = 0, cap;
+  Carve(void* b, size_t c) : base(reinterpret_cast<uint8_t*>(b)), cap(c) {}
+  void* take(size_t bytes) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+int conv_len(int in, int k, int s) { return in < k ? 0 : (in - k) / s + 1; }
+
+struct Saved {
+  int t[8], frames, pooled;
+  void* conv_x[7];     // bf16 [B, t[i+1], 512] : output of conv layer i
+  float* conv_pre[6];  // fp32 [B, t[i+2], 512] : pre-norm output of conv layer i+1
+  void* hp_bf;         // bf16 [rows, H] feature-projection output (positional conv input)
+  void* pos_pre;       // bf16 [rows, H] positional conv output before GELU
+  float* h;            // fp32 [L+1][rows][H]
+  float* h_mid;        // fp32 [L][rows][H]
+  void* qkv;           // bf16 [L][rows][3H]
+  void* ao;            // bf16 [L][rows][H]
+  float* lse;          // fp32 [L][rows][heads]
+  void* ff_pre;        // bf16 [L][rows][F]
+  void* ff;            // bf16 [L][rows][F]
+  void* pooled_x;      // bf16 [B*pooled][H]
+  void* xn;            // bf16 [rows][max(H,512)] transient
+  int* cu;
+  size_t bytes;
+};
+
+void plan_saved(const b2s_hubert_weights* w, int batches, int samples, void* ws, size_t cap, Saved* s) {
+  s->t[0] = samples;
+  s->t[1] = conv_len(samples, 10, 5);
+  for (int i = 0; i < 6; ++i) s->t[i + 2] = conv_len(s->t[i + 1], w->conv_k[i], w->conv_stride[i]);
+  s->frames = s->t[7];
+  s->pooled = s->frames >= w->pool_kernel ? (s->frames - w->pool_kernel) / w->pool_stride + 1 : 0;
+  const size_t B = batches, H = w->hidden, F = w->ffn, L = w->num_layers;
+  const size_t rows = B * (s->frames > 0 ? s->frames : 1);
+  Carve c(ws, cap);
+  for (int i = 0; i < 7; ++i) s->conv_x[i] = c.take(B * (s->t[i + 1] > 0 ? s->t[i + 1] : 1) * 512 * 2 + 4096);
+  for (int i = 0; i < 6; ++i)
+    s->conv_pre[i] = reinterpret_cast<float*>(c.take(B * (s->t[i + 2] > 0 ? s->t[i + 2] : 1) * 512 * 4));
+  s->hp_bf = c.take(rows * H * 2 + 4096);
+  s->pos_pre = c.take(rows * H * 2);
+  s->h = reinterpret_cast<float*>(c.take((L + 1) * rows * H * 4));
+  s->h_mid = reinterpret_cast<float*>(c.take(L * rows * H * 4));
+  s->qkv = c.take(L * rows * 3 * H * 2);
+  s->ao = c.take(L * rows * H * 2);
+  s->lse = reinterpret_cast<float*>(c.take(L * rows * w->heads * 4));
+  s->ff_pre = c.take(L * rows * F * 2);
+  s->ff = c.take(L * rows * F * 2);
+  s->pooled_x = c.take(B * (s->pooled > 0 ? s->pooled : 1) * H * 2);
+  s->xn = c.take(rows * (H > 512 ? H : 512) * 2);
+  s->cu = reinterpret_cast<int*>(c.take((B + 1) * sizeof(int)));
+  s->bytes = c.off + 256;
+}
+
+struct BwdWs {
+  float *dh, *dxn_f, *dpool, *delta;
+  void *dyb, *dbig, *dsm, *xn, *da, *dpre, *dcol, *dxa, *dxb;
+  size_t bytes;
+};
+
+void plan_bwd(const b2s_hubert_weights* w, int batches, const Saved& s, void* ws, size_t cap, BwdWs* p) {
+  const size_t B = batches, H = w->hidden, F = w->ffn;
+  const size_t rows = B * (s.frames > 0 ? s.frames : 1);
+  const size_t big = F > 3 * H ? F : 3 * H;
+  const size_t np = B * (s.pooled > 0 ? s.pooled : 1);
+  Carve c(ws, cap);
+  p->dh = reinterpret_cast<float*>(c.take(rows * H * 4));
+  p->dxn_f = reinterpret_cast<float*>(c.take(rows * H * 4));
+  p->dpool = reinterpret_cast<float*>(c.take(np * H * 4));
+  p->delta = reinterpret_cast<float*>(c.take(rows * w->heads * 4));
+  p->dyb = c.take(rows * H * 2 + 4096);
+  p->dbig = c.take(rows * big * 2 + 4096);
+  p->dsm = c.take(rows * H * 2 + 4096);
+  p->xn = c.take(rows * (H > 512 ? H : 512) * 2 + 4096);
+  p->da = c.take(np * w->llm_dim * 2 + 4096);
+  const size_t t1 = s.t[1] > 0 ? s.t[1] : 1, t2 = s.t[2] > 0 ? s.t[2] : 1;
+  p->dpre = c.take(B * t2 * 512 * 2 + 4096);
+  p->dcol = c.take(B * t2 * 3 * 512 * 2 + 4096);
+  p->dxa = c.take(B * t1 * 512 * 2 + 4096);
+  p->dxb = c.take(B * t1 * 512 * 2 + 4096);
+  p->bytes = c.off + 256;
+}
+
+__global__ void iota_scaled(int* out, int n, int scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i * scale;
+}
+
+GemmArgs lin(const void* A, const void* W, long long M, int N, int K) {
+  GemmArgs g{};
+  g.A = A;
+  g.a_dim0 = K;
+  g.a_row_stride = K;
+  g.a_rows = static_cast<int>(M);
+  g.W = W;
+  g.w_rows = N;
+  g.w_cols = K;
+  g.M = static_cast<int>(M);
+  g.N = N;
+  g.batches = 1;
+  g.groups = 1;
+  g.taps = 1;
+  g.k_per_tap = K;
+  g.ldo = N;
+  return g;
+}
+
+// dX[M, K] = dY[M, N] . W[N, K]   (W in its forward layout, read MN-major)
+int dgrad(const void* dy, const void* W, long long M, int N, int K, int epi, void* out, cudaStream_t st) {
+  GemmArgs g{};
+  g.A = dy;
+  g.a_dim0 = N;
+  g.a_row_stride = N;
+  g.a_rows = static_cast<int>(M);
+  g.W = W;
+  g.w_rows = N;
+  g.w_cols = K;
+  g.b_mn = 1;
+  g.M = static_cast<int>(M);
+  g.N = K;
+  g.batches = 1;
+  g.groups = 1;
+  g.taps = 1;
+  g.k_per_tap = N;
+  g.epi = epi;
+  g.out = out;
+  g.ldo = K;
+  return gemm_bf16_launch(g, st);
+}
+
+// dW[N, K] += dY[rows, N]^T . X[rows, K]
+int wgrad(const void* dy, const void* x, long long rows, int N, int K, float* dW, cudaStream_t st) {
+  GemmArgs g{};
+  g.A = dy;
+  g.a_dim0 = N;
+  g.a_row_stride = N;
+  g.a_rows = static_cast<int>(rows);
+  g.a_mn = 1;
+  g.W = x;
+  g.w_rows = static_cast<int>(rows);
+  g.w_cols = K;
+  g.w_row_stride = K;
+  g.b_mn = 1;
+  g.M = N;
+  g.N = K;
+  g.batches = 1;
+  g.groups = 1;
+  g.taps = 1;
+  g.k_per_tap = static_cast<int>(rows);
+  g.k_batches = 1;
+  g.epi = EPI_ACCUM_F32;
+  g.out = dW;
+  g.ldo = K;
+  return gemm_bf16_launch(g, st);
+}
+
+#define RC(expr)                 \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != B2S_OK) return _rc; \
+  } while (0)
+
+}  // namespace
+
+size_t hubert_saved_bytes(const b2s_hubert_weights* w, int batches, int samples) {
+  if (w == nullptr || batches <= 0 || samples <= 0) return 0;
+  Saved s;
+  plan_saved(w, batches, samples, nullptr, 0, &s);
+  return s.bytes;
+}
+
+size_t hubert_backward_workspace_bytes(const b2s_hubert_weights* w, int batches, int samples) {
+  if (w == nullptr || batches <= 0 || samples <= 0) return 0;
+  Saved s;
+  plan_saved(w, batches, samples, nullptr, 0, &s);
+  BwdWs b;
+  plan_bwd(w, batches, s, nullptr, 0, &b);
+  return b.bytes;
+}
+
+int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long long wave_stride, int batches, int samples,
+                         void* saved, size_t saved_bytes, float* audio_embeds, cudaStream_t stream) {
+  B2S_REQUIRE(w && wave && saved && audio_embeds, "hubert_forward_train: null pointer");
+  B2S_REQUIRE(batches > 0 && samples > 0, "hubert_forward_train: empty batch");
+  B2S_REQUIRE(w->hidden % 256 == 0 && w->hidden % w->heads == 0 && w->hidden / w->heads == 64,
+              "hubert_forward_train: hidden/heads must give head_dim 64");
+  B2S_REQUIRE(w->pos_groups > 0 && w->hidden / w->pos_groups == 64, "hubert_forward_train: positional conv needs 64 ch/group");
+  Saved s;
+  plan_saved(w, batches, samples, saved, saved_bytes, &s);
+  B2S_REQUIRE(s.bytes <= saved_bytes, "hubert_forward_train: saved region too small: need %zu bytes, got %zu", s.bytes,
+              saved_bytes);
+  B2S_REQUIRE(s.frames > 0 && s.pooled > 0, "hubert_forward_train: audio too short (%d samples -> %d frames)", samples,
+              s.frames);
+  const int B = batches, H = w->hidden, F = w->ffn, L = w->num_layers;
+  const long long rows = static_cast<long long>(B) * s.frames;
+  const float eps = w->ln_eps;
+
+  RC(conv0_ln_gelu_fwd(wave, wave_stride, B, samples, w->conv0_w, w->conv0_b, w->conv0_ln_g, w->conv0_ln_b, eps,
+                       s.conv_x[0], s.t[1], stream));
+  for (int i = 0; i < 6; ++i) {
+    const int tin = s.t[i + 1], tout = s.t[i + 2];
+    const int k = w->conv_k[i], sd = w->conv_stride[i];
+    GemmArgs g{};
+    g.A = s.conv_x[i];
+    g.a_dim0 = k * 512;
+    g.a_row_stride = static_cast<long long>(sd) * 512;
+    g.a_batch_stride = static_cast<long long>(tin) * 512;
+    g.a_rows = tout;
+    g.W = w->conv_w[i];
+    g.w_rows = 512;
+    g.w_cols = k * 512;
+    g.M = tout;
+    g.N = 512;
+    g.batches = B;
+    g.groups = 1;
+    g.taps = 1;
+    g.k_per_tap = k * 512;
+    g.epi = EPI_F32;
+    g.bias = w->conv_b[i];
+    g.out = s.conv_pre[i];
+    g.ldo = 512;
+    g.out_batch_rows = tout;
+    RC(gemm_bf16_launch(g, stream));
+    RC(layernorm_fwd(s.conv_pre[i], 0, w->conv_ln_g[i], w->conv_ln_b[i], eps, 1, s.conv_x[i + 1],
+                     static_cast<long long>(B) * tout, 512, stream));
+  }
+  // feature projection -> h[0]
+  RC(layernorm_fwd(s.conv_x[6], 1, w->fp_ln_g, w->fp_ln_b, eps, 0, s.xn, rows, 512, stream));
+  {
+    GemmArgs g = lin(s.xn, w->fp_w, rows, H, 512);
+    g.epi = EPI_F32;
+    g.bias = w->fp_b;
+    g.out = s.h;
+    RC(gemm_bf16_launch(g, stream));
+  }
+  RC(cast_f32_to_bf16(s.h, s.hp_bf, rows * H, stream));
+  {
+    GemmArgs g{};
+    g.A = s.hp_bf;
+    g.a_dim0 = H;
+    g.a_row_stride = H;
+    g.a_batch_stride = static_cast<long long>(s.frames) * H;
+    g.a_rows = s.frames;
+    g.W = w->pos_w;
+    g.w_rows = H;
+    g.w_cols = w->pos_k * 64;
+    g.M = s.frames;
+    g.N = 64;
+    g.batches = B;
+    g.groups = w->pos_groups;
+    g.taps = w->pos_k;
+    g.k_per_tap = 64;
+    g.a_pad = w->pos_k / 2;
+    g.a_group_off = 64;
+    g.w_group_off = 64;
+    g.epi = EPI_RESID_F32;
+    g.act = ACT_GELU;
+    g.bias = w->pos_b;
+    g.out = s.h;
+    g.resid = s.h;
+    g.ldo = H;
+    g.out_batch_rows = s.frames;
+    g.out2 = s.pos_pre;
+    g.ld2 = H;
+    RC(gemm_bf16_launch(g, stream));
+  }
+  iota_scaled<<<(B + 1 + 255) / 256, 256, 0, stream>>>(s.cu, B + 1, s.frames);
+  B2S_LAUNCH_CHECK();
+  const size_t rH = static_cast<size_t>(rows) * H;
+  for (int l = 0; l < L; ++l) {
+    const b2s_encoder_layer& Ly = w->layers[l];
+    float* h_in = s.h + l * rH;
+    float* h_mid = s.h_mid + l * rH;
+    float* h_out = s.h + (l + 1) * rH;
+    __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(s.qkv) + l * 3 * rH;
+    __nv_bfloat16* ao = reinterpret_cast<__nv_bfloat16*>(s.ao) + l * rH;
+    __nv_bfloat16* ffp = reinterpret_cast<__nv_bfloat16*>(s.ff_pre) + static_cast<size_t>(l) * rows * F;
+    __nv_bfloat16* ff = reinterpret_cast<__nv_bfloat16*>(s.ff) + static_cast<size_t>(l) * rows * F;
+    RC(layernorm_fwd(h_in, 0, Ly.ln1_g, Ly.ln1_b, eps, 0, s.xn, rows, H, stream));
+    {
+      GemmArgs g = lin(s.xn, Ly.wqkv, rows, 3 * H, H);
+      g.epi = EPI_BF16;
+      g.bias = Ly.bqkv;
+      g.out = qkv;
+      RC(gemm_bf16_launch(g, stream));
+    }
+    RC(attention_fwd(qkv, qkv + H, qkv + 2 * H, 3 * H, ao, H, s.cu, B, s.frames, rows, w->heads, w->heads, 64, 0.125f, 0,
+                     s.lse + static_cast<size_t>(l) * rows * w->heads, stream));
+    {
+      GemmArgs g = lin(ao, Ly.wo, rows, H, H);
+      g.epi = EPI_RESID_F32;
+      g.bias = Ly.bo;
+      g.out = h_mid;
+      g.resid = h_in;
+      RC(gemm_bf16_launch(g, stream));
+    }
+    RC(layernorm_fwd(h_mid, 0, Ly.ln2_g, Ly.ln2_b, eps, 0, s.xn, rows, H, stream));
+    {
+      GemmArgs g = lin(s.xn, Ly.w1, rows, F, H);
+      g.epi = EPI_BF16;
+      g.act = ACT_GELU;
+      g.bias = Ly.b1;
+      g.out = ff;
+      g.out2 = ffp;
+      g.ld2 = F;
+      RC(gemm_bf16_launch(g, stream));
+    }
+    {
+      GemmArgs g = lin(ff, Ly.w2, rows, H, F);
+      g.epi = EPI_RESID_F32;
+      g.bias = Ly.b2;
+      g.out = h_out;
+      g.resid = h_mid;
+      RC(gemm_bf16_launch(g, stream));
+    }
+  }
+  RC(layernorm_avgpool_fwd(s.h + L * rH, w->final_ln_g, w->final_ln_b, eps, s.pooled_x, B, s.frames, H, w->pool_kernel,
+                           w->pool_stride, s.pooled, stream));
+  {
+    GemmArgs g = lin(s.pooled_x, w->proj_w, static_cast<long long>(B) * s.pooled, w->llm_dim, H);
+    g.epi = EPI_F32;
+    g.bias = w->proj_b;
+    g.out = audio_embeds;
+    RC(gemm_bf16_launch(g, stream));
+  }
+  return B2S_OK;
+}
+
+int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* gr, const float* wave,
+                    long long wave_stride, int batches, int samples, void* saved, size_t saved_bytes,
+                    const float* d_audio_embeds, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  B2S_REQUIRE(w && pos_w_dgrad && gr && gr->layers && wave && saved && d_audio_embeds && workspace,
+              "hubert_backward: null pointer");
+  Saved s;
+  plan_saved(w, batches, samples, saved, saved_bytes, &s);
+  B2S_REQUIRE(s.bytes <= saved_bytes && s.frames > 0 && s.pooled > 0, "hubert_backward: bad saved region");
+  BwdWs b;
+  plan_bwd(w, batches, s, workspace, workspace_bytes, &b);
+  B2S_REQUIRE(b.bytes <= workspace_bytes, "hubert_backward: workspace too small: need %zu bytes, got %zu", b.bytes,
+              workspace_bytes);
+  const int B = batches, H = w->hidden, F = w->ffn, L = w->num_layers, Cl = w->llm_dim;
+  const long long rows = static_cast<long long>(B) * s.frames;
+  const long long np = static_cast<long long>(B) * s.pooled;
+  const float eps = w->ln_eps;
+  const size_t rH = static_cast<size_t>(rows) * H;
+
+  // ---- projector + AvgPool + final LayerNorm
+  RC(cast_f32_to_bf16(d_audio_embeds, b.da, np * Cl, stream));
+  RC(colsum_accum(d_audio_embeds, 0, gr->proj_b, np, Cl, stream));
+  RC(wgrad(b.da, s.pooled_x, np, Cl, H, gr->proj_w, stream));
+  RC(dgrad(b.da, w->proj_w, np, Cl, H, EPI_F32, b.dpool, stream));
+  RC(avgpool_bwd(b.dpool, b.dxn_f, B, s.frames, H, w->pool_kernel, w->pool_stride, s.pooled, stream));
+  RC(layernorm_bwd_ex(s.h + L * rH, 0, w->final_ln_g, w->final_ln_b, 0, eps, b.dxn_f, 0, b.dh, 0, b.dyb, gr->final_ln_g,
+                      gr->final_ln_b, rows, H, stream));
+
+  // ---- transformer layers, last to first
+  for (int l = L - 1; l >= 0; --l) {
+    const b2s_encoder_layer& Ly = w->layers[l];
+    const b2s_encoder_layer_grads& G = gr->layers[l];
+    const float* h_in = s.h + l * rH;
+    const float* h_mid = s.h_mid + l * rH;
+    const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(s.qkv) + l * 3 * rH;
+    const __nv_bfloat16* ao = reinterpret_cast<const __nv_bfloat16*>(s.ao) + l * rH;
+    const __nv_bfloat16* ffp = reinterpret_cast<const __nv_bfloat16*>(s.ff_pre) + static_cast<size_t>(l) * rows * F;
+    const __nv_bfloat16* ff = reinterpret_cast<const __nv_bfloat16*>(s.ff) + static_cast<size_t>(l) * rows * F;
+    // feed-forward: h_out = h_mid + W2 gelu(W1 LN2(h_mid) + b1) + b2
+    RC(colsum_accum(b.dh, 0, G.b2, rows, H, stream));
+    RC(wgrad(b.dyb, ff, rows, H, F, G.w2, stream));
+    RC(dgrad(b.dyb, Ly.w2, rows, H, F, EPI_BF16, b.dbig, stream));
+    RC(gelu_bwd(ffp, b.dbig, b.dbig, rows * F, stream));
+    RC(colsum_accum(b.dbig, 1, G.b1, rows, F, stream));
+    RC(layernorm_fwd(h_mid, 0, Ly.ln2_g, Ly.ln2_b, eps, 0, b.xn, rows, H, stream));
+    RC(wgrad(b.dbig, b.xn, rows, F, H, G.w1, stream));
+    RC(dgrad(b.dbig, Ly.w1, rows, F, H, EPI_BF16, b.dsm, stream));
+    RC(layernorm_bwd_ex(h_mid, 0, Ly.ln2_g, Ly.ln2_b, 0, eps, b.dsm, 1, b.dh, 1, b.dyb, G.ln2_g, G.ln2_b, rows, H,
+                        stream));
+    // attention: h_mid = h_in + Wo attn(Wqkv LN1(h_in) + bqkv) + bo
+    RC(colsum_accum(b.dh, 0, G.bo, rows, H, stream));
+    RC(wgrad(b.dyb, ao, rows, H, H, G.wo, stream));
+    RC(dgrad(b.dyb, Ly.wo, rows, H, H, EPI_BF16, b.dsm, stream));
+    {
+      __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(b.dbig);
+      RC(attention_bwd(qkv, qkv + H, qkv + 2 * H, 3 * H, ao, H, b.dsm, H, s.lse + static_cast<size_t>(l) * rows * w->heads,
+                       b.delta, dqkv, dqkv + H, dqkv + 2 * H, 3 * H, s.cu, B, s.frames, rows, w->heads, w->heads, 64,
+                       0.125f, 0, nullptr, stream));
+    }
+    RC(colsum_accum(b.dbig, 1, G.bqkv, rows, 3 * H, stream));
+    RC(layernorm_fwd(h_in, 0, Ly.ln1_g, Ly.ln1_b, eps, 0, b.xn, rows, H, stream));
+    RC(wgrad(b.dbig, b.xn, rows, 3 * H, H, G.wqkv, stream));
+    RC(dgrad(b.dbig, Ly.wqkv, rows, 3 * H, H, EPI_BF16, b.dsm, stream));
+    RC(layernorm_bwd_ex(h_in, 0, Ly.ln1_g, Ly.ln1_b, 0, eps, b.dsm, 1, b.dh, 1, b.dyb, G.ln1_g, G.ln1_b, rows, H, stream));
+  }
+
+  // ---- positional conv embedding: h0 = hp + gelu(conv(hp) + b); dh / dyb = gradient w.r.t. h0
+  RC(gelu_bwd(s.pos_pre, b.dyb, b.dsm, rows * H, stream));  // dsm = d(pre-GELU conv output), bf16
+  RC(colsum_accum(b.dsm, 1, gr->pos_b, rows, H, stream));
+  {
+    // grouped wgrad: dW[g*64 + o][tap*64 + i] += sum_{b,t} dsm[b, t, g*64 + o] * hp[b, t + tap - pad, g*64 + i]
+    GemmArgs g{};
+    g.A = b.dsm;
+    g.a_dim0 = H;
+    g.a_row_stride = H;
+    g.a_batch_stride = static_cast<long long>(s.frames) * H;
+    g.a_rows = s.frames;
+    g.a_mn = 1;
+    g.a_group_off = 64;
+    g.W = s.hp_bf;
+    g.w_rows = s.frames;
+    g.w_cols = H;
+    g.w_row_stride = H;
+    g.w_batch_stride = static_cast<long long>(s.frames) * H;
+    g.w_group_off = 64;
+    g.b_mn = 1;
+    g.b_tap_atoms = 1;
+    g.a_pad = w->pos_k / 2;
+    g.M = 64;
+    g.N = w->pos_k * 64;
+    g.batches = 1;
+    g.groups = w->pos_groups;
+    g.taps = 1;
+    g.k_per_tap = s.frames;
+    g.k_batches = B;
+    g.epi = EPI_ACCUM_F32;
+    g.out = gr->pos_w;
+    g.ldo = static_cast<long long>(w->pos_k) * 64;
+    g.out_group_rows = 64;
+    g.out_group_cols = 0;
+    g.cta_group = 1;
+    RC(gemm_bf16_launch(g, stream));
+  }
+  {
+    // grouped dgrad: dh += conv^T(dsm) -- the forward's tap walk with flipped taps and transposed 64x64 blocks
+    GemmArgs g{};
+    g.A = b.dsm;
+    g.a_dim0 = H;
+    g.a_row_stride = H;
+    g.a_batch_stride = static_cast<long long>(s.frames) * H;
+    g.a_rows = s.frames;
+    g.W = pos_w_dgrad;
+    g.w_rows = H;
+    g.w_cols = w->pos_k * 64;
+    g.M = s.frames;
+    g.N = 64;
+    g.batches = B;
+    g.groups = w->pos_groups;
+    g.taps = w->pos_k;
+    g.k_per_tap = 64;
+    g.a_pad = w->pos_k - 1 - w->pos_k / 2;
+    g.a_group_off = 64;
+    g.w_group_off = 64;
+    g.epi = EPI_RESID_F32;
+    g.out = b.dh;
+    g.resid = b.dh;
+    g.ldo = H;
+    g.out_batch_rows = s.frames;
+    RC(gemm_bf16_launch(g, stream));
+  }
+  // ---- feature projection: hp = fp_w LN(conv_x[6]) + fp_b ; dh = gradient w.r.t. hp
+  RC(colsum_accum(b.dh, 0, gr->fp_b, rows, H, stream));
+  RC(cast_f32_to_bf16(b.dh, b.dyb, rows * H, stream));
+  RC(layernorm_fwd(s.conv_x[6], 1, w->fp_ln_g, w->fp_ln_b, eps, 0, b.xn, rows, 512, stream));
+  RC(wgrad(b.dyb, b.xn, rows, H, 512, gr->fp_w, stream));
+  RC(dgrad(b.dyb, w->fp_w, rows, H, 512, EPI_BF16, b.dsm, stream));
+  void* dcur = b.dxa;  // gradient w.r.t. conv_x[6], bf16 [B, frames, 512]
+  void* dnxt = b.dxb;
+  RC(layernorm_bwd_ex(s.conv_x[6], 1, w->fp_ln_g, w->fp_ln_b, 0, eps, b.dsm, 1, nullptr, 0, dcur, gr->fp_ln_g,
+                      gr->fp_ln_b, rows, 512, stream));
+  // ---- conv feature extractor, layers 6..1 (implicit GEMM) then layer 0
+  for (int i = 5; i >= 0; --i) {
+    const int tin = s.t[i + 1], tout = s.t[i + 2];
+    const int k = w->conv_k[i], sd = w->conv_stride[i];
+    const long long orows = static_cast<long long>(B) * tout;
+    RC(layernorm_bwd_ex(s.conv_pre[i], 0, w->conv_ln_g[i], w->conv_ln_b[i], 1, eps, dcur, 1, nullptr, 0, b.dpre,
+                        gr->conv_ln_g[i], gr->conv_ln_b[i], orows, 512, stream));
+    RC(colsum_accum(b.dpre, 1, gr->conv_b[i], orows, 512, stream));
+    {
+      GemmArgs g{};
+      g.A = b.dpre;
+      g.a_dim0 = 512;
+      g.a_row_stride = 512;
+      g.a_batch_stride = static_cast<long long>(tout) * 512;
+      g.a_rows = tout;
+      g.a_mn = 1;
+      g.W = s.conv_x[i];
+      g.w_rows = tout;
+      g.w_cols = k * 512;
+      g.w_row_stride = static_cast<long long>(sd) * 512;
+      g.w_batch_stride = static_cast<long long>(tin) * 512;
+      g.b_mn = 1;
+      g.M = 512;
+      g.N = k * 512;
+      g.batches = 1;
+      g.groups = 1;
+      g.taps = 1;
+      g.k_per_tap = tout;
+      g.k_batches = B;
+      g.epi = EPI_ACCUM_F32;
+      g.out = gr->conv_w[i];
+      g.ldo = static_cast<long long>(k) * 512;
+      RC(gemm_bf16_launch(g, stream));
+    }
+    RC(dgrad(b.dpre, w->conv_w[i], orows, 512, k * 512, EPI_BF16, b.dcol, stream));
+    RC(col2im_add(b.dcol, dnxt, B, tin, tout, k, sd, 512, stream));
+    void* tmp = dcur;
+    dcur = dnxt;
+    dnxt = tmp;
+  }
+  RC(conv0_bwd(wave, wave_stride, B, samples, w->conv0_w, w->conv0_b, w->conv0_ln_g, w->conv0_ln_b, eps, dcur, s.t[1],
+               gr->conv0_w, gr->conv0_b, gr->conv0_ln_g, gr->conv0_ln_b, stream));
+  return B2S_OK;
+}
+
+}  // namespace b2s

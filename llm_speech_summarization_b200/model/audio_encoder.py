@@ -212,6 +212,10 @@ class AudioEncoder(nn.Module):
 
         self._packed = None
         self._packed_key = None
+        self._pos_w_packed = None
+        self._pos_w_dgrad = None
+        self._grads = None
+        self._train_ctx = None
         self._register_load_state_dict_pre_hook(self._rename_legacy_weight_norm)
 
     # -- checkpoints written by torch 2.0 spell the weight-norm parameters weight_g / weight_v
@@ -265,8 +269,10 @@ class AudioEncoder(nn.Module):
         w.fp_ln_g, w.fp_ln_b = K(f32(fp.layer_norm.weight)), K(f32(fp.layer_norm.bias))
         w.fp_w, w.fp_b = K(bf(fp.projection.weight)), K(f32(fp.projection.bias))
         pc = enc.encoder.pos_conv_embed.conv
-        w.pos_w = K(ops.posconv_weight_pack(f32(pc.parametrizations.weight.original0).reshape(-1),
-                                            f32(pc.parametrizations.weight.original1)))
+        self._pos_w_packed = ops.posconv_weight_pack(f32(pc.parametrizations.weight.original0).reshape(-1),
+                                                     f32(pc.parametrizations.weight.original1))
+        self._pos_w_dgrad = None
+        w.pos_w = K(self._pos_w_packed)
         w.pos_b, w.pos_k, w.pos_groups = K(f32(pc.bias)), arch.pos_k, arch.pos_groups
         layers = (_lib.EncoderLayer * arch.layers)()
         for l, lay in enumerate(enc.encoder.layers):
@@ -367,8 +373,8 @@ class AudioEncoder(nn.Module):
             raise RuntimeError("AudioEncoder.forward (B200 path) needs a CUDA input; there is no CPU path")
         if self.training and torch.is_grad_enabled():
             raise NotImplementedError(
-                "training-mode forward/backward of the audio encoder is not built yet (SURVEY.md 8/a13, K13); "
-                "call .eval() / torch.no_grad() for the forward path")
+                "autograd does not flow through the B200 forward: use forward_train() / backward() / flush_grads() "
+                "(the explicit training path), or call .eval() / torch.no_grad() for inference")
         if self.encoder_base == "whisper":
             return self._whisper_forward_fp32(input, return_last_hidden)
         w = self.pack_weights()[0]
@@ -388,6 +394,160 @@ class AudioEncoder(nn.Module):
                                           out.data_ptr(), None if last is None else last.data_ptr(),
                                           torch.cuda.current_stream().cuda_stream), "hubert_forward")
         return (out, last) if return_last_hidden else out
+
+    # ------------------------------------------------------------------------------------------ training
+    def _grad_buffers(self):
+        """fp32 gradient accumulators in the kernels' packed layouts (include/b2s.h: b2s_hubert_grads)."""
+        if self._grads is not None:
+            return self._grads
+        if self.encoder_base != "hubert":
+            raise NotImplementedError("the training backward is built for the HuBERT encoder")
+        arch = self.encoder.arch
+        dev = self.embed_projection.weight.device
+        H, F_, L = arch.hidden, arch.ffn, arch.layers
+        z = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.float32)
+        t = {"conv0_w": z(arch.conv_dim[0], arch.conv_kernel[0]), "conv0_b": z(512), "conv0_ln_g": z(512),
+             "conv0_ln_b": z(512), "fp_ln_g": z(512), "fp_ln_b": z(512), "fp_w": z(H, 512), "fp_b": z(H),
+             "pos_w": z(H, arch.pos_k * (H // arch.pos_groups)), "pos_b": z(H), "final_ln_g": z(H), "final_ln_b": z(H),
+             "proj_w": z(self.embed_projection.out_features, H), "proj_b": z(self.embed_projection.out_features)}
+        for i in range(6):
+            t[f"conv_w{i}"] = z(512, arch.conv_kernel[i + 1] * 512)
+            t[f"conv_b{i}"], t[f"conv_ln_g{i}"], t[f"conv_ln_b{i}"] = z(512), z(512), z(512)
+        g = _lib.HubertGrads()
+        for k in ("conv0_w", "conv0_b", "conv0_ln_g", "conv0_ln_b", "fp_ln_g", "fp_ln_b", "fp_w", "fp_b", "pos_w",
+                  "pos_b", "final_ln_g", "final_ln_b", "proj_w", "proj_b"):
+            setattr(g, k, t[k].data_ptr())
+        for i in range(6):
+            g.conv_w[i], g.conv_b[i] = t[f"conv_w{i}"].data_ptr(), t[f"conv_b{i}"].data_ptr()
+            g.conv_ln_g[i], g.conv_ln_b[i] = t[f"conv_ln_g{i}"].data_ptr(), t[f"conv_ln_b{i}"].data_ptr()
+        layers = (_lib.EncoderLayerGrads * L)()
+        shapes = dict(ln1_g=(H,), ln1_b=(H,), wqkv=(3 * H, H), bqkv=(3 * H,), wo=(H, H), bo=(H,), ln2_g=(H,),
+                      ln2_b=(H,), w1=(F_, H), b1=(F_,), w2=(H, F_), b2=(H,))
+        for l in range(L):
+            for k, shp in shapes.items():
+                t[f"l{l}.{k}"] = z(*shp)
+                setattr(layers[l], k, t[f"l{l}.{k}"].data_ptr())
+        g.layers = C.cast(layers, C.POINTER(_lib.EncoderLayerGrads))
+        self._grads = (g, layers, t)
+        return self._grads
+
+    def forward_train(self, input: torch.Tensor) -> torch.Tensor:
+        """Training forward (REF/trainer.py:278): (B, T0) waveform -> fp32 (B, A, llm_dim), keeping the activations
+        for `backward`. Deterministic: dropout / LayerDrop / SpecAugment of the HF train mode are not applied."""
+        if not input.is_cuda:
+            raise RuntimeError("AudioEncoder.forward_train (B200 path) needs a CUDA input; there is no CPU path")
+        if self.encoder_base != "hubert":
+            raise NotImplementedError("the training backward is built for the HuBERT encoder")
+        w = self.pack_weights()[0]
+        wave = input.to(torch.float32)
+        if wave.dim() != 2:
+            raise ValueError("expected a (B, T0) waveform batch")
+        if wave.stride(1) != 1:
+            wave = wave.contiguous()
+        B, T0 = wave.shape
+        frames, pooled = self.num_frames(T0)
+        lib = _lib.load()
+        nbytes = lib.b2s_hubert_saved_bytes(C.byref(w), B, T0)
+        ctx = self._train_ctx
+        if ctx is None or ctx["saved"].numel() < nbytes:
+            ctx = {"saved": torch.empty(nbytes, device=wave.device, dtype=torch.uint8)}
+        out = torch.empty(B, pooled, w.llm_dim, device=wave.device, dtype=torch.float32)
+        _lib.check(lib.b2s_hubert_forward_train(C.byref(w), wave.data_ptr(), wave.stride(0), B, T0,
+                                                ctx["saved"].data_ptr(), ctx["saved"].numel(), out.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), "hubert_forward_train")
+        ctx.update(wave=wave, B=B, T0=T0, pooled=pooled)
+        self._train_ctx = ctx
+        return out
+
+    def backward(self, d_audio_embeds: torch.Tensor) -> None:
+        """Accumulate d(loss)/d(parameters) for the last `forward_train` batch given d(loss)/d(audio_embeds)
+        (fp32 (B, A, llm_dim)). Gradients stay in packed accumulators until `flush_grads`."""
+        ctx = self._train_ctx
+        if ctx is None or "wave" not in ctx:
+            raise RuntimeError("AudioEncoder.backward called without a preceding forward_train")
+        w = self.pack_weights()[0]
+        arch = self.encoder.arch
+        g = self._grad_buffers()[0]
+        d = d_audio_embeds.to(torch.float32).contiguous()
+        assert d.shape == (ctx["B"], ctx["pooled"], w.llm_dim), "d_audio_embeds shape mismatch"
+        if self._pos_w_dgrad is None:
+            G, K_, cg = arch.pos_groups, arch.pos_k, arch.hidden // arch.pos_groups
+            # conv transpose: taps reversed, each (out, in) block transposed: [g*cg+o][j][i] -> [g*cg+i][K-1-j][o]
+            self._pos_w_dgrad = (self._pos_w_packed.view(G, cg, K_, cg).flip(2).permute(0, 3, 2, 1)
+                                 .contiguous().view(arch.hidden, K_ * cg))
+        lib = _lib.load()
+        nbytes = lib.b2s_hubert_backward_workspace_bytes(C.byref(w), ctx["B"], ctx["T0"])
+        if ctx.get("bws") is None or ctx["bws"].numel() < nbytes:
+            ctx["bws"] = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
+        wave = ctx["wave"]
+        _lib.check(lib.b2s_hubert_backward(C.byref(w), self._pos_w_dgrad.data_ptr(), C.byref(g), wave.data_ptr(),
+                                           wave.stride(0), ctx["B"], ctx["T0"], ctx["saved"].data_ptr(),
+                                           ctx["saved"].numel(), d.data_ptr(), ctx["bws"].data_ptr(),
+                                           ctx["bws"].numel(), torch.cuda.current_stream().cuda_stream),
+                   "hubert_backward")
+        del ctx["wave"]
+
+    @torch.no_grad()
+    def flush_grads(self) -> None:
+        """Packed accumulators -> `.grad` of the parameters (HF layouts; += like autograd), then zero them.
+        Pure re-indexing plus the weight-norm chain rule of the positional conv (once per optimizer step)."""
+        _, _, t = self._grad_buffers()
+        enc = self.encoder
+        arch = enc.arch
+        H = arch.hidden
+
+        def add(p, g):
+            g = g.reshape(p.shape).to(p.dtype)
+            p.grad = g.clone() if p.grad is None else p.grad.add_(g)
+
+        fe = enc.feature_extractor.conv_layers
+        add(fe[0].conv.weight, t["conv0_w"])
+        add(fe[0].conv.bias, t["conv0_b"])
+        add(fe[0].layer_norm.weight, t["conv0_ln_g"])
+        add(fe[0].layer_norm.bias, t["conv0_ln_b"])
+        for i in range(6):
+            k = arch.conv_kernel[i + 1]
+            add(fe[i + 1].conv.weight, t[f"conv_w{i}"].view(512, k, 512).permute(0, 2, 1))
+            add(fe[i + 1].conv.bias, t[f"conv_b{i}"])
+            add(fe[i + 1].layer_norm.weight, t[f"conv_ln_g{i}"])
+            add(fe[i + 1].layer_norm.bias, t[f"conv_ln_b{i}"])
+        fp = enc.feature_projection
+        add(fp.layer_norm.weight, t["fp_ln_g"])
+        add(fp.layer_norm.bias, t["fp_ln_b"])
+        add(fp.projection.weight, t["fp_w"])
+        add(fp.projection.bias, t["fp_b"])
+        pc = enc.encoder.pos_conv_embed.conv
+        cg = H // arch.pos_groups
+        dW = t["pos_w"].view(H, arch.pos_k, cg).permute(0, 2, 1)  # [H, cg, K] like original1
+        g0 = pc.parametrizations.weight.original0.detach().float()  # [1, 1, K]
+        v = pc.parametrizations.weight.original1.detach().float()   # [H, cg, K]
+        nrm = v.pow(2).sum(dim=(0, 1), keepdim=True).sqrt()
+        dot = (dW * v).sum(dim=(0, 1), keepdim=True)
+        add(pc.parametrizations.weight.original0, dot / nrm)
+        add(pc.parametrizations.weight.original1, (g0 / nrm) * (dW - dot / (nrm * nrm) * v))
+        add(pc.bias, t["pos_b"])
+        for l, lay in enumerate(enc.encoder.layers):
+            a = lay.attention
+            q = lambda k: t[f"l{l}.{k}"]
+            add(lay.layer_norm.weight, q("ln1_g"))
+            add(lay.layer_norm.bias, q("ln1_b"))
+            for j, proj in enumerate((a.q_proj, a.k_proj, a.v_proj)):
+                add(proj.weight, q("wqkv")[j * H:(j + 1) * H])
+                add(proj.bias, q("bqkv")[j * H:(j + 1) * H])
+            add(a.out_proj.weight, q("wo"))
+            add(a.out_proj.bias, q("bo"))
+            add(lay.final_layer_norm.weight, q("ln2_g"))
+            add(lay.final_layer_norm.bias, q("ln2_b"))
+            add(lay.feed_forward.intermediate_dense.weight, q("w1"))
+            add(lay.feed_forward.intermediate_dense.bias, q("b1"))
+            add(lay.feed_forward.output_dense.weight, q("w2"))
+            add(lay.feed_forward.output_dense.bias, q("b2"))
+        add(enc.encoder.layer_norm.weight, t["final_ln_g"])
+        add(enc.encoder.layer_norm.bias, t["final_ln_b"])
+        add(self.embed_projection.weight, t["proj_w"])
+        add(self.embed_projection.bias, t["proj_b"])
+        for buf in t.values():
+            buf.zero_()
 
     def forward(self, input, ctc_pool_ranges=None):
         """Same contract as REF/model/audio_encoder.py:56-88 (`pool` branch): (B, T0) -> (B, A, llm_dim).

@@ -70,3 +70,41 @@ def test_llm_backward_batched_and_scaled(cuda):
     assert rel_l2(both["d_audio_embeds"][0] * 4, one0["d_audio_embeds"][0]) < 5e-3
     assert rel_l2(both["d_audio_embeds"][1] * 4, one1["d_audio_embeds"][0]) < 5e-3
     assert torch.allclose(both["total_loss"], torch.cat([one0["total_loss"], one1["total_loss"]]), rtol=1e-3)
+
+
+def _encoder_grads_vs_oracle(cuda, B, samples, seed=21):
+    """Per-parameter gradients of sum(audio_embeds * R) for a fixed random R: CUDA path vs oracle autograd."""
+    from oracle import reference_math as rm
+    configs, enc_cfg, llm_cfg, enc_sd, llm_sd = _tiny()
+    cfg, enc, llm = build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, cuda)
+    g = torch.Generator().manual_seed(seed)
+    wave = torch.randn(B, samples, generator=g) * 0.1
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in enc_sd.items()}
+    out_ref = rm.audio_encoder_forward(sd, wave, enc_cfg)
+    R = torch.randn(out_ref.shape, generator=g)
+    names = [k for k, v in sd.items() if torch.is_tensor(v) and v.requires_grad]
+    grads = torch.autograd.grad((out_ref * R).sum(), [sd[k] for k in names], allow_unused=True)
+    ref = {k: gr for k, gr in zip(names, grads) if gr is not None}
+
+    out = enc.forward_train(wave.to(cuda))
+    assert rel_l2(out.cpu(), out_ref.detach()) < 2e-2
+    enc.backward(R.to(cuda))
+    enc.flush_grads()
+    got = {k: p.grad for k, p in enc.named_parameters() if p.grad is not None}
+    return ref, got
+
+
+@pytest.mark.parametrize("B,samples", [(1, 4000), (3, 6000)])
+def test_encoder_backward_matches_oracle_autograd(cuda, B, samples):
+    ref, got = _encoder_grads_vs_oracle(cuda, B, samples)
+    missing = [k for k in ref if k not in got and float(ref[k].norm()) > 0]
+    assert not missing, missing
+    worst = {}
+    for k, gr in ref.items():
+        n = float(gr.norm())
+        if n < 1e-6:  # e.g. k_proj.bias: softmax is shift-invariant, the true gradient is zero
+            assert float(got[k].norm()) < 1e-2
+            continue
+        worst[k] = rel_l2(got[k].cpu().float(), gr)
+    bad = {k: v for k, v in worst.items() if v > 4e-2}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:12]
