@@ -9,7 +9,9 @@
 Workload (BASELINE.json configs[1], the one the metric is quoted on): Llama-3.2-3B + HuBERT-large, synthetic 10 s
 16 kHz utterances, random-init weights. One step = one micro-batch of `--batch` utterances per GPU through
     encoder -> splice -> packed student (audio prompt) + teacher (text prompt) prefill -> fused CE + KD (+FD) loss,
-i.e. "encoder + prefill + KD loss" (forward; the backward of configs[2] is not built yet and is NOT timed).
+i.e. "encoder + prefill + KD loss" (forward). `--workload train` times BASELINE.json configs[2] instead: the same
+forward with activations kept, the backward through the frozen LLM into every encoder/projector parameter, the SUM
+all-reduce of the flat gradient over the ranks and one AdamW update per step (grad_accum window = the global batch).
 
 `value`  : utterances/s, inputs already resident in HBM, CUDA-event timed, max over ranks.
 `e2e`    : the same through AudioPromptStep.__call__ with HOST (pinned) inputs: H2D of the waveforms + ids and a
@@ -30,6 +32,8 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line under torchrun
+
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -48,6 +52,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="prefill", choices=["prefill", "train"],
+                    help="prefill = configs[1] (default, the metric's configuration); train = configs[2]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts", type=int, default=3, help="utterances timed for the CPU baseline sample")
     ap.add_argument("--profile-mode", action="store_true",
@@ -224,21 +230,29 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+METRIC_TRAIN = "utterances/sec (10 s audio, training step: encoder+prefill+KD loss forward, backward, AdamW)"
+WORKLOAD_TRAIN = ("configs[2] Llama-3.2-3B + HuBERT-large training step (encoder/projector trainable, LLM frozen), "
+                  "CE + logit-KD + FD loss, synthetic 10 s utterances (L_audio=200, L_text=117, R=64), deterministic "
+                  "(no dropout/LayerDrop/SpecAugment)")
 WORKLOAD = ("configs[1] Llama-3.2-3B + HuBERT-large audio-prompt forward: encoder + packed student&teacher prefill "
             "+ fused CE/KD/FD loss, synthetic 10 s utterances (L_audio=200, L_text=117, R=64)")
 
 
 # ------------------------------------------------------------------------------------------ main arm
-def gemm_flops_per_utt():
-    """Algorithmic forward FLOPs per utterance credited to the GEMM kernel (attention and
-    conv0 excluded, LM head on the 2*R consumed rows only)."""
-    conv = 2 * 512 * 512 * (3 * (15999 + 7999 + 3999 + 1999) + 2 * (999 + 499))
+def gemm_flops_per_utt(train=False):
+    """Algorithmic FLOPs per utterance credited to the GEMM kernel (attention and conv0
+    excluded, LM head on the 2*R consumed rows only). Training adds dgrad + wgrad for the encoder (no dgrad into the
+    waveform) and dgrad only for the student sequence of the frozen LLM."""
+    conv1 = 2 * 512 * 512 * 3 * 15999
+    conv = conv1 + 2 * 512 * 512 * (3 * (7999 + 3999 + 1999) + 2 * (999 + 499))
     N = 499
     enc = conv + 2 * N * 512 * 1024 + 2 * N * 1024 * 64 * 128 + 24 * (2 * N * 1024 * (4 * 1024 + 2 * 4096)) \
         + 2 * 123 * 1024 * 3072
     per_tok = 2 * 3072 * (5120 + 3072 + 2 * 8192 + 8192)
     llm = 28 * per_tok * (200 + 117) + 2 * 2 * R_RESP * 3072 * 128256
-    return enc + llm
+    if not train:
+        return enc + llm
+    return 3 * enc + llm + 28 * per_tok * 200 + 2 * R_RESP * 3072 * 128256
 
 
 def main():
@@ -273,8 +287,14 @@ def main():
     llm.eval().to(dev)
     tok = FixedTokenizer(la.vocab, la.bos)
     step = AudioPromptStep(enc, llm, tok, cfg.model.llm_type)
-
+    train = args.workload == "train"
     B = args.batch
+    trainer = None
+    if train:
+        from llm_speech_summarization_b200.training import EncoderTrainer
+        trainer = EncoderTrainer(step, enc, llm, lr=5e-5, betas=(0.9, 0.999), grad_accum_interval=B * world,
+                                 total_optimizer_steps=10 ** 6)
+
     n_pool = 2  # rotate through distinct micro-batches
     host = [synth_batch(B, la.vocab, 1000 * (rank + 1) + i) for i in range(n_pool)]
     host = [(w.pin_memory(), t, r) for (w, t, r) in host]
@@ -284,7 +304,11 @@ def main():
 
     def run_resident(i):
         w, t, r = resident[i % n_pool]
+        if train:
+            return trainer.train_step(w, t, r, plan=plans[i % n_pool])
         return step.forward_losses(w, t, r, plan=plans[i % n_pool])
+
+    public = trainer if train else step
 
     lib = _lib.load()
     # ---- value: inputs resident in HBM
@@ -316,13 +340,13 @@ def main():
         return
     # ---- e2e: host buffers -> H2D -> step -> D2H, through the public call
     for i in range(min(2, args.warmup)):
-        step(host[i % n_pool][0], host[i % n_pool][1], host[i % n_pool][2], dev)
+        public(host[i % n_pool][0], host[i % n_pool][1], host[i % n_pool][2], dev)
     torch.cuda.synchronize()
     dp.barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         w, t, r = host[i % n_pool]
-        res = step(w, t, r, dev)
+        res = public(w, t, r, dev)
     torch.cuda.synchronize()
     e2e_s = dp.max_over_ranks(time.perf_counter() - t0, dev)
     dp.barrier()
@@ -349,7 +373,7 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained)"
-    flops_step = gemm_flops_per_utt() * B
+    flops_step = gemm_flops_per_utt(train) * B
     gemm_ms_step = g_ms.value / 2
     achieved = flops_step / (gemm_ms_step / 1e3) / 1e12 if gemm_ms_step > 0 else None
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all launches of one step)",
@@ -357,22 +381,25 @@ def main():
                 "frac": (achieved / peak_tf) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "launches_per_step": g_n.value // 2, "gemm_ms_per_step": gemm_ms_step,
                 "gemm_share_of_step": gemm_ms_step / (ms / args.steps) if ms > 0 else None,
-                "algorithmic_gflop_per_utt": gemm_flops_per_utt() / 1e9}
+                "algorithmic_gflop_per_utt": gemm_flops_per_utt(train) / 1e9}
 
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not train:
             enc_cpu = {k: v.float().cpu() for k, v in enc_sd.items()}
             llm_cpu = {k: v.float().cpu() for k, v in llm_sd.items() if k != "lm_head.weight"}
             llm_cpu["lm_head.weight"] = llm_cpu["model.embed_tokens.weight"]
             cpu, _ = cpu_reference(args.cpu_utts, enc_cpu, llm_cpu, steps=1, warmup=0)
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        workload = WORKLOAD_TRAIN if train else WORKLOAD
+        timed = ("forward with kept activations + backward to all encoder/projector parameters + gradient all-reduce "
+                 "+ AdamW, every step" if train else "forward only (encoder + student/teacher prefill + CE/KD/FD)")
+        line = {"metric": METRIC_TRAIN if train else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "utterances_per_step_per_gpu": B, "parallelism": f"dp{world}",
+                "config": {"workload": workload, "utterances_per_step_per_gpu": B, "parallelism": f"dp{world}",
                            "l2": "no flush needed: every step streams ~7 GB of weights and >2 GB of activations "
                                  "(>> 126 MB L2); two distinct micro-batches alternate",
-                           "timed": "forward only (encoder + student/teacher prefill + CE/KD/FD); backward not built"},
+                           "timed": timed},
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

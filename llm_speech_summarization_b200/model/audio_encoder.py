@@ -396,6 +396,13 @@ class AudioEncoder(nn.Module):
         return (out, last) if return_last_hidden else out
 
     # ------------------------------------------------------------------------------------------ training
+    def mark_weights_changed(self) -> None:
+        """The optimizer updates the parameters in place with its own kernel (no autograd version bump): drop the
+        packed bf16 copies so the next forward rebuilds them."""
+        self._packed = None
+        self._packed_key = None
+        self._pos_w_dgrad = None
+
     def _grad_buffers(self):
         """fp32 gradient accumulators in the kernels' packed layouts (include/b2s.h: b2s_hubert_grads)."""
         if self._grads is not None:

@@ -229,6 +229,19 @@ class AudioPromptStep:
         out["plan"] = plan
         return out
 
+    @torch.no_grad()
+    def forward_backward(self, waves: torch.Tensor, text_ids, resp_ids, loss_scale: float = 1.0,
+                         plan: Optional[StepPlan] = None) -> Dict[str, torch.Tensor]:
+        """One training micro-batch (REF/trainer.py:270-374): encoder forward with kept activations -> LLM
+        forward/backward -> encoder backward. Parameter gradients (x loss_scale) accumulate inside the encoder
+        until `audio_encoder.flush_grads()`."""
+        if not waves.is_cuda:
+            raise RuntimeError("AudioPromptStep needs CUDA inputs; there is no CPU path")
+        audio = self.audio_encoder.forward_train(waves)
+        out = self.llm_forward_backward(audio, text_ids, resp_ids, loss_scale=loss_scale, plan=plan)
+        self.audio_encoder.backward(out["d_audio_embeds"])
+        return out
+
     def __call__(self, waves_host: torch.Tensor, text_ids, resp_ids, device) -> Dict[str, float]:
         """End-to-end call from HOST buffers: pinned H2D copy of the waveforms and ids, the fused step, and a D2H
         read of the per-utterance losses (what bench.py's `e2e` times)."""

@@ -1,0 +1,217 @@
+"""Training step of the reference's Trainer (REF/trainer.py:98-110, 250-395, 518-526) on the B200 path.
+
+    FlatAdamW     torch.optim.AdamW(audio_encoder.parameters(), lr, betas) (REF/trainer.py:98-105) with every
+                  trainable tensor re-homed as a view of ONE flat fp32 buffer (params, grads, exp_avg, exp_avg_sq):
+                  the update is one b2s_adamw_step launch and the data-parallel gradient exchange one SUM
+                  all-reduce. state_dict()/load_state_dict() keep torch.optim.AdamW's layout, so the reference's
+                  checkpoints (`optimizer` key, REF/trainer.py:518-526) load unchanged.
+    PolynomialLR  torch.optim.lr_scheduler.PolynomialLR(power=1.0) (REF/trainer.py:106-110), closed form.
+    EncoderTrainer.train_step
+                  one micro-batch: encoder forward (activations kept) -> splice -> frozen-LLM student+teacher pass ->
+                  CE/KD/FD losses -> backward to the encoder's parameters, scaled by 1/grad_accum_interval
+                  (REF/trainer.py:372-374); optimizer.step / scheduler.step / zero_grad every grad_accum_interval
+                  micro-batches (REF/trainer.py:376-384). Under torch.distributed every rank runs its shard of the
+                  accumulation window and the flat gradient is SUM-all-reduced before the update.
+
+The LLM is frozen (REF/trainer.py:62-64); its parameters sit in the reference optimizer's second param group without
+ever receiving a gradient, so they carry no optimizer state -- FlatAdamW reproduces that group as an empty-state one.
+Dropout / LayerDrop / SpecAugment of HF's train mode are not applied (deterministic step, see csrc/train_enc.cu).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class FlatAdamW:
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
+                 frozen_params=(), exclude=()):
+        self.params: List[torch.nn.Parameter] = [p for p in params]
+        skip = {id(p) for p in exclude}  # parameters that never receive a gradient: torch keeps no state for them
+        self.trainable = [p for p in self.params if p.requires_grad and id(p) not in skip]
+        if not self.trainable:
+            raise ValueError("FlatAdamW: no trainable parameters")
+        dev = self.trainable[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatAdamW (B200 path) needs CUDA parameters; there is no CPU path")
+        self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
+        self.lr = lr
+        self.n_frozen = len(list(frozen_params))
+        n = sum(p.numel() for p in self.trainable)
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.offsets = []
+        off = 0
+        for p in self.trainable:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.detach().reshape(-1).float())
+            p.data = self.flat[off:off + k].view(p.shape)
+            p.grad = self.grad[off:off + k].view(p.shape)
+            self.offsets.append(off)
+            off += k
+        self.step_count = 0
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.grad.zero_()
+
+    def all_reduce_grads(self):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+
+    @torch.no_grad()
+    def step(self):
+        self.step_count += 1
+        b1, b2 = self.defaults["betas"]
+        _lib.check(_lib.load().b2s_adamw_step(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                              self.exp_avg_sq.data_ptr(), self.flat.numel(), float(self.lr), b1, b2,
+                                              self.defaults["eps"], self.defaults["weight_decay"], self.step_count,
+                                              1.0, torch.cuda.current_stream().cuda_stream), "adamw_step")
+
+    # ---- torch.optim.AdamW-compatible state dict ------------------------------------------------
+    def state_dict(self) -> Dict:
+        state = {}
+        idx_of = {id(p): i for i, p in enumerate(self.params)}
+        if self.step_count > 0:
+            for p, off in zip(self.trainable, self.offsets):
+                k = p.numel()
+                state[idx_of[id(p)]] = {"step": torch.tensor(float(self.step_count)),
+                                        "exp_avg": self.exp_avg[off:off + k].view(p.shape).clone(),
+                                        "exp_avg_sq": self.exp_avg_sq[off:off + k].view(p.shape).clone()}
+        group = dict(lr=self.lr, betas=self.defaults["betas"], eps=self.defaults["eps"],
+                     weight_decay=self.defaults["weight_decay"], amsgrad=False, maximize=False, foreach=None,
+                     capturable=False, differentiable=False, fused=None, initial_lr=self.defaults["lr"])
+        n = len(self.params)
+        groups = [dict(group, params=list(range(n))), dict(group, params=list(range(n, n + self.n_frozen)))]
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd: Dict):
+        idx_of = {id(p): i for i, p in enumerate(self.params)}
+        steps = set()
+        for p, off in zip(self.trainable, self.offsets):
+            st = sd["state"].get(idx_of[id(p)])
+            if st is None:
+                continue
+            k = p.numel()
+            self.exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1).to(self.exp_avg.device, torch.float32))
+            self.exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1).to(self.exp_avg.device, torch.float32))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("FlatAdamW.load_state_dict: parameters with different step counts are not supported")
+        self.step_count = steps.pop() if steps else 0
+        if sd.get("param_groups"):
+            self.lr = sd["param_groups"][0].get("lr", self.lr)
+
+
+class PolynomialLR:
+    """lr_t = base_lr * (1 - min(t, total_iters) / total_iters) ** power (torch's PolynomialLR, closed form)."""
+
+    def __init__(self, optimizer: FlatAdamW, total_iters: int, power: float = 1.0):
+        self.optimizer = optimizer
+        self.total_iters = max(1, int(total_iters))
+        self.power = power
+        self.base_lr = optimizer.defaults["lr"]
+        self.last_epoch = 0
+        self._apply()
+
+    def _apply(self):
+        t = min(self.last_epoch, self.total_iters)
+        self.optimizer.lr = self.base_lr * (1.0 - t / self.total_iters) ** self.power
+
+    def step(self):
+        self.last_epoch += 1
+        self._apply()
+
+    def get_last_lr(self):
+        return [self.optimizer.lr]
+
+    def state_dict(self):
+        return {"total_iters": self.total_iters, "power": self.power, "base_lrs": [self.base_lr],
+                "last_epoch": self.last_epoch, "_last_lr": [self.optimizer.lr]}
+
+    def load_state_dict(self, sd):
+        self.total_iters = sd.get("total_iters", self.total_iters)
+        self.power = sd.get("power", self.power)
+        self.base_lr = sd.get("base_lrs", [self.base_lr])[0]
+        self.last_epoch = sd.get("last_epoch", 0)
+        self._apply()
+
+
+class EncoderTrainer:
+    """The optimisation loop body of REF/trainer.py:250-395 (data loading, logging and validation stay with the
+    caller). `step` counts micro-batches like the reference's `self.step`."""
+
+    def __init__(self, step_fn, audio_encoder, llm=None, *, lr: float = 5e-5, betas=(0.9, 0.999),
+                 grad_accum_interval: int = 16, total_optimizer_steps: int = 1000, weight_decay: float = 1e-2):
+        self.step_fn = step_fn
+        self.audio_encoder = audio_encoder
+        frozen = list(llm.parameters()) if llm is not None else []
+        # masked_spec_embed is only read by SpecAugment (train-mode HF, not applied): it never gets a gradient
+        unused = [p for n, p in audio_encoder.named_parameters() if n.endswith("masked_spec_embed")]
+        self.optimizer = FlatAdamW(audio_encoder.parameters(), lr=lr, betas=betas, weight_decay=weight_decay,
+                                   frozen_params=frozen, exclude=unused)
+        self.lr_scheduler = PolynomialLR(self.optimizer, total_iters=total_optimizer_steps, power=1.0)
+        self.grad_accum_interval = int(grad_accum_interval)
+        self.step = 0
+        self.start_epoch = 0
+        self._micro = 0
+
+    @classmethod
+    def from_config(cls, config, step_fn, audio_encoder, llm=None, batches_per_epoch: int = 1):
+        t = config.train
+        total = (t.epochs * batches_per_epoch) // t.grad_accum_interval
+        return cls(step_fn, audio_encoder, llm, lr=t.optimizer.lr, betas=(t.optimizer.beta1, t.optimizer.beta2),
+                   grad_accum_interval=t.grad_accum_interval, total_optimizer_steps=total)
+
+    def world(self) -> int:
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    @torch.no_grad()
+    def train_step(self, waves: torch.Tensor, text_ids, resp_ids, last_batch: bool = False,
+                   plan=None) -> Dict[str, torch.Tensor]:
+        """One micro-batch of B utterances on this rank. The accumulation window counts utterances GLOBALLY:
+        an optimizer step happens once world * (micro-batches * B) reaches grad_accum_interval (or at loader end)."""
+        B = waves.shape[0]
+        out = self.step_fn.forward_backward(waves, text_ids, resp_ids, loss_scale=1.0 / self.grad_accum_interval,
+                                            plan=plan)
+        self._micro += B * self.world()
+        self.step += 1
+        out["optimizer_step"] = False
+        if self._micro >= self.grad_accum_interval or last_batch:
+            self.audio_encoder.flush_grads()
+            self.optimizer.all_reduce_grads()
+            self.optimizer.step()
+            self.audio_encoder.mark_weights_changed()
+            self.lr_scheduler.step()
+            self.optimizer.zero_grad()
+            self._micro = 0
+            out["optimizer_step"] = True
+        return out
+
+    def __call__(self, waves_host: torch.Tensor, text_ids, resp_ids, device) -> Dict[str, torch.Tensor]:
+        """End-to-end micro-batch from HOST buffers: pinned H2D copy of the waveforms and ids, the training step, and
+        a D2H read of the per-utterance losses (what bench.py's `e2e` times for the training workload)."""
+        out = self.train_step(waves_host.to(device, non_blocking=True), text_ids, resp_ids)
+        keys = [k for k in ("ntp_loss", "ld_loss", "fd_loss", "total_loss") if k in out]
+        stacked = torch.stack([out[k] for k in keys]).cpu()
+        return {k: stacked[i] for i, k in enumerate(keys)}
+
+    def checkpoint(self, epoch: int) -> Dict:
+        """Same keys as REF/trainer.py:518-526."""
+        return {"audio_encoder": {k: v.detach().clone() for k, v in self.audio_encoder.state_dict().items()},
+                "optimizer": self.optimizer.state_dict(), "lr_scheduler": self.lr_scheduler.state_dict(),
+                "epoch": epoch, "step": self.step}
+
+    def load_checkpoint(self, ckpt: Dict):
+        """REF/trainer.py:116-122. load_state_dict copies INTO the flat views, so the optimizer keeps its buffers."""
+        self.audio_encoder.load_state_dict(ckpt["audio_encoder"])
+        self.audio_encoder.mark_weights_changed()
+        self.optimizer.load_state_dict(ckpt["optimizer"])
+        self.lr_scheduler.load_state_dict(ckpt["lr_scheduler"])
+        self.start_epoch = ckpt["epoch"]
+        self.step = ckpt["step"]
