@@ -182,106 +182,171 @@ col2im_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict_
   st8bf(dx + bu * C + c, acc);
 }
 
-// ---- conv layer 0 backward: thread = output channel, kR frames per iteration ------------------------------------
-constexpr int kC0 = 512, kK0 = 10, kS0 = 5, kR = 8, kW0 = kC0 / 32;
+// ---- conv layer 0 backward ------------------------------------------------------------------------------------
+// Tile = 32 output frames per block iteration. Phase 1 (warp per frame, lane = 16 channels, like the forward kernel):
+// recompute conv + LayerNorm, back-propagate GELU and LayerNorm, leave d(pre-norm) in shared memory; dgamma / dbeta
+// accumulate in registers. Phase 2 (thread = 2 channels): dW[c, j] += dpre[r, c] * x[r, j], db[c] += dpre[r, c] over
+// the tile, accumulators in registers for the whole kernel. Two block barriers per 32 frames.
+constexpr int kC0 = 512, kK0 = 10, kS0 = 5, kTile0 = 32, kTT0 = 2;
+constexpr int kConv0BwdSmem = (kK0 * kC0 + kTile0 * kC0 + kTile0 * 12) * 4;
 
-template <int N>
-__device__ __forceinline__ void block_sum(float (&v)[N], float (*s)[N], int warp, int lane) {
-#pragma unroll
-  for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) s[warp][i] = v[i];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < kW0; ++w) t += s[w][i];
-    v[i] = t;
-  }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(kC0)
+__global__ void __launch_bounds__(256)
 conv0_bwd_kernel(const float* __restrict__ wave, long long wave_stride, int samples, int frames, long long total_rows,
                  const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dW,
                  float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float s_x[kR][kK0 + 2];
-  __shared__ float s_a[kW0][kR];
-  __shared__ float s_b[kW0][2 * kR];
-  const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
-  float wr[kK0], aw[kK0];
+  extern __shared__ float sm0[];
+  float* ws = sm0;                 // [kK0][kC0] transposed taps
+  float* sd = ws + kK0 * kC0;      // [kTile0][kC0] d(pre-norm)
+  float* sx = sd + kTile0 * kC0;   // [kTile0][12] input windows
+  for (int i = threadIdx.x; i < kK0 * kC0; i += blockDim.x) {
+    const int c = i / kK0, j = i - c * kK0;
+    ws[j * kC0 + c] = w[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float aw[2][kK0], ab[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < kK0; ++j) aw[0][j] = aw[1][j] = 0.f;
+  float adg[16], adb[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) adg[i] = adb[i] = 0.f;
+
+  const long long tiles = (total_rows + kTile0 - 1) / kTile0;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // ---------------- phase 1
+#pragma unroll 1
+    for (int it = 0; it < 4 / kTT0; ++it) {
+      float xs[kTT0][kK0], acc[kTT0][16];
+      long long rows[kTT0];
+#pragma unroll
+      for (int tt = 0; tt < kTT0; ++tt) {
+        const int rt = warp * 4 + it * kTT0 + tt;
+        rows[tt] = tile * kTile0 + rt;
+        const bool ok = rows[tt] < total_rows;
+        const long long b = ok ? rows[tt] / frames : 0;
+        const long long t = ok ? rows[tt] - b * frames : 0;
+#pragma unroll
+        for (int j = 0; j < kK0; ++j) {
+          const long long idx = t * kS0 + j;
+          xs[tt][j] = (ok && idx < samples) ? __ldg(wave + b * wave_stride + idx) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kK0; ++j)
+          if (lane == j) sx[rt * 12 + j] = xs[tt][j];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 bb = *reinterpret_cast<const float2*>(bias + 64 * i + 2 * lane);
+#pragma unroll
+        for (int tt = 0; tt < kTT0; ++tt) {
+          acc[tt][2 * i] = bb.x;
+          acc[tt][2 * i + 1] = bb.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kK0; ++j) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 ww = *reinterpret_cast<const float2*>(&ws[j * kC0 + 64 * i + 2 * lane]);
+#pragma unroll
+          for (int tt = 0; tt < kTT0; ++tt) {
+            acc[tt][2 * i] = fmaf(ww.x, xs[tt][j], acc[tt][2 * i]);
+            acc[tt][2 * i + 1] = fmaf(ww.y, xs[tt][j], acc[tt][2 * i + 1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int tt = 0; tt < kTT0; ++tt) {
+        const int rt = warp * 4 + it * kTT0 + tt;
+        const bool ok = rows[tt] < total_rows;
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sum += acc[tt][i];
+        const float mean = warp_sum(sum) * (1.0f / kC0);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          acc[tt][i] -= mean;
+          q = fmaf(acc[tt][i], acc[tt][i], q);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / kC0) + eps);
+        float g16[16];
+        float sg = 0.f, sgx = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 gm = *reinterpret_cast<const float2*>(gamma + 64 * i + 2 * lane);
+          const float2 bt = *reinterpret_cast<const float2*>(beta + 64 * i + 2 * lane);
+          float2 d = make_float2(0.f, 0.f);
+          if (ok) {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(dy + rows[tt] * kC0 + 64 * i + 2 * lane);
+            d = make_float2(bf16_lo(u), bf16_hi(u));
+          }
+          const float xh0 = acc[tt][2 * i] * rstd, xh1 = acc[tt][2 * i + 1] * rstd;
+          const float dz0 = d.x * gelu_erf_grad(fmaf(gm.x, xh0, bt.x));
+          const float dz1 = d.y * gelu_erf_grad(fmaf(gm.y, xh1, bt.y));
+          adg[2 * i] = fmaf(dz0, xh0, adg[2 * i]);
+          adg[2 * i + 1] = fmaf(dz1, xh1, adg[2 * i + 1]);
+          adb[2 * i] += dz0;
+          adb[2 * i + 1] += dz1;
+          acc[tt][2 * i] = xh0;
+          acc[tt][2 * i + 1] = xh1;
+          g16[2 * i] = gm.x * dz0;
+          g16[2 * i + 1] = gm.y * dz1;
+          sg += g16[2 * i] + g16[2 * i + 1];
+          sgx = fmaf(g16[2 * i], xh0, fmaf(g16[2 * i + 1], xh1, sgx));
+        }
+        sg = warp_sum(sg) * (1.0f / kC0);
+        sgx = warp_sum(sgx) * (1.0f / kC0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float o0 = rstd * (g16[2 * i] - sg - acc[tt][2 * i] * sgx);
+          const float o1 = rstd * (g16[2 * i + 1] - sg - acc[tt][2 * i + 1] * sgx);
+          *reinterpret_cast<float2*>(&sd[rt * kC0 + 64 * i + 2 * lane]) = make_float2(o0, o1);
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------- phase 2: thread owns channels 2*tid, 2*tid + 1
+#pragma unroll 4
+    for (int r = 0; r < kTile0; ++r) {
+      const float2 d = *reinterpret_cast<const float2*>(&sd[r * kC0 + 2 * threadIdx.x]);
+      ab[0] += d.x;
+      ab[1] += d.y;
+#pragma unroll
+      for (int j = 0; j < kK0; ++j) {
+        const float xv = sx[r * 12 + j];
+        aw[0][j] = fmaf(d.x, xv, aw[0][j]);
+        aw[1][j] = fmaf(d.y, xv, aw[1][j]);
+      }
+    }
+    __syncthreads();
+  }
+  const int c0 = 2 * threadIdx.x;
 #pragma unroll
   for (int j = 0; j < kK0; ++j) {
-    wr[j] = w[c * kK0 + j];
-    aw[j] = 0.f;
+    atomicAdd(dW + c0 * kK0 + j, aw[0][j]);
+    atomicAdd(dW + (c0 + 1) * kK0 + j, aw[1][j]);
   }
-  const float bs = bias[c], gm = gamma[c], bt = beta[c];
-  float ab = 0.f, ag = 0.f, abt = 0.f;
-  for (long long r0 = static_cast<long long>(blockIdx.x) * kR; r0 < total_rows;
-       r0 += static_cast<long long>(gridDim.x) * kR) {
-    if (c < kR * kK0) {
-      const int rr = c / kK0, j = c - rr * kK0;
-      const long long row = r0 + rr;
-      float v = 0.f;
-      if (row < total_rows) {
-        const long long b = row / frames;
-        const long long idx = (row - b * frames) * kS0 + j;
-        if (idx < samples) v = wave[b * wave_stride + idx];
-      }
-      s_x[rr][j] = v;
+  atomicAdd(db + c0, ab[0]);
+  atomicAdd(db + c0 + 1, ab[1]);
+  // dgamma / dbeta: per-warp registers -> shared [8][512] -> one atomic per channel per block
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float* a = pass == 0 ? adg : adb;
+      *reinterpret_cast<float2*>(&sd[warp * kC0 + 64 * i + 2 * lane]) = make_float2(a[2 * i], a[2 * i + 1]);
     }
     __syncthreads();
-    float pre[kR], d[kR], st[kR];
+    for (int c = threadIdx.x; c < kC0; c += blockDim.x) {
+      float t = 0.f;
 #pragma unroll
-    for (int rr = 0; rr < kR; ++rr) {
-      float a = bs;
-#pragma unroll
-      for (int j = 0; j < kK0; ++j) a = fmaf(wr[j], s_x[rr][j], a);
-      pre[rr] = a;
-      st[rr] = a;
-      d[rr] = (r0 + rr < total_rows) ? __bfloat162float(dy[(r0 + rr) * kC0 + c]) : 0.f;
-    }
-    block_sum<kR>(st, s_a, warp, lane);
-    float mean[kR];
-#pragma unroll
-    for (int rr = 0; rr < kR; ++rr) {
-      mean[rr] = st[rr] * (1.0f / kC0);
-      pre[rr] -= mean[rr];
-      st[rr] = pre[rr] * pre[rr];
-    }
-    block_sum<kR>(st, s_a, warp, lane);
-    float st2[2 * kR], rstd[kR];
-#pragma unroll
-    for (int rr = 0; rr < kR; ++rr) {
-      rstd[rr] = rsqrtf(st[rr] * (1.0f / kC0) + eps);
-      const float xh = pre[rr] * rstd[rr];
-      const float dz = d[rr] * gelu_erf_grad(fmaf(gm, xh, bt));
-      ag = fmaf(dz, xh, ag);
-      abt += dz;
-      pre[rr] = xh;
-      d[rr] = gm * dz;
-      st2[rr] = d[rr];
-      st2[kR + rr] = d[rr] * xh;
-    }
-    block_sum<2 * kR>(st2, s_b, warp, lane);
-#pragma unroll
-    for (int rr = 0; rr < kR; ++rr) {
-      const float dpre = rstd[rr] * (d[rr] - st2[rr] * (1.0f / kC0) - pre[rr] * st2[kR + rr] * (1.0f / kC0));
-      ab += dpre;
-#pragma unroll
-      for (int j = 0; j < kK0; ++j) aw[j] = fmaf(dpre, s_x[rr][j], aw[j]);
+      for (int wq = 0; wq < 8; ++wq) t += sd[wq * kC0 + c];
+      atomicAdd((pass == 0 ? dgamma : dbeta) + c, t);
     }
     __syncthreads();
   }
-#pragma unroll
-  for (int j = 0; j < kK0; ++j) atomicAdd(dW + c * kK0 + j, aw[j]);
-  atomicAdd(db + c, ab);
-  atomicAdd(dgamma + c, ag);
-  atomicAdd(dbeta + c, abt);
 }
 
 }  // namespace
@@ -359,10 +424,15 @@ int conv0_bwd(const float* wave, long long wave_stride, int batches, int samples
   B2S_REQUIRE(wave && w && bias && gamma && beta && dy_bf16 && dW && db && dgamma && dbeta, "conv0_bwd: null pointer");
   B2S_REQUIRE(frames == (samples - kK0) / kS0 + 1, "conv0_bwd: frames mismatch");
   const long long total = static_cast<long long>(batches) * frames;
-  long long blocks = (total + kR - 1) / kR;
-  const long long cap = 2LL * num_sms();
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2S_CUDA_CHECK(cudaFuncSetAttribute(conv0_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv0BwdSmem));
+    attr_set = true;
+  }
+  long long blocks = (total + kTile0 - 1) / kTile0;
+  const long long cap = num_sms();  // 177 registers x 256 threads + 87 KB shared memory: one resident block per SM
   if (blocks > cap) blocks = cap;
-  conv0_bwd_kernel<<<static_cast<unsigned>(blocks), kC0, 0, stream>>>(
+  conv0_bwd_kernel<<<static_cast<unsigned>(blocks), 256, kConv0BwdSmem, stream>>>(
       wave, wave_stride, samples, frames, total, w, bias, gamma, beta, eps,
       reinterpret_cast<const __nv_bfloat16*>(dy_bf16), dW, db, dgamma, dbeta);
   B2S_LAUNCH_CHECK();

@@ -704,7 +704,21 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
     int splits = a.k_splits;
     if (splits == 0) {  // auto: only the accumulate epilogue can split
       splits = 1;
-      if (a.epi == EPI_ACCUM_F32 && total > 0) splits = static_cast<int>((sms / cg) / total);
+      if (a.epi == EPI_ACCUM_F32 && total > 0) {
+        // fill whole waves of the persistent grid: maximise tiles*s / (waves * clusters), small cost per extra split
+        // for the added atomic traffic (measured: profiles/r01_bench_splits.jsonl)
+        const long long clusters = sms / cg;
+        double best = -1.0;
+        for (int sp = 1; sp <= 16 && sp * 4 <= p.num_kb; ++sp) {
+          const long long work = total * sp;
+          const long long waves = (work + clusters - 1) / clusters;
+          const double eff = static_cast<double>(work) / static_cast<double>(waves * clusters) - 0.004 * sp;
+          if (eff > best + 1e-9) {
+            best = eff;
+            splits = sp;
+          }
+        }
+      }
     }
     if (splits > p.num_kb / 4) splits = p.num_kb / 4;
     if (splits < 1) splits = 1;

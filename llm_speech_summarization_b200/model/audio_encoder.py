@@ -403,39 +403,112 @@ class AudioEncoder(nn.Module):
         self._packed_key = None
         self._pos_w_dgrad = None
 
+    def flat_param_order(self):
+        """Parameter order for a flat optimizer buffer that makes q|k|v weights (and biases) of every layer adjacent,
+        so the fused-QKV gradient [3H, H] the kernels produce IS the concatenation of the three `.grad` views."""
+        if self.encoder_base != "hubert":
+            return list(self.parameters())
+        order, seen = [], set()
+
+        def push(p):
+            if id(p) not in seen:
+                seen.add(id(p))
+                order.append(p)
+
+        for lay in self.encoder.encoder.layers:
+            a = lay.attention
+            for proj in (a.q_proj, a.k_proj, a.v_proj):
+                push(proj.weight)
+            for proj in (a.q_proj, a.k_proj, a.v_proj):
+                push(proj.bias)
+        for p in self.parameters():
+            push(p)
+        return order
+
+    def _grad_spec(self):
+        """(buffer name, packed shape, parameters that tile the buffer row-wise) for every accumulator whose packed
+        layout equals the parameters' own layout (everything except the conv weights and the weight-normed pos conv)."""
+        enc = self.encoder
+        arch = enc.arch
+        H, F_ = arch.hidden, arch.ffn
+        fe, fp, pc = enc.feature_extractor.conv_layers, enc.feature_projection, enc.encoder.pos_conv_embed.conv
+        C_ = self.embed_projection.out_features
+        spec = [("conv0_w", (arch.conv_dim[0], arch.conv_kernel[0]), [fe[0].conv.weight]),
+                ("conv0_b", (512,), [fe[0].conv.bias]), ("conv0_ln_g", (512,), [fe[0].layer_norm.weight]),
+                ("conv0_ln_b", (512,), [fe[0].layer_norm.bias]),
+                ("fp_ln_g", (512,), [fp.layer_norm.weight]), ("fp_ln_b", (512,), [fp.layer_norm.bias]),
+                ("fp_w", (H, 512), [fp.projection.weight]), ("fp_b", (H,), [fp.projection.bias]),
+                ("pos_b", (H,), [pc.bias]), ("final_ln_g", (H,), [enc.encoder.layer_norm.weight]),
+                ("final_ln_b", (H,), [enc.encoder.layer_norm.bias]), ("proj_w", (C_, H), [self.embed_projection.weight]),
+                ("proj_b", (C_,), [self.embed_projection.bias])]
+        for i in range(6):
+            spec += [(f"conv_b{i}", (512,), [fe[i + 1].conv.bias]), (f"conv_ln_g{i}", (512,), [fe[i + 1].layer_norm.weight]),
+                     (f"conv_ln_b{i}", (512,), [fe[i + 1].layer_norm.bias])]
+        for l, lay in enumerate(enc.encoder.layers):
+            a, ff = lay.attention, lay.feed_forward
+            spec += [(f"l{l}.ln1_g", (H,), [lay.layer_norm.weight]), (f"l{l}.ln1_b", (H,), [lay.layer_norm.bias]),
+                     (f"l{l}.wqkv", (3 * H, H), [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight]),
+                     (f"l{l}.bqkv", (3 * H,), [a.q_proj.bias, a.k_proj.bias, a.v_proj.bias]),
+                     (f"l{l}.wo", (H, H), [a.out_proj.weight]), (f"l{l}.bo", (H,), [a.out_proj.bias]),
+                     (f"l{l}.ln2_g", (H,), [lay.final_layer_norm.weight]), (f"l{l}.ln2_b", (H,), [lay.final_layer_norm.bias]),
+                     (f"l{l}.w1", (F_, H), [ff.intermediate_dense.weight]), (f"l{l}.b1", (F_,), [ff.intermediate_dense.bias]),
+                     (f"l{l}.w2", (H, F_), [ff.output_dense.weight]), (f"l{l}.b2", (H,), [ff.output_dense.bias])]
+        return spec
+
     def _grad_buffers(self):
-        """fp32 gradient accumulators in the kernels' packed layouts (include/b2s.h: b2s_hubert_grads)."""
-        if self._grads is not None:
-            return self._grads
+        """fp32 gradient accumulators in the kernels' packed layouts (include/b2s.h: b2s_hubert_grads). When the
+        parameters already own fp32 `.grad` tensors laid out like the packed buffer (a flat optimizer buffer in
+        `flat_param_order`), the kernels accumulate straight into them; otherwise into scratch that `flush_grads`
+        adds to `.grad`."""
         if self.encoder_base != "hubert":
             raise NotImplementedError("the training backward is built for the HuBERT encoder")
+        key = tuple(0 if p.grad is None else p.grad.data_ptr() for p in self.parameters())
+        if self._grads is not None and self._grads[3] == key:
+            return self._grads
+        if self._grads is not None and any(float(t.abs().max()) != 0.0 for t in self._grads[2].values()):
+            raise RuntimeError("AudioEncoder: .grad tensors were replaced while un-flushed gradients are pending")
         arch = self.encoder.arch
         dev = self.embed_projection.weight.device
-        H, F_, L = arch.hidden, arch.ffn, arch.layers
+        H, L = arch.hidden, arch.layers
         z = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.float32)
-        t = {"conv0_w": z(arch.conv_dim[0], arch.conv_kernel[0]), "conv0_b": z(512), "conv0_ln_g": z(512),
-             "conv0_ln_b": z(512), "fp_ln_g": z(512), "fp_ln_b": z(512), "fp_w": z(H, 512), "fp_b": z(H),
-             "pos_w": z(H, arch.pos_k * (H // arch.pos_groups)), "pos_b": z(H), "final_ln_g": z(H), "final_ln_b": z(H),
-             "proj_w": z(self.embed_projection.out_features, H), "proj_b": z(self.embed_projection.out_features)}
+        scratch, ptr, pending = {}, {}, []
+
+        def direct(ps):
+            addr = None
+            for q in ps:
+                gq = q.grad
+                if gq is None or gq.dtype != torch.float32 or not gq.is_contiguous() or gq.shape != q.shape:
+                    return None
+                if addr is not None and gq.data_ptr() != addr:
+                    return None
+                addr = gq.data_ptr() + gq.numel() * 4
+            return ps[0].grad.data_ptr()
+
+        for name, shape, ps in self._grad_spec():
+            d = direct(ps)
+            if d is None:
+                scratch[name] = z(*shape)
+                pending.append((name, ps))
+                d = scratch[name].data_ptr()
+            ptr[name] = d
+        scratch["pos_w"] = z(H, arch.pos_k * (H // arch.pos_groups))
+        ptr["pos_w"] = scratch["pos_w"].data_ptr()
         for i in range(6):
-            t[f"conv_w{i}"] = z(512, arch.conv_kernel[i + 1] * 512)
-            t[f"conv_b{i}"], t[f"conv_ln_g{i}"], t[f"conv_ln_b{i}"] = z(512), z(512), z(512)
+            scratch[f"conv_w{i}"] = z(512, arch.conv_kernel[i + 1] * 512)
+            ptr[f"conv_w{i}"] = scratch[f"conv_w{i}"].data_ptr()
         g = _lib.HubertGrads()
         for k in ("conv0_w", "conv0_b", "conv0_ln_g", "conv0_ln_b", "fp_ln_g", "fp_ln_b", "fp_w", "fp_b", "pos_w",
                   "pos_b", "final_ln_g", "final_ln_b", "proj_w", "proj_b"):
-            setattr(g, k, t[k].data_ptr())
+            setattr(g, k, ptr[k])
         for i in range(6):
-            g.conv_w[i], g.conv_b[i] = t[f"conv_w{i}"].data_ptr(), t[f"conv_b{i}"].data_ptr()
-            g.conv_ln_g[i], g.conv_ln_b[i] = t[f"conv_ln_g{i}"].data_ptr(), t[f"conv_ln_b{i}"].data_ptr()
+            g.conv_w[i], g.conv_b[i] = ptr[f"conv_w{i}"], ptr[f"conv_b{i}"]
+            g.conv_ln_g[i], g.conv_ln_b[i] = ptr[f"conv_ln_g{i}"], ptr[f"conv_ln_b{i}"]
         layers = (_lib.EncoderLayerGrads * L)()
-        shapes = dict(ln1_g=(H,), ln1_b=(H,), wqkv=(3 * H, H), bqkv=(3 * H,), wo=(H, H), bo=(H,), ln2_g=(H,),
-                      ln2_b=(H,), w1=(F_, H), b1=(F_,), w2=(H, F_), b2=(H,))
         for l in range(L):
-            for k, shp in shapes.items():
-                t[f"l{l}.{k}"] = z(*shp)
-                setattr(layers[l], k, t[f"l{l}.{k}"].data_ptr())
+            for k in ("ln1_g", "ln1_b", "wqkv", "bqkv", "wo", "bo", "ln2_g", "ln2_b", "w1", "b1", "w2", "b2"):
+                setattr(layers[l], k, ptr[f"l{l}.{k}"])
         g.layers = C.cast(layers, C.POINTER(_lib.EncoderLayerGrads))
-        self._grads = (g, layers, t)
+        self._grads = (g, layers, scratch, key, pending)
         return self._grads
 
     def forward_train(self, input: torch.Tensor) -> torch.Tensor:
@@ -496,33 +569,31 @@ class AudioEncoder(nn.Module):
 
     @torch.no_grad()
     def flush_grads(self) -> None:
-        """Packed accumulators -> `.grad` of the parameters (HF layouts; += like autograd), then zero them.
-        Pure re-indexing plus the weight-norm chain rule of the positional conv (once per optimizer step)."""
-        _, _, t = self._grad_buffers()
+        """Scratch accumulators -> `.grad` of the parameters (HF layouts; += like autograd), then zero the scratch.
+        Pure re-indexing plus the weight-norm chain rule of the positional conv (once per optimizer step); buffers
+        that alias `.grad` directly need nothing."""
+        _, _, t, _, pending = self._grad_buffers()
         enc = self.encoder
         arch = enc.arch
         H = arch.hidden
 
         def add(p, g):
             g = g.reshape(p.shape).to(p.dtype)
-            p.grad = g.clone() if p.grad is None else p.grad.add_(g)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.add_(g)
 
+        for name, ps in pending:
+            row = 0
+            for p in ps:
+                n = p.shape[0]
+                add(p, t[name][row:row + n])
+                row += n
         fe = enc.feature_extractor.conv_layers
-        add(fe[0].conv.weight, t["conv0_w"])
-        add(fe[0].conv.bias, t["conv0_b"])
-        add(fe[0].layer_norm.weight, t["conv0_ln_g"])
-        add(fe[0].layer_norm.bias, t["conv0_ln_b"])
         for i in range(6):
             k = arch.conv_kernel[i + 1]
             add(fe[i + 1].conv.weight, t[f"conv_w{i}"].view(512, k, 512).permute(0, 2, 1))
-            add(fe[i + 1].conv.bias, t[f"conv_b{i}"])
-            add(fe[i + 1].layer_norm.weight, t[f"conv_ln_g{i}"])
-            add(fe[i + 1].layer_norm.bias, t[f"conv_ln_b{i}"])
-        fp = enc.feature_projection
-        add(fp.layer_norm.weight, t["fp_ln_g"])
-        add(fp.layer_norm.bias, t["fp_ln_b"])
-        add(fp.projection.weight, t["fp_w"])
-        add(fp.projection.bias, t["fp_b"])
         pc = enc.encoder.pos_conv_embed.conv
         cg = H // arch.pos_groups
         dW = t["pos_w"].view(H, arch.pos_k, cg).permute(0, 2, 1)  # [H, cg, K] like original1
@@ -532,27 +603,6 @@ class AudioEncoder(nn.Module):
         dot = (dW * v).sum(dim=(0, 1), keepdim=True)
         add(pc.parametrizations.weight.original0, dot / nrm)
         add(pc.parametrizations.weight.original1, (g0 / nrm) * (dW - dot / (nrm * nrm) * v))
-        add(pc.bias, t["pos_b"])
-        for l, lay in enumerate(enc.encoder.layers):
-            a = lay.attention
-            q = lambda k: t[f"l{l}.{k}"]
-            add(lay.layer_norm.weight, q("ln1_g"))
-            add(lay.layer_norm.bias, q("ln1_b"))
-            for j, proj in enumerate((a.q_proj, a.k_proj, a.v_proj)):
-                add(proj.weight, q("wqkv")[j * H:(j + 1) * H])
-                add(proj.bias, q("bqkv")[j * H:(j + 1) * H])
-            add(a.out_proj.weight, q("wo"))
-            add(a.out_proj.bias, q("bo"))
-            add(lay.final_layer_norm.weight, q("ln2_g"))
-            add(lay.final_layer_norm.bias, q("ln2_b"))
-            add(lay.feed_forward.intermediate_dense.weight, q("w1"))
-            add(lay.feed_forward.intermediate_dense.bias, q("b1"))
-            add(lay.feed_forward.output_dense.weight, q("w2"))
-            add(lay.feed_forward.output_dense.bias, q("b2"))
-        add(enc.encoder.layer_norm.weight, t["final_ln_g"])
-        add(enc.encoder.layer_norm.bias, t["final_ln_b"])
-        add(self.embed_projection.weight, t["proj_w"])
-        add(self.embed_projection.bias, t["proj_b"])
         for buf in t.values():
             buf.zero_()
 

@@ -29,7 +29,7 @@ from . import _lib
 
 class FlatAdamW:
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
-                 frozen_params=(), exclude=()):
+                 frozen_params=(), exclude=(), order=None):
         self.params: List[torch.nn.Parameter] = [p for p in params]
         skip = {id(p) for p in exclude}  # parameters that never receive a gradient: torch keeps no state for them
         self.trainable = [p for p in self.params if p.requires_grad and id(p) not in skip]
@@ -46,6 +46,10 @@ class FlatAdamW:
         self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(n, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
+        if order is not None:  # layout of the flat buffers (state_dict indices still follow `params`)
+            keep = {id(p) for p in self.trainable}
+            self.trainable = [p for p in order if id(p) in keep]
+            assert len(self.trainable) == len(keep), "FlatAdamW: `order` must cover every trainable parameter"
         self.offsets = []
         off = 0
         for p in self.trainable:
@@ -154,7 +158,8 @@ class EncoderTrainer:
         # masked_spec_embed is only read by SpecAugment (train-mode HF, not applied): it never gets a gradient
         unused = [p for n, p in audio_encoder.named_parameters() if n.endswith("masked_spec_embed")]
         self.optimizer = FlatAdamW(audio_encoder.parameters(), lr=lr, betas=betas, weight_decay=weight_decay,
-                                   frozen_params=frozen, exclude=unused)
+                                   frozen_params=frozen, exclude=unused,
+                                   order=getattr(audio_encoder, "flat_param_order", lambda: None)())
         self.lr_scheduler = PolynomialLR(self.optimizer, total_iters=total_optimizer_steps, power=1.0)
         self.grad_accum_interval = int(grad_accum_interval)
         self.step = 0
