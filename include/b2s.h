@@ -271,6 +271,24 @@ int b2s_llama_prefill(const b2s_llama_weights* w, float* h, int32_t rows, const 
                       const int32_t* tap_rows_b, int32_t pairs, float* fd_sq, float* all_hidden, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ---- greedy decode with a KV cache (REF/inference.py:55-74, REF/trainer.py:530-545: HF generate after the prefill).
+ * Cache: bf16 [layers][slots][2*kv_heads*head_dim], one row = k (post-RoPE) | v of one token.
+ * b2s_llama_prefill_kv = b2s_llama_prefill that also stores packed row r of every layer into slot kv_slot_of_row[r]
+ * (< 0 = skip). b2s_llama_decode_step consumes ONE new token per sequence: its k|v are appended at slot
+ * seq_start[b] + seq_len[b] (seq_len = tokens already cached = the new token's position) and logits bf16 [batch, vocab]
+ * come back; the caller advances seq_len. */
+size_t b2s_llama_kv_cache_bytes(const b2s_llama_weights* w, int32_t slots);
+int b2s_llama_prefill_kv(const b2s_llama_weights* w, float* h, int32_t rows, const int32_t* cu_seqlens,
+                         int32_t num_seqs, int32_t max_seqlen, const int32_t* positions,
+                         const int32_t* logit_rows_index, int32_t logit_rows, void* logits_bf16, void* kv_cache,
+                         int32_t kv_slots, const int32_t* kv_slot_of_row, void* workspace, size_t workspace_bytes,
+                         void* stream);
+size_t b2s_llama_decode_workspace_bytes(const b2s_llama_weights* w, int32_t batch);
+int b2s_llama_decode_step(const b2s_llama_weights* w, const void* embed_table_bf16, const int32_t* token_ids,
+                          int32_t batch, void* kv_cache, int32_t kv_slots, const int32_t* seq_start,
+                          const int32_t* seq_len, void* logits_bf16, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Training step (REF/trainer.py:270-384): forward with saved activations + backward of the frozen LLM
  * (data gradients only: REF/trainer.py:62-64), memory-bound backward kernels, AdamW. */

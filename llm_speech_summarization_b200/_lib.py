@@ -158,6 +158,13 @@ PROTOTYPES = {
     "b2s_swiglu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "b2s_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2s_gather_rows_f32": (c_int, [P_f32, P_int, P_f32, c_int64, c_int, c_void_p]),
+    "b2s_llama_kv_cache_bytes": (C.c_size_t, [C.POINTER(LlamaWeights), c_int]),
+    "b2s_llama_prefill_kv": (c_int, [C.POINTER(LlamaWeights), c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
+                                     c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, C.c_size_t,
+                                     c_void_p]),
+    "b2s_llama_decode_workspace_bytes": (C.c_size_t, [C.POINTER(LlamaWeights), c_int]),
+    "b2s_llama_decode_step": (c_int, [C.POINTER(LlamaWeights), c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, C.c_size_t, c_void_p]),
     "b2s_hubert_saved_bytes": (C.c_size_t, [C.POINTER(HubertWeights), c_int, c_int]),
     "b2s_hubert_backward_workspace_bytes": (C.c_size_t, [C.POINTER(HubertWeights), c_int, c_int]),
     "b2s_hubert_forward_train": (c_int, [C.POINTER(HubertWeights), c_void_p, c_int64, c_int, c_int, c_void_p,

@@ -58,6 +58,16 @@ int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_
                   float* fd_sq, float* all_hidden, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 size_t llama_train_workspace_bytes(const b2s_llama_weights* w, int rows, int logit_rows);
+size_t llama_kv_cache_bytes(const b2s_llama_weights* w, int slots);
+int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* cu_seqlens, int num_seqs,
+                     int max_seqlen, const int* positions, const int* logit_rows_index, int logit_rows,
+                     void* logits_bf16, const int* tap_layers, int num_taps, const int* tap_rows_a,
+                     const int* tap_rows_b, int pairs, float* fd_sq, float* all_hidden, void* kv_cache, int kv_slots,
+                     const int* kv_slot_of_row, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t llama_decode_workspace_bytes(const b2s_llama_weights* w, int batch);
+int llama_decode_step(const b2s_llama_weights* w, const void* embed_table, const int* token_ids, int batch,
+                      void* kv_cache, int kv_slots, const int* seq_start, const int* seq_len, void* logits_bf16,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t hubert_saved_bytes(const b2s_hubert_weights* w, int batches, int samples);
 size_t hubert_backward_workspace_bytes(const b2s_hubert_weights* w, int batches, int samples);
 int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long long wave_stride, int batches, int samples,
@@ -338,6 +348,27 @@ int b2s_conv0_bwd(const float* wave, int64_t wave_stride, int32_t batches, int32
                   int32_t frames, float* dW, float* db, float* dgamma, float* dbeta, void* stream) {
   return conv0_bwd(wave, wave_stride, batches, samples, w, bias, gamma, beta, eps, dy_bf16, frames, dW, db, dgamma,
                    dbeta, S(stream));
+}
+
+size_t b2s_llama_kv_cache_bytes(const b2s_llama_weights* w, int32_t slots) { return llama_kv_cache_bytes(w, slots); }
+int b2s_llama_prefill_kv(const b2s_llama_weights* w, float* h, int32_t rows, const int32_t* cu_seqlens,
+                         int32_t num_seqs, int32_t max_seqlen, const int32_t* positions,
+                         const int32_t* logit_rows_index, int32_t logit_rows, void* logits_bf16, void* kv_cache,
+                         int32_t kv_slots, const int32_t* kv_slot_of_row, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  return llama_prefill_kv(w, h, rows, cu_seqlens, num_seqs, max_seqlen, positions, logit_rows_index, logit_rows,
+                          logits_bf16, nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr, kv_cache, kv_slots,
+                          kv_slot_of_row, workspace, workspace_bytes, S(stream));
+}
+size_t b2s_llama_decode_workspace_bytes(const b2s_llama_weights* w, int32_t batch) {
+  return llama_decode_workspace_bytes(w, batch);
+}
+int b2s_llama_decode_step(const b2s_llama_weights* w, const void* embed_table_bf16, const int32_t* token_ids,
+                          int32_t batch, void* kv_cache, int32_t kv_slots, const int32_t* seq_start,
+                          const int32_t* seq_len, void* logits_bf16, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  return llama_decode_step(w, embed_table_bf16, token_ids, batch, kv_cache, kv_slots, seq_start, seq_len, logits_bf16,
+                           workspace, workspace_bytes, S(stream));
 }
 
 }  // extern "C"

@@ -480,10 +480,32 @@ size_t llama_workspace_bytes(const b2s_llama_weights* w, int rows, int logit_row
   return pl.bytes;
 }
 
+int kv_cache_store(const b2s_llama_weights* w, int layer, const void* qkv, long long rows, void* kv_cache, int kv_slots,
+                   const int* slot_of_row, cudaStream_t stream);  // decode.cu
+
+int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* cu_seqlens, int num_seqs,
+                     int max_seqlen, const int* positions, const int* logit_rows_index, int logit_rows,
+                     void* logits_bf16, const int* tap_layers, int num_taps, const int* tap_rows_a,
+                     const int* tap_rows_b, int pairs, float* fd_sq, float* all_hidden, void* kv_cache, int kv_slots,
+                     const int* kv_slot_of_row, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_seqlens, int num_seqs, int max_seqlen,
                   const int* positions, const int* logit_rows_index, int logit_rows, void* logits_bf16,
                   const int* tap_layers, int num_taps, const int* tap_rows_a, const int* tap_rows_b, int pairs,
                   float* fd_sq, float* all_hidden, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return llama_prefill_kv(w, h, rows, cu_seqlens, num_seqs, max_seqlen, positions, logit_rows_index, logit_rows,
+                          logits_bf16, tap_layers, num_taps, tap_rows_a, tap_rows_b, pairs, fd_sq, all_hidden, nullptr, 0,
+                          nullptr, workspace, workspace_bytes, stream);
+}
+
+// llama_prefill that additionally leaves every layer's post-RoPE k | v rows in a KV cache (decode.cu) so a greedy
+// decode loop can continue from the prompt (REF/inference.py:55-74).
+int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* cu_seqlens, int num_seqs,
+                     int max_seqlen, const int* positions, const int* logit_rows_index, int logit_rows,
+                     void* logits_bf16, const int* tap_layers, int num_taps, const int* tap_rows_a,
+                     const int* tap_rows_b, int pairs, float* fd_sq, float* all_hidden, void* kv_cache, int kv_slots,
+                     const int* kv_slot_of_row, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  B2S_REQUIRE(kv_cache == nullptr || (kv_slots > 0 && kv_slot_of_row != nullptr), "llama_prefill: bad KV cache arguments");
   B2S_REQUIRE(w && h && cu_seqlens && positions && workspace, "llama_prefill: null pointer");
   B2S_REQUIRE(rows > 0 && num_seqs > 0 && max_seqlen > 0, "llama_prefill: empty batch");
   B2S_REQUIRE(w->head_dim == 128, "llama_prefill: head_dim must be 128 (got %d)", w->head_dim);
@@ -520,6 +542,10 @@ int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_
       g.positions = positions;
       g.rope_cols = (Hq + Hkv) * D;
       rc = gemm_bf16_launch(g, stream);
+      if (rc != B2S_OK) return rc;
+    }
+    if (kv_cache != nullptr) {
+      rc = kv_cache_store(w, l, pl.qkv, rows, kv_cache, kv_slots, kv_slot_of_row, stream);
       if (rc != B2S_OK) return rc;
     }
     {

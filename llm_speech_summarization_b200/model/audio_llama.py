@@ -394,25 +394,93 @@ class AudioLlamaForCausalLM(nn.Module):
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=hidden_states,
                                       attentions=None)
 
+    # ------------------------------------------------------------------------------------------ KV-cache decode
     @torch.no_grad()
-    def generate(self, input_ids=None, inputs_embeds=None, max_new_tokens: int = 256, **kwargs):
+    def prefill_with_cache(self, embeds: Sequence[torch.Tensor], max_new_tokens: int):
+        """Prefill B prompts (list of (L_b, H) embeddings) and leave their K/V in a fresh cache with room for
+        max_new_tokens more tokens each. Returns (last-row logits bf16 [B, V], cache state dict)."""
+        w = self.packed()[0]
+        a = self.arch
+        lib = _lib.load()
+        dev = self.device
+        lens = [int(e.shape[0]) for e in embeds]
+        B = len(lens)
+        cap = [L + int(max_new_tokens) for L in lens]
+        starts = [sum(cap[:b]) for b in range(B)]
+        slots = sum(cap)
+        if max(cap) > a.max_pos:
+            raise ValueError(f"prompt + max_new_tokens = {max(cap)} exceeds the RoPE table ({a.max_pos})")
+        i32 = lambda x: torch.tensor(x, dtype=torch.int32, device=dev)
+        cu = i32([0] + [sum(lens[:b + 1]) for b in range(B)])
+        pos = i32([t for L in lens for t in range(L)])
+        slot_of_row = i32([starts[b] + t for b, L in enumerate(lens) for t in range(L)])
+        last = i32([sum(lens[:b + 1]) - 1 for b in range(B)])
+        h = torch.cat([e.to(dev, torch.float32) for e in embeds], dim=0).contiguous()
+        rows = h.shape[0]
+        cache = torch.empty(lib.b2s_llama_kv_cache_bytes(C.byref(w), slots), device=dev, dtype=torch.uint8)
+        logits = torch.empty(B, a.vocab, device=dev, dtype=torch.bfloat16)
+        nbytes = lib.b2s_llama_workspace_bytes(C.byref(w), rows, B)
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        _lib.check(lib.b2s_llama_prefill_kv(C.byref(w), h.data_ptr(), rows, cu.data_ptr(), B, max(lens), pos.data_ptr(),
+                                            last.data_ptr(), B, logits.data_ptr(), cache.data_ptr(), slots,
+                                            slot_of_row.data_ptr(), ws.data_ptr(), nbytes,
+                                            torch.cuda.current_stream().cuda_stream), "llama_prefill_kv")
+        dbytes = lib.b2s_llama_decode_workspace_bytes(C.byref(w), B)
+        state = dict(cache=cache, slots=slots, seq_start=i32(starts), seq_len=i32(lens), B=B,
+                     ws=torch.empty(dbytes, device=dev, dtype=torch.uint8), cap=cap, lens=list(lens))
+        return logits, state
+
+    @torch.no_grad()
+    def decode_step(self, token_ids: torch.Tensor, state) -> torch.Tensor:
+        """Append one token per sequence (int32 [B], device) and return the next-token logits bf16 [B, V]."""
+        w = self.packed()[0]
+        lib = _lib.load()
+        B = state["B"]
+        if max(l + 1 for l in state["lens"]) > max(state["cap"]):
+            raise RuntimeError("KV cache is full")
+        tok = token_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        logits = torch.empty(B, self.arch.vocab, device=self.device, dtype=torch.bfloat16)
+        _lib.check(lib.b2s_llama_decode_step(C.byref(w), self.model.embed_tokens.weight.data_ptr(), tok.data_ptr(), B,
+                                             state["cache"].data_ptr(), state["slots"], state["seq_start"].data_ptr(),
+                                             state["seq_len"].data_ptr(), logits.data_ptr(), state["ws"].data_ptr(),
+                                             state["ws"].numel(), torch.cuda.current_stream().cuda_stream),
+                   "llama_decode_step")
+        state["seq_len"] += 1
+        state["lens"] = [l + 1 for l in state["lens"]]
+        return logits
+
+    @torch.no_grad()
+    def generate(self, input_ids=None, inputs_embeds=None, max_new_tokens: int = 256, use_kv_cache: bool = True,
+                 **kwargs):
         """Greedy decoding from a prompt given as embeddings (REF/inference.py:55-66, REF/trainer.py:530-545);
-        returns only the new token ids, like HF generate with inputs_embeds.
-        Round-1 note: the prompt prefill is the B200 path; each new token re-runs the prefill over the grown
-        sequence (no KV cache yet -- the cached decode loop is row f1 of SURVEY.md section 8)."""
+        returns only the new token ids, like HF generate with inputs_embeds. The prompt is prefilled once into a KV
+        cache and every new token is one `b2s_llama_decode_step` (use_kv_cache=False re-runs the prefill per token:
+        the O(n^2) cross-check used by the tests)."""
         if inputs_embeds is None:
             inputs_embeds = self.model.embed_tokens(input_ids)
         if inputs_embeds.shape[0] != 1:
             raise NotImplementedError("generate() is batch-1 like the reference")
-        seq = inputs_embeds.to(torch.bfloat16)
         eos = set(int(e) for e in self.arch.eos)
         out: List[int] = []
-        for _ in range(int(max_new_tokens)):
-            logits = self.forward(inputs_embeds=seq, num_logits_to_keep=1).logits
-            nxt = int(logits[0, -1].float().argmax())
+        if not use_kv_cache:
+            seq = inputs_embeds.to(torch.bfloat16)
+            for _ in range(int(max_new_tokens)):
+                logits = self.forward(inputs_embeds=seq, num_logits_to_keep=1).logits
+                nxt = int(logits[0, -1].float().argmax())
+                out.append(nxt)
+                if nxt in eos:
+                    break
+                tok = torch.tensor([[nxt]], device=seq.device)
+                seq = torch.cat([seq, self.model.embed_tokens(tok)], dim=1)
+            return torch.tensor([out], dtype=torch.long, device=seq.device)
+        if int(max_new_tokens) <= 0:
+            return torch.zeros(1, 0, dtype=torch.long, device=self.device)
+        logits, state = self.prefill_with_cache([inputs_embeds[0]], int(max_new_tokens))
+        for i in range(int(max_new_tokens)):
+            nxt_t = logits[0].float().argmax().to(torch.int32).reshape(1)
+            nxt = int(nxt_t)
             out.append(nxt)
-            if nxt in eos:
+            if nxt in eos or i + 1 == int(max_new_tokens):
                 break
-            tok = torch.tensor([[nxt]], device=seq.device)
-            seq = torch.cat([seq, self.model.embed_tokens(tok)], dim=1)
-        return torch.tensor([out], dtype=torch.long, device=seq.device)
+            logits = self.decode_step(nxt_t, state)
+        return torch.tensor([out], dtype=torch.long, device=self.device)
