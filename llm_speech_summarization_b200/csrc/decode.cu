@@ -35,35 +35,48 @@ kv_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int col0,
       *reinterpret_cast<const uint4*>(qkv + r * ld + col0 + c);
 }
 
-// one query row per (sequence, head) against the cached keys: 4 warps split the keys, lane = 4 of the 128 dims
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// one query row per (sequence, head) against the cached keys plus the new token's own k|v (read from the QKV buffer and
+// appended to the cache by the first query head of each kv group): 4 warps split the keys, lane = 4 of the 128 dims
 constexpr int kDecWarps = 4;
 __global__ void __launch_bounds__(kDecWarps * 32)
-decode_attn_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ cache,
+decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, long long ldq, __nv_bfloat16* __restrict__ cache,
                    const int* __restrict__ seq_start, const int* __restrict__ seq_len, __nv_bfloat16* __restrict__ o,
                    int Hq, int Hkv, float scale_log2) {
   constexpr int D = 128;
   __shared__ float s_m[kDecWarps], s_l[kDecWarps], s_acc[kDecWarps][D];
+  pdl_launch_dependents();
   const int b = blockIdx.x, h = blockIdx.y;
-  const int kvh = h / (Hq / Hkv);
+  const int group = Hq / Hkv, kvh = h / group;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = seq_len[b] + 1;  // the new token's k|v were appended before this launch
+  pdl_wait();  // everything below depends on the QKV projection of this step
+  const int n = seq_len[b];  // cached tokens; the new token is key number n
   const long long ldkv = 2LL * Hkv * D;
-  const __nv_bfloat16* kbase = cache + static_cast<long long>(seq_start[b]) * ldkv + kvh * D + lane * 4;
+  __nv_bfloat16* kbase = cache + static_cast<long long>(seq_start[b]) * ldkv + kvh * D + lane * 4;
   const __nv_bfloat16* vbase = kbase + Hkv * D;
+  const __nv_bfloat16* qrow = qkv + b * ldq;
+  const uint2 knew = *reinterpret_cast<const uint2*>(qrow + (Hq + kvh) * D + lane * 4);
+  const uint2 vnew = *reinterpret_cast<const uint2*>(qrow + (Hq + Hkv + kvh) * D + lane * 4);
+  if (warp == 0 && h % group == 0) {  // append: nobody reads slot n of the cache during this launch
+    *reinterpret_cast<uint2*>(kbase + n * ldkv) = knew;
+    *reinterpret_cast<uint2*>(kbase + Hkv * D + n * ldkv) = vnew;
+  }
   float qv[4];
   {
-    const uint2 u = *reinterpret_cast<const uint2*>(q + b * ldq + h * D + lane * 4);
+    const uint2 u = *reinterpret_cast<const uint2*>(qrow + h * D + lane * 4);
     qv[0] = bf16_lo(u.x) * scale_log2; qv[1] = bf16_hi(u.x) * scale_log2;
     qv[2] = bf16_lo(u.y) * scale_log2; qv[3] = bf16_hi(u.y) * scale_log2;
   }
   float m = -INFINITY, l = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int j = warp; j < n; j += kDecWarps) {
-    const uint2 ku = *reinterpret_cast<const uint2*>(kbase + j * ldkv);
+  for (int j = warp; j <= n; j += kDecWarps) {
+    const uint2 ku = j < n ? *reinterpret_cast<const uint2*>(kbase + j * ldkv) : knew;
+    const uint2 vu = j < n ? *reinterpret_cast<const uint2*>(vbase + j * ldkv) : vnew;
     float s = qv[0] * bf16_lo(ku.x) + qv[1] * bf16_hi(ku.x) + qv[2] * bf16_lo(ku.y) + qv[3] * bf16_hi(ku.y);
     s = warp_sum(s);
     const float mn = fmaxf(m, s);
     const float corr = exp2f(m - mn), p = exp2f(s - mn);
-    const uint2 vu = *reinterpret_cast<const uint2*>(vbase + j * ldkv);
     l = l * corr + p;
     acc[0] = acc[0] * corr + p * bf16_lo(vu.x);
     acc[1] = acc[1] * corr + p * bf16_hi(vu.x);
@@ -96,6 +109,201 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __n
     u.y = pack_bf16(out[2] * inv, out[3] * inv);
     *reinterpret_cast<uint2*>(o + static_cast<long long>(b) * Hq * D + h * D + lane * 4) = u;
   }
+}
+
+// ---- weight-streaming GEMV for decode batches of <= 4 rows -------------------------------------------------------
+// out[b, n] = epi( sum_k x[b, k] * W[n, k] ): every weight element is read exactly once with 16-byte loads (the step is
+// HBM-bound: 2 bytes of weight per B FMAs), the <= 4 activation rows live in shared memory, one warp owns one output
+// column -- or, for the paired epilogues, the two columns a SwiGLU / rotate-half pair needs (n and n + 64 of a
+// 128-row block), so the epilogue needs no second pass. No split-K: each output element has one owner, the fp32
+// residual add is a plain read-modify-write.
+enum GemvEpi : int { GV_BF16 = 0, GV_ACCUM_F32 = 1, GV_SWIGLU = 2, GV_ROPE = 3 };
+constexpr int kGvWarps = 8;
+
+__device__ __forceinline__ float dot8(const uint4& w, const uint4& x) {
+  float s = bf16_lo(w.x) * bf16_lo(x.x);
+  s = fmaf(bf16_hi(w.x), bf16_hi(x.x), s);
+  s = fmaf(bf16_lo(w.y), bf16_lo(x.y), s);
+  s = fmaf(bf16_hi(w.y), bf16_hi(x.y), s);
+  s = fmaf(bf16_lo(w.z), bf16_lo(x.z), s);
+  s = fmaf(bf16_hi(w.z), bf16_hi(x.z), s);
+  s = fmaf(bf16_lo(w.w), bf16_lo(x.w), s);
+  s = fmaf(bf16_hi(w.w), bf16_hi(x.w), s);
+  return s;
+}
+
+template <int NB, bool PAIRED>
+__global__ void __launch_bounds__(kGvWarps * 32, 2)
+gemv_bf16_kernel(const void* __restrict__ x, const float* __restrict__ norm_w, float norm_eps,
+                 const __nv_bfloat16* __restrict__ W, int B, int N, int K, int epi, void* out, long long ldo,
+                 const float* __restrict__ rope_cs, const int* __restrict__ positions, int rope_cols) {
+  extern __shared__ uint4 sx[];  // [NB][K / 8] bf16 activations
+  __shared__ float s_part[NB][kGvWarps];
+  pdl_launch_dependents();  // the next kernel may start prefetching ITS weights while this one runs
+  const int k8 = K / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int units = PAIRED ? N / 2 : N;
+  int u = blockIdx.x * kGvWarps + warp;
+  // weights do not depend on the previous kernel: get the first chunks in flight before waiting for it
+  constexpr int kPre = 4;
+  uint4 pre0[kPre], pre1[kPre];
+  {
+    const int n0 = u < units ? (PAIRED ? (u >> 6) * 128 + (u & 63) : u) : 0;
+    const uint4* w0 = reinterpret_cast<const uint4*>(W + static_cast<long long>(n0) * K);
+#pragma unroll
+    for (int i = 0; i < kPre; ++i) {
+      const int c = lane + 32 * i;
+      pre0[i] = (u < units && c < k8) ? ld_stream_u4(w0 + c) : make_uint4(0u, 0u, 0u, 0u);
+      pre1[i] = (PAIRED && u < units && c < k8) ? ld_stream_u4(w0 + 64 * k8 + c) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  pdl_wait();
+  if (norm_w == nullptr) {  // x: bf16 [B, K]
+    for (int i = threadIdx.x; i < NB * k8; i += blockDim.x) {
+      const int b = i / k8;
+      sx[i] = b < B ? reinterpret_cast<const uint4*>(x)[static_cast<long long>(b) * k8 + (i - b * k8)]
+                    : make_uint4(0u, 0u, 0u, 0u);
+    }
+  } else {  // x: fp32 residual stream [B, K]; stage RMSNorm(x) * w rounded to bf16 (LlamaRMSNorm)
+    const float* xf = reinterpret_cast<const float*>(x);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float q = 0.f;
+      if (b < B)
+        for (int c = threadIdx.x; c < k8; c += blockDim.x) {
+          float v[8];
+          ld8f(xf + static_cast<long long>(b) * K + c * 8, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) q = fmaf(v[j], v[j], q);
+        }
+      q = warp_sum(q);
+      if (lane == 0) s_part[b][warp] = q;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float q = 0.f;
+#pragma unroll
+      for (int w = 0; w < kGvWarps; ++w) q += s_part[b][w];
+      const float rstd = rsqrtf(q / static_cast<float>(K) + norm_eps);
+      for (int c = threadIdx.x; c < k8; c += blockDim.x) {
+        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+        if (b < B) {
+          float v[8], wt[8];
+          ld8f(xf + static_cast<long long>(b) * K + c * 8, v);
+          ld8f(norm_w + c * 8, wt);
+          pk.x = pack_bf16(wt[0] * (v[0] * rstd), wt[1] * (v[1] * rstd));
+          pk.y = pack_bf16(wt[2] * (v[2] * rstd), wt[3] * (v[3] * rstd));
+          pk.z = pack_bf16(wt[4] * (v[4] * rstd), wt[5] * (v[5] * rstd));
+          pk.w = pack_bf16(wt[6] * (v[6] * rstd), wt[7] * (v[7] * rstd));
+        }
+        sx[b * k8 + c] = pk;
+      }
+    }
+  }
+  __syncthreads();
+  bool first = true;
+  for (; u < units; u += gridDim.x * kGvWarps, first = false) {
+    const int n0 = PAIRED ? (u >> 6) * 128 + (u & 63) : u;
+    const uint4* w0 = reinterpret_cast<const uint4*>(W + static_cast<long long>(n0) * K);
+    const uint4* w1 = w0 + 64 * k8;  // row n0 + 64
+    float a0[NB], a1[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) a0[b] = a1[b] = 0.f;
+    int c = lane;
+    if (first) {  // consume the prefetched chunks
+#pragma unroll
+      for (int i = 0; i < kPre; ++i, c += 32) {
+        if (c < k8) {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const uint4 xv = sx[b * k8 + c];
+            a0[b] += dot8(pre0[i], xv);
+            if (PAIRED) a1[b] += dot8(pre1[i], xv);
+          }
+        }
+      }
+    }
+#pragma unroll 4
+    for (; c < k8; c += 32) {
+      const uint4 wv0 = ld_stream_u4(w0 + c);
+      uint4 wv1 = make_uint4(0u, 0u, 0u, 0u);
+      if (PAIRED) wv1 = ld_stream_u4(w1 + c);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const uint4 xv = sx[b * k8 + c];
+        a0[b] += dot8(wv0, xv);
+        if (PAIRED) a1[b] += dot8(wv1, xv);
+      }
+    }
+    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const float s0 = warp_sum(a0[b]);
+      const float s1 = PAIRED ? warp_sum(a1[b]) : 0.f;
+      if (lane == b) {
+        v0 = s0;
+        v1 = s1;
+      }
+    }
+    if (lane < B) {
+      const long long row = static_cast<long long>(lane) * ldo;
+      if (epi == GV_BF16) {
+        reinterpret_cast<__nv_bfloat16*>(out)[row + n0] = __float2bfloat16(v0);
+      } else if (epi == GV_ACCUM_F32) {
+        reinterpret_cast<float*>(out)[row + n0] += v0;
+      } else if (epi == GV_SWIGLU) {
+        reinterpret_cast<__nv_bfloat16*>(out)[row + (u >> 6) * 64 + (u & 63)] = __float2bfloat16(silu(v0) * v1);
+      } else {  // GV_ROPE: rotate-half pair (d, d + 64) of a 128-wide head
+        float lo = v0, hi = v1;
+        if (n0 < rope_cols) {
+          const float* cs = rope_cs + static_cast<long long>(positions[lane]) * 128 + (u & 63);
+          const float cc = cs[0], sn = cs[64];
+          lo = v0 * cc - v1 * sn;
+          hi = v1 * cc + v0 * sn;
+        }
+        reinterpret_cast<__nv_bfloat16*>(out)[row + n0] = __float2bfloat16(lo);
+        reinterpret_cast<__nv_bfloat16*>(out)[row + n0 + 64] = __float2bfloat16(hi);
+      }
+    }
+  }
+}
+
+// launch with programmatic dependent launch: the kernel's prologue (weight prefetch) overlaps its predecessor's tail
+template <typename Kern, typename... Args>
+int launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B2S_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, args...));
+  count_launch();
+  return B2S_OK;
+}
+
+template <int NB, bool PAIRED>
+int launch_gemv(const void* x, const float* norm_w, float norm_eps, const void* W, int B, int N, int K, int epi,
+                void* out, long long ldo, const float* rope_cs, const int* positions, int rope_cols,
+                cudaStream_t stream) {
+  auto kern = gemv_bf16_kernel<NB, PAIRED>;
+  const int smem = NB * K * 2;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    B2S_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  const int units = PAIRED ? N / 2 : N;
+  int blocks = (units + kGvWarps - 1) / kGvWarps;
+  const int cap = 4 * num_sms();
+  if (blocks > cap) blocks = cap;
+  return launch_pdl(kern, dim3(blocks), dim3(kGvWarps * 32), static_cast<size_t>(smem), stream, x, norm_w, norm_eps,
+                    reinterpret_cast<const __nv_bfloat16*>(W), B, N, K, epi, out, ldo, rope_cs, positions, rope_cols);
 }
 
 struct Carve {
@@ -153,6 +361,26 @@ GemmArgs lin(const void* A, const void* W, long long M, int N, int K) {
 
 }  // namespace
 
+// x: bf16 [B <= 4, K] (norm_w == nullptr) or the fp32 residual stream [B, K] with RMSNorm(norm_w, eps) fused into the
+// staging; W bf16 [N, K]; see GemvEpi
+int gemv_bf16(const void* x, const float* norm_w, float norm_eps, const void* W, int B, int N, int K, int epi, void* out,
+              long long ldo, const float* rope_cs, const int* positions, int rope_cols, cudaStream_t stream) {
+  B2S_REQUIRE(x && W && out && B >= 1 && B <= 4, "gemv: needs 1..4 rows");
+  B2S_REQUIRE(K % 8 == 0 && K * 2 * 4 <= 200 * 1024, "gemv: K must be a multiple of 8 and fit shared memory");
+  const bool paired = epi == GV_SWIGLU || epi == GV_ROPE;
+  if (paired) B2S_REQUIRE(N % 128 == 0, "gemv: paired epilogues need N %% 128 == 0");
+  if (epi == GV_ROPE) B2S_REQUIRE(rope_cs && positions, "gemv: rope epilogue needs tables");
+#define B2S_GEMV(NB)                                                                                                   \
+  return paired ? launch_gemv<NB, true>(x, norm_w, norm_eps, W, B, N, K, epi, out, ldo, rope_cs, positions, rope_cols, \
+                                        stream)                                                                        \
+                : launch_gemv<NB, false>(x, norm_w, norm_eps, W, B, N, K, epi, out, ldo, rope_cs, positions, rope_cols, \
+                                         stream)
+  if (B == 1) { B2S_GEMV(1); }
+  if (B == 2) { B2S_GEMV(2); }
+  B2S_GEMV(4);
+#undef B2S_GEMV
+}
+
 size_t llama_kv_cache_bytes(const b2s_llama_weights* w, int slots) {
   if (w == nullptr || slots <= 0) return 0;
   return static_cast<size_t>(w->num_layers) * slots * 2 * w->kv_heads * w->head_dim * 2;
@@ -194,9 +422,21 @@ int llama_decode_step(const b2s_llama_weights* w, const void* embed_table, const
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(D));
 
   RC(embed_splice_fwd(embed_table, nullptr, token_ids, p.h, B, H, stream));
+  const bool gv = B <= 4;  // weight-streaming GEMV path (RMSNorm fused into its staging, PDL-chained launches)
   for (int l = 0; l < w->num_layers; ++l) {
     const b2s_llama_layer& L = w->layers[l];
     __nv_bfloat16* cache = reinterpret_cast<__nv_bfloat16*>(kv_cache) + static_cast<size_t>(l) * kv_slots * width;
+    if (gv) {
+      RC(gemv_bf16(p.h, L.ln1_w, w->rms_eps, L.wqkv, B, qkv_cols, H, GV_ROPE, p.qkv, qkv_cols, w->rope_cs, seq_len,
+                   (Hq + Hkv) * D, stream));
+      RC(launch_pdl(decode_attn_kernel, dim3(B, Hq), dim3(kDecWarps * 32), 0, stream,
+                    reinterpret_cast<const __nv_bfloat16*>(p.qkv), static_cast<long long>(qkv_cols), cache, seq_start,
+                    seq_len, reinterpret_cast<__nv_bfloat16*>(p.ao), Hq, Hkv, scale_log2));
+      RC(gemv_bf16(p.ao, nullptr, 0.f, L.wo, B, H, Hq * D, GV_ACCUM_F32, p.h, H, nullptr, nullptr, 0, stream));
+      RC(gemv_bf16(p.h, L.ln2_w, w->rms_eps, L.wgu, B, 2 * F, H, GV_SWIGLU, p.act, F, nullptr, nullptr, 0, stream));
+      RC(gemv_bf16(p.act, nullptr, 0.f, L.wd, B, H, F, GV_ACCUM_F32, p.h, H, nullptr, nullptr, 0, stream));
+      continue;
+    }
     RC(rmsnorm_fwd(p.h, L.ln1_w, w->rms_eps, p.xn, B, H, stream));
     {
       GemmArgs g = lin(p.xn, L.wqkv, B, qkv_cols, H);
@@ -209,16 +449,10 @@ int llama_decode_step(const b2s_llama_weights* w, const void* embed_table, const
       g.cta_group = 1;
       RC(gemm_bf16_launch(g, stream));
     }
-    {
-      const long long n = static_cast<long long>(B) * (width / 8);
-      kv_scatter_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-          reinterpret_cast<const __nv_bfloat16*>(p.qkv), qkv_cols, Hq * D, width, cache, nullptr, seq_start, seq_len, B);
-      B2S_LAUNCH_CHECK();
-      decode_attn_kernel<<<dim3(B, Hq), kDecWarps * 32, 0, stream>>>(
-          reinterpret_cast<const __nv_bfloat16*>(p.qkv), qkv_cols, cache, seq_start, seq_len,
-          reinterpret_cast<__nv_bfloat16*>(p.ao), Hq, Hkv, scale_log2);
-      B2S_LAUNCH_CHECK();
-    }
+    decode_attn_kernel<<<dim3(B, Hq), kDecWarps * 32, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(p.qkv), qkv_cols, cache, seq_start, seq_len,
+        reinterpret_cast<__nv_bfloat16*>(p.ao), Hq, Hkv, scale_log2);
+    B2S_LAUNCH_CHECK();
     {
       GemmArgs g = lin(p.ao, L.wo, B, H, Hq * D);
       g.epi = EPI_ACCUM_F32;  // h += ao . Wo^T, split-K over the whole chip
@@ -244,8 +478,11 @@ int llama_decode_step(const b2s_llama_weights* w, const void* embed_table, const
       RC(gemm_bf16_launch(g, stream));
     }
   }
-  RC(rmsnorm_fwd(p.h, w->final_norm_w, w->rms_eps, p.xn, B, H, stream));
-  {
+  if (gv) {
+    RC(gemv_bf16(p.h, w->final_norm_w, w->rms_eps, w->lm_head, B, w->vocab, H, GV_BF16, logits_bf16, w->vocab, nullptr,
+                 nullptr, 0, stream));
+  } else {
+    RC(rmsnorm_fwd(p.h, w->final_norm_w, w->rms_eps, p.xn, B, H, stream));
     GemmArgs g = lin(p.xn, w->lm_head, B, w->vocab, H);
     g.epi = EPI_BF16;
     g.out = logits_bf16;

@@ -431,23 +431,43 @@ class AudioLlamaForCausalLM(nn.Module):
         return logits, state
 
     @torch.no_grad()
-    def decode_step(self, token_ids: torch.Tensor, state) -> torch.Tensor:
-        """Append one token per sequence (int32 [B], device) and return the next-token logits bf16 [B, V]."""
+    def decode_step(self, token_ids: torch.Tensor, state, use_graph: bool = True) -> torch.Tensor:
+        """Append one token per sequence (int [B], device) and return the next-token logits bf16 [B, V] (a buffer
+        owned by `state`, overwritten by the next call). A step is ~230 short launches, so after one eager call the
+        whole step (kernels + the seq_len increment) is captured into a CUDA graph and replayed: every buffer the
+        kernels touch is persistent in `state`, positions / cache lengths are read from device memory."""
         w = self.packed()[0]
         lib = _lib.load()
         B = state["B"]
         if max(l + 1 for l in state["lens"]) > max(state["cap"]):
             raise RuntimeError("KV cache is full")
-        tok = token_ids.to(device=self.device, dtype=torch.int32).contiguous()
-        logits = torch.empty(B, self.arch.vocab, device=self.device, dtype=torch.bfloat16)
-        _lib.check(lib.b2s_llama_decode_step(C.byref(w), self.model.embed_tokens.weight.data_ptr(), tok.data_ptr(), B,
-                                             state["cache"].data_ptr(), state["slots"], state["seq_start"].data_ptr(),
-                                             state["seq_len"].data_ptr(), logits.data_ptr(), state["ws"].data_ptr(),
-                                             state["ws"].numel(), torch.cuda.current_stream().cuda_stream),
-                   "llama_decode_step")
-        state["seq_len"] += 1
+        if "tok" not in state:
+            state["tok"] = torch.zeros(B, device=self.device, dtype=torch.int32)
+            state["logits"] = torch.empty(B, self.arch.vocab, device=self.device, dtype=torch.bfloat16)
+            state["calls"], state["graph"] = 0, None
+        state["tok"].copy_(token_ids.to(device=self.device, dtype=torch.int32).reshape(B))
+
+        def run():
+            _lib.check(lib.b2s_llama_decode_step(
+                C.byref(w), self.model.embed_tokens.weight.data_ptr(), state["tok"].data_ptr(), B,
+                state["cache"].data_ptr(), state["slots"], state["seq_start"].data_ptr(), state["seq_len"].data_ptr(),
+                state["logits"].data_ptr(), state["ws"].data_ptr(), state["ws"].numel(),
+                torch.cuda.current_stream().cuda_stream), "llama_decode_step")
+            state["seq_len"].add_(1)
+
+        if state["graph"] is not None:
+            state["graph"].replay()
+        elif use_graph and state["calls"] >= 1:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                run()
+            state["graph"] = graph
+            graph.replay()
+        else:
+            run()
+        state["calls"] += 1
         state["lens"] = [l + 1 for l in state["lens"]]
-        return logits
+        return state["logits"]
 
     @torch.no_grad()
     def generate(self, input_ids=None, inputs_embeds=None, max_new_tokens: int = 256, use_kv_cache: bool = True,

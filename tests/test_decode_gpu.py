@@ -20,19 +20,20 @@ def _setup(cuda, llm_name="llama"):
     return configs, llm_cfg, llm_sd, llm
 
 
+@pytest.mark.parametrize("lens", [[11, 5], [7], [7, 9, 4, 6, 5]], ids=["b2_gemv", "b1_gemv", "b5_gemm"])
 @pytest.mark.parametrize("llm_name", ["llama", "minichat"])
-def test_decode_steps_match_full_prefill_and_oracle(cuda, llm_name):
+def test_decode_steps_match_full_prefill_and_oracle(cuda, llm_name, lens):
     from oracle import reference_math as rm
     configs, llm_cfg, llm_sd, llm = _setup(cuda, llm_name)
     g = torch.Generator().manual_seed(7)
-    lens = [11, 5]
+    nb = len(lens)
     prompts = [(torch.randn(L, llm_cfg.hidden, generator=g) * 0.05).to(torch.bfloat16).float() for L in lens]
-    new_tokens = torch.randint(0, llm_cfg.vocab - 256, (2, 6), generator=g)
+    new_tokens = torch.randint(0, llm_cfg.vocab - 256, (nb, 4), generator=g)
     logits, state = llm.prefill_with_cache([p.to(cuda) for p in prompts], max_new_tokens=8)
     table = llm_sd["model.embed_tokens.weight"]
     seqs = [p.clone() for p in prompts]
     for step in range(new_tokens.shape[1] + 1):
-        for b in range(2):
+        for b in range(nb):
             full = llm(inputs_embeds=seqs[b][None].to(cuda).to(torch.bfloat16), num_logits_to_keep=1).logits[0, -1]
             assert rel_l2(logits[b].float(), full.float()) < 1e-2, (step, b)
             _, ref, _ = rm.audio_llama_forward(llm_sd, seqs[b][None].to(torch.bfloat16).float(), None, None, llm_cfg,
@@ -41,8 +42,8 @@ def test_decode_steps_match_full_prefill_and_oracle(cuda, llm_name):
         if step == new_tokens.shape[1]:
             break
         tok = new_tokens[:, step]
-        logits = llm.decode_step(tok.to(cuda), state)
-        for b in range(2):
+        logits = llm.decode_step(tok.to(cuda), state)  # step 0 eager, step 1 captures a CUDA graph, then replays
+        for b in range(nb):
             seqs[b] = torch.cat([seqs[b], table[tok[b]][None].float()], dim=0)
 
 
