@@ -87,10 +87,14 @@ struct TileCoord {
   int b, g, m_t, n_t, split;
 };
 
+template <bool EXT>
 __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
   constexpr int kGroupM = 8;
-  const int split = t / p.tiles_per_split;
-  t -= split * p.tiles_per_split;
+  int split = 0;
+  if constexpr (EXT) {
+    split = t / p.tiles_per_split;
+    t -= split * p.tiles_per_split;
+  }
   const int per_bg = p.m_tiles * p.n_tiles;
   const int bg = t / per_bg;
   const int r = t - bg * per_bg;
@@ -218,12 +222,20 @@ __device__ __forceinline__ void emit_bf16(uint32_t stg, const float (&v)[32], in
   __syncwarp();
 }
 
-template <int BN, int CG>
+// MODE 0: the forward instantiation (K-major operands, no split-K, no second output) -- the hot loops carry nothing
+//         they do not need.
+// MODE 1: K-major operands + split-K, the accumulate epilogue, per-group output offsets and the pre-activation copy
+//         (training forward, decode).
+// MODE 2: MODE 1 with an MN-major B operand (dgrad).   MODE 3: both operands MN-major, reduction over batches (wgrad).
+// Operand major-ness is a compile-time property so the single-thread producer / MMA-issue loops stay branch-free.
+template <int BN, int CG, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                          const KParams p) {
   using C = Cfg<BN, CG>;
   constexpr int kStages = C::kStages;
+  constexpr bool EXT = MODE >= 1;
+  constexpr bool kAmn = MODE == 3, kBmn = MODE >= 2;
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
@@ -277,12 +289,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int stage = 0;
     uint32_t phase = 0;
     for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
-      const TileCoord tc = decode_tile(p, t);
+      const TileCoord tc = decode_tile<EXT>(p, t);
       const int m0 = tc.m_t * (128 * CG) + static_cast<int>(cta_rank) * 128;
       const int n0 = tc.g * p.w_group_off + tc.n_t * BN + static_cast<int>(cta_rank) * C::kBRows;
       const int a_c0_base = tc.g * p.a_group_off;
-      const int kb_lo = tc.split * p.kb_per_split;
-      const int kb_hi = min(p.num_kb, kb_lo + p.kb_per_split);
+      const int kb_lo = EXT ? tc.split * p.kb_per_split : 0;
+      const int kb_hi = EXT ? min(p.num_kb, kb_lo + p.kb_per_split) : p.num_kb;
       for (int kb = kb_lo; kb < kb_hi; ++kb) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * C::kStageBytes;
@@ -294,7 +306,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         } else {
           ptx::mbar_arrive_cluster(full_bar(stage), 0);
         }
-        if ((p.a_mn | p.b_mn) == 0) {
+        if constexpr (!kBmn) {
           const int tap = kb / p.kb_per_tap;
           const int kk = (kb - tap * p.kb_per_tap) * kBlockK;
           if (CG == 1) {
@@ -309,7 +321,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           // set of [64 k-rows x 64 columns] boxes, one per 64-wide M / N atom, 8 KiB apart.
           const int kbat = kb / p.kb_per_batch;
           const int kk = (kb - kbat * p.kb_per_batch) * kBlockK;
-          if (p.a_mn) {
+          if constexpr (kAmn) {
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
               if (CG == 1) ptx::tma_load_3d(&tmap_a, full_bar(stage), sa + a * 8192, a_c0_base + m0 + a * 64, kk, kbat);
@@ -341,11 +353,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp == 1 && lane == 0 && cta_rank == 0) {
     // ============================== MMA issuer ==============================
-    const uint32_t idesc = ptx::make_idesc_bf16_f32(128 * CG, BN) | (p.a_mn ? (1u << 15) : 0u) |
-                           (p.b_mn ? (1u << 16) : 0u);
+    constexpr bool a_mn = kAmn, b_mn = kBmn;
+    constexpr uint32_t idesc =
+        ptx::make_idesc_bf16_f32(128 * CG, BN) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
     // K step of 16 inside a stage: K-major = 32 bytes along the swizzled row; MN-major = 16 rows of 128 bytes
-    const uint32_t a_kstep = p.a_mn ? (2048u >> 4) : 2u;
-    const uint32_t b_kstep = p.b_mn ? (2048u >> 4) : 2u;
+    constexpr uint32_t a_kstep = a_mn ? (2048u >> 4) : 2u;
+    constexpr uint32_t b_kstep = b_mn ? (2048u >> 4) : 2u;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -355,16 +368,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
-      const int split = t / p.tiles_per_split;
-      const int kb_lo = split * p.kb_per_split;
-      const int kb_hi = min(p.num_kb, kb_lo + p.kb_per_split);
+      const int kb_lo = EXT ? (t / p.tiles_per_split) * p.kb_per_split : 0;
+      const int kb_hi = EXT ? min(p.num_kb, kb_lo + p.kb_per_split) : p.num_kb;
       for (int kb = kb_lo; kb < kb_hi; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
         const uint32_t sa = smem_base + stage * C::kStageBytes;
-        const uint64_t adesc = p.a_mn ? ptx::make_mnmajor_sw128_desc(sa, 8192) : ptx::make_kmajor_sw128_desc(sa);
-        const uint64_t bdesc = p.b_mn ? ptx::make_mnmajor_sw128_desc(sa + kATileBytes, 8192)
-                                      : ptx::make_kmajor_sw128_desc(sa + kATileBytes);
+        const uint64_t adesc = a_mn ? ptx::make_mnmajor_sw128_desc(sa, 8192) : ptx::make_kmajor_sw128_desc(sa);
+        const uint64_t bdesc = b_mn ? ptx::make_mnmajor_sw128_desc(sa + kATileBytes, 8192)
+                                    : ptx::make_kmajor_sw128_desc(sa + kATileBytes);
 #pragma unroll
         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
           ptx::umma_bf16<CG>(tmem_d, adesc + a_kstep * k, bdesc + b_kstep * k, idesc,
@@ -389,14 +401,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const uint32_t stg = stage_base + static_cast<uint32_t>(quarter) * 4096u;
     int it = 0;
     for (int t = cluster_id; t < p.total_tiles; t += num_clusters, ++it) {
-      const TileCoord tc = decode_tile(p, t);
+      const TileCoord tc = decode_tile<EXT>(p, t);
+      const int og_cols = EXT ? p.og_cols : p.N;
+      void* const out2 = EXT ? p.out2 : nullptr;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m0w = tc.m_t * (128 * CG) + static_cast<int>(cta_rank) * 128 + quarter * 32;  // warp's first row
       const int rows_valid = max(0, min(32, p.M - m0w));
       const bool row_ok = lane < rows_valid;
       const long long orow0 = static_cast<long long>(tc.b) * p.out_batch_rows +
-                              static_cast<long long>(tc.g) * p.og_rows + m0w;
+                              (EXT ? static_cast<long long>(tc.g) * p.og_rows : 0LL) + m0w;
       const int ncol0 = tc.n_t * BN;  // column inside the group
       const float* bias = p.bias ? p.bias + static_cast<long long>(tc.g) * p.N : nullptr;
 
@@ -404,7 +418,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + lane_base + as * BN;
 
-      if (p.epi == EPI_BF16 || p.epi == EPI_F32 || p.epi == EPI_RESID_F32 || p.epi == EPI_ACCUM_F32) {
+      if (p.epi == EPI_BF16 || p.epi == EPI_F32 || p.epi == EPI_RESID_F32 || (EXT && p.epi == EPI_ACCUM_F32)) {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           const int col = ncol0 + c * 32;
@@ -416,24 +430,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
           const int valid = min(32, p.N - col);
-          if (p.out2 != nullptr) {  // training: keep the pre-activation (acc + bias) for the backward
+          if (EXT && out2 != nullptr) {  // training: keep the pre-activation (acc + bias) for the backward
             add_bias_act(v, bias ? bias + col : nullptr, ACT_NONE);
             emit_bf16(stg, v, lane,
-                      reinterpret_cast<__nv_bfloat16*>(p.out2) + orow0 * p.ld2 + static_cast<long long>(tc.g) * p.og_cols + col,
+                      reinterpret_cast<__nv_bfloat16*>(out2) + orow0 * p.ld2 + static_cast<long long>(tc.g) * og_cols + col,
                       p.ld2, rows_valid, valid);
             add_bias_act(v, nullptr, p.act);
           } else {
             add_bias_act(v, bias ? bias + col : nullptr, p.act);
           }
-          const long long off0 = orow0 * p.ldo + static_cast<long long>(tc.g) * p.og_cols + col;
+          const long long off0 = orow0 * p.ldo + static_cast<long long>(tc.g) * og_cols + col;
           if (p.epi == EPI_BF16) {
             emit_bf16(stg, v, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, valid);
-          } else if (p.epi == EPI_ACCUM_F32) {
+          } else if (EXT && p.epi == EPI_ACCUM_F32) {
             emit_accum_f32(stg, v, lane, reinterpret_cast<float*>(p.out) + off0, p.ldo, rows_valid, valid);
           } else {
             // resid_bcast: the residual is indexed by the row inside the batch only (e.g. a positional table)
             const long long roff0 = p.resid_bcast
-                                        ? static_cast<long long>(m0w) * p.ldo + static_cast<long long>(tc.g) * p.og_cols + col
+                                        ? static_cast<long long>(m0w) * p.ldo + static_cast<long long>(tc.g) * og_cols + col
                                         : off0;
             emit_f32(stg, v, lane, reinterpret_cast<float*>(p.out) + off0,
                      p.epi == EPI_RESID_F32 ? p.resid + roff0 : nullptr, p.ldo, rows_valid, valid);
@@ -463,8 +477,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             add_bias_act(lo, bias ? bias + bcol + c * 32 : nullptr, ACT_NONE);
             add_bias_act(hi, bias ? bias + bcol + (c + 2) * 32 : nullptr, ACT_NONE);
             if (p.epi == EPI_SWIGLU) {
-              if (p.out2 != nullptr) {  // training: raw gate | up (the GEMM's natural [M, N] layout)
-                __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(p.out2) + orow0 * p.ld2 +
+              if (EXT && out2 != nullptr) {  // training: raw gate | up (the GEMM's natural [M, N] layout)
+                __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(out2) + orow0 * p.ld2 +
                                      static_cast<long long>(tc.g) * p.N + bcol + c * 32;
                 emit_bf16(stg, lo, lane, raw, p.ld2, rows_valid, 32);
                 emit_bf16(stg, hi, lane, raw + 64, p.ld2, rows_valid, 32);
@@ -562,10 +576,10 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
   return B2S_OK;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, int MODE>
 int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const KParams& p, cudaStream_t stream) {
   using C = Cfg<BN, CG>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, CG>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, CG, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     B2S_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -652,6 +666,7 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
     B2S_REQUIRE(a.taps == 1 && (a.epi == EPI_BF16 || a.epi == EPI_F32 || a.epi == EPI_ACCUM_F32 || a.epi == EPI_RESID_F32),
                 "gemm: MN-major operands support plain epilogues and taps == 1 only");
     B2S_REQUIRE(!a.a_mn || a.batches == 1, "gemm: MN-major A reduces over k_batches; tile batches must be 1");
+    B2S_REQUIRE(!a.a_mn || a.b_mn, "gemm: MN-major A needs MN-major W");
     B2S_REQUIRE(a.a_mn || a.k_batches <= 1, "gemm: k_batches needs MN-major A");
   } else {
     B2S_REQUIRE(a.k_batches <= 1 && !a.b_tap_atoms, "gemm: k_batches / b_tap_atoms need MN-major operands");
@@ -778,11 +793,24 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
     if (rc != B2S_OK) return rc;
   }
 
-  if (bn == 256 && cg == 1) return launch_cfg<256, 1>(ta, tw, p, stream);
-  if (bn == 128 && cg == 1) return launch_cfg<128, 1>(ta, tw, p, stream);
-  if (bn == 64 && cg == 1) return launch_cfg<64, 1>(ta, tw, p, stream);
-  if (bn == 256 && cg == 2) return launch_cfg<256, 2>(ta, tw, p, stream);
-  if (bn == 128 && cg == 2) return launch_cfg<128, 2>(ta, tw, p, stream);
+  const bool ext = mn || a.epi == EPI_ACCUM_F32 || p.k_splits > 1 || a.out2 != nullptr || a.out_group_rows != 0 ||
+                   (a.out_group_cols > 0 && a.out_group_cols != a.N);
+  const int mode = a.a_mn ? 3 : (a.b_mn ? 2 : (ext ? 1 : 0));
+#define B2S_GEMM_CASE(BN_, CG_)                                          \
+  if (bn == BN_ && cg == CG_) {                                          \
+    switch (mode) {                                                      \
+      case 0: return launch_cfg<BN_, CG_, 0>(ta, tw, p, stream);         \
+      case 1: return launch_cfg<BN_, CG_, 1>(ta, tw, p, stream);         \
+      case 2: return launch_cfg<BN_, CG_, 2>(ta, tw, p, stream);         \
+      default: return launch_cfg<BN_, CG_, 3>(ta, tw, p, stream);        \
+    }                                                                    \
+  }
+  B2S_GEMM_CASE(256, 1);
+  B2S_GEMM_CASE(128, 1);
+  B2S_GEMM_CASE(64, 1);
+  B2S_GEMM_CASE(256, 2);
+  B2S_GEMM_CASE(128, 2);
+#undef B2S_GEMM_CASE
   set_last_error("gemm: unsupported (block_n=%d, cta_group=%d)", bn, cg);
   return B2S_ERR_UNSUPPORTED;
 }
