@@ -368,23 +368,30 @@ attn_bwd_dkv_kernel(const BwdParams p) {
   store_frag_rows<D>(dv, p.dv + static_cast<long long>(s0 + k0) * p.ld_dqkv + hk * D, p.ld_dqkv, warp * 16, krows, g, t);
 }
 
-// delta[row, h] = sum_d dO[row, h, d] * O[row, h, d]; one warp per (row, head)
+// delta[row, h] = sum_d dO[row, h, d] * O[row, h, d]; one warp per row, 16-byte loads, lanes of one head reduce together
+template <int D>
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, long long ld_o,
-                  long long ld_do, float* __restrict__ delta, long long rows, int Hq, int D) {
-  const long long idx = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (idx >= rows * Hq) return;
-  const long long row = idx / Hq;
-  const int h = static_cast<int>(idx - row * Hq);
+                  long long ld_do, float* __restrict__ delta, long long rows, int Hq) {
+  constexpr int kLanesPerHead = D / 8;            // 8 (D = 64) or 16 (D = 128)
+  constexpr int kHeadsPerIter = 32 / kLanesPerHead;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  float s = 0.f;
-  for (int d = lane * 2; d < D; d += 64) {
-    const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(o + row * ld_o + h * D + d));
-    const float2 b = unpack_bf16(*reinterpret_cast<const uint32_t*>(dout + row * ld_do + h * D + d));
-    s += a.x * b.x + a.y * b.y;
+  for (int h0 = 0; h0 < Hq; h0 += kHeadsPerIter) {
+    const int h = h0 + lane / kLanesPerHead;
+    float s = 0.f;
+    if (h < Hq) {
+      float a[8], b[8];
+      ld8bf(o + row * ld_o + h0 * D + lane * 8, a);
+      ld8bf(dout + row * ld_do + h0 * D + lane * 8, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(a[i], b[i], s);
+    }
+#pragma unroll
+    for (int off = kLanesPerHead / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (h < Hq && lane % kLanesPerHead == 0) delta[row * Hq + h] = s;
   }
-  s = warp_sum(s);
-  if (lane == 0) delta[idx] = s;
 }
 
 template <int D>
@@ -416,12 +423,19 @@ int attention_bwd(const void* q, const void* k, const void* v, long long ld_qkv,
               "attention_bwd: bad sizes");
   B2S_REQUIRE(ld_qkv % 8 == 0 && ld_do % 8 == 0 && ld_o % 2 == 0 && ld_dqkv % 2 == 0,
               "attention_bwd: strides must keep 16-byte row alignment");
+  B2S_REQUIRE(D == 64 || D == 128, "attention_bwd: head_dim %d unsupported (64 or 128)", D);
+  B2S_REQUIRE(ld_o % 8 == 0, "attention_bwd: the forward output needs 16-byte aligned rows");
   {
-    const long long n = total_rows * Hq;
-    attn_delta_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(dout), ld_o, ld_do, delta_ws,
-        total_rows, Hq, D);
+    const unsigned grid = static_cast<unsigned>((total_rows + 7) / 8);
+    const __nv_bfloat16* ob = reinterpret_cast<const __nv_bfloat16*>(o);
+    const __nv_bfloat16* dob = reinterpret_cast<const __nv_bfloat16*>(dout);
+    if (D == 64) attn_delta_kernel<64><<<grid, 256, 0, stream>>>(ob, dob, ld_o, ld_do, delta_ws, total_rows, Hq);
+    else attn_delta_kernel<128><<<grid, 256, 0, stream>>>(ob, dob, ld_o, ld_do, delta_ws, total_rows, Hq);
     B2S_LAUNCH_CHECK();
+  }
+  if (attention_get_impl() == 1) {  // tcgen05 kernels (attention_bwd_tc.cu); 0 keeps the mma.sync kernels below
+    return attention_bwd_tc(q, k, v, ld_qkv, dout, ld_do, lse, delta_ws, dq, dk, dv, ld_dqkv, cu_seqlens, num_seqs,
+                            max_seqlen, total_rows, Hq, Hkv, D, scale, causal, rope_cs, stream);
   }
   BwdParams p{};
   p.q = reinterpret_cast<const __nv_bfloat16*>(q);

@@ -95,6 +95,10 @@ int attention_bwd(const void* q, const void* k, const void* v, long long ld_qkv,
                   const void* dout, long long ld_do, const float* lse, float* delta_ws, void* dq, void* dk, void* dv,
                   long long ld_dqkv, const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq,
                   int Hkv, int D, float scale, int causal, const float* rope_cs, cudaStream_t stream);
+int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld_qkv, const void* dout, long long ld_do,
+                     const float* lse, const float* delta, void* dq, void* dk, void* dv, long long ld_dqkv,
+                     const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
+                     float scale, int causal, const float* rope_cs, cudaStream_t stream);
 void attention_set_impl(int impl);  // 1 = tcgen05 kernel (default), 0 = legacy mma.sync kernel
 int attention_get_impl();
 

@@ -156,7 +156,6 @@ def _attn_ref(qkv, cu, Hq, Hkv, D, scale, causal):
 @pytest.mark.parametrize("impl", [1, 0], ids=["tcgen05", "mma_sync"])
 def test_attention(cuda, Hq, Hkv, D, causal, lens, impl):
     from llm_speech_summarization_b200 import ops
-    ops.attention_set_impl(impl)
     try:
         _run_attention_case(cuda, Hq, Hkv, D, causal, lens)
     finally:
@@ -185,7 +184,8 @@ def _run_attention_case(cuda, Hq, Hkv, D, causal, lens):
     (6, 6, 128, True, [136, 300]),
     (4, 2, 64, True, [77, 200]),
 ])
-def test_attention_backward(cuda, Hq, Hkv, D, causal, lens):
+@pytest.mark.parametrize("impl", [1, 0], ids=["tcgen05", "mma_sync"])
+def test_attention_backward(cuda, Hq, Hkv, D, causal, lens, impl):
     """dQ / dK / dV of the packed attention vs autograd through fp32 SDPA on the same bf16 inputs."""
     from llm_speech_summarization_b200 import ops
     g = torch.Generator().manual_seed(sum(lens) * D + Hq)
@@ -198,7 +198,11 @@ def test_attention_backward(cuda, Hq, Hkv, D, causal, lens):
     cu_t = torch.tensor(cu, dtype=torch.int32, device=cuda)
     scale = 1.0 / math.sqrt(D)
     o, lse = ops.attention(qkv, cu_t, max(lens), Hq, Hkv, D, scale, causal, return_lse=True)
-    dqkv = ops.attention_bwd(qkv, o, dout, lse, cu_t, max(lens), Hq, Hkv, D, scale, causal)
+    ops.attention_set_impl(impl)  # the forward (and its lse) is always the tcgen05 kernel
+    try:
+        dqkv = ops.attention_bwd(qkv, o, dout, lse, cu_t, max(lens), Hq, Hkv, D, scale, causal)
+    finally:
+        ops.attention_set_impl(1)
     x = qkv.float().requires_grad_(True)
     ref = _attn_ref(x, cu, Hq, Hkv, D, scale, causal)
     ref.backward(dout.float())
