@@ -176,6 +176,39 @@ __device__ __forceinline__ void emit_f32(uint32_t stg, const float (&v)[32], int
   __syncwarp();
 }
 
+// residual tile of one 32x32 chunk in the coalesced (row = i*4 + lane/8, 16-byte chunk = lane%8) register layout
+__device__ __forceinline__ void load_resid(float4 (&r)[8], const float* resid0, long long ld, int lane, int rows_valid,
+                                           int cols_valid) {
+  const int chunk = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (resid0 != nullptr && row < rows_valid && chunk * 4 < cols_valid) {
+      r[i] = *reinterpret_cast<const float4*>(resid0 + row * ld + chunk * 4);
+    }
+  }
+}
+
+// emit_f32 with the residual already in registers (loaded one chunk ahead: the global-load latency of the residual
+// overlaps the TMEM read / transpose of the previous chunk instead of sitting between them)
+__device__ __forceinline__ void emit_f32_pre(uint32_t stg, const float (&v)[32], int lane, float* out0,
+                                             const float4 (&r)[8], long long ld, int rows_valid, int cols_valid) {
+  stage_write(stg, v, lane);
+  __syncwarp();
+  const int chunk = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    const float4 x = stage_read(stg, row, chunk);
+    if (row < rows_valid && chunk * 4 < cols_valid) {
+      *reinterpret_cast<float4*>(out0 + row * ld + chunk * 4) =
+          make_float4(x.x + r[i].x, x.y + r[i].y, x.z + r[i].z, x.w + r[i].w);
+    }
+  }
+  __syncwarp();
+}
+
 // out += v (fp32 reduction in L2: split-K partial sums and gradient accumulation across micro-batches)
 __device__ __forceinline__ void emit_accum_f32(uint32_t stg, const float (&v)[32], int lane, float* out0, long long ld,
                                                int rows_valid, int cols_valid) {
@@ -419,10 +452,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const uint32_t taddr = tmem_base + lane_base + as * BN;
 
       if (p.epi == EPI_BF16 || p.epi == EPI_F32 || p.epi == EPI_RESID_F32 || (EXT && p.epi == EPI_ACCUM_F32)) {
+        const bool has_resid = p.epi == EPI_RESID_F32;
+        const long long rbase = (p.resid_bcast ? static_cast<long long>(m0w) : orow0) * p.ldo +
+                                static_cast<long long>(tc.g) * og_cols;
+        float4 rnext[8];
+        if (has_resid) load_resid(rnext, p.resid + rbase + ncol0, p.ldo, lane, rows_valid, min(32, p.N - ncol0));
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           const int col = ncol0 + c * 32;
           if (col >= p.N) break;
+          float4 rcur[8];
+          if (has_resid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+            if (c + 1 < BN / 32 && col + 32 < p.N)
+              load_resid(rnext, p.resid + rbase + col + 32, p.ldo, lane, rows_valid, min(32, p.N - col - 32));
+          }
           uint32_t raw[32];
           ptx::tmem_ld_32x32(taddr + c * 32, raw);
           ptx::tmem_ld_wait();
@@ -444,13 +489,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             emit_bf16(stg, v, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, valid);
           } else if (EXT && p.epi == EPI_ACCUM_F32) {
             emit_accum_f32(stg, v, lane, reinterpret_cast<float*>(p.out) + off0, p.ldo, rows_valid, valid);
+          } else if (has_resid) {
+            // (resid_bcast: the residual is indexed by the row inside the batch only, e.g. a positional table)
+            emit_f32_pre(stg, v, lane, reinterpret_cast<float*>(p.out) + off0, rcur, p.ldo, rows_valid, valid);
           } else {
-            // resid_bcast: the residual is indexed by the row inside the batch only (e.g. a positional table)
-            const long long roff0 = p.resid_bcast
-                                        ? static_cast<long long>(m0w) * p.ldo + static_cast<long long>(tc.g) * og_cols + col
-                                        : off0;
-            emit_f32(stg, v, lane, reinterpret_cast<float*>(p.out) + off0,
-                     p.epi == EPI_RESID_F32 ? p.resid + roff0 : nullptr, p.ldo, rows_valid, valid);
+            emit_f32(stg, v, lane, reinterpret_cast<float*>(p.out) + off0, nullptr, p.ldo, rows_valid, valid);
           }
         }
       } else {

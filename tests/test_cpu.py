@@ -283,3 +283,66 @@ def test_whisper_state_dict_layout():
     assert set(enc.state_dict().keys()) == set(sd.keys())
     enc.load_state_dict(sd, strict=True)
     assert "encoder.layers.0.self_attn.k_proj.bias" not in enc.state_dict()
+
+
+# --------------------------------------------------------------------------------------- training host logic
+def test_polynomial_lr_matches_torch():
+    """PolynomialLR(power=1.0) of REF/trainer.py:106-110 in closed form == torch's scheduler, step by step."""
+    from llm_speech_summarization_b200.training import PolynomialLR
+
+    class _Opt:
+        defaults = {"lr": 5e-5}
+        lr = 5e-5
+
+    ours = PolynomialLR(_Opt(), total_iters=7, power=1.0)
+    p = torch.nn.Parameter(torch.zeros(1))
+    topt = torch.optim.AdamW([p], lr=5e-5)
+    theirs = torch.optim.lr_scheduler.PolynomialLR(topt, total_iters=7, power=1.0)
+    for _ in range(10):
+        assert abs(ours.get_last_lr()[0] - theirs.get_last_lr()[0]) < 1e-12
+        topt.step()
+        theirs.step()
+        ours.step()
+    sd = ours.state_dict()
+    again = PolynomialLR(_Opt(), total_iters=3)
+    again.load_state_dict(sd)
+    assert again.get_last_lr() == ours.get_last_lr() and again.last_epoch == ours.last_epoch
+
+
+def test_flat_param_order_and_grad_spec_cover_every_parameter():
+    """The flat optimizer layout lists every parameter once with q|k|v weights (and biases) of a layer adjacent, and
+    the packed gradient buffers tile exactly the parameters the reference optimises (REF/trainer.py:98-105)."""
+    from oracle import configs
+    from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
+    enc = AudioEncoder(ns_config(configs.TINY_ENCODER, configs.TINY_LLAMA), "cpu")
+    params = list(enc.parameters())
+    order = enc.flat_param_order()
+    assert len(order) == len(params) and {id(p) for p in order} == {id(p) for p in params}
+    pos = {id(p): i for i, p in enumerate(order)}
+    for lay in enc.encoder.encoder.layers:
+        a = lay.attention
+        assert pos[id(a.k_proj.weight)] == pos[id(a.q_proj.weight)] + 1 == pos[id(a.v_proj.weight)] - 1
+        assert pos[id(a.k_proj.bias)] == pos[id(a.q_proj.bias)] + 1 == pos[id(a.v_proj.bias)] - 1
+    covered = {}
+    for name, shape, ps in enc._grad_spec():
+        assert sum(p.numel() for p in ps) == int(torch.tensor(shape).prod()), name
+        for p in ps:
+            assert id(p) not in covered, name
+            covered[id(p)] = name
+    named = dict(enc.named_parameters())
+    missing = [n for n, p in named.items() if id(p) not in covered]
+    # conv weights (permuted layout), the weight-normed positional conv and the unused SpecAugment embedding go
+    # through scratch / get no gradient; everything else accumulates in place
+    assert all(("conv.weight" in n and "conv_layers.0" not in n) or "parametrizations" in n or n.endswith(
+        "masked_spec_embed") for n in missing), missing
+
+
+def test_training_path_fails_loudly_without_gpu():
+    from oracle import configs
+    from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
+    from llm_speech_summarization_b200.training import FlatAdamW
+    enc = AudioEncoder(ns_config(configs.TINY_ENCODER, configs.TINY_LLAMA), "cpu")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        FlatAdamW(enc.parameters())
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        enc.forward_train(torch.zeros(1, 4000))
