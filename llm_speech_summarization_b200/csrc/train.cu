@@ -206,9 +206,10 @@ int llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt, co
 
   B2S_CUDA_CHECK(cudaMemsetAsync(dh, 0, static_cast<size_t>(Ms) * H * 4, stream));
   B2S_CUDA_CHECK(cudaMemsetAsync(pl.dh_bf16, 0, static_cast<size_t>(Ms) * H * 2, stream));
-  {  // LM head dgrad on the consumed rows
+  {  // LM head dgrad on the consumed rows: few output tiles and K = vocab, so split K over the whole chip
+    B2S_CUDA_CHECK(cudaMemsetAsync(pl.dxf, 0, static_cast<size_t>(n_dl) * H * 4, stream));
     GemmArgs g = lin(d_logits, wt->lm_head_t, n_dl, H, w->vocab);
-    g.epi = EPI_F32;
+    g.epi = EPI_ACCUM_F32;
     g.out = pl.dxf;
     rc = gemm_bf16_launch(g, stream);
     if (rc != B2S_OK) return rc;
@@ -238,6 +239,7 @@ int llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt, co
       rc = gemm_bf16_launch(g, stream);
       if (rc != B2S_OK) return rc;
     }
+    // (fusing this into the dgrad epilogue was measured: the GEMMs lose more than the 80 us launch saves)
     rc = swiglu_bwd(gu, pl.dact, pl.dgu, Ms, F, stream);
     if (rc != B2S_OK) return rc;
     {  // gate|up dgrad
