@@ -271,6 +271,13 @@ int b2s_llama_prefill(const b2s_llama_weights* w, float* h, int32_t rows, const 
                       const int32_t* tap_rows_b, int32_t pairs, float* fd_sq, float* all_hidden, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ---- Whisper log-mel features on the GPU (row f2): replaces transformers' WhisperFeatureExtractor call in the
+ * reference's collate function (REF/trainer.py:178-182; TF/models/whisper/feature_extraction_whisper.py:105-133).
+ * wave fp32 [batches, samples] (row stride wave_stride), mel_filters fp32 [201, 80] (slaney, as the extractor holds
+ * them), out fp32 [batches, 80, frames] with frames = samples / 160, max_ws int32 [batches] scratch. */
+int b2s_whisper_log_mel(const float* wave, int64_t wave_stride, int32_t batches, int32_t samples,
+                        const float* mel_filters, float* out, int32_t frames, int32_t* max_ws, void* stream);
+
 /* ---- greedy decode with a KV cache (REF/inference.py:55-74, REF/trainer.py:530-545: HF generate after the prefill).
  * Cache: bf16 [layers][slots][2*kv_heads*head_dim], one row = k (post-RoPE) | v of one token.
  * b2s_llama_prefill_kv = b2s_llama_prefill that also stores packed row r of every layer into slot kv_slot_of_row[r]

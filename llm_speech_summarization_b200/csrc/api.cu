@@ -371,4 +371,9 @@ int b2s_llama_decode_step(const b2s_llama_weights* w, const void* embed_table_bf
                            workspace, workspace_bytes, S(stream));
 }
 
+int b2s_whisper_log_mel(const float* wave, int64_t wave_stride, int32_t batches, int32_t samples,
+                        const float* mel_filters, float* out, int32_t frames, int32_t* max_ws, void* stream) {
+  return whisper_log_mel(wave, wave_stride, batches, samples, mel_filters, out, frames, max_ws, S(stream));
+}
+
 }  // extern "C"

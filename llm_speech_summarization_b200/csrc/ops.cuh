@@ -51,6 +51,11 @@ int cast_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t stream);
 int cast_bf16_to_f32(const void* x, float* y, long long n, cudaStream_t stream);
 // y_bf16 = gelu(x_f32 + residual) etc. are fused in GEMM epilogues; nothing else elementwise is needed.
 
+// ---- logmel.cu: WhisperFeatureExtractor on the GPU (reflect-padded STFT 400/160, 80 slaney mels, log10, clamp, scale)
+// out fp32 [batches, 80, frames], frames = samples / 160; max_ws int32 [batches] scratch
+int whisper_log_mel(const float* wave, long long wave_stride, int batches, int samples, const float* mel_filters,
+                    float* out, int frames, int* max_ws, cudaStream_t stream);
+
 // ---- backward.cu (training step: memory-bound backward kernels + optimizer)
 // dh[dst] += RMSNorm^T(dy) ; x / dst rows optionally gathered through index lists; optional bf16 copy of dh rows
 int rmsnorm_bwd(const float* x, const int* x_index, const float* w, float eps, const float* dy, float* dh,

@@ -359,6 +359,24 @@ class AudioEncoder(nn.Module):
                                            torch.cuda.current_stream().cuda_stream), "whisper_forward")
         return (out, last) if return_last_hidden else out
 
+    def extract_features(self, waves: torch.Tensor) -> torch.Tensor:
+        """Whisper collate step on the GPU (REF/trainer.py:178-182): (B, n_samples) fp32 CUDA waveforms, already padded
+        / truncated to the extractor's 30 s window, -> (B, 80, 3000) log-mel `input_features`. Same numbers as
+        `self.feature_extractor(..., return_tensors="pt").input_features` without the CPU STFT."""
+        if self.encoder_base != "whisper":
+            raise Exception("Unexpected encoder type in config.")
+        if not waves.is_cuda:
+            raise RuntimeError("AudioEncoder.extract_features (B200 path) needs a CUDA input; there is no CPU path")
+        if self.feature_extractor is None:
+            raise RuntimeError("transformers' WhisperFeatureExtractor (mel filter bank) is unavailable")
+        if getattr(self, "_mel_filters", None) is None or self._mel_filters.device != waves.device:
+            self._mel_filters = torch.as_tensor(self.feature_extractor.mel_filters, dtype=torch.float32).contiguous().to(
+                waves.device)
+        w = waves.to(torch.float32)
+        if w.stride(-1) != 1:
+            w = w.contiguous()
+        return ops.whisper_log_mel(w, self._mel_filters)
+
     def num_frames(self, samples: int):
         w = self.pack_weights()[0]
         frames, pooled = C.c_int32(), C.c_int32()

@@ -282,6 +282,21 @@ def gather_rows(src: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def whisper_log_mel(waves: torch.Tensor, mel_filters: torch.Tensor) -> torch.Tensor:
+    """(B, samples) fp32 waveforms -> (B, 80, samples // 160) fp32 log-mel features, WhisperFeatureExtractor's numbers
+    (TF/models/whisper/feature_extraction_whisper.py:105-133). mel_filters: fp32 [201, 80]."""
+    _need_cuda(waves, mel_filters)
+    assert waves.dtype == torch.float32 and waves.dim() == 2 and waves.stride(1) == 1
+    assert mel_filters.dtype == torch.float32 and mel_filters.shape == (201, 80) and mel_filters.is_contiguous()
+    B, n = waves.shape
+    frames = n // 160
+    out = torch.empty(B, 80, frames, device=waves.device, dtype=torch.float32)
+    mx = torch.empty(B, device=waves.device, dtype=torch.int32)
+    _lib.check(_lib.load().b2s_whisper_log_mel(waves.data_ptr(), waves.stride(0), B, n, mel_filters.data_ptr(),
+                                               out.data_ptr(), frames, mx.data_ptr(), _stream()), "whisper_log_mel")
+    return out
+
+
 def attention_set_impl(impl: int) -> None:
     """1 = tcgen05 kernel (default), 0 = legacy mma.sync kernel (A/B tests only)."""
     _lib.load().b2s_attention_set_impl(int(impl))

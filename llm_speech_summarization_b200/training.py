@@ -206,9 +206,17 @@ class EncoderTrainer:
         stacked = torch.stack([out[k] for k in keys]).cpu()
         return {k: stacked[i] for i, k in enumerate(keys)}
 
-    def checkpoint(self, epoch: int) -> Dict:
-        """Same keys as REF/trainer.py:518-526."""
-        return {"audio_encoder": {k: v.detach().clone() for k, v in self.audio_encoder.state_dict().items()},
+    def checkpoint(self, epoch: int, legacy_weight_norm_keys: bool = False) -> Dict:
+        """Same keys as REF/trainer.py:518-526. `legacy_weight_norm_keys=True` spells the positional conv's weight-norm
+        parameters `weight_g` / `weight_v` (what the reference's pinned torch 2.0 writes and expects); the default is
+        the `parametrizations.weight.original0/1` spelling of current torch. Loading accepts both."""
+        enc_sd = {k: v.detach().clone() for k, v in self.audio_encoder.state_dict().items()}
+        if legacy_weight_norm_keys:
+            for new, old in (("parametrizations.weight.original0", "weight_g"),
+                             ("parametrizations.weight.original1", "weight_v")):
+                for k in [k for k in enc_sd if k.endswith(new)]:
+                    enc_sd[k[:-len(new)] + old] = enc_sd.pop(k)
+        return {"audio_encoder": enc_sd,
                 "optimizer": self.optimizer.state_dict(), "lr_scheduler": self.lr_scheduler.state_dict(),
                 "epoch": epoch, "step": self.step}
 

@@ -375,3 +375,21 @@ def audio_prompt_prefill(enc_sd, llm_sd, enc_cfg, llm_cfg, tokenizer, audio: tor
     prompt = merge_prompt_tokens(combined, tokenizer, embed, llm_cfg.llm_type)
     _, logits, _ = audio_llama_forward(llm_sd, prompt, None, None, llm_cfg, num_logits_to_keep=1)
     return audio_embeds, prompt, logits[:, -1, :]
+
+
+def whisper_log_mel(wave, mel_filters, n_fft: int = 400, hop: int = 160):
+    """WhisperFeatureExtractor._np_extract_fbank_features (TF/models/whisper/feature_extraction_whisper.py:105-133 over
+    TF/audio_utils.py spectrogram): reflect-padded (center) STFT with a periodic Hann window, power spectrum, mel
+    filter bank [201, 80], log10(max(., 1e-10)), last frame dropped, clamp to max - 8, (x + 4) / 4.
+    wave: 1-D float array of n samples (already padded to the 30 s window) -> float64 [80, n // hop]."""
+    import numpy as np
+    x = np.asarray(wave, dtype=np.float64)
+    xp = np.pad(x, (n_fft // 2, n_fft // 2), mode="reflect")
+    n_frames = 1 + (len(xp) - n_fft) // hop
+    win = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n_fft) / n_fft)
+    idx = np.arange(n_fft)[None, :] + hop * np.arange(n_frames)[:, None]
+    spec = np.abs(np.fft.rfft(xp[idx] * win[None, :], axis=1)) ** 2          # [frames, 201]
+    mel = np.maximum(np.asarray(mel_filters, dtype=np.float64).T @ spec.T, 1e-10)  # [80, frames]
+    log_spec = np.log10(mel)[:, :-1]
+    log_spec = np.maximum(log_spec, log_spec.max() - 8.0)
+    return (log_spec + 4.0) / 4.0

@@ -346,3 +346,20 @@ def test_training_path_fails_loudly_without_gpu():
         FlatAdamW(enc.parameters())
     with pytest.raises(RuntimeError, match="no CPU path"):
         enc.forward_train(torch.zeros(1, 4000))
+
+
+def test_whisper_log_mel_oracle_matches_transformers_extractor():
+    """oracle.whisper_log_mel restates WhisperFeatureExtractor (the reference's collate-side dependency,
+    REF/trainer.py:178-182); pinned here against the extractor itself on seeded audio."""
+    transformers = pytest.importorskip("transformers")
+    import numpy as np
+    from oracle import reference_math as rm
+    fe = transformers.WhisperFeatureExtractor()
+    g = torch.Generator().manual_seed(77)
+    wave = (torch.randn(48000, generator=g) * 0.1).numpy()
+    feats = fe(wave, sampling_rate=16000, return_tensors="np").input_features[0]   # pads to 30 s
+    padded = np.zeros(480000, dtype=np.float32)
+    padded[:48000] = wave
+    ours = rm.whisper_log_mel(padded, fe.mel_filters)
+    assert ours.shape == feats.shape == (80, 3000)
+    assert float(np.abs(ours - feats).max()) < 2e-4

@@ -216,3 +216,47 @@ def test_attention_backward(cuda, Hq, Hkv, D, causal, lens, impl):
     assert torch.allclose(lse[a:b].t() * math.log(2.0), torch.logsumexp(s, -1), atol=2e-3, rtol=2e-3)
     for name, sl in (("dq", slice(0, Hq * D)), ("dk", slice(Hq * D, (Hq + Hkv) * D)), ("dv", slice((Hq + Hkv) * D, None))):
         assert rel_l2(dqkv[:, sl].float(), x.grad[:, sl]) < 1.5e-2, name
+
+
+# ------------------------------------------------------------------------------------------------ Whisper log-mel (f2)
+@pytest.mark.parametrize("B,seconds_of_signal", [(1, 30.0), (3, 7.3)])
+def test_whisper_log_mel_matches_oracle(cuda, B, seconds_of_signal):
+    """GPU log-mel == the oracle's restatement of WhisperFeatureExtractor (itself pinned against transformers in the
+    CPU suite). Tolerance 2e-4 absolute on features that live in (-1, 1.6): fp32 DFT vs float64 FFT."""
+    transformers = pytest.importorskip("transformers")
+    import numpy as np
+    from oracle import reference_math as rm
+    from llm_speech_summarization_b200 import ops
+    mel = np.asarray(transformers.WhisperFeatureExtractor().mel_filters, dtype=np.float32)
+    g = torch.Generator().manual_seed(3 + B)
+    n = int(seconds_of_signal * 16000)
+    waves = torch.zeros(B, 480000)
+    waves[:, :n] = torch.randn(B, n, generator=g) * 0.1 * torch.linspace(0.2, 1.0, n)  # zero-padded to the 30 s window
+    out = ops.whisper_log_mel(waves.to(cuda), torch.from_numpy(mel).to(cuda))
+    assert out.shape == (B, 80, 3000)
+    for b in range(B):
+        ref = rm.whisper_log_mel(waves[b].numpy(), mel)
+        assert float((out[b].cpu().double() - torch.from_numpy(ref)).abs().max()) < 2e-4
+
+
+def test_whisper_extract_features_feeds_the_encoder(cuda):
+    """AudioEncoder.extract_features (GPU) == the extractor's input_features, and the encoder consumes it directly."""
+    transformers = pytest.importorskip("transformers")
+    from oracle import configs
+    from helpers import ns_config_whisper
+    from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
+    cfg = configs.WhisperCfg(hidden=256, layers=1, heads=4, ffn=512, max_positions=1500, llm_dim=256)
+    enc = AudioEncoder(ns_config_whisper(cfg), cuda)
+    enc.load_state_dict(configs.make_whisper_state_dict(cfg, seed=5), strict=True)
+    enc.eval().to(cuda)
+    g = torch.Generator().manual_seed(8)
+    wave = torch.randn(52000, generator=g) * 0.05
+    want = enc.feature_extractor(wave.numpy(), sampling_rate=16000, return_tensors="pt").input_features  # CPU STFT
+    padded = torch.zeros(1, 480000)
+    padded[0, :52000] = wave
+    got = enc.extract_features(padded.to(cuda))
+    assert got.shape == want.shape and float((got.cpu() - want).abs().max()) < 2e-4
+    with torch.no_grad():
+        a = enc.forward_fp32(got)
+        b = enc.forward_fp32(want.to(cuda))
+    assert rel_l2(a, b) < 5e-3

@@ -192,3 +192,11 @@ def test_trainer_accumulates_and_matches_torch_adamw(cuda):
     torch_opt.load_state_dict(ck["optimizer"])  # layout-compatible with the reference's optimizer
     tr.load_checkpoint(ck)
     assert tr.step == 4 and tr.optimizer.step_count == 1
+    # torch-2.0 spelling of the weight-norm parameters (what the reference's pinned torch writes) round-trips too
+    legacy = tr.checkpoint(epoch=0, legacy_weight_norm_keys=True)
+    assert any(k.endswith("pos_conv_embed.conv.weight_g") for k in legacy["audio_encoder"])
+    assert not any("parametrizations" in k for k in legacy["audio_encoder"])
+    before = {k: v.clone() for k, v in enc.state_dict().items()}
+    tr.load_checkpoint(legacy)
+    after = enc.state_dict()
+    assert all(torch.equal(before[k], after[k]) for k in before)
