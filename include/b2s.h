@@ -369,6 +369,21 @@ int b2s_hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, co
                         const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, void* saved,
                         size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
                         void* stream);
+/* Whisper encoder (REF/config/llama3_whisper.yaml trains it like the HuBERT one): same contract; mel fp32
+ * [batches, mel_bins, 2*max_positions]; conv weights' gradients in the packed [H, 3*C_in] layout; the sinusoid table is
+ * frozen; the k_proj slot of bqkv's gradient has no parameter behind it. */
+typedef struct {
+  float *conv1_w, *conv1_b, *conv2_w, *conv2_b;
+  const b2s_encoder_layer_grads* layers; /* host array */
+  float *final_ln_g, *final_ln_b, *proj_w, *proj_b;
+} b2s_whisper_grads;
+size_t b2s_whisper_saved_bytes(const b2s_whisper_weights* w, int32_t batches);
+size_t b2s_whisper_backward_workspace_bytes(const b2s_whisper_weights* w, int32_t batches);
+int b2s_whisper_forward_train(const b2s_whisper_weights* w, const float* mel, int32_t batches, int32_t frames_in,
+                              void* saved, size_t saved_bytes, float* audio_embeds, void* stream);
+int b2s_whisper_backward(const b2s_whisper_weights* w, const b2s_whisper_grads* grads, int32_t batches, void* saved,
+                         size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
+                         void* stream);
 /* memory-bound backward kernels of the encoder (see csrc/backward_enc.cu) */
 int b2s_layernorm_bwd_ex(const void* x, int32_t x_bf16, const float* gamma, const float* beta, int32_t act_gelu,
                          float eps, const void* dy, int32_t dy_bf16, float* dh, int32_t accumulate, void* dx_bf16,

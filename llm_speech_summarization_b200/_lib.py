@@ -65,6 +65,12 @@ class HubertGrads(C.Structure):
     ]
 
 
+class WhisperGrads(C.Structure):
+    _fields_ = [("conv1_w", c_void_p), ("conv1_b", c_void_p), ("conv2_w", c_void_p), ("conv2_b", c_void_p),
+                ("layers", C.POINTER(EncoderLayerGrads)), ("final_ln_g", c_void_p), ("final_ln_b", c_void_p),
+                ("proj_w", c_void_p), ("proj_b", c_void_p)]
+
+
 class WhisperWeights(C.Structure):
     _fields_ = [
         ("conv1_w", c_void_p), ("conv1_b", c_void_p), ("conv2_w", c_void_p), ("conv2_b", c_void_p),
@@ -172,6 +178,12 @@ PROTOTYPES = {
                                          C.c_size_t, c_void_p, c_void_p]),
     "b2s_hubert_backward": (c_int, [C.POINTER(HubertWeights), c_void_p, C.POINTER(HubertGrads), c_void_p, c_int64,
                                     c_int, c_int, c_void_p, C.c_size_t, c_void_p, c_void_p, C.c_size_t, c_void_p]),
+    "b2s_whisper_saved_bytes": (C.c_size_t, [C.POINTER(WhisperWeights), c_int]),
+    "b2s_whisper_backward_workspace_bytes": (C.c_size_t, [C.POINTER(WhisperWeights), c_int]),
+    "b2s_whisper_forward_train": (c_int, [C.POINTER(WhisperWeights), c_void_p, c_int, c_int, c_void_p, C.c_size_t,
+                                          c_void_p, c_void_p]),
+    "b2s_whisper_backward": (c_int, [C.POINTER(WhisperWeights), C.POINTER(WhisperGrads), c_int, c_void_p, C.c_size_t,
+                                     c_void_p, c_void_p, C.c_size_t, c_void_p]),
     "b2s_layernorm_bwd_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p,
                                      c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "b2s_colsum_accum": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p]),

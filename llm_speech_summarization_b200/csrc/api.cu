@@ -58,6 +58,13 @@ int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_
                   float* fd_sq, float* all_hidden, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 size_t llama_train_workspace_bytes(const b2s_llama_weights* w, int rows, int logit_rows);
+size_t whisper_saved_bytes(const b2s_whisper_weights* w, int batches);
+size_t whisper_backward_workspace_bytes(const b2s_whisper_weights* w, int batches);
+int whisper_forward_train(const b2s_whisper_weights* w, const float* mel, int batches, int frames_in, void* saved,
+                          size_t saved_bytes, float* audio_embeds, cudaStream_t stream);
+int whisper_backward(const b2s_whisper_weights* w, const b2s_whisper_grads* gr, int batches, void* saved,
+                     size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream);
 size_t llama_kv_cache_bytes(const b2s_llama_weights* w, int slots);
 int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* cu_seqlens, int num_seqs,
                      int max_seqlen, const int* positions, const int* logit_rows_index, int logit_rows,
@@ -374,6 +381,20 @@ int b2s_llama_decode_step(const b2s_llama_weights* w, const void* embed_table_bf
 int b2s_whisper_log_mel(const float* wave, int64_t wave_stride, int32_t batches, int32_t samples,
                         const float* mel_filters, float* out, int32_t frames, int32_t* max_ws, void* stream) {
   return whisper_log_mel(wave, wave_stride, batches, samples, mel_filters, out, frames, max_ws, S(stream));
+}
+
+size_t b2s_whisper_saved_bytes(const b2s_whisper_weights* w, int32_t batches) { return whisper_saved_bytes(w, batches); }
+size_t b2s_whisper_backward_workspace_bytes(const b2s_whisper_weights* w, int32_t batches) {
+  return whisper_backward_workspace_bytes(w, batches);
+}
+int b2s_whisper_forward_train(const b2s_whisper_weights* w, const float* mel, int32_t batches, int32_t frames_in,
+                              void* saved, size_t saved_bytes, float* audio_embeds, void* stream) {
+  return whisper_forward_train(w, mel, batches, frames_in, saved, saved_bytes, audio_embeds, S(stream));
+}
+int b2s_whisper_backward(const b2s_whisper_weights* w, const b2s_whisper_grads* grads, int32_t batches, void* saved,
+                         size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  return whisper_backward(w, grads, batches, saved, saved_bytes, d_audio_embeds, workspace, workspace_bytes, S(stream));
 }
 
 }  // extern "C"

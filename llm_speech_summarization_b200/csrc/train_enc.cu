@@ -188,6 +188,133 @@ int wgrad(const void* dy, const void* x, long long rows, int N, int K, float* dW
     if (_rc != B2S_OK) return _rc; \
   } while (0)
 
+
+// ---- pieces shared by the HuBERT and Whisper encoders: the pre-LN transformer stack and the pool + projector head
+struct StackBufs {   // per-layer saved activations (see Saved)
+  float *h, *h_mid, *lse;
+  void *qkv, *ao, *ff_pre, *ff;
+};
+struct StackScratch {  // backward scratch
+  float *dh, *delta;
+  void *dyb, *dbig, *dsm, *xn;
+};
+
+int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, int heads, float eps, const StackBufs& s,
+                        void* xn, const int* cu, int B, int frames, cudaStream_t stream) {
+  const long long rows = static_cast<long long>(B) * frames;
+  const size_t rH = static_cast<size_t>(rows) * H;
+  for (int l = 0; l < L; ++l) {
+    const b2s_encoder_layer& Ly = layers[l];
+    float* h_in = s.h + l * rH;
+    float* h_mid = s.h_mid + l * rH;
+    float* h_out = s.h + (l + 1) * rH;
+    __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(s.qkv) + l * 3 * rH;
+    __nv_bfloat16* ao = reinterpret_cast<__nv_bfloat16*>(s.ao) + l * rH;
+    __nv_bfloat16* ffp = reinterpret_cast<__nv_bfloat16*>(s.ff_pre) + static_cast<size_t>(l) * rows * F;
+    __nv_bfloat16* ff = reinterpret_cast<__nv_bfloat16*>(s.ff) + static_cast<size_t>(l) * rows * F;
+    RC(layernorm_fwd(h_in, 0, Ly.ln1_g, Ly.ln1_b, eps, 0, xn, rows, H, stream));
+    {
+      GemmArgs g = lin(xn, Ly.wqkv, rows, 3 * H, H);
+      g.epi = EPI_BF16;
+      g.bias = Ly.bqkv;
+      g.out = qkv;
+      RC(gemm_bf16_launch(g, stream));
+    }
+    RC(attention_fwd(qkv, qkv + H, qkv + 2 * H, 3 * H, ao, H, cu, B, frames, rows, heads, heads, 64, 0.125f, 0,
+                     s.lse + static_cast<size_t>(l) * rows * heads, stream));
+    {
+      GemmArgs g = lin(ao, Ly.wo, rows, H, H);
+      g.epi = EPI_RESID_F32;
+      g.bias = Ly.bo;
+      g.out = h_mid;
+      g.resid = h_in;
+      RC(gemm_bf16_launch(g, stream));
+    }
+    RC(layernorm_fwd(h_mid, 0, Ly.ln2_g, Ly.ln2_b, eps, 0, xn, rows, H, stream));
+    {
+      GemmArgs g = lin(xn, Ly.w1, rows, F, H);
+      g.epi = EPI_BF16;
+      g.act = ACT_GELU;
+      g.bias = Ly.b1;
+      g.out = ff;
+      g.out2 = ffp;
+      g.ld2 = F;
+      RC(gemm_bf16_launch(g, stream));
+    }
+    {
+      GemmArgs g = lin(ff, Ly.w2, rows, H, F);
+      g.epi = EPI_RESID_F32;
+      g.bias = Ly.b2;
+      g.out = h_out;
+      g.resid = h_mid;
+      RC(gemm_bf16_launch(g, stream));
+    }
+  }
+  return B2S_OK;
+}
+
+// on entry b.dh / b.dyb hold d(loss)/d(h[L]) (fp32 / bf16); on exit d(loss)/d(h[0])
+int stack_backward(const b2s_encoder_layer* layers, const b2s_encoder_layer_grads* grads, int L, int H, int F, int heads,
+                   float eps, const StackBufs& s, const StackScratch& b, const int* cu, int B, int frames,
+                   cudaStream_t stream) {
+  const long long rows = static_cast<long long>(B) * frames;
+  const size_t rH = static_cast<size_t>(rows) * H;
+  for (int l = L - 1; l >= 0; --l) {
+    const b2s_encoder_layer& Ly = layers[l];
+    const b2s_encoder_layer_grads& G = grads[l];
+    const float* h_in = s.h + l * rH;
+    const float* h_mid = s.h_mid + l * rH;
+    const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(s.qkv) + l * 3 * rH;
+    const __nv_bfloat16* ao = reinterpret_cast<const __nv_bfloat16*>(s.ao) + l * rH;
+    const __nv_bfloat16* ffp = reinterpret_cast<const __nv_bfloat16*>(s.ff_pre) + static_cast<size_t>(l) * rows * F;
+    const __nv_bfloat16* ff = reinterpret_cast<const __nv_bfloat16*>(s.ff) + static_cast<size_t>(l) * rows * F;
+    // feed-forward: h_out = h_mid + W2 gelu(W1 LN2(h_mid) + b1) + b2
+    RC(colsum_accum(b.dh, 0, G.b2, rows, H, stream));
+    RC(wgrad(b.dyb, ff, rows, H, F, G.w2, stream));
+    RC(dgrad(b.dyb, Ly.w2, rows, H, F, EPI_BF16, b.dbig, stream));
+    RC(gelu_bwd(ffp, b.dbig, b.dbig, rows * F, stream));
+    RC(colsum_accum(b.dbig, 1, G.b1, rows, F, stream));
+    RC(layernorm_fwd(h_mid, 0, Ly.ln2_g, Ly.ln2_b, eps, 0, b.xn, rows, H, stream));
+    RC(wgrad(b.dbig, b.xn, rows, F, H, G.w1, stream));
+    RC(dgrad(b.dbig, Ly.w1, rows, F, H, EPI_BF16, b.dsm, stream));
+    RC(layernorm_bwd_ex(h_mid, 0, Ly.ln2_g, Ly.ln2_b, 0, eps, b.dsm, 1, b.dh, 1, b.dyb, G.ln2_g, G.ln2_b, rows, H,
+                        stream));
+    // attention: h_mid = h_in + Wo attn(Wqkv LN1(h_in) + bqkv) + bo
+    RC(colsum_accum(b.dh, 0, G.bo, rows, H, stream));
+    RC(wgrad(b.dyb, ao, rows, H, H, G.wo, stream));
+    RC(dgrad(b.dyb, Ly.wo, rows, H, H, EPI_BF16, b.dsm, stream));
+    {
+      __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(b.dbig);
+      RC(attention_bwd(qkv, qkv + H, qkv + 2 * H, 3 * H, ao, H, b.dsm, H, s.lse + static_cast<size_t>(l) * rows * heads,
+                       b.delta, dqkv, dqkv + H, dqkv + 2 * H, 3 * H, cu, B, frames, rows, heads, heads, 64, 0.125f, 0,
+                       nullptr, stream));
+    }
+    RC(colsum_accum(b.dbig, 1, G.bqkv, rows, 3 * H, stream));
+    RC(layernorm_fwd(h_in, 0, Ly.ln1_g, Ly.ln1_b, eps, 0, b.xn, rows, H, stream));
+    RC(wgrad(b.dbig, b.xn, rows, 3 * H, H, G.wqkv, stream));
+    RC(dgrad(b.dbig, Ly.wqkv, rows, 3 * H, H, EPI_BF16, b.dsm, stream));
+    RC(layernorm_bwd_ex(h_in, 0, Ly.ln1_g, Ly.ln1_b, 0, eps, b.dsm, 1, b.dh, 1, b.dyb, G.ln1_g, G.ln1_b, rows, H, stream));
+  }
+  return B2S_OK;
+}
+
+// projector + AvgPool + final LayerNorm backward: d_audio_embeds -> b.dh / b.dyb = d(loss)/d(h[L])
+int head_backward(const void* proj_w, const float* final_ln_g, const float* final_ln_b, float* g_proj_w, float* g_proj_b,
+                  float* g_ln_g, float* g_ln_b, const float* h_last, const void* pooled_x, const float* d_audio_embeds,
+                  void* da, float* dpool, float* dxn_f, const StackScratch& b, int B, int frames, int pooled, int H,
+                  int Cl, int pool_kernel, int pool_stride, float eps, cudaStream_t stream) {
+  const long long rows = static_cast<long long>(B) * frames;
+  const long long np = static_cast<long long>(B) * pooled;
+  RC(cast_f32_to_bf16(d_audio_embeds, da, np * Cl, stream));
+  RC(colsum_accum(d_audio_embeds, 0, g_proj_b, np, Cl, stream));
+  RC(wgrad(da, pooled_x, np, Cl, H, g_proj_w, stream));
+  RC(dgrad(da, proj_w, np, Cl, H, EPI_F32, dpool, stream));
+  RC(avgpool_bwd(dpool, dxn_f, B, frames, H, pool_kernel, pool_stride, pooled, stream));
+  RC(layernorm_bwd_ex(h_last, 0, final_ln_g, final_ln_b, 0, eps, dxn_f, 0, b.dh, 0, b.dyb, g_ln_g, g_ln_b, rows, H,
+                      stream));
+  return B2S_OK;
+}
+
 }  // namespace
 
 size_t hubert_saved_bytes(const b2s_hubert_weights* w, int batches, int samples) {
@@ -295,52 +422,9 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
   iota_scaled<<<(B + 1 + 255) / 256, 256, 0, stream>>>(s.cu, B + 1, s.frames);
   B2S_LAUNCH_CHECK();
   const size_t rH = static_cast<size_t>(rows) * H;
-  for (int l = 0; l < L; ++l) {
-    const b2s_encoder_layer& Ly = w->layers[l];
-    float* h_in = s.h + l * rH;
-    float* h_mid = s.h_mid + l * rH;
-    float* h_out = s.h + (l + 1) * rH;
-    __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(s.qkv) + l * 3 * rH;
-    __nv_bfloat16* ao = reinterpret_cast<__nv_bfloat16*>(s.ao) + l * rH;
-    __nv_bfloat16* ffp = reinterpret_cast<__nv_bfloat16*>(s.ff_pre) + static_cast<size_t>(l) * rows * F;
-    __nv_bfloat16* ff = reinterpret_cast<__nv_bfloat16*>(s.ff) + static_cast<size_t>(l) * rows * F;
-    RC(layernorm_fwd(h_in, 0, Ly.ln1_g, Ly.ln1_b, eps, 0, s.xn, rows, H, stream));
-    {
-      GemmArgs g = lin(s.xn, Ly.wqkv, rows, 3 * H, H);
-      g.epi = EPI_BF16;
-      g.bias = Ly.bqkv;
-      g.out = qkv;
-      RC(gemm_bf16_launch(g, stream));
-    }
-    RC(attention_fwd(qkv, qkv + H, qkv + 2 * H, 3 * H, ao, H, s.cu, B, s.frames, rows, w->heads, w->heads, 64, 0.125f, 0,
-                     s.lse + static_cast<size_t>(l) * rows * w->heads, stream));
-    {
-      GemmArgs g = lin(ao, Ly.wo, rows, H, H);
-      g.epi = EPI_RESID_F32;
-      g.bias = Ly.bo;
-      g.out = h_mid;
-      g.resid = h_in;
-      RC(gemm_bf16_launch(g, stream));
-    }
-    RC(layernorm_fwd(h_mid, 0, Ly.ln2_g, Ly.ln2_b, eps, 0, s.xn, rows, H, stream));
-    {
-      GemmArgs g = lin(s.xn, Ly.w1, rows, F, H);
-      g.epi = EPI_BF16;
-      g.act = ACT_GELU;
-      g.bias = Ly.b1;
-      g.out = ff;
-      g.out2 = ffp;
-      g.ld2 = F;
-      RC(gemm_bf16_launch(g, stream));
-    }
-    {
-      GemmArgs g = lin(ff, Ly.w2, rows, H, F);
-      g.epi = EPI_RESID_F32;
-      g.bias = Ly.b2;
-      g.out = h_out;
-      g.resid = h_mid;
-      RC(gemm_bf16_launch(g, stream));
-    }
+  {
+    StackBufs sb{s.h, s.h_mid, s.lse, s.qkv, s.ao, s.ff_pre, s.ff};
+    RC(stack_forward_train(w->layers, L, H, F, w->heads, eps, sb, s.xn, s.cu, B, s.frames, stream));
   }
   RC(layernorm_avgpool_fwd(s.h + L * rH, w->final_ln_g, w->final_ln_b, eps, s.pooled_x, B, s.frames, H, w->pool_kernel,
                            w->pool_stride, s.pooled, stream));
@@ -368,56 +452,16 @@ int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const 
               workspace_bytes);
   const int B = batches, H = w->hidden, F = w->ffn, L = w->num_layers, Cl = w->llm_dim;
   const long long rows = static_cast<long long>(B) * s.frames;
-  const long long np = static_cast<long long>(B) * s.pooled;
   const float eps = w->ln_eps;
   const size_t rH = static_cast<size_t>(rows) * H;
 
-  // ---- projector + AvgPool + final LayerNorm
-  RC(cast_f32_to_bf16(d_audio_embeds, b.da, np * Cl, stream));
-  RC(colsum_accum(d_audio_embeds, 0, gr->proj_b, np, Cl, stream));
-  RC(wgrad(b.da, s.pooled_x, np, Cl, H, gr->proj_w, stream));
-  RC(dgrad(b.da, w->proj_w, np, Cl, H, EPI_F32, b.dpool, stream));
-  RC(avgpool_bwd(b.dpool, b.dxn_f, B, s.frames, H, w->pool_kernel, w->pool_stride, s.pooled, stream));
-  RC(layernorm_bwd_ex(s.h + L * rH, 0, w->final_ln_g, w->final_ln_b, 0, eps, b.dxn_f, 0, b.dh, 0, b.dyb, gr->final_ln_g,
-                      gr->final_ln_b, rows, H, stream));
-
-  // ---- transformer layers, last to first
-  for (int l = L - 1; l >= 0; --l) {
-    const b2s_encoder_layer& Ly = w->layers[l];
-    const b2s_encoder_layer_grads& G = gr->layers[l];
-    const float* h_in = s.h + l * rH;
-    const float* h_mid = s.h_mid + l * rH;
-    const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(s.qkv) + l * 3 * rH;
-    const __nv_bfloat16* ao = reinterpret_cast<const __nv_bfloat16*>(s.ao) + l * rH;
-    const __nv_bfloat16* ffp = reinterpret_cast<const __nv_bfloat16*>(s.ff_pre) + static_cast<size_t>(l) * rows * F;
-    const __nv_bfloat16* ff = reinterpret_cast<const __nv_bfloat16*>(s.ff) + static_cast<size_t>(l) * rows * F;
-    // feed-forward: h_out = h_mid + W2 gelu(W1 LN2(h_mid) + b1) + b2
-    RC(colsum_accum(b.dh, 0, G.b2, rows, H, stream));
-    RC(wgrad(b.dyb, ff, rows, H, F, G.w2, stream));
-    RC(dgrad(b.dyb, Ly.w2, rows, H, F, EPI_BF16, b.dbig, stream));
-    RC(gelu_bwd(ffp, b.dbig, b.dbig, rows * F, stream));
-    RC(colsum_accum(b.dbig, 1, G.b1, rows, F, stream));
-    RC(layernorm_fwd(h_mid, 0, Ly.ln2_g, Ly.ln2_b, eps, 0, b.xn, rows, H, stream));
-    RC(wgrad(b.dbig, b.xn, rows, F, H, G.w1, stream));
-    RC(dgrad(b.dbig, Ly.w1, rows, F, H, EPI_BF16, b.dsm, stream));
-    RC(layernorm_bwd_ex(h_mid, 0, Ly.ln2_g, Ly.ln2_b, 0, eps, b.dsm, 1, b.dh, 1, b.dyb, G.ln2_g, G.ln2_b, rows, H,
-                        stream));
-    // attention: h_mid = h_in + Wo attn(Wqkv LN1(h_in) + bqkv) + bo
-    RC(colsum_accum(b.dh, 0, G.bo, rows, H, stream));
-    RC(wgrad(b.dyb, ao, rows, H, H, G.wo, stream));
-    RC(dgrad(b.dyb, Ly.wo, rows, H, H, EPI_BF16, b.dsm, stream));
-    {
-      __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(b.dbig);
-      RC(attention_bwd(qkv, qkv + H, qkv + 2 * H, 3 * H, ao, H, b.dsm, H, s.lse + static_cast<size_t>(l) * rows * w->heads,
-                       b.delta, dqkv, dqkv + H, dqkv + 2 * H, 3 * H, s.cu, B, s.frames, rows, w->heads, w->heads, 64,
-                       0.125f, 0, nullptr, stream));
-    }
-    RC(colsum_accum(b.dbig, 1, G.bqkv, rows, 3 * H, stream));
-    RC(layernorm_fwd(h_in, 0, Ly.ln1_g, Ly.ln1_b, eps, 0, b.xn, rows, H, stream));
-    RC(wgrad(b.dbig, b.xn, rows, 3 * H, H, G.wqkv, stream));
-    RC(dgrad(b.dbig, Ly.wqkv, rows, 3 * H, H, EPI_BF16, b.dsm, stream));
-    RC(layernorm_bwd_ex(h_in, 0, Ly.ln1_g, Ly.ln1_b, 0, eps, b.dsm, 1, b.dh, 1, b.dyb, G.ln1_g, G.ln1_b, rows, H, stream));
-  }
+  // ---- projector + AvgPool + final LayerNorm, then the transformer layers last to first
+  StackBufs sb{s.h, s.h_mid, s.lse, s.qkv, s.ao, s.ff_pre, s.ff};
+  StackScratch sc{b.dh, b.delta, b.dyb, b.dbig, b.dsm, b.xn};
+  RC(head_backward(w->proj_w, w->final_ln_g, w->final_ln_b, gr->proj_w, gr->proj_b, gr->final_ln_g, gr->final_ln_b,
+                   s.h + L * rH, s.pooled_x, d_audio_embeds, b.da, b.dpool, b.dxn_f, sc, B, s.frames, s.pooled, H, Cl,
+                   w->pool_kernel, w->pool_stride, eps, stream));
+  RC(stack_backward(w->layers, gr->layers, L, H, F, w->heads, eps, sb, sc, s.cu, B, s.frames, stream));
 
   // ---- positional conv embedding: h0 = hp + gelu(conv(hp) + b); dh / dyb = gradient w.r.t. h0
   RC(gelu_bwd(s.pos_pre, b.dyb, b.dsm, rows * H, stream));  // dsm = d(pre-GELU conv output), bf16
@@ -535,6 +579,269 @@ int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const 
   }
   RC(conv0_bwd(wave, wave_stride, B, samples, w->conv0_w, w->conv0_b, w->conv0_ln_g, w->conv0_ln_b, eps, dcur, s.t[1],
                gr->conv0_w, gr->conv0_b, gr->conv0_ln_g, gr->conv0_ln_b, stream));
+  return B2S_OK;
+}
+
+// ================================================================================================ Whisper
+// Same training path for AudioEncoder(base="whisper") (REF/config/llama3_whisper.yaml trains it the same way):
+// conv1 (k3, pad 1) + GELU -> conv2 (k3, stride 2, pad 1) + GELU + frozen sinusoid table -> the shared pre-LN stack ->
+// final LN + AvgPool + projector (TF/models/whisper/modeling_whisper.py:593-647). The positional table is frozen
+// (requires_grad False in HF), k_proj has no bias (its slot of the fused-QKV bias gradient is discarded by the caller).
+namespace {
+
+struct WSaved {
+  int frames_in, frames, pooled;
+  void* x0;       // bf16 [B, T+2, mel]  zero-padded channels-last log-mel
+  void* x1;       // bf16 [B, T+2, H]    zero-padded gelu(conv1)
+  void* pre1;     // bf16 [B, T+2, H]    conv1 output before GELU (same geometry as x1)
+  void* pre2;     // bf16 [B*frames, H]  conv2 output before GELU
+  float *h, *h_mid, *lse;
+  void *qkv, *ao, *ff_pre, *ff, *pooled_x, *xn;
+  int* cu;
+  size_t bytes;
+};
+
+void plan_wsaved(const b2s_whisper_weights* w, int batches, void* ws, size_t cap, WSaved* s) {
+  s->frames_in = 2 * w->max_positions;
+  s->frames = w->max_positions;
+  s->pooled = s->frames >= w->pool_kernel ? (s->frames - w->pool_kernel) / w->pool_stride + 1 : 0;
+  const size_t B = batches, H = w->hidden, F = w->ffn, L = w->num_layers, T = s->frames_in;
+  const size_t rows = B * s->frames;
+  Carve c(ws, cap);
+  s->x0 = c.take(B * (T + 2) * w->mel_bins * 2 + 4096);
+  s->x1 = c.take(B * (T + 2) * H * 2 + 4096);
+  s->pre1 = c.take(B * (T + 2) * H * 2 + 4096);
+  s->pre2 = c.take(rows * H * 2 + 4096);
+  s->h = reinterpret_cast<float*>(c.take((L + 1) * rows * H * 4));
+  s->h_mid = reinterpret_cast<float*>(c.take(L * rows * H * 4));
+  s->qkv = c.take(L * rows * 3 * H * 2);
+  s->ao = c.take(L * rows * H * 2);
+  s->lse = reinterpret_cast<float*>(c.take(L * rows * w->heads * 4));
+  s->ff_pre = c.take(L * rows * F * 2);
+  s->ff = c.take(L * rows * F * 2);
+  s->pooled_x = c.take(B * (s->pooled > 0 ? s->pooled : 1) * H * 2);
+  s->xn = c.take(rows * H * 2 + 4096);
+  s->cu = reinterpret_cast<int*>(c.take((B + 1) * sizeof(int)));
+  s->bytes = c.off + 256;
+}
+
+struct WBwdWs {
+  float *dh, *dxn_f, *dpool, *delta;
+  void *dyb, *dbig, *dsm, *xn, *da, *dpre2, *dcol, *dx1;
+  size_t bytes;
+};
+
+void plan_wbwd(const b2s_whisper_weights* w, int batches, const WSaved& s, void* ws, size_t cap, WBwdWs* p) {
+  const size_t B = batches, H = w->hidden, F = w->ffn, T = s.frames_in;
+  const size_t rows = B * s.frames;
+  const size_t big = F > 3 * H ? F : 3 * H;
+  const size_t np = B * (s.pooled > 0 ? s.pooled : 1);
+  Carve c(ws, cap);
+  p->dh = reinterpret_cast<float*>(c.take(rows * H * 4));
+  p->dxn_f = reinterpret_cast<float*>(c.take(rows * H * 4));
+  p->dpool = reinterpret_cast<float*>(c.take(np * H * 4));
+  p->delta = reinterpret_cast<float*>(c.take(rows * w->heads * 4));
+  p->dyb = c.take(rows * H * 2 + 4096);
+  p->dbig = c.take(rows * big * 2 + 4096);
+  p->dsm = c.take(rows * H * 2 + 4096);
+  p->xn = c.take(rows * H * 2 + 4096);
+  p->da = c.take(np * w->llm_dim * 2 + 4096);
+  p->dpre2 = c.take(rows * H * 2 + 4096);
+  p->dcol = c.take(rows * 3 * H * 2 + 4096);
+  p->dx1 = c.take(B * (T + 2) * H * 2 + 4096);
+  p->bytes = c.off + 256;
+}
+
+}  // namespace
+
+size_t whisper_saved_bytes(const b2s_whisper_weights* w, int batches) {
+  if (w == nullptr || batches <= 0) return 0;
+  WSaved s;
+  plan_wsaved(w, batches, nullptr, 0, &s);
+  return s.bytes;
+}
+
+size_t whisper_backward_workspace_bytes(const b2s_whisper_weights* w, int batches) {
+  if (w == nullptr || batches <= 0) return 0;
+  WSaved s;
+  plan_wsaved(w, batches, nullptr, 0, &s);
+  WBwdWs b;
+  plan_wbwd(w, batches, s, nullptr, 0, &b);
+  return b.bytes;
+}
+
+int whisper_forward_train(const b2s_whisper_weights* w, const float* mel, int batches, int frames_in, void* saved,
+                          size_t saved_bytes, float* audio_embeds, cudaStream_t stream) {
+  B2S_REQUIRE(w && mel && saved && audio_embeds, "whisper_forward_train: null pointer");
+  B2S_REQUIRE(batches > 0, "whisper_forward_train: empty batch");
+  B2S_REQUIRE(frames_in == 2 * w->max_positions,
+              "Whisper expects the mel input features to be of length %d, but found %d", 2 * w->max_positions,
+              frames_in);
+  B2S_REQUIRE(w->hidden % 256 == 0 && w->hidden / w->heads == 64 && w->mel_bins % 8 == 0,
+              "whisper_forward_train: hidden %% 256, head_dim 64 and mel_bins %% 8 required");
+  WSaved s;
+  plan_wsaved(w, batches, saved, saved_bytes, &s);
+  B2S_REQUIRE(s.bytes <= saved_bytes && s.pooled > 0, "whisper_forward_train: saved region too small (%zu < %zu)",
+              saved_bytes, s.bytes);
+  const int B = batches, H = w->hidden, F = w->ffn, C = w->mel_bins, T = frames_in, L = w->num_layers;
+  const long long rows = static_cast<long long>(B) * s.frames;
+
+  RC(mel_to_padded_cl(mel, s.x0, B, C, T, stream));
+  B2S_CUDA_CHECK(cudaMemsetAsync(s.x1, 0, static_cast<size_t>(B) * (T + 2) * H * 2, stream));
+  B2S_CUDA_CHECK(cudaMemsetAsync(s.pre1, 0, static_cast<size_t>(B) * (T + 2) * H * 2, stream));
+  {
+    GemmArgs g{};
+    g.A = s.x0;
+    g.a_dim0 = 3 * C;
+    g.a_row_stride = C;
+    g.a_batch_stride = static_cast<long long>(T + 2) * C;
+    g.a_rows = T;
+    g.W = w->conv1_w;
+    g.w_rows = H;
+    g.w_cols = 3 * C;
+    g.M = T;
+    g.N = H;
+    g.batches = B;
+    g.groups = 1;
+    g.taps = 1;
+    g.k_per_tap = 3 * C;
+    g.epi = EPI_BF16;
+    g.act = ACT_GELU;
+    g.bias = w->conv1_b;
+    g.out = reinterpret_cast<__nv_bfloat16*>(s.x1) + H;
+    g.ldo = H;
+    g.out_batch_rows = T + 2;
+    g.out2 = reinterpret_cast<__nv_bfloat16*>(s.pre1) + H;
+    g.ld2 = H;
+    RC(gemm_bf16_launch(g, stream));
+  }
+  {
+    GemmArgs g{};
+    g.A = s.x1;
+    g.a_dim0 = 3 * H;
+    g.a_row_stride = 2LL * H;
+    g.a_batch_stride = static_cast<long long>(T + 2) * H;
+    g.a_rows = s.frames;
+    g.W = w->conv2_w;
+    g.w_rows = H;
+    g.w_cols = 3 * H;
+    g.M = s.frames;
+    g.N = H;
+    g.batches = B;
+    g.groups = 1;
+    g.taps = 1;
+    g.k_per_tap = 3 * H;
+    g.epi = EPI_RESID_F32;
+    g.act = ACT_GELU;
+    g.bias = w->conv2_b;
+    g.out = s.h;
+    g.resid = w->pos_emb;
+    g.resid_bcast = 1;
+    g.ldo = H;
+    g.out_batch_rows = s.frames;
+    g.out2 = s.pre2;
+    g.ld2 = H;
+    RC(gemm_bf16_launch(g, stream));
+  }
+  iota_scaled<<<(B + 1 + 255) / 256, 256, 0, stream>>>(s.cu, B + 1, s.frames);
+  B2S_LAUNCH_CHECK();
+  StackBufs sb{s.h, s.h_mid, s.lse, s.qkv, s.ao, s.ff_pre, s.ff};
+  RC(stack_forward_train(w->layers, L, H, F, w->heads, w->ln_eps, sb, s.xn, s.cu, B, s.frames, stream));
+  RC(layernorm_avgpool_fwd(s.h + static_cast<size_t>(L) * rows * H, w->final_ln_g, w->final_ln_b, w->ln_eps, s.pooled_x,
+                           B, s.frames, H, w->pool_kernel, w->pool_stride, s.pooled, stream));
+  {
+    GemmArgs g = lin(s.pooled_x, w->proj_w, static_cast<long long>(B) * s.pooled, w->llm_dim, H);
+    g.epi = EPI_F32;
+    g.bias = w->proj_b;
+    g.out = audio_embeds;
+    RC(gemm_bf16_launch(g, stream));
+  }
+  return B2S_OK;
+}
+
+int whisper_backward(const b2s_whisper_weights* w, const b2s_whisper_grads* gr, int batches, void* saved,
+                     size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
+  B2S_REQUIRE(w && gr && gr->layers && saved && d_audio_embeds && workspace, "whisper_backward: null pointer");
+  WSaved s;
+  plan_wsaved(w, batches, saved, saved_bytes, &s);
+  B2S_REQUIRE(s.bytes <= saved_bytes && s.pooled > 0, "whisper_backward: bad saved region");
+  WBwdWs b;
+  plan_wbwd(w, batches, s, workspace, workspace_bytes, &b);
+  B2S_REQUIRE(b.bytes <= workspace_bytes, "whisper_backward: workspace too small: need %zu bytes, got %zu", b.bytes,
+              workspace_bytes);
+  const int B = batches, H = w->hidden, F = w->ffn, C = w->mel_bins, T = s.frames_in, L = w->num_layers;
+  const long long rows = static_cast<long long>(B) * s.frames;
+  const size_t rH = static_cast<size_t>(rows) * H;
+  StackBufs sb{s.h, s.h_mid, s.lse, s.qkv, s.ao, s.ff_pre, s.ff};
+  StackScratch sc{b.dh, b.delta, b.dyb, b.dbig, b.dsm, b.xn};
+  RC(head_backward(w->proj_w, w->final_ln_g, w->final_ln_b, gr->proj_w, gr->proj_b, gr->final_ln_g, gr->final_ln_b,
+                   s.h + L * rH, s.pooled_x, d_audio_embeds, b.da, b.dpool, b.dxn_f, sc, B, s.frames, s.pooled, H,
+                   w->llm_dim, w->pool_kernel, w->pool_stride, w->ln_eps, stream));
+  RC(stack_backward(w->layers, gr->layers, L, H, F, w->heads, w->ln_eps, sb, sc, s.cu, B, s.frames, stream));
+  // ---- conv2: h0 = gelu(conv2(x1) + b2) + pos (pos frozen); dyb = bf16 d(loss)/d(h0)
+  RC(gelu_bwd(s.pre2, b.dyb, b.dpre2, rows * H, stream));
+  RC(colsum_accum(b.dpre2, 1, gr->conv2_b, rows, H, stream));
+  {
+    GemmArgs g{};  // dW2[o, (j, c)] += sum_{b,t} dpre2[b,t,o] * x1p[b, 2t + j, c]
+    g.A = b.dpre2;
+    g.a_dim0 = H;
+    g.a_row_stride = H;
+    g.a_batch_stride = static_cast<long long>(s.frames) * H;
+    g.a_rows = s.frames;
+    g.a_mn = 1;
+    g.W = s.x1;
+    g.w_rows = s.frames;
+    g.w_cols = 3 * H;
+    g.w_row_stride = 2LL * H;
+    g.w_batch_stride = static_cast<long long>(T + 2) * H;
+    g.b_mn = 1;
+    g.M = H;
+    g.N = 3 * H;
+    g.batches = 1;
+    g.groups = 1;
+    g.taps = 1;
+    g.k_per_tap = s.frames;
+    g.k_batches = B;
+    g.epi = EPI_ACCUM_F32;
+    g.out = gr->conv2_w;
+    g.ldo = 3LL * H;
+    RC(gemm_bf16_launch(g, stream));
+  }
+  RC(dgrad(b.dpre2, w->conv2_w, rows, H, 3 * H, EPI_BF16, b.dcol, stream));
+  RC(col2im_add(b.dcol, b.dx1, B, T + 2, s.frames, 3, 2, H, stream));  // gradient on the PADDED x1 rows
+  // ---- conv1: x1 = gelu(conv1(x0) + b1); the two padding rows of every utterance carry no gradient
+  RC(gelu_bwd(s.pre1, b.dx1, b.dx1, static_cast<long long>(B) * (T + 2) * H, stream));
+  B2S_CUDA_CHECK(cudaMemset2DAsync(b.dx1, static_cast<size_t>(T + 2) * H * 2, 0, static_cast<size_t>(H) * 2, B, stream));
+  B2S_CUDA_CHECK(cudaMemset2DAsync(reinterpret_cast<__nv_bfloat16*>(b.dx1) + static_cast<size_t>(T + 1) * H,
+                                   static_cast<size_t>(T + 2) * H * 2, 0, static_cast<size_t>(H) * 2, B, stream));
+  RC(colsum_accum(b.dx1, 1, gr->conv1_b, static_cast<long long>(B) * (T + 2), H, stream));
+  {
+    GemmArgs g{};  // dW1[o, (j, c)] += sum_{b,t} dpre1[b,t,o] * x0p[b, t + j, c]
+    g.A = reinterpret_cast<__nv_bfloat16*>(b.dx1) + H;
+    g.a_dim0 = H;
+    g.a_row_stride = H;
+    g.a_batch_stride = static_cast<long long>(T + 2) * H;
+    g.a_rows = T;
+    g.a_mn = 1;
+    g.W = s.x0;
+    g.w_rows = T;
+    g.w_cols = 3 * C;
+    g.w_row_stride = C;
+    g.w_batch_stride = static_cast<long long>(T + 2) * C;
+    g.b_mn = 1;
+    g.M = H;
+    g.N = 3 * C;
+    g.batches = 1;
+    g.groups = 1;
+    g.taps = 1;
+    g.k_per_tap = T;
+    g.k_batches = B;
+    g.epi = EPI_ACCUM_F32;
+    g.out = gr->conv1_w;
+    g.ldo = 3LL * C;
+    RC(gemm_bf16_launch(g, stream));
+  }
   return B2S_OK;
 }
 

@@ -424,21 +424,21 @@ class AudioEncoder(nn.Module):
     def flat_param_order(self):
         """Parameter order for a flat optimizer buffer that makes q|k|v weights (and biases) of every layer adjacent,
         so the fused-QKV gradient [3H, H] the kernels produce IS the concatenation of the three `.grad` views."""
-        if self.encoder_base != "hubert":
-            return list(self.parameters())
         order, seen = [], set()
 
         def push(p):
-            if id(p) not in seen:
+            if p is not None and id(p) not in seen:
                 seen.add(id(p))
                 order.append(p)
 
-        for lay in self.encoder.encoder.layers:
-            a = lay.attention
+        hubert = self.encoder_base == "hubert"
+        for lay in (self.encoder.encoder.layers if hubert else self.encoder.layers):
+            a = lay.attention if hubert else lay.self_attn
             for proj in (a.q_proj, a.k_proj, a.v_proj):
                 push(proj.weight)
-            for proj in (a.q_proj, a.k_proj, a.v_proj):
-                push(proj.bias)
+            if hubert:  # Whisper's k_proj has no bias: its fused bias gradient goes through scratch
+                for proj in (a.q_proj, a.k_proj, a.v_proj):
+                    push(proj.bias)
         for p in self.parameters():
             push(p)
         return order
@@ -446,6 +446,8 @@ class AudioEncoder(nn.Module):
     def _grad_spec(self):
         """(buffer name, packed shape, parameters that tile the buffer row-wise) for every accumulator whose packed
         layout equals the parameters' own layout (everything except the conv weights and the weight-normed pos conv)."""
+        if self.encoder_base == "whisper":
+            return self._grad_spec_whisper()
         enc = self.encoder
         arch = enc.arch
         H, F_ = arch.hidden, arch.ffn
@@ -473,13 +475,31 @@ class AudioEncoder(nn.Module):
                      (f"l{l}.w2", (H, F_), [ff.output_dense.weight]), (f"l{l}.b2", (H,), [ff.output_dense.bias])]
         return spec
 
+    def _grad_spec_whisper(self):
+        enc = self.encoder
+        arch = enc.arch
+        H, F_ = arch.hidden, arch.ffn
+        C_ = self.embed_projection.out_features
+        spec = [("conv1_b", (H,), [enc.conv1.bias]), ("conv2_b", (H,), [enc.conv2.bias]),
+                ("final_ln_g", (H,), [enc.layer_norm.weight]), ("final_ln_b", (H,), [enc.layer_norm.bias]),
+                ("proj_w", (C_, H), [self.embed_projection.weight]), ("proj_b", (C_,), [self.embed_projection.bias])]
+        for l, lay in enumerate(enc.layers):
+            a = lay.self_attn
+            spec += [(f"l{l}.ln1_g", (H,), [lay.self_attn_layer_norm.weight]),
+                     (f"l{l}.ln1_b", (H,), [lay.self_attn_layer_norm.bias]),
+                     (f"l{l}.wqkv", (3 * H, H), [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight]),
+                     (f"l{l}.wo", (H, H), [a.out_proj.weight]), (f"l{l}.bo", (H,), [a.out_proj.bias]),
+                     (f"l{l}.ln2_g", (H,), [lay.final_layer_norm.weight]), (f"l{l}.ln2_b", (H,), [lay.final_layer_norm.bias]),
+                     (f"l{l}.w1", (F_, H), [lay.fc1.weight]), (f"l{l}.b1", (F_,), [lay.fc1.bias]),
+                     (f"l{l}.w2", (H, F_), [lay.fc2.weight]), (f"l{l}.b2", (H,), [lay.fc2.bias])]
+        return spec
+
     def _grad_buffers(self):
         """fp32 gradient accumulators in the kernels' packed layouts (include/b2s.h: b2s_hubert_grads). When the
         parameters already own fp32 `.grad` tensors laid out like the packed buffer (a flat optimizer buffer in
         `flat_param_order`), the kernels accumulate straight into them; otherwise into scratch that `flush_grads`
         adds to `.grad`."""
-        if self.encoder_base != "hubert":
-            raise NotImplementedError("the training backward is built for the HuBERT encoder")
+        hubert = self.encoder_base == "hubert"
         key = tuple(0 if p.grad is None else p.grad.data_ptr() for p in self.parameters())
         if self._grads is not None and self._grads[3] == key:
             return self._grads
@@ -509,18 +529,28 @@ class AudioEncoder(nn.Module):
                 pending.append((name, ps))
                 d = scratch[name].data_ptr()
             ptr[name] = d
-        scratch["pos_w"] = z(H, arch.pos_k * (H // arch.pos_groups))
-        ptr["pos_w"] = scratch["pos_w"].data_ptr()
-        for i in range(6):
-            scratch[f"conv_w{i}"] = z(512, arch.conv_kernel[i + 1] * 512)
-            ptr[f"conv_w{i}"] = scratch[f"conv_w{i}"].data_ptr()
-        g = _lib.HubertGrads()
-        for k in ("conv0_w", "conv0_b", "conv0_ln_g", "conv0_ln_b", "fp_ln_g", "fp_ln_b", "fp_w", "fp_b", "pos_w",
-                  "pos_b", "final_ln_g", "final_ln_b", "proj_w", "proj_b"):
+        if hubert:
+            scratch["pos_w"] = z(H, arch.pos_k * (H // arch.pos_groups))
+            for i in range(6):
+                scratch[f"conv_w{i}"] = z(512, arch.conv_kernel[i + 1] * 512)
+            g = _lib.HubertGrads()
+            names = ("conv0_w", "conv0_b", "conv0_ln_g", "conv0_ln_b", "fp_ln_g", "fp_ln_b", "fp_w", "fp_b", "pos_w",
+                     "pos_b", "final_ln_g", "final_ln_b", "proj_w", "proj_b")
+        else:
+            scratch["conv1_w"] = z(H, 3 * arch.mel_bins)
+            scratch["conv2_w"] = z(H, 3 * H)
+            for l in range(L):  # q | (no k bias) | v
+                scratch[f"l{l}.bqkv"] = z(3 * H)
+            g = _lib.WhisperGrads()
+            names = ("conv1_w", "conv1_b", "conv2_w", "conv2_b", "final_ln_g", "final_ln_b", "proj_w", "proj_b")
+        for k, v in scratch.items():
+            ptr.setdefault(k, v.data_ptr())
+        for k in names:
             setattr(g, k, ptr[k])
-        for i in range(6):
-            g.conv_w[i], g.conv_b[i] = ptr[f"conv_w{i}"], ptr[f"conv_b{i}"]
-            g.conv_ln_g[i], g.conv_ln_b[i] = ptr[f"conv_ln_g{i}"], ptr[f"conv_ln_b{i}"]
+        if hubert:
+            for i in range(6):
+                g.conv_w[i], g.conv_b[i] = ptr[f"conv_w{i}"], ptr[f"conv_b{i}"]
+                g.conv_ln_g[i], g.conv_ln_b[i] = ptr[f"conv_ln_g{i}"], ptr[f"conv_ln_b{i}"]
         layers = (_lib.EncoderLayerGrads * L)()
         for l in range(L):
             for k in ("ln1_g", "ln1_b", "wqkv", "bqkv", "wo", "bo", "ln2_g", "ln2_b", "w1", "b1", "w2", "b2"):
@@ -534,8 +564,8 @@ class AudioEncoder(nn.Module):
         for `backward`. Deterministic: dropout / LayerDrop / SpecAugment of the HF train mode are not applied."""
         if not input.is_cuda:
             raise RuntimeError("AudioEncoder.forward_train (B200 path) needs a CUDA input; there is no CPU path")
-        if self.encoder_base != "hubert":
-            raise NotImplementedError("the training backward is built for the HuBERT encoder")
+        if self.encoder_base == "whisper":
+            return self._whisper_forward_train(input)
         w = self.pack_weights()[0]
         wave = input.to(torch.float32)
         if wave.dim() != 2:
@@ -557,6 +587,30 @@ class AudioEncoder(nn.Module):
         self._train_ctx = ctx
         return out
 
+    def _whisper_forward_train(self, input: torch.Tensor) -> torch.Tensor:
+        """(B, mel_bins, 2*max_positions) log-mel features -> fp32 (B, pooled, llm_dim), activations kept."""
+        w = self.pack_weights()[0]
+        mel = input.to(torch.float32).contiguous()
+        if mel.dim() != 3 or mel.shape[1] != w.mel_bins:
+            raise ValueError(f"expected (B, {w.mel_bins}, T) log-mel features")
+        B, _, T = mel.shape
+        if T != 2 * w.max_positions:
+            raise ValueError(f"Whisper expects the mel input features to be of length {2 * w.max_positions}, but "
+                             f"found {T}. Make sure to pad the input mel features to {2 * w.max_positions}.")
+        pooled = (w.max_positions - w.pool_kernel) // w.pool_stride + 1
+        lib = _lib.load()
+        nbytes = lib.b2s_whisper_saved_bytes(C.byref(w), B)
+        ctx = self._train_ctx
+        if ctx is None or ctx["saved"].numel() < nbytes:
+            ctx = {"saved": torch.empty(nbytes, device=mel.device, dtype=torch.uint8)}
+        out = torch.empty(B, pooled, w.llm_dim, device=mel.device, dtype=torch.float32)
+        _lib.check(lib.b2s_whisper_forward_train(C.byref(w), mel.data_ptr(), B, T, ctx["saved"].data_ptr(),
+                                                 ctx["saved"].numel(), out.data_ptr(),
+                                                 torch.cuda.current_stream().cuda_stream), "whisper_forward_train")
+        ctx.update(wave=mel, B=B, T0=T, pooled=pooled)
+        self._train_ctx = ctx
+        return out
+
     def backward(self, d_audio_embeds: torch.Tensor) -> None:
         """Accumulate d(loss)/d(parameters) for the last `forward_train` batch given d(loss)/d(audio_embeds)
         (fp32 (B, A, llm_dim)). Gradients stay in packed accumulators until `flush_grads`."""
@@ -568,6 +622,17 @@ class AudioEncoder(nn.Module):
         g = self._grad_buffers()[0]
         d = d_audio_embeds.to(torch.float32).contiguous()
         assert d.shape == (ctx["B"], ctx["pooled"], w.llm_dim), "d_audio_embeds shape mismatch"
+        if self.encoder_base == "whisper":
+            lib = _lib.load()
+            nbytes = lib.b2s_whisper_backward_workspace_bytes(C.byref(w), ctx["B"])
+            if ctx.get("bws") is None or ctx["bws"].numel() < nbytes:
+                ctx["bws"] = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
+            _lib.check(lib.b2s_whisper_backward(C.byref(w), C.byref(g), ctx["B"], ctx["saved"].data_ptr(),
+                                                ctx["saved"].numel(), d.data_ptr(), ctx["bws"].data_ptr(),
+                                                ctx["bws"].numel(), torch.cuda.current_stream().cuda_stream),
+                       "whisper_backward")
+            del ctx["wave"]
+            return
         if self._pos_w_dgrad is None:
             G, K_, cg = arch.pos_groups, arch.pos_k, arch.hidden // arch.pos_groups
             # conv transpose: taps reversed, each (out, in) block transposed: [g*cg+o][j][i] -> [g*cg+i][K-1-j][o]
@@ -608,6 +673,15 @@ class AudioEncoder(nn.Module):
                 n = p.shape[0]
                 add(p, t[name][row:row + n])
                 row += n
+        if self.encoder_base == "whisper":
+            add(enc.conv1.weight, t["conv1_w"].view(H, 3, arch.mel_bins).permute(0, 2, 1))
+            add(enc.conv2.weight, t["conv2_w"].view(H, 3, H).permute(0, 2, 1))
+            for l, lay in enumerate(enc.layers):  # fused bias gradient: q | (k_proj has no bias) | v
+                add(lay.self_attn.q_proj.bias, t[f"l{l}.bqkv"][:H])
+                add(lay.self_attn.v_proj.bias, t[f"l{l}.bqkv"][2 * H:])
+            for buf in t.values():
+                buf.zero_()
+            return
         fe = enc.feature_extractor.conv_layers
         for i in range(6):
             k = arch.conv_kernel[i + 1]

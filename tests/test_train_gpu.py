@@ -200,3 +200,38 @@ def test_trainer_accumulates_and_matches_torch_adamw(cuda):
     tr.load_checkpoint(legacy)
     after = enc.state_dict()
     assert all(torch.equal(before[k], after[k]) for k in before)
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_whisper_encoder_backward_matches_oracle_autograd(cuda, B):
+    """AudioEncoder(base="whisper") training path: per-parameter gradients of sum(audio_embeds * R) vs oracle autograd
+    (conv1 / conv2 with their GELUs, the shared pre-LN stack, final LN + pool + projector; frozen sinusoid table)."""
+    from oracle import configs, reference_math as rm
+    from helpers import ns_config_whisper
+    from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
+    cfg = configs.TINY_WHISPER
+    sd0 = configs.make_whisper_state_dict(cfg, seed=6)
+    enc = AudioEncoder(ns_config_whisper(cfg), cuda)
+    enc.load_state_dict(sd0, strict=True)
+    enc.eval().to(cuda)
+    mel = configs.synthetic_log_mel(cfg, 3, batch=B)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "embed_positions" not in k else v)
+          for k, v in sd0.items()}
+    out_ref = rm.audio_encoder_forward_whisper(sd, mel, cfg)
+    R = torch.randn(out_ref.shape, generator=torch.Generator().manual_seed(1))
+    names = [k for k, v in sd.items() if torch.is_tensor(v) and v.requires_grad]
+    grads = torch.autograd.grad((out_ref * R).sum(), [sd[k] for k in names], allow_unused=True)
+    ref = {k: g for k, g in zip(names, grads) if g is not None}
+    out = enc.forward_train(mel.to(cuda))
+    assert rel_l2(out.cpu(), out_ref.detach()) < 2e-2
+    enc.backward(R.to(cuda))
+    enc.flush_grads()
+    got = {k: p.grad for k, p in enc.named_parameters() if p.grad is not None}
+    assert "encoder.embed_positions.weight" not in got
+    bad = {}
+    for k, gr in ref.items():
+        assert k in got, k
+        e = rel_l2(got[k].cpu().float(), gr)
+        if e > 4e-2:
+            bad[k] = e
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:10]
