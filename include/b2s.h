@@ -359,16 +359,37 @@ typedef struct {
 } b2s_hubert_grads;
 size_t b2s_hubert_saved_bytes(const b2s_hubert_weights* w, int32_t batches, int32_t samples);
 size_t b2s_hubert_backward_workspace_bytes(const b2s_hubert_weights* w, int32_t batches, int32_t samples);
-/* b2s_hubert_forward keeping every activation the backward needs in `saved` (deterministic: no dropout / LayerDrop /
- * SpecAugment, TF/models/hubert/modeling_hubert.py:596-599,842-886). */
+/* Train-mode regularisers of HubertModel (REF/trainer.py:258 puts the encoder in .train()): the nn.Dropout sites of
+ * TF/models/hubert/modeling_hubert.py (:223-230 feature projection, :585-587 after hidden + positional conv, :254
+ * attention probabilities, :383-393 / :536 after the attention block, :351-368 FFN activation and output), LayerDrop
+ * (:596-599) and SpecAugment time masking (:842-886). Keep / drop decisions are a pure function of
+ * (seed, site, element index) -- csrc/rng.cuh, restated in oracle/regularizers.py -- so forward and backward take the
+ * SAME block and no mask is stored. LayerDrop decisions and the SpecAugment frame mask are drawn by the caller (the
+ * reference draws both on the host: torch.rand([]) per layer, numpy in _compute_mask_indices). NULL = eval behaviour. */
+typedef struct {
+  uint64_t seed;                  /* one value per micro-batch */
+  float p_feat_proj;              /* config.feat_proj_dropout */
+  float p_hidden;                 /* config.hidden_dropout */
+  float p_attention;              /* config.attention_dropout */
+  float p_activation;             /* config.activation_dropout */
+  const uint8_t* layer_skip;      /* HOST [num_layers], 1 = LayerDrop skips the layer; NULL = none */
+  const uint8_t* time_mask;       /* DEVICE [batches*frames], 1 = frame replaced by masked_spec_embed; NULL = none */
+  const float* masked_spec_embed; /* DEVICE fp32 [hidden] (required with time_mask) */
+  float* g_masked_spec_embed;     /* DEVICE fp32 [hidden] gradient accumulator (backward only; may be NULL) */
+} b2s_encoder_regularizers;
+/* b2s_hubert_forward keeping every activation the backward needs in `saved`; reg = NULL: deterministic (eval) math. */
 int b2s_hubert_forward_train(const b2s_hubert_weights* w, const float* wave, int64_t wave_stride, int32_t batches,
-                             int32_t samples, void* saved, size_t saved_bytes, float* audio_embeds, void* stream);
+                             int32_t samples, void* saved, size_t saved_bytes, float* audio_embeds,
+                             const b2s_encoder_regularizers* reg, void* stream);
+/* test hook: out[i] = 1 if element e_first + i of stream (seed, site, a, b) is KEPT at drop probability p */
+int b2s_drop_mask_dump(uint8_t* out, int64_t n, uint64_t seed, uint32_t site, uint32_t a, uint32_t b, float p,
+                       uint32_t e_first, void* stream);
 /* d_audio_embeds fp32 [batches*pooled, llm_dim] -> grads (+=). pos_w_dgrad: bf16 [H][k][H/groups], the packed
  * positional-conv weight with taps reversed and each (out, in) block transposed (the conv's transpose). */
 int b2s_hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* grads,
                         const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, void* saved,
                         size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
-                        void* stream);
+                        const b2s_encoder_regularizers* reg /* the block the forward ran with */, void* stream);
 /* Whisper encoder (REF/config/llama3_whisper.yaml trains it like the HuBERT one): same contract; mel fp32
  * [batches, mel_bins, 2*max_positions]; conv weights' gradients in the packed [H, 3*C_in] layout; the sinusoid table is
  * frozen; the k_proj slot of bqkv's gradient has no parameter behind it. */

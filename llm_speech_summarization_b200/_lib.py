@@ -65,6 +65,12 @@ class HubertGrads(C.Structure):
     ]
 
 
+class EncoderRegularizers(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("p_feat_proj", C.c_float), ("p_hidden", C.c_float), ("p_attention", C.c_float),
+                ("p_activation", C.c_float), ("layer_skip", c_void_p), ("time_mask", c_void_p),
+                ("masked_spec_embed", c_void_p), ("g_masked_spec_embed", c_void_p)]
+
+
 class WhisperGrads(C.Structure):
     _fields_ = [("conv1_w", c_void_p), ("conv1_b", c_void_p), ("conv2_w", c_void_p), ("conv2_b", c_void_p),
                 ("layers", C.POINTER(EncoderLayerGrads)), ("final_ln_g", c_void_p), ("final_ln_b", c_void_p),
@@ -175,9 +181,12 @@ PROTOTYPES = {
     "b2s_hubert_saved_bytes": (C.c_size_t, [C.POINTER(HubertWeights), c_int, c_int]),
     "b2s_hubert_backward_workspace_bytes": (C.c_size_t, [C.POINTER(HubertWeights), c_int, c_int]),
     "b2s_hubert_forward_train": (c_int, [C.POINTER(HubertWeights), c_void_p, c_int64, c_int, c_int, c_void_p,
-                                         C.c_size_t, c_void_p, c_void_p]),
+                                         C.c_size_t, c_void_p, C.POINTER(EncoderRegularizers), c_void_p]),
     "b2s_hubert_backward": (c_int, [C.POINTER(HubertWeights), c_void_p, C.POINTER(HubertGrads), c_void_p, c_int64,
-                                    c_int, c_int, c_void_p, C.c_size_t, c_void_p, c_void_p, C.c_size_t, c_void_p]),
+                                    c_int, c_int, c_void_p, C.c_size_t, c_void_p, c_void_p, C.c_size_t,
+                                    C.POINTER(EncoderRegularizers), c_void_p]),
+    "b2s_drop_mask_dump": (c_int, [c_void_p, c_int64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, c_float,
+                                   C.c_uint32, c_void_p]),
     "b2s_whisper_saved_bytes": (C.c_size_t, [C.POINTER(WhisperWeights), c_int]),
     "b2s_whisper_backward_workspace_bytes": (C.c_size_t, [C.POINTER(WhisperWeights), c_int]),
     "b2s_whisper_forward_train": (c_int, [C.POINTER(WhisperWeights), c_void_p, c_int, c_int, c_void_p, C.c_size_t,

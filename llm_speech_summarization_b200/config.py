@@ -49,6 +49,17 @@ class EncoderArch:
     pos_k: int = 128
     pos_groups: int = 16
     ln_eps: float = 1e-5
+    # train-mode regularisers of facebook/hubert-large-ls960-ft; only read when the training
+    # step runs with regularisers enabled (llm_speech_summarization_b200/regularizers.py)
+    feat_proj_dropout: float = 0.1
+    hidden_dropout: float = 0.1
+    attention_dropout: float = 0.1
+    activation_dropout: float = 0.1
+    layerdrop: float = 0.1
+    apply_spec_augment: bool = True
+    mask_time_prob: float = 0.05
+    mask_time_length: int = 10
+    mask_time_min_masks: int = 2
 
 
 @dataclass

@@ -265,7 +265,7 @@ int launch_attn(const void* q, const void* k, const void* v, long long ld, void*
 // attention_tc.cu
 int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
                      const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
-                     float scale, int causal, float* lse, cudaStream_t stream);
+                     float scale, int causal, float* lse, cudaStream_t stream, const AttnDrop* drop);
 
 namespace {
 int g_attn_impl = 1;  // 1 = tcgen05 / TMEM / TMA kernel (attention_tc.cu), 0 = legacy mma.sync kernel (this file)
@@ -275,8 +275,9 @@ int attention_get_impl() { return g_attn_impl; }
 
 int attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
                   const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
-                  float scale, int causal, float* lse, cudaStream_t stream) {
+                  float scale, int causal, float* lse, cudaStream_t stream, const AttnDrop* drop) {
   B2S_REQUIRE(q && k && v && o && cu_seqlens, "attention_fwd: null pointer");
+  if (drop != nullptr && drop->thresh == 0u) drop = nullptr;
   B2S_REQUIRE(total_rows > 0, "attention_fwd: total_rows must be the row count of the packed q/k/v buffers");
   B2S_REQUIRE(num_seqs > 0 && max_seqlen > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "attention_fwd: bad head counts");
   B2S_REQUIRE(ld_qkv % 8 == 0 && ld_o % 2 == 0, "attention_fwd: strides must keep 16-byte row alignment");
@@ -286,8 +287,9 @@ int attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv,
   if (g_attn_impl == 1 && (D == 64 || D == 128) && (ld_qkv * 2) % 16 == 0 && ld_o % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
     return attention_fwd_tc(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, D, scale,
-                            causal, lse, stream);
+                            causal, lse, stream, drop);
   }
+  B2S_REQUIRE(drop == nullptr, "attention_fwd: attention dropout needs the tcgen05 kernel (impl 1, D = 64 / 128)");
   B2S_REQUIRE(lse == nullptr, "attention_fwd: the log-sum-exp output needs the tcgen05 kernel (impl 1, D = 64 / 128)");
   if (D == 64) return launch_attn<64>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, Hq, Hkv, scale, causal, stream);
   if (D == 128) return launch_attn<128>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, Hq, Hkv, scale, causal, stream);

@@ -417,8 +417,10 @@ int launch_bwd(const BwdParams& p, int num_seqs, int max_seqlen, cudaStream_t st
 int attention_bwd(const void* q, const void* k, const void* v, long long ld_qkv, const void* o, long long ld_o,
                   const void* dout, long long ld_do, const float* lse, float* delta_ws, void* dq, void* dk, void* dv,
                   long long ld_dqkv, const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq,
-                  int Hkv, int D, float scale, int causal, const float* rope_cs, cudaStream_t stream) {
+                  int Hkv, int D, float scale, int causal, const float* rope_cs, cudaStream_t stream,
+                  const AttnDrop* drop) {
   B2S_REQUIRE(q && k && v && o && dout && lse && delta_ws && dq && dk && dv && cu_seqlens, "attention_bwd: null pointer");
+  if (drop != nullptr && drop->thresh == 0u) drop = nullptr;
   B2S_REQUIRE(num_seqs > 0 && max_seqlen > 0 && total_rows > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0,
               "attention_bwd: bad sizes");
   B2S_REQUIRE(ld_qkv % 8 == 0 && ld_do % 8 == 0 && ld_o % 2 == 0 && ld_dqkv % 2 == 0,
@@ -435,8 +437,9 @@ int attention_bwd(const void* q, const void* k, const void* v, long long ld_qkv,
   }
   if (attention_get_impl() == 1) {  // tcgen05 kernels (attention_bwd_tc.cu); 0 keeps the mma.sync kernels below
     return attention_bwd_tc(q, k, v, ld_qkv, dout, ld_do, lse, delta_ws, dq, dk, dv, ld_dqkv, cu_seqlens, num_seqs,
-                            max_seqlen, total_rows, Hq, Hkv, D, scale, causal, rope_cs, stream);
+                            max_seqlen, total_rows, Hq, Hkv, D, scale, causal, rope_cs, stream, drop);
   }
+  B2S_REQUIRE(drop == nullptr, "attention_bwd: attention dropout needs the tcgen05 kernels (impl 1)");
   BwdParams p{};
   p.q = reinterpret_cast<const __nv_bfloat16*>(q);
   p.k = reinterpret_cast<const __nv_bfloat16*>(k);

@@ -42,6 +42,7 @@ struct BwdTcParams {
   float scale, scale_log2;
   int causal;
   const float* rope_cs;  // optional [npos, D]: cos[0:D/2] | sin[0:D/2]
+  AttnDrop drop;         // attention-probability dropout of the forward (thresh 0 = off), regenerated here
 };
 
 __device__ __forceinline__ float ex2b(float x) {
@@ -124,7 +125,9 @@ struct DqCfg {
 };
 
 // ------------------------------------------------------------------------------------------------ dQ
-template <int D>
+// With dropout O = (P o M) V, M = keep / (1 - p): dP = M o (dO V^T), dV = (P o M)^T dO, and delta = rowsum(dO o O) is
+// unchanged (sum_j P_j M_j (dO . V_j) = dO . O), so only the two elementwise stages below see the mask.
+template <int D, bool DROP>
 __global__ void __launch_bounds__(kThreadsB, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                       const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
@@ -247,6 +250,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const float dl = valid ? p.delta[grow * p.Hq + h] : 0.f;
     const int row_limit = valid ? (p.causal ? min(L, qi + 1) : L) : 0;
     const float sc2 = p.scale_log2, sc = p.scale, dls = dl * p.scale;
+    uint32_t dk1 = 0u, dk2 = 0u;
+    if (DROP) rng_stream_key(p.drop.seed, p.drop.site, static_cast<uint32_t>(seq), static_cast<uint32_t>(h), &dk1, &dk2);
+    const uint32_t drow = static_cast<uint32_t>(qi) << 16;
     for (int j = 0; j < nblk; ++j) {
       ptx::mbar_wait(bar_s, j & 1);
       ptx::tc_fence_after();
@@ -260,6 +266,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         ptx::tmem_ld_wait();
         const int nv = nvis - c * 32;
         uint32_t pk[16];
+        if (DROP) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t e = drow | static_cast<uint32_t>(j * kSmall + c * 32 + i);
+            rd[i] = rng_keep(e, dk1, dk2, p.drop.thresh) ? __float_as_uint(__uint_as_float(rd[i]) * p.drop.inv_keep) : 0u;
+          }
+        }
         if (full_blk) {  // every row of the warp sees the whole block: no per-element predicates
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -308,7 +321,7 @@ struct DkvCfg {
   static constexpr int kTmemCols = (D == 64) ? 256 : 512;  // S^T [0,64) dP^T [64,128) dV [128,128+D) dK [128+D,128+2D)
 };
 
-template <int D>
+template <int D, bool DROP>
 __global__ void __launch_bounds__(kThreadsB, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                        const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
@@ -449,6 +462,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the 128 softmax threads only
       // whole tile visible to every key row of this CTA: all keys and queries in range (and, causal, queries >= keys)
       const bool full_blk = (k0 + kBig <= L) && (q0 + kSmall <= L) && (!p.causal || q0 >= k0 + kBig - 1);
+      uint32_t dk1 = 0u, dk2 = 0u;
+      if (DROP) rng_stream_key(p.drop.seed, p.drop.site, static_cast<uint32_t>(seq), static_cast<uint32_t>(hq), &dk1, &dk2);
       ptx::mbar_wait(bar_s, it & 1);
       ptx::tc_fence_after();
 #pragma unroll 1
@@ -458,6 +473,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         ptx::tmem_ld_32x32(tDP + c * 32, rd);
         ptx::tmem_ld_wait();
         uint32_t pp[16], pd[16];
+        float mk[32];  // dropout multiplier of (query q0 + 32c + i, this key); dead code without DROP
+        if (DROP) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t e = (static_cast<uint32_t>(q0 + c * 32 + i) << 16) | static_cast<uint32_t>(key);
+            mk[i] = rng_keep(e, dk1, dk2, p.drop.thresh) ? p.drop.inv_keep : 0.f;
+            rd[i] = __float_as_uint(__uint_as_float(rd[i]) * mk[i]);
+          }
+        }
         if (full_blk) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -465,7 +489,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             const float2 ds = *reinterpret_cast<const float2*>(st_dl + c * 32 + i);   // delta * scale
             const float p0 = ex2b(fmaf(__uint_as_float(rs[i]), sc2, -nl.x));
             const float p1 = ex2b(fmaf(__uint_as_float(rs[i + 1]), sc2, -nl.y));
-            pp[i >> 1] = pack_bf16(p0, p1);
+            pp[i >> 1] = DROP ? pack_bf16(p0 * mk[i], p1 * mk[i + 1]) : pack_bf16(p0, p1);
             pd[i >> 1] = pack_bf16(p0 * fmaf(__uint_as_float(rd[i]), sc, -ds.x),
                                    p1 * fmaf(__uint_as_float(rd[i + 1]), sc, -ds.y));
           }
@@ -479,7 +503,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             const float2 ds = *reinterpret_cast<const float2*>(st_dl + c * 32 + i);
             const float p0 = ok0 ? ex2b(fmaf(__uint_as_float(rs[i]), sc2, -nl.x)) : 0.f;
             const float p1 = ok1 ? ex2b(fmaf(__uint_as_float(rs[i + 1]), sc2, -nl.y)) : 0.f;
-            pp[i >> 1] = pack_bf16(p0, p1);
+            pp[i >> 1] = DROP ? pack_bf16(p0 * mk[i], p1 * mk[i + 1]) : pack_bf16(p0, p1);
             pd[i >> 1] = pack_bf16(p0 * fmaf(__uint_as_float(rd[i]), sc, -ds.x),
                                    p1 * fmaf(__uint_as_float(rd[i + 1]), sc, -ds.y));
           }
@@ -507,11 +531,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   }
 }
 
-template <int D>
+template <int D, bool DROP>
 int launch_bwd_tc(const void* q, const void* k, const void* v, long long ld_qkv, const void* dout, long long ld_do,
                   const BwdTcParams& p, int num_seqs, int max_seqlen, long long total_rows, cudaStream_t stream) {
-  auto kdq = attn_bwd_dq_tc_kernel<D>;
-  auto kdkv = attn_bwd_dkv_tc_kernel<D>;
+  auto kdq = attn_bwd_dq_tc_kernel<D, DROP>;
+  auto kdkv = attn_bwd_dkv_tc_kernel<D, DROP>;
   static bool attr_set = false;
   if (!attr_set) {
     B2S_CUDA_CHECK(cudaFuncSetAttribute(kdq, cudaFuncAttributeMaxDynamicSharedMemorySize, DqCfg<D>::kSmemBytes));
@@ -543,7 +567,7 @@ int launch_bwd_tc(const void* q, const void* k, const void* v, long long ld_qkv,
 int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld_qkv, const void* dout, long long ld_do,
                      const float* lse, const float* delta, void* dq, void* dk, void* dv, long long ld_dqkv,
                      const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
-                     float scale, int causal, const float* rope_cs, cudaStream_t stream) {
+                     float scale, int causal, const float* rope_cs, cudaStream_t stream, const AttnDrop* drop) {
   BwdTcParams p{};
   p.cu = cu_seqlens;
   p.lse = lse;
@@ -558,8 +582,13 @@ int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld_q
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
   p.rope_cs = rope_cs;
-  if (D == 64) return launch_bwd_tc<64>(q, k, v, ld_qkv, dout, ld_do, p, num_seqs, max_seqlen, total_rows, stream);
-  if (D == 128) return launch_bwd_tc<128>(q, k, v, ld_qkv, dout, ld_do, p, num_seqs, max_seqlen, total_rows, stream);
+  if (drop != nullptr && drop->thresh != 0u) {
+    B2S_REQUIRE(D == 64 && max_seqlen < 65536, "attention_bwd_tc: attention dropout supports head_dim 64, seqlen < 65536");
+    p.drop = *drop;
+    return launch_bwd_tc<64, true>(q, k, v, ld_qkv, dout, ld_do, p, num_seqs, max_seqlen, total_rows, stream);
+  }
+  if (D == 64) return launch_bwd_tc<64, false>(q, k, v, ld_qkv, dout, ld_do, p, num_seqs, max_seqlen, total_rows, stream);
+  if (D == 128) return launch_bwd_tc<128, false>(q, k, v, ld_qkv, dout, ld_do, p, num_seqs, max_seqlen, total_rows, stream);
   set_last_error("attention_bwd_tc: head_dim %d unsupported (64 or 128)", D);
   return B2S_ERR_UNSUPPORTED;
 }

@@ -54,6 +54,7 @@ struct AttnParams {
   float scale_log2;
   int causal;
   float* lse;  // optional [rows, Hq]: log2-domain log-sum-exp of the scaled scores (saved for the backward)
+  AttnDrop drop;  // attention-probability dropout (thresh 0 = off): softmax statistics stay those of the un-dropped row
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -75,7 +76,7 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-template <int D, int BN>
+template <int D, int BN, bool DROP>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -193,6 +194,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     float m_ref = -INFINITY;  // log2-domain reference the accumulated O / l are expressed against
     float pend = -INFINITY;   // larger reference to adopt at the next safe point (no PV in flight)
     float l_run = 0.f;
+    uint32_t dk1 = 0u, dk2 = 0u;  // dropout stream of this (sequence, head); element = (query << 16) | key
+    if (DROP) rng_stream_key(p.drop.seed, p.drop.site, static_cast<uint32_t>(seq), static_cast<uint32_t>(h), &dk1, &dk2);
+    const uint32_t drow = static_cast<uint32_t>(qi) << 16;
 
     // adopt `pend` as the new reference where it is larger: rescale l (registers) and O (TMEM); warp-uniform
     auto adopt = [&](bool o_valid) {
@@ -254,8 +258,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             for (int i = 0; i < 32; i += 2) {
               const float x0 = __uint_as_float(raw[i]), x1 = __uint_as_float(raw[i + 1]);
               bmax = fmaxf(bmax, fmaxf(x0, x1));
-              const float p0 = ex2f(fmaf(x0, sc, -mr)), p1 = ex2f(fmaf(x1, sc, -mr));
+              float p0 = ex2f(fmaf(x0, sc, -mr)), p1 = ex2f(fmaf(x1, sc, -mr));
               rs += p0 + p1;
+              if (DROP) {  // the row sum keeps every key; only the P fed to P.V is thinned (1/(1-p) folded into 1/l)
+                const uint32_t e = drow | static_cast<uint32_t>(j * kBN + c * 32 + i);
+                p0 = rng_keep(e, dk1, dk2, p.drop.thresh) ? p0 : 0.f;
+                p1 = rng_keep(e + 1u, dk1, dk2, p.drop.thresh) ? p1 : 0.f;
+              }
               pk[i >> 1] = pack_bf16(p0, p1);
             }
           } else {
@@ -265,9 +274,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
               const float x0 = __uint_as_float(raw[i]), x1 = __uint_as_float(raw[i + 1]);
               const bool ok0 = i < nv, ok1 = i + 1 < nv;
               bmax = fmaxf(bmax, fmaxf(ok0 ? x0 : -INFINITY, ok1 ? x1 : -INFINITY));
-              const float p0 = ok0 ? ex2f(fmaf(x0, sc, -mr)) : 0.f;
-              const float p1 = ok1 ? ex2f(fmaf(x1, sc, -mr)) : 0.f;
+              float p0 = ok0 ? ex2f(fmaf(x0, sc, -mr)) : 0.f;
+              float p1 = ok1 ? ex2f(fmaf(x1, sc, -mr)) : 0.f;
               rs += p0 + p1;
+              if (DROP) {
+                const uint32_t e = drow | static_cast<uint32_t>(j * kBN + c * 32 + i);
+                p0 = rng_keep(e, dk1, dk2, p.drop.thresh) ? p0 : 0.f;
+                p1 = rng_keep(e + 1u, dk1, dk2, p.drop.thresh) ? p1 : 0.f;
+              }
               pk[i >> 1] = pack_bf16(p0, p1);
             }
           }
@@ -300,7 +314,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // epilogue: O / l -> bf16 -> global (one row per thread)
     ptx::mbar_wait(bar_o, (nblk - 1) & 1);
     ptx::tc_fence_after();
-    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    const float inv = (l_run > 0.f ? 1.0f / l_run : 0.f) * (DROP ? p.drop.inv_keep : 1.0f);
     if (p.lse != nullptr && qi < L) p.lse[static_cast<long long>(s0 + qi) * p.Hq + h] = m_ref + log2f(l_run);
     __nv_bfloat16* orow = p.o + static_cast<long long>(s0 + qi) * p.ldo + h * D;
 #pragma unroll 1
@@ -330,13 +344,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   }
 }
 
-template <int D, int BN>
+template <int D, int BN, bool DROP>
 int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, const int* cu,
                    int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, float scale, int causal,
-                   float* lse, cudaStream_t stream) {
+                   float* lse, cudaStream_t stream, const AttnDrop* drop) {
   using C = AttnCfg<D, BN>;
   constexpr int kBN = BN;
-  auto kern = attn_fwd_tc_kernel<D, BN>;
+  auto kern = attn_fwd_tc_kernel<D, BN, DROP>;
   static bool attr_set = false;
   if (!attr_set) {
     B2S_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -359,6 +373,7 @@ int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, vo
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
   p.lse = lse;
+  if (DROP) p.drop = *drop;
   dim3 grid((max_seqlen + kBM - 1) / kBM, Hq, num_seqs);
   kern<<<grid, kThreadsTc, C::kSmemBytes, stream>>>(tq, tk, tv, p);
   B2S_LAUNCH_CHECK();
@@ -369,16 +384,21 @@ int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, vo
 
 int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
                      const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
-                     float scale, int causal, float* lse, cudaStream_t stream) {
+                     float scale, int causal, float* lse, cudaStream_t stream, const AttnDrop* drop) {
+  if (drop != nullptr && drop->thresh != 0u) {  // train-mode HuBERT attention only (TF/.../modeling_hubert.py:254)
+    B2S_REQUIRE(D == 64 && max_seqlen < 65536, "attention_fwd_tc: attention dropout supports head_dim 64, seqlen < 65536");
+    return launch_attn_tc<64, 128, true>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq,
+                                         Hkv, scale, causal, lse, stream, drop);
+  }
   if (D == 64)
-    return launch_attn_tc<64, 128>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv,
-                                   scale, causal, lse, stream);
+    return launch_attn_tc<64, 128, false>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq,
+                                          Hkv, scale, causal, lse, stream, nullptr);
   if (D == 128 && max_seqlen <= 512)  // short prompts: per-CTA latency dominates -> two CTAs per SM
-    return launch_attn_tc<128, 64>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv,
-                                   scale, causal, lse, stream);
+    return launch_attn_tc<128, 64, false>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq,
+                                          Hkv, scale, causal, lse, stream, nullptr);
   if (D == 128)
-    return launch_attn_tc<128, 128>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv,
-                                    scale, causal, lse, stream);
+    return launch_attn_tc<128, 128, false>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq,
+                                           Hkv, scale, causal, lse, stream, nullptr);
   set_last_error("attention_fwd_tc: head_dim %d unsupported (64 or 128)", D);
   return B2S_ERR_UNSUPPORTED;
 }

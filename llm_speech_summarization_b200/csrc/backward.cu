@@ -162,12 +162,17 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __nv_bfloat16* __r
 // erf-GELU backward: dpre = dy * (Phi(x) + x phi(x))
 __global__ void __launch_bounds__(256)
 gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dy,
-                __nv_bfloat16* __restrict__ dpre, long long n8) {
+                __nv_bfloat16* __restrict__ dpre, long long n8, DropSpec drop) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   float x[8], d[8];
   ld8bf(pre + i * 8, x);
   ld8bf(dy + i * 8, d);
+  if (drop.thresh != 0u) {  // dy is the gradient w.r.t. dropout(gelu(pre)): mask first (activation dropout site)
+    const uint32_t e0 = static_cast<uint32_t>(i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = rng_keep(e0 + j, drop.k1, drop.k2, drop.thresh) ? d[j] * drop.inv_keep : 0.f;
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float cdf = 0.5f * (1.0f + erff(x[j] * 0.70710678118654752f));
@@ -289,13 +294,14 @@ int swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows, int 
   return B2S_OK;
 }
 
-int gelu_bwd(const void* pre, const void* dy, void* dpre, long long n, cudaStream_t stream) {
+int gelu_bwd(const void* pre, const void* dy, void* dpre, long long n, cudaStream_t stream, const DropSpec* drop) {
   B2S_REQUIRE(pre && dy && dpre, "gelu_bwd: null pointer");
   B2S_REQUIRE(n % 8 == 0, "gelu_bwd: element count must be a multiple of 8");
+  B2S_REQUIRE(drop == nullptr || n < (1LL << 32), "gelu_bwd: dropout element index exceeds 32 bits");
   if (n <= 0) return B2S_OK;
   gelu_bwd_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<const __nv_bfloat16*>(dy),
-      reinterpret_cast<__nv_bfloat16*>(dpre), n / 8);
+      reinterpret_cast<__nv_bfloat16*>(dpre), n / 8, drop ? *drop : DropSpec{});
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

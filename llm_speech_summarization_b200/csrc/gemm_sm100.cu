@@ -27,6 +27,7 @@
 
 #include "b2s_common.cuh"
 #include "b2s_ptx.cuh"
+#include "rng.cuh"
 
 namespace b2s {
 
@@ -81,6 +82,8 @@ struct KParams {
   int tiles_per_split;
   int b_tap_atoms;        // MN-major B: 64-column atom j of the N axis = the same columns shifted by j - a_pad rows
   int og_rows, og_cols;   // output offset per group: rows += g * og_rows, cols += g * og_cols
+  uint32_t drop_k1, drop_k2, drop_thresh;  // fused dropout (rng.cuh); thresh 0 = off
+  float drop_inv_keep;
 };
 
 struct TileCoord {
@@ -485,6 +488,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             add_bias_act(v, bias ? bias + col : nullptr, p.act);
           }
           const long long off0 = orow0 * p.ldo + static_cast<long long>(tc.g) * og_cols + col;
+          if (EXT && p.drop_thresh != 0u) {  // train-mode dropout: this thread's row, 32 consecutive columns
+            const uint32_t e0 = static_cast<uint32_t>(off0 + static_cast<long long>(lane) * p.ldo);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              v[i] = rng_keep(e0 + i, p.drop_k1, p.drop_k2, p.drop_thresh) ? v[i] * p.drop_inv_keep : 0.f;
+          }
           if (p.epi == EPI_BF16) {
             emit_bf16(stg, v, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, valid);
           } else if (EXT && p.epi == EPI_ACCUM_F32) {
@@ -803,6 +812,15 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   p.rope_cs = a.rope_cs;
   p.positions = a.positions;
   p.rope_cols = a.rope_cols;
+  p.drop_k1 = a.drop_k1;
+  p.drop_k2 = a.drop_k2;
+  p.drop_thresh = a.drop_thresh;
+  p.drop_inv_keep = a.drop_inv_keep;
+  if (a.drop_thresh != 0u) {
+    B2S_REQUIRE(a.epi == EPI_BF16 || a.epi == EPI_F32 || a.epi == EPI_RESID_F32, "gemm: dropout needs a plain epilogue");
+    B2S_REQUIRE(static_cast<long long>(a.batches) * (a.out_batch_rows > 0 ? a.out_batch_rows : a.M) * a.ldo < (1LL << 32),
+                "gemm: dropout element index exceeds 32 bits");
+  }
 
   CUtensorMap ta, tw;
   {
@@ -837,7 +855,7 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   }
 
   const bool ext = mn || a.epi == EPI_ACCUM_F32 || p.k_splits > 1 || a.out2 != nullptr || a.out_group_rows != 0 ||
-                   (a.out_group_cols > 0 && a.out_group_cols != a.N);
+                   (a.out_group_cols > 0 && a.out_group_cols != a.N) || a.drop_thresh != 0u;
   const int mode = a.a_mn ? 3 : (a.b_mn ? 2 : (ext ? 1 : 0));
 #define B2S_GEMM_CASE(BN_, CG_)                                          \
   if (bn == BN_ && cg == CG_) {                                          \

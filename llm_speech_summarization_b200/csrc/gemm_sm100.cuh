@@ -72,6 +72,11 @@ struct GemmArgs {
   int b_tap_atoms;          // grouped-conv wgrad: N atom j reads W columns [g*w_group_off, +64) at rows k + j - a_pad
   int out_group_rows;       // output row offset per group   (default 0)
   int out_group_cols;       // output column offset per group (default N when out_group_rows == 0)
+  // ---- train-mode dropout fused into the epilogue (rng.cuh): applied to act(acc + bias), i.e. AFTER the activation and
+  // BEFORE the residual add -- the order of nn.Dropout in HubertFeedForward / HubertEncoderLayerStableLayerNorm.
+  // Element index = output_row * ldo + output_col. drop_thresh == 0: off. out2 keeps the un-dropped pre-activation.
+  unsigned drop_k1, drop_k2, drop_thresh;
+  float drop_inv_keep;
 };
 
 int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream);

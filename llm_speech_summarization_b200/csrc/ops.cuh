@@ -5,6 +5,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "rng.cuh"
+
 namespace b2s {
 
 // ---- loss.cu
@@ -64,7 +66,9 @@ int rmsnorm_bwd(const float* x, const int* x_index, const float* w, float eps, c
 int layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int dy_bf16, float* dh, int accumulate,
                   void* dh_bf16, float* dgamma, float* dbeta, long long rows, int C, cudaStream_t stream);
 int swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows, int F, cudaStream_t stream);
-int gelu_bwd(const void* pre, const void* dy, void* dpre, long long n, cudaStream_t stream);
+// drop (optional): dy is the gradient w.r.t. dropout(gelu(pre)) of that site (element index = linear index)
+int gelu_bwd(const void* pre, const void* dy, void* dpre, long long n, cudaStream_t stream,
+             const DropSpec* drop = nullptr);
 int add_rowdiff(const float* h, const int* rows_a, const int* rows_b, const float* coef, float* dh, void* dh_bf16,
                 int pairs, int C, cudaStream_t stream);
 int gather_rows_f32(const float* src, const int* index, float* out, long long rows, int C, cudaStream_t stream);
@@ -85,6 +89,19 @@ int conv0_bwd(const float* wave, long long wave_stride, int batches, int samples
               const float* gamma, const float* beta, float eps, const void* dy_bf16, int frames, float* dW, float* db,
               float* dgamma, float* dbeta, cudaStream_t stream);
 
+// ---- regularize.cu (train-mode regularisers of the HuBERT encoder; decisions regenerated from counters, rng.cuh)
+// x *= keep ? 1/(1-p) : 0 in place on an fp32 tensor and / or its bf16 copy (element index = linear index)
+int dropout_apply(float* x_f32, void* x_bf16, long long n, const DropSpec& d, cudaStream_t stream);
+// SpecAugment: h[row, :] = embed where time_mask[row] != 0
+int mask_rows_f32(float* h, const unsigned char* time_mask, const float* embed, long long rows, int C,
+                  cudaStream_t stream);
+// backward of [feature-projection dropout -> SpecAugment] on dh in place; g_embed += gradient of the replaced rows
+int featproj_reg_bwd(float* dh, const unsigned char* time_mask, float* g_embed, long long rows, int C, const DropSpec& d,
+                     cudaStream_t stream);
+// test hook: out[i] = 1 if element e_first + i of stream (seed, site, a, b) is kept at drop probability p
+int drop_mask_dump(unsigned char* out, long long n, unsigned long long seed, uint32_t site, uint32_t a, uint32_t b,
+                   float p, uint32_t e_first, cudaStream_t stream);
+
 // ---- attention.cu
 // Packed variable-length attention. q/k/v are bf16 views into one [rows, ld] buffer (fused QKV output):
 // head h of row r lives at base + r*ld + h*D. Sequences are rows [cu[s], cu[s+1]).
@@ -92,18 +109,20 @@ int conv0_bwd(const float* wave, long long wave_stride, int batches, int samples
 // total_rows = rows of the packed buffers (the TMA tensor maps zero-fill beyond it).
 int attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
                   const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
-                  float scale, int causal, float* lse /* optional [rows, Hq] */, cudaStream_t stream);
+                  float scale, int causal, float* lse /* optional [rows, Hq] */, cudaStream_t stream,
+                  const AttnDrop* drop = nullptr /* attention-probability dropout (tcgen05 kernels only) */);
 // Backward of attention_fwd. lse = the forward's saved log-sum-exp; delta_ws = fp32 [rows, Hq] scratch.
 // dq / dk / dv are bf16 views with row stride ld_dqkv (head h at column h*D). rope_cs (optional, [npos, D]) fuses
 // the inverse rotary rotation into the dq / dk stores (positions = row index inside its sequence).
 int attention_bwd(const void* q, const void* k, const void* v, long long ld_qkv, const void* o, long long ld_o,
                   const void* dout, long long ld_do, const float* lse, float* delta_ws, void* dq, void* dk, void* dv,
                   long long ld_dqkv, const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq,
-                  int Hkv, int D, float scale, int causal, const float* rope_cs, cudaStream_t stream);
+                  int Hkv, int D, float scale, int causal, const float* rope_cs, cudaStream_t stream,
+                  const AttnDrop* drop = nullptr);
 int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld_qkv, const void* dout, long long ld_do,
                      const float* lse, const float* delta, void* dq, void* dk, void* dv, long long ld_dqkv,
                      const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
-                     float scale, int causal, const float* rope_cs, cudaStream_t stream);
+                     float scale, int causal, const float* rope_cs, cudaStream_t stream, const AttnDrop* drop = nullptr);
 void attention_set_impl(int impl);  // 1 = tcgen05 kernel (default), 0 = legacy mma.sync kernel
 int attention_get_impl();
 

@@ -10,8 +10,10 @@
 // Every dense contraction is the tcgen05 GEMM: dgrad reads the forward's bf16 weights MN-major (no transposed
 // copies, the weights change every optimizer step), wgrad reads dY and X MN-major and accumulates with fp32 atomics
 // (split-K fills the 148 SMs; accumulation across micro-batches = REF/trainer.py:372-380 comes for free).
-// Dropout / LayerDrop / SpecAugment (train-mode only, TF/.../modeling_hubert.py:596-599,842-886) are not applied:
-// the step is the deterministic one the oracle restates.
+// Train-mode regularisers (TF/.../modeling_hubert.py:223-230 feature-projection dropout, :842-886 SpecAugment, :585-587
+// hidden dropout, :596-599 LayerDrop, :254 attention dropout, :351-368 FFN dropouts, :383-393 layer dropout) are applied
+// when the caller passes a b2s_encoder_regularizers block; with NULL the step is the
+// deterministic one. Elementwise dropouts are GEMM-epilogue fusions, masks are regenerated from counters (rng.cuh).
 #include "../../include/b2s.h"
 #include "b2s_common.cuh"
 #include "gemm_sm100.cuh"
@@ -199,8 +201,31 @@ struct StackScratch {  // backward scratch
   void *dyb, *dbig, *dsm, *xn;
 };
 
+void set_drop(GemmArgs& g, const DropSpec& d) {
+  g.drop_k1 = d.k1;
+  g.drop_k2 = d.k2;
+  g.drop_thresh = d.thresh;
+  g.drop_inv_keep = d.inv_keep;
+}
+
+AttnDrop attn_drop(const b2s_encoder_regularizers* reg, int l) {
+  AttnDrop a{};
+  if (reg != nullptr) {
+    a.seed = reg->seed;
+    a.site = site_attn_prob(l);
+    a.thresh = drop_threshold(reg->p_attention);
+    a.inv_keep = reg->p_attention < 1.f ? 1.0f / (1.0f - reg->p_attention) : 0.f;
+  }
+  return a;
+}
+
+bool layer_skipped(const b2s_encoder_regularizers* reg, int l) {
+  return reg != nullptr && reg->layer_skip != nullptr && reg->layer_skip[l] != 0;
+}
+
 int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, int heads, float eps, const StackBufs& s,
-                        void* xn, const int* cu, int B, int frames, cudaStream_t stream) {
+                        void* xn, const int* cu, int B, int frames, cudaStream_t stream,
+                        const b2s_encoder_regularizers* reg = nullptr) {
   const long long rows = static_cast<long long>(B) * frames;
   const size_t rH = static_cast<size_t>(rows) * H;
   for (int l = 0; l < L; ++l) {
@@ -208,6 +233,11 @@ int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, in
     float* h_in = s.h + l * rH;
     float* h_mid = s.h_mid + l * rH;
     float* h_out = s.h + (l + 1) * rH;
+    if (layer_skipped(reg, l)) {  // LayerDrop: the layer is the identity for this micro-batch
+      B2S_CUDA_CHECK(cudaMemcpyAsync(h_out, h_in, rH * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+      continue;
+    }
+    const AttnDrop adrop = attn_drop(reg, l);
     __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(s.qkv) + l * 3 * rH;
     __nv_bfloat16* ao = reinterpret_cast<__nv_bfloat16*>(s.ao) + l * rH;
     __nv_bfloat16* ffp = reinterpret_cast<__nv_bfloat16*>(s.ff_pre) + static_cast<size_t>(l) * rows * F;
@@ -221,13 +251,14 @@ int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, in
       RC(gemm_bf16_launch(g, stream));
     }
     RC(attention_fwd(qkv, qkv + H, qkv + 2 * H, 3 * H, ao, H, cu, B, frames, rows, heads, heads, 64, 0.125f, 0,
-                     s.lse + static_cast<size_t>(l) * rows * heads, stream));
+                     s.lse + static_cast<size_t>(l) * rows * heads, stream, reg ? &adrop : nullptr));
     {
       GemmArgs g = lin(ao, Ly.wo, rows, H, H);
       g.epi = EPI_RESID_F32;
       g.bias = Ly.bo;
       g.out = h_mid;
       g.resid = h_in;
+      if (reg) set_drop(g, make_drop_spec(reg->seed, site_attn_out(l), reg->p_hidden));
       RC(gemm_bf16_launch(g, stream));
     }
     RC(layernorm_fwd(h_mid, 0, Ly.ln2_g, Ly.ln2_b, eps, 0, xn, rows, H, stream));
@@ -239,6 +270,7 @@ int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, in
       g.out = ff;
       g.out2 = ffp;
       g.ld2 = F;
+      if (reg) set_drop(g, make_drop_spec(reg->seed, site_ff_act(l), reg->p_activation));
       RC(gemm_bf16_launch(g, stream));
     }
     {
@@ -247,6 +279,7 @@ int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, in
       g.bias = Ly.b2;
       g.out = h_out;
       g.resid = h_mid;
+      if (reg) set_drop(g, make_drop_spec(reg->seed, site_ff_out(l), reg->p_hidden));
       RC(gemm_bf16_launch(g, stream));
     }
   }
@@ -256,10 +289,12 @@ int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, in
 // on entry b.dh / b.dyb hold d(loss)/d(h[L]) (fp32 / bf16); on exit d(loss)/d(h[0])
 int stack_backward(const b2s_encoder_layer* layers, const b2s_encoder_layer_grads* grads, int L, int H, int F, int heads,
                    float eps, const StackBufs& s, const StackScratch& b, const int* cu, int B, int frames,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const b2s_encoder_regularizers* reg = nullptr) {
   const long long rows = static_cast<long long>(B) * frames;
   const size_t rH = static_cast<size_t>(rows) * H;
+  const bool drop_h = reg != nullptr && reg->p_hidden > 0.f;
   for (int l = L - 1; l >= 0; --l) {
+    if (layer_skipped(reg, l)) continue;  // identity layer: the gradient passes through unchanged
     const b2s_encoder_layer& Ly = layers[l];
     const b2s_encoder_layer_grads& G = grads[l];
     const float* h_in = s.h + l * rH;
@@ -268,26 +303,40 @@ int stack_backward(const b2s_encoder_layer* layers, const b2s_encoder_layer_grad
     const __nv_bfloat16* ao = reinterpret_cast<const __nv_bfloat16*>(s.ao) + l * rH;
     const __nv_bfloat16* ffp = reinterpret_cast<const __nv_bfloat16*>(s.ff_pre) + static_cast<size_t>(l) * rows * F;
     const __nv_bfloat16* ff = reinterpret_cast<const __nv_bfloat16*>(s.ff) + static_cast<size_t>(l) * rows * F;
-    // feed-forward: h_out = h_mid + W2 gelu(W1 LN2(h_mid) + b1) + b2
-    RC(colsum_accum(b.dh, 0, G.b2, rows, H, stream));
+    // feed-forward: h_out = h_mid + drop(W2 drop(gelu(W1 LN2(h_mid) + b1)) + b2)
+    if (drop_h) {  // the branch gradient is the masked copy; the residual path keeps b.dh
+      RC(dropout_apply(nullptr, b.dyb, rows * H, make_drop_spec(reg->seed, site_ff_out(l), reg->p_hidden), stream));
+      RC(colsum_accum(b.dyb, 1, G.b2, rows, H, stream));
+    } else {
+      RC(colsum_accum(b.dh, 0, G.b2, rows, H, stream));
+    }
     RC(wgrad(b.dyb, ff, rows, H, F, G.w2, stream));
     RC(dgrad(b.dyb, Ly.w2, rows, H, F, EPI_BF16, b.dbig, stream));
-    RC(gelu_bwd(ffp, b.dbig, b.dbig, rows * F, stream));
+    {
+      const DropSpec dact = reg ? make_drop_spec(reg->seed, site_ff_act(l), reg->p_activation) : DropSpec{};
+      RC(gelu_bwd(ffp, b.dbig, b.dbig, rows * F, stream, dact.thresh != 0u ? &dact : nullptr));
+    }
     RC(colsum_accum(b.dbig, 1, G.b1, rows, F, stream));
     RC(layernorm_fwd(h_mid, 0, Ly.ln2_g, Ly.ln2_b, eps, 0, b.xn, rows, H, stream));
     RC(wgrad(b.dbig, b.xn, rows, F, H, G.w1, stream));
     RC(dgrad(b.dbig, Ly.w1, rows, F, H, EPI_BF16, b.dsm, stream));
     RC(layernorm_bwd_ex(h_mid, 0, Ly.ln2_g, Ly.ln2_b, 0, eps, b.dsm, 1, b.dh, 1, b.dyb, G.ln2_g, G.ln2_b, rows, H,
                         stream));
-    // attention: h_mid = h_in + Wo attn(Wqkv LN1(h_in) + bqkv) + bo
-    RC(colsum_accum(b.dh, 0, G.bo, rows, H, stream));
+    // attention: h_mid = h_in + drop(Wo attn(Wqkv LN1(h_in) + bqkv) + bo)
+    if (drop_h) {
+      RC(dropout_apply(nullptr, b.dyb, rows * H, make_drop_spec(reg->seed, site_attn_out(l), reg->p_hidden), stream));
+      RC(colsum_accum(b.dyb, 1, G.bo, rows, H, stream));
+    } else {
+      RC(colsum_accum(b.dh, 0, G.bo, rows, H, stream));
+    }
     RC(wgrad(b.dyb, ao, rows, H, H, G.wo, stream));
     RC(dgrad(b.dyb, Ly.wo, rows, H, H, EPI_BF16, b.dsm, stream));
     {
       __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(b.dbig);
+      const AttnDrop adrop = attn_drop(reg, l);
       RC(attention_bwd(qkv, qkv + H, qkv + 2 * H, 3 * H, ao, H, b.dsm, H, s.lse + static_cast<size_t>(l) * rows * heads,
                        b.delta, dqkv, dqkv + H, dqkv + 2 * H, 3 * H, cu, B, frames, rows, heads, heads, 64, 0.125f, 0,
-                       nullptr, stream));
+                       nullptr, stream, reg ? &adrop : nullptr));
     }
     RC(colsum_accum(b.dbig, 1, G.bqkv, rows, 3 * H, stream));
     RC(layernorm_fwd(h_in, 0, Ly.ln1_g, Ly.ln1_b, eps, 0, b.xn, rows, H, stream));
@@ -333,9 +382,20 @@ size_t hubert_backward_workspace_bytes(const b2s_hubert_weights* w, int batches,
   return b.bytes;
 }
 
+int check_regularizers(const b2s_encoder_regularizers* reg) {
+  if (reg == nullptr) return B2S_OK;
+  const float ps[4] = {reg->p_feat_proj, reg->p_hidden, reg->p_attention, reg->p_activation};
+  for (float p : ps) B2S_REQUIRE(p >= 0.f && p < 1.f, "regularizers: dropout probabilities must lie in [0, 1)");
+  B2S_REQUIRE(reg->time_mask == nullptr || reg->masked_spec_embed != nullptr,
+              "regularizers: time_mask needs masked_spec_embed");
+  return B2S_OK;
+}
+
 int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long long wave_stride, int batches, int samples,
-                         void* saved, size_t saved_bytes, float* audio_embeds, cudaStream_t stream) {
+                         void* saved, size_t saved_bytes, float* audio_embeds, const b2s_encoder_regularizers* reg,
+                         cudaStream_t stream) {
   B2S_REQUIRE(w && wave && saved && audio_embeds, "hubert_forward_train: null pointer");
+  RC(check_regularizers(reg));
   B2S_REQUIRE(batches > 0 && samples > 0, "hubert_forward_train: empty batch");
   B2S_REQUIRE(w->hidden % 256 == 0 && w->hidden % w->heads == 0 && w->hidden / w->heads == 64,
               "hubert_forward_train: hidden/heads must give head_dim 64");
@@ -386,8 +446,11 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
     g.epi = EPI_F32;
     g.bias = w->fp_b;
     g.out = s.h;
+    if (reg) set_drop(g, make_drop_spec(reg->seed, SITE_FEAT_PROJ, reg->p_feat_proj));
     RC(gemm_bf16_launch(g, stream));
   }
+  if (reg && reg->time_mask)  // SpecAugment: masked frames become masked_spec_embed (after the projection dropout)
+    RC(mask_rows_f32(s.h, reg->time_mask, reg->masked_spec_embed, rows, H, stream));
   RC(cast_f32_to_bf16(s.h, s.hp_bf, rows * H, stream));
   {
     GemmArgs g{};
@@ -419,12 +482,14 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
     g.ld2 = H;
     RC(gemm_bf16_launch(g, stream));
   }
+  if (reg)  // dropout(hidden + positional embedding): after the residual add, so not an epilogue of that GEMM
+    RC(dropout_apply(s.h, nullptr, rows * H, make_drop_spec(reg->seed, SITE_POS_ADD, reg->p_hidden), stream));
   iota_scaled<<<(B + 1 + 255) / 256, 256, 0, stream>>>(s.cu, B + 1, s.frames);
   B2S_LAUNCH_CHECK();
   const size_t rH = static_cast<size_t>(rows) * H;
   {
     StackBufs sb{s.h, s.h_mid, s.lse, s.qkv, s.ao, s.ff_pre, s.ff};
-    RC(stack_forward_train(w->layers, L, H, F, w->heads, eps, sb, s.xn, s.cu, B, s.frames, stream));
+    RC(stack_forward_train(w->layers, L, H, F, w->heads, eps, sb, s.xn, s.cu, B, s.frames, stream, reg));
   }
   RC(layernorm_avgpool_fwd(s.h + L * rH, w->final_ln_g, w->final_ln_b, eps, s.pooled_x, B, s.frames, H, w->pool_kernel,
                            w->pool_stride, s.pooled, stream));
@@ -440,9 +505,11 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
 
 int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* gr, const float* wave,
                     long long wave_stride, int batches, int samples, void* saved, size_t saved_bytes,
-                    const float* d_audio_embeds, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                    const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
+                    const b2s_encoder_regularizers* reg, cudaStream_t stream) {
   B2S_REQUIRE(w && pos_w_dgrad && gr && gr->layers && wave && saved && d_audio_embeds && workspace,
               "hubert_backward: null pointer");
+  RC(check_regularizers(reg));
   Saved s;
   plan_saved(w, batches, samples, saved, saved_bytes, &s);
   B2S_REQUIRE(s.bytes <= saved_bytes && s.frames > 0 && s.pooled > 0, "hubert_backward: bad saved region");
@@ -461,9 +528,10 @@ int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const 
   RC(head_backward(w->proj_w, w->final_ln_g, w->final_ln_b, gr->proj_w, gr->proj_b, gr->final_ln_g, gr->final_ln_b,
                    s.h + L * rH, s.pooled_x, d_audio_embeds, b.da, b.dpool, b.dxn_f, sc, B, s.frames, s.pooled, H, Cl,
                    w->pool_kernel, w->pool_stride, eps, stream));
-  RC(stack_backward(w->layers, gr->layers, L, H, F, w->heads, eps, sb, sc, s.cu, B, s.frames, stream));
+  RC(stack_backward(w->layers, gr->layers, L, H, F, w->heads, eps, sb, sc, s.cu, B, s.frames, stream, reg));
 
-  // ---- positional conv embedding: h0 = hp + gelu(conv(hp) + b); dh / dyb = gradient w.r.t. h0
+  // ---- positional conv embedding: h0 = drop(hp + gelu(conv(hp) + b)); dh / dyb = gradient w.r.t. h0
+  if (reg) RC(dropout_apply(b.dh, b.dyb, rows * H, make_drop_spec(reg->seed, SITE_POS_ADD, reg->p_hidden), stream));
   RC(gelu_bwd(s.pos_pre, b.dyb, b.dsm, rows * H, stream));  // dsm = d(pre-GELU conv output), bf16
   RC(colsum_accum(b.dsm, 1, gr->pos_b, rows, H, stream));
   {
@@ -527,7 +595,10 @@ int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const 
     g.out_batch_rows = s.frames;
     RC(gemm_bf16_launch(g, stream));
   }
-  // ---- feature projection: hp = fp_w LN(conv_x[6]) + fp_b ; dh = gradient w.r.t. hp
+  // ---- feature projection: hp = specaug(drop(fp_w LN(conv_x[6]) + fp_b)) ; dh = gradient w.r.t. hp
+  if (reg)
+    RC(featproj_reg_bwd(b.dh, reg->time_mask, reg->g_masked_spec_embed, rows, H,
+                        make_drop_spec(reg->seed, SITE_FEAT_PROJ, reg->p_feat_proj), stream));
   RC(colsum_accum(b.dh, 0, gr->fp_b, rows, H, stream));
   RC(cast_f32_to_bf16(b.dh, b.dyb, rows * H, stream));
   RC(layernorm_fwd(s.conv_x[6], 1, w->fp_ln_g, w->fp_ln_b, eps, 0, b.xn, rows, 512, stream));

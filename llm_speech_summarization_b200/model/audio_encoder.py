@@ -20,6 +20,16 @@ from .. import _lib, ops, packing
 from ..config import EncoderArch, encoder_arch_from_config
 
 
+class _Ptr:
+    """A raw device address with the one method the ctypes marshalling code calls."""
+
+    def __init__(self, addr: int):
+        self.addr = addr
+
+    def data_ptr(self) -> int:
+        return self.addr
+
+
 class _Params(nn.Module):
     """A bag of named parameters (so state_dict keys read `<name>.weight` / `<name>.bias`)."""
 
@@ -216,6 +226,10 @@ class AudioEncoder(nn.Module):
         self._pos_w_dgrad = None
         self._grads = None
         self._train_ctx = None
+        # train-mode regularisers (dropout / LayerDrop / SpecAugment, regularizers.RegularizerConfig). None keeps
+        # forward_train deterministic; EncoderTrainer(regularize=True) or the caller sets it. HuBERT only: Whisper-medium
+        # has dropout = encoder_layerdrop = 0.
+        self.regularizers = None
         self._register_load_state_dict_pre_hook(self._rename_legacy_weight_norm)
 
     # -- checkpoints written by torch 2.0 spell the weight-norm parameters weight_g / weight_v
@@ -453,7 +467,8 @@ class AudioEncoder(nn.Module):
         H, F_ = arch.hidden, arch.ffn
         fe, fp, pc = enc.feature_extractor.conv_layers, enc.feature_projection, enc.encoder.pos_conv_embed.conv
         C_ = self.embed_projection.out_features
-        spec = [("conv0_w", (arch.conv_dim[0], arch.conv_kernel[0]), [fe[0].conv.weight]),
+        spec = [("masked_spec_embed", (H,), [enc.masked_spec_embed]),
+                ("conv0_w", (arch.conv_dim[0], arch.conv_kernel[0]), [fe[0].conv.weight]),
                 ("conv0_b", (512,), [fe[0].conv.bias]), ("conv0_ln_g", (512,), [fe[0].layer_norm.weight]),
                 ("conv0_ln_b", (512,), [fe[0].layer_norm.bias]),
                 ("fp_ln_g", (512,), [fp.layer_norm.weight]), ("fp_ln_b", (512,), [fp.layer_norm.bias]),
@@ -556,12 +571,13 @@ class AudioEncoder(nn.Module):
             for k in ("ln1_g", "ln1_b", "wqkv", "bqkv", "wo", "bo", "ln2_g", "ln2_b", "w1", "b1", "w2", "b2"):
                 setattr(layers[l], k, ptr[f"l{l}.{k}"])
         g.layers = C.cast(layers, C.POINTER(_lib.EncoderLayerGrads))
-        self._grads = (g, layers, scratch, key, pending)
+        self._grads = (g, layers, scratch, key, pending, _Ptr(ptr["masked_spec_embed"]) if hubert else None)
         return self._grads
 
-    def forward_train(self, input: torch.Tensor) -> torch.Tensor:
+    def forward_train(self, input: torch.Tensor, generator=None, draw=None) -> torch.Tensor:
         """Training forward (REF/trainer.py:278): (B, T0) waveform -> fp32 (B, A, llm_dim), keeping the activations
-        for `backward`. Deterministic: dropout / LayerDrop / SpecAugment of the HF train mode are not applied."""
+        for `backward`. With `self.regularizers` set and the module in train mode, HF's train-mode dropout / LayerDrop /
+        SpecAugment are applied (host randomness from `generator`, or an explicit `draw`); otherwise deterministic."""
         if not input.is_cuda:
             raise RuntimeError("AudioEncoder.forward_train (B200 path) needs a CUDA input; there is no CPU path")
         if self.encoder_base == "whisper":
@@ -580,10 +596,20 @@ class AudioEncoder(nn.Module):
         if ctx is None or ctx["saved"].numel() < nbytes:
             ctx = {"saved": torch.empty(nbytes, device=wave.device, dtype=torch.uint8)}
         out = torch.empty(B, pooled, w.llm_dim, device=wave.device, dtype=torch.float32)
+        if draw is None and self.regularizers is not None and self.training:
+            from ..regularizers import draw as _draw
+            draw = _draw(self.regularizers, B, frames, w.num_layers, wave.device, generator)
+        reg = None
+        if draw is not None:
+            mse = self.encoder.masked_spec_embed.detach()
+            if mse.dtype != torch.float32 or not mse.is_contiguous():
+                mse = mse.float().contiguous()
+            ctx["mse"] = mse
+            reg = C.byref(draw.c_struct(mse, None))
         _lib.check(lib.b2s_hubert_forward_train(C.byref(w), wave.data_ptr(), wave.stride(0), B, T0,
-                                                ctx["saved"].data_ptr(), ctx["saved"].numel(), out.data_ptr(),
+                                                ctx["saved"].data_ptr(), ctx["saved"].numel(), out.data_ptr(), reg,
                                                 torch.cuda.current_stream().cuda_stream), "hubert_forward_train")
-        ctx.update(wave=wave, B=B, T0=T0, pooled=pooled)
+        ctx.update(wave=wave, B=B, T0=T0, pooled=pooled, draw=draw)
         self._train_ctx = ctx
         return out
 
@@ -643,10 +669,13 @@ class AudioEncoder(nn.Module):
         if ctx.get("bws") is None or ctx["bws"].numel() < nbytes:
             ctx["bws"] = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
         wave = ctx["wave"]
+        reg = None
+        if ctx.get("draw") is not None:
+            reg = C.byref(ctx["draw"].c_struct(ctx["mse"], self._grad_buffers()[5]))
         _lib.check(lib.b2s_hubert_backward(C.byref(w), self._pos_w_dgrad.data_ptr(), C.byref(g), wave.data_ptr(),
                                            wave.stride(0), ctx["B"], ctx["T0"], ctx["saved"].data_ptr(),
                                            ctx["saved"].numel(), d.data_ptr(), ctx["bws"].data_ptr(),
-                                           ctx["bws"].numel(), torch.cuda.current_stream().cuda_stream),
+                                           ctx["bws"].numel(), reg, torch.cuda.current_stream().cuda_stream),
                    "hubert_backward")
         del ctx["wave"]
 
@@ -655,7 +684,7 @@ class AudioEncoder(nn.Module):
         """Scratch accumulators -> `.grad` of the parameters (HF layouts; += like autograd), then zero the scratch.
         Pure re-indexing plus the weight-norm chain rule of the positional conv (once per optimizer step); buffers
         that alias `.grad` directly need nothing."""
-        _, _, t, _, pending = self._grad_buffers()
+        _, _, t, _, pending, _ = self._grad_buffers()
         enc = self.encoder
         arch = enc.arch
         H = arch.hidden

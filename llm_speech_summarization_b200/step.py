@@ -231,13 +231,17 @@ class AudioPromptStep:
 
     @torch.no_grad()
     def forward_backward(self, waves: torch.Tensor, text_ids, resp_ids, loss_scale: float = 1.0,
-                         plan: Optional[StepPlan] = None) -> Dict[str, torch.Tensor]:
+                         plan: Optional[StepPlan] = None, generator=None, draw=None) -> Dict[str, torch.Tensor]:
         """One training micro-batch (REF/trainer.py:270-374): encoder forward with kept activations -> LLM
         forward/backward -> encoder backward. Parameter gradients (x loss_scale) accumulate inside the encoder
-        until `audio_encoder.flush_grads()`."""
+        until `audio_encoder.flush_grads()`. `generator` / `draw` feed the encoder's train-mode regularisers
+        (AudioEncoder.forward_train)."""
         if not waves.is_cuda:
             raise RuntimeError("AudioPromptStep needs CUDA inputs; there is no CPU path")
-        audio = self.audio_encoder.forward_train(waves)
+        if generator is not None or draw is not None:
+            audio = self.audio_encoder.forward_train(waves, generator=generator, draw=draw)
+        else:
+            audio = self.audio_encoder.forward_train(waves)
         out = self.llm_forward_backward(audio, text_ids, resp_ids, loss_scale=loss_scale, plan=plan)
         self.audio_encoder.backward(out["d_audio_embeds"])
         return out

@@ -15,7 +15,9 @@
 
 The LLM is frozen (REF/trainer.py:62-64); its parameters sit in the reference optimizer's second param group without
 ever receiving a gradient, so they carry no optimizer state -- FlatAdamW reproduces that group as an empty-state one.
-Dropout / LayerDrop / SpecAugment of HF's train mode are not applied (deterministic step, see csrc/train_enc.cu).
+`regularize=True` switches on HF's train-mode dropout / LayerDrop / SpecAugment for the HuBERT encoder (what the
+reference's `audio_encoder.train()` does, REF/trainer.py:258; regularizers.py, csrc/rng.cuh); the default is the
+deterministic step.
 """
 from __future__ import annotations
 
@@ -151,12 +153,22 @@ class EncoderTrainer:
     caller). `step` counts micro-batches like the reference's `self.step`."""
 
     def __init__(self, step_fn, audio_encoder, llm=None, *, lr: float = 5e-5, betas=(0.9, 0.999),
-                 grad_accum_interval: int = 16, total_optimizer_steps: int = 1000, weight_decay: float = 1e-2):
+                 grad_accum_interval: int = 16, total_optimizer_steps: int = 1000, weight_decay: float = 1e-2,
+                 regularize: bool = False, generator: Optional[torch.Generator] = None):
         self.step_fn = step_fn
         self.audio_encoder = audio_encoder
+        self.generator = generator
         frozen = list(llm.parameters()) if llm is not None else []
-        # masked_spec_embed is only read by SpecAugment (train-mode HF, not applied): it never gets a gradient
-        unused = [p for n, p in audio_encoder.named_parameters() if n.endswith("masked_spec_embed")]
+        spec_augment = False
+        if regularize and getattr(audio_encoder, "encoder_base", None) == "hubert":
+            from .regularizers import RegularizerConfig
+            audio_encoder.regularizers = RegularizerConfig.from_arch(audio_encoder.encoder.arch)
+            audio_encoder.train()
+            cfg = audio_encoder.regularizers
+            spec_augment = cfg.apply_spec_augment and cfg.mask_time_prob > 0
+        # masked_spec_embed is only read by SpecAugment: without it the parameter never gets a gradient
+        unused = [] if spec_augment else [p for n, p in audio_encoder.named_parameters()
+                                          if n.endswith("masked_spec_embed")]
         self.optimizer = FlatAdamW(audio_encoder.parameters(), lr=lr, betas=betas, weight_decay=weight_decay,
                                    frozen_params=frozen, exclude=unused,
                                    order=getattr(audio_encoder, "flat_param_order", lambda: None)())
@@ -183,7 +195,7 @@ class EncoderTrainer:
         an optimizer step happens once world * (micro-batches * B) reaches grad_accum_interval (or at loader end)."""
         B = waves.shape[0]
         out = self.step_fn.forward_backward(waves, text_ids, resp_ids, loss_scale=1.0 / self.grad_accum_interval,
-                                            plan=plan)
+                                            plan=plan, generator=self.generator)
         self._micro += B * self.world()
         self.step += 1
         out["optimizer_step"] = False

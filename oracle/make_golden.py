@@ -211,6 +211,118 @@ def run_whisper_case(name, cfg, write=True):
                     "num_audio_embeds": n, "torch": torch.__version__}, os.path.join(GOLD, f"{name}.pt"))
 
 
+def run_train_mode_case(name, enc_cfg, samples, batch, seed, layer_skip, write=True):
+    """The reference's AudioEncoder in .train() mode (REF/trainer.py:258) with HF's host / device randomness replaced
+    by the masks of oracle/regularizers.py: torch.nn.functional.dropout (every nn.Dropout and the eager attention's
+    probability dropout route through it) consumes the sites in HF's call order, torch.rand([]) (LayerDrop) returns
+    preset values, _compute_mask_indices (SpecAugment) returns the preset frame mask. Pins the oracle's train-mode
+    restatement (forward and autograd gradients) and writes the fixture the CUDA tests compare against."""
+    import numpy as np
+    from transformers import HubertModel
+    from transformers.models.hubert import modeling_hubert
+    from oracle import configs, reference_math as rm, regularizers as rg
+    from llm_speech_summarization_b200.regularizers import compute_time_mask
+    ref_audio_encoder, _, _ = import_reference()
+    hc = hubert_config(enc_cfg)
+    hc.feat_proj_dropout = hc.hidden_dropout = hc.attention_dropout = hc.activation_dropout = 0.1
+    hc.layerdrop = 0.1
+    hc.apply_spec_augment, hc.mask_time_prob, hc.mask_time_length, hc.mask_time_min_masks = True, 0.05, 10, 2
+    hc._attn_implementation = "eager"
+    ref_audio_encoder.load_hubert_encoder = lambda config: HubertModel(hc)
+    config = ns(model=ns(audio_encoder=ns(base="hubert", type="facebook/hubert-large-ls960-ft",
+                                          downsample_method="pool", downsample_factor=4,
+                                          pooling=ns(kernel_size=enc_cfg.pool_kernel, stride=enc_cfg.pool_stride)),
+                         llm_type="meta-llama/Llama-3.2-3B-Instruct", llm_embedding_channels=enc_cfg.llm_dim))
+    enc = ref_audio_encoder.AudioEncoder(config, torch.device("cpu"))
+    enc_sd = configs.make_encoder_state_dict(enc_cfg, seed=1234)
+    g = torch.Generator().manual_seed(77)
+    enc_sd["encoder.masked_spec_embed"] = torch.randn(enc_cfg.hidden, generator=g) * 0.5
+    enc.load_state_dict(enc_sd, strict=True)
+    enc.train()
+    wave = torch.randn(batch, samples, generator=g) * 0.1
+    frames = samples
+    for k, st in zip(enc_cfg.conv_kernel, enc_cfg.conv_stride):
+        frames = (frames - k) // st + 1
+    time_mask = compute_time_mask(batch, frames, 0.05, 10, 2, np.random.default_rng(5))
+    skip = np.asarray(layer_skip, dtype=np.uint8)
+    reg = rg.OracleRegularizers(seed=seed, layer_skip=skip, time_mask=time_mask)
+    H, nh, L = enc_cfg.hidden, enc_cfg.heads, enc_cfg.layers
+
+    sites = [("elt", rg.SITE_FEAT_PROJ, reg.p_feat_proj), ("elt", rg.SITE_POS_ADD, reg.p_hidden)]
+    for l in range(L):
+        if not skip[l]:
+            sites += [("att", l, reg.p_attention), ("elt", rg.site_attn_out(l), reg.p_hidden),
+                      ("elt", rg.site_ff_act(l), reg.p_activation), ("elt", rg.site_ff_out(l), reg.p_hidden)]
+    it = iter(sites)
+
+    def fake_dropout(x, p=0.5, training=True, inplace=False):
+        kind, site, ps = next(it)
+        assert training and abs(p - ps) < 1e-9, (kind, site, p, ps)
+        if kind == "att":
+            assert x.shape == (batch, nh, frames, frames), x.shape
+            return x * rg.attention_multiplier(seed, site, ps, batch, nh, frames)
+        assert x.shape[:2] == (batch, frames), x.shape
+        return x * rg.elementwise_multiplier(seed, site, ps, batch * frames, x.shape[-1]).view(x.shape)
+
+    rand_vals = iter([0.0 if s else 1.0 for s in skip])  # < layerdrop  <=>  skip
+    real_rand = torch.rand
+
+    def fake_rand(*a, **kw):
+        if len(a) == 1 and isinstance(a[0], (list, tuple)) and len(a[0]) == 0:
+            return torch.tensor(next(rand_vals))
+        return real_rand(*a, **kw)
+
+    real = (torch.nn.functional.dropout, modeling_hubert._compute_mask_indices)
+    torch.nn.functional.dropout = fake_dropout
+    torch.rand = fake_rand
+    modeling_hubert._compute_mask_indices = lambda *a, **kw: time_mask
+    try:
+        ref_out = enc(wave)
+    finally:
+        torch.nn.functional.dropout, modeling_hubert._compute_mask_indices = real
+        torch.rand = real_rand
+    assert next(it, None) is None, "the reference consumed fewer dropout sites than expected"
+    R = torch.randn(ref_out.shape, generator=g)
+    names = ["encoder.masked_spec_embed", "encoder.feature_projection.projection.bias",
+             "encoder.encoder.layers.0.attention.q_proj.weight", "encoder.encoder.layers.0.attention.v_proj.bias",
+             f"encoder.encoder.layers.{L - 1}.feed_forward.intermediate_dense.weight",
+             f"encoder.encoder.layers.{L - 1}.feed_forward.output_dense.bias",
+             "encoder.encoder.layer_norm.weight", "encoder.feature_extractor.conv_layers.6.conv.bias",
+             "encoder.encoder.pos_conv_embed.conv.bias", "embed_projection.weight"]
+    skipped = [l for l in range(L) if skip[l]]
+    if skipped:
+        names.append(f"encoder.encoder.layers.{skipped[0]}.attention.out_proj.weight")
+    ref_params = dict(enc.named_parameters())
+    ref_grads = torch.autograd.grad((ref_out * R).sum(), [ref_params[k] for k in names], allow_unused=True)
+
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in enc_sd.items()}
+    ora_out = rm.audio_encoder_forward(sd, wave, enc_cfg, reg=reg)
+    ora_grads = torch.autograd.grad((ora_out * R).sum(), [sd[k] for k in names], allow_unused=True)
+    errs = {"audio_embeds": rel(ora_out, ref_out)}
+    for k, a, b in zip(names, ora_grads, ref_grads):
+        if b is None or float(b.norm()) == 0.0:
+            assert a is None or float(a.norm()) == 0.0, k
+            errs["grad:" + k] = 0.0
+        else:
+            errs["grad:" + k] = rel(a, b)
+    with torch.no_grad():
+        eval_out = rm.audio_encoder_forward(enc_sd, wave, enc_cfg)
+    print(f"[{name}] train-mode oracle vs reference:", {k: f"{v:.2e}" for k, v in errs.items()},
+          f"frames={frames} masked={int(time_mask.sum())} skip={skip.tolist()} "
+          f"train-vs-eval={rel(ref_out.detach(), eval_out):.3f}")
+    bad = {k: v for k, v in errs.items() if v > 2e-4}
+    assert not bad, f"train-mode oracle disagrees with the reference: {bad}"
+    if write:
+        torch.save({"case": name, "enc_cfg": configs.cfg_dict(enc_cfg), "enc_seed": 1234, "samples": samples,
+                    "batch": batch, "seed": seed, "layer_skip": torch.from_numpy(skip.copy()),
+                    "time_mask": torch.from_numpy(time_mask.copy()), "wave": wave.clone(), "R": R.clone(),
+                    "masked_spec_embed": enc_sd["encoder.masked_spec_embed"].clone(),
+                    "audio_embeds": ref_out.detach().clone(),
+                    "grads": {k: (None if gr is None else gr.detach().clone()) for k, gr in zip(names, ref_grads)},
+                    "torch": torch.__version__}, os.path.join(GOLD, f"{name}.pt"))
+    return errs
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also check the full-size architectures (no fixture written)")
@@ -222,6 +334,9 @@ def main():
     run_case("tiny_minichat_hubert", configs.TINY_ENCODER, configs.TINY_MINICHAT, samples=8000, T=5, R=4,
              fd_layers=(0, 1), extra_text=3)
     run_whisper_case("tiny_whisper", configs.TINY_WHISPER)
+    import dataclasses
+    run_train_mode_case("tiny_hubert_train_mode", dataclasses.replace(configs.TINY_ENCODER, layers=3), samples=8000,
+                        batch=2, seed=0x1234_5678_9ABC_DEF0 >> 2, layer_skip=(0, 1, 0))
     if args.full:
         run_whisper_case("full_whisper_medium", configs.WHISPER_MEDIUM, write=False)
         run_case("full_llama32_hubert", configs.HUBERT_LARGE, configs.LLAMA32_3B, samples=160000, T=40, R=64,

@@ -64,23 +64,45 @@ def _pos_conv_weight(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
 
 
 def hubert_encoder(sd: Dict[str, torch.Tensor], feats: torch.Tensor, cfg: EncoderCfg,
-                   return_pre_norm: bool = False) -> torch.Tensor:
+                   return_pre_norm: bool = False, reg=None) -> torch.Tensor:
     """Feature projection, positional conv embedding and the stable-layer-norm transformer stack; (B, N, 512) ->
     (B, N, H). TF/models/hubert/modeling_hubert.py:216-231 (projection), :45-103 (pos conv + same-pad),
-    :262-345 (attention, scaling head_dim**-0.5, no mask), :348-369 (FFN), :505-548 (layer), :563-624 (stack)."""
+    :262-345 (attention, scaling head_dim**-0.5, no mask), :348-369 (FFN), :505-548 (layer), :563-624 (stack).
+    `reg` (oracle.regularizers.OracleRegularizers) switches on the train-mode regularisers with explicit masks:
+    dropout after the projection (:230), SpecAugment (:842-886), dropout after the positional add (:587), LayerDrop
+    (:596-599), attention-probability dropout (:254), dropout after the attention block (:536), after the FFN
+    activation (:365) and after the FFN output (:368)."""
     H, nh = cfg.hidden, cfg.heads
     hd = H // nh
+    Bn, Nn = feats.shape[0], feats.shape[1]
+    if reg is not None:
+        from . import regularizers as rg
+
+        def drop(t, site, p):
+            return t * rg.elementwise_multiplier(reg.seed, site, p, Bn * Nn, t.shape[-1]).view(t.shape)
+    else:
+        def drop(t, site, p):
+            return t
     x = F.layer_norm(feats, (feats.shape[-1],), sd["encoder.feature_projection.layer_norm.weight"],
                      sd["encoder.feature_projection.layer_norm.bias"], cfg.ln_eps)
     x = F.linear(x, sd["encoder.feature_projection.projection.weight"],
                  sd["encoder.feature_projection.projection.bias"])
+    if reg is not None:
+        x = drop(x, rg.SITE_FEAT_PROJ, reg.p_feat_proj)
+        if reg.time_mask is not None:
+            tm = torch.from_numpy(reg.time_mask.astype(bool)).view(Bn, Nn, 1)
+            x = torch.where(tm, sd["encoder.masked_spec_embed"].view(1, 1, -1).to(x.dtype), x)
     pos = F.conv1d(x.transpose(1, 2), _pos_conv_weight(sd), sd["encoder.encoder.pos_conv_embed.conv.bias"],
                    padding=cfg.pos_k // 2, groups=cfg.pos_groups)
     if cfg.pos_k % 2 == 0:
         pos = pos[:, :, :-1]
     x = x + F.gelu(pos).transpose(1, 2)
+    if reg is not None:
+        x = drop(x, rg.SITE_POS_ADD, reg.p_hidden)
     B, N, _ = x.shape
     for l in range(cfg.layers):
+        if reg is not None and reg.skipped(l):
+            continue
         p = f"encoder.encoder.layers.{l}."
         y = F.layer_norm(x, (H,), sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"], cfg.ln_eps)
         q = F.linear(y, sd[p + "attention.q_proj.weight"], sd[p + "attention.q_proj.bias"])
@@ -90,30 +112,41 @@ def hubert_encoder(sd: Dict[str, torch.Tensor], feats: torch.Tensor, cfg: Encode
         k = k.view(B, N, nh, hd).transpose(1, 2)
         v = v.view(B, N, nh, hd).transpose(1, 2)
         a = torch.softmax(torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5), dim=-1)
+        if reg is not None:
+            a = a * rg.attention_multiplier(reg.seed, l, reg.p_attention, B, nh, N)
         a = torch.matmul(a, v).transpose(1, 2).reshape(B, N, H)
-        x = x + F.linear(a, sd[p + "attention.out_proj.weight"], sd[p + "attention.out_proj.bias"])
+        o = F.linear(a, sd[p + "attention.out_proj.weight"], sd[p + "attention.out_proj.bias"])
+        if reg is not None:
+            o = drop(o, rg.site_attn_out(l), reg.p_hidden)
+        x = x + o
         y = F.layer_norm(x, (H,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], cfg.ln_eps)
         y = F.gelu(F.linear(y, sd[p + "feed_forward.intermediate_dense.weight"],
                             sd[p + "feed_forward.intermediate_dense.bias"]))
-        x = x + F.linear(y, sd[p + "feed_forward.output_dense.weight"], sd[p + "feed_forward.output_dense.bias"])
+        if reg is not None:
+            y = drop(y, rg.site_ff_act(l), reg.p_activation)
+        y = F.linear(y, sd[p + "feed_forward.output_dense.weight"], sd[p + "feed_forward.output_dense.bias"])
+        if reg is not None:
+            y = drop(y, rg.site_ff_out(l), reg.p_hidden)
+        x = x + y
     if return_pre_norm:
         return x
     return F.layer_norm(x, (H,), sd["encoder.encoder.layer_norm.weight"], sd["encoder.encoder.layer_norm.bias"],
                         cfg.ln_eps)
 
 
-def hubert_last_hidden_state(sd, wave, cfg: EncoderCfg) -> torch.Tensor:
-    """HubertModel.forward(...).last_hidden_state, eval mode (TF/models/hubert/modeling_hubert.py:889-958)."""
+def hubert_last_hidden_state(sd, wave, cfg: EncoderCfg, reg=None) -> torch.Tensor:
+    """HubertModel.forward(...).last_hidden_state (TF/models/hubert/modeling_hubert.py:889-958): eval mode, or train
+    mode under the explicit masks of `reg`."""
     feats = hubert_feature_extractor(sd, wave, cfg).transpose(1, 2)
-    return hubert_encoder(sd, feats, cfg)
+    return hubert_encoder(sd, feats, cfg, reg=reg)
 
 
 # ----------------------------------------------------------------------------------------------------------
 # AudioEncoder.forward (the reference's own code)
-def audio_encoder_forward(sd, wave: torch.Tensor, cfg: EncoderCfg) -> torch.Tensor:
+def audio_encoder_forward(sd, wave: torch.Tensor, cfg: EncoderCfg, reg=None) -> torch.Tensor:
     """REF/model/audio_encoder.py:56-88, `pool` branch: last_hidden_state -> AvgPool1d(kernel, stride) over time
     (:59-63) -> embed_projection Linear (:87). (B, T0) -> (B, A, llm_dim)."""
-    enc = hubert_last_hidden_state(sd, wave, cfg)
+    enc = hubert_last_hidden_state(sd, wave, cfg, reg=reg)
     pooled = F.avg_pool1d(enc.transpose(1, 2), kernel_size=cfg.pool_kernel, stride=cfg.pool_stride).transpose(1, 2)
     return F.linear(pooled, sd["embed_projection.weight"], sd["embed_projection.bias"])
 

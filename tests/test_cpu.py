@@ -363,3 +363,96 @@ def test_whisper_log_mel_oracle_matches_transformers_extractor():
     ours = rm.whisper_log_mel(padded, fe.mel_filters)
     assert ours.shape == feats.shape == (80, 3000)
     assert float(np.abs(ours - feats).max()) < 2e-4
+
+
+# ----------------------------------------------------------------------------------------------------------
+# train-mode regularisers
+def test_train_mode_oracle_matches_reference_golden():
+    """The oracle's train-mode HuBERT (dropout sites, LayerDrop, SpecAugment under the explicit masks of
+    oracle/regularizers.py) against the fixture produced by the REFERENCE's AudioEncoder in .train() mode with HF's
+    randomness replaced by the same masks (oracle/make_golden.py:run_train_mode_case): outputs and gradients."""
+    import dataclasses
+    import numpy as np
+    from oracle import configs, reference_math as rm, regularizers as rg
+    gold = torch.load(os.path.join(GOLDEN, "tiny_hubert_train_mode.pt"), weights_only=False)
+    cfg = dataclasses.replace(configs.TINY_ENCODER, layers=gold["enc_cfg"]["layers"])
+    sd = configs.make_encoder_state_dict(cfg, seed=gold["enc_seed"])
+    sd["encoder.masked_spec_embed"] = gold["masked_spec_embed"]
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    reg = rg.OracleRegularizers(seed=gold["seed"], layer_skip=gold["layer_skip"].numpy(),
+                                time_mask=gold["time_mask"].numpy())
+    out = rm.audio_encoder_forward(sd, gold["wave"], cfg, reg=reg)
+    assert rel_l2(out.detach(), gold["audio_embeds"]) < 1e-5
+    names = [k for k, g in gold["grads"].items() if g is not None]
+    grads = torch.autograd.grad((out * gold["R"]).sum(), [sd[k] for k in names], allow_unused=True)
+    for k, g in zip(names, grads):
+        ref = gold["grads"][k]
+        if float(ref.norm()) == 0.0:  # the LayerDrop-skipped layer
+            assert g is None or float(g.norm()) == 0.0, k
+        else:
+            assert rel_l2(g, ref) < 1e-4, k
+    # and the masks really bite: the eval-mode output is far away
+    with torch.no_grad():
+        ev = rm.audio_encoder_forward({k: (v.detach() if torch.is_tensor(v) else v) for k, v in sd.items()},
+                                      gold["wave"], cfg)
+    assert rel_l2(ev, gold["audio_embeds"]) > 0.2
+
+
+def test_mask_generator_statistics():
+    """The counter-based generator (oracle restatement of csrc/rng.cuh): keep rate = 1 - p, streams independent."""
+    import numpy as np
+    from oracle import regularizers as rg
+    e = np.arange(1 << 18, dtype=np.uint64)
+    for p in (0.05, 0.1, 0.5):
+        k = rg.keep(e, 1234567, rg.site_ff_act(3), 0, 0, p)
+        assert abs(float(k.mean()) - (1 - p)) < 4e-3
+    a = rg.keep(e, 42, rg.site_attn_out(0), 0, 0, 0.5)
+    for other in (rg.keep(e, 43, rg.site_attn_out(0), 0, 0, 0.5), rg.keep(e, 42, rg.site_attn_out(1), 0, 0, 0.5),
+                  rg.keep(e, 42, rg.site_attn_prob(0), 1, 0, 0.5), rg.keep(e, 42, rg.site_attn_prob(0), 0, 1, 0.5)):
+        assert abs(float((a == other).mean()) - 0.5) < 5e-3  # uncorrelated with any other stream
+    assert abs(float((a[1:] == a[:-1]).mean()) - 0.5) < 5e-3  # and along the element index
+    assert rg.keep(e, 42, 1, 0, 0, 0.0).all() and rg.threshold(0.0) == 0
+    m = rg.attention_multiplier(7, 2, 0.1, 1, 2, 64)
+    assert set(torch.unique(m).tolist()) == {0.0, float(np.float32(1) / (np.float32(1) - np.float32(0.1)))}
+
+
+def test_spec_augment_time_mask_follows_hf_sampling():
+    """compute_time_mask (host side of SpecAugment) against HF's _compute_mask_indices
+    (TF/models/hubert/modeling_hubert.py, the reference's dependency): same span structure and the same mean number
+    of masked frames."""
+    import numpy as np
+    from llm_speech_summarization_b200.regularizers import compute_time_mask
+    rng = np.random.default_rng(0)
+    ours = np.stack([compute_time_mask(4, 499, 0.05, 10, 2, rng) for _ in range(200)])
+    assert ours.shape == (200, 4, 499) and ours.dtype == bool
+    per_row = ours.sum(-1)
+    assert per_row.min() >= 10 and per_row.max() <= 30      # 2..3 spans of 10 frames, overlaps allowed
+    # every masked run is a union of length-10 spans: no run shorter than 10
+    for row in ours.reshape(-1, 499)[:200]:
+        d = np.diff(np.concatenate([[0], row.astype(np.int8), [0]]))
+        runs = np.flatnonzero(d == -1) - np.flatnonzero(d == 1)
+        assert runs.min() >= 10
+    assert compute_time_mask(2, 24, 0.05, 10, 2, rng).sum(-1).max() <= 20   # capped at frames // mask_length spans
+    with pytest.raises(ValueError):
+        compute_time_mask(1, 5, 0.05, 10, 2, rng)
+    hub = pytest.importorskip("transformers.models.hubert.modeling_hubert")
+    np.random.seed(0)
+    theirs = np.stack([hub._compute_mask_indices((4, 499), 0.05, 10, min_masks=2) for _ in range(200)])
+    assert abs(float(ours.sum(-1).mean()) - float(theirs.sum(-1).mean())) < 0.6
+
+
+def test_regularizer_draw_is_reproducible_and_layerdrop_rate():
+    from llm_speech_summarization_b200.regularizers import RegularizerConfig, draw
+    from llm_speech_summarization_b200.config import EncoderArch
+    cfg = RegularizerConfig.from_arch(EncoderArch())
+    assert (cfg.hidden_dropout, cfg.layerdrop, cfg.mask_time_prob, cfg.mask_time_length) == (0.1, 0.1, 0.05, 10)
+    g1, g2 = torch.Generator().manual_seed(3), torch.Generator().manual_seed(3)
+    a, b = draw(cfg, 2, 499, 24, "cpu", g1), draw(cfg, 2, 499, 24, "cpu", g2)
+    assert a.seed == b.seed and (a.layer_skip == b.layer_skip).all() and torch.equal(a.time_mask, b.time_mask)
+    c = draw(cfg, 2, 499, 24, "cpu", g1)
+    assert c.seed != a.seed
+    g = torch.Generator().manual_seed(1)
+    skips = sum(int(draw(cfg, 1, 499, 24, "cpu", g).layer_skip.sum()) for _ in range(200))
+    assert abs(skips / (200 * 24) - 0.1) < 0.02
+    off = RegularizerConfig(apply_spec_augment=False)
+    assert draw(off, 1, 499, 24, "cpu", g).time_mask is None

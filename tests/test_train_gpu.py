@@ -235,3 +235,170 @@ def test_whisper_encoder_backward_matches_oracle_autograd(cuda, B):
         if e > 4e-2:
             bad[k] = e
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:10]
+
+
+# ----------------------------------------------------------------------------------------------------------
+# train-mode regularisers of the HuBERT encoder: dropout sites, LayerDrop,
+# SpecAugment. Exact-mask protocol: the kernels regenerate their keep/drop decisions from (seed, site, element), the
+# oracle is run under the SAME decisions (oracle/regularizers.py), so outputs and gradients are compared with the
+# tolerances of the deterministic step; the golden fixture holds the REFERENCE's own train-mode module outputs.
+def test_drop_mask_stream_is_bit_exact_with_the_oracle_generator(cuda):
+    import ctypes as C
+    import numpy as np
+    from oracle import regularizers as rg
+    from llm_speech_summarization_b200 import _lib
+    lib = _lib.load()
+    for seed, site, a, b, p, first in [(1, rg.SITE_FEAT_PROJ, 0, 0, 0.1, 0), (2 ** 61 + 12345, rg.site_ff_act(23), 0, 0, 0.1, 7),
+                                       (987654321987, rg.site_attn_prob(5), 31, 15, 0.1, (498 << 16) | 480),
+                                       (5, rg.SITE_POS_ADD, 0, 0, 0.5, 2 ** 32 - 5000)]:
+        n = 4096
+        out = torch.empty(n, dtype=torch.uint8, device=cuda)
+        _lib.check(lib.b2s_drop_mask_dump(out.data_ptr(), n, seed, site, a, b, p, first, None), "drop_mask_dump")
+        torch.cuda.synchronize()
+        e = (np.arange(n, dtype=np.uint64) + np.uint64(first)) & np.uint64(0xFFFFFFFF)
+        ref = rg.keep(e, seed, site, a, b, p)
+        assert np.array_equal(out.cpu().numpy().astype(bool), ref), (seed, site)
+
+
+def _train_mode_setup(cuda, gold):
+    import dataclasses
+    from types import SimpleNamespace as NS
+    from oracle import configs
+    from helpers import ns_config
+    from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
+    enc_cfg = dataclasses.replace(configs.TINY_ENCODER, layers=gold["enc_cfg"]["layers"])
+    enc_sd = configs.make_encoder_state_dict(enc_cfg, seed=gold["enc_seed"])
+    enc_sd["encoder.masked_spec_embed"] = gold["masked_spec_embed"]
+    enc = AudioEncoder(ns_config(enc_cfg, configs.TINY_LLAMA), cuda)
+    enc.load_state_dict(enc_sd, strict=True)
+    enc.train().to(cuda)
+    return enc_cfg, enc_sd, enc
+
+
+def _draw_from(gold, cuda, cfg=None):
+    from llm_speech_summarization_b200.regularizers import RegularizerConfig, RegularizerDraw
+    return RegularizerDraw(seed=int(gold["seed"]), layer_skip=gold["layer_skip"].numpy().astype("uint8").copy(),
+                           time_mask=gold["time_mask"].reshape(-1).to(torch.uint8).to(cuda),
+                           cfg=cfg or RegularizerConfig())
+
+
+def test_encoder_train_mode_matches_reference_golden_and_oracle(cuda):
+    """forward_train / backward under dropout + LayerDrop + SpecAugment vs (a) the reference's own train-mode module
+    (golden fixture) and (b) autograd through the oracle under the same masks, for EVERY parameter."""
+    import os
+    from helpers import GOLDEN
+    from oracle import reference_math as rm, regularizers as rg
+    gold = torch.load(os.path.join(GOLDEN, "tiny_hubert_train_mode.pt"), weights_only=False)
+    enc_cfg, enc_sd, enc = _train_mode_setup(cuda, gold)
+    out = enc.forward_train(gold["wave"].to(cuda), draw=_draw_from(gold, cuda))
+    err = rel_l2(out.cpu(), gold["audio_embeds"])
+    assert err < 2e-2, err                                     # north-star tolerance for the projected embeddings
+    enc.backward(gold["R"].to(cuda))
+    enc.flush_grads()
+    got = {k: p.grad.cpu().float() for k, p in enc.named_parameters() if p.grad is not None}
+    for k, g in gold["grads"].items():
+        if g is None:
+            continue
+        if float(g.norm()) == 0.0:                             # parameters of the LayerDrop-skipped layer
+            assert k not in got or float(got[k].norm()) == 0.0, k
+        else:
+            assert rel_l2(got[k], g) < 4e-2, (k, rel_l2(got[k], g))
+    # every parameter against the oracle's autograd under the same masks
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in enc_sd.items()}
+    reg = rg.OracleRegularizers(seed=int(gold["seed"]), layer_skip=gold["layer_skip"].numpy(),
+                                time_mask=gold["time_mask"].numpy())
+    o = rm.audio_encoder_forward(sd, gold["wave"], enc_cfg, reg=reg)
+    names = [k for k, v in sd.items() if torch.is_tensor(v) and v.requires_grad]
+    grads = torch.autograd.grad((o * gold["R"]).sum(), [sd[k] for k in names], allow_unused=True)
+    bad = {}
+    for k, g in zip(names, grads):
+        if g is None or float(g.norm()) < 1e-6:
+            assert k not in got or float(got[k].norm()) < 1e-2, k
+            continue
+        e = rel_l2(got[k], g)
+        if e > 4e-2:
+            bad[k] = e
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:12]
+    assert float(got["encoder.masked_spec_embed"].norm()) > 0
+
+
+def test_each_regulariser_alone_and_none_equals_eval(cuda):
+    """One regulariser at a time (isolates every site's forward AND backward), and the all-off block is bit-identical
+    to the deterministic path."""
+    import os
+    import numpy as np
+    from helpers import GOLDEN
+    from oracle import reference_math as rm, regularizers as rg
+    from llm_speech_summarization_b200.regularizers import RegularizerConfig
+    gold = torch.load(os.path.join(GOLDEN, "tiny_hubert_train_mode.pt"), weights_only=False)
+    enc_cfg, enc_sd, enc = _train_mode_setup(cuda, gold)
+    wave, R = gold["wave"], gold["R"]
+    L = enc_cfg.layers
+    base = enc.forward_train(wave.to(cuda)).clone()            # no draw, enc.regularizers is None -> deterministic
+    off = RegularizerConfig(0.0, 0.0, 0.0, 0.0, 0.0, False)
+    d = _draw_from(gold, cuda, off)
+    d.layer_skip[:] = 0
+    d.time_mask = None
+    assert torch.equal(enc.forward_train(wave.to(cuda), draw=d), base)
+    cases = {"feat_proj": dict(p_feat_proj=0.3), "hidden": dict(p_hidden=0.3), "attention": dict(p_attention=0.3),
+             "activation": dict(p_activation=0.3), "layerdrop": dict(layer_skip=np.array([1] + [0] * (L - 1))),
+             "specaug": dict(time_mask=gold["time_mask"].numpy())}
+    names = [k for k, v in enc_sd.items() if v.is_floating_point()]
+    for label, kw in cases.items():
+        ps = dict(p_feat_proj=0.0, p_hidden=0.0, p_attention=0.0, p_activation=0.0)
+        ps.update({k: v for k, v in kw.items() if k.startswith("p_")})
+        reg = rg.OracleRegularizers(seed=99 + len(label), layer_skip=kw.get("layer_skip"), time_mask=kw.get("time_mask"),
+                                    **ps)
+        cfg = RegularizerConfig(ps["p_feat_proj"], ps["p_hidden"], ps["p_attention"], ps["p_activation"], 0.0, False)
+        d = _draw_from(gold, cuda, cfg)
+        d.seed = reg.seed
+        d.layer_skip = (np.zeros(L, dtype=np.uint8) if reg.layer_skip is None else reg.layer_skip.astype(np.uint8))
+        d.time_mask = None if reg.time_mask is None else torch.from_numpy(reg.time_mask.reshape(-1).astype(np.uint8)).to(cuda)
+        for p in enc.parameters():
+            p.grad = None
+        enc._grads = None
+        out = enc.forward_train(wave.to(cuda), draw=d)
+        enc.backward(R.to(cuda))
+        enc.flush_grads()
+        sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in enc_sd.items()}
+        o = rm.audio_encoder_forward(sd, wave, enc_cfg, reg=reg)
+        assert rel_l2(out.cpu(), o.detach()) < 2e-2, (label, rel_l2(out.cpu(), o.detach()))
+        assert rel_l2(o.detach(), base.cpu()) > 0.02, label    # the regulariser did something
+        grads = torch.autograd.grad((o * R).sum(), [sd[k] for k in names], allow_unused=True)
+        got = dict(enc.named_parameters())
+        tot_ref = torch.cat([g.reshape(-1) for g in grads if g is not None])
+        tot_got = torch.cat([got[k].grad.cpu().float().reshape(-1) for k, g in zip(names, grads) if g is not None])
+        assert rel_l2(tot_got, tot_ref) < 3e-2, (label, rel_l2(tot_got, tot_ref))
+
+
+def test_trainer_with_regularisers_runs_and_is_reproducible(cuda):
+    """EncoderTrainer(regularize=True): train-mode step end to end; same generator seed -> same losses and the same
+    parameter update; masked_spec_embed is optimised; a different seed changes the loss."""
+    from llm_speech_summarization_b200.step import AudioPromptStep
+    from llm_speech_summarization_b200.training import EncoderTrainer
+    configs, enc_cfg, llm_cfg, enc_sd, llm_sd = _tiny()
+    utts = [configs.synthetic_utterance(llm_cfg, i, 8000, T=5 + i, R=4 + i) for i in range(2)]
+
+    def run(seed):
+        cfg, enc, llm = build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, cuda)
+        tok = configs.stub_tokenizer(llm_cfg)
+        step = AudioPromptStep(enc, llm, tok, llm_cfg.llm_type, fd_loss_connector_layers=[0, 1, 2])
+        tr = EncoderTrainer(step, enc, llm, lr=1e-3, grad_accum_interval=2, total_optimizer_steps=10, regularize=True,
+                            generator=torch.Generator().manual_seed(seed))
+        assert enc.training and enc.regularizers is not None
+        losses = []
+        for i, (wave, t, r) in enumerate(utts):
+            out = tr.train_step(wave[None, :].to(cuda), [t], [r])
+            losses.append(float(out["total_loss"][0]))
+            assert out["optimizer_step"] == (i == 1)
+        return losses, {k: v.detach().clone() for k, v in enc.state_dict().items()}
+
+    l1, p1 = run(5)
+    l2, p2 = run(5)
+    l3, _ = run(6)
+    assert l1 == l2   # both micro-batches run before the first update: forward determinism under a fixed seed
+    # (the parameter update itself goes through fp32 atomics in the wgrad GEMMs: equal up to summation order)
+    big = "encoder.encoder.layers.0.feed_forward.intermediate_dense.weight"
+    assert rel_l2(p1[big].float().cpu() - enc_sd[big], p2[big].float().cpu() - enc_sd[big]) < 0.1
+    assert l1 != l3 and all(x == x and abs(x) < 1e4 for x in l1 + l3)
+    assert not torch.equal(p1["encoder.masked_spec_embed"].cpu(), enc_sd["encoder.masked_spec_embed"])
