@@ -54,6 +54,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="prefill", choices=["prefill", "train"],
                     help="prefill = configs[1] (default, the metric's configuration); train = configs[2]")
+    ap.add_argument("--regularize", default="none", choices=["none", "dropout", "all"],
+                    help="train workload: HF train-mode regularisers of the encoder (REF/trainer.py:258). 'dropout' = "
+                         "every dropout site + SpecAugment (same work as the deterministic step plus the mask "
+                         "generation), 'all' = also LayerDrop (skips ~10%% of the encoder layers, like the reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts", type=int, default=3, help="utterances timed for the CPU baseline sample")
     ap.add_argument("--profile-mode", action="store_true",
@@ -232,8 +236,8 @@ def run_reference(args):
 
 METRIC_TRAIN = "utterances/sec (10 s audio, training step: encoder+prefill+KD loss forward, backward, AdamW)"
 WORKLOAD_TRAIN = ("configs[2] Llama-3.2-3B + HuBERT-large training step (encoder/projector trainable, LLM frozen), "
-                  "CE + logit-KD + FD loss, synthetic 10 s utterances (L_audio=200, L_text=117, R=64), deterministic "
-                  "(no dropout/LayerDrop/SpecAugment)")
+                  "CE + logit-KD + FD loss, synthetic 10 s utterances (L_audio=200, L_text=117, R=64); train-mode "
+                  "regularisers per config.regularize (none = deterministic step)")
 WORKLOAD = ("configs[1] Llama-3.2-3B + HuBERT-large audio-prompt forward: encoder + packed student&teacher prefill "
             "+ fused CE/KD/FD loss, synthetic 10 s utterances (L_audio=200, L_text=117, R=64)")
 
@@ -293,7 +297,10 @@ def main():
     if train:
         from llm_speech_summarization_b200.training import EncoderTrainer
         trainer = EncoderTrainer(step, enc, llm, lr=5e-5, betas=(0.9, 0.999), grad_accum_interval=B * world,
-                                 total_optimizer_steps=10 ** 6)
+                                 total_optimizer_steps=10 ** 6, regularize=args.regularize != "none",
+                                 generator=torch.Generator().manual_seed(1234 + rank))
+        if args.regularize == "dropout":
+            enc.regularizers.layerdrop = 0.0
 
     n_pool = 2  # rotate through distinct micro-batches
     host = [synth_batch(B, la.vocab, 1000 * (rank + 1) + i) for i in range(n_pool)]
@@ -399,7 +406,7 @@ def main():
                 "config": {"workload": workload, "utterances_per_step_per_gpu": B, "parallelism": f"dp{world}",
                            "l2": "no flush needed: every step streams ~7 GB of weights and >2 GB of activations "
                                  "(>> 126 MB L2); two distinct micro-batches alternate",
-                           "timed": timed},
+                           "timed": timed, **({"regularize": args.regularize} if train else {})},
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

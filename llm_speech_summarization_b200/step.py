@@ -99,6 +99,7 @@ class AudioPromptStep:
                  fd_loss_weight: float = 1.0, fd_loss_connector_layers: Sequence[int] = (0, 5, 11, 17, 23)):
         self.audio_encoder = audio_encoder
         self.llm = llm
+        self.llm_type = llm_type
         self.prefix, self.suffix = prompt_ids(tokenizer, llm_type)
         self.use_ld, self.use_fd = use_ld_loss, use_fd_loss
         self.w_ntp, self.w_ld, self.w_fd = ntp_loss_weight, ld_loss_weight, fd_loss_weight
@@ -177,6 +178,23 @@ class AudioPromptStep:
             out["kd_stats"] = res
             out["plan"] = plan
         return out
+
+    @torch.no_grad()
+    def validation_losses(self, waves: torch.Tensor, text_ids, resp_ids) -> Dict[str, torch.Tensor]:
+        """Per-utterance next-token losses of the audio-prompt AND the text-prompt sequence (REF/trainer.py:438-451:
+        `llm_audio_output.loss`, `llm_text_output.loss`), eval mode, from ONE packed pass. The fused loss kernel gives
+        the student CE; called with the roles swapped it gives the text-prompt CE."""
+        saved = self.use_ld, self.use_fd
+        self.use_ld, self.use_fd = True, False  # teacher sequence needed, no taps
+        try:
+            out = self.forward_losses(waves, text_ids, resp_ids, keep=True)
+        finally:
+            self.use_ld, self.use_fd = saved
+        plan = out["plan"]
+        swapped = ops.kd_ce_loss(out["teacher_logits"], out["student_logits"], plan.labels, plan.row_offsets,
+                                 scale_kd=0.0, scale_ce=1.0)
+        return {"audio_ntp_loss": out["ntp_loss"], "text_ntp_loss": swapped.loss_ntp,
+                "audio_embeds": out["audio_embeds"]}
 
     @torch.no_grad()
     def llm_forward_backward(self, audio: torch.Tensor, text_ids, resp_ids, loss_scale: float = 1.0,

@@ -218,6 +218,57 @@ class EncoderTrainer:
         stacked = torch.stack([out[k] for k in keys]).cpu()
         return {k: stacked[i] for i, k in enumerate(keys)}
 
+    @torch.no_grad()
+    def validate(self, batches, epoch: int = 0, *, num_generate_samples: int = 0, tokenizer=None, writer=None,
+                 save_path: Optional[str] = None) -> Dict:
+        """REF/trainer.py:400-528. `batches` yields (waves CUDA (B, T0), text_ids, resp_ids) like `train_step`.
+        Encoder in eval mode; per-utterance next-token NLL of the audio-prompt and the text-prompt sequence; perplexity
+        = exp(mean NLL) over the whole set (:502-505); for the first `num_generate_samples` utterances both prompts
+        are decoded greedily with max_new_tokens = 2 * (number of audio embeddings) (:460-476, :530-537); the
+        checkpoint of :516-526 is written to `save_path` when given. `writer` (optional) receives the reference's
+        LogWriter calls. The encoder's train/eval mode is restored on exit."""
+        from .utils import merge_prompt_tokens
+        enc, llm = self.audio_encoder, self.step_fn.llm
+        was_training = enc.training
+        enc.eval()
+        audio_nlls, text_nlls, audio_resp, text_resp = [], [], [], []
+        seen = 0
+        try:
+            for waves, text_ids, resp_ids in batches:
+                out = self.step_fn.validation_losses(waves, text_ids, resp_ids)
+                audio_nlls.append(out["audio_ntp_loss"])
+                text_nlls.append(out["text_ntp_loss"])
+                if writer is not None:
+                    for v in out["audio_ntp_loss"].tolist():
+                        writer.log_validation({"ntp_loss": v}, self.step)
+                for b in range(waves.shape[0]):
+                    if seen >= num_generate_samples:
+                        break
+                    seen += 1
+                    emb = out["audio_embeds"][b:b + 1].to(torch.bfloat16)
+                    n_new = 2 * emb.shape[1]
+                    llm_type = self.step_fn.llm_type
+                    prompts = [merge_prompt_tokens(emb, tokenizer, llm.model.embed_tokens, llm_type, emb.device),
+                               merge_prompt_tokens(llm.model.embed_tokens(torch.as_tensor(text_ids[b])[None].to(
+                                   emb.device)), tokenizer, llm.model.embed_tokens, llm_type, emb.device)]
+                    for dst, pe in zip((audio_resp, text_resp), prompts):
+                        ids = llm.generate(input_ids=None, inputs_embeds=pe, max_new_tokens=n_new)
+                        dst.append(tokenizer.batch_decode(ids, skip_special_tokens=True,
+                                                          clean_up_tokenization_spaces=True)[0]
+                                   if hasattr(tokenizer, "batch_decode") else ids[0].tolist())
+        finally:
+            enc.train(was_training)
+        res = {"audio_perplexity": float(torch.exp(torch.cat(audio_nlls).mean())),
+               "text_perplexity": float(torch.exp(torch.cat(text_nlls).mean())),
+               "audio_nlls": torch.cat(audio_nlls), "text_nlls": torch.cat(text_nlls),
+               "audio_responses": audio_resp, "text_responses": text_resp}
+        if writer is not None:
+            writer.log_validation_perplexity(res["audio_perplexity"], "audio", self.step)
+            writer.log_validation_perplexity(res["text_perplexity"], "text", self.step)
+        if save_path is not None:
+            torch.save(self.checkpoint(epoch), save_path)
+        return res
+
     def checkpoint(self, epoch: int, legacy_weight_norm_keys: bool = False) -> Dict:
         """Same keys as REF/trainer.py:518-526. `legacy_weight_norm_keys=True` spells the positional conv's weight-norm
         parameters `weight_g` / `weight_v` (what the reference's pinned torch 2.0 writes and expects); the default is

@@ -402,3 +402,42 @@ def test_trainer_with_regularisers_runs_and_is_reproducible(cuda):
     assert rel_l2(p1[big].float().cpu() - enc_sd[big], p2[big].float().cpu() - enc_sd[big]) < 0.1
     assert l1 != l3 and all(x == x and abs(x) < 1e4 for x in l1 + l3)
     assert not torch.equal(p1["encoder.masked_spec_embed"].cpu(), enc_sd["encoder.masked_spec_embed"])
+
+
+def test_validate_matches_oracle_perplexities(cuda):
+    """EncoderTrainer.validate (REF/trainer.py:400-528): audio / text prompt perplexities vs the oracle's CE on the
+    same utterances, greedy generations of both prompts, checkpoint written, train mode restored."""
+    import math
+    import os
+    import tempfile
+    from oracle import reference_math as rm
+    from llm_speech_summarization_b200.step import AudioPromptStep
+    from llm_speech_summarization_b200.training import EncoderTrainer
+    configs, enc_cfg, llm_cfg, enc_sd, llm_sd = _tiny()
+    cfg, enc, llm = build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, cuda)
+    tok = configs.stub_tokenizer(llm_cfg)
+    step = AudioPromptStep(enc, llm, tok, llm_cfg.llm_type, fd_loss_connector_layers=[0, 1, 2])
+    tr = EncoderTrainer(step, enc, llm, regularize=True)
+    utts = [configs.synthetic_utterance(llm_cfg, i, 6000, T=5 + i, R=4 + i) for i in range(3)]
+    a_ref, t_ref = [], []
+    with torch.no_grad():
+        for wave, t, r in utts:
+            o = rm.train_step_losses(enc_sd, llm_sd, enc_cfg, llm_cfg, tok, wave, t, r, fd_layers=[0, 1, 2], keep=True)
+            a_ref.append(float(o["ntp_loss"]))
+            lt = o["teacher_logits"].reshape(-1, llm_cfg.vocab)          # last R rows of the text-prompt sequence
+            t_ref.append(float(torch.nn.functional.cross_entropy(lt[:-1], torch.as_tensor(r)[1:].long())))
+    batches = [(torch.stack([utts[0][0], utts[1][0]]).to(cuda), [utts[0][1], utts[1][1]], [utts[0][2], utts[1][2]]),
+               (utts[2][0][None].to(cuda), [utts[2][1]], [utts[2][2]])]
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "epoch_0_step_0.pt")
+        res = tr.validate(batches, epoch=0, num_generate_samples=1, tokenizer=tok, save_path=path)
+        ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"audio_encoder", "optimizer", "lr_scheduler", "epoch", "step"}
+    assert enc.training                                                   # restored (regularize=True put it in train)
+    assert abs(res["audio_perplexity"] / math.exp(sum(a_ref) / 3) - 1) < 2e-2
+    assert abs(res["text_perplexity"] / math.exp(sum(t_ref) / 3) - 1) < 2e-2
+    assert torch.allclose(res["audio_nlls"].cpu(), torch.tensor(a_ref), rtol=1e-2)
+    assert torch.allclose(res["text_nlls"].cpu(), torch.tensor(t_ref), rtol=1e-2)
+    assert len(res["audio_responses"]) == len(res["text_responses"]) == 1
+    n_audio = rm.compute_num_audio_embeds(6000)
+    assert 1 <= len(res["audio_responses"][0]) <= 2 * (n_audio + 1)
