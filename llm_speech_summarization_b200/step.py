@@ -132,7 +132,7 @@ class AudioPromptStep:
 
     @torch.no_grad()
     def forward_losses(self, waves: torch.Tensor, text_ids, resp_ids, plan: Optional[StepPlan] = None,
-                       keep: bool = False) -> Dict[str, torch.Tensor]:
+                       keep: bool = False, num_audio_embeds: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """waves: CUDA fp32 (B, T0), equal-length utterances (the reference's collate zero-pads a batch to one
         length, REF/trainer.py:146-149; batch-1 has no padding). Returns per-utterance device tensors
         ntp_loss / ld_loss / fd_loss / total_loss of shape (B,)."""
@@ -141,6 +141,10 @@ class AudioPromptStep:
         dev = waves.device
         B = waves.shape[0]
         audio = self.audio_encoder.forward_fp32(waves)  # (B, A, C) fp32
+        if num_audio_embeds is not None and num_audio_embeds < audio.shape[1]:
+            # the trainer's un-padding (REF/trainer.py:280-291): Whisper's fixed 30 s window gives 374 pooled frames,
+            # compute_num_audio_embeds keeps the ones covered by audio
+            audio = audio[:, :num_audio_embeds].contiguous()
         A, Cdim = audio.shape[1], audio.shape[2]
         if plan is None:
             plan = self.plan(A, text_ids, resp_ids, dev)
@@ -180,14 +184,15 @@ class AudioPromptStep:
         return out
 
     @torch.no_grad()
-    def validation_losses(self, waves: torch.Tensor, text_ids, resp_ids) -> Dict[str, torch.Tensor]:
+    def validation_losses(self, waves: torch.Tensor, text_ids, resp_ids,
+                          num_audio_embeds: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """Per-utterance next-token losses of the audio-prompt AND the text-prompt sequence (REF/trainer.py:438-451:
         `llm_audio_output.loss`, `llm_text_output.loss`), eval mode, from ONE packed pass. The fused loss kernel gives
         the student CE; called with the roles swapped it gives the text-prompt CE."""
         saved = self.use_ld, self.use_fd
         self.use_ld, self.use_fd = True, False  # teacher sequence needed, no taps
         try:
-            out = self.forward_losses(waves, text_ids, resp_ids, keep=True)
+            out = self.forward_losses(waves, text_ids, resp_ids, keep=True, num_audio_embeds=num_audio_embeds)
         finally:
             self.use_ld, self.use_fd = saved
         plan = out["plan"]
@@ -249,7 +254,8 @@ class AudioPromptStep:
 
     @torch.no_grad()
     def forward_backward(self, waves: torch.Tensor, text_ids, resp_ids, loss_scale: float = 1.0,
-                         plan: Optional[StepPlan] = None, generator=None, draw=None) -> Dict[str, torch.Tensor]:
+                         plan: Optional[StepPlan] = None, generator=None, draw=None,
+                         num_audio_embeds: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """One training micro-batch (REF/trainer.py:270-374): encoder forward with kept activations -> LLM
         forward/backward -> encoder backward. Parameter gradients (x loss_scale) accumulate inside the encoder
         until `audio_encoder.flush_grads()`. `generator` / `draw` feed the encoder's train-mode regularisers
@@ -260,8 +266,14 @@ class AudioPromptStep:
             audio = self.audio_encoder.forward_train(waves, generator=generator, draw=draw)
         else:
             audio = self.audio_encoder.forward_train(waves)
+        A_full = audio.shape[1]
+        if num_audio_embeds is not None and num_audio_embeds < A_full:  # REF/trainer.py:280-291 (see forward_losses)
+            audio = audio[:, :num_audio_embeds].contiguous()
         out = self.llm_forward_backward(audio, text_ids, resp_ids, loss_scale=loss_scale, plan=plan)
-        self.audio_encoder.backward(out["d_audio_embeds"])
+        d = out["d_audio_embeds"]
+        if d.shape[1] < A_full:  # the cropped embeddings get no gradient
+            d = torch.nn.functional.pad(d, (0, 0, 0, A_full - d.shape[1]))
+        self.audio_encoder.backward(d)
         return out
 
     def __call__(self, waves_host: torch.Tensor, text_ids, resp_ids, device) -> Dict[str, float]:

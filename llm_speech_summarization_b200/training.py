@@ -190,12 +190,13 @@ class EncoderTrainer:
 
     @torch.no_grad()
     def train_step(self, waves: torch.Tensor, text_ids, resp_ids, last_batch: bool = False,
-                   plan=None) -> Dict[str, torch.Tensor]:
+                   plan=None, num_audio_embeds: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """One micro-batch of B utterances on this rank. The accumulation window counts utterances GLOBALLY:
         an optimizer step happens once world * (micro-batches * B) reaches grad_accum_interval (or at loader end)."""
         B = waves.shape[0]
         out = self.step_fn.forward_backward(waves, text_ids, resp_ids, loss_scale=1.0 / self.grad_accum_interval,
-                                            plan=plan, generator=self.generator)
+                                            plan=plan, generator=self.generator,
+                                            **({} if num_audio_embeds is None else {"num_audio_embeds": num_audio_embeds}))
         self._micro += B * self.world()
         self.step += 1
         out["optimizer_step"] = False
@@ -221,7 +222,7 @@ class EncoderTrainer:
     @torch.no_grad()
     def validate(self, batches, epoch: int = 0, *, num_generate_samples: int = 0, tokenizer=None, writer=None,
                  save_path: Optional[str] = None) -> Dict:
-        """REF/trainer.py:400-528. `batches` yields (waves CUDA (B, T0), text_ids, resp_ids) like `train_step`.
+        """REF/trainer.py:400-528. `batches` yields (waves CUDA (B, T0), text_ids, resp_ids[, num_audio_embeds]).
         Encoder in eval mode; per-utterance next-token NLL of the audio-prompt and the text-prompt sequence; perplexity
         = exp(mean NLL) over the whole set (:502-505); for the first `num_generate_samples` utterances both prompts
         are decoded greedily with max_new_tokens = 2 * (number of audio embeddings) (:460-476, :530-537); the
@@ -234,8 +235,10 @@ class EncoderTrainer:
         audio_nlls, text_nlls, audio_resp, text_resp = [], [], [], []
         seen = 0
         try:
-            for waves, text_ids, resp_ids in batches:
-                out = self.step_fn.validation_losses(waves, text_ids, resp_ids)
+            for batch in batches:
+                waves, text_ids, resp_ids = batch[:3]
+                out = self.step_fn.validation_losses(waves, text_ids, resp_ids,
+                                                     num_audio_embeds=batch[3] if len(batch) > 3 else None)
                 audio_nlls.append(out["audio_ntp_loss"])
                 text_nlls.append(out["text_ntp_loss"])
                 if writer is not None:

@@ -456,3 +456,31 @@ def test_regularizer_draw_is_reproducible_and_layerdrop_rate():
     assert abs(skips / (200 * 24) - 0.1) < 0.02
     off = RegularizerConfig(apply_spec_augment=False)
     assert draw(off, 1, 499, 24, "cpu", g).time_mask is None
+
+
+def test_trainer_collate_matches_reference_semantics():
+    """Trainer.collate_audio_batch_hubert / _whisper (REF/trainer.py:134-199): right zero-padding to the longest clip,
+    BOS stripped from the text ids and from row 0 of the nested response ids, everything else passed through."""
+    from llm_speech_summarization_b200.trainer import Trainer, WHISPER_WINDOW_SAMPLES
+    tr = object.__new__(Trainer)
+    data = [{"audio": {"array": torch.arange(5.0)}, "text": "a", "text_input_ids": torch.tensor([1, 7, 8]),
+             "response_input_ids": torch.tensor([[1, 4, 5, 6]]), "pool_ranges_4": [0]},
+            {"audio": {"array": torch.arange(3.0)}, "text": "b", "text_input_ids": torch.tensor([1, 9]),
+             "response_input_ids": torch.tensor([[1, 2]]), "pool_ranges_4": [1]}]
+    raw, padded, lens, texts, t_ids, r_ids, ranges = tr.collate_audio_batch_hubert(data)
+    assert lens == [5, 3] and texts == ["a", "b"] and ranges == [[0], [1]]
+    assert padded.shape == (2, 5) and padded.dtype == torch.float32
+    assert padded[1].tolist() == [0.0, 1.0, 2.0, 0.0, 0.0]
+    assert [t.tolist() for t in t_ids] == [[7, 8], [9]] and [r.tolist() for r in r_ids] == [[4, 5, 6], [2]]
+    _, pw, lens_w, _, t_w, r_w, _ = tr.collate_audio_batch_whisper(data)
+    assert pw.shape == (2, WHISPER_WINDOW_SAMPLES) and lens_w == [5, 3] and float(pw[0, 5:].abs().sum()) == 0.0
+    assert [t.tolist() for t in t_w] == [[7, 8], [9]] and [r.tolist() for r in r_w] == [[4, 5, 6], [2]]
+    # micro-batches: equal-length utterances are packed together, others run on their own, nothing is padded
+    tr.encoder_base = "hubert"
+    data3 = data + [dict(data[0], text="c")]
+    _, padded, lens, _, t_ids, r_ids, _ = tr.collate_audio_batch_hubert(data3)
+    micro = tr._micro_batches(padded, lens, t_ids, r_ids)
+    assert sorted((m[0].shape for m in micro)) == [(1, 3), (2, 5)] and all(m[3] is None for m in micro)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        from types import SimpleNamespace as NS
+        Trainer(NS(run_name="x", checkpoint_path=None), NS(), "cpu")

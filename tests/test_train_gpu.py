@@ -441,3 +441,60 @@ def test_validate_matches_oracle_perplexities(cuda):
     assert len(res["audio_responses"]) == len(res["text_responses"]) == 1
     n_audio = rm.compute_num_audio_embeds(6000)
     assert 1 <= len(res["audio_responses"][0]) <= 2 * (n_audio + 1)
+
+
+def test_trainer_dropin_runs_the_reference_loop(cuda, tmp_path):
+    """`Trainer(args, config, device).train()` (REF/train.py:25-27, REF/trainer.py:250-398): loop bookkeeping of the
+    reference -- `step` counts batches, an optimizer + scheduler step every grad_accum_interval batches and at loader
+    end, logging / validation intervals, checkpoint files in <checkpoint_dir>/<run_name>/, resume from a checkpoint."""
+    import os
+    from types import SimpleNamespace as NS
+    from helpers import ns_config
+    from llm_speech_summarization_b200.config import llm_arch_from_config
+    from llm_speech_summarization_b200.model.audio_llama import AudioLlamaForCausalLM
+    from llm_speech_summarization_b200.trainer import NullWriter, Trainer
+    configs, enc_cfg, llm_cfg, enc_sd, llm_sd = _tiny()
+    cfg = ns_config(enc_cfg, llm_cfg)
+    cfg.train = NS(num_gpus=1, num_workers=0, optimizer=NS(lr=1e-3, beta1=0.9, beta2=0.999), batch_size=1,
+                   grad_accum_interval=2, epochs=1, use_ld_loss=True, use_fd_loss=True, ntp_loss_weight=0.5,
+                   ld_loss_weight=0.5, fd_loss_weight=1.0, fd_loss_connector_layers=[0, 1, 2])
+    cfg.log = NS(checkpoint_dir=str(tmp_path / "ck"), log_dir=str(tmp_path / "logs"), log_interval=1,
+                 validation_interval=4, num_generate_samples=1)
+    llm = AudioLlamaForCausalLM(llm_arch_from_config(cfg))
+    llm.load_state_dict({k: v.to(torch.bfloat16) for k, v in llm_sd.items()}, strict=True)
+    tok = configs.stub_tokenizer(llm_cfg)
+
+    def item(i, samples):
+        wave, t, r = configs.synthetic_utterance(llm_cfg, i, samples, T=5 + i, R=4 + i)
+        bos = torch.tensor([llm_cfg.bos])
+        return {"audio": {"array": wave}, "text": f"utt {i}", "text_input_ids": torch.cat([bos, torch.as_tensor(t)]),
+                "response_input_ids": torch.cat([bos, torch.as_tensor(r)])[None], "pool_ranges_4": []}
+
+    train_set = [item(i, 5000 + 400 * (i % 2)) for i in range(5)]
+    val_set = [item(10 + i, 5000) for i in range(2)]
+    args = NS(run_name="run0", checkpoint_path=None, gpu_idx=0)
+    w = NullWriter()
+    tr = Trainer(args, cfg, cuda, tokenizer=tok, llm=llm, train_dataset=train_set, val_dataset=val_set, writer=w,
+                 regularize=True, generator=torch.Generator().manual_seed(0))
+    tr.audio_encoder.load_state_dict(enc_sd)
+    tr.audio_encoder.mark_weights_changed()
+    before = {k: v.detach().clone() for k, v in tr.audio_encoder.state_dict().items()}
+    tr.train()
+    assert tr.step == 5                                            # one per loader batch
+    assert tr.optimizer.step_count == 3                            # batches 2, 4 and the loader end (5)
+    assert tr.lr_scheduler.last_epoch == 3
+    assert len(w.scalars["train/ntp_loss"]) == 5 and len(w.scalars["learning_rate"]) == 5
+    assert [s for s, _ in w.scalars["validation/audio_perplexity"]] == [4, 5]   # interval + end of epoch
+    assert all(v == v and v > 1.0 for _, v in w.scalars["validation/text_perplexity"])
+    files = sorted(os.listdir(tmp_path / "ck" / "run0"))
+    assert files == ["epoch_0_step_4.pt", "epoch_0_step_5.pt"]
+    after = tr.audio_encoder.state_dict()
+    assert any(not torch.equal(after[k], before[k]) for k in before)
+    assert "llm_audio_responses/response_0" in w.texts
+    # resume (REF/trainer.py:112-132)
+    args2 = NS(run_name="run1", checkpoint_path=str(tmp_path / "ck" / "run0" / "epoch_0_step_5.pt"), gpu_idx=0)
+    tr2 = Trainer(args2, cfg, cuda, tokenizer=tok, llm=llm, train_dataset=train_set, val_dataset=val_set,
+                  writer=NullWriter(), regularize=False)
+    assert tr2.step == 5 and tr2.start_epoch == 0 and tr2.optimizer.step_count == 3
+    for k, v in tr2.audio_encoder.state_dict().items():
+        assert torch.equal(v.cpu(), after[k].cpu()), k
