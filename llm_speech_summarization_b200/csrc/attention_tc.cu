@@ -1,18 +1,25 @@
 // attention_tc.cu -- packed variable-length flash attention forward on tcgen05 / TMEM / TMA (sm_100a).
 //
-// One CTA per (sequence, query head, 128-query block); 5 warps:
+// Work item = (sequence, query head, 128-query block); persistent CTAs (as many as stay resident) walk the items.
+// 5 warps per CTA:
 //   warps 0-3 : softmax. Thread r owns query row r (TMEM lane r): it reads its row of S straight from TMEM
 //               (no cross-thread reductions) ONCE per block, masks only in partial / diagonal blocks, keeps the
 //               online-softmax state (reference max m, running sum l) in registers, writes P = exp2(S - m) as bf16
 //               into a 128B-swizzled K-major shared-memory tile, and moves the reference (rescaling O in TMEM) only
 //               when the row max outgrew it by 2^16 (lazy, deferred, warp-uniform).
-//   warp 4    : lane 0 issues TMA loads (Q once, K/V double-buffered) and all tcgen05.mma:
-//               S[128 x 128 keys] = Q K^T   (A = Q smem K-major, B = K smem K-major, fp32 accumulators in TMEM cols [0,128))
-//               O[128 x D]       += P V      (A = P smem K-major, B = V smem MN-major, accumulators in TMEM cols [128,128+D))
+//   warp 4    : lane 0 issues TMA loads (Q per item, K/V per step, 1 or 2 stages) and all tcgen05.mma:
+//               S[128 x BN keys] = Q K^T   (A = Q smem K-major, B = K smem K-major, fp32 accumulators in TMEM cols [0,BN))
+//               O[128 x D]      += P V      (A = P smem K-major, B = V smem MN-major, accumulators in TMEM cols [BN,BN+D))
+//               and runs ahead over item boundaries (next item's Q / first K/V in flight during the output store).
+// BN = 64 keys per step with single-buffered K/V is the default: 48 KiB + 128 TMEM columns per CTA at D = 64, so four
+// CTAs (16 softmax warps) share an SM -- the kernel is bound by the per-step latency chain, not by the tensor pipe
+// (profiles/r01_attention_configs.md).
 // Hand-offs are mbarriers (tcgen05.commit -> softmax, softmax -> MMA issuer); every wait is bounded.
 //
 // Covers HuBERT / Whisper (non-causal, D=64) and Llama / MiniChat (causal GQA, D=128); same C entry point and
 // semantics as attention.cu (TF/models/hubert/modeling_hubert.py:262-345, TF/models/llama/modeling_llama.py:225-289).
+#include <cstdio>
+#include <cstdlib>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -31,7 +38,7 @@ constexpr int kBM = 128;   // queries per CTA
 constexpr int kThreadsTc = 160;
 
 // BN = keys per step (128, or 64 for short sequences at D = 128 so that two CTAs fit on an SM)
-template <int D, int BN>
+template <int D, int BN, int KVS>
 struct AttnCfg {
   static constexpr int kQBytes = kBM * D * 2;
   static constexpr int kKBytes = BN * D * 2;
@@ -39,10 +46,11 @@ struct AttnCfg {
   static constexpr int kPBytes = kBM * BN * 2;
   // D = 64: single-buffered K/V keeps the CTA at ~81 KiB so two CTAs (2 x 256 TMEM columns) share an SM and overlap
   // each other's TMA / MMA / softmax phases; D = 128: one CTA per SM, K/V double-buffered inside it.
-  static constexpr int kKvStages = (D == 64 || BN == 64) ? 1 : 2;
-  static constexpr int kSmemBytes = kQBytes + kKvStages * (kKBytes + kVBytes) + kPBytes + 256 + 1024;
-  static constexpr int kTmemCols = 256;  // S: [0, BN), O: [128, 128 + D)
-  static constexpr int kOCol = 128;
+  static constexpr int kKvStages = KVS;  // K/V tiles in flight: 1 keeps the CTA small (more CTAs per SM), 2 prefetches
+  // the dynamic shared-memory window is declared 1024-byte aligned (128B-swizzle atoms), so no alignment slack
+  static constexpr int kSmemBytes = kQBytes + kKvStages * (kKBytes + kVBytes) + kPBytes + 256;
+  static constexpr int kOCol = BN;                                // S: [0, BN), O: [BN, BN + D)
+  static constexpr int kTmemCols = (BN + D) <= 128 ? 128 : 256;  // power of two >= BN + D
 };
 
 struct AttnParams {
@@ -55,6 +63,8 @@ struct AttnParams {
   int causal;
   float* lse;  // optional [rows, Hq]: log2-domain log-sum-exp of the scaled scores (saved for the backward)
   AttnDrop drop;  // attention-probability dropout (thresh 0 = off): softmax statistics stay those of the un-dropped row
+  int n_qblk;       // 128-query blocks per (sequence, head) = ceil(max_seqlen / 128)
+  int total_items;  // num_seqs * Hq * n_qblk
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -76,25 +86,51 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-template <int D, int BN, bool DROP>
+// One work item = (sequence, query head, 128-query block). The kernel is PERSISTENT: a CTA walks items
+// blockIdx.x, blockIdx.x + gridDim.x, ... with its TMEM columns, barriers and tensor-map prefetches set up once, and
+// the issuing thread runs ahead across item boundaries (Q and the first K/V tile of the next item are in flight while
+// the softmax warps store the current item's output), so the per-item fixed latencies that dominated the one-CTA-per-
+// item version at prompt lengths of a few hundred tokens are amortised. All barrier phases are tracked with running
+// counters (g = blocks processed by this CTA so far, items done so far).
+struct AttnItem {
+  int seq, h, hk, s0, L, q0, nblk;
+};
+
+template <int BN>
+__device__ __forceinline__ bool attn_decode_item(const AttnParams& p, int item, AttnItem* it) {
+  const int qb = item % p.n_qblk;
+  const int r = item / p.n_qblk;
+  it->h = r % p.Hq;
+  it->seq = r / p.Hq;
+  it->s0 = p.cu[it->seq];
+  it->L = p.cu[it->seq + 1] - it->s0;
+  it->q0 = qb * kBM;
+  if (it->q0 >= it->L) return false;
+  it->hk = it->h / (p.Hq / p.Hkv);
+  const int kv_len = p.causal ? min(it->L, it->q0 + kBM) : it->L;
+  it->nblk = (kv_len + BN - 1) / BN;
+  return true;
+}
+
+// first valid item at or after `item` (stride gridDim.x); returns total_items when there is none
+template <int BN>
+__device__ __forceinline__ int attn_next_item(const AttnParams& p, int item, AttnItem* it) {
+  for (; item < p.total_items; item += gridDim.x)
+    if (attn_decode_item<BN>(p, item, it)) return item;
+  return p.total_items;
+}
+
+template <int D, int BN, int KVS, bool DROP>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  using C = AttnCfg<D, BN>;
+  using C = AttnCfg<D, BN, KVS>;
   constexpr int kBN = BN;
   constexpr int kAtoms = D / 64;  // 64-element (128 B) column atoms per row
 
-  const int seq = blockIdx.z, h = blockIdx.y;
-  const int s0 = p.cu[seq];
-  const int L = p.cu[seq + 1] - s0;
-  const int q0 = blockIdx.x * kBM;
-  if (q0 >= L) return;  // uniform for the CTA
-  const int hk = h / (p.Hq / p.Hkv);
-  const int kv_len = p.causal ? min(L, q0 + kBM) : L;
-  const int nblk = (kv_len + kBN - 1) / kBN;
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = ptx::smem_u32(smem_raw);
+  if ((base & 1023u) != 0u) __trap();  // the swizzled tiles need 1024-byte alignment
   const uint32_t sQ = base;
   constexpr int kKvStages = C::kKvStages;
   const uint32_t sK = sQ + C::kQBytes;
@@ -102,7 +138,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const uint32_t sP = sV + kKvStages * C::kVBytes;
   const uint32_t bars = sP + C::kPBytes;
   const uint32_t bar_q = bars, bar_kv0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40;
-  const uint32_t tmem_slot = bars + 48;
+  const uint32_t bar_oe = bars + 48;  // softmax warps -> issuer: the item's O accumulator has been read out
+  const uint32_t tmem_slot = bars + 56;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -112,6 +149,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     ptx::mbar_init(bar_s, 1);
     ptx::mbar_init(bar_p, kBM);
     ptx::mbar_init(bar_o, 1);
+    ptx::mbar_init(bar_oe, kBM);
     ptx::fence_mbar_init();
   }
   if (warp == 4) ptx::tmem_alloc<1>(tmem_slot, C::kTmemCols);
@@ -127,70 +165,97 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       ptx::prefetch_tmap(&tmap_q);
       ptx::prefetch_tmap(&tmap_k);
       ptx::prefetch_tmap(&tmap_v);
-      ptx::mbar_arrive_expect_tx(bar_q, C::kQBytes);
+      auto load_q = [&](const AttnItem& it) {
+        ptx::mbar_arrive_expect_tx(bar_q, C::kQBytes);
 #pragma unroll
-      for (int a = 0; a < kAtoms; ++a)
-        ptx::tma_load_2d(&tmap_q, bar_q, sQ + a * (kBM * 128), p.q_col0 + h * D + a * 64, s0 + q0);
-      auto load_kv = [&](int j) {
-        const int st = j % kKvStages;
+        for (int a = 0; a < kAtoms; ++a)
+          ptx::tma_load_2d(&tmap_q, bar_q, sQ + a * (kBM * 128), p.q_col0 + it.h * D + a * 64, it.s0 + it.q0);
+      };
+      auto load_kv = [&](const AttnItem& it, int j, uint32_t g) {  // key block j of item `it` = CTA-global block g
+        const int st = g % kKvStages;
         ptx::mbar_arrive_expect_tx(bar_kv0 + 8 * st, C::kKBytes + C::kVBytes);
 #pragma unroll
         for (int a = 0; a < kAtoms; ++a) {
           ptx::tma_load_2d(&tmap_k, bar_kv0 + 8 * st, sK + st * C::kKBytes + a * (kBN * 128),
-                           p.k_col0 + hk * D + a * 64, s0 + j * kBN);
+                           p.k_col0 + it.hk * D + a * 64, it.s0 + j * kBN);
           ptx::tma_load_2d(&tmap_v, bar_kv0 + 8 * st, sV + st * C::kVBytes + a * (kBN * 128),
-                           p.v_col0 + hk * D + a * 64, s0 + j * kBN);
+                           p.v_col0 + it.hk * D + a * 64, it.s0 + j * kBN);
         }
       };
-      load_kv(0);
       constexpr uint32_t idesc_s = ptx::make_idesc_bf16_f32(kBM, kBN);
       constexpr uint32_t idesc_o = ptx::make_idesc_bf16_f32(kBM, D) | (1u << 16);  // B (= V) is MN-major
-      ptx::mbar_wait(bar_q, 0);
-      for (int j = 0; j < nblk; ++j) {
-        const int st = j % kKvStages;
-        if (kKvStages == 2 && j + 1 < nblk) {
-          // stage st^1 was last read by PV(j-1): refill it only after that MMA has retired
-          if (j >= 1) ptx::mbar_wait(bar_o, (j - 1) & 1);
-          load_kv(j + 1);
-        }
-        ptx::mbar_wait(bar_kv0 + 8 * st, (j / kKvStages) & 1);
-        ptx::tc_fence_after();
-        // S = Q K^T
+      AttnItem cur, nxt;
+      int item = attn_next_item<BN>(p, blockIdx.x, &cur);
+      uint32_t g = 0, items_done = 0;
+      if (item < p.total_items) {
+        load_q(cur);
+        load_kv(cur, 0, 0);
+      }
+      while (item < p.total_items) {
+        const int item_nxt = attn_next_item<BN>(p, item + gridDim.x, &nxt);
+        const bool have_nxt = item_nxt < p.total_items;
+        ptx::mbar_wait(bar_q, items_done & 1);
+        for (int j = 0; j < cur.nblk; ++j, ++g) {
+          const int st = g % kKvStages;
+          const bool last = j + 1 == cur.nblk;
+          const bool has_next = !last || have_nxt;
+          if (kKvStages == 2 && has_next) {
+            // stage st^1 was last read by PV(g-1): refill it only after that MMA has retired
+            if (g >= 1) ptx::mbar_wait(bar_o, (g - 1) & 1);
+            if (!last) load_kv(cur, j + 1, g + 1);
+            else load_kv(nxt, 0, g + 1);
+          }
+          ptx::mbar_wait(bar_kv0 + 8 * st, (g / kKvStages) & 1);
+          ptx::tc_fence_after();
+          // S = Q K^T
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t q_off = (k >> 2) * (kBM * 128) + (k & 3) * 32;  // 64-column atoms are kBM rows tall
-          const uint32_t k_off = (k >> 2) * (kBN * 128) + (k & 3) * 32;  // ... and kBN rows tall for K
-          ptx::umma_bf16<1>(tmem_base, ptx::make_kmajor_sw128_desc(sQ + q_off),
-                            ptx::make_kmajor_sw128_desc(sK + st * C::kKBytes + k_off), idesc_s, k > 0 ? 1u : 0u);
-        }
-        ptx::umma_commit<1>(bar_s);
-        // O += P V once the softmax warps have published P (and finished reading S / rescaling O)
-        ptx::mbar_wait(bar_p, j & 1);
-        ptx::tc_fence_after();
+          for (int k = 0; k < D / 16; ++k) {
+            const uint32_t q_off = (k >> 2) * (kBM * 128) + (k & 3) * 32;  // 64-column atoms are kBM rows tall
+            const uint32_t k_off = (k >> 2) * (kBN * 128) + (k & 3) * 32;  // ... and kBN rows tall for K
+            ptx::umma_bf16<1>(tmem_base, ptx::make_kmajor_sw128_desc(sQ + q_off),
+                              ptx::make_kmajor_sw128_desc(sK + st * C::kKBytes + k_off), idesc_s, k > 0 ? 1u : 0u);
+          }
+          ptx::umma_commit<1>(bar_s);
+          // O += P V once the softmax warps have published P (and finished reading S / rescaling O)
+          ptx::mbar_wait(bar_p, g & 1);
+          if (j == 0 && items_done > 0) ptx::mbar_wait(bar_oe, (items_done - 1) & 1);  // previous O read out
+          ptx::tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < kBN / 16; ++k) {
-          const uint64_t pdesc = ptx::make_kmajor_sw128_desc(sP + (k >> 2) * (kBM * 128) + (k & 3) * 32);
-          const uint64_t vdesc = ptx::make_mnmajor_sw128_desc(sV + st * C::kVBytes + k * 2048, kBN * 128);
-          ptx::umma_bf16<1>(tmem_base + C::kOCol, pdesc, vdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBN / 16; ++k) {
+            const uint64_t pdesc = ptx::make_kmajor_sw128_desc(sP + (k >> 2) * (kBM * 128) + (k & 3) * 32);
+            const uint64_t vdesc = ptx::make_mnmajor_sw128_desc(sV + st * C::kVBytes + k * 2048, kBN * 128);
+            ptx::umma_bf16<1>(tmem_base + C::kOCol, pdesc, vdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit<1>(bar_o);
+          // bar_p(g) has fired, so every S MMA of this item has retired: Q's tile can take the next item's rows
+          if (last && have_nxt) load_q(nxt);
+          if (kKvStages == 1 && has_next) {  // single buffer: refill once PV(g) has retired
+            ptx::mbar_wait(bar_o, g & 1);
+            if (!last) load_kv(cur, j + 1, g + 1);
+            else load_kv(nxt, 0, g + 1);
+          }
+          // S(g+1) may now overwrite S (the softmax warps are done with it); P's smem and O are protected because
+          // bar_s(g+1) -- a tcgen05.commit -- only fires after every earlier MMA of this thread, PV(g) included.
         }
-        ptx::umma_commit<1>(bar_o);
-        if (kKvStages == 1 && j + 1 < nblk) {  // single buffer: refill once PV(j) has retired
-          ptx::mbar_wait(bar_o, j & 1);
-          load_kv(j + 1);
-        }
-        // S(j+1) may now overwrite S (the softmax warps are done with it); P's smem and O are protected because
-        // bar_s(j+1) -- a tcgen05.commit -- only fires after every earlier MMA of this thread, PV(j) included.
+        cur = nxt;
+        item = item_nxt;
+        ++items_done;
       }
     }
   } else {
     // ---------------- softmax warps: thread = query row ----------------
     const int r = warp * 32 + lane;
-    const int qi = q0 + r;  // sequence-local query index
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     const uint32_t tS = tmem_base + lane_base;
     const uint32_t tO = tmem_base + lane_base + C::kOCol;
+    const float sc = p.scale_log2;  // > 0
+    AttnItem cur;
+    uint32_t g = 0;
+    for (int item = attn_next_item<BN>(p, blockIdx.x, &cur); item < p.total_items;
+         item = attn_next_item<BN>(p, item + gridDim.x, &cur)) {
+    const int seq = cur.seq, h = cur.h, s0 = cur.s0, L = cur.L, q0 = cur.q0, nblk = cur.nblk;
+    const int qi = q0 + r;  // sequence-local query index
     const int row_limit = p.causal ? min(L, qi + 1) : L;  // this row sees keys [0, row_limit)
-    const float sc = p.scale_log2;                         // > 0
     float m_ref = -INFINITY;  // log2-domain reference the accumulated O / l are expressed against
     float pend = -INFINITY;   // larger reference to adopt at the next safe point (no PV in flight)
     float l_run = 0.f;
@@ -222,8 +287,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       }
     };
 
-    for (int j = 0; j < nblk; ++j) {
-      ptx::mbar_wait(bar_s, j & 1);  // S(j) is in TMEM; every earlier MMA (PV(j-1) included) has retired
+    for (int j = 0; j < nblk; ++j, ++g) {
+      ptx::mbar_wait(bar_s, g & 1);  // S(g) is in TMEM; every earlier MMA (PV(g-1) included) has retired
       ptx::tc_fence_after();
       const int nvis = row_limit - j * kBN;  // visible keys of this row inside this block (<= 0 .. >= 128)
       const bool full_blk = __all_sync(0xffffffffu, nvis >= kBN);
@@ -312,7 +377,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       ptx::mbar_arrive(bar_p);
     }
     // epilogue: O / l -> bf16 -> global (one row per thread)
-    ptx::mbar_wait(bar_o, (nblk - 1) & 1);
+    ptx::mbar_wait(bar_o, (g - 1) & 1);
     ptx::tc_fence_after();
     const float inv = (l_run > 0.f ? 1.0f / l_run : 0.f) * (DROP ? p.drop.inv_keep : 1.0f);
     if (p.lse != nullptr && qi < L) p.lse[static_cast<long long>(s0 + qi) * p.Hq + h] = m_ref + log2f(l_run);
@@ -322,6 +387,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       uint32_t raw[32];
       ptx::tmem_ld_32x32(tO + c * 32, raw);
       ptx::tmem_ld_wait();
+      if (c + 1 == D / 32) {  // the accumulator is in registers: the issuer may start the next item's P.V
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(bar_oe);
+      }
       if (qi < L) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -334,6 +403,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
       }
     }
+    }  // items
   }
 
   ptx::tc_fence_before();
@@ -344,13 +414,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   }
 }
 
-template <int D, int BN, bool DROP>
+template <int D, int BN, int KVS, bool DROP>
 int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, const int* cu,
                    int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, float scale, int causal,
                    float* lse, cudaStream_t stream, const AttnDrop* drop) {
-  using C = AttnCfg<D, BN>;
+  using C = AttnCfg<D, BN, KVS>;
   constexpr int kBN = BN;
-  auto kern = attn_fwd_tc_kernel<D, BN, DROP>;
+  auto kern = attn_fwd_tc_kernel<D, BN, KVS, DROP>;
   static bool attr_set = false;
   if (!attr_set) {
     B2S_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -374,7 +444,16 @@ int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, vo
   p.causal = causal;
   p.lse = lse;
   if (DROP) p.drop = *drop;
-  dim3 grid((max_seqlen + kBM - 1) / kBM, Hq, num_seqs);
+  p.n_qblk = (max_seqlen + kBM - 1) / kBM;
+  const long long total = static_cast<long long>(p.n_qblk) * Hq * num_seqs;
+  B2S_REQUIRE(total < (1LL << 31), "attention_fwd_tc: too many work items");
+  p.total_items = static_cast<int>(total);
+  // resident CTAs per SM: limited by shared memory (227 KiB, 1 KiB reserved per CTA) and TMEM (512 columns)
+  constexpr int by_smem = (227 * 1024) / (C::kSmemBytes + 1024);
+  constexpr int by_tmem = 512 / C::kTmemCols;
+  constexpr int ctas_per_sm = by_smem < by_tmem ? (by_smem < 1 ? 1 : by_smem) : by_tmem;
+  const long long resident = static_cast<long long>(num_sms()) * ctas_per_sm;
+  const unsigned grid = static_cast<unsigned>(total < resident ? total : resident);
   kern<<<grid, kThreadsTc, C::kSmemBytes, stream>>>(tq, tk, tv, p);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
@@ -382,23 +461,37 @@ int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, vo
 
 }  // namespace
 
+// experiment hook: B2S_ATTN_CFG="<keys per step>,<K/V stages>" overrides the default tile configuration
+static int g_cfg_bn = 0, g_cfg_kvs = 0;
+static const bool g_cfg_read = [] {
+  if (const char* e = getenv("B2S_ATTN_CFG")) sscanf(e, "%d,%d", &g_cfg_bn, &g_cfg_kvs);
+  return true;
+}();
+
 int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
                      const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
                      float scale, int causal, float* lse, cudaStream_t stream, const AttnDrop* drop) {
+#define B2S_ATTN_ARGS q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, scale, causal, lse, stream
   if (drop != nullptr && drop->thresh != 0u) {  // train-mode HuBERT attention only (TF/.../modeling_hubert.py:254)
     B2S_REQUIRE(D == 64 && max_seqlen < 65536, "attention_fwd_tc: attention dropout supports head_dim 64, seqlen < 65536");
-    return launch_attn_tc<64, 128, true>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq,
-                                         Hkv, scale, causal, lse, stream, drop);
+    return launch_attn_tc<64, 64, 1, true>(B2S_ATTN_ARGS, drop);
   }
-  if (D == 64)
-    return launch_attn_tc<64, 128, false>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq,
-                                          Hkv, scale, causal, lse, stream, nullptr);
-  if (D == 128 && max_seqlen <= 512)  // short prompts: per-CTA latency dominates -> two CTAs per SM
-    return launch_attn_tc<128, 64, false>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq,
-                                          Hkv, scale, causal, lse, stream, nullptr);
-  if (D == 128)
-    return launch_attn_tc<128, 128, false>(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq,
-                                           Hkv, scale, causal, lse, stream, nullptr);
+  int bn = g_cfg_bn, kvs = g_cfg_kvs;
+  if (bn == 0) {
+    // measured on B200 (profiles/r01_attention_configs.md): the kernel is bound by the per-step latency chain, so the
+    // configuration that keeps the most CTAs resident wins at these sequence lengths
+    bn = 64;
+    kvs = 1;
+    if (D == 128 && max_seqlen > 1024) bn = 128, kvs = 2;
+  }
+  if (D == 64 && bn == 64 && kvs == 1) return launch_attn_tc<64, 64, 1, false>(B2S_ATTN_ARGS, nullptr);
+  if (D == 64 && bn == 64 && kvs == 2) return launch_attn_tc<64, 64, 2, false>(B2S_ATTN_ARGS, nullptr);
+  if (D == 64 && bn == 128 && kvs == 1) return launch_attn_tc<64, 128, 1, false>(B2S_ATTN_ARGS, nullptr);
+  if (D == 64 && bn == 128 && kvs == 2) return launch_attn_tc<64, 128, 2, false>(B2S_ATTN_ARGS, nullptr);
+  if (D == 128 && bn == 64 && kvs == 1) return launch_attn_tc<128, 64, 1, false>(B2S_ATTN_ARGS, nullptr);
+  if (D == 128 && bn == 64 && kvs == 2) return launch_attn_tc<128, 64, 2, false>(B2S_ATTN_ARGS, nullptr);
+  if (D == 128 && bn == 128 && kvs == 2) return launch_attn_tc<128, 128, 2, false>(B2S_ATTN_ARGS, nullptr);
+#undef B2S_ATTN_ARGS
   set_last_error("attention_fwd_tc: head_dim %d unsupported (64 or 128)", D);
   return B2S_ERR_UNSUPPORTED;
 }
