@@ -120,7 +120,8 @@ struct DqCfg {
   static constexpr int kBigBytes = kBig * D * 2;
   static constexpr int kSmallBytes = kSmall * D * 2;
   static constexpr int kDsBytes = kBig * kSmall * 2;
-  static constexpr int kSmemBytes = 2 * kBigBytes + kStages * 2 * kSmallBytes + kDsBytes + 256 + 1024;
+  // no alignment slack (the window is declared 1024-byte aligned): at D = 128 this is what lets two CTAs share an SM
+  static constexpr int kSmemBytes = 2 * kBigBytes + kStages * 2 * kSmallBytes + kDsBytes + 256;
   static constexpr int kTmemCols = 256;  // S [0,64) dP [64,128) dQ [128,128+D)
 };
 
@@ -144,8 +145,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   const int kv_len = p.causal ? min(L, q0 + kBig) : L;
   const int nblk = (kv_len + kSmall - 1) / kSmall;
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = ptx::smem_u32(smem_raw);
+  if ((base & 1023u) != 0u) __trap();  // the swizzled tiles need 1024-byte alignment
   const uint32_t sQ = base;
   const uint32_t sDO = sQ + C::kBigBytes;
   const uint32_t sK = sDO + C::kBigBytes;
@@ -317,7 +319,7 @@ struct DkvCfg {
   static constexpr int kBigBytes = kBig * D * 2;
   static constexpr int kSmallBytes = kSmall * D * 2;
   static constexpr int kPtBytes = kBig * kSmall * 2;
-  static constexpr int kSmemBytes = 2 * kBigBytes + kStages * 2 * kSmallBytes + 2 * kPtBytes + 2 * 2 * kSmall * 4 + 256 + 1024;
+  static constexpr int kSmemBytes = 2 * kBigBytes + kStages * 2 * kSmallBytes + 2 * kPtBytes + 2 * 2 * kSmall * 4 + 256;
   static constexpr int kTmemCols = (D == 64) ? 256 : 512;  // S^T [0,64) dP^T [64,128) dV [128,128+D) dK [128+D,128+2D)
 };
 
@@ -340,8 +342,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   const int per_head = nq - i0;
   const int iters = G * per_head;
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = ptx::smem_u32(smem_raw);
+  if ((base & 1023u) != 0u) __trap();  // the swizzled tiles need 1024-byte alignment
   const uint32_t sK = base;
   const uint32_t sV = sK + C::kBigBytes;
   const uint32_t sQ = sV + C::kBigBytes;

@@ -292,16 +292,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       ptx::tc_fence_after();
       const int nvis = row_limit - j * kBN;  // visible keys of this row inside this block (<= 0 .. >= 128)
       const bool full_blk = __all_sync(0xffffffffu, nvis >= kBN);
+      // D = 128 with 64-key steps (two CTAs per SM, registers to spare): the thread's whole row of S (64 fp32) is read
+      // from TMEM ONCE, both 32-column loads in flight before the single wait, and stays in registers for the
+      // first-block max pass, the main pass and a retry. Elsewhere the row is re-read chunk by chunk: at D = 64 the
+      // four-CTAs-per-SM residency needs <= 102 registers per thread.
+      constexpr bool kHold = (kBN == 64 && D == 128);
+      uint32_t held[kHold ? kBN : 1];
+      if (kHold) {
+        ptx::tmem_ld_32x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&held[0]));
+        ptx::tmem_ld_32x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&held[kHold ? 32 : 0]));
+        ptx::tmem_ld_wait();
+      }
       if (j == 0) {
         // first block: exact masked row max as the initial reference (nothing accumulated yet)
         float bm = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < kBN / 32; ++c) {
-          uint32_t raw[32];
-          ptx::tmem_ld_32x32(tS + c * 32, raw);
-          ptx::tmem_ld_wait();
+        if (kHold) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) bm = fmaxf(bm, (c * 32 + i < nvis) ? __uint_as_float(raw[i]) : -INFINITY);
+          for (int i = 0; i < kBN; ++i) bm = fmaxf(bm, (i < nvis) ? __uint_as_float(held[kHold ? i : 0]) : -INFINITY);
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < kBN / 32; ++c) {
+            uint32_t raw[32];
+            ptx::tmem_ld_32x32(tS + c * 32, raw);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bm = fmaxf(bm, (c * 32 + i < nvis) ? __uint_as_float(raw[i]) : -INFINITY);
+          }
         }
         pend = bm * sc;
       }
@@ -312,11 +328,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         adopt(j > 0);
         const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;
         float rs = 0.f, bmax = -INFINITY;
-#pragma unroll 1
+#pragma unroll(kHold ? 2 : 1)
         for (int c = 0; c < kBN / 32; ++c) {
-          uint32_t raw[32];
-          ptx::tmem_ld_32x32(tS + c * 32, raw);
-          ptx::tmem_ld_wait();
+          uint32_t raw_c[kHold ? 1 : 32];
+          if (!kHold) {
+            ptx::tmem_ld_32x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&raw_c[0]));
+            ptx::tmem_ld_wait();
+          }
+          const uint32_t* raw = kHold ? &held[kHold ? c * 32 : 0] : &raw_c[0];
           uint32_t pk[16];
           if (full_blk) {
 #pragma unroll

@@ -62,7 +62,7 @@ def bench_conv0_bwd(B, samples):
                       "GBps": round(dy.numel() * 2 / ms / 1e6, 1)}), flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__":  # noqa
     R = 32 * 499
     if len(sys.argv) > 1 and sys.argv[1] == "splits":
         for (N, K, lab) in [(1024, 4096, "enc w2 wgrad"), (4096, 1024, "enc w1 wgrad"), (1024, 1024, "enc wo wgrad"),
