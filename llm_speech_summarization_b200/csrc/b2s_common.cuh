@@ -66,7 +66,27 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-GELU (TF/activations.py:318 `gelu` = x * Phi(x), exact erf form). h(|x|) = 0.5 * erfc(|x| / sqrt 2) is evaluated
+// with Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 on erf, i.e. the accuracy class of erff): 5 FMAs, one MUFU.RCP and
+// one MUFU.EX2 -- about half the instructions of 0.5 * x * (1 + erff(x / sqrt 2)), which is what bounded the FFN1
+// GEMM epilogue and the conv front end (profiles/r01_gemm_shapes.md). x * Phi(x) = max(x, 0) - |x| * h(|x|).
+__device__ __forceinline__ float half_erfc_abs(float ax /* |x| */, float* gauss /* exp(-x^2/2) */) {
+  const float z = ax * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  *gauss = e;
+  return p * t * e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float e;
+  const float ax = fabsf(x);
+  return fmaf(-ax, half_erfc_abs(ax, &e), fmaxf(x, 0.0f));
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 // 8-element vector IO (32 B fp32 / 16 B bf16 per call)
@@ -91,7 +111,9 @@ __device__ __forceinline__ void ld8bf(const __nv_bfloat16* p, float (&f)[8]) {
 
 // erf-GELU derivative: Phi(x) + x phi(x)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  float e;
+  const float h = half_erfc_abs(fabsf(x), &e);
+  return (x >= 0.0f ? 1.0f - h : h) + x * 0.3989422804014327f * e;
 }
 
 // streaming 16-byte load that does not pollute L1

@@ -175,9 +175,7 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __re
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float cdf = 0.5f * (1.0f + erff(x[j] * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * x[j] * x[j]);
-    d[j] *= cdf + x[j] * pdf;
+    d[j] *= gelu_erf_grad(x[j]);
   }
   st8bf(dpre + i * 8, d);
 }
