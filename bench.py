@@ -63,6 +63,34 @@ def ncu_traffic_per_launch(train: bool):
     return None, None
 
 
+def write_gemm_shapes(lib, n, path, steps):
+    """Per-shape aggregation of the per-launch CUDA-event timings (hot, inside the real step)."""
+    import ctypes as C
+    agg = {}
+    ms, shape = C.c_double(), (C.c_int32 * 10)()
+    for i in range(n):
+        lib.b2s_gemm_timing_get(i, C.byref(ms), shape)
+        key = tuple(shape)
+        a = agg.setdefault(key, [0, 0.0])
+        a[0] += 1
+        a[1] += ms.value
+    epi = {0: "bf16", 1: "resid_f32", 2: "swiglu", 3: "rope", 4: "f32", 5: "accum_f32"}
+    mode = {0: "fwd", 1: "fwd+", 2: "dgrad", 3: "wgrad"}
+    rows = []
+    for (M, N, K, b, g, e, act, md, bn, cg), (cnt, t) in agg.items():
+        fl = 2.0 * M * N * K * b * g * cnt
+        rows.append((t / steps, cnt // steps, M, N, K, b, g, epi.get(e, e), "gelu" if act else "-", mode.get(md, md),
+                     bn, cg, fl / (t / 1e3) / 1e12))
+    rows.sort(reverse=True)
+    tot = sum(r[0] for r in rows)
+    with open(path, "w") as f:
+        f.write(f"# per-shape GEMM timings inside the step (CUDA events per launch, hot); {tot:.2f} ms of GEMM per step\n")
+        f.write("# ms/step  launches  M N K batches groups  epilogue act mode  bn cg  TFLOP/s\n")
+        for r in rows:
+            f.write(f"{r[0]:8.3f} {r[1]:4d}  {r[2]:6d} {r[3]:6d} {r[4]:7d} {r[5]:3d} {r[6]:3d}  {r[7]:>9s} {r[8]:>4s} "
+                    f"{r[9]:>5s}  {r[10]:3d} {r[11]}  {r[12]:7.1f}\n")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -76,6 +104,7 @@ def parse():
                     help="train workload: HF train-mode regularisers of the encoder (REF/trainer.py:258). 'dropout' = "
                          "every dropout site + SpecAugment (same work as the deterministic step plus the mask "
                          "generation), 'all' = also LayerDrop (skips ~10%% of the encoder layers, like the reference)")
+    ap.add_argument("--gemm-shapes", default="", help="write the per-shape GEMM table of the instrumented steps here")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts", type=int, default=3, help="utterances timed for the CPU baseline sample")
     ap.add_argument("--profile-mode", action="store_true",
@@ -390,6 +419,8 @@ def main():
     import ctypes as C
     g_ms, g_n = C.c_double(), C.c_longlong()
     lib.b2s_gemm_timing_read(C.byref(g_ms), C.byref(g_n))
+    if args.gemm_shapes and rank == 0:
+        write_gemm_shapes(lib, g_n.value, args.gemm_shapes, steps=2)
     lib.b2s_gemm_timing_enable(0)
     peaks = {}
     try:

@@ -85,6 +85,9 @@ int b2s_gemm_bf16(const b2s_gemm_args* args, void* stream);
  * stream; read() synchronises them and returns the summed device time (host pointers) and the launch count. */
 void b2s_gemm_timing_enable(int32_t on);
 int b2s_gemm_timing_read(double* total_ms, long long* launches);
+/* launch `index` of the instrumented window: duration and shape[10] = M, N, K (whole reduction), batches, groups,
+ * epilogue id, activation id, kernel mode (0 fwd / 1 train-fwd / 2 dgrad / 3 wgrad), block_n, cta_group */
+int b2s_gemm_timing_get(int64_t index, double* ms, int32_t* shape);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused CE + logit-KD loss over packed response rows.  Replaces utils.soft_cross_entropy

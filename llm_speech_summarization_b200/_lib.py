@@ -120,6 +120,7 @@ PROTOTYPES = {
     "b2s_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "b2s_gemm_timing_enable": (None, [c_int]),
     "b2s_gemm_timing_read": (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "b2s_gemm_timing_get": (c_int, [c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "b2s_kd_ce_workspace_bytes": (c_size_t, [c_int, c_int]),
     "b2s_kd_ce_loss_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, P_int, P_int, c_int, c_float,
                                    c_float, c_void_p, P_f32, P_f32, P_f32, P_f32, P_f32, P_f32, c_void_p]),

@@ -160,6 +160,7 @@ int b2s_gemm_bf16(const b2s_gemm_args* a, void* stream) {
 
 void b2s_gemm_timing_enable(int32_t on) { gemm_timing_enable(on); }
 int b2s_gemm_timing_read(double* total_ms, long long* launches) { return gemm_timing_read(total_ms, launches); }
+int b2s_gemm_timing_get(int64_t index, double* ms, int32_t* shape) { return gemm_timing_get(index, ms, shape); }
 
 size_t b2s_kd_ce_workspace_bytes(int32_t rows, int32_t V) { return kd_ce_workspace_bytes(rows, V); }
 

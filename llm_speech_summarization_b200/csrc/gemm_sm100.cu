@@ -35,6 +35,11 @@ namespace {
 
 bool g_timing = false;
 std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
+struct TimedShape {
+  int M, N, K, batches, groups, epi, act, mode, bn, cg;
+};
+std::vector<TimedShape> g_shapes;  // one per entry of g_events
+TimedShape g_pending{};            // filled by gemm_bf16_launch just before launch_cfg records the events
 
 constexpr int kBlockK = 64;           // bf16 elements = 128 bytes = one swizzle atom
 constexpr int kUmmaK = 16;
@@ -663,6 +668,7 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const KParams& p, c
   if (g_timing) {
     B2S_CUDA_CHECK(cudaEventRecord(ev1, stream));
     g_events.emplace_back(ev0, ev1);
+    g_shapes.push_back(g_pending);
   }
   return B2S_OK;
 }
@@ -686,7 +692,22 @@ void gemm_timing_enable(int on) {
     cudaEventDestroy(e.second);
   }
   g_events.clear();
+  g_shapes.clear();
   g_timing = on != 0;
+}
+
+// per-launch record: shape[10] = M, N, K (whole reduction), batches, groups, epilogue, activation, mode, block_n, cta_group
+int gemm_timing_get(long long index, double* ms, int* shape) {
+  B2S_REQUIRE(index >= 0 && index < static_cast<long long>(g_events.size()) && ms && shape, "gemm_timing_get: bad index");
+  auto& e = g_events[static_cast<size_t>(index)];
+  B2S_CUDA_CHECK(cudaEventSynchronize(e.second));
+  float t = 0.f;
+  B2S_CUDA_CHECK(cudaEventElapsedTime(&t, e.first, e.second));
+  *ms = t;
+  const TimedShape& d = g_shapes[static_cast<size_t>(index)];
+  const int v[10] = {d.M, d.N, d.K, d.batches, d.groups, d.epi, d.act, d.mode, d.bn, d.cg};
+  for (int i = 0; i < 10; ++i) shape[i] = v[i];
+  return B2S_OK;
 }
 
 int gemm_timing_read(double* total_ms, long long* launches) {
@@ -857,6 +878,8 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   const bool ext = mn || a.epi == EPI_ACCUM_F32 || p.k_splits > 1 || a.out2 != nullptr || a.out_group_rows != 0 ||
                    (a.out_group_cols > 0 && a.out_group_cols != a.N) || a.drop_thresh != 0u;
   const int mode = a.a_mn ? 3 : (a.b_mn ? 2 : (ext ? 1 : 0));
+  if (g_timing)
+    g_pending = TimedShape{a.M, a.N, a.k_per_tap * a.taps * k_batches, a.batches, a.groups, a.epi, a.act, mode, bn, cg};
 #define B2S_GEMM_CASE(BN_, CG_)                                          \
   if (bn == BN_ && cg == CG_) {                                          \
     switch (mode) {                                                      \

@@ -82,5 +82,6 @@ struct GemmArgs {
 int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream);
 void gemm_timing_enable(int on);
 int gemm_timing_read(double* total_ms, long long* launches);
+int gemm_timing_get(long long index, double* ms, int* shape /* [10] */);
 
 }  // namespace b2s
