@@ -14,8 +14,10 @@ forward with activations kept, the backward through the frozen LLM into every en
 all-reduce of the flat gradient over the ranks and one AdamW update per step (grad_accum window = the global batch).
 
 `value`  : utterances/s, inputs already resident in HBM, CUDA-event timed, max over ranks.
-`e2e`    : the same through AudioPromptStep.__call__ with HOST (pinned) inputs: H2D of the waveforms + ids and a
-           D2H read of the per-utterance losses inside the timed region.
+`e2e`    : the same through the public streaming call AudioPromptStep.submit(...) / .result() with HOST (pinned)
+           inputs: every step's H2D of the waveforms + ids and the D2H read of its per-utterance losses happen inside
+           the timed region; batch i+1 is submitted before batch i's losses are read, so the copies and the host-side
+           plan building overlap the GPU work (the blocking form is `__call__` = submit(...).result()).
 `roofline`: the dominant kernel family (the tcgen05 GEMM): algorithmic FLOPs of every GEMM launch of one step
            divided by the summed per-launch CUDA-event durations (b2s_gemm_timing_*), vs the measured sustained
            bf16 peak in MEASURED_PEAKS.json.
@@ -398,9 +400,14 @@ def main():
     torch.cuda.synchronize()
     dp.barrier()
     t0 = time.perf_counter()
+    pending = None  # the streaming form of the public call: batch i+1 is submitted before batch i's losses are read
     for i in range(args.steps):
         w, t, r = host[i % n_pool]
-        res = public(w, t, r, dev)
+        nxt = public.submit(w, t, r, dev)
+        if pending is not None:
+            res = pending.result()
+        pending = nxt
+    res = pending.result()
     torch.cuda.synchronize()
     e2e_s = dp.max_over_ranks(time.perf_counter() - t0, dev)
     dp.barrier()
@@ -489,7 +496,8 @@ def main():
                                  "(>> 126 MB L2); two distinct micro-batches alternate",
                            "timed": timed, **({"regularize": args.regularize} if train else {})},
                 "clocks": clk,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "submit()/result(), one batch in flight ahead of the one being read"},
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_loss": roofline_loss,
                 "cpu_baseline": cpu,
                 "check": {"mean_total_loss": loss_check}}

@@ -93,6 +93,43 @@ def build_plan(prefix: Sequence[int], suffix: Sequence[int], n_audio: int, text_
                 student_rows_total=cu[B])
 
 
+class PendingStep:
+    """A submitted micro-batch (`AudioPromptStep.submit` / `EncoderTrainer.submit`): the per-utterance losses travel
+    to pinned host memory asynchronously; `result()` waits for exactly that copy."""
+
+    def __init__(self, keys, host_buf: torch.Tensor, event: torch.cuda.Event, extra=None):
+        self.keys, self.host_buf, self.event, self.extra = keys, host_buf, event, extra or {}
+
+    def result(self) -> Dict[str, torch.Tensor]:
+        self.event.synchronize()
+        out = {k: self.host_buf[i] for i, k in enumerate(self.keys)}
+        out.update(self.extra)
+        return out
+
+
+def _stage_to_device(host: torch.Tensor, device, copy_stream: torch.cuda.Stream) -> torch.Tensor:
+    """Pinned host tensor -> device on a side stream, so the copy of batch i+1 overlaps the compute of batch i; the
+    compute stream waits on the copy's event and the allocator is told about the cross-stream use."""
+    main = torch.cuda.current_stream(device)
+    with torch.cuda.stream(copy_stream):
+        dev = host.to(device, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(copy_stream)
+    main.wait_event(done)
+    dev.record_stream(main)
+    return dev
+
+
+def _losses_to_host(out: Dict[str, torch.Tensor]) -> PendingStep:
+    keys = [k for k in ("ntp_loss", "ld_loss", "fd_loss", "total_loss") if k in out]
+    stacked = torch.stack([out[k] for k in keys])
+    host = torch.empty(stacked.shape, dtype=stacked.dtype, pin_memory=True)
+    host.copy_(stacked, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    return PendingStep(keys, host, ev)
+
+
 class AudioPromptStep:
     def __init__(self, audio_encoder, llm, tokenizer, llm_type: str, *, use_ld_loss: bool = True,
                  use_fd_loss: bool = True, ntp_loss_weight: float = 0.5, ld_loss_weight: float = 0.5,
@@ -279,8 +316,13 @@ class AudioPromptStep:
     def __call__(self, waves_host: torch.Tensor, text_ids, resp_ids, device) -> Dict[str, float]:
         """End-to-end call from HOST buffers: pinned H2D copy of the waveforms and ids, the fused step, and a D2H
         read of the per-utterance losses (what bench.py's `e2e` times)."""
-        waves = waves_host.to(device, non_blocking=True)
-        out = self.forward_losses(waves, text_ids, resp_ids)
-        keys = [k for k in ("ntp_loss", "ld_loss", "fd_loss", "total_loss") if k in out]
-        stacked = torch.stack([out[k] for k in keys]).cpu()  # one D2H, synchronises
-        return {k: stacked[i] for i, k in enumerate(keys)}
+        return self.submit(waves_host, text_ids, resp_ids, device).result()
+
+    def submit(self, waves_host: torch.Tensor, text_ids, resp_ids, device) -> PendingStep:
+        """Streaming form of `__call__`: enqueue H2D (side stream) + the fused step + an asynchronous D2H of the
+        per-utterance losses, and return at once. Submitting batch i+1 before calling `result()` of batch i hides the
+        host-side plan building and the PCIe copies behind the GPU work of batch i."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device)
+        waves = _stage_to_device(waves_host, device, self._copy_stream)
+        return _losses_to_host(self.forward_losses(waves, text_ids, resp_ids))

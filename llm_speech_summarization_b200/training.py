@@ -214,10 +214,18 @@ class EncoderTrainer:
     def __call__(self, waves_host: torch.Tensor, text_ids, resp_ids, device) -> Dict[str, torch.Tensor]:
         """End-to-end micro-batch from HOST buffers: pinned H2D copy of the waveforms and ids, the training step, and
         a D2H read of the per-utterance losses (what bench.py's `e2e` times for the training workload)."""
-        out = self.train_step(waves_host.to(device, non_blocking=True), text_ids, resp_ids)
-        keys = [k for k in ("ntp_loss", "ld_loss", "fd_loss", "total_loss") if k in out]
-        stacked = torch.stack([out[k] for k in keys]).cpu()
-        return {k: stacked[i] for i, k in enumerate(keys)}
+        return self.submit(waves_host, text_ids, resp_ids, device).result()
+
+    def submit(self, waves_host: torch.Tensor, text_ids, resp_ids, device):
+        """Streaming form of `__call__` (see AudioPromptStep.submit): returns a PendingStep whose `result()` holds the
+        losses and `optimizer_step`."""
+        from .step import _losses_to_host, _stage_to_device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device)
+        out = self.train_step(_stage_to_device(waves_host, device, self._copy_stream), text_ids, resp_ids)
+        pending = _losses_to_host(out)
+        pending.extra["optimizer_step"] = out["optimizer_step"]
+        return pending
 
     @torch.no_grad()
     def validate(self, batches, epoch: int = 0, *, num_generate_samples: int = 0, tokenizer=None, writer=None,

@@ -252,3 +252,27 @@ def test_whisper_medium_full_size_vs_oracle(cuda):
         ref = rm.audio_encoder_forward_whisper(sd, mel, cfg)
     assert out.shape == (2, 374, 3072)
     assert rel_l2(out.cpu(), ref) < TOL_EMBED
+
+
+def test_streaming_submit_equals_blocking_call(cuda):
+    """AudioPromptStep.submit(...).result() (side-stream H2D, async D2H into pinned memory, several batches in flight)
+    returns exactly what the blocking __call__ returns for each batch."""
+    from oracle import configs
+    from llm_speech_summarization_b200.step import AudioPromptStep
+    enc_cfg, llm_cfg = configs.TINY_ENCODER, configs.TINY_LLAMA
+    enc_sd = configs.make_encoder_state_dict(enc_cfg, seed=1234)
+    llm_sd = configs.make_llm_state_dict(llm_cfg, seed=4321)
+    _, enc, llm = build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, cuda)
+    tok = configs.stub_tokenizer(llm_cfg)
+    step = AudioPromptStep(enc, llm, tok, llm_cfg.llm_type, fd_loss_connector_layers=(0, 1, 2))
+    batches = []
+    for b in range(4):
+        utts = [configs.synthetic_utterance(llm_cfg, 10 * b + i, 8000, T=5 + i, R=4 + b) for i in range(2)]
+        batches.append((torch.stack([u[0] for u in utts]).pin_memory(), [u[1] for u in utts], [u[2] for u in utts]))
+    blocking = [step(w, t, r, cuda) for (w, t, r) in batches]
+    pending = [step.submit(w, t, r, cuda) for (w, t, r) in batches]          # all four in flight
+    for ref, p in zip(blocking, reversed(list(reversed(pending)))):
+        got = p.result()
+        assert set(got) == set(ref)
+        for k in ref:
+            assert torch.equal(got[k], ref[k]), k
