@@ -380,17 +380,24 @@ typedef struct {
   const float* masked_spec_embed; /* DEVICE fp32 [hidden] (required with time_mask) */
   float* g_masked_spec_embed;     /* DEVICE fp32 [hidden] gradient accumulator (backward only; may be NULL) */
 } b2s_encoder_regularizers;
-/* b2s_hubert_forward keeping every activation the backward needs in `saved`; reg = NULL: deterministic (eval) math. */
+/* b2s_hubert_forward keeping every activation the backward needs in `saved`; reg = NULL: deterministic (eval) math.
+ * samples_per_utt (HOST int32 [batches], NULL = every utterance has `samples` samples): a ragged micro-batch. The
+ * waveforms are zero-padded on the right to `samples` (the reference's collate, REF/trainer.py:146-149), every
+ * utterance still gets exactly the numbers it would get alone: the front end runs on the padded layout, the
+ * transformer stack on the packed valid frames with per-utterance attention, the pooling windows per utterance.
+ * audio_embeds is [batches, pooled(samples), llm_dim]; rows >= pooled(samples_per_utt[b]) of utterance b are padding. */
 int b2s_hubert_forward_train(const b2s_hubert_weights* w, const float* wave, int64_t wave_stride, int32_t batches,
-                             int32_t samples, void* saved, size_t saved_bytes, float* audio_embeds,
-                             const b2s_encoder_regularizers* reg, void* stream);
+                             int32_t samples, const int32_t* samples_per_utt, void* saved, size_t saved_bytes,
+                             float* audio_embeds, const b2s_encoder_regularizers* reg, void* stream);
 /* test hook: out[i] = 1 if element e_first + i of stream (seed, site, a, b) is KEPT at drop probability p */
 int b2s_drop_mask_dump(uint8_t* out, int64_t n, uint64_t seed, uint32_t site, uint32_t a, uint32_t b, float p,
                        uint32_t e_first, void* stream);
 /* d_audio_embeds fp32 [batches*pooled, llm_dim] -> grads (+=). pos_w_dgrad: bf16 [H][k][H/groups], the packed
- * positional-conv weight with taps reversed and each (out, in) block transposed (the conv's transpose). */
+ * positional-conv weight with taps reversed and each (out, in) block transposed (the conv's transpose).
+ * samples_per_utt: as given to the forward; the padding rows of d_audio_embeds must be zero. */
 int b2s_hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* grads,
-                        const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, void* saved,
+                        const float* wave, int64_t wave_stride, int32_t batches, int32_t samples,
+                        const int32_t* samples_per_utt, void* saved,
                         size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
                         const b2s_encoder_regularizers* reg /* the block the forward ran with */, void* stream);
 /* Whisper encoder (REF/config/llama3_whisper.yaml trains it like the HuBERT one): same contract; mel fp32

@@ -181,11 +181,12 @@ PROTOTYPES = {
                                       c_void_p, c_void_p, c_void_p, C.c_size_t, c_void_p]),
     "b2s_hubert_saved_bytes": (C.c_size_t, [C.POINTER(HubertWeights), c_int, c_int]),
     "b2s_hubert_backward_workspace_bytes": (C.c_size_t, [C.POINTER(HubertWeights), c_int, c_int]),
-    "b2s_hubert_forward_train": (c_int, [C.POINTER(HubertWeights), c_void_p, c_int64, c_int, c_int, c_void_p,
-                                         C.c_size_t, c_void_p, C.POINTER(EncoderRegularizers), c_void_p]),
+    "b2s_hubert_forward_train": (c_int, [C.POINTER(HubertWeights), c_void_p, c_int64, c_int, c_int,
+                                         C.POINTER(C.c_int32), c_void_p, C.c_size_t, c_void_p,
+                                         C.POINTER(EncoderRegularizers), c_void_p]),
     "b2s_hubert_backward": (c_int, [C.POINTER(HubertWeights), c_void_p, C.POINTER(HubertGrads), c_void_p, c_int64,
-                                    c_int, c_int, c_void_p, C.c_size_t, c_void_p, c_void_p, C.c_size_t,
-                                    C.POINTER(EncoderRegularizers), c_void_p]),
+                                    c_int, c_int, C.POINTER(C.c_int32), c_void_p, C.c_size_t, c_void_p, c_void_p,
+                                    C.c_size_t, C.POINTER(EncoderRegularizers), c_void_p]),
     "b2s_drop_mask_dump": (c_int, [c_void_p, c_int64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, c_float,
                                    C.c_uint32, c_void_p]),
     "b2s_whisper_saved_bytes": (C.c_size_t, [C.POINTER(WhisperWeights), c_int]),

@@ -78,11 +78,11 @@ int llama_decode_step(const b2s_llama_weights* w, const void* embed_table, const
 size_t hubert_saved_bytes(const b2s_hubert_weights* w, int batches, int samples);
 size_t hubert_backward_workspace_bytes(const b2s_hubert_weights* w, int batches, int samples);
 int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long long wave_stride, int batches, int samples,
-                         void* saved, size_t saved_bytes, float* audio_embeds, const b2s_encoder_regularizers* reg,
-                         cudaStream_t stream);
+                         const int* samples_per_utt, void* saved, size_t saved_bytes, float* audio_embeds,
+                         const b2s_encoder_regularizers* reg, cudaStream_t stream);
 int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* gr, const float* wave,
-                    long long wave_stride, int batches, int samples, void* saved, size_t saved_bytes,
-                    const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
+                    long long wave_stride, int batches, int samples, const int* samples_per_utt, void* saved,
+                    size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
                     const b2s_encoder_regularizers* reg, cudaStream_t stream);
 size_t llama_backward_workspace_bytes(const b2s_llama_weights* w, int rows_bwd, int n_dl);
 int llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* sv, int rows, const int* cu_seqlens,
@@ -326,16 +326,17 @@ size_t b2s_hubert_backward_workspace_bytes(const b2s_hubert_weights* w, int32_t 
   return hubert_backward_workspace_bytes(w, batches, samples);
 }
 int b2s_hubert_forward_train(const b2s_hubert_weights* w, const float* wave, int64_t wave_stride, int32_t batches,
-                             int32_t samples, void* saved, size_t saved_bytes, float* audio_embeds,
-                             const b2s_encoder_regularizers* reg, void* stream) {
-  return hubert_forward_train(w, wave, wave_stride, batches, samples, saved, saved_bytes, audio_embeds, reg, S(stream));
+                             int32_t samples, const int32_t* samples_per_utt, void* saved, size_t saved_bytes,
+                             float* audio_embeds, const b2s_encoder_regularizers* reg, void* stream) {
+  return hubert_forward_train(w, wave, wave_stride, batches, samples, samples_per_utt, saved, saved_bytes, audio_embeds,
+                              reg, S(stream));
 }
 int b2s_hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* grads,
-                        const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, void* saved,
-                        size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
-                        const b2s_encoder_regularizers* reg, void* stream) {
-  return hubert_backward(w, pos_w_dgrad, grads, wave, wave_stride, batches, samples, saved, saved_bytes, d_audio_embeds,
-                         workspace, workspace_bytes, reg, S(stream));
+                        const float* wave, int64_t wave_stride, int32_t batches, int32_t samples,
+                        const int32_t* samples_per_utt, void* saved, size_t saved_bytes, const float* d_audio_embeds,
+                        void* workspace, size_t workspace_bytes, const b2s_encoder_regularizers* reg, void* stream) {
+  return hubert_backward(w, pos_w_dgrad, grads, wave, wave_stride, batches, samples, samples_per_utt, saved, saved_bytes,
+                         d_audio_embeds, workspace, workspace_bytes, reg, S(stream));
 }
 int b2s_drop_mask_dump(uint8_t* out, int64_t n, uint64_t seed, uint32_t site, uint32_t a, uint32_t b, float p,
                        uint32_t e_first, void* stream) {

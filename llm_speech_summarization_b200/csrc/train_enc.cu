@@ -19,6 +19,13 @@
 #include "gemm_sm100.cuh"
 #include "ops.cuh"
 
+// Ragged micro-batches (utterances of different lengths, `samples_per_utt`): the convolutional front end, the
+// feature projection, the positional convolution and the final LayerNorm + AvgPool run on the zero-padded [B, T_max]
+// layout (valid frames never read padded ones; the positional conv sees zeroed tail rows = its own zero padding),
+// the transformer stack runs on the PACKED valid rows with per-utterance cu_seqlens (attention is varlen already),
+// and two row gathers convert between the layouts. Every utterance gets exactly the numbers it would get alone.
+#include <vector>
+
 namespace b2s {
 namespace {
 
@@ -52,6 +59,12 @@ struct Saved {
   void* pooled_x;      // bf16 [B*pooled][H]
   void* xn;            // bf16 [rows][max(H,512)] transient
   int* cu;
+  // ragged batches only (rows = B * frames is the PADDED row count, packed rows <= rows)
+  float* hpad;         // fp32 [rows][H] padded-layout stream: h0 before the gather, then h[L] scattered back
+  float* zeros_h;      // fp32 [H] zeros (tail-row "embedding" for mask_rows_f32)
+  int* pack_idx;       // int [rows] packed row -> padded row
+  int* unpack_idx;     // int [rows] padded row -> packed row, -1 on tail rows
+  unsigned char* tail; // [rows] 1 on tail rows
   size_t bytes;
 };
 
@@ -79,12 +92,56 @@ void plan_saved(const b2s_hubert_weights* w, int batches, int samples, void* ws,
   s->pooled_x = c.take(B * (s->pooled > 0 ? s->pooled : 1) * H * 2);
   s->xn = c.take(rows * (H > 512 ? H : 512) * 2);
   s->cu = reinterpret_cast<int*>(c.take((B + 1) * sizeof(int)));
+  s->hpad = reinterpret_cast<float*>(c.take(rows * H * 4));
+  s->zeros_h = reinterpret_cast<float*>(c.take(H * 4));
+  s->pack_idx = reinterpret_cast<int*>(c.take(rows * sizeof(int)));
+  s->unpack_idx = reinterpret_cast<int*>(c.take(rows * sizeof(int)));
+  s->tail = reinterpret_cast<unsigned char*>(c.take(rows));
   s->bytes = c.off + 256;
+}
+
+// host-side geometry of a ragged batch
+struct Ragged {
+  bool on = false;
+  long long rows_packed = 0;
+  int max_frames = 0;
+  std::vector<int> frames, cu, pack, unpack;
+  std::vector<unsigned char> tail;
+};
+
+int plan_ragged(const b2s_hubert_weights* w, int batches, int samples, const int* samples_per_utt, int frames_pad,
+                Ragged* r) {
+  r->on = samples_per_utt != nullptr;
+  if (!r->on) return B2S_OK;
+  r->frames.resize(batches);
+  r->cu.assign(batches + 1, 0);
+  r->pack.clear();
+  r->unpack.assign(static_cast<size_t>(batches) * frames_pad, -1);
+  r->tail.assign(static_cast<size_t>(batches) * frames_pad, 1);
+  for (int b = 0; b < batches; ++b) {
+    B2S_REQUIRE(samples_per_utt[b] > 0 && samples_per_utt[b] <= samples,
+                "ragged batch: utterance %d has %d samples (padded length %d)", b, samples_per_utt[b], samples);
+    int t = conv_len(samples_per_utt[b], 10, 5);
+    for (int i = 0; i < 6; ++i) t = conv_len(t, w->conv_k[i], w->conv_stride[i]);
+    B2S_REQUIRE(t >= w->pool_kernel, "ragged batch: utterance %d is too short (%d frames)", b, t);
+    r->frames[b] = t;
+    r->cu[b + 1] = r->cu[b] + t;
+    if (t > r->max_frames) r->max_frames = t;
+    for (int f = 0; f < t; ++f) {
+      r->unpack[static_cast<size_t>(b) * frames_pad + f] = static_cast<int>(r->pack.size());
+      r->tail[static_cast<size_t>(b) * frames_pad + f] = 0;
+      r->pack.push_back(b * frames_pad + f);
+    }
+  }
+  r->rows_packed = r->cu[batches];
+  return B2S_OK;
 }
 
 struct BwdWs {
   float *dh, *dxn_f, *dpool, *delta;
   void *dyb, *dbig, *dsm, *xn, *da, *dpre, *dcol, *dxa, *dxb;
+  float* dh_pad;  // ragged batches: the padded-layout twin of dh (fp32 [rows][H]) ...
+  void* dyb_pad;  // ... and of dyb (bf16)
   size_t bytes;
 };
 
@@ -108,6 +165,8 @@ void plan_bwd(const b2s_hubert_weights* w, int batches, const Saved& s, void* ws
   p->dcol = c.take(B * t2 * 3 * 512 * 2 + 4096);
   p->dxa = c.take(B * t1 * 512 * 2 + 4096);
   p->dxb = c.take(B * t1 * 512 * 2 + 4096);
+  p->dh_pad = reinterpret_cast<float*>(c.take(rows * H * 4));
+  p->dyb_pad = c.take(rows * H * 2 + 4096);
   p->bytes = c.off + 256;
 }
 
@@ -225,8 +284,9 @@ bool layer_skipped(const b2s_encoder_regularizers* reg, int l) {
 
 int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, int heads, float eps, const StackBufs& s,
                         void* xn, const int* cu, int B, int frames, cudaStream_t stream,
-                        const b2s_encoder_regularizers* reg = nullptr) {
-  const long long rows = static_cast<long long>(B) * frames;
+                        const b2s_encoder_regularizers* reg = nullptr, long long rows_packed = -1) {
+  // `frames` is the longest sequence (attention grid); rows = all packed rows (B * frames unless the batch is ragged)
+  const long long rows = rows_packed >= 0 ? rows_packed : static_cast<long long>(B) * frames;
   const size_t rH = static_cast<size_t>(rows) * H;
   for (int l = 0; l < L; ++l) {
     const b2s_encoder_layer& Ly = layers[l];
@@ -289,8 +349,8 @@ int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, in
 // on entry b.dh / b.dyb hold d(loss)/d(h[L]) (fp32 / bf16); on exit d(loss)/d(h[0])
 int stack_backward(const b2s_encoder_layer* layers, const b2s_encoder_layer_grads* grads, int L, int H, int F, int heads,
                    float eps, const StackBufs& s, const StackScratch& b, const int* cu, int B, int frames,
-                   cudaStream_t stream, const b2s_encoder_regularizers* reg = nullptr) {
-  const long long rows = static_cast<long long>(B) * frames;
+                   cudaStream_t stream, const b2s_encoder_regularizers* reg = nullptr, long long rows_packed = -1) {
+  const long long rows = rows_packed >= 0 ? rows_packed : static_cast<long long>(B) * frames;
   const size_t rH = static_cast<size_t>(rows) * H;
   const bool drop_h = reg != nullptr && reg->p_hidden > 0.f;
   for (int l = L - 1; l >= 0; --l) {
@@ -392,8 +452,8 @@ int check_regularizers(const b2s_encoder_regularizers* reg) {
 }
 
 int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long long wave_stride, int batches, int samples,
-                         void* saved, size_t saved_bytes, float* audio_embeds, const b2s_encoder_regularizers* reg,
-                         cudaStream_t stream) {
+                         const int* samples_per_utt, void* saved, size_t saved_bytes, float* audio_embeds,
+                         const b2s_encoder_regularizers* reg, cudaStream_t stream) {
   B2S_REQUIRE(w && wave && saved && audio_embeds, "hubert_forward_train: null pointer");
   RC(check_regularizers(reg));
   B2S_REQUIRE(batches > 0 && samples > 0, "hubert_forward_train: empty batch");
@@ -409,6 +469,17 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
   const int B = batches, H = w->hidden, F = w->ffn, L = w->num_layers;
   const long long rows = static_cast<long long>(B) * s.frames;
   const float eps = w->ln_eps;
+  Ragged rg;
+  RC(plan_ragged(w, B, samples, samples_per_utt, s.frames, &rg));
+  float* const h0 = rg.on ? s.hpad : s.h;  // padded-layout stream the front end writes
+  if (rg.on) {
+    B2S_CUDA_CHECK(cudaMemcpyAsync(s.cu, rg.cu.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    B2S_CUDA_CHECK(cudaMemcpyAsync(s.pack_idx, rg.pack.data(), rg.pack.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    B2S_CUDA_CHECK(cudaMemcpyAsync(s.unpack_idx, rg.unpack.data(), rg.unpack.size() * sizeof(int), cudaMemcpyHostToDevice,
+                                   stream));
+    B2S_CUDA_CHECK(cudaMemcpyAsync(s.tail, rg.tail.data(), rg.tail.size(), cudaMemcpyHostToDevice, stream));
+    B2S_CUDA_CHECK(cudaMemsetAsync(s.zeros_h, 0, static_cast<size_t>(H) * 4, stream));
+  }
 
   RC(conv0_ln_gelu_fwd(wave, wave_stride, B, samples, w->conv0_w, w->conv0_b, w->conv0_ln_g, w->conv0_ln_b, eps,
                        s.conv_x[0], s.t[1], stream));
@@ -445,13 +516,15 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
     GemmArgs g = lin(s.xn, w->fp_w, rows, H, 512);
     g.epi = EPI_F32;
     g.bias = w->fp_b;
-    g.out = s.h;
+    g.out = h0;
     if (reg) set_drop(g, make_drop_spec(reg->seed, SITE_FEAT_PROJ, reg->p_feat_proj));
     RC(gemm_bf16_launch(g, stream));
   }
   if (reg && reg->time_mask)  // SpecAugment: masked frames become masked_spec_embed (after the projection dropout)
-    RC(mask_rows_f32(s.h, reg->time_mask, reg->masked_spec_embed, rows, H, stream));
-  RC(cast_f32_to_bf16(s.h, s.hp_bf, rows * H, stream));
+    RC(mask_rows_f32(h0, reg->time_mask, reg->masked_spec_embed, rows, H, stream));
+  if (rg.on)  // frames past an utterance's end become the zero padding its positional conv must see
+    RC(mask_rows_f32(h0, s.tail, s.zeros_h, rows, H, stream));
+  RC(cast_f32_to_bf16(h0, s.hp_bf, rows * H, stream));
   {
     GemmArgs g{};
     g.A = s.hp_bf;
@@ -474,8 +547,8 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
     g.epi = EPI_RESID_F32;
     g.act = ACT_GELU;
     g.bias = w->pos_b;
-    g.out = s.h;
-    g.resid = s.h;
+    g.out = h0;
+    g.resid = h0;
     g.ldo = H;
     g.out_batch_rows = s.frames;
     g.out2 = s.pos_pre;
@@ -483,15 +556,26 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
     RC(gemm_bf16_launch(g, stream));
   }
   if (reg)  // dropout(hidden + positional embedding): after the residual add, so not an epilogue of that GEMM
-    RC(dropout_apply(s.h, nullptr, rows * H, make_drop_spec(reg->seed, SITE_POS_ADD, reg->p_hidden), stream));
-  iota_scaled<<<(B + 1 + 255) / 256, 256, 0, stream>>>(s.cu, B + 1, s.frames);
-  B2S_LAUNCH_CHECK();
-  const size_t rH = static_cast<size_t>(rows) * H;
+    RC(dropout_apply(h0, nullptr, rows * H, make_drop_spec(reg->seed, SITE_POS_ADD, reg->p_hidden), stream));
+  const long long srows = rg.on ? rg.rows_packed : rows;  // rows of the transformer stack
+  if (rg.on) {
+    RC(gather_rows_f32(h0, s.pack_idx, s.h, srows, H, stream));  // padded -> packed valid rows
+  } else {
+    iota_scaled<<<(B + 1 + 255) / 256, 256, 0, stream>>>(s.cu, B + 1, s.frames);
+    B2S_LAUNCH_CHECK();
+  }
+  const size_t rH = static_cast<size_t>(srows) * H;
   {
     StackBufs sb{s.h, s.h_mid, s.lse, s.qkv, s.ao, s.ff_pre, s.ff};
-    RC(stack_forward_train(w->layers, L, H, F, w->heads, eps, sb, s.xn, s.cu, B, s.frames, stream, reg));
+    RC(stack_forward_train(w->layers, L, H, F, w->heads, eps, sb, s.xn, s.cu, B, rg.on ? rg.max_frames : s.frames,
+                           stream, reg, rg.on ? srows : -1));
   }
-  RC(layernorm_avgpool_fwd(s.h + L * rH, w->final_ln_g, w->final_ln_b, eps, s.pooled_x, B, s.frames, H, w->pool_kernel,
+  const float* h_last = s.h + L * rH;
+  if (rg.on) {  // packed -> padded (tail rows zero) for the per-utterance pooling windows
+    RC(gather_rows_f32(s.h + L * rH, s.unpack_idx, s.hpad, rows, H, stream));
+    h_last = s.hpad;
+  }
+  RC(layernorm_avgpool_fwd(h_last, w->final_ln_g, w->final_ln_b, eps, s.pooled_x, B, s.frames, H, w->pool_kernel,
                            w->pool_stride, s.pooled, stream));
   {
     GemmArgs g = lin(s.pooled_x, w->proj_w, static_cast<long long>(B) * s.pooled, w->llm_dim, H);
@@ -504,8 +588,8 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
 }
 
 int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* gr, const float* wave,
-                    long long wave_stride, int batches, int samples, void* saved, size_t saved_bytes,
-                    const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
+                    long long wave_stride, int batches, int samples, const int* samples_per_utt, void* saved,
+                    size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
                     const b2s_encoder_regularizers* reg, cudaStream_t stream) {
   B2S_REQUIRE(w && pos_w_dgrad && gr && gr->layers && wave && saved && d_audio_embeds && workspace,
               "hubert_backward: null pointer");
@@ -520,15 +604,35 @@ int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const 
   const int B = batches, H = w->hidden, F = w->ffn, L = w->num_layers, Cl = w->llm_dim;
   const long long rows = static_cast<long long>(B) * s.frames;
   const float eps = w->ln_eps;
-  const size_t rH = static_cast<size_t>(rows) * H;
+  Ragged rg;
+  RC(plan_ragged(w, B, samples, samples_per_utt, s.frames, &rg));  // device index arrays are still in `saved`
+  const long long srows = rg.on ? rg.rows_packed : rows;
+  const size_t rH = static_cast<size_t>(srows) * H;
 
   // ---- projector + AvgPool + final LayerNorm, then the transformer layers last to first
   StackBufs sb{s.h, s.h_mid, s.lse, s.qkv, s.ao, s.ff_pre, s.ff};
   StackScratch sc{b.dh, b.delta, b.dyb, b.dbig, b.dsm, b.xn};
-  RC(head_backward(w->proj_w, w->final_ln_g, w->final_ln_b, gr->proj_w, gr->proj_b, gr->final_ln_g, gr->final_ln_b,
-                   s.h + L * rH, s.pooled_x, d_audio_embeds, b.da, b.dpool, b.dxn_f, sc, B, s.frames, s.pooled, H, Cl,
-                   w->pool_kernel, w->pool_stride, eps, stream));
-  RC(stack_backward(w->layers, gr->layers, L, H, F, w->heads, eps, sb, sc, s.cu, B, s.frames, stream, reg));
+  if (rg.on) {
+    // padded layout: h[L] scattered back by the forward lives in s.hpad; the head's gradient goes to the padded twins
+    StackScratch sc_pad{b.dh_pad, b.delta, b.dyb_pad, b.dbig, b.dsm, b.xn};
+    RC(head_backward(w->proj_w, w->final_ln_g, w->final_ln_b, gr->proj_w, gr->proj_b, gr->final_ln_g, gr->final_ln_b,
+                     s.hpad, s.pooled_x, d_audio_embeds, b.da, b.dpool, b.dxn_f, sc_pad, B, s.frames, s.pooled, H, Cl,
+                     w->pool_kernel, w->pool_stride, eps, stream));
+    RC(gather_rows_f32(b.dh_pad, s.pack_idx, b.dh, srows, H, stream));
+    RC(cast_f32_to_bf16(b.dh, b.dyb, srows * H, stream));
+  } else {
+    RC(head_backward(w->proj_w, w->final_ln_g, w->final_ln_b, gr->proj_w, gr->proj_b, gr->final_ln_g, gr->final_ln_b,
+                     s.h + L * rH, s.pooled_x, d_audio_embeds, b.da, b.dpool, b.dxn_f, sc, B, s.frames, s.pooled, H,
+                     Cl, w->pool_kernel, w->pool_stride, eps, stream));
+  }
+  RC(stack_backward(w->layers, gr->layers, L, H, F, w->heads, eps, sb, sc, s.cu, B, rg.on ? rg.max_frames : s.frames,
+                    stream, reg, rg.on ? srows : -1));
+  if (rg.on) {  // packed -> padded gradient of h0 (tail rows zero); the front end's backward runs on the padded layout
+    RC(gather_rows_f32(b.dh, s.unpack_idx, b.dh_pad, rows, H, stream));
+    RC(cast_f32_to_bf16(b.dh_pad, b.dyb_pad, rows * H, stream));
+    b.dh = b.dh_pad;
+    b.dyb = b.dyb_pad;
+  }
 
   // ---- positional conv embedding: h0 = drop(hp + gelu(conv(hp) + b)); dh / dyb = gradient w.r.t. h0
   if (reg) RC(dropout_apply(b.dh, b.dyb, rows * H, make_drop_spec(reg->seed, SITE_POS_ADD, reg->p_hidden), stream));
@@ -596,6 +700,8 @@ int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const 
     RC(gemm_bf16_launch(g, stream));
   }
   // ---- feature projection: hp = specaug(drop(fp_w LN(conv_x[6]) + fp_b)) ; dh = gradient w.r.t. hp
+  if (rg.on)  // the forward zeroed the tail rows: they pass no gradient on (the conv transpose wrote into them)
+    RC(mask_rows_f32(b.dh, s.tail, s.zeros_h, rows, H, stream));
   if (reg)
     RC(featproj_reg_bwd(b.dh, reg->time_mask, reg->g_masked_spec_embed, rows, H,
                         make_drop_spec(reg->seed, SITE_FEAT_PROJ, reg->p_feat_proj), stream));

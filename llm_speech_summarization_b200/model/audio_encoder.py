@@ -574,13 +574,22 @@ class AudioEncoder(nn.Module):
         self._grads = (g, layers, scratch, key, pending, _Ptr(ptr["masked_spec_embed"]) if hubert else None)
         return self._grads
 
-    def forward_train(self, input: torch.Tensor, generator=None, draw=None) -> torch.Tensor:
+    def num_audio_embeds(self, samples: int) -> int:
+        """Pooled frames (= projected audio embeddings) an utterance of `samples` samples produces on its own."""
+        return self.num_frames(int(samples))[1]
+
+    def forward_train(self, input: torch.Tensor, generator=None, draw=None, lengths=None) -> torch.Tensor:
         """Training forward (REF/trainer.py:278): (B, T0) waveform -> fp32 (B, A, llm_dim), keeping the activations
         for `backward`. With `self.regularizers` set and the module in train mode, HF's train-mode dropout / LayerDrop /
-        SpecAugment are applied (host randomness from `generator`, or an explicit `draw`); otherwise deterministic."""
+        SpecAugment are applied (host randomness from `generator`, or an explicit `draw`); otherwise deterministic.
+        `lengths` (samples per utterance, HuBERT only): a ragged batch, zero-padded on the right to T0 like the
+        reference's collate (REF/trainer.py:146-149). Every utterance gets the numbers it would get alone; rows
+        >= num_audio_embeds(lengths[b]) of output b are padding (REF/trainer.py:280-291 crops them)."""
         if not input.is_cuda:
             raise RuntimeError("AudioEncoder.forward_train (B200 path) needs a CUDA input; there is no CPU path")
         if self.encoder_base == "whisper":
+            if lengths is not None:
+                raise NotImplementedError("ragged batches are a HuBERT feature: Whisper inputs are fixed 30 s windows")
             return self._whisper_forward_train(input)
         w = self.pack_weights()[0]
         wave = input.to(torch.float32)
@@ -606,10 +615,18 @@ class AudioEncoder(nn.Module):
                 mse = mse.float().contiguous()
             ctx["mse"] = mse
             reg = C.byref(draw.c_struct(mse, None))
-        _lib.check(lib.b2s_hubert_forward_train(C.byref(w), wave.data_ptr(), wave.stride(0), B, T0,
+        c_len, n_valid = None, None
+        if lengths is not None:
+            lengths = [int(n) for n in lengths]
+            if len(lengths) != B or max(lengths) > T0 or min(lengths) <= 0:
+                raise ValueError("lengths must give 0 < samples <= T0 for each of the B utterances")
+            if any(n != T0 for n in lengths):
+                c_len = (C.c_int32 * B)(*lengths)
+                n_valid = [self.num_audio_embeds(n) for n in lengths]
+        _lib.check(lib.b2s_hubert_forward_train(C.byref(w), wave.data_ptr(), wave.stride(0), B, T0, c_len,
                                                 ctx["saved"].data_ptr(), ctx["saved"].numel(), out.data_ptr(), reg,
                                                 torch.cuda.current_stream().cuda_stream), "hubert_forward_train")
-        ctx.update(wave=wave, B=B, T0=T0, pooled=pooled, draw=draw)
+        ctx.update(wave=wave, B=B, T0=T0, pooled=pooled, draw=draw, c_len=c_len, n_valid=n_valid)
         self._train_ctx = ctx
         return out
 
@@ -672,8 +689,13 @@ class AudioEncoder(nn.Module):
         reg = None
         if ctx.get("draw") is not None:
             reg = C.byref(ctx["draw"].c_struct(ctx["mse"], self._grad_buffers()[5]))
+        if ctx.get("n_valid") is not None:  # ragged batch: the padding rows of the embeddings carry no gradient
+            d = d.clone() if d.data_ptr() == d_audio_embeds.data_ptr() else d
+            for b_, nv in enumerate(ctx["n_valid"]):
+                d[b_, nv:].zero_()
         _lib.check(lib.b2s_hubert_backward(C.byref(w), self._pos_w_dgrad.data_ptr(), C.byref(g), wave.data_ptr(),
-                                           wave.stride(0), ctx["B"], ctx["T0"], ctx["saved"].data_ptr(),
+                                           wave.stride(0), ctx["B"], ctx["T0"], ctx.get("c_len"),
+                                           ctx["saved"].data_ptr(),
                                            ctx["saved"].numel(), d.data_ptr(), ctx["bws"].data_ptr(),
                                            ctx["bws"].numel(), reg, torch.cuda.current_stream().cuda_stream),
                    "hubert_backward")

@@ -42,15 +42,22 @@ class StepPlan:
     student_rows_total: int = 0                # rows of all student sequences (they are packed first)
 
 
-def build_plan(prefix: Sequence[int], suffix: Sequence[int], n_audio: int, text_ids: Sequence[Sequence[int]],
-               resp_ids: Sequence[Sequence[int]], with_teacher: bool = True) -> Dict[str, object]:
+def build_plan(prefix: Sequence[int], suffix: Sequence[int], n_audio, text_ids: Sequence[Sequence[int]],
+               resp_ids: Sequence[Sequence[int]], with_teacher: bool = True,
+               audio_stride: Optional[int] = None) -> Dict[str, object]:
     """Pure-python index construction (no torch, unit-tested on CPU).
     Sequence layout (REF/utils.py:27-46 + the double BOS strip):
         student_i = prefix | audio rows of utterance i | suffix[1:] | response_i[1:]
         teacher_i = prefix | transcript_i              | suffix[1:] | response_i[1:]
     Packed order: student_0..student_{B-1}, teacher_0..teacher_{B-1}. Logits are produced for the last R_i rows of
-    each; CE labels for row j < R_i - 1 of utterance i are response_i[j+1], the last row has none (-1)."""
+    each; CE labels for row j < R_i - 1 of utterance i are response_i[j+1], the last row has none (-1).
+    `n_audio` is one count for all utterances or a per-utterance list (ragged batch); the audio embeddings sit in a
+    [B, audio_stride, C] tensor (audio_stride = the largest count by default) and only the first n_audio[i] rows of
+    utterance i enter its sequence (REF/trainer.py:280-291)."""
     B = len(resp_ids)
+    n_each = [int(n_audio)] * B if isinstance(n_audio, int) else [int(n) for n in n_audio]
+    A = max(n_each) if audio_stride is None else int(audio_stride)
+    assert len(n_each) == B and max(n_each) <= A
     row_src: List[int] = []
     cu = [0]
     positions: List[int] = []
@@ -58,7 +65,7 @@ def build_plan(prefix: Sequence[int], suffix: Sequence[int], n_audio: int, text_
     suf = list(suffix[1:])
     for i in range(B):
         resp = list(resp_ids[i])[1:]
-        seq = list(prefix) + [-(i * n_audio + r) - 1 for r in range(n_audio)] + suf + resp
+        seq = list(prefix) + [-(i * A + r) - 1 for r in range(n_each[i])] + suf + resp
         row_src.extend(seq)
         positions.extend(range(len(seq)))
         cu.append(cu[-1] + len(seq))
@@ -86,7 +93,8 @@ def build_plan(prefix: Sequence[int], suffix: Sequence[int], n_audio: int, text_
         labels.extend(list(resp_ids[i])[1:] + [-1])
         offs.append(offs[-1] + R)
     P = len(prefix)
-    audio_rows = [cu[i] + P + r for i in range(B) for r in range(n_audio)]
+    # packed row of audio embedding (i, r) in the [B, A] layout; -1 = padding row of a ragged batch (zero gradient)
+    audio_rows = [cu[i] + P + r if r < n_each[i] else -1 for i in range(B) for r in range(A)]
     return dict(row_src=row_src, cu_seqlens=cu, positions=positions, student_rows=s_rows, teacher_rows=t_rows,
                 labels=labels, row_offsets=offs, max_seqlen=max(L_audio + L_text), rows=cu[-1], sum_r=offs[-1],
                 resp_lens=resp_lens, L_audio=L_audio, L_text=L_text, audio_rows=audio_rows,
@@ -152,10 +160,10 @@ class AudioPromptStep:
                    use_fd_loss=t.use_fd_loss, ntp_loss_weight=t.ntp_loss_weight, ld_loss_weight=t.ld_loss_weight,
                    fd_loss_weight=t.fd_loss_weight, fd_loss_connector_layers=t.fd_loss_connector_layers)
 
-    def plan(self, n_audio: int, text_ids, resp_ids, device) -> StepPlan:
+    def plan(self, n_audio, text_ids, resp_ids, device, audio_stride: Optional[int] = None) -> StepPlan:
         as_list = lambda xs: [x.tolist() if torch.is_tensor(x) else list(x) for x in xs]
         d = build_plan(self.prefix, self.suffix, n_audio, as_list(text_ids), as_list(resp_ids),
-                       with_teacher=(self.use_ld or self.use_fd))
+                       with_teacher=(self.use_ld or self.use_fd), audio_stride=audio_stride)
         i32 = lambda x: torch.tensor(x, dtype=torch.int32).pin_memory().to(device, non_blocking=True)
         return StepPlan(row_src=i32(d["row_src"]), cu_seqlens=i32(d["cu_seqlens"]), positions=i32(d["positions"]),
                         logit_rows=i32(d["student_rows"] + d["teacher_rows"]), labels=i32(d["labels"]),
@@ -240,15 +248,15 @@ class AudioPromptStep:
 
     @torch.no_grad()
     def llm_forward_backward(self, audio: torch.Tensor, text_ids, resp_ids, loss_scale: float = 1.0,
-                             plan: Optional[StepPlan] = None) -> Dict[str, torch.Tensor]:
+                             plan: Optional[StepPlan] = None, n_audio=None) -> Dict[str, torch.Tensor]:
         """The LLM half of the TRAINING step for projected audio embeddings `audio` (B, A, C) fp32:
         splice -> training forward (activations kept) -> losses -> backward through the frozen LLM
         (REF/trainer.py:299-374). Returns the per-utterance losses and `d_audio_embeds` (B, A, C) fp32 =
         d( sum_u loss_scale * total_u ) / d audio  -- loss_scale = 1 / grad_accum_interval in the reference."""
         dev = audio.device
         B, A, Cdim = audio.shape
-        if plan is None:
-            plan = self.plan(A, text_ids, resp_ids, dev)
+        if plan is None:  # n_audio: per-utterance counts of a ragged batch (the first n_audio[i] rows of audio[i])
+            plan = self.plan(A if n_audio is None else n_audio, text_ids, resp_ids, dev, audio_stride=A)
         with_teacher = self.use_ld or self.use_fd
         saved, st = self.llm.alloc_saved(plan.rows, dev)
         ops.embed_splice(self.llm.model.embed_tokens.weight, audio.reshape(B * A, Cdim).contiguous(), plan.row_src,
@@ -292,21 +300,24 @@ class AudioPromptStep:
     @torch.no_grad()
     def forward_backward(self, waves: torch.Tensor, text_ids, resp_ids, loss_scale: float = 1.0,
                          plan: Optional[StepPlan] = None, generator=None, draw=None,
-                         num_audio_embeds: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                         num_audio_embeds: Optional[int] = None, lengths=None) -> Dict[str, torch.Tensor]:
         """One training micro-batch (REF/trainer.py:270-374): encoder forward with kept activations -> LLM
         forward/backward -> encoder backward. Parameter gradients (x loss_scale) accumulate inside the encoder
         until `audio_encoder.flush_grads()`. `generator` / `draw` feed the encoder's train-mode regularisers
         (AudioEncoder.forward_train)."""
         if not waves.is_cuda:
             raise RuntimeError("AudioPromptStep needs CUDA inputs; there is no CPU path")
+        kw = {}
         if generator is not None or draw is not None:
-            audio = self.audio_encoder.forward_train(waves, generator=generator, draw=draw)
-        else:
-            audio = self.audio_encoder.forward_train(waves)
+            kw.update(generator=generator, draw=draw)
+        if lengths is not None:  # ragged batch: waves zero-padded on the right, samples per utterance in `lengths`
+            kw.update(lengths=lengths)
+        audio = self.audio_encoder.forward_train(waves, **kw)
+        n_valid = (self.audio_encoder._train_ctx or {}).get("n_valid") if lengths is not None else None
         A_full = audio.shape[1]
         if num_audio_embeds is not None and num_audio_embeds < A_full:  # REF/trainer.py:280-291 (see forward_losses)
             audio = audio[:, :num_audio_embeds].contiguous()
-        out = self.llm_forward_backward(audio, text_ids, resp_ids, loss_scale=loss_scale, plan=plan)
+        out = self.llm_forward_backward(audio, text_ids, resp_ids, loss_scale=loss_scale, plan=plan, n_audio=n_valid)
         d = out["d_audio_embeds"]
         if d.shape[1] < A_full:  # the cropped embeddings get no gradient
             d = torch.nn.functional.pad(d, (0, 0, 0, A_full - d.shape[1]))

@@ -190,13 +190,14 @@ class EncoderTrainer:
 
     @torch.no_grad()
     def train_step(self, waves: torch.Tensor, text_ids, resp_ids, last_batch: bool = False,
-                   plan=None, num_audio_embeds: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                   plan=None, num_audio_embeds: Optional[int] = None, lengths=None) -> Dict[str, torch.Tensor]:
         """One micro-batch of B utterances on this rank. The accumulation window counts utterances GLOBALLY:
         an optimizer step happens once world * (micro-batches * B) reaches grad_accum_interval (or at loader end)."""
         B = waves.shape[0]
         out = self.step_fn.forward_backward(waves, text_ids, resp_ids, loss_scale=1.0 / self.grad_accum_interval,
                                             plan=plan, generator=self.generator,
-                                            **({} if num_audio_embeds is None else {"num_audio_embeds": num_audio_embeds}))
+                                            **({} if num_audio_embeds is None else {"num_audio_embeds": num_audio_embeds}),
+                                            **({} if lengths is None else {"lengths": lengths}))
         self._micro += B * self.world()
         self.step += 1
         out["optimizer_step"] = False

@@ -498,3 +498,56 @@ def test_trainer_dropin_runs_the_reference_loop(cuda, tmp_path):
     assert tr2.step == 5 and tr2.start_epoch == 0 and tr2.optimizer.step_count == 3
     for k, v in tr2.audio_encoder.state_dict().items():
         assert torch.equal(v.cpu(), after[k].cpu()), k
+
+
+def test_ragged_batch_equals_each_utterance_alone(cuda):
+    """Utterances of different lengths in ONE micro-batch (zero-padded waveforms + `lengths`, the reference's collate
+    layout): projected embeddings, losses and the accumulated parameter gradients equal running every utterance on
+    its own -- the reference's own batch_size > 1 path attends over the padding and does not have this property."""
+    from llm_speech_summarization_b200.step import AudioPromptStep
+    configs, enc_cfg, llm_cfg, enc_sd, llm_sd = _tiny()
+    lens = [6000, 4800, 5610]
+    utts = [configs.synthetic_utterance(llm_cfg, i, n, T=5 + i, R=4 + i) for i, n in enumerate(lens)]
+    T0 = max(lens)
+    padded = torch.zeros(len(lens), T0)
+    for i, (w, _, _) in enumerate(utts):
+        padded[i, :lens[i]] = w
+    t_ids, r_ids = [u[1] for u in utts], [u[2] for u in utts]
+
+    def fresh():
+        cfg, enc, llm = build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, cuda)
+        tok = configs.stub_tokenizer(llm_cfg)
+        return enc, AudioPromptStep(enc, llm, tok, llm_cfg.llm_type, fd_loss_connector_layers=[0, 1, 2])
+
+    enc, step = fresh()
+    emb = enc.forward_train(padded.to(cuda), lengths=lens).clone()
+    n_valid = [enc.num_audio_embeds(n) for n in lens]
+    assert len(set(n_valid)) > 1 and emb.shape[1] == max(n_valid)
+    out = step.forward_backward(padded.to(cuda), t_ids, r_ids, loss_scale=0.5, lengths=lens)
+    enc.flush_grads()
+    g_ragged = {k: p.grad.detach().clone() for k, p in enc.named_parameters() if p.grad is not None}
+
+    enc1, step1 = fresh()
+    losses = []
+    for i, (w, t, r) in enumerate(utts):
+        e1 = enc1.forward_train(w[None].to(cuda))
+        assert e1.shape[1] == n_valid[i]
+        assert rel_l2(emb[i, :n_valid[i]].cpu(), e1[0].cpu()) < 1e-3, i
+        o1 = step1.forward_backward(w[None].to(cuda), [t], [r], loss_scale=0.5)
+        losses.append(float(o1["total_loss"][0]))
+    enc1.flush_grads()
+    assert torch.allclose(out["total_loss"].cpu(), torch.tensor(losses), rtol=1e-3)
+    g_single = {k: p.grad for k, p in enc1.named_parameters() if p.grad is not None}
+    tot_a = torch.cat([g_ragged[k].reshape(-1) for k in g_single])
+    tot_b = torch.cat([g_single[k].reshape(-1) for k in g_single])
+    assert rel_l2(tot_a.cpu(), tot_b.cpu()) < 1e-2, rel_l2(tot_a.cpu(), tot_b.cpu())
+    for k in g_single:
+        if float(g_single[k].norm()) > 1e-2 * float(tot_b.norm()):
+            assert rel_l2(g_ragged[k].cpu(), g_single[k].cpu()) < 2e-2, k
+    # with regularisers on the ragged path still runs and stays finite
+    from llm_speech_summarization_b200.regularizers import RegularizerConfig
+    enc.regularizers = RegularizerConfig()
+    enc.train()
+    o2 = step.forward_backward(padded.to(cuda), t_ids, r_ids, loss_scale=0.5, lengths=lens,
+                               generator=torch.Generator().manual_seed(0))
+    assert bool(torch.isfinite(o2["total_loss"]).all())
