@@ -106,6 +106,9 @@ def parse():
                     help="train workload: HF train-mode regularisers of the encoder (REF/trainer.py:258). 'dropout' = "
                          "every dropout site + SpecAugment (same work as the deterministic step plus the mask "
                          "generation), 'all' = also LayerDrop (skips ~10%% of the encoder layers, like the reference)")
+    ap.add_argument("--ragged", action="store_true",
+                    help="train workload: utterance lengths drawn uniformly from [5 s, 10 s] (one ragged micro-batch "
+                         "per step, zero-padded waveforms + lengths) instead of 10 s each")
     ap.add_argument("--gemm-shapes", default="", help="write the per-shape GEMM table of the instrumented steps here")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts", type=int, default=3, help="utterances timed for the CPU baseline sample")
@@ -358,8 +361,21 @@ def main():
     plans = [step.plan(123, t, r, dev) for (_, t, r) in resident]
     torch.cuda.synchronize()
 
+    ragged_lens = None
+    if args.ragged:
+        assert train, "--ragged applies to --workload train"
+        gl = torch.Generator().manual_seed(4242 + rank)
+        ragged_lens = [[int(x) for x in torch.randint(SAMPLES // 2, SAMPLES + 1, (B,), generator=gl)] for _ in range(n_pool)]
+        for k in range(n_pool):
+            ragged_lens[k][0] = SAMPLES  # the padded length is the longest utterance
+            for b_, n_ in enumerate(ragged_lens[k]):
+                resident[k][0][b_, n_:] = 0
+                host[k][0][b_, n_:] = 0
+
     def run_resident(i):
         w, t, r = resident[i % n_pool]
+        if train and ragged_lens is not None:
+            return trainer.train_step(w, t, r, lengths=ragged_lens[i % n_pool])
         if train:
             return trainer.train_step(w, t, r, plan=plans[i % n_pool])
         return step.forward_losses(w, t, r, plan=plans[i % n_pool])
@@ -395,15 +411,16 @@ def main():
             print(json.dumps({"profile_mode": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)}))
         return
     # ---- e2e: host buffers -> H2D -> step -> D2H, through the public call
+    rag = (lambda i: {"lengths": ragged_lens[i % n_pool]}) if ragged_lens is not None else (lambda i: {})
     for i in range(min(2, args.warmup)):
-        public(host[i % n_pool][0], host[i % n_pool][1], host[i % n_pool][2], dev)
+        public.submit(host[i % n_pool][0], host[i % n_pool][1], host[i % n_pool][2], dev, **rag(i)).result()
     torch.cuda.synchronize()
     dp.barrier()
     t0 = time.perf_counter()
     pending = None  # the streaming form of the public call: batch i+1 is submitted before batch i's losses are read
     for i in range(args.steps):
         w, t, r = host[i % n_pool]
-        nxt = public.submit(w, t, r, dev)
+        nxt = public.submit(w, t, r, dev, **rag(i))
         if pending is not None:
             res = pending.result()
         pending = nxt
@@ -494,7 +511,9 @@ def main():
                 "config": {"workload": workload, "utterances_per_step_per_gpu": B, "parallelism": f"dp{world}",
                            "l2": "no flush needed: every step streams ~7 GB of weights and >2 GB of activations "
                                  "(>> 126 MB L2); two distinct micro-batches alternate",
-                           "timed": timed, **({"regularize": args.regularize} if train else {})},
+                           "timed": timed, **({"regularize": args.regularize} if train else {}),
+                           **({"ragged": "utterance lengths uniform in [5 s, 10 s], mean %.2f s" % (
+                               sum(map(sum, ragged_lens)) / (len(ragged_lens) * B) / 16000.0)} if ragged_lens else {})},
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "submit()/result(), one batch in flight ahead of the one being read"},

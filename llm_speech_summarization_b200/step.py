@@ -177,7 +177,8 @@ class AudioPromptStep:
 
     @torch.no_grad()
     def forward_losses(self, waves: torch.Tensor, text_ids, resp_ids, plan: Optional[StepPlan] = None,
-                       keep: bool = False, num_audio_embeds: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                       keep: bool = False, num_audio_embeds: Optional[int] = None,
+                       lengths=None) -> Dict[str, torch.Tensor]:
         """waves: CUDA fp32 (B, T0), equal-length utterances (the reference's collate zero-pads a batch to one
         length, REF/trainer.py:146-149; batch-1 has no padding). Returns per-utterance device tensors
         ntp_loss / ld_loss / fd_loss / total_loss of shape (B,)."""
@@ -185,14 +186,24 @@ class AudioPromptStep:
             raise RuntimeError("AudioPromptStep needs CUDA inputs; there is no CPU path")
         dev = waves.device
         B = waves.shape[0]
-        audio = self.audio_encoder.forward_fp32(waves)  # (B, A, C) fp32
+        n_valid = None
+        if lengths is not None and len(set(int(n) for n in lengths)) > 1:
+            # ragged batch (zero-padded waveforms + samples per utterance): the ragged-aware kernels are the training
+            # forward's; in eval mode it applies no regulariser, its saved activations are simply not used
+            was_training = self.audio_encoder.training
+            self.audio_encoder.eval()
+            audio = self.audio_encoder.forward_train(waves, lengths=lengths)
+            self.audio_encoder.train(was_training)
+            n_valid = self.audio_encoder._train_ctx.get("n_valid")
+        else:
+            audio = self.audio_encoder.forward_fp32(waves)  # (B, A, C) fp32
         if num_audio_embeds is not None and num_audio_embeds < audio.shape[1]:
             # the trainer's un-padding (REF/trainer.py:280-291): Whisper's fixed 30 s window gives 374 pooled frames,
             # compute_num_audio_embeds keeps the ones covered by audio
             audio = audio[:, :num_audio_embeds].contiguous()
         A, Cdim = audio.shape[1], audio.shape[2]
         if plan is None:
-            plan = self.plan(A, text_ids, resp_ids, dev)
+            plan = self.plan(A if n_valid is None else n_valid, text_ids, resp_ids, dev, audio_stride=A)
         h = ops.embed_splice(self.llm.model.embed_tokens.weight, audio.view(B * A, Cdim), plan.row_src)
         with_teacher = self.use_ld or self.use_fd
         taps = [l for l in self.fd_layers if l > 0] if self.use_fd else []

@@ -10,9 +10,10 @@ What is different underneath: the batch goes through `EncoderTrainer.train_step`
 hand-written CUDA path, no autograd, no GradScaler: bf16 needs no loss scaling), the optimizer is the flat AdamW with
 `torch.optim.AdamW`'s state layout, the Whisper log-mel features are computed on the GPU instead of inside the collate
 function, and under `torch.distributed` every rank takes its shard of the utterances (DistributedSampler) with one SUM
-all-reduce per optimizer step. Utterances of one loader batch are run as packed micro-batches of EQUAL length
-(different lengths run one after another): every utterance keeps the reference's batch-1 numerics -- the reference's
-own batch_size > 1 path attends over zero padding without a mask and is not reproduced.
+all-reduce per optimizer step. A loader batch of utterances of DIFFERENT lengths is one ragged micro-batch (HuBERT:
+the zero-padded waveforms plus their lengths go to `b2s_hubert_forward_train`, which keeps every utterance's batch-1
+numerics; Whisper inputs are fixed 30 s windows anyway) -- the reference's own batch_size > 1 path attends over the
+zero padding without a mask and is not reproduced.
 
 Offline use (tests, benchmarks): `tokenizer`, `llm`, `train_dataset`, `val_dataset` and `writer` can be injected; left
 as None they are loaded exactly like the reference does (AutoTokenizer / from_pretrained / datasets.load_from_disk /
@@ -275,14 +276,20 @@ class Trainer():
                 self.train_sampler.set_epoch(epoch)
             for batch_idx, (_, padded_inputs, audio_len_samples, _, text_input_ids, response_input_ids,
                             _) in enumerate(self.train_dataloader):
-                micro = self._micro_batches(padded_inputs, audio_len_samples, text_input_ids, response_input_ids)
+                if self.encoder_base == "hubert":  # one ragged micro-batch (lengths=None when they are all equal)
+                    ragged = len(set(int(n) for n in audio_len_samples)) > 1
+                    micro = [(padded_inputs, text_input_ids, response_input_ids, None,
+                              [int(n) for n in audio_len_samples] if ragged else None)]
+                else:
+                    micro = [m + (None,) for m in self._micro_batches(padded_inputs, audio_len_samples, text_input_ids,
+                                                                      response_input_ids)]
                 last_of_loader = batch_idx + 1 == n_batches
                 sums: Dict[str, float] = {}
                 count = 0
-                for j, (waves, t_ids, r_ids, keep) in enumerate(micro):
+                for j, (waves, t_ids, r_ids, keep, lengths) in enumerate(micro):
                     out = self.core.train_step(self._encoder_input(waves), t_ids, r_ids,
                                                last_batch=last_of_loader and j + 1 == len(micro),
-                                               num_audio_embeds=keep)
+                                               num_audio_embeds=keep, lengths=lengths)
                     if (self.step + 1) % log.log_interval == 0:  # .item()-style syncs only when logging
                         for k in ("ntp_loss", "ld_loss", "fd_loss"):
                             if k in out:

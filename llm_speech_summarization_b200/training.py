@@ -217,13 +217,14 @@ class EncoderTrainer:
         a D2H read of the per-utterance losses (what bench.py's `e2e` times for the training workload)."""
         return self.submit(waves_host, text_ids, resp_ids, device).result()
 
-    def submit(self, waves_host: torch.Tensor, text_ids, resp_ids, device):
+    def submit(self, waves_host: torch.Tensor, text_ids, resp_ids, device, lengths=None):
         """Streaming form of `__call__` (see AudioPromptStep.submit): returns a PendingStep whose `result()` holds the
         losses and `optimizer_step`."""
         from .step import _losses_to_host, _stage_to_device
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device)
-        out = self.train_step(_stage_to_device(waves_host, device, self._copy_stream), text_ids, resp_ids)
+        out = self.train_step(_stage_to_device(waves_host, device, self._copy_stream), text_ids, resp_ids,
+                              lengths=lengths)
         pending = _losses_to_host(out)
         pending.extra["optimizer_step"] = out["optimizer_step"]
         return pending

@@ -484,3 +484,19 @@ def test_trainer_collate_matches_reference_semantics():
     with pytest.raises(RuntimeError, match="no CPU path"):
         from types import SimpleNamespace as NS
         Trainer(NS(run_name="x", checkpoint_path=None), NS(), "cpu")
+
+
+def test_build_plan_ragged_audio_counts():
+    """Per-utterance audio-embedding counts (ragged batch): sources index the [B, stride] embedding layout, padding
+    rows never enter a sequence and map to -1 in the gradient gather; an int count is the uniform special case."""
+    from llm_speech_summarization_b200.step import build_plan
+    prefix, suffix = [1, 2], [9, 8, 7]
+    d = build_plan(prefix, suffix, [3, 1], [[5, 6], [5]], [[0, 4, 4], [0, 4]], audio_stride=3)
+    assert d["row_src"][:9] == [1, 2, -1, -2, -3, 8, 7, 4, 4]            # utterance 0: 3 audio rows (sources 0..2)
+    assert d["row_src"][9:15] == [1, 2, -4, 8, 7, 4]                     # utterance 1: 1 audio row (source 3 = 1*3+0)
+    assert d["L_audio"] == [9, 6] and d["cu_seqlens"][:3] == [0, 9, 15]
+    assert d["audio_rows"] == [2, 3, 4, 11, -1, -1]
+    u = build_plan(prefix, suffix, 2, [[5, 6], [5]], [[0, 4, 4], [0, 4]])
+    assert u == build_plan(prefix, suffix, [2, 2], [[5, 6], [5]], [[0, 4, 4], [0, 4]], audio_stride=2)
+    with pytest.raises(AssertionError):
+        build_plan(prefix, suffix, [3, 1], [[5, 6], [5]], [[0, 4, 4], [0, 4]], audio_stride=2)

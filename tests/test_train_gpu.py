@@ -498,6 +498,15 @@ def test_trainer_dropin_runs_the_reference_loop(cuda, tmp_path):
     assert tr2.step == 5 and tr2.start_epoch == 0 and tr2.optimizer.step_count == 3
     for k, v in tr2.audio_encoder.state_dict().items():
         assert torch.equal(v.cpu(), after[k].cpu()), k
+    # batch_size 2: every loader batch holds two utterances of different lengths -> one ragged micro-batch each
+    cfg.train.batch_size = 2
+    cfg.train.grad_accum_interval = 1
+    tr3 = Trainer(NS(run_name="run2", checkpoint_path=None, gpu_idx=0), cfg, cuda, tokenizer=tok, llm=llm,
+                  train_dataset=train_set[:4], val_dataset=val_set, writer=NullWriter(), regularize=False)
+    tr3.audio_encoder.load_state_dict(enc_sd)
+    tr3.audio_encoder.mark_weights_changed()
+    tr3.train()
+    assert tr3.step == 2 and tr3.optimizer.step_count == 2
 
 
 def test_ragged_batch_equals_each_utterance_alone(cuda):
@@ -544,6 +553,9 @@ def test_ragged_batch_equals_each_utterance_alone(cuda):
     for k in g_single:
         if float(g_single[k].norm()) > 1e-2 * float(tot_b.norm()):
             assert rel_l2(g_ragged[k].cpu(), g_single[k].cpu()) < 2e-2, k
+    # eval-mode losses of the ragged batch (validation / inference batches) = the per-utterance losses too
+    ev = step.forward_losses(padded.to(cuda), t_ids, r_ids, lengths=lens)
+    assert torch.allclose(ev["total_loss"].cpu(), torch.tensor(losses), rtol=1e-3)
     # with regularisers on the ragged path still runs and stays finite
     from llm_speech_summarization_b200.regularizers import RegularizerConfig
     enc.regularizers = RegularizerConfig()
