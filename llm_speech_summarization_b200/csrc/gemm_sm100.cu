@@ -18,6 +18,7 @@
 // (TF/models/llama/modeling_llama.py:171-289, REF/model/audio_llama.py:67).
 #include "gemm_sm100.cuh"
 
+#include <cstdlib>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -89,6 +90,7 @@ struct KParams {
   int og_rows, og_cols;   // output offset per group: rows += g * og_rows, cols += g * og_cols
   uint32_t drop_k1, drop_k2, drop_thresh;  // fused dropout (rng.cuh); thresh 0 = off
   float drop_inv_keep;
+  int resid_red;  // in-place residual adds go through red.global.add (B2S_RESID_RED=0 keeps load + add + store, A/B)
 };
 
 struct TileCoord {
@@ -460,7 +462,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const uint32_t taddr = tmem_base + lane_base + as * BN;
 
       if (p.epi == EPI_BF16 || p.epi == EPI_F32 || p.epi == EPI_RESID_F32 || (EXT && p.epi == EPI_ACCUM_F32)) {
-        const bool has_resid = p.epi == EPI_RESID_F32;
+        // In-place residual (out aliases resid: the inference forward's h += proj(...)): the add is done by the L2 as
+        // an fp32 reduction (red.global.add.v4.f32, one per element, so still deterministic) and the residual never
+        // travels to the SM -- the load -> add -> store chain with one 4 KiB chunk per warp in flight was what bound
+        // the K = 1024 shapes (profiles/r01_gemm_shapes.md).
+        const bool resid_inplace = p.resid_red && p.epi == EPI_RESID_F32 && static_cast<const void*>(p.resid) == p.out &&
+                                   !p.resid_bcast;
+        const bool has_resid = p.epi == EPI_RESID_F32 && !resid_inplace;
         const long long rbase = (p.resid_bcast ? static_cast<long long>(m0w) : orow0) * p.ldo +
                                 static_cast<long long>(tc.g) * og_cols;
         float4 rnext[8];
@@ -501,7 +509,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           if (p.epi == EPI_BF16) {
             emit_bf16(stg, v, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, valid);
-          } else if (EXT && p.epi == EPI_ACCUM_F32) {
+          } else if ((EXT && p.epi == EPI_ACCUM_F32) || resid_inplace) {
             emit_accum_f32(stg, v, lane, reinterpret_cast<float*>(p.out) + off0, p.ldo, rows_valid, valid);
           } else if (has_resid) {
             // (resid_bcast: the residual is indexed by the row inside the batch only, e.g. a positional table)
@@ -833,6 +841,8 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   p.rope_cs = a.rope_cs;
   p.positions = a.positions;
   p.rope_cols = a.rope_cols;
+  static const int resid_red = getenv("B2S_RESID_RED") ? atoi(getenv("B2S_RESID_RED")) : 1;
+  p.resid_red = resid_red;
   p.drop_k1 = a.drop_k1;
   p.drop_k2 = a.drop_k2;
   p.drop_thresh = a.drop_thresh;
