@@ -307,7 +307,9 @@ def gemm_flops_per_utt(train=False):
     per_tok = 2 * 3072 * (5120 + 3072 + 2 * 8192 + 8192)
     llm = 28 * per_tok * (200 + 117) + 2 * 2 * R_RESP * 3072 * 128256
     if not train:
-        return enc + llm
+        # the forward runs the last layer's out-projection / MLP on the 2 * R consumed rows only: credit what is done
+        skipped = (200 + 117 - 2 * R_RESP) * 2 * 3072 * (3072 + 2 * 8192 + 8192)
+        return enc + llm - skipped
     return 3 * enc + llm + 28 * per_tok * 200 + 2 * R_RESP * 3072 * 128256
 
 

@@ -260,7 +260,9 @@ typedef struct {
 size_t b2s_llama_workspace_bytes(const b2s_llama_weights* w, int32_t rows, int32_t logit_rows);
 /* LlamaModel.forward + lm_head over a packed batch of sequences (REF/model/audio_llama.py:49-67 over
  * TF/models/llama/modeling_llama.py:375-425), eval mode, causal per sequence.
- *   h: fp32 [rows, hidden] in: inputs_embeds (spliced); out: last layer's residual stream (pre final norm);
+ *   h: fp32 [rows, hidden] in: inputs_embeds (spliced); out: the residual stream after the last layer (pre final
+ *   norm) when all_hidden is requested or no / all logits are; otherwise the INPUT of the last layer (the rest of the
+ *   last layer then runs on the logit rows only, in the workspace);
  *   cu_seqlens int32 [num_seqs+1]; positions int32 [rows];
  *   logit_rows_index int32 [logit_rows]: rows whose logits are produced -> logits bf16 [logit_rows, vocab];
  *   fd taps (optional): for each t < num_taps, before layer tap_layers[t] runs, out

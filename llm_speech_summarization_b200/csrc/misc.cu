@@ -253,6 +253,28 @@ int mel_to_padded_cl(const float* x, void* y_bf16, int batches, int channels, in
   return B2S_OK;
 }
 
+// out[i, :] = src[index[i], :] for bf16 rows (C % 8 == 0): warp per row, 16-byte accesses
+__global__ void __launch_bounds__(256)
+gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ index,
+                        __nv_bfloat16* __restrict__ out, long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long i = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (i >= rows) return;
+  const long long s = index[i];
+  for (int k = lane * 8; k < C; k += 256)
+    *reinterpret_cast<uint4*>(out + i * C + k) = *reinterpret_cast<const uint4*>(src + s * C + k);
+}
+
+int gather_rows_bf16(const void* src, const int* index, void* out, long long rows, int C, cudaStream_t stream) {
+  B2S_REQUIRE(src && index && out, "gather_rows_bf16: null pointer");
+  B2S_REQUIRE(C % 8 == 0, "gather_rows_bf16: C must be a multiple of 8");
+  if (rows <= 0) return B2S_OK;
+  gather_rows_bf16_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), index, reinterpret_cast<__nv_bfloat16*>(out), rows, C);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
 int cast_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t stream) {
   if (n <= 0) return B2S_OK;
   B2S_REQUIRE(x && y, "cast_f32_to_bf16: null pointer");

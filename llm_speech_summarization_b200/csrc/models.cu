@@ -453,6 +453,9 @@ struct LlamaPlan {
   void* ao;   // bf16 [rows, Hq*D]
   void* act;  // bf16 [rows, F]
   void* xf;   // bf16 [logit_rows, H]
+  // last layer on the consumed rows only (see llama_prefill_kv)
+  float* hsel;  // fp32 [logit_rows, H]
+  void* aosel;  // bf16 [logit_rows, Hq*D]
   size_t bytes;
 };
 int plan_llama(const b2s_llama_weights* w, long long rows, long long logit_rows, void* ws, size_t ws_bytes,
@@ -464,6 +467,8 @@ int plan_llama(const b2s_llama_weights* w, long long rows, long long logit_rows,
   pl->ao = c.take(static_cast<size_t>(rows) * w->heads * w->head_dim * 2);
   pl->act = c.take(static_cast<size_t>(rows) * w->ffn * 2);
   pl->xf = c.take(static_cast<size_t>(logit_rows > 0 ? logit_rows : 1) * w->hidden * 2);
+  pl->hsel = reinterpret_cast<float*>(c.take(static_cast<size_t>(logit_rows > 0 ? logit_rows : 1) * w->hidden * 4));
+  pl->aosel = c.take(static_cast<size_t>(logit_rows > 0 ? logit_rows : 1) * w->heads * w->head_dim * 2);
   pl->bytes = c.off + 256;
   if (ws != nullptr && !c.ok()) {
     set_last_error("llama workspace too small: need %zu bytes, got %zu", pl->bytes, ws_bytes);
@@ -520,6 +525,11 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
 
   const size_t h_bytes = static_cast<size_t>(rows) * H * sizeof(float);
+  // Only the rows whose logits are requested leave the last layer (REF/model/audio_llama.py:67 computes all of them;
+  // the trainer reads the last R, REF/trainer.py:334,350-351, generate() the last one): after the last layer's
+  // attention -- which needs every row's K / V -- the out-projection, the MLP and the final norm run on those rows
+  // only. Not when the caller wants every hidden state. `h` then keeps the INPUT of the last layer on exit.
+  const bool last_on_selected = all_hidden == nullptr && logit_rows > 0 && logit_rows < rows;
   for (int l = 0; l < w->num_layers; ++l) {
     if (all_hidden != nullptr) {  // output_hidden_states: hidden_states[l] = input of layer l
       B2S_CUDA_CHECK(cudaMemcpyAsync(all_hidden + static_cast<size_t>(l) * rows * H, h, h_bytes,
@@ -554,18 +564,29 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
                          max_seqlen, rows, Hq, Hkv, D, scale, 1, nullptr, stream);
       if (rc != B2S_OK) return rc;
     }
+    const bool sel = last_on_selected && l == w->num_layers - 1;
+    const long long m = sel ? logit_rows : rows;  // rows that go through the rest of this layer
+    float* hs = sel ? pl.hsel : h;
+    const void* ao = pl.ao;
+    if (sel) {
+      rc = gather_rows_f32(h, logit_rows_index, pl.hsel, m, H, stream);
+      if (rc != B2S_OK) return rc;
+      rc = gather_rows_bf16(pl.ao, logit_rows_index, pl.aosel, m, Hq * D, stream);
+      if (rc != B2S_OK) return rc;
+      ao = pl.aosel;
+    }
     {
-      GemmArgs g = plain_gemm(pl.ao, L.wo, rows, H, Hq * D);
+      GemmArgs g = plain_gemm(ao, L.wo, m, H, Hq * D);
       g.epi = EPI_RESID_F32;
-      g.out = h;
-      g.resid = h;
+      g.out = hs;
+      g.resid = hs;
       rc = gemm_bf16_launch(g, stream);
       if (rc != B2S_OK) return rc;
     }
-    rc = rmsnorm_fwd(h, L.ln2_w, w->rms_eps, pl.xn, rows, H, stream);
+    rc = rmsnorm_fwd(hs, L.ln2_w, w->rms_eps, pl.xn, m, H, stream);
     if (rc != B2S_OK) return rc;
     {
-      GemmArgs g = plain_gemm(pl.xn, L.wgu, rows, 2 * F, H);
+      GemmArgs g = plain_gemm(pl.xn, L.wgu, m, 2 * F, H);
       g.epi = EPI_SWIGLU;
       g.out = pl.act;
       g.ldo = F;
@@ -573,10 +594,10 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
       if (rc != B2S_OK) return rc;
     }
     {
-      GemmArgs g = plain_gemm(pl.act, L.wd, rows, H, F);
+      GemmArgs g = plain_gemm(pl.act, L.wd, m, H, F);
       g.epi = EPI_RESID_F32;
-      g.out = h;
-      g.resid = h;
+      g.out = hs;
+      g.resid = hs;
       rc = gemm_bf16_launch(g, stream);
       if (rc != B2S_OK) return rc;
     }
@@ -595,7 +616,8 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
     if (rc != B2S_OK) return rc;
   }
   if (logit_rows > 0) {
-    rc = rmsnorm_gather_fwd(h, logit_rows_index, w->final_norm_w, w->rms_eps, pl.xf, logit_rows, H, stream);
+    if (last_on_selected) rc = rmsnorm_fwd(pl.hsel, w->final_norm_w, w->rms_eps, pl.xf, logit_rows, H, stream);
+    else rc = rmsnorm_gather_fwd(h, logit_rows_index, w->final_norm_w, w->rms_eps, pl.xf, logit_rows, H, stream);
     if (rc != B2S_OK) return rc;
     GemmArgs g = plain_gemm(pl.xf, w->lm_head, logit_rows, w->vocab, H);
     g.epi = EPI_BF16;

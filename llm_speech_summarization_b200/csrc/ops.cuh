@@ -49,6 +49,7 @@ int posconv_weight_pack(const float* g, const float* v, void* w_packed_bf16, int
                         cudaStream_t stream);
 // log-mel (B, C, T) fp32 -> channels-last bf16 (B, T+2, C), zero row before/after each utterance (conv padding)
 int mel_to_padded_cl(const float* x, void* y_bf16, int batches, int channels, int frames, cudaStream_t stream);
+int gather_rows_bf16(const void* src, const int* index, void* out, long long rows, int C, cudaStream_t stream);
 int cast_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t stream);
 int cast_bf16_to_f32(const void* x, float* y, long long n, cudaStream_t stream);
 // y_bf16 = gelu(x_f32 + residual) etc. are fused in GEMM epilogues; nothing else elementwise is needed.
