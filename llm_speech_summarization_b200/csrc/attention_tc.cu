@@ -127,6 +127,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   using C = AttnCfg<D, BN, KVS>;
   constexpr int kBN = BN;
   constexpr int kAtoms = D / 64;  // 64-element (128 B) column atoms per row
+  pdl_trigger();  // PDL: the out-projection GEMM that follows may take the SMs this grid frees (b2s_common.cuh)
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = ptx::smem_u32(smem_raw);

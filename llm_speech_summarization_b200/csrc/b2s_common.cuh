@@ -116,6 +116,13 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return (x >= 0.0f ? 1.0f - h : h) + x * 0.3989422804014327f * e;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may be
+// scheduled while its predecessor drains. pdl_trigger() at the top of a kernel lets such a successor's CTAs take the SMs
+// this grid frees in its tail (it is a no-op when the successor was launched normally); the successor calls pdl_wait()
+// before its first access to global memory, which blocks until the predecessor has completed and flushed.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // streaming 16-byte load that does not pollute L1
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
   uint4 r;

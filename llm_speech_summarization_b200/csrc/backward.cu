@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 rmsnorm_bwd_kernel(const float* __restrict__ x, const int* __restrict__ x_index, const float* __restrict__ w, float eps,
                    const float* __restrict__ dy, float* dh, const int* __restrict__ dh_index,
                    __nv_bfloat16* dh_bf16, long long rows) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   constexpr int C = GROUPS * 256;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float eps, const void* __restrict__ dy,
                      float* dh, int accumulate, __nv_bfloat16* dh_bf16, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, long long rows) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   constexpr int C = GROUPS * 256;
   __shared__ float s_dg[C], s_db[C];
   for (int i = threadIdx.x; i < C; i += blockDim.x) s_dg[i] = s_db[i] = 0.f;
@@ -137,6 +139,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 __global__ void __launch_bounds__(256)
 swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __nv_bfloat16* __restrict__ dact,
                   __nv_bfloat16* __restrict__ dgu, long long rows, int F) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // one 8-element vector of dact
   const long long per_row = F / 8;
   if (i >= rows * per_row) return;
@@ -163,6 +166,7 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __nv_bfloat16* __r
 __global__ void __launch_bounds__(256)
 gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dy,
                 __nv_bfloat16* __restrict__ dpre, long long n8, DropSpec drop) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   float x[8], d[8];
@@ -184,6 +188,7 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256)
 add_rowdiff_kernel(const float* __restrict__ h, const int* __restrict__ rows_a, const int* __restrict__ rows_b,
                    const float* __restrict__ coef, float* dh, __nv_bfloat16* dh_bf16, int pairs, int C) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= pairs) return;
@@ -208,6 +213,7 @@ add_rowdiff_kernel(const float* __restrict__ h, const int* __restrict__ rows_a, 
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ index, float* __restrict__ out, long long rows,
                    int C) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const int lane = threadIdx.x & 31;
   const long long i = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (i >= rows) return;

@@ -22,6 +22,7 @@ layernorm_bwd_ex_kernel(const void* __restrict__ x, int x_bf16, const float* __r
                         const float* __restrict__ beta, float eps, const void* __restrict__ dy, int dy_bf16, float* dh,
                         int accumulate, __nv_bfloat16* dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
                         long long rows) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   constexpr int C = GROUPS * 256;
   __shared__ float s_red[kWarps][C];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -110,6 +111,7 @@ layernorm_bwd_ex_kernel(const void* __restrict__ x, int x_bf16, const float* __r
 // out[c] += sum_r x[r, c]
 __global__ void __launch_bounds__(kWarps * 32)
 colsum_kernel(const void* __restrict__ x, int x_bf16, float* __restrict__ out, long long rows, int C) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   __shared__ float s_red[kWarps][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 256 + lane * 8;
@@ -136,6 +138,7 @@ colsum_kernel(const void* __restrict__ x, int x_bf16, float* __restrict__ out, l
 __global__ void __launch_bounds__(256)
 avgpool_bwd_kernel(const float* __restrict__ dp, float* __restrict__ dx, int frames, int C, int kernel, int stride,
                    int pooled, long long total4) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int c4 = C / 4;
@@ -159,6 +162,7 @@ avgpool_bwd_kernel(const float* __restrict__ dp, float* __restrict__ dx, int fra
 __global__ void __launch_bounds__(256)
 col2im_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, int tin, int tout, int k, int s,
               int C, long long total8) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const int c8 = C / 8;

@@ -296,6 +296,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
   const int cluster_id = blockIdx.x / CG;
   const int num_clusters = gridDim.x / CG;
+  // PDL (b2s_common.cuh): this grid may have been scheduled while its predecessor drains -- barrier init, TMEM
+  // allocation and the cluster handshakes below touch no global memory and overlap the predecessor's tail; every role
+  // passes pdl_wait() before its first global access. And a dependent GEMM may take the SMs this grid frees.
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -326,6 +330,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // the predecessor's writes (A operand, residual, the buffer this grid overwrites) are complete from here
 
   if (warp == 0 && lane == 0) {
     // ============================== TMA producer ==============================
@@ -658,13 +663,16 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const KParams& p, c
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static const int use_pdl = getenv("B2S_PDL") ? atoi(getenv("B2S_PDL")) : 1;  // B2S_PDL=0: plain serialization (A/B)
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = use_pdl ? 2 : 1;
   count_launch();
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (g_timing) {

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256)
 conv0_ln_gelu_kernel(const float* __restrict__ wave, long long wave_stride, int samples, const float* __restrict__ w,
                      const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
                      float eps, __nv_bfloat16* __restrict__ y, int out_frames) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   __shared__ float ws[kConv0K][kConv0Out];  // transposed taps: ws[j][c]
   for (int i = threadIdx.x; i < kConv0K * kConv0Out; i += blockDim.x) {
     const int c = i / kConv0K, j = i - c * kConv0K;
@@ -96,6 +97,7 @@ conv0_ln_gelu_kernel(const float* __restrict__ wave, long long wave_stride, int 
 __global__ void __launch_bounds__(256)
 embed_splice_kernel(const __nv_bfloat16* __restrict__ table, const float* __restrict__ audio,
                     const int* __restrict__ row_src, float* __restrict__ h0, long long rows, int C) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -169,6 +171,7 @@ posconv_weight_pack_kernel(const float* __restrict__ g, const float* __restrict_
 // (the zero padding of Whisper's conv1/conv2, TF/models/whisper/modeling_whisper.py:566-567)
 __global__ void mel_to_padded_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C,
                                         int T) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * (T + 2) * C;
   if (i >= total) return;
@@ -182,6 +185,7 @@ __global__ void mel_to_padded_cl_kernel(const float* __restrict__ x, __nv_bfloat
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(x + i);
@@ -257,6 +261,7 @@ int mel_to_padded_cl(const float* x, void* y_bf16, int batches, int channels, in
 __global__ void __launch_bounds__(256)
 gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ index,
                         __nv_bfloat16* __restrict__ out, long long rows, int C) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const int lane = threadIdx.x & 31;
   const long long i = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (i >= rows) return;

@@ -61,6 +61,7 @@ template <int GROUPS, bool IN_BF16, bool GELU>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, void* __restrict__ y, long long rows) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   constexpr int C = GROUPS * 256;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
@@ -86,6 +87,7 @@ template <int GROUPS, bool GATHER>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 rmsnorm_kernel(const float* __restrict__ x, const int* __restrict__ row_index, const float* __restrict__ w, float eps,
                void* __restrict__ y, long long rows) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   constexpr int C = GROUPS * 256;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 layernorm_avgpool_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                          float eps, void* __restrict__ y, int batches, int frames, int kernel, int stride,
                          int out_frames) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   constexpr int C = GROUPS * 256;
   const int lane = threadIdx.x & 31;
   const long long orow = static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);

@@ -12,6 +12,7 @@ namespace {
 // x (fp32 and / or bf16 copy of the same logical tensor) *= keep ? 1/(1-p) : 0, element index = linear index
 __global__ void __launch_bounds__(256)
 dropout_apply_kernel(float* __restrict__ xf, __nv_bfloat16* __restrict__ xb, long long n8, DropSpec d) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const uint32_t e0 = static_cast<uint32_t>(i * 8);
@@ -38,6 +39,7 @@ dropout_apply_kernel(float* __restrict__ xf, __nv_bfloat16* __restrict__ xb, lon
 __global__ void __launch_bounds__(256)
 mask_rows_kernel(float* __restrict__ h, const unsigned char* __restrict__ time_mask, const float* __restrict__ embed,
                  long long rows, int C) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows || time_mask[row] == 0) return;
@@ -50,6 +52,7 @@ mask_rows_kernel(float* __restrict__ h, const unsigned char* __restrict__ time_m
 __global__ void __launch_bounds__(256)
 featproj_reg_bwd_kernel(float* __restrict__ dh, const unsigned char* __restrict__ time_mask, float* __restrict__ g_embed,
                         long long rows, int C, DropSpec d) {
+  pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
