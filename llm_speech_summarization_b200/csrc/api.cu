@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/b2s.h"
 #include "b2s_common.cuh"
@@ -29,6 +30,11 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("B2S_PDL") && atoi(getenv("B2S_PDL")) == 0);
+  return on;
+}
 
 int num_sms() {
   static int sms = 0;

@@ -159,6 +159,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // launched with PDL: barriers / TMEM are set up while the QKV GEMM drains; its output is complete from here
 
   if (warp == 4) {
     if (lane == 0) {
@@ -474,7 +475,8 @@ int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, vo
   constexpr int ctas_per_sm = by_smem < by_tmem ? (by_smem < 1 ? 1 : by_smem) : by_tmem;
   const long long resident = static_cast<long long>(num_sms()) * ctas_per_sm;
   const unsigned grid = static_cast<unsigned>(total < resident ? total : resident);
-  kern<<<grid, kThreadsTc, C::kSmemBytes, stream>>>(tq, tk, tv, p);
+  rc = launch_pdl_kernel(kern, dim3(grid), dim3(kThreadsTc), C::kSmemBytes, stream, tq, tk, tv, p);
+  if (rc != B2S_OK) return rc;
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

@@ -43,6 +43,27 @@ long long launch_count();
 
 int num_sms();
 
+// Launch `kern` with the programmatic-stream-serialization attribute (PDL, see pdl_trigger / pdl_wait below): the grid
+// may be scheduled while its predecessor drains and must call pdl_wait() before its first global access.
+// B2S_PDL=0 in the environment falls back to plain stream serialisation (A/B runs).
+bool pdl_enabled();
+template <typename Kern, typename... Args>
+int launch_pdl_kernel(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx", __FILE__, __LINE__);
+  return B2S_OK;
+}
+
 // ---- device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

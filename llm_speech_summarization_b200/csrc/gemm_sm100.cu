@@ -670,9 +670,8 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const KParams& p, c
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  static const int use_pdl = getenv("B2S_PDL") ? atoi(getenv("B2S_PDL")) : 1;  // B2S_PDL=0: plain serialization (A/B)
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 2 : 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;  // B2S_PDL=0: plain stream serialisation (A/B runs)
   count_launch();
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (g_timing) {

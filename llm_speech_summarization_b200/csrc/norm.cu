@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, void* __restrict__ y, long long rows) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
+  pdl_wait();     // ... and this grid itself may have been launched early: the predecessor's rows are complete from here
   constexpr int C = GROUPS * 256;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 rmsnorm_kernel(const float* __restrict__ x, const int* __restrict__ row_index, const float* __restrict__ w, float eps,
                void* __restrict__ y, long long rows) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
+  pdl_wait();     // ... and this grid itself may have been launched early: the predecessor's rows are complete from here
   constexpr int C = GROUPS * 256;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
@@ -119,6 +121,7 @@ layernorm_avgpool_kernel(const float* __restrict__ x, const float* __restrict__ 
                          float eps, void* __restrict__ y, int batches, int frames, int kernel, int stride,
                          int out_frames) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
+  pdl_wait();     // ... and this grid itself may have been launched early: the predecessor's rows are complete from here
   constexpr int C = GROUPS * 256;
   const int lane = threadIdx.x & 31;
   const long long orow = static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
@@ -175,15 +178,17 @@ int layernorm_fwd(const void* x, int in_bf16, const float* gamma, const float* b
   B2S_REQUIRE(C > 0 && C % 256 == 0, "layernorm_fwd: C must be a multiple of 256");
   if (rows <= 0) return B2S_OK;
   const unsigned grid = static_cast<unsigned>((rows + kWarpsPerCta - 1) / kWarpsPerCta);
+  int rc_ = B2S_OK;
   B2S_DISPATCH_GROUPS(C, {
     if (in_bf16) {
-      if (act_gelu) layernorm_kernel<G, true, true><<<grid, kWarpsPerCta * 32, 0, stream>>>(x, gamma, beta, eps, y_bf16, rows);
-      else layernorm_kernel<G, true, false><<<grid, kWarpsPerCta * 32, 0, stream>>>(x, gamma, beta, eps, y_bf16, rows);
+      if (act_gelu) rc_ = launch_pdl_kernel(layernorm_kernel<G, true, true>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, gamma, beta, eps, y_bf16, rows);
+      else rc_ = launch_pdl_kernel(layernorm_kernel<G, true, false>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, gamma, beta, eps, y_bf16, rows);
     } else {
-      if (act_gelu) layernorm_kernel<G, false, true><<<grid, kWarpsPerCta * 32, 0, stream>>>(x, gamma, beta, eps, y_bf16, rows);
-      else layernorm_kernel<G, false, false><<<grid, kWarpsPerCta * 32, 0, stream>>>(x, gamma, beta, eps, y_bf16, rows);
+      if (act_gelu) rc_ = launch_pdl_kernel(layernorm_kernel<G, false, true>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, gamma, beta, eps, y_bf16, rows);
+      else rc_ = launch_pdl_kernel(layernorm_kernel<G, false, false>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, gamma, beta, eps, y_bf16, rows);
     }
   });
+  if (rc_ != B2S_OK) return rc_;
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -193,7 +198,11 @@ int rmsnorm_fwd(const float* x, const float* w, float eps, void* y_bf16, long lo
   B2S_REQUIRE(C > 0 && C % 256 == 0, "rmsnorm_fwd: C must be a multiple of 256");
   if (rows <= 0) return B2S_OK;
   const unsigned grid = static_cast<unsigned>((rows + kWarpsPerCta - 1) / kWarpsPerCta);
-  B2S_DISPATCH_GROUPS(C, (rmsnorm_kernel<G, false><<<grid, kWarpsPerCta * 32, 0, stream>>>(x, nullptr, w, eps, y_bf16, rows)));
+  int rc_ = B2S_OK;
+  const int* no_index = nullptr;
+  B2S_DISPATCH_GROUPS(C, (rc_ = launch_pdl_kernel(rmsnorm_kernel<G, false>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream,
+                                                  x, no_index, w, eps, y_bf16, rows)));
+  if (rc_ != B2S_OK) return rc_;
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -204,7 +213,10 @@ int rmsnorm_gather_fwd(const float* x, const int* row_index, const float* w, flo
   B2S_REQUIRE(C > 0 && C % 256 == 0, "rmsnorm_gather_fwd: C must be a multiple of 256");
   if (rows <= 0) return B2S_OK;
   const unsigned grid = static_cast<unsigned>((rows + kWarpsPerCta - 1) / kWarpsPerCta);
-  B2S_DISPATCH_GROUPS(C, (rmsnorm_kernel<G, true><<<grid, kWarpsPerCta * 32, 0, stream>>>(x, row_index, w, eps, y_bf16, rows)));
+  int rc_ = B2S_OK;
+  B2S_DISPATCH_GROUPS(C, (rc_ = launch_pdl_kernel(rmsnorm_kernel<G, true>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream,
+                                                  x, row_index, w, eps, y_bf16, rows)));
+  if (rc_ != B2S_OK) return rc_;
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
