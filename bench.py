@@ -441,7 +441,7 @@ def main():
     plan0 = plans[0]
     h2d = B * SAMPLES * 4 + 4 * (plan0.row_src.numel() + plan0.cu_seqlens.numel() + plan0.positions.numel() +
                                  plan0.logit_rows.numel() + plan0.labels.numel() + plan0.row_offsets.numel()) \
-        + 8 * plan0.seg.numel() + 4 * plan0.resp_len_f.numel()
+        + 4 * plan0.audio_rows.numel() + 4 * plan0.seg.numel() + 4 * plan0.resp_len_f.numel()
     d2h = 4 * 4 * B
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): per-launch CUDA events over instrumented steps

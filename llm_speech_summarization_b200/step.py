@@ -164,16 +164,32 @@ class AudioPromptStep:
         as_list = lambda xs: [x.tolist() if torch.is_tensor(x) else list(x) for x in xs]
         d = build_plan(self.prefix, self.suffix, n_audio, as_list(text_ids), as_list(resp_ids),
                        with_teacher=(self.use_ld or self.use_fd), audio_stride=audio_stride)
-        i32 = lambda x: torch.tensor(x, dtype=torch.int32).pin_memory().to(device, non_blocking=True)
-        return StepPlan(row_src=i32(d["row_src"]), cu_seqlens=i32(d["cu_seqlens"]), positions=i32(d["positions"]),
-                        logit_rows=i32(d["student_rows"] + d["teacher_rows"]), labels=i32(d["labels"]),
-                        row_offsets=i32(d["row_offsets"]), max_seqlen=d["max_seqlen"], rows=d["rows"],
-                        sum_r=d["sum_r"], resp_lens=d["resp_lens"], L_audio=d["L_audio"], L_text=d["L_text"],
-                        seg=torch.tensor([i for i, R in enumerate(d["resp_lens"]) for _ in range(R)],
-                                         dtype=torch.int64).pin_memory().to(device, non_blocking=True),
-                        resp_len_f=torch.tensor(d["resp_lens"], dtype=torch.float32).pin_memory().to(
-                            device, non_blocking=True),
-                        audio_rows=i32(d["audio_rows"]), student_rows_total=d["student_rows_total"])
+        # every index array of the plan travels in ONE pinned staging buffer and one H2D copy (each array starts on a
+        # 16-byte boundary); the fp32 response lengths ride along as raw bits
+        seg = [i for i, R in enumerate(d["resp_lens"]) for _ in range(R)]
+        parts = {"row_src": d["row_src"], "cu_seqlens": d["cu_seqlens"], "positions": d["positions"],
+                 "logit_rows": d["student_rows"] + d["teacher_rows"], "labels": d["labels"],
+                 "row_offsets": d["row_offsets"], "audio_rows": d["audio_rows"], "seg": seg}
+        offs, total = {}, 0
+        for k, v in parts.items():
+            offs[k] = total
+            total += (len(v) + 3) // 4 * 4
+        offs["resp_len_f"] = total
+        total += (len(d["resp_lens"]) + 3) // 4 * 4
+        host = torch.zeros(total, dtype=torch.int32).pin_memory()
+        for k, v in parts.items():
+            if v:
+                host[offs[k]:offs[k] + len(v)] = torch.tensor(v, dtype=torch.int32)
+        nB = len(d["resp_lens"])
+        host[offs["resp_len_f"]:offs["resp_len_f"] + nB] = torch.tensor(d["resp_lens"], dtype=torch.float32).view(torch.int32)
+        dev_buf = host.to(device, non_blocking=True)
+        i32 = lambda k: dev_buf[offs[k]:offs[k] + len(parts[k])]
+        return StepPlan(row_src=i32("row_src"), cu_seqlens=i32("cu_seqlens"), positions=i32("positions"),
+                        logit_rows=i32("logit_rows"), labels=i32("labels"), row_offsets=i32("row_offsets"),
+                        max_seqlen=d["max_seqlen"], rows=d["rows"], sum_r=d["sum_r"], resp_lens=d["resp_lens"],
+                        L_audio=d["L_audio"], L_text=d["L_text"], seg=i32("seg").to(torch.int64),
+                        resp_len_f=dev_buf[offs["resp_len_f"]:offs["resp_len_f"] + nB].view(torch.float32),
+                        audio_rows=i32("audio_rows"), student_rows_total=d["student_rows_total"])
 
     @torch.no_grad()
     def forward_losses(self, waves: torch.Tensor, text_ids, resp_ids, plan: Optional[StepPlan] = None,
