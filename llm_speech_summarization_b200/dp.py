@@ -10,7 +10,7 @@ sharding preserves when every rank scales by the GLOBAL window and gradients are
 from __future__ import annotations
 
 import os
-from typing import Iterable, List, Sequence
+from typing import Iterable, List
 
 import torch
 import torch.distributed as dist

@@ -11,7 +11,7 @@ There is no CPU path: forward() on a non-CUDA device raises.
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.nn as nn

@@ -6,7 +6,7 @@ restatement lives in oracle/ and is test infrastructure only).
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence
+from typing import Optional
 
 import torch
 

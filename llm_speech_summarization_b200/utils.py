@@ -7,7 +7,7 @@ log_softmax/softmax (REF/utils.py:167-178). Everything here needs CUDA tensors; 
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import List, Optional
 
 import torch
 
