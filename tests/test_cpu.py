@@ -500,3 +500,55 @@ def test_build_plan_ragged_audio_counts():
     assert u == build_plan(prefix, suffix, [2, 2], [[5, 6], [5]], [[0, 4, 4], [0, 4]], audio_stride=2)
     with pytest.raises(AssertionError):
         build_plan(prefix, suffix, [3, 1], [[5, 6], [5]], [[0, 4, 4], [0, 4]], audio_stride=2)
+
+
+def test_rng_header_host_functions_match_the_oracle_generator(tmp_path):
+    """csrc/rng.cuh is host + device code: compile its HOST side with nvcc (no GPU needed) and compare the mixer, the
+    stream keys, the threshold and keep/drop decisions with oracle/regularizers.py, the numpy restatement the
+    train-mode parity tests rely on."""
+    import shutil
+    import subprocess
+    import numpy as np
+    from oracle import regularizers as rg
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    src = tmp_path / "rng_host.cu"
+    src.write_text('''
+#include <cstdio>
+#include "%s/llm_speech_summarization_b200/csrc/rng.cuh"
+int main() {
+  using namespace b2s;
+  const unsigned long long seeds[3] = {1ull, 0x123456789ABCDEFull, (1ull << 61) + 12345ull};
+  for (auto seed : seeds) {
+    for (unsigned site : {1u, 2u, 16u, 19u, 111u}) {
+      unsigned k1, k2;
+      rng_stream_key(seed, site, 31u, 15u, &k1, &k2);
+      std::printf("K %%llu %%u %%u %%u\\n", seed, site, k1, k2);
+      const unsigned th = drop_threshold(0.1f);
+      for (unsigned e : {0u, 1u, 12345u, 0xFFFFFFFFu, (498u << 16) | 480u})
+        std::printf("E %%u %%u %%d\\n", e, rng_mix(e ^ k1, k2), rng_mix(e ^ k1, k2) >= th ? 1 : 0);
+    }
+  }
+  std::printf("T %%u %%u %%u\\n", drop_threshold(0.0f), drop_threshold(0.1f), drop_threshold(0.5f));
+  return 0;
+}
+''' % ROOT)
+    exe = tmp_path / "rng_host"
+    subprocess.run([nvcc, "-std=c++17", "-O1", "-o", str(exe), str(src)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()
+    k1 = k2 = seed = site = None
+    n_checked = 0
+    for line in out:
+        f = line.split()
+        if f[0] == "K":
+            seed, site, k1, k2 = int(f[1]), int(f[2]), int(f[3]), int(f[4])
+            assert rg.stream_key(seed, site, 31, 15) == (k1, k2), line
+        elif f[0] == "E":
+            e, h, keep = int(f[1]), int(f[2]), int(f[3])
+            assert int(rg.mix(np.uint64(e ^ k1), k2)) == h, line
+            assert bool(rg.keep(np.array([e], dtype=np.uint64), seed, site, 31, 15, 0.1)[0]) == bool(keep), line
+            n_checked += 1
+        elif f[0] == "T":
+            assert [int(x) for x in f[1:]] == [rg.threshold(0.0), rg.threshold(0.1), rg.threshold(0.5)]
+    assert n_checked == 75
