@@ -19,6 +19,9 @@ Parity pin: the reference has no tests, golden vectors or fixtures of its own (S
 is "outputs of the reference itself run here": oracle/make_golden.py imports the reference's modules from
 /root/reference (plus the installed transformers) in the build container, runs them on seeded tiny
 configurations, checks this restatement against them and commits the resulting vectors under tests/golden/.
-tests/test_oracle_golden.py re-checks the restatement against those vectors on every run (CPU, no reference
-needed); the `-m gpu` tests then compare the CUDA path with both.
+tests/test_cpu.py re-checks the restatement against those vectors on every run (CPU, no reference needed); the
+`-m gpu` tests then compare the CUDA path with both. The train-mode restatement (dropout sites, LayerDrop,
+SpecAugment under explicit masks, oracle/regularizers.py) is pinned the same way against the reference's AudioEncoder
+in .train() mode with HF's randomness replaced by the same masks (make_golden.py:run_train_mode_case ->
+tests/golden/tiny_hubert_train_mode.pt).
 """

@@ -4,8 +4,8 @@ TEST INFRASTRUCTURE (see oracle/__init__.py) -- checker and timed CPU baseline o
 
 REF/ = /root/reference, TF/ = the transformers package the reference delegates its arithmetic to
 (pinned 4.47.0, REF/requirements.txt:15). Every function names the lines it follows. Everything runs in the dtype
-of the tensors it is given (fp32 for the baseline, fp64 for tight checks), eval mode (no dropout / LayerDrop /
-SpecAugment).
+of the tensors it is given (fp32 for the baseline, fp64 for tight checks); eval mode by default, HF's train mode
+(dropout sites, LayerDrop, SpecAugment) when a `reg` block with explicit masks is passed to the HuBERT functions.
 """
 from __future__ import annotations
 
