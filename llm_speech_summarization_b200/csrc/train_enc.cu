@@ -24,6 +24,7 @@
 // layout (valid frames never read padded ones; the positional conv sees zeroed tail rows = its own zero padding),
 // the transformer stack runs on the PACKED valid rows with per-utterance cu_seqlens (attention is varlen already),
 // and two row gathers convert between the layouts. Every utterance gets exactly the numbers it would get alone.
+#include <cstring>
 #include <vector>
 
 namespace b2s {
@@ -136,6 +137,40 @@ int plan_ragged(const b2s_hubert_weights* w, int batches, int samples, const int
   r->rows_packed = r->cu[batches];
   return B2S_OK;
 }
+
+// Pinned staging for the ragged index arrays: cudaMemcpyAsync from pageable memory synchronises the stream before the
+// copy starts, which would stop the host from running ahead of the GPU. A small ring of pinned slots (one event each,
+// waited on before a slot is reused) keeps the upload asynchronous.
+class PinnedRing {
+ public:
+  // copies `bytes` from `src` into a pinned slot and enqueues the H2D copy to `dst`
+  int upload(void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+    Slot& sl = slots_[next_];
+    next_ = (next_ + 1) % kSlots;
+    if (sl.event != nullptr) B2S_CUDA_CHECK(cudaEventSynchronize(sl.event));
+    if (sl.cap < bytes) {
+      if (sl.ptr != nullptr) B2S_CUDA_CHECK(cudaFreeHost(sl.ptr));
+      sl.cap = (bytes + 65535) & ~static_cast<size_t>(65535);
+      B2S_CUDA_CHECK(cudaHostAlloc(&sl.ptr, sl.cap, cudaHostAllocDefault));
+    }
+    if (sl.event == nullptr) B2S_CUDA_CHECK(cudaEventCreateWithFlags(&sl.event, cudaEventDisableTiming));
+    memcpy(sl.ptr, src, bytes);
+    B2S_CUDA_CHECK(cudaMemcpyAsync(dst, sl.ptr, bytes, cudaMemcpyHostToDevice, stream));
+    B2S_CUDA_CHECK(cudaEventRecord(sl.event, stream));
+    return B2S_OK;
+  }
+
+ private:
+  static constexpr int kSlots = 16;
+  struct Slot {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    cudaEvent_t event = nullptr;
+  };
+  Slot slots_[kSlots];
+  int next_ = 0;
+};
+PinnedRing g_ring;  // one host thread per process drives the library (include/b2s.h: not thread-safe per handle)
 
 struct BwdWs {
   float *dh, *dxn_f, *dpool, *delta;
@@ -473,11 +508,10 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
   RC(plan_ragged(w, B, samples, samples_per_utt, s.frames, &rg));
   float* const h0 = rg.on ? s.hpad : s.h;  // padded-layout stream the front end writes
   if (rg.on) {
-    B2S_CUDA_CHECK(cudaMemcpyAsync(s.cu, rg.cu.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-    B2S_CUDA_CHECK(cudaMemcpyAsync(s.pack_idx, rg.pack.data(), rg.pack.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-    B2S_CUDA_CHECK(cudaMemcpyAsync(s.unpack_idx, rg.unpack.data(), rg.unpack.size() * sizeof(int), cudaMemcpyHostToDevice,
-                                   stream));
-    B2S_CUDA_CHECK(cudaMemcpyAsync(s.tail, rg.tail.data(), rg.tail.size(), cudaMemcpyHostToDevice, stream));
+    RC(g_ring.upload(s.cu, rg.cu.data(), (B + 1) * sizeof(int), stream));
+    RC(g_ring.upload(s.pack_idx, rg.pack.data(), rg.pack.size() * sizeof(int), stream));
+    RC(g_ring.upload(s.unpack_idx, rg.unpack.data(), rg.unpack.size() * sizeof(int), stream));
+    RC(g_ring.upload(s.tail, rg.tail.data(), rg.tail.size(), stream));
     B2S_CUDA_CHECK(cudaMemsetAsync(s.zeros_h, 0, static_cast<size_t>(H) * 4, stream));
   }
 
