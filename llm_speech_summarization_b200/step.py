@@ -101,6 +101,53 @@ def build_plan(prefix: Sequence[int], suffix: Sequence[int], n_audio, text_ids: 
                 student_rows_total=cu[B])
 
 
+def build_plan_arrays(prefix: Sequence[int], suffix: Sequence[int], n_audio, text_ids, resp_ids,
+                      with_teacher: bool = True, audio_stride: Optional[int] = None) -> Dict[str, object]:
+    """`build_plan` with numpy (same keys, int32 arrays instead of lists): what the step calls per micro-batch -- the
+    list version costs ~7 ms of Python per 32 utterances, this one well under 1 ms. Equality with `build_plan` is a
+    CPU unit test."""
+    import numpy as np
+    B = len(resp_ids)
+    n_each = [int(n_audio)] * B if isinstance(n_audio, int) else [int(n) for n in n_audio]
+    A = max(n_each) if audio_stride is None else int(audio_stride)
+    assert len(n_each) == B and max(n_each) <= A
+    i32 = lambda x: np.asarray(x, dtype=np.int32).reshape(-1)
+    pre, suf = i32(prefix), i32(suffix)[1:]
+    resp = [i32(r) for r in resp_ids]
+    text = [i32(t) for t in text_ids] if with_teacher else []
+    seqs = [np.concatenate([pre, -(i * A + np.arange(n_each[i], dtype=np.int32)) - 1, suf, resp[i][1:]]) for i in range(B)]
+    L_audio = [len(q) for q in seqs]
+    L_text = []
+    if with_teacher:
+        t_seqs = [np.concatenate([pre, text[i], suf, resp[i][1:]]) for i in range(B)]
+        L_text = [len(q) for q in t_seqs]
+        seqs = seqs + t_seqs
+    lens = np.asarray([len(q) for q in seqs], dtype=np.int64)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    row_src = np.concatenate(seqs).astype(np.int32)
+    positions = (np.arange(int(cu[-1]), dtype=np.int64) - np.repeat(cu[:-1].astype(np.int64), lens)).astype(np.int32)
+    resp_lens = [len(r) for r in resp]
+    for i in range(B):
+        if resp_lens[i] > L_audio[i]:
+            raise ValueError("response longer than its sequence")
+    R = np.asarray(resp_lens, dtype=np.int64)
+    within = np.arange(int(R.sum()), dtype=np.int64) - np.repeat(np.concatenate([[0], np.cumsum(R)[:-1]]), R)
+    s_rows = (np.repeat(cu[1:B + 1].astype(np.int64) - R, R) + within).astype(np.int32)
+    t_rows = ((np.repeat(cu[B + 1:2 * B + 1].astype(np.int64) - R, R) + within).astype(np.int32) if with_teacher
+              else np.zeros(0, dtype=np.int32))
+    labels = np.concatenate([np.concatenate([resp[i][1:], [-1]]) for i in range(B)]).astype(np.int32) if B else i32([])
+    offs = np.concatenate([[0], np.cumsum(R)]).astype(np.int32)
+    P = len(pre)
+    r_idx = np.arange(A, dtype=np.int64)[None, :]
+    audio_rows = np.where(r_idx < np.asarray(n_each, dtype=np.int64)[:, None],
+                          cu[:B].astype(np.int64)[:, None] + P + r_idx, -1).astype(np.int32).reshape(-1)
+    seg = np.repeat(np.arange(B, dtype=np.int32), R)
+    return dict(row_src=row_src, cu_seqlens=cu, positions=positions, student_rows=s_rows, teacher_rows=t_rows,
+                labels=labels, row_offsets=offs, max_seqlen=int(lens.max()), rows=int(cu[-1]), sum_r=int(R.sum()),
+                resp_lens=resp_lens, L_audio=L_audio, L_text=L_text, audio_rows=audio_rows,
+                student_rows_total=int(cu[B]), seg=seg)
+
+
 class PendingStep:
     """A submitted micro-batch (`AudioPromptStep.submit` / `EncoderTrainer.submit`): the per-utterance losses travel
     to pinned host memory asynchronously; `result()` waits for exactly that copy."""
@@ -161,27 +208,27 @@ class AudioPromptStep:
                    fd_loss_weight=t.fd_loss_weight, fd_loss_connector_layers=t.fd_loss_connector_layers)
 
     def plan(self, n_audio, text_ids, resp_ids, device, audio_stride: Optional[int] = None) -> StepPlan:
-        as_list = lambda xs: [x.tolist() if torch.is_tensor(x) else list(x) for x in xs]
-        d = build_plan(self.prefix, self.suffix, n_audio, as_list(text_ids), as_list(resp_ids),
-                       with_teacher=(self.use_ld or self.use_fd), audio_stride=audio_stride)
+        import numpy as np
+        as_np = lambda xs: [x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x) for x in xs]
+        d = build_plan_arrays(self.prefix, self.suffix, n_audio, as_np(text_ids), as_np(resp_ids),
+                              with_teacher=(self.use_ld or self.use_fd), audio_stride=audio_stride)
         # every index array of the plan travels in ONE pinned staging buffer and one H2D copy (each array starts on a
         # 16-byte boundary); the fp32 response lengths ride along as raw bits
-        seg = [i for i, R in enumerate(d["resp_lens"]) for _ in range(R)]
         parts = {"row_src": d["row_src"], "cu_seqlens": d["cu_seqlens"], "positions": d["positions"],
-                 "logit_rows": d["student_rows"] + d["teacher_rows"], "labels": d["labels"],
-                 "row_offsets": d["row_offsets"], "audio_rows": d["audio_rows"], "seg": seg}
+                 "logit_rows": np.concatenate([d["student_rows"], d["teacher_rows"]]), "labels": d["labels"],
+                 "row_offsets": d["row_offsets"], "audio_rows": d["audio_rows"], "seg": d["seg"]}
         offs, total = {}, 0
         for k, v in parts.items():
             offs[k] = total
             total += (len(v) + 3) // 4 * 4
         offs["resp_len_f"] = total
-        total += (len(d["resp_lens"]) + 3) // 4 * 4
-        host = torch.zeros(total, dtype=torch.int32).pin_memory()
-        for k, v in parts.items():
-            if v:
-                host[offs[k]:offs[k] + len(v)] = torch.tensor(v, dtype=torch.int32)
         nB = len(d["resp_lens"])
-        host[offs["resp_len_f"]:offs["resp_len_f"] + nB] = torch.tensor(d["resp_lens"], dtype=torch.float32).view(torch.int32)
+        total += (nB + 3) // 4 * 4
+        host = torch.zeros(total, dtype=torch.int32).pin_memory()
+        host_np = host.numpy()
+        for k, v in parts.items():
+            host_np[offs[k]:offs[k] + len(v)] = v
+        host_np[offs["resp_len_f"]:offs["resp_len_f"] + nB] = np.asarray(d["resp_lens"], dtype=np.float32).view(np.int32)
         dev_buf = host.to(device, non_blocking=True)
         i32 = lambda k: dev_buf[offs[k]:offs[k] + len(parts[k])]
         return StepPlan(row_src=i32("row_src"), cu_seqlens=i32("cu_seqlens"), positions=i32("positions"),

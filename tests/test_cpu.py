@@ -552,3 +552,34 @@ int main() {
         elif f[0] == "T":
             assert [int(x) for x in f[1:]] == [rg.threshold(0.0), rg.threshold(0.1), rg.threshold(0.5)]
     assert n_checked == 75
+
+
+def test_build_plan_arrays_equals_build_plan():
+    """The numpy plan builder the step uses per micro-batch == the pure-python reference construction, on random
+    ragged batches (with and without the teacher sequences, uniform and per-utterance audio counts)."""
+    import random
+    import numpy as np
+    from llm_speech_summarization_b200.step import build_plan, build_plan_arrays
+    rnd = random.Random(7)
+    for trial in range(40):
+        B = rnd.randint(1, 6)
+        prefix = [rnd.randrange(100) for _ in range(rnd.randint(1, 9))]
+        suffix = [rnd.randrange(100) for _ in range(rnd.randint(2, 6))]
+        text = [[rnd.randrange(1000) for _ in range(rnd.randint(1, 12))] for _ in range(B)]
+        resp = [[rnd.randrange(1000) for _ in range(rnd.randint(2, 9))] for _ in range(B)]
+        if trial % 2:
+            n_audio, stride = [rnd.randint(1, 7) for _ in range(B)], None
+            if trial % 4 == 1:
+                stride = max(n_audio) + 2
+        else:
+            n_audio, stride = rnd.randint(1, 7), None
+        for with_teacher in (True, False):
+            a = build_plan(prefix, suffix, n_audio, text, resp, with_teacher=with_teacher, audio_stride=stride)
+            b = build_plan_arrays(prefix, suffix, n_audio, [np.asarray(t) for t in text], [np.asarray(r) for r in resp],
+                                  with_teacher=with_teacher, audio_stride=stride)
+            for k, v in a.items():
+                got = b[k].tolist() if hasattr(b[k], "tolist") else b[k]
+                assert got == v, (trial, with_teacher, k)
+            assert b["seg"].tolist() == [i for i, r in enumerate(resp) for _ in r]
+    with pytest.raises(ValueError):
+        build_plan_arrays([], [2], 0, [np.asarray([4])], [np.asarray([5, 6, 7, 8, 9])], with_teacher=False)
