@@ -154,7 +154,7 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __nv_bfloat16* __r
   ld8bf(dact + row * F + col, da);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float sg = 1.0f / (1.0f + __expf(-g[j]));
+    const float sg = __fdividef(1.0f, 1.0f + __expf(-g[j]));
     dg[j] = da[j] * u[j] * sg * (1.0f + g[j] * (1.0f - sg));
     du[j] = da[j] * g[j] * sg;
   }
