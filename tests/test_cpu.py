@@ -583,3 +583,23 @@ def test_build_plan_arrays_equals_build_plan():
             assert b["seg"].tolist() == [i for i, r in enumerate(resp) for _ in r]
     with pytest.raises(ValueError):
         build_plan_arrays([], [2], 0, [np.asarray([4])], [np.asarray([5, 6, 7, 8, 9])], with_teacher=False)
+
+
+def test_bench_algorithmic_flops_match_the_survey_figures():
+    """bench.py's roofline numerator: SURVEY.md section 8d gives 384.6 GFLOP for the HuBERT-large forward (10 s) and
+    1184.7 + 712.3 GFLOP for the student + teacher prefill with the LM head on the consumed rows; the forward credits
+    what is computed (the last layer's out-projection / MLP run on the 2 * R consumed rows only)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    fwd, train = bench.gemm_flops_per_utt(False), bench.gemm_flops_per_utt(True)
+    skipped = (200 + 117 - 128) * 2 * 3072 * (3072 + 2 * 8192 + 8192)
+    # SURVEY counts attention (LLM: causal-halved; encoder: 4 * N^2 * H per layer) and conv layer 0 too, which are not
+    # launches of the GEMM kernel here
+    attn = 28 * 2 * 3072 * (200 ** 2 + 117 ** 2) + 24 * 4 * 499 ** 2 * 1024
+    conv0 = 2 * 512 * 10 * 31999
+    survey_total = (384.6 + 1184.7 + 712.3) * 1e9
+    assert abs((fwd + skipped + attn + conv0) - survey_total) / survey_total < 5e-3
+    assert abs(fwd / 1e9 - 2215.5) < 1.0
+    assert train > 2.5 * fwd * 0.6 and train < 3.0 * fwd
