@@ -147,6 +147,9 @@ def parse():
     ap.add_argument("--ragged", action="store_true",
                     help="train workload: utterance lengths drawn uniformly from [5 s, 10 s] (one ragged micro-batch "
                          "per step, zero-padded waveforms + lengths) instead of 10 s each")
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"],
+                    help="16-bit operand format of the encoder and the LLM (fp16 = the reference's autocast dtype and the "
+                         "default; bf16 = the round-1 path, for A/B)")
     ap.add_argument("--gemm-shapes", default="", help="write the per-shape GEMM table of the instrumented steps here")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts", type=int, default=3, help="utterances timed for the CPU baseline sample")
@@ -370,15 +373,18 @@ def main():
         print(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
 
     cfg = to_namespace({"model": {"audio_encoder": {"base": "hubert", "type": "facebook/hubert-large-ls960-ft",
+                                                    "random_init": True,  # no hub offline: synthetic weights below
                                                     "downsample_method": "pool", "downsample_factor": 4,
                                                     "pooling": {"kernel_size": 8, "stride": 4}},
                                   "llm_type": "meta-llama/Llama-3.2-3B-Instruct", "llm_embedding_channels": 3072}})
     la = KNOWN_LLMS[cfg.model.llm_type]
     enc_sd, llm_sd = synth_weights(dev)
+    op_dtype = torch.float16 if args.dtype == "fp16" else torch.bfloat16
     enc = AudioEncoder(cfg, dev)
+    enc.operand_dtype = op_dtype
     enc.load_state_dict(enc_sd, strict=True)
     enc.eval().to(dev)
-    llm = AudioLlamaForCausalLM(la)
+    llm = AudioLlamaForCausalLM(la, dtype=op_dtype)
     llm.load_state_dict(llm_sd, strict=True)
     llm.eval().to(dev)
     tok = FixedTokenizer(la.vocab, la.bos)
@@ -540,7 +546,7 @@ def main():
                  "+ AdamW, every step" if train else "forward only (encoder + student/teacher prefill + CE/KD/FD)")
         line = {"metric": METRIC_TRAIN if train else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": workload, "utterances_per_step_per_gpu": B, "parallelism": f"dp{world}",
                            "l2": "no flush needed: every step streams ~7 GB of weights and >2 GB of activations "
                                  "(>> 126 MB L2); two distinct micro-batches alternate",

@@ -33,6 +33,11 @@ typedef enum {
 /* epilogue ids of b2s_gemm_bf16 */
 enum { B2S_EPI_BF16 = 0, B2S_EPI_RESID_F32 = 1, B2S_EPI_SWIGLU = 2, B2S_EPI_ROPE = 3, B2S_EPI_F32 = 4 };
 enum { B2S_ACT_NONE = 0, B2S_ACT_GELU = 1 };
+/* 16-bit storage format of a tensor. Arithmetic is fp32 everywhere; the format only says how GEMM / attention operands
+ * are rounded when they are stored. The reference runs this path under fp16 autocast with an fp16 LLM
+ * (REF/trainer.py:57-61,270; REF/inference.py:97-99), so B2S_FMT_F16 is the default of the Python shim for weights and
+ * activations; gradients are always B2S_FMT_BF16 (fp16's range would need the reference's GradScaler). */
+enum { B2S_FMT_BF16 = 0, B2S_FMT_F16 = 1 };
 
 const char* b2s_last_error(void);
 int b2s_version(void);
@@ -79,6 +84,9 @@ typedef struct {
   int32_t b_tap_atoms;    /* grouped-conv wgrad: N atom j = W columns [g*w_group_off, +64) at rows k + j - a_pad */
   int32_t out_group_rows; /* output row offset per group */
   int32_t out_group_cols; /* output column offset per group (default N when out_group_rows == 0) */
+  /* 16-bit storage formats (B2S_FMT_*) of A, of W and of the 16-bit outputs (out / out2). A and W must agree (a mixed
+   * bf16 x fp16 tcgen05.mma traps on B200); the output format is free. */
+  int32_t a_fmt, w_fmt, out_fmt;
 } b2s_gemm_args;
 int b2s_gemm_bf16(const b2s_gemm_args* args, void* stream);
 /* measurement hook (bench.py roofline leg): while enabled, every GEMM launch is bracketed by CUDA events on its
@@ -101,50 +109,52 @@ int b2s_kd_ce_loss_fwd(const void* student, const void* teacher, int64_t lds, in
                        const int32_t* labels, const int32_t* row_offsets, int32_t utterances, float scale_kd,
                        float scale_ce, void* workspace, float* lse_s, float* lse_t, float* coef_kd, float* coef_ce,
                        float* loss_ld, float* loss_ntp, void* stream);
-/* d(sum_u scale_kd*ld_u + scale_ce*ntp_u)/d student, bf16 [rows, V]; the teacher gets no gradient
- * (.detach(), REF/trainer.py:351). */
+/* d(sum_u scale_kd*ld_u + scale_ce*ntp_u)/d student, 16-bit [rows, V] in format fmt, multiplied by *loss_scale (device
+ * scalar, may be NULL = 1: the GradScaler scale, REF/trainer.py:374); the teacher gets no gradient (.detach(),
+ * REF/trainer.py:351). The logits themselves are bf16. */
 int b2s_kd_ce_loss_bwd(const void* student, const void* teacher, int64_t lds, int64_t ldt, int32_t rows, int32_t V,
                        const int32_t* labels, const float* lse_s, const float* lse_t, const float* coef_kd,
-                       const float* coef_ce, void* d_student, int64_t ldd, void* stream);
+                       const float* coef_ce, const float* loss_scale, void* d_student, int64_t ldd, int32_t fmt,
+                       void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Normalisation family (TF/models/hubert/modeling_hubert.py:127-151,216-231,505-548,613;
  * TF/models/llama/modeling_llama.py:53-67; REF/model/audio_encoder.py:59-63). */
 int b2s_layernorm_fwd(const void* x, int32_t in_bf16, const float* gamma, const float* beta, float eps,
-                      int32_t act_gelu, void* y_bf16, int64_t rows, int32_t C, void* stream);
-int b2s_rmsnorm_fwd(const float* x, const float* w, float eps, void* y_bf16, int64_t rows, int32_t C, void* stream);
+                      int32_t act_gelu, void* y_bf16, int64_t rows, int32_t C, int32_t fmt, void* stream);
+int b2s_rmsnorm_fwd(const float* x, const float* w, float eps, void* y_bf16, int64_t rows, int32_t C, int32_t fmt, void* stream);
 int b2s_rmsnorm_gather_fwd(const float* x, const int32_t* row_index, const float* w, float eps, void* y_bf16,
-                           int64_t rows, int32_t C, void* stream);
+                           int64_t rows, int32_t C, int32_t fmt, void* stream);
 int b2s_layernorm_avgpool_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y_bf16,
                               int32_t batches, int32_t frames, int32_t C, int32_t kernel, int32_t stride,
-                              int32_t out_frames, void* stream);
+                              int32_t out_frames, int32_t fmt, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Remaining memory-bound ops. */
 /* HuBERT feature-extractor layer 0 (TF/models/hubert/modeling_hubert.py:127-151, layer_id 0) */
 int b2s_conv0_ln_gelu_fwd(const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, const float* w,
                           const float* bias, const float* gamma, const float* beta, float eps, void* y_bf16,
-                          int32_t out_frames, void* stream);
+                          int32_t out_frames, int32_t fmt, void* stream);
 /* embedding gather + audio splice (REF/utils.py:27-46,49-73,85-164; REF/inference.py:113-134):
  * h0[row] = row_src[row] >= 0 ? embed_tokens[row_src[row]] : audio_embeds[-(row_src[row]+1)];
  * row_src[row] == INT32_MIN writes a zero row (the reference's left padding). */
 int b2s_embed_splice_fwd(const void* embed_table_bf16, const float* audio_embeds, const int32_t* row_src, float* h0,
-                         int64_t rows, int32_t C, void* stream);
+                         int64_t rows, int32_t C, int32_t fmt, void* stream);
 /* per-row-pair sum of squared differences, the core of the FD MSE (REF/trainer.py:358-370) */
 int b2s_rowpair_sqdiff_fwd(const float* h, const int32_t* rows_a, const int32_t* rows_b, float* out, int32_t pairs,
                            int32_t C, void* stream);
 /* weight-norm(dim=2) + K-major repack of the positional conv weight (TF/models/hubert/modeling_hubert.py:45-92) */
 int b2s_posconv_weight_pack(const float* g, const float* v, void* w_packed_bf16, int32_t cout, int32_t cin_g,
-                            int32_t k, void* stream);
-int b2s_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
-int b2s_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
+                            int32_t k, int32_t fmt, void* stream);
+int b2s_cast_f32_to_h16(const float* x, void* y, int64_t n, int32_t fmt, void* stream);
+int b2s_cast_h16_to_f32(const void* x, float* y, int64_t n, int32_t fmt, void* stream);
 
 /* Packed varlen attention forward (TF/models/hubert/modeling_hubert.py:262-345;
  * TF/models/llama/modeling_llama.py:225-289). */
 int b2s_attention_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
                       const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int64_t total_rows, int32_t Hq,
                       int32_t Hkv, int32_t D, float scale, int32_t causal, float* lse /* optional [rows, Hq] */,
-                      void* stream);
+                      int32_t fmt, void* stream);
 /* Backward of b2s_attention_fwd (autograd through HubertAttention / LlamaAttention, REF/trainer.py:373-374).
  * lse: the forward's saved log-sum-exp; delta_ws: fp32 [rows, Hq] scratch; dq/dk/dv: bf16, row stride ld_dqkv;
  * rope_cs (optional): fuses the inverse rotary rotation into the dq / dk stores. */
@@ -152,10 +162,7 @@ int b2s_attention_bwd(const void* q, const void* k, const void* v, int64_t ld_qk
                       const void* dout, int64_t ld_do, const float* lse, float* delta_ws, void* dq, void* dk, void* dv,
                       int64_t ld_dqkv, const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen,
                       int64_t total_rows, int32_t Hq, int32_t Hkv, int32_t D, float scale, int32_t causal,
-                      const float* rope_cs, void* stream);
-/* kernel selection for A/B tests: 1 = tcgen05/TMEM/TMA flash attention (default), 0 = legacy mma.sync kernel */
-void b2s_attention_set_impl(int32_t impl);
-int b2s_attention_get_impl(void);
+                      const float* rope_cs, int32_t fmt, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Whole-model entry points (the layer loops run in C++, one call per forward). */
@@ -199,6 +206,8 @@ typedef struct {
   const void* proj_w; /* bf16 [llm_dim, H] */
   const float* proj_b;
   int32_t llm_dim;
+  int32_t fmt; /* B2S_FMT_*: format of every 16-bit weight above ("bf16" in the comments = "16-bit in fmt") and of every
+                  16-bit activation / gradient buffer the entry points taking this struct read or write */
 } b2s_hubert_weights;
 
 /* frames produced by the conv stack for `samples` input samples; pooled = AvgPool1d output length */
@@ -228,6 +237,7 @@ typedef struct {
   const void* proj_w;
   const float* proj_b;
   int32_t llm_dim;
+  int32_t fmt; /* B2S_FMT_*, as in b2s_hubert_weights */
 } b2s_whisper_weights;
 
 size_t b2s_whisper_workspace_bytes(const b2s_whisper_weights* w, int32_t batches);
@@ -255,6 +265,9 @@ typedef struct {
   const void* lm_head;   /* bf16 [vocab, H] */
   const float* rope_cs;  /* fp32 [max_pos, head_dim]: cos[0:D/2] | sin[0:D/2] */
   int32_t max_pos;
+  int32_t fmt; /* B2S_FMT_*: format of the weights, of the embedding table handed to decode, of the KV cache and of
+                  every 16-bit activation / gradient buffer (logits stay bf16: the fused loss reads them once, their
+                  2^-9 rounding is 1e-3 of the 2e-2 budget) */
 } b2s_llama_weights;
 
 size_t b2s_llama_workspace_bytes(const b2s_llama_weights* w, int32_t rows, int32_t logit_rows);
@@ -335,14 +348,15 @@ int b2s_llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* s
                             const int32_t* tap_rows_b, int32_t pairs, float* fd_sq, void* workspace,
                             size_t workspace_bytes, void* stream);
 /* Gradient w.r.t. the LLM input rows [0, rows_bwd) (the student sequences, packed first):
- *   d_logits bf16 [n_dl, vocab] for rows dl_rows_index; FD term: before layer l runs backward, rows tap_rows_a get
- *   tap_coef[i] * (h[l+1][a_i] - h[l+1][b_i]) for every tap layer l+1; dh fp32 [rows_bwd, H] = dL/d h[0]. */
+ *   d_logits 16-bit (w->fmt) [n_dl, vocab] for rows dl_rows_index; FD term: before layer l runs backward, rows
+ *   tap_rows_a get tap_coef[i] * (*loss_scale) * (h[l+1][a_i] - h[l+1][b_i]) for every tap layer l+1 (loss_scale: device
+ *   scalar or NULL = 1, the same one b2s_kd_ce_loss_bwd was given); dh fp32 [rows_bwd, H] = dL/d h[0] (scaled). */
 int b2s_llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt, const b2s_llama_saved* saved,
                        int32_t rows, int32_t rows_bwd, const int32_t* cu_seqlens, int32_t num_seqs_bwd,
                        int32_t max_seqlen, const void* d_logits, const int32_t* dl_rows_index, int32_t n_dl,
                        const int32_t* tap_layers /*host*/, int32_t num_taps, const int32_t* tap_rows_a,
-                       const int32_t* tap_rows_b, const float* tap_coef, int32_t pairs, float* dh, void* workspace,
-                       size_t workspace_bytes, void* stream);
+                       const int32_t* tap_rows_b, const float* tap_coef, const float* loss_scale, int32_t pairs,
+                       float* dh, void* workspace, size_t workspace_bytes, void* stream);
 /* ---- trainable HuBERT audio encoder (REF/trainer.py:98-105: every AudioEncoder parameter is optimised).
  * Gradient accumulators: fp32, zeroed by the caller, shaped like the packed tensors of b2s_hubert_weights
  * (conv_w[i] [512, k*512], wqkv [3H, H], pos_w [H][k][H/groups] = gradient w.r.t. the weight-normed effective
@@ -396,12 +410,16 @@ int b2s_drop_mask_dump(uint8_t* out, int64_t n, uint64_t seed, uint32_t site, ui
                        uint32_t e_first, void* stream);
 /* d_audio_embeds fp32 [batches*pooled, llm_dim] -> grads (+=). pos_w_dgrad: bf16 [H][k][H/groups], the packed
  * positional-conv weight with taps reversed and each (out, in) block transposed (the conv's transpose).
- * samples_per_utt: as given to the forward; the padding rows of d_audio_embeds must be zero. */
+ * samples_per_utt: as given to the forward; the padding rows of d_audio_embeds must be zero.
+ * layer_done_events (HOST array of num_layers cudaEvent_t, or NULL): event l is recorded on `stream` once every kernel
+ * that writes a gradient of transformer layer l has been enqueued (layers run last to first), so a communication
+ * stream can all-reduce layer l's gradients under the backward of layers l-1 ... 0. */
 int b2s_hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* grads,
                         const float* wave, int64_t wave_stride, int32_t batches, int32_t samples,
                         const int32_t* samples_per_utt, void* saved,
                         size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
-                        const b2s_encoder_regularizers* reg /* the block the forward ran with */, void* stream);
+                        const b2s_encoder_regularizers* reg /* the block the forward ran with */,
+                        void* const* layer_done_events, void* stream);
 /* Whisper encoder (REF/config/llama3_whisper.yaml trains it like the HuBERT one): same contract; mel fp32
  * [batches, mel_bins, 2*max_positions]; conv weights' gradients in the packed [H, 3*C_in] layout; the sinusoid table is
  * frozen; the k_proj slot of bqkv's gradient has no parameter behind it. */
@@ -416,30 +434,52 @@ int b2s_whisper_forward_train(const b2s_whisper_weights* w, const float* mel, in
                               void* saved, size_t saved_bytes, float* audio_embeds, void* stream);
 int b2s_whisper_backward(const b2s_whisper_weights* w, const b2s_whisper_grads* grads, int32_t batches, void* saved,
                          size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
-                         void* stream);
+                         void* const* layer_done_events, void* stream);
 /* memory-bound backward kernels of the encoder (see csrc/backward_enc.cu) */
 int b2s_layernorm_bwd_ex(const void* x, int32_t x_bf16, const float* gamma, const float* beta, int32_t act_gelu,
                          float eps, const void* dy, int32_t dy_bf16, float* dh, int32_t accumulate, void* dx_bf16,
-                         float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream);
-int b2s_colsum_accum(const void* x, int32_t x_bf16, float* out, int64_t rows, int32_t C, void* stream);
+                         float* dgamma, float* dbeta, int64_t rows, int32_t C, int32_t fmt, void* stream);
+int b2s_colsum_accum(const void* x, int32_t x_bf16, float* out, int64_t rows, int32_t C, int32_t fmt, void* stream);
 int b2s_avgpool_bwd(const float* dpooled, float* dx, int32_t batches, int32_t frames, int32_t C, int32_t kernel,
                     int32_t stride, int32_t pooled, void* stream);
 int b2s_col2im_add(const void* dcol_bf16, void* dx_bf16, int32_t batches, int32_t tin, int32_t tout, int32_t k,
-                   int32_t s, int32_t C, void* stream);
+                   int32_t s, int32_t C, int32_t fmt, void* stream);
 int b2s_conv0_bwd(const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, const float* w,
                   const float* bias, const float* gamma, const float* beta, float eps, const void* dy_bf16,
-                  int32_t frames, float* dW, float* db, float* dgamma, float* dbeta, void* stream);
+                  int32_t frames, float* dW, float* db, float* dgamma, float* dbeta, int32_t fmt, void* stream);
 int b2s_rmsnorm_bwd(const float* x, const int32_t* x_index, const float* w, float eps, const float* dy, float* dh,
-                    const int32_t* dh_index, void* dh_bf16, int64_t rows, int32_t C, void* stream);
+                    const int32_t* dh_index, void* dh_bf16, int64_t rows, int32_t C, int32_t fmt, void* stream);
 int b2s_layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int32_t dy_bf16, float* dh,
                       int32_t accumulate, void* dh_bf16, float* dgamma, float* dbeta, int64_t rows, int32_t C,
-                      void* stream);
-int b2s_swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t rows, int32_t F, void* stream);
-int b2s_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, void* stream);
+                      int32_t fmt, void* stream);
+int b2s_swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t rows, int32_t F, int32_t fmt, void* stream);
+int b2s_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, int32_t fmt, void* stream);
 int b2s_gather_rows_f32(const float* src, const int32_t* index, float* out, int64_t rows, int32_t C, void* stream);
-/* torch.optim.AdamW step on one flat fp32 tensor (REF/trainer.py:98-105,381); grad_scale multiplies the gradient. */
+/* Dynamic loss scaling, torch.cuda.amp.GradScaler semantics (REF/trainer.py:252,374,381-382), with its state in DEVICE
+ * memory so that neither the skip-on-overflow decision nor the scale update synchronises the host:
+ *   forward/backward: the loss gradient is multiplied by state->scale where it enters the backward pass
+ *                     (b2s_kd_ce_loss_bwd / b2s_llama_backward take &state->scale);
+ *   optimizer step  : b2s_nonfinite_check(flat gradient) -> b2s_adamw_step(..., state) -> b2s_grad_scaler_update. */
+typedef struct {
+  float scale;            /* current loss scale (GradScaler init_scale = 65536) */
+  int32_t growth_tracker; /* clean optimizer steps since the last scale change */
+  int32_t found_inf;      /* set by b2s_nonfinite_check, cleared by b2s_grad_scaler_update */
+  int32_t opt_steps;      /* optimizer steps actually taken (AdamW bias-correction step) */
+  int32_t skipped_steps;  /* steps skipped on overflow */
+  int32_t reserved[3];
+} b2s_grad_scaler_state;
+/* state->found_inf |= (any element of g is inf / nan); g: 16-byte aligned, n % 4 == 0 */
+int b2s_nonfinite_check(const float* g, int64_t n, b2s_grad_scaler_state* state, void* stream);
+/* GradScaler.update(): on overflow scale *= backoff_factor (and the step counts as skipped), else after growth_interval
+ * consecutive clean steps scale *= growth_factor; clears found_inf */
+int b2s_grad_scaler_update(b2s_grad_scaler_state* state, float growth_factor, float backoff_factor,
+                           int32_t growth_interval, void* stream);
+/* torch.optim.AdamW step on one flat fp32 tensor (REF/trainer.py:98-105,381); grad_scale multiplies the gradient.
+ * scaler (device, may be NULL): the gradient is additionally divided by scaler->scale, the whole step is a no-op when
+ * scaler->found_inf is set (GradScaler.step), and the bias corrections use scaler->opt_steps + 1 instead of `step`. */
 int b2s_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                   float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+                   float eps, float weight_decay, int32_t step, float grad_scale, const b2s_grad_scaler_state* scaler,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ class GemmArgs(C.Structure):
         ("rope_cols", c_int), ("resid_bcast", c_int), ("out2", c_void_p), ("ld2", c_int64), ("block_n", c_int),
         ("cta_group", c_int), ("a_mn", c_int), ("b_mn", c_int), ("k_batches", c_int), ("w_row_stride", c_int64),
         ("w_batch_stride", c_int64), ("k_splits", c_int), ("b_tap_atoms", c_int), ("out_group_rows", c_int),
-        ("out_group_cols", c_int),
+        ("out_group_cols", c_int), ("a_fmt", c_int), ("w_fmt", c_int), ("out_fmt", c_int),
     ]
 
 
@@ -46,7 +46,7 @@ class HubertWeights(C.Structure):
         ("layers", C.POINTER(EncoderLayer)), ("num_layers", c_int), ("hidden", c_int), ("heads", c_int),
         ("ffn", c_int), ("final_ln_g", c_void_p), ("final_ln_b", c_void_p), ("ln_eps", c_float),
         ("pool_kernel", c_int), ("pool_stride", c_int), ("proj_w", c_void_p), ("proj_b", c_void_p),
-        ("llm_dim", c_int),
+        ("llm_dim", c_int), ("fmt", c_int),
     ]
 
 
@@ -84,7 +84,7 @@ class WhisperWeights(C.Structure):
         ("heads", c_int), ("ffn", c_int), ("mel_bins", c_int), ("max_positions", c_int),
         ("final_ln_g", c_void_p), ("final_ln_b", c_void_p), ("ln_eps", c_float),
         ("pool_kernel", c_int), ("pool_stride", c_int), ("proj_w", c_void_p), ("proj_b", c_void_p),
-        ("llm_dim", c_int),
+        ("llm_dim", c_int), ("fmt", c_int),
     ]
 
 
@@ -97,6 +97,7 @@ class LlamaWeights(C.Structure):
         ("layers", C.POINTER(LlamaLayer)), ("num_layers", c_int), ("hidden", c_int), ("heads", c_int),
         ("kv_heads", c_int), ("head_dim", c_int), ("ffn", c_int), ("vocab", c_int), ("rms_eps", c_float),
         ("final_norm_w", c_void_p), ("lm_head", c_void_p), ("rope_cs", c_void_p), ("max_pos", c_int),
+        ("fmt", c_int),
     ]
 
 
@@ -106,6 +107,12 @@ class LlamaLayerT(C.Structure):
 
 class LlamaWeightsT(C.Structure):
     _fields_ = [("layers", C.POINTER(LlamaLayerT)), ("lm_head_t", c_void_p)]
+
+
+class GradScalerState(C.Structure):
+    """b2s_grad_scaler_state (device memory; this mirror is for sizing and for reading it back)."""
+    _fields_ = [("scale", c_float), ("growth_tracker", c_int), ("found_inf", c_int), ("opt_steps", c_int),
+                ("skipped_steps", c_int), ("reserved", c_int * 3)]
 
 
 class LlamaSaved(C.Structure):
@@ -125,26 +132,24 @@ PROTOTYPES = {
     "b2s_kd_ce_loss_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, P_int, P_int, c_int, c_float,
                                    c_float, c_void_p, P_f32, P_f32, P_f32, P_f32, P_f32, P_f32, c_void_p]),
     "b2s_kd_ce_loss_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, P_int, P_f32, P_f32, P_f32,
-                                   P_f32, c_void_p, c_int64, c_void_p]),
-    "b2s_layernorm_fwd": (c_int, [c_void_p, c_int, P_f32, P_f32, c_float, c_int, c_void_p, c_int64, c_int, c_void_p]),
-    "b2s_rmsnorm_fwd": (c_int, [P_f32, P_f32, c_float, c_void_p, c_int64, c_int, c_void_p]),
-    "b2s_rmsnorm_gather_fwd": (c_int, [P_f32, P_int, P_f32, c_float, c_void_p, c_int64, c_int, c_void_p]),
+                                   P_f32, P_f32, c_void_p, c_int64, c_int, c_void_p]),
+    "b2s_layernorm_fwd": (c_int, [c_void_p, c_int, P_f32, P_f32, c_float, c_int, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "b2s_rmsnorm_fwd": (c_int, [P_f32, P_f32, c_float, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "b2s_rmsnorm_gather_fwd": (c_int, [P_f32, P_int, P_f32, c_float, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "b2s_layernorm_avgpool_fwd": (c_int, [P_f32, P_f32, P_f32, c_float, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                          c_int, c_void_p]),
+                                          c_int, c_int, c_void_p]),
     "b2s_conv0_ln_gelu_fwd": (c_int, [P_f32, c_int64, c_int, c_int, P_f32, P_f32, P_f32, P_f32, c_float, c_void_p,
-                                      c_int, c_void_p]),
-    "b2s_embed_splice_fwd": (c_int, [c_void_p, P_f32, P_int, P_f32, c_int64, c_int, c_void_p]),
+                                      c_int, c_int, c_void_p]),
+    "b2s_embed_splice_fwd": (c_int, [c_void_p, P_f32, P_int, P_f32, c_int64, c_int, c_int, c_void_p]),
     "b2s_rowpair_sqdiff_fwd": (c_int, [P_f32, P_int, P_int, P_f32, c_int, c_int, c_void_p]),
-    "b2s_posconv_weight_pack": (c_int, [P_f32, P_f32, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "b2s_cast_f32_to_bf16": (c_int, [P_f32, c_void_p, c_int64, c_void_p]),
-    "b2s_cast_bf16_to_f32": (c_int, [c_void_p, P_f32, c_int64, c_void_p]),
+    "b2s_posconv_weight_pack": (c_int, [P_f32, P_f32, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "b2s_cast_f32_to_h16": (c_int, [P_f32, c_void_p, c_int64, c_int, c_void_p]),
+    "b2s_cast_h16_to_f32": (c_int, [c_void_p, P_f32, c_int64, c_int, c_void_p]),
     "b2s_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, P_int, c_int, c_int,
-                                  c_int64, c_int, c_int, c_int, c_float, c_int, P_f32, c_void_p]),
+                                  c_int64, c_int, c_int, c_int, c_float, c_int, P_f32, c_int, c_void_p]),
     "b2s_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, P_f32,
                                   P_f32, c_void_p, c_void_p, c_void_p, c_int64, P_int, c_int, c_int, c_int64, c_int,
-                                  c_int, c_int, c_float, c_int, P_f32, c_void_p]),
-    "b2s_attention_set_impl": (None, [c_int]),
-    "b2s_attention_get_impl": (c_int, []),
+                                  c_int, c_int, c_float, c_int, P_f32, c_int, c_void_p]),
     "b2s_hubert_num_frames": (c_int, [C.POINTER(HubertWeights), c_int, C.POINTER(c_int), C.POINTER(c_int)]),
     "b2s_hubert_workspace_bytes": (c_size_t, [C.POINTER(HubertWeights), c_int, c_int]),
     "b2s_hubert_forward": (c_int, [C.POINTER(HubertWeights), P_f32, c_int64, c_int, c_int, c_void_p, c_size_t, P_f32,
@@ -163,13 +168,13 @@ PROTOTYPES = {
                                         P_f32, c_void_p, c_size_t, c_void_p]),
     "b2s_llama_backward": (c_int, [C.POINTER(LlamaWeights), C.POINTER(LlamaWeightsT), C.POINTER(LlamaSaved), c_int,
                                    c_int, P_int, c_int, c_int, c_void_p, P_int, c_int, C.POINTER(c_int), c_int, P_int,
-                                   P_int, P_f32, c_int, P_f32, c_void_p, c_size_t, c_void_p]),
+                                   P_int, P_f32, P_f32, c_int, P_f32, c_void_p, c_size_t, c_void_p]),
     "b2s_rmsnorm_bwd": (c_int, [P_f32, P_int, P_f32, c_float, P_f32, P_f32, P_int, c_void_p, c_int64, c_int,
-                                c_void_p]),
+                                c_int, c_void_p]),
     "b2s_layernorm_bwd": (c_int, [P_f32, P_f32, c_float, c_void_p, c_int, P_f32, c_int, c_void_p, P_f32, P_f32,
-                                  c_int64, c_int, c_void_p]),
-    "b2s_swiglu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
-    "b2s_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+                                  c_int64, c_int, c_int, c_void_p]),
+    "b2s_swiglu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "b2s_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "b2s_gather_rows_f32": (c_int, [P_f32, P_int, P_f32, c_int64, c_int, c_void_p]),
     "b2s_whisper_log_mel": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b2s_llama_kv_cache_bytes": (C.c_size_t, [C.POINTER(LlamaWeights), c_int]),
@@ -186,7 +191,7 @@ PROTOTYPES = {
                                          C.POINTER(EncoderRegularizers), c_void_p]),
     "b2s_hubert_backward": (c_int, [C.POINTER(HubertWeights), c_void_p, C.POINTER(HubertGrads), c_void_p, c_int64,
                                     c_int, c_int, C.POINTER(C.c_int32), c_void_p, C.c_size_t, c_void_p, c_void_p,
-                                    C.c_size_t, C.POINTER(EncoderRegularizers), c_void_p]),
+                                    C.c_size_t, C.POINTER(EncoderRegularizers), C.POINTER(c_void_p), c_void_p]),
     "b2s_drop_mask_dump": (c_int, [c_void_p, c_int64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, c_float,
                                    C.c_uint32, c_void_p]),
     "b2s_whisper_saved_bytes": (C.c_size_t, [C.POINTER(WhisperWeights), c_int]),
@@ -194,16 +199,18 @@ PROTOTYPES = {
     "b2s_whisper_forward_train": (c_int, [C.POINTER(WhisperWeights), c_void_p, c_int, c_int, c_void_p, C.c_size_t,
                                           c_void_p, c_void_p]),
     "b2s_whisper_backward": (c_int, [C.POINTER(WhisperWeights), C.POINTER(WhisperGrads), c_int, c_void_p, C.c_size_t,
-                                     c_void_p, c_void_p, C.c_size_t, c_void_p]),
+                                     c_void_p, c_void_p, C.c_size_t, C.POINTER(c_void_p), c_void_p]),
     "b2s_layernorm_bwd_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p,
-                                     c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
-    "b2s_colsum_accum": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p]),
+                                     c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "b2s_colsum_accum": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "b2s_avgpool_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "b2s_col2im_add": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b2s_col2im_add": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b2s_conv0_bwd": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
-                              c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                              c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "b2s_adamw_step": (c_int, [P_f32, P_f32, P_f32, P_f32, c_int64, c_float, c_float, c_float, c_float, c_float,
-                               c_int, c_float, c_void_p]),
+                               c_int, c_float, c_void_p, c_void_p]),
+    "b2s_nonfinite_check": (c_int, [P_f32, c_int64, c_void_p, c_void_p]),
+    "b2s_grad_scaler_update": (c_int, [c_void_p, c_float, c_float, c_int, c_void_p]),
 }
 
 _lib = None

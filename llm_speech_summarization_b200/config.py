@@ -31,10 +31,31 @@ def to_namespace(obj):
     return obj
 
 
+def _yaml_loader():
+    """SafeLoader with YAML 1.2 float resolution: PyYAML (YAML 1.1) reads `lr: 5e-5` -- the spelling of every shipped
+    reference yaml (REF/config/*.yaml, train.optimizer.lr) -- as the STRING '5e-5' because it has no dot; OmegaConf, which
+    the reference uses (REF/train.py:21), reads a float."""
+    import re
+    import yaml
+
+    class Loader(yaml.SafeLoader):
+        pass
+
+    Loader.add_implicit_resolver(
+        "tag:yaml.org,2002:float",
+        re.compile(r"""^(?:[-+]?(?:[0-9][0-9_]*)\.[0-9_]*(?:[eE][-+]?[0-9]+)?
+                       |[-+]?(?:[0-9][0-9_]*)(?:[eE][-+]?[0-9]+)
+                       |\.[0-9_]+(?:[eE][-+]?[0-9]+)?
+                       |[-+]?\.(?:inf|Inf|INF)
+                       |\.(?:nan|NaN|NAN))$""", re.X),
+        list("-+0123456789."))
+    return Loader
+
+
 def load_config(path: str) -> Namespace:
     import yaml
     with open(path) as f:
-        return to_namespace(yaml.safe_load(f))
+        return to_namespace(yaml.load(f, Loader=_yaml_loader()))
 
 
 @dataclass

@@ -70,7 +70,7 @@ int whisper_forward_train(const b2s_whisper_weights* w, const float* mel, int ba
                           size_t saved_bytes, float* audio_embeds, cudaStream_t stream);
 int whisper_backward(const b2s_whisper_weights* w, const b2s_whisper_grads* gr, int batches, void* saved,
                      size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
-                     cudaStream_t stream);
+                     void* const* layer_done, cudaStream_t stream);
 size_t llama_kv_cache_bytes(const b2s_llama_weights* w, int slots);
 int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* cu_seqlens, int num_seqs,
                      int max_seqlen, const int* positions, const int* logit_rows_index, int logit_rows,
@@ -89,7 +89,7 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
 int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* gr, const float* wave,
                     long long wave_stride, int batches, int samples, const int* samples_per_utt, void* saved,
                     size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
-                    const b2s_encoder_regularizers* reg, cudaStream_t stream);
+                    const b2s_encoder_regularizers* reg, void* const* layer_done, cudaStream_t stream);
 size_t llama_backward_workspace_bytes(const b2s_llama_weights* w, int rows_bwd, int n_dl);
 int llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* sv, int rows, const int* cu_seqlens,
                         int num_seqs, int max_seqlen, const int* positions, const int* logit_rows_index,
@@ -99,8 +99,8 @@ int llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* sv, i
 int llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt, const b2s_llama_saved* sv, int rows,
                    int rows_bwd, const int* cu_seqlens, int num_seqs_bwd, int max_seqlen, const void* d_logits,
                    const int* dl_rows_index, int n_dl, const int* tap_layers, int num_taps, const int* tap_rows_a,
-                   const int* tap_rows_b, const float* tap_coef, int pairs, float* dh, void* workspace,
-                   size_t workspace_bytes, cudaStream_t stream);
+                   const int* tap_rows_b, const float* tap_coef, const float* loss_scale, int pairs, float* dh,
+                   void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 }  // namespace b2s
 
@@ -161,6 +161,9 @@ int b2s_gemm_bf16(const b2s_gemm_args* a, void* stream) {
   g.b_tap_atoms = a->b_tap_atoms;
   g.out_group_rows = a->out_group_rows;
   g.out_group_cols = a->out_group_cols;
+  g.a_fmt = a->a_fmt;
+  g.w_fmt = a->w_fmt;
+  g.out_fmt = a->out_fmt;
   return gemm_bf16_launch(g, S(stream));
 }
 
@@ -180,67 +183,66 @@ int b2s_kd_ce_loss_fwd(const void* student, const void* teacher, int64_t lds, in
 
 int b2s_kd_ce_loss_bwd(const void* student, const void* teacher, int64_t lds, int64_t ldt, int32_t rows, int32_t V,
                        const int32_t* labels, const float* lse_s, const float* lse_t, const float* coef_kd,
-                       const float* coef_ce, void* d_student, int64_t ldd, void* stream) {
-  return kd_ce_loss_bwd(student, teacher, lds, ldt, rows, V, labels, lse_s, lse_t, coef_kd, coef_ce, d_student, ldd,
-                        S(stream));
+                       const float* coef_ce, const float* loss_scale, void* d_student, int64_t ldd, int32_t fmt,
+                       void* stream) {
+  return kd_ce_loss_bwd(student, teacher, lds, ldt, rows, V, labels, lse_s, lse_t, coef_kd, coef_ce, loss_scale,
+                        d_student, ldd, fmt, S(stream));
 }
 
 int b2s_layernorm_fwd(const void* x, int32_t in_bf16, const float* gamma, const float* beta, float eps,
-                      int32_t act_gelu, void* y_bf16, int64_t rows, int32_t C, void* stream) {
-  return layernorm_fwd(x, in_bf16, gamma, beta, eps, act_gelu, y_bf16, rows, C, S(stream));
+                      int32_t act_gelu, void* y_bf16, int64_t rows, int32_t C, int32_t fmt, void* stream) {
+  return layernorm_fwd(x, in_bf16, gamma, beta, eps, act_gelu, y_bf16, rows, C, fmt, S(stream));
 }
-int b2s_rmsnorm_fwd(const float* x, const float* w, float eps, void* y_bf16, int64_t rows, int32_t C, void* stream) {
-  return rmsnorm_fwd(x, w, eps, y_bf16, rows, C, S(stream));
+int b2s_rmsnorm_fwd(const float* x, const float* w, float eps, void* y_bf16, int64_t rows, int32_t C, int32_t fmt, void* stream) {
+  return rmsnorm_fwd(x, w, eps, y_bf16, rows, C, fmt, S(stream));
 }
 int b2s_rmsnorm_gather_fwd(const float* x, const int32_t* row_index, const float* w, float eps, void* y_bf16,
-                           int64_t rows, int32_t C, void* stream) {
-  return rmsnorm_gather_fwd(x, row_index, w, eps, y_bf16, rows, C, S(stream));
+                           int64_t rows, int32_t C, int32_t fmt, void* stream) {
+  return rmsnorm_gather_fwd(x, row_index, w, eps, y_bf16, rows, C, fmt, S(stream));
 }
 int b2s_layernorm_avgpool_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y_bf16,
                               int32_t batches, int32_t frames, int32_t C, int32_t kernel, int32_t stride,
-                              int32_t out_frames, void* stream) {
-  return layernorm_avgpool_fwd(x, gamma, beta, eps, y_bf16, batches, frames, C, kernel, stride, out_frames, S(stream));
+                              int32_t out_frames, int32_t fmt, void* stream) {
+  return layernorm_avgpool_fwd(x, gamma, beta, eps, y_bf16, batches, frames, C, kernel, stride, out_frames, fmt, S(stream));
 }
 int b2s_conv0_ln_gelu_fwd(const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, const float* w,
                           const float* bias, const float* gamma, const float* beta, float eps, void* y_bf16,
-                          int32_t out_frames, void* stream) {
+                          int32_t out_frames, int32_t fmt, void* stream) {
   return conv0_ln_gelu_fwd(wave, wave_stride, batches, samples, w, bias, gamma, beta, eps, y_bf16, out_frames,
-                           S(stream));
+                           fmt, S(stream));
 }
 int b2s_embed_splice_fwd(const void* embed_table_bf16, const float* audio_embeds, const int32_t* row_src, float* h0,
-                         int64_t rows, int32_t C, void* stream) {
-  return embed_splice_fwd(embed_table_bf16, audio_embeds, row_src, h0, rows, C, S(stream));
+                         int64_t rows, int32_t C, int32_t fmt, void* stream) {
+  return embed_splice_fwd(embed_table_bf16, audio_embeds, row_src, h0, rows, C, fmt, S(stream));
 }
 int b2s_rowpair_sqdiff_fwd(const float* h, const int32_t* rows_a, const int32_t* rows_b, float* out, int32_t pairs,
                            int32_t C, void* stream) {
   return rowpair_sqdiff_fwd(h, rows_a, rows_b, out, pairs, C, S(stream));
 }
 int b2s_posconv_weight_pack(const float* g, const float* v, void* w_packed_bf16, int32_t cout, int32_t cin_g,
-                            int32_t k, void* stream) {
-  return posconv_weight_pack(g, v, w_packed_bf16, cout, cin_g, k, S(stream));
+                            int32_t k, int32_t fmt, void* stream) {
+  return posconv_weight_pack(g, v, w_packed_bf16, cout, cin_g, k, fmt, S(stream));
 }
-int b2s_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
-  return cast_f32_to_bf16(x, y, n, S(stream));
+int b2s_cast_f32_to_h16(const float* x, void* y, int64_t n, int32_t fmt, void* stream) {
+  return cast_f32_to_h16(x, y, n, fmt, S(stream));
 }
-int b2s_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
-  return cast_bf16_to_f32(x, y, n, S(stream));
+int b2s_cast_h16_to_f32(const void* x, float* y, int64_t n, int32_t fmt, void* stream) {
+  return cast_h16_to_f32(x, y, n, fmt, S(stream));
 }
 int b2s_attention_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
                       const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int64_t total_rows, int32_t Hq,
-                      int32_t Hkv, int32_t D, float scale, int32_t causal, float* lse, void* stream) {
+                      int32_t Hkv, int32_t D, float scale, int32_t causal, float* lse, int32_t fmt, void* stream) {
   return attention_fwd(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, D, scale,
-                       causal, lse, S(stream));
+                       causal, lse, fmt, S(stream));
 }
 int b2s_attention_bwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const void* o, int64_t ld_o,
                       const void* dout, int64_t ld_do, const float* lse, float* delta_ws, void* dq, void* dk, void* dv,
                       int64_t ld_dqkv, const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen,
                       int64_t total_rows, int32_t Hq, int32_t Hkv, int32_t D, float scale, int32_t causal,
-                      const float* rope_cs, void* stream) {
+                      const float* rope_cs, int32_t fmt, void* stream) {
   return attention_bwd(q, k, v, ld_qkv, o, ld_o, dout, ld_do, lse, delta_ws, dq, dk, dv, ld_dqkv, cu_seqlens, num_seqs,
-                       max_seqlen, total_rows, Hq, Hkv, D, scale, causal, rope_cs, S(stream));
+                       max_seqlen, total_rows, Hq, Hkv, D, scale, causal, rope_cs, fmt, S(stream));
 }
-void b2s_attention_set_impl(int32_t impl) { attention_set_impl(impl); }
-int b2s_attention_get_impl(void) { return attention_get_impl(); }
 
 int b2s_hubert_num_frames(const b2s_hubert_weights* w, int32_t samples, int32_t* frames, int32_t* pooled) {
   return hubert_num_frames(w, samples, frames, pooled);
@@ -296,34 +298,45 @@ int b2s_llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt
                        int32_t rows, int32_t rows_bwd, const int32_t* cu_seqlens, int32_t num_seqs_bwd,
                        int32_t max_seqlen, const void* d_logits, const int32_t* dl_rows_index, int32_t n_dl,
                        const int32_t* tap_layers, int32_t num_taps, const int32_t* tap_rows_a,
-                       const int32_t* tap_rows_b, const float* tap_coef, int32_t pairs, float* dh, void* workspace,
-                       size_t workspace_bytes, void* stream) {
+                       const int32_t* tap_rows_b, const float* tap_coef, const float* loss_scale, int32_t pairs,
+                       float* dh, void* workspace, size_t workspace_bytes, void* stream) {
   return llama_backward(w, wt, saved, rows, rows_bwd, cu_seqlens, num_seqs_bwd, max_seqlen, d_logits, dl_rows_index,
-                        n_dl, tap_layers, num_taps, tap_rows_a, tap_rows_b, tap_coef, pairs, dh, workspace,
+                        n_dl, tap_layers, num_taps, tap_rows_a, tap_rows_b, tap_coef, loss_scale, pairs, dh, workspace,
                         workspace_bytes, S(stream));
 }
 int b2s_rmsnorm_bwd(const float* x, const int32_t* x_index, const float* w, float eps, const float* dy, float* dh,
-                    const int32_t* dh_index, void* dh_bf16, int64_t rows, int32_t C, void* stream) {
-  return rmsnorm_bwd(x, x_index, w, eps, dy, dh, dh_index, dh_bf16, rows, C, S(stream));
+                    const int32_t* dh_index, void* dh_bf16, int64_t rows, int32_t C, int32_t fmt, void* stream) {
+  return rmsnorm_bwd(x, x_index, w, eps, dy, dh, dh_index, dh_bf16, rows, C, fmt, S(stream));
 }
 int b2s_layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int32_t dy_bf16, float* dh,
                       int32_t accumulate, void* dh_bf16, float* dgamma, float* dbeta, int64_t rows, int32_t C,
-                      void* stream) {
-  return layernorm_bwd(x, gamma, eps, dy, dy_bf16, dh, accumulate, dh_bf16, dgamma, dbeta, rows, C, S(stream));
+                      int32_t fmt, void* stream) {
+  return layernorm_bwd(x, gamma, eps, dy, dy_bf16, dh, accumulate, dh_bf16, dgamma, dbeta, rows, C, fmt, S(stream));
 }
-int b2s_swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t rows, int32_t F, void* stream) {
-  return swiglu_bwd(gu, dact, dgu, rows, F, S(stream));
+int b2s_swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t rows, int32_t F, int32_t fmt, void* stream) {
+  return swiglu_bwd(gu, dact, dgu, rows, F, fmt, S(stream));
 }
-int b2s_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, void* stream) {
-  return gelu_bwd(pre, dy, dpre, n, S(stream));
+int b2s_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, int32_t fmt, void* stream) {
+  return gelu_bwd(pre, dy, dpre, n, fmt, S(stream));
 }
 int b2s_gather_rows_f32(const float* src, const int32_t* index, float* out, int64_t rows, int32_t C, void* stream) {
   return gather_rows_f32(src, index, out, rows, C, S(stream));
 }
 int b2s_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                   float eps, float weight_decay, int32_t step, float grad_scale, void* stream) {
-  return adamw_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
+                   float eps, float weight_decay, int32_t step, float grad_scale, const b2s_grad_scaler_state* scaler,
+                   void* stream) {
+  return adamw_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                    reinterpret_cast<const GradScalerState*>(scaler), S(stream));
 }
+int b2s_nonfinite_check(const float* g, int64_t n, b2s_grad_scaler_state* scaler, void* stream) {
+  return nonfinite_check(g, n, reinterpret_cast<GradScalerState*>(scaler), S(stream));
+}
+int b2s_grad_scaler_update(b2s_grad_scaler_state* scaler, float growth_factor, float backoff_factor,
+                           int32_t growth_interval, void* stream) {
+  return grad_scaler_update(reinterpret_cast<GradScalerState*>(scaler), growth_factor, backoff_factor, growth_interval,
+                            S(stream));
+}
+static_assert(sizeof(b2s_grad_scaler_state) == sizeof(GradScalerState), "scaler state layouts must match");
 
 size_t b2s_hubert_saved_bytes(const b2s_hubert_weights* w, int32_t batches, int32_t samples) {
   return hubert_saved_bytes(w, batches, samples);
@@ -340,9 +353,10 @@ int b2s_hubert_forward_train(const b2s_hubert_weights* w, const float* wave, int
 int b2s_hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* grads,
                         const float* wave, int64_t wave_stride, int32_t batches, int32_t samples,
                         const int32_t* samples_per_utt, void* saved, size_t saved_bytes, const float* d_audio_embeds,
-                        void* workspace, size_t workspace_bytes, const b2s_encoder_regularizers* reg, void* stream) {
+                        void* workspace, size_t workspace_bytes, const b2s_encoder_regularizers* reg,
+                        void* const* layer_done_events, void* stream) {
   return hubert_backward(w, pos_w_dgrad, grads, wave, wave_stride, batches, samples, samples_per_utt, saved, saved_bytes,
-                         d_audio_embeds, workspace, workspace_bytes, reg, S(stream));
+                         d_audio_embeds, workspace, workspace_bytes, reg, layer_done_events, S(stream));
 }
 int b2s_drop_mask_dump(uint8_t* out, int64_t n, uint64_t seed, uint32_t site, uint32_t a, uint32_t b, float p,
                        uint32_t e_first, void* stream) {
@@ -350,26 +364,26 @@ int b2s_drop_mask_dump(uint8_t* out, int64_t n, uint64_t seed, uint32_t site, ui
 }
 int b2s_layernorm_bwd_ex(const void* x, int32_t x_bf16, const float* gamma, const float* beta, int32_t act_gelu,
                          float eps, const void* dy, int32_t dy_bf16, float* dh, int32_t accumulate, void* dx_bf16,
-                         float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream) {
+                         float* dgamma, float* dbeta, int64_t rows, int32_t C, int32_t fmt, void* stream) {
   return layernorm_bwd_ex(x, x_bf16, gamma, beta, act_gelu, eps, dy, dy_bf16, dh, accumulate, dx_bf16, dgamma, dbeta,
-                          rows, C, S(stream));
+                          rows, C, fmt, S(stream));
 }
-int b2s_colsum_accum(const void* x, int32_t x_bf16, float* out, int64_t rows, int32_t C, void* stream) {
-  return colsum_accum(x, x_bf16, out, rows, C, S(stream));
+int b2s_colsum_accum(const void* x, int32_t x_bf16, float* out, int64_t rows, int32_t C, int32_t fmt, void* stream) {
+  return colsum_accum(x, x_bf16, out, rows, C, fmt, S(stream));
 }
 int b2s_avgpool_bwd(const float* dpooled, float* dx, int32_t batches, int32_t frames, int32_t C, int32_t kernel,
                     int32_t stride, int32_t pooled, void* stream) {
   return avgpool_bwd(dpooled, dx, batches, frames, C, kernel, stride, pooled, S(stream));
 }
 int b2s_col2im_add(const void* dcol_bf16, void* dx_bf16, int32_t batches, int32_t tin, int32_t tout, int32_t k,
-                   int32_t s, int32_t C, void* stream) {
-  return col2im_add(dcol_bf16, dx_bf16, batches, tin, tout, k, s, C, S(stream));
+                   int32_t s, int32_t C, int32_t fmt, void* stream) {
+  return col2im_add(dcol_bf16, dx_bf16, batches, tin, tout, k, s, C, fmt, S(stream));
 }
 int b2s_conv0_bwd(const float* wave, int64_t wave_stride, int32_t batches, int32_t samples, const float* w,
                   const float* bias, const float* gamma, const float* beta, float eps, const void* dy_bf16,
-                  int32_t frames, float* dW, float* db, float* dgamma, float* dbeta, void* stream) {
+                  int32_t frames, float* dW, float* db, float* dgamma, float* dbeta, int32_t fmt, void* stream) {
   return conv0_bwd(wave, wave_stride, batches, samples, w, bias, gamma, beta, eps, dy_bf16, frames, dW, db, dgamma,
-                   dbeta, S(stream));
+                   dbeta, fmt, S(stream));
 }
 
 size_t b2s_llama_kv_cache_bytes(const b2s_llama_weights* w, int32_t slots) { return llama_kv_cache_bytes(w, slots); }
@@ -408,8 +422,9 @@ int b2s_whisper_forward_train(const b2s_whisper_weights* w, const float* mel, in
 }
 int b2s_whisper_backward(const b2s_whisper_weights* w, const b2s_whisper_grads* grads, int32_t batches, void* saved,
                          size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
-                         void* stream) {
-  return whisper_backward(w, grads, batches, saved, saved_bytes, d_audio_embeds, workspace, workspace_bytes, S(stream));
+                         void* const* layer_done_events, void* stream) {
+  return whisper_backward(w, grads, batches, saved, saved_bytes, d_audio_embeds, workspace, workspace_bytes,
+                          layer_done_events, S(stream));
 }
 
 }  // extern "C"

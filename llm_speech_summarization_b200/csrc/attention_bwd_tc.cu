@@ -1,7 +1,9 @@
 // attention_bwd_tc.cu -- flash-attention backward on tcgen05 / TMEM / TMA (sm_100a), the training counterpart of
-// attention_tc.cu. Same decomposition as the mma.sync kernels in attention_bwd.cu (delta kernel + a dQ kernel over
-// query tiles + a dK/dV kernel over key tiles, scores recomputed from the saved log-sum-exp), but every matmul is a
-// tcgen05.mma with its accumulator in TMEM and its operands in 128B-swizzled shared memory:
+// attention_tc.cu: a delta kernel (rowsum(dO o O)) + a dQ kernel over query tiles + a dK/dV kernel over key tiles, scores
+// recomputed from the saved log-sum-exp; every matmul is a tcgen05.mma with its accumulator in TMEM and its operands in
+// 128B-swizzled shared memory. All 16-bit tensors share ONE format (template F16): tcgen05 kind::f16 rejects mixed
+// bf16 / fp16 operands (measured: illegal instruction), so fp16 activations mean fp16 gradients (loss-scaled by the
+// caller, as the reference's GradScaler does).
 //
 //   dQ kernel  (CTA = sequence x query head x 128 queries; keys in blocks of 64)
 //       S  = Q K^T, dP = dO V^T            A = Q / dO (K-major), B = K / V (K-major)      TMEM [0,64) / [64,128)
@@ -45,6 +47,11 @@ struct BwdTcParams {
   AttnDrop drop;         // attention-probability dropout of the forward (thresh 0 = off), regenerated here
 };
 
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_op(float lo, float hi) {
+  return F16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
+}
+
 __device__ __forceinline__ float ex2b(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -64,8 +71,8 @@ __device__ __forceinline__ void st_row_chunk(uint32_t tile, int r, int c, const 
   }
 }
 
-// TMEM accumulator row (D fp32) -> optional RoPE^T -> bf16 -> global row
-template <int D>
+// TMEM accumulator row (D fp32) -> optional RoPE^T -> 16-bit (bf16 / fp16) -> global row
+template <int D, bool F16>
 __device__ __forceinline__ void store_acc_row(uint32_t taddr, __nv_bfloat16* dst, bool valid, float mul,
                                               const float* rope_row /* [D] cos|sin or null */) {
   if (rope_row != nullptr && D == 128) {
@@ -92,8 +99,8 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, __nv_bfloat16* dst
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          st8bf(dst + c * 32 + q * 8, *reinterpret_cast<const float(*)[8]>(&a[q * 8]));
-          st8bf(dst + 64 + c * 32 + q * 8, *reinterpret_cast<const float(*)[8]>(&b[q * 8]));
+          st8h(dst + c * 32 + q * 8, *reinterpret_cast<const float(*)[8]>(&a[q * 8]), F16);
+          st8h(dst + 64 + c * 32 + q * 8, *reinterpret_cast<const float(*)[8]>(&b[q * 8]), F16);
         }
       }
     }
@@ -109,7 +116,7 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, __nv_bfloat16* dst
 #pragma unroll
       for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(raw[i]) * mul;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) st8bf(dst + c * 32 + q * 8, *reinterpret_cast<const float(*)[8]>(&a[q * 8]));
+      for (int q = 0; q < 4; ++q) st8h(dst + c * 32 + q * 8, *reinterpret_cast<const float(*)[8]>(&a[q * 8]), F16);
     }
   }
 }
@@ -128,7 +135,7 @@ struct DqCfg {
 // ------------------------------------------------------------------------------------------------ dQ
 // With dropout O = (P o M) V, M = keep / (1 - p): dP = M o (dO V^T), dV = (P o M)^T dO, and delta = rowsum(dO o O) is
 // unchanged (sum_j P_j M_j (dO . V_j) = dO . O), so only the two elementwise stages below see the mask.
-template <int D, bool DROP>
+template <int D, bool DROP, bool F16>
 __global__ void __launch_bounds__(kThreadsB, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                       const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
@@ -198,8 +205,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
       };
       load_kv(0);
-      constexpr uint32_t idesc_s = ptx::make_idesc_bf16_f32(kBig, kSmall);
-      constexpr uint32_t idesc_o = ptx::make_idesc_bf16_f32(kBig, D) | (1u << 16);  // B (= K) read MN-major
+      constexpr uint32_t idesc_s = ptx::make_idesc_f32acc(kBig, kSmall) | ptx::idesc_formats(F16, F16);
+      constexpr uint32_t idesc_o =
+          ptx::make_idesc_f32acc(kBig, D) | ptx::idesc_formats(F16, F16) | (1u << 16);  // B (= K) read MN-major
       ptx::mbar_wait(bar_q, 0);
       for (int j = 0; j < nblk; ++j) {
         const int st = j % kStages;
@@ -280,7 +288,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           for (int i = 0; i < 32; i += 2) {
             const float p0 = ex2b(fmaf(__uint_as_float(rs[i]), sc2, -lse));
             const float p1 = ex2b(fmaf(__uint_as_float(rs[i + 1]), sc2, -lse));
-            pk[i >> 1] = pack_bf16(p0 * fmaf(__uint_as_float(rd[i]), sc, -dls),
+            pk[i >> 1] = pack_op<F16>(p0 * fmaf(__uint_as_float(rd[i]), sc, -dls),
                                    p1 * fmaf(__uint_as_float(rd[i + 1]), sc, -dls));
           }
         } else {
@@ -288,7 +296,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           for (int i = 0; i < 32; i += 2) {
             const float p0 = (i < nv) ? ex2b(fmaf(__uint_as_float(rs[i]), sc2, -lse)) : 0.f;
             const float p1 = (i + 1 < nv) ? ex2b(fmaf(__uint_as_float(rs[i + 1]), sc2, -lse)) : 0.f;
-            pk[i >> 1] = pack_bf16(p0 * fmaf(__uint_as_float(rd[i]), sc, -dls),
+            pk[i >> 1] = pack_op<F16>(p0 * fmaf(__uint_as_float(rd[i]), sc, -dls),
                                    p1 * fmaf(__uint_as_float(rd[i + 1]), sc, -dls));
           }
         }
@@ -301,7 +309,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     ptx::mbar_wait(bar_o, (nblk - 1) & 1);
     ptx::tc_fence_after();
     const float* rope_row = p.rope_cs != nullptr ? p.rope_cs + static_cast<long long>(valid ? qi : 0) * D : nullptr;
-    store_acc_row<D>(tDQ, p.dq + grow * p.ld_d + h * D, valid, 1.0f, rope_row);
+    store_acc_row<D, F16>(tDQ, p.dq + grow * p.ld_d + h * D, valid, 1.0f, rope_row);
   }
 
   ptx::tc_fence_before();
@@ -323,7 +331,7 @@ struct DkvCfg {
   static constexpr int kTmemCols = (D == 64) ? 256 : 512;  // S^T [0,64) dP^T [64,128) dV [128,128+D) dK [128+D,128+2D)
 };
 
-template <int D, bool DROP>
+template <int D, bool DROP, bool F16>
 __global__ void __launch_bounds__(kThreadsB, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                        const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
@@ -399,8 +407,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         }
       };
       load_q(0);
-      constexpr uint32_t idesc_s = ptx::make_idesc_bf16_f32(kBig, kSmall);
-      constexpr uint32_t idesc_o = ptx::make_idesc_bf16_f32(kBig, D) | (1u << 16);
+      constexpr uint32_t idesc_s = ptx::make_idesc_f32acc(kBig, kSmall) | ptx::idesc_formats(F16, F16);
+      constexpr uint32_t idesc_o = ptx::make_idesc_f32acc(kBig, D) | ptx::idesc_formats(F16, F16) | (1u << 16);
       ptx::mbar_wait(bar_kv, 0);
       for (int it = 0; it < iters; ++it) {
         const int st = it % kStages;
@@ -492,8 +500,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             const float2 ds = *reinterpret_cast<const float2*>(st_dl + c * 32 + i);   // delta * scale
             const float p0 = ex2b(fmaf(__uint_as_float(rs[i]), sc2, -nl.x));
             const float p1 = ex2b(fmaf(__uint_as_float(rs[i + 1]), sc2, -nl.y));
-            pp[i >> 1] = DROP ? pack_bf16(p0 * mk[i], p1 * mk[i + 1]) : pack_bf16(p0, p1);
-            pd[i >> 1] = pack_bf16(p0 * fmaf(__uint_as_float(rd[i]), sc, -ds.x),
+            pp[i >> 1] = DROP ? pack_op<F16>(p0 * mk[i], p1 * mk[i + 1]) : pack_op<F16>(p0, p1);
+            pd[i >> 1] = pack_op<F16>(p0 * fmaf(__uint_as_float(rd[i]), sc, -ds.x),
                                    p1 * fmaf(__uint_as_float(rd[i + 1]), sc, -ds.y));
           }
         } else {
@@ -506,8 +514,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             const float2 ds = *reinterpret_cast<const float2*>(st_dl + c * 32 + i);
             const float p0 = ok0 ? ex2b(fmaf(__uint_as_float(rs[i]), sc2, -nl.x)) : 0.f;
             const float p1 = ok1 ? ex2b(fmaf(__uint_as_float(rs[i + 1]), sc2, -nl.y)) : 0.f;
-            pp[i >> 1] = DROP ? pack_bf16(p0 * mk[i], p1 * mk[i + 1]) : pack_bf16(p0, p1);
-            pd[i >> 1] = pack_bf16(p0 * fmaf(__uint_as_float(rd[i]), sc, -ds.x),
+            pp[i >> 1] = DROP ? pack_op<F16>(p0 * mk[i], p1 * mk[i + 1]) : pack_op<F16>(p0, p1);
+            pd[i >> 1] = pack_op<F16>(p0 * fmaf(__uint_as_float(rd[i]), sc, -ds.x),
                                    p1 * fmaf(__uint_as_float(rd[i + 1]), sc, -ds.y));
           }
         }
@@ -521,9 +529,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     ptx::mbar_wait(bar_o, (iters - 1) & 1);
     ptx::tc_fence_after();
     const long long grow = static_cast<long long>(s0 + key);
-    store_acc_row<D>(tS + 2 * kSmall, p.dv + grow * p.ld_d + hk * D, kvalid, 1.0f, nullptr);
+    store_acc_row<D, F16>(tS + 2 * kSmall, p.dv + grow * p.ld_d + hk * D, kvalid, 1.0f, nullptr);
     const float* rope_row = p.rope_cs != nullptr ? p.rope_cs + static_cast<long long>(kvalid ? key : 0) * D : nullptr;
-    store_acc_row<D>(tS + 2 * kSmall + D, p.dk + grow * p.ld_d + hk * D, kvalid, 1.0f, rope_row);
+    store_acc_row<D, F16>(tS + 2 * kSmall + D, p.dk + grow * p.ld_d + hk * D, kvalid, 1.0f, rope_row);
   }
 
   ptx::tc_fence_before();
@@ -534,11 +542,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   }
 }
 
-template <int D, bool DROP>
+template <int D, bool DROP, bool F16>
 int launch_bwd_tc(const void* q, const void* k, const void* v, long long ld_qkv, const void* dout, long long ld_do,
                   const BwdTcParams& p, int num_seqs, int max_seqlen, long long total_rows, cudaStream_t stream) {
-  auto kdq = attn_bwd_dq_tc_kernel<D, DROP>;
-  auto kdkv = attn_bwd_dkv_tc_kernel<D, DROP>;
+  auto kdq = attn_bwd_dq_tc_kernel<D, DROP, F16>;
+  auto kdkv = attn_bwd_dkv_tc_kernel<D, DROP, F16>;
   static bool attr_set = false;
   if (!attr_set) {
     B2S_CUDA_CHECK(cudaFuncSetAttribute(kdq, cudaFuncAttributeMaxDynamicSharedMemorySize, DqCfg<D>::kSmemBytes));
@@ -564,17 +572,62 @@ int launch_bwd_tc(const void* q, const void* k, const void* v, long long ld_qkv,
   return B2S_OK;
 }
 
+
+// delta[row, h] = sum_d dO[row, h, d] * O[row, h, d]; one warp per row, 16-byte loads, lanes of one head reduce together
+template <int D>
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, long long ld_o,
+                  long long ld_do, float* __restrict__ delta, long long rows, int Hq, int f16) {
+  constexpr int kLanesPerHead = D / 8;            // 8 (D = 64) or 16 (D = 128)
+  constexpr int kHeadsPerIter = 32 / kLanesPerHead;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  for (int h0 = 0; h0 < Hq; h0 += kHeadsPerIter) {
+    const int h = h0 + lane / kLanesPerHead;
+    float s = 0.f;
+    if (h < Hq) {
+      float a[8], b[8];
+      ld8h(o + row * ld_o + h0 * D + lane * 8, a, f16);
+      ld8h(dout + row * ld_do + h0 * D + lane * 8, b, f16);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(a[i], b[i], s);
+    }
+#pragma unroll
+    for (int off = kLanesPerHead / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (h < Hq && lane % kLanesPerHead == 0) delta[row * Hq + h] = s;
+  }
+}
+
 }  // namespace
 
-// q / k / v: bf16 views with row stride ld_qkv, head h at column h*D of EACH view (as in attention_bwd)
-int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld_qkv, const void* dout, long long ld_do,
-                     const float* lse, const float* delta, void* dq, void* dk, void* dv, long long ld_dqkv,
-                     const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
-                     float scale, int causal, const float* rope_cs, cudaStream_t stream, const AttnDrop* drop) {
+// Backward of attention_fwd (ops.cuh). q / k / v / o / dout / dq / dk / dv share one 16-bit format (fmt: B2S_FMT_*);
+// head h of a row sits at column h*D of EACH view.
+int attention_bwd(const void* q, const void* k, const void* v, long long ld_qkv, const void* o, long long ld_o,
+                  const void* dout, long long ld_do, const float* lse, float* delta_ws, void* dq, void* dk, void* dv,
+                  long long ld_dqkv, const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq,
+                  int Hkv, int D, float scale, int causal, const float* rope_cs, int fmt, cudaStream_t stream,
+                  const AttnDrop* drop) {
+  B2S_REQUIRE(q && k && v && o && dout && lse && delta_ws && dq && dk && dv && cu_seqlens, "attention_bwd: null pointer");
+  if (drop != nullptr && drop->thresh == 0u) drop = nullptr;
+  B2S_REQUIRE(num_seqs > 0 && max_seqlen > 0 && total_rows > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0,
+              "attention_bwd: bad sizes");
+  B2S_REQUIRE(ld_qkv % 8 == 0 && ld_do % 8 == 0 && ld_o % 8 == 0 && ld_dqkv % 8 == 0,
+              "attention_bwd: strides must keep 16-byte row alignment");
+  B2S_REQUIRE(D == 64 || D == 128, "attention_bwd: head_dim %d unsupported (64 or 128)", D);
+  const bool f16 = fmt != 0;
+  {
+    const unsigned grid = static_cast<unsigned>((total_rows + 7) / 8);
+    const __nv_bfloat16* ob = reinterpret_cast<const __nv_bfloat16*>(o);
+    const __nv_bfloat16* dob = reinterpret_cast<const __nv_bfloat16*>(dout);
+    if (D == 64) attn_delta_kernel<64><<<grid, 256, 0, stream>>>(ob, dob, ld_o, ld_do, delta_ws, total_rows, Hq, fmt);
+    else attn_delta_kernel<128><<<grid, 256, 0, stream>>>(ob, dob, ld_o, ld_do, delta_ws, total_rows, Hq, fmt);
+    B2S_LAUNCH_CHECK();
+  }
   BwdTcParams p{};
   p.cu = cu_seqlens;
   p.lse = lse;
-  p.delta = delta;
+  p.delta = delta_ws;
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq);
   p.dk = reinterpret_cast<__nv_bfloat16*>(dk);
   p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
@@ -585,15 +638,17 @@ int attention_bwd_tc(const void* q, const void* k, const void* v, long long ld_q
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
   p.rope_cs = rope_cs;
-  if (drop != nullptr && drop->thresh != 0u) {
-    B2S_REQUIRE(D == 64 && max_seqlen < 65536, "attention_bwd_tc: attention dropout supports head_dim 64, seqlen < 65536");
+#define B2S_BWD_GO(D_, DROP_)                                                                                          \
+  return f16 ? launch_bwd_tc<D_, DROP_, true>(q, k, v, ld_qkv, dout, ld_do, p, num_seqs, max_seqlen, total_rows, stream) \
+             : launch_bwd_tc<D_, DROP_, false>(q, k, v, ld_qkv, dout, ld_do, p, num_seqs, max_seqlen, total_rows, stream)
+  if (drop != nullptr) {
+    B2S_REQUIRE(D == 64 && max_seqlen < 65536, "attention_bwd: attention dropout supports head_dim 64, seqlen < 65536");
     p.drop = *drop;
-    return launch_bwd_tc<64, true>(q, k, v, ld_qkv, dout, ld_do, p, num_seqs, max_seqlen, total_rows, stream);
+    B2S_BWD_GO(64, true);
   }
-  if (D == 64) return launch_bwd_tc<64, false>(q, k, v, ld_qkv, dout, ld_do, p, num_seqs, max_seqlen, total_rows, stream);
-  if (D == 128) return launch_bwd_tc<128, false>(q, k, v, ld_qkv, dout, ld_do, p, num_seqs, max_seqlen, total_rows, stream);
-  set_last_error("attention_bwd_tc: head_dim %d unsupported (64 or 128)", D);
-  return B2S_ERR_UNSUPPORTED;
+  if (D == 64) { B2S_BWD_GO(64, false); }
+  B2S_BWD_GO(128, false);
+#undef B2S_BWD_GO
 }
 
 }  // namespace b2s

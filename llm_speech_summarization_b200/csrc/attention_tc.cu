@@ -16,8 +16,9 @@
 // (profiles/r01_attention_configs.md).
 // Hand-offs are mbarriers (tcgen05.commit -> softmax, softmax -> MMA issuer); every wait is bounded.
 //
-// Covers HuBERT / Whisper (non-causal, D=64) and Llama / MiniChat (causal GQA, D=128); same C entry point and
-// semantics as attention.cu (TF/models/hubert/modeling_hubert.py:262-345, TF/models/llama/modeling_llama.py:225-289).
+// Covers HuBERT / Whisper (non-causal, D=64) and Llama / MiniChat (causal GQA, D=128)
+// (TF/models/hubert/modeling_hubert.py:262-345, TF/models/llama/modeling_llama.py:225-289). Operands (Q, K, V, P, O)
+// are bf16 or fp16 (template F16): same tcgen05 kind::f16 rate, 3 more mantissa bits for fp16.
 #include <cstdio>
 #include <cstdlib>
 #include <cuda.h>
@@ -120,7 +121,7 @@ __device__ __forceinline__ int attn_next_item(const AttnParams& p, int item, Att
   return p.total_items;
 }
 
-template <int D, int BN, int KVS, bool DROP>
+template <int D, int BN, int KVS, bool DROP, bool F16>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -184,8 +185,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                            p.v_col0 + it.hk * D + a * 64, it.s0 + j * kBN);
         }
       };
-      constexpr uint32_t idesc_s = ptx::make_idesc_bf16_f32(kBM, kBN);
-      constexpr uint32_t idesc_o = ptx::make_idesc_bf16_f32(kBM, D) | (1u << 16);  // B (= V) is MN-major
+      constexpr uint32_t idesc_s = ptx::make_idesc_f32acc(kBM, kBN) | ptx::idesc_formats(F16, F16);
+      constexpr uint32_t idesc_o =
+          ptx::make_idesc_f32acc(kBM, D) | ptx::idesc_formats(F16, F16) | (1u << 16);  // B (= V) is MN-major
       AttnItem cur, nxt;
       int item = attn_next_item<BN>(p, blockIdx.x, &cur);
       uint32_t g = 0, items_done = 0;
@@ -351,7 +353,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 p0 = rng_keep(e, dk1, dk2, p.drop.thresh) ? p0 : 0.f;
                 p1 = rng_keep(e + 1u, dk1, dk2, p.drop.thresh) ? p1 : 0.f;
               }
-              pk[i >> 1] = pack_bf16(p0, p1);
+              pk[i >> 1] = F16 ? pack_f16(p0, p1) : pack_bf16(p0, p1);
             }
           } else {
             const int nv = nvis - c * 32;
@@ -368,7 +370,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 p0 = rng_keep(e, dk1, dk2, p.drop.thresh) ? p0 : 0.f;
                 p1 = rng_keep(e + 1u, dk1, dk2, p.drop.thresh) ? p1 : 0.f;
               }
-              pk[i >> 1] = pack_bf16(p0, p1);
+              pk[i >> 1] = F16 ? pack_f16(p0, p1) : pack_bf16(p0, p1);
             }
           }
           // chunk c covers keys [32c, 32c+32) = 64 bytes = four 16-byte chunks of atom (c >> 1)
@@ -383,13 +385,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           }
         }
         const float bm = bmax * sc;
-        const bool overflow_risk = bm > m_ref + 60.0f;
+        // P is stored in the operand format: bf16 shares fp32's exponent range (redo only past 2^60); fp16 tops out at
+        // 65504, so a block whose max outgrew the reference by 2^14 is redone at once and 2^8 already moves it
+        constexpr float kRedo = F16 ? 14.0f : 60.0f, kDefer = F16 ? 8.0f : 16.0f;
+        const bool overflow_risk = bm > m_ref + kRedo;
         if (attempt == 0 && __any_sync(0xffffffffu, overflow_risk)) {
           if (overflow_risk) pend = bm;
           continue;  // adopt now and redo this block (P in smem is simply rewritten; nothing has consumed it)
         }
         l_run += rs;
-        if (bm > m_ref + 16.0f) pend = bm;
+        if (bm > m_ref + kDefer) pend = bm;
         break;
       }
       // publish P to the async proxy (UMMA reads smem) and hand S / O back to the MMA issuer
@@ -416,10 +421,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 u;
-          u.x = pack_bf16(__uint_as_float(raw[8 * q + 0]) * inv, __uint_as_float(raw[8 * q + 1]) * inv);
-          u.y = pack_bf16(__uint_as_float(raw[8 * q + 2]) * inv, __uint_as_float(raw[8 * q + 3]) * inv);
-          u.z = pack_bf16(__uint_as_float(raw[8 * q + 4]) * inv, __uint_as_float(raw[8 * q + 5]) * inv);
-          u.w = pack_bf16(__uint_as_float(raw[8 * q + 6]) * inv, __uint_as_float(raw[8 * q + 7]) * inv);
+          u.x = pack_h16(__uint_as_float(raw[8 * q + 0]) * inv, __uint_as_float(raw[8 * q + 1]) * inv, F16);
+          u.y = pack_h16(__uint_as_float(raw[8 * q + 2]) * inv, __uint_as_float(raw[8 * q + 3]) * inv, F16);
+          u.z = pack_h16(__uint_as_float(raw[8 * q + 4]) * inv, __uint_as_float(raw[8 * q + 5]) * inv, F16);
+          u.w = pack_h16(__uint_as_float(raw[8 * q + 6]) * inv, __uint_as_float(raw[8 * q + 7]) * inv, F16);
           *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = u;
         }
       }
@@ -435,13 +440,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   }
 }
 
-template <int D, int BN, int KVS, bool DROP>
+template <int D, int BN, int KVS, bool DROP, bool F16>
 int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, const int* cu,
                    int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, float scale, int causal,
                    float* lse, cudaStream_t stream, const AttnDrop* drop) {
   using C = AttnCfg<D, BN, KVS>;
   constexpr int kBN = BN;
-  auto kern = attn_fwd_tc_kernel<D, BN, KVS, DROP>;
+  auto kern = attn_fwd_tc_kernel<D, BN, KVS, DROP, F16>;
   static bool attr_set = false;
   if (!attr_set) {
     B2S_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -490,13 +495,27 @@ static const bool g_cfg_read = [] {
   return true;
 }();
 
-int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
-                     const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
-                     float scale, int causal, float* lse, cudaStream_t stream, const AttnDrop* drop) {
+// Packed variable-length attention forward (ops.cuh). q / k / v / o share one 16-bit format (fmt: B2S_FMT_*).
+int attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
+                  const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
+                  float scale, int causal, float* lse, int fmt, cudaStream_t stream, const AttnDrop* drop) {
+  B2S_REQUIRE(q && k && v && o && cu_seqlens, "attention_fwd: null pointer");
+  if (drop != nullptr && drop->thresh == 0u) drop = nullptr;
+  B2S_REQUIRE(total_rows > 0, "attention_fwd: total_rows must be the row count of the packed q/k/v buffers");
+  B2S_REQUIRE(num_seqs > 0 && max_seqlen > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "attention_fwd: bad head counts");
+  B2S_REQUIRE(ld_qkv % 8 == 0 && ld_o % 8 == 0, "attention_fwd: strides must keep 16-byte row alignment");
+  B2S_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(v) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0,
+              "attention_fwd: q/k/v/o must be 16-byte aligned");
+  B2S_REQUIRE(D == 64 || D == 128, "attention_fwd: head_dim %d unsupported (64 or 128)", D);
+  const bool f16 = fmt != 0;
 #define B2S_ATTN_ARGS q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, scale, causal, lse, stream
-  if (drop != nullptr && drop->thresh != 0u) {  // train-mode HuBERT attention only (TF/.../modeling_hubert.py:254)
-    B2S_REQUIRE(D == 64 && max_seqlen < 65536, "attention_fwd_tc: attention dropout supports head_dim 64, seqlen < 65536");
-    return launch_attn_tc<64, 64, 1, true>(B2S_ATTN_ARGS, drop);
+#define B2S_ATTN_GO(D_, BN_, KVS_, DROP_, DP_)                                     \
+  return f16 ? launch_attn_tc<D_, BN_, KVS_, DROP_, true>(B2S_ATTN_ARGS, DP_)      \
+             : launch_attn_tc<D_, BN_, KVS_, DROP_, false>(B2S_ATTN_ARGS, DP_)
+  if (drop != nullptr) {  // train-mode HuBERT attention only (TF/.../modeling_hubert.py:254)
+    B2S_REQUIRE(D == 64 && max_seqlen < 65536, "attention_fwd: attention dropout supports head_dim 64, seqlen < 65536");
+    B2S_ATTN_GO(64, 64, 1, true, drop);
   }
   int bn = g_cfg_bn, kvs = g_cfg_kvs;
   if (bn == 0) {
@@ -506,15 +525,16 @@ int attention_fwd_tc(const void* q, const void* k, const void* v, long long ld_q
     kvs = 1;
     if (D == 128 && max_seqlen > 1024) bn = 128, kvs = 2;
   }
-  if (D == 64 && bn == 64 && kvs == 1) return launch_attn_tc<64, 64, 1, false>(B2S_ATTN_ARGS, nullptr);
-  if (D == 64 && bn == 64 && kvs == 2) return launch_attn_tc<64, 64, 2, false>(B2S_ATTN_ARGS, nullptr);
-  if (D == 64 && bn == 128 && kvs == 1) return launch_attn_tc<64, 128, 1, false>(B2S_ATTN_ARGS, nullptr);
-  if (D == 64 && bn == 128 && kvs == 2) return launch_attn_tc<64, 128, 2, false>(B2S_ATTN_ARGS, nullptr);
-  if (D == 128 && bn == 64 && kvs == 1) return launch_attn_tc<128, 64, 1, false>(B2S_ATTN_ARGS, nullptr);
-  if (D == 128 && bn == 64 && kvs == 2) return launch_attn_tc<128, 64, 2, false>(B2S_ATTN_ARGS, nullptr);
-  if (D == 128 && bn == 128 && kvs == 2) return launch_attn_tc<128, 128, 2, false>(B2S_ATTN_ARGS, nullptr);
+  if (D == 64 && bn == 64 && kvs == 1) { B2S_ATTN_GO(64, 64, 1, false, nullptr); }
+  if (D == 64 && bn == 64 && kvs == 2) { B2S_ATTN_GO(64, 64, 2, false, nullptr); }
+  if (D == 64 && bn == 128 && kvs == 1) { B2S_ATTN_GO(64, 128, 1, false, nullptr); }
+  if (D == 64 && bn == 128 && kvs == 2) { B2S_ATTN_GO(64, 128, 2, false, nullptr); }
+  if (D == 128 && bn == 64 && kvs == 1) { B2S_ATTN_GO(128, 64, 1, false, nullptr); }
+  if (D == 128 && bn == 64 && kvs == 2) { B2S_ATTN_GO(128, 64, 2, false, nullptr); }
+  if (D == 128 && bn == 128 && kvs == 2) { B2S_ATTN_GO(128, 128, 2, false, nullptr); }
+#undef B2S_ATTN_GO
 #undef B2S_ATTN_ARGS
-  set_last_error("attention_fwd_tc: head_dim %d unsupported (64 or 128)", D);
+  set_last_error("attention_fwd: tile configuration %d,%d unsupported for head_dim %d", bn, kvs, D);
   return B2S_ERR_UNSUPPORTED;
 }
 

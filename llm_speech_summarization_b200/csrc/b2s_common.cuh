@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace b2s {
@@ -84,6 +85,20 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 p = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(p);
 }
+// 16-bit storage format of a tensor: B2S_FMT_BF16 = 0, B2S_FMT_F16 = 1 (include/b2s.h). `f16` is warp-uniform
+// everywhere (a kernel argument), so these are a predicated pair of conversions, not divergence.
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 p = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t u) {
+  __half2 p = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(p);
+}
+__device__ __forceinline__ uint32_t pack_h16(float lo, float hi, int f16) {
+  return f16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
+}
+__device__ __forceinline__ float2 unpack_h16(uint32_t u, int f16) { return f16 ? unpack_f16(u) : unpack_bf16(u); }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
@@ -130,6 +145,36 @@ __device__ __forceinline__ void ld8bf(const __nv_bfloat16* p, float (&f)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
   f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+
+// format-generic twins (f16 = 1: IEEE half, 0: bfloat16). Pointers to 16-bit tensors are typed __nv_bfloat16* throughout
+// the library purely as "2-byte element" pointers; the format travels separately.
+__device__ __forceinline__ void unpack8_h16(const uint4& u, float (&f)[8], int f16) {
+  if (f16) {
+    const float2 a = unpack_f16(u.x), b = unpack_f16(u.y), c = unpack_f16(u.z), d = unpack_f16(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  } else {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+  }
+}
+__device__ __forceinline__ uint4 pack8_h16(const float (&f)[8], int f16) {
+  uint4 u;
+  u.x = pack_h16(f[0], f[1], f16); u.y = pack_h16(f[2], f[3], f16);
+  u.z = pack_h16(f[4], f[5], f16); u.w = pack_h16(f[6], f[7], f16);
+  return u;
+}
+__device__ __forceinline__ void ld8h(const __nv_bfloat16* p, float (&f)[8], int f16) {
+  unpack8_h16(*reinterpret_cast<const uint4*>(p), f, f16);
+}
+__device__ __forceinline__ void st8h(__nv_bfloat16* p, const float (&f)[8], int f16) {
+  *reinterpret_cast<uint4*>(p) = pack8_h16(f, f16);
+}
+__device__ __forceinline__ float h16_to_float(uint16_t bits, int f16) {
+  return f16 ? __half2float(__ushort_as_half(bits)) : __uint_as_float(static_cast<uint32_t>(bits) << 16);
+}
+__device__ __forceinline__ uint16_t float_to_h16(float x, int f16) {
+  return f16 ? __half_as_ushort(__float2half_rn(x)) : __bfloat16_as_ushort(__float2bfloat16(x));
 }
 
 // erf-GELU derivative: Phi(x) + x phi(x)

@@ -257,14 +257,20 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
   return d;
 }
 
-// Instruction descriptor for kind::f16: bf16 A/B (K-major both), fp32 accumulate, shape M x N.
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
+// Instruction descriptor for kind::f16: fp32 accumulate, shape M x N, both operands K-major; the operand formats
+// (a_format bits [7,10), b_format bits [10,13): 0 = fp16, 1 = bf16) are OR-ed in separately -- they are independent
+// fields, so A and B may differ (bf16 gradients against fp16 activations / weights in the backward GEMMs).
+__host__ __device__ constexpr uint32_t make_idesc_f32acc(int M, int N) {
   return (1u << 4)                              // c_format = F32
-         | (1u << 7)                            // a_format = BF16
-         | (1u << 10)                           // b_format = BF16
          | (0u << 15) | (0u << 16)              // A, B K-major
          | (static_cast<uint32_t>(N >> 3) << 17)  // n_dim
          | (static_cast<uint32_t>(M >> 4) << 24); // m_dim
+}
+__host__ __device__ constexpr uint32_t idesc_formats(bool a_f16, bool b_f16) {
+  return ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10);
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
+  return make_idesc_f32acc(M, N) | idesc_formats(false, false);
 }
 
 }  // namespace ptx

@@ -16,7 +16,7 @@ template <int GROUPS>
 __global__ void __launch_bounds__(kWarps * 32)
 rmsnorm_bwd_kernel(const float* __restrict__ x, const int* __restrict__ x_index, const float* __restrict__ w, float eps,
                    const float* __restrict__ dy, float* dh, const int* __restrict__ dh_index,
-                   __nv_bfloat16* dh_bf16, long long rows) {
+                   __nv_bfloat16* dh_bf16, long long rows, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   constexpr int C = GROUPS * 256;
   const int lane = threadIdx.x & 31;
@@ -52,7 +52,7 @@ rmsnorm_bwd_kernel(const float* __restrict__ x, const int* __restrict__ x_index,
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += rstd * gv[g][j] - coef * xv[g][j];
     st8f(dh + dr * C + c, acc);
-    if (dh_bf16 != nullptr) st8bf(dh_bf16 + dr * C + c, acc);
+    if (dh_bf16 != nullptr) st8h(dh_bf16 + dr * C + c, acc, f16);
   }
 }
 
@@ -63,7 +63,7 @@ template <int GROUPS, bool DY_BF16>
 __global__ void __launch_bounds__(kWarps * 32)
 layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float eps, const void* __restrict__ dy,
                      float* dh, int accumulate, __nv_bfloat16* dh_bf16, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, long long rows) {
+                     float* __restrict__ dbeta, long long rows, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   constexpr int C = GROUPS * 256;
   __shared__ float s_dg[C], s_db[C];
@@ -78,7 +78,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     for (int g = 0; g < GROUPS; ++g) {
       const int c = (g * 32 + lane) * 8;
       ld8f(x + row * C + c, xv[g]);
-      if constexpr (DY_BF16) ld8bf(reinterpret_cast<const __nv_bfloat16*>(dy) + row * C + c, dv[g]);
+      if constexpr (DY_BF16) ld8h(reinterpret_cast<const __nv_bfloat16*>(dy) + row * C + c, dv[g], f16);
       else ld8f(reinterpret_cast<const float*>(dy) + row * C + c, dv[g]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += xv[g][j];
@@ -124,7 +124,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += rstd * (dv[g][j] - sg - xv[g][j] * sgx);
       st8f(dh + row * C + c, acc);
-      if (dh_bf16 != nullptr) st8bf(dh_bf16 + row * C + c, acc);
+      if (dh_bf16 != nullptr) st8h(dh_bf16 + row * C + c, acc, f16);
     }
   }
   __syncthreads();
@@ -138,7 +138,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 //   a = silu(g) u ; dg = da u sig(g) (1 + g (1 - sig(g))) ; du = da silu(g)
 __global__ void __launch_bounds__(256)
 swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __nv_bfloat16* __restrict__ dact,
-                  __nv_bfloat16* __restrict__ dgu, long long rows, int F) {
+                  __nv_bfloat16* __restrict__ dgu, long long rows, int F, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // one 8-element vector of dact
   const long long per_row = F / 8;
@@ -149,29 +149,29 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __nv_bfloat16* __r
   const int blk = col / 64, within = col % 64;  // 64-wide block
   const long long gbase = row * 2 * F + blk * 128 + within;
   float g[8], u[8], da[8], dg[8], du[8];
-  ld8bf(gu + gbase, g);
-  ld8bf(gu + gbase + 64, u);
-  ld8bf(dact + row * F + col, da);
+  ld8h(gu + gbase, g, f16);
+  ld8h(gu + gbase + 64, u, f16);
+  ld8h(dact + row * F + col, da, f16);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float sg = __fdividef(1.0f, 1.0f + __expf(-g[j]));
     dg[j] = da[j] * u[j] * sg * (1.0f + g[j] * (1.0f - sg));
     du[j] = da[j] * g[j] * sg;
   }
-  st8bf(dgu + gbase, dg);
-  st8bf(dgu + gbase + 64, du);
+  st8h(dgu + gbase, dg, f16);
+  st8h(dgu + gbase + 64, du, f16);
 }
 
 // erf-GELU backward: dpre = dy * (Phi(x) + x phi(x))
 __global__ void __launch_bounds__(256)
 gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dy,
-                __nv_bfloat16* __restrict__ dpre, long long n8, DropSpec drop) {
+                __nv_bfloat16* __restrict__ dpre, long long n8, DropSpec drop, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   float x[8], d[8];
-  ld8bf(pre + i * 8, x);
-  ld8bf(dy + i * 8, d);
+  ld8h(pre + i * 8, x, f16);
+  ld8h(dy + i * 8, d, f16);
   if (drop.thresh != 0u) {  // dy is the gradient w.r.t. dropout(gelu(pre)): mask first (activation dropout site)
     const uint32_t e0 = static_cast<uint32_t>(i * 8);
 #pragma unroll
@@ -181,19 +181,20 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __re
   for (int j = 0; j < 8; ++j) {
     d[j] *= gelu_erf_grad(x[j]);
   }
-  st8bf(dpre + i * 8, d);
+  st8h(dpre + i * 8, d, f16);
 }
 
 // dh[rows_a[i]] += c * (h[rows_a[i]] - h[rows_b[i]])  (feature-distillation MSE backward, REF/trainer.py:358-370)
 __global__ void __launch_bounds__(256)
 add_rowdiff_kernel(const float* __restrict__ h, const int* __restrict__ rows_a, const int* __restrict__ rows_b,
-                   const float* __restrict__ coef, float* dh, __nv_bfloat16* dh_bf16, int pairs, int C) {
+                   const float* __restrict__ coef, const float* __restrict__ loss_scale, float* dh,
+                   __nv_bfloat16* dh_bf16, int pairs, int C, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= pairs) return;
   const long long ra = rows_a[i], rb = rows_b[i];
-  const float c = coef[i];
+  const float c = coef[i] * (loss_scale != nullptr ? *loss_scale : 1.0f);
   for (int k = lane * 4; k < C; k += 128) {
     const float4 a = *reinterpret_cast<const float4*>(h + ra * C + k);
     const float4 b = *reinterpret_cast<const float4*>(h + rb * C + k);
@@ -202,8 +203,8 @@ add_rowdiff_kernel(const float* __restrict__ h, const int* __restrict__ rows_a, 
     *reinterpret_cast<float4*>(dh + ra * C + k) = d;
     if (dh_bf16 != nullptr) {
       uint2 u;
-      u.x = pack_bf16(d.x, d.y);
-      u.y = pack_bf16(d.z, d.w);
+      u.x = pack_h16(d.x, d.y, f16);
+      u.y = pack_h16(d.z, d.w, f16);
       *reinterpret_cast<uint2*>(dh_bf16 + ra * C + k) = u;
     }
   }
@@ -226,10 +227,29 @@ gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ index,
 }
 
 // AdamW (torch.optim.AdamW semantics, REF/trainer.py:98-105): decoupled weight decay, bias-corrected moments.
+// scaler (optional, device): the dynamic loss-scaling state of grad_scaler_update below -- the gradients carry the
+// factor scaler->scale, and a step whose gradients held an inf / nan is skipped entirely (torch.cuda.amp.GradScaler.step,
+// REF/trainer.py:381); the bias corrections then use the number of steps actually taken.
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2,
-             float grad_scale) {
+             float grad_scale, const GradScalerState* __restrict__ scaler) {
+  if (scaler != nullptr) {  // block-uniform: one thread evaluates the state, everybody reads it from shared memory
+    __shared__ float s_par[3];
+    __shared__ int s_skip;
+    if (threadIdx.x == 0) {
+      s_skip = scaler->found_inf;
+      const float t = static_cast<float>(scaler->opt_steps + 1);
+      s_par[0] = grad_scale / scaler->scale;
+      s_par[1] = 1.0f - powf(beta1, t);
+      s_par[2] = 1.0f - powf(beta2, t);
+    }
+    __syncthreads();
+    if (s_skip != 0) return;
+    grad_scale = s_par[0];
+    bc1 = s_par[1];
+    bc2 = s_par[2];
+  }
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float gr = g[i] * grad_scale;
@@ -240,6 +260,35 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   v[i] = vv;
   pv -= lr * (mv / bc1) / (sqrtf(vv / bc2) + eps);
   p[i] = pv;
+}
+
+// found_inf |= any non-finite element of g (the unscale_ + inf check of GradScaler, fused: nothing is rewritten)
+__global__ void __launch_bounds__(256)
+nonfinite_check_kernel(const float* __restrict__ g, long long n4, GradScalerState* __restrict__ scaler) {
+  bool bad = false;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    // x - x is 0 for finite x and nan for inf / nan
+    bad |= !((v.x - v.x) + (v.y - v.y) + (v.z - v.z) + (v.w - v.w) == 0.0f);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&scaler->found_inf, 1);
+}
+
+// GradScaler.update(): scale *= backoff on an overflow step, else *= growth after `interval` clean steps
+__global__ void grad_scaler_update_kernel(GradScalerState* s, float growth, float backoff, int interval) {
+  if (s->found_inf != 0) {
+    s->scale *= backoff;
+    s->growth_tracker = 0;
+    s->skipped_steps += 1;
+  } else {
+    s->opt_steps += 1;
+    if (++s->growth_tracker >= interval) {
+      s->scale *= growth;
+      s->growth_tracker = 0;
+    }
+  }
+  s->found_inf = 0;
 }
 
 }  // namespace
@@ -256,19 +305,19 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 
 int rmsnorm_bwd(const float* x, const int* x_index, const float* w, float eps, const float* dy, float* dh,
-                const int* dh_index, void* dh_bf16, long long rows, int C, cudaStream_t stream) {
+                const int* dh_index, void* dh_bf16, long long rows, int C, int fmt, cudaStream_t stream) {
   B2S_REQUIRE(x && w && dy && dh, "rmsnorm_bwd: null pointer");
   B2S_REQUIRE(C % 256 == 0, "rmsnorm_bwd: C must be a multiple of 256");
   if (rows <= 0) return B2S_OK;
   const unsigned grid = static_cast<unsigned>((rows + kWarps - 1) / kWarps);
   B2S_GROUPS_SWITCH(C, (rmsnorm_bwd_kernel<G><<<grid, kWarps * 32, 0, stream>>>(
-                           x, x_index, w, eps, dy, dh, dh_index, reinterpret_cast<__nv_bfloat16*>(dh_bf16), rows)));
+                           x, x_index, w, eps, dy, dh, dh_index, reinterpret_cast<__nv_bfloat16*>(dh_bf16), rows, fmt)));
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 int layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int dy_bf16, float* dh, int accumulate,
-                  void* dh_bf16, float* dgamma, float* dbeta, long long rows, int C, cudaStream_t stream) {
+                  void* dh_bf16, float* dgamma, float* dbeta, long long rows, int C, int fmt, cudaStream_t stream) {
   B2S_REQUIRE(x && gamma && dy && dh && dgamma && dbeta, "layernorm_bwd: null pointer");
   B2S_REQUIRE(C % 256 == 0, "layernorm_bwd: C must be a multiple of 256");
   if (rows <= 0) return B2S_OK;
@@ -276,47 +325,48 @@ int layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy,
   if (dy_bf16) {
     B2S_GROUPS_SWITCH(C, (layernorm_bwd_kernel<G, true><<<grid, kWarps * 32, 0, stream>>>(
                              x, gamma, eps, dy, dh, accumulate, reinterpret_cast<__nv_bfloat16*>(dh_bf16), dgamma, dbeta,
-                             rows)));
+                             rows, fmt)));
   } else {
     B2S_GROUPS_SWITCH(C, (layernorm_bwd_kernel<G, false><<<grid, kWarps * 32, 0, stream>>>(
                              x, gamma, eps, dy, dh, accumulate, reinterpret_cast<__nv_bfloat16*>(dh_bf16), dgamma, dbeta,
-                             rows)));
+                             rows, fmt)));
   }
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
-int swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows, int F, cudaStream_t stream) {
+int swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows, int F, int fmt, cudaStream_t stream) {
   B2S_REQUIRE(gu && dact && dgu, "swiglu_bwd: null pointer");
   B2S_REQUIRE(F % 64 == 0, "swiglu_bwd: F must be a multiple of 64");
   if (rows <= 0) return B2S_OK;
   const long long n = rows * (F / 8);
   swiglu_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(gu), reinterpret_cast<const __nv_bfloat16*>(dact),
-      reinterpret_cast<__nv_bfloat16*>(dgu), rows, F);
+      reinterpret_cast<__nv_bfloat16*>(dgu), rows, F, fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
-int gelu_bwd(const void* pre, const void* dy, void* dpre, long long n, cudaStream_t stream, const DropSpec* drop) {
+int gelu_bwd(const void* pre, const void* dy, void* dpre, long long n, int fmt, cudaStream_t stream,
+             const DropSpec* drop) {
   B2S_REQUIRE(pre && dy && dpre, "gelu_bwd: null pointer");
   B2S_REQUIRE(n % 8 == 0, "gelu_bwd: element count must be a multiple of 8");
   B2S_REQUIRE(drop == nullptr || n < (1LL << 32), "gelu_bwd: dropout element index exceeds 32 bits");
   if (n <= 0) return B2S_OK;
   gelu_bwd_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<const __nv_bfloat16*>(dy),
-      reinterpret_cast<__nv_bfloat16*>(dpre), n / 8, drop ? *drop : DropSpec{});
+      reinterpret_cast<__nv_bfloat16*>(dpre), n / 8, drop ? *drop : DropSpec{}, fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
-int add_rowdiff(const float* h, const int* rows_a, const int* rows_b, const float* coef, float* dh, void* dh_bf16,
-                int pairs, int C, cudaStream_t stream) {
+int add_rowdiff(const float* h, const int* rows_a, const int* rows_b, const float* coef, const float* loss_scale,
+                float* dh, void* dh_bf16, int pairs, int C, int fmt, cudaStream_t stream) {
   B2S_REQUIRE(h && rows_a && rows_b && coef && dh, "add_rowdiff: null pointer");
   B2S_REQUIRE(C % 4 == 0, "add_rowdiff: C must be a multiple of 4");
   if (pairs <= 0) return B2S_OK;
-  add_rowdiff_kernel<<<(pairs + 7) / 8, 256, 0, stream>>>(h, rows_a, rows_b, coef, dh,
-                                                          reinterpret_cast<__nv_bfloat16*>(dh_bf16), pairs, C);
+  add_rowdiff_kernel<<<(pairs + 7) / 8, 256, 0, stream>>>(h, rows_a, rows_b, coef, loss_scale, dh,
+                                                          reinterpret_cast<__nv_bfloat16*>(dh_bf16), pairs, C, fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -331,13 +381,33 @@ int gather_rows_f32(const float* src, const int* index, float* out, long long ro
 }
 
 int adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-               float weight_decay, int step, float grad_scale, cudaStream_t stream) {
-  B2S_REQUIRE(p && g && m && v && step >= 1, "adamw_step: bad arguments");
+               float weight_decay, int step, float grad_scale, const GradScalerState* scaler, cudaStream_t stream) {
+  B2S_REQUIRE(p && g && m && v && (step >= 1 || scaler != nullptr), "adamw_step: bad arguments");
   if (n <= 0) return B2S_OK;
   const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
   adamw_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps,
-                                                                           weight_decay, bc1, bc2, grad_scale);
+                                                                           weight_decay, bc1, bc2, grad_scale, scaler);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+int nonfinite_check(const float* g, long long n, GradScalerState* scaler, cudaStream_t stream) {
+  B2S_REQUIRE(g && scaler && n % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0,
+              "nonfinite_check: needs a 16-byte aligned buffer of a multiple of 4 floats");
+  if (n <= 0) return B2S_OK;
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = 8LL * num_sms();
+  if (blocks > cap) blocks = cap;
+  nonfinite_check_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(g, n / 4, scaler);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+int grad_scaler_update(GradScalerState* scaler, float growth, float backoff, int interval, cudaStream_t stream) {
+  B2S_REQUIRE(scaler && growth >= 1.0f && backoff > 0.0f && backoff <= 1.0f && interval >= 1,
+              "grad_scaler_update: bad arguments");
+  grad_scaler_update_kernel<<<1, 1, 0, stream>>>(scaler, growth, backoff, interval);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

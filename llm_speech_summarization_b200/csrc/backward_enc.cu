@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 layernorm_bwd_ex_kernel(const void* __restrict__ x, int x_bf16, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float eps, const void* __restrict__ dy, int dy_bf16, float* dh,
                         int accumulate, __nv_bfloat16* dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                        long long rows) {
+                        long long rows, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   constexpr int C = GROUPS * 256;
   __shared__ float s_red[kWarps][C];
@@ -42,9 +42,9 @@ layernorm_bwd_ex_kernel(const void* __restrict__ x, int x_bf16, const float* __r
 #pragma unroll
     for (int g = 0; g < GROUPS; ++g) {
       const int c = (g * 32 + lane) * 8;
-      if (x_bf16) ld8bf(reinterpret_cast<const __nv_bfloat16*>(x) + row * C + c, xv[g]);
+      if (x_bf16) ld8h(reinterpret_cast<const __nv_bfloat16*>(x) + row * C + c, xv[g], f16);
       else ld8f(reinterpret_cast<const float*>(x) + row * C + c, xv[g]);
-      if (dy_bf16) ld8bf(reinterpret_cast<const __nv_bfloat16*>(dy) + row * C + c, dv[g]);
+      if (dy_bf16) ld8h(reinterpret_cast<const __nv_bfloat16*>(dy) + row * C + c, dv[g], f16);
       else ld8f(reinterpret_cast<const float*>(dy) + row * C + c, dv[g]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += xv[g][j];
@@ -89,7 +89,7 @@ layernorm_bwd_ex_kernel(const void* __restrict__ x, int x_bf16, const float* __r
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += rstd * (dv[g][j] - sg - xv[g][j] * sgx);
       if (dh != nullptr) st8f(dh + row * C + c, acc);
-      if (dx_bf16 != nullptr) st8bf(dx_bf16 + row * C + c, acc);
+      if (dx_bf16 != nullptr) st8h(dx_bf16 + row * C + c, acc, f16);
     }
   }
   // parameter gradients: registers -> shared (per warp) -> one atomic per column per block
@@ -110,7 +110,7 @@ layernorm_bwd_ex_kernel(const void* __restrict__ x, int x_bf16, const float* __r
 
 // out[c] += sum_r x[r, c]
 __global__ void __launch_bounds__(kWarps * 32)
-colsum_kernel(const void* __restrict__ x, int x_bf16, float* __restrict__ out, long long rows, int C) {
+colsum_kernel(const void* __restrict__ x, int x_bf16, float* __restrict__ out, long long rows, int C, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   __shared__ float s_red[kWarps][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -121,7 +121,7 @@ colsum_kernel(const void* __restrict__ x, int x_bf16, float* __restrict__ out, l
   for (long long row = static_cast<long long>(blockIdx.y) * kWarps + warp; row < rows;
        row += static_cast<long long>(gridDim.y) * kWarps) {
     float v[8];
-    if (x_bf16) ld8bf(reinterpret_cast<const __nv_bfloat16*>(x) + row * C + c, v);
+    if (x_bf16) ld8h(reinterpret_cast<const __nv_bfloat16*>(x) + row * C + c, v, f16);
     else ld8f(reinterpret_cast<const float*>(x) + row * C + c, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += v[j];
@@ -161,7 +161,7 @@ avgpool_bwd_kernel(const float* __restrict__ dp, float* __restrict__ dx, int fra
 // dx[b, u, :] = sum_{j < k, (u - j) % s == 0, t = (u - j) / s < tout} dcol[b, t, j*C + :]
 __global__ void __launch_bounds__(256)
 col2im_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, int tin, int tout, int k, int s,
-              int C, long long total8) {
+              int C, long long total8, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total8) return;
@@ -179,11 +179,11 @@ col2im_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict_
     const int t = d / s;
     if (t >= tout) continue;
     float v[8];
-    ld8bf(dcol + ((b * tout + t) * k + j) * C + c, v);
+    ld8h(dcol + ((b * tout + t) * k + j) * C + c, v, f16);
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[q] += v[q];
   }
-  st8bf(dx + bu * C + c, acc);
+  st8h(dx + bu * C + c, acc, f16);
 }
 
 // ---- conv layer 0 backward ------------------------------------------------------------------------------------
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256)
 conv0_bwd_kernel(const float* __restrict__ wave, long long wave_stride, int samples, int frames, long long total_rows,
                  const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dW,
-                 float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                 float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, int f16) {
   extern __shared__ float sm0[];
   float* ws = sm0;                 // [kK0][kC0] transposed taps
   float* sd = ws + kK0 * kC0;      // [kTile0][kC0] d(pre-norm)
@@ -284,7 +284,7 @@ conv0_bwd_kernel(const float* __restrict__ wave, long long wave_stride, int samp
           float2 d = make_float2(0.f, 0.f);
           if (ok) {
             const uint32_t u = *reinterpret_cast<const uint32_t*>(dy + rows[tt] * kC0 + 64 * i + 2 * lane);
-            d = make_float2(bf16_lo(u), bf16_hi(u));
+            d = unpack_h16(u, f16);
           }
           const float xh0 = acc[tt][2 * i] * rstd, xh1 = acc[tt][2 * i + 1] * rstd;
           const float dz0 = d.x * gelu_erf_grad(fmaf(gm.x, xh0, bt.x));
@@ -357,7 +357,7 @@ conv0_bwd_kernel(const float* __restrict__ wave, long long wave_stride, int samp
 
 int layernorm_bwd_ex(const void* x, int x_bf16, const float* gamma, const float* beta, int act_gelu, float eps,
                      const void* dy, int dy_bf16, float* dh, int accumulate, void* dx_bf16, float* dgamma, float* dbeta,
-                     long long rows, int C, cudaStream_t stream) {
+                     long long rows, int C, int fmt, cudaStream_t stream) {
   B2S_REQUIRE(x && gamma && dy && dgamma && dbeta && (dh || dx_bf16), "layernorm_bwd_ex: null pointer");
   B2S_REQUIRE(!act_gelu || beta != nullptr, "layernorm_bwd_ex: the GELU variant needs beta");
   if (rows <= 0) return B2S_OK;
@@ -369,10 +369,10 @@ int layernorm_bwd_ex(const void* x, int x_bf16, const float* gamma, const float*
 #define B2S_LNBWD(G)                                                                                                  \
   if (act_gelu)                                                                                                       \
     layernorm_bwd_ex_kernel<G, true><<<grid, kWarps * 32, 0, stream>>>(x, x_bf16, gamma, beta, eps, dy, dy_bf16, dh,  \
-                                                                       accumulate, dxb, dgamma, dbeta, rows);        \
+                                                                       accumulate, dxb, dgamma, dbeta, rows, fmt);   \
   else                                                                                                                \
     layernorm_bwd_ex_kernel<G, false><<<grid, kWarps * 32, 0, stream>>>(x, x_bf16, gamma, beta, eps, dy, dy_bf16, dh, \
-                                                                        accumulate, dxb, dgamma, dbeta, rows);
+                                                                        accumulate, dxb, dgamma, dbeta, rows, fmt);
   switch (C) {
     case 256: B2S_LNBWD(1); break;
     case 512: B2S_LNBWD(2); break;
@@ -386,7 +386,7 @@ int layernorm_bwd_ex(const void* x, int x_bf16, const float* gamma, const float*
   return B2S_OK;
 }
 
-int colsum_accum(const void* x, int x_bf16, float* out, long long rows, int C, cudaStream_t stream) {
+int colsum_accum(const void* x, int x_bf16, float* out, long long rows, int C, int fmt, cudaStream_t stream) {
   B2S_REQUIRE(x && out, "colsum_accum: null pointer");
   B2S_REQUIRE(C % 256 == 0, "colsum_accum: C must be a multiple of 256");
   if (rows <= 0) return B2S_OK;
@@ -394,7 +394,7 @@ int colsum_accum(const void* x, int x_bf16, float* out, long long rows, int C, c
   const long long cap = (4LL * num_sms() + C / 256 - 1) / (C / 256);
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
-  colsum_kernel<<<dim3(C / 256, static_cast<unsigned>(chunks)), kWarps * 32, 0, stream>>>(x, x_bf16, out, rows, C);
+  colsum_kernel<<<dim3(C / 256, static_cast<unsigned>(chunks)), kWarps * 32, 0, stream>>>(x, x_bf16, out, rows, C, fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -410,21 +410,21 @@ int avgpool_bwd(const float* dpooled, float* dx, int batches, int frames, int C,
   return B2S_OK;
 }
 
-int col2im_add(const void* dcol_bf16, void* dx_bf16, int batches, int tin, int tout, int k, int s, int C,
+int col2im_add(const void* dcol_bf16, void* dx_bf16, int batches, int tin, int tout, int k, int s, int C, int fmt,
                cudaStream_t stream) {
   B2S_REQUIRE(dcol_bf16 && dx_bf16 && C % 8 == 0 && k > 0 && s > 0, "col2im_add: bad arguments");
   const long long total8 = static_cast<long long>(batches) * tin * (C / 8);
   if (total8 <= 0) return B2S_OK;
   col2im_kernel<<<static_cast<unsigned>((total8 + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dcol_bf16), reinterpret_cast<__nv_bfloat16*>(dx_bf16), tin, tout, k, s, C,
-      total8);
+      total8, fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 int conv0_bwd(const float* wave, long long wave_stride, int batches, int samples, const float* w, const float* bias,
               const float* gamma, const float* beta, float eps, const void* dy_bf16, int frames, float* dW, float* db,
-              float* dgamma, float* dbeta, cudaStream_t stream) {
+              float* dgamma, float* dbeta, int fmt, cudaStream_t stream) {
   B2S_REQUIRE(wave && w && bias && gamma && beta && dy_bf16 && dW && db && dgamma && dbeta, "conv0_bwd: null pointer");
   B2S_REQUIRE(frames == (samples - kK0) / kS0 + 1, "conv0_bwd: frames mismatch");
   const long long total = static_cast<long long>(batches) * frames;
@@ -438,7 +438,7 @@ int conv0_bwd(const float* wave, long long wave_stride, int batches, int samples
   if (blocks > cap) blocks = cap;
   conv0_bwd_kernel<<<static_cast<unsigned>(blocks), 256, kConv0BwdSmem, stream>>>(
       wave, wave_stride, samples, frames, total, w, bias, gamma, beta, eps,
-      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), dW, db, dgamma, dbeta);
+      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), dW, db, dgamma, dbeta, fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

@@ -44,7 +44,7 @@ constexpr int kDecWarps = 4;
 __global__ void __launch_bounds__(kDecWarps * 32)
 decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, long long ldq, __nv_bfloat16* __restrict__ cache,
                    const int* __restrict__ seq_start, const int* __restrict__ seq_len, __nv_bfloat16* __restrict__ o,
-                   int Hq, int Hkv, float scale_log2) {
+                   int Hq, int Hkv, float scale_log2, int f16) {
   constexpr int D = 128;
   __shared__ float s_m[kDecWarps], s_l[kDecWarps], s_acc[kDecWarps][D];
   pdl_launch_dependents();
@@ -66,22 +66,25 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, long long ldq, __nv_bf
   float qv[4];
   {
     const uint2 u = *reinterpret_cast<const uint2*>(qrow + h * D + lane * 4);
-    qv[0] = bf16_lo(u.x) * scale_log2; qv[1] = bf16_hi(u.x) * scale_log2;
-    qv[2] = bf16_lo(u.y) * scale_log2; qv[3] = bf16_hi(u.y) * scale_log2;
+    const float2 a = unpack_h16(u.x, f16), b2 = unpack_h16(u.y, f16);
+    qv[0] = a.x * scale_log2; qv[1] = a.y * scale_log2;
+    qv[2] = b2.x * scale_log2; qv[3] = b2.y * scale_log2;
   }
   float m = -INFINITY, l = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int j = warp; j <= n; j += kDecWarps) {
     const uint2 ku = j < n ? *reinterpret_cast<const uint2*>(kbase + j * ldkv) : knew;
     const uint2 vu = j < n ? *reinterpret_cast<const uint2*>(vbase + j * ldkv) : vnew;
-    float s = qv[0] * bf16_lo(ku.x) + qv[1] * bf16_hi(ku.x) + qv[2] * bf16_lo(ku.y) + qv[3] * bf16_hi(ku.y);
+    const float2 k0 = unpack_h16(ku.x, f16), k1 = unpack_h16(ku.y, f16);
+    const float2 v0 = unpack_h16(vu.x, f16), v1 = unpack_h16(vu.y, f16);
+    float s = qv[0] * k0.x + qv[1] * k0.y + qv[2] * k1.x + qv[3] * k1.y;
     s = warp_sum(s);
     const float mn = fmaxf(m, s);
     const float corr = exp2f(m - mn), p = exp2f(s - mn);
     l = l * corr + p;
-    acc[0] = acc[0] * corr + p * bf16_lo(vu.x);
-    acc[1] = acc[1] * corr + p * bf16_hi(vu.x);
-    acc[2] = acc[2] * corr + p * bf16_lo(vu.y);
-    acc[3] = acc[3] * corr + p * bf16_hi(vu.y);
+    acc[0] = acc[0] * corr + p * v0.x;
+    acc[1] = acc[1] * corr + p * v0.y;
+    acc[2] = acc[2] * corr + p * v1.x;
+    acc[3] = acc[3] * corr + p * v1.y;
     m = mn;
   }
   if (lane == 0) {
@@ -105,8 +108,8 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, long long ldq, __nv_bf
     }
     const float inv = 1.0f / ll;
     uint2 u;
-    u.x = pack_bf16(out[0] * inv, out[1] * inv);
-    u.y = pack_bf16(out[2] * inv, out[3] * inv);
+    u.x = pack_h16(out[0] * inv, out[1] * inv, f16);
+    u.y = pack_h16(out[2] * inv, out[3] * inv, f16);
     *reinterpret_cast<uint2*>(o + static_cast<long long>(b) * Hq * D + h * D + lane * 4) = u;
   }
 }
@@ -120,7 +123,20 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, long long ldq, __nv_bf
 enum GemvEpi : int { GV_BF16 = 0, GV_ACCUM_F32 = 1, GV_SWIGLU = 2, GV_ROPE = 3 };
 constexpr int kGvWarps = 8;
 
-__device__ __forceinline__ float dot8(const uint4& w, const uint4& x) {
+__device__ __forceinline__ float dot8_f16(const uint4& w, const uint4& x) {
+  const float2 w0 = unpack_f16(w.x), w1 = unpack_f16(w.y), w2 = unpack_f16(w.z), w3 = unpack_f16(w.w);
+  const float2 x0 = unpack_f16(x.x), x1 = unpack_f16(x.y), x2 = unpack_f16(x.z), x3 = unpack_f16(x.w);
+  float s = w0.x * x0.x;
+  s = fmaf(w0.y, x0.y, s);
+  s = fmaf(w1.x, x1.x, s);
+  s = fmaf(w1.y, x1.y, s);
+  s = fmaf(w2.x, x2.x, s);
+  s = fmaf(w2.y, x2.y, s);
+  s = fmaf(w3.x, x3.x, s);
+  s = fmaf(w3.y, x3.y, s);
+  return s;
+}
+__device__ __forceinline__ float dot8_bf16(const uint4& w, const uint4& x) {
   float s = bf16_lo(w.x) * bf16_lo(x.x);
   s = fmaf(bf16_hi(w.x), bf16_hi(x.x), s);
   s = fmaf(bf16_lo(w.y), bf16_lo(x.y), s);
@@ -132,11 +148,13 @@ __device__ __forceinline__ float dot8(const uint4& w, const uint4& x) {
   return s;
 }
 
-template <int NB, bool PAIRED>
+// F16: operand format of x / W (compile-time: the dot product is the hot loop); out_f16: format of 16-bit outputs
+template <int NB, bool PAIRED, bool F16>
 __global__ void __launch_bounds__(kGvWarps * 32, 2)
-gemv_bf16_kernel(const void* __restrict__ x, const float* __restrict__ norm_w, float norm_eps,
-                 const __nv_bfloat16* __restrict__ W, int B, int N, int K, int epi, void* out, long long ldo,
-                 const float* __restrict__ rope_cs, const int* __restrict__ positions, int rope_cols) {
+gemv_h16_kernel(const void* __restrict__ x, const float* __restrict__ norm_w, float norm_eps,
+                const __nv_bfloat16* __restrict__ W, int B, int N, int K, int epi, void* out, long long ldo,
+                const float* __restrict__ rope_cs, const int* __restrict__ positions, int rope_cols, int out_f16) {
+  auto dot8 = [](const uint4& w, const uint4& xv) { return F16 ? dot8_f16(w, xv) : dot8_bf16(w, xv); };
   extern __shared__ uint4 sx[];  // [NB][K / 8] bf16 activations
   __shared__ float s_part[NB][kGvWarps];
   pdl_launch_dependents();  // the next kernel may start prefetching ITS weights while this one runs
@@ -192,10 +210,10 @@ gemv_bf16_kernel(const void* __restrict__ x, const float* __restrict__ norm_w, f
           float v[8], wt[8];
           ld8f(xf + static_cast<long long>(b) * K + c * 8, v);
           ld8f(norm_w + c * 8, wt);
-          pk.x = pack_bf16(wt[0] * (v[0] * rstd), wt[1] * (v[1] * rstd));
-          pk.y = pack_bf16(wt[2] * (v[2] * rstd), wt[3] * (v[3] * rstd));
-          pk.z = pack_bf16(wt[4] * (v[4] * rstd), wt[5] * (v[5] * rstd));
-          pk.w = pack_bf16(wt[6] * (v[6] * rstd), wt[7] * (v[7] * rstd));
+          pk.x = pack_h16(wt[0] * (v[0] * rstd), wt[1] * (v[1] * rstd), F16);
+          pk.y = pack_h16(wt[2] * (v[2] * rstd), wt[3] * (v[3] * rstd), F16);
+          pk.z = pack_h16(wt[4] * (v[4] * rstd), wt[5] * (v[5] * rstd), F16);
+          pk.w = pack_h16(wt[6] * (v[6] * rstd), wt[7] * (v[7] * rstd), F16);
         }
         sx[b * k8 + c] = pk;
       }
@@ -249,11 +267,11 @@ gemv_bf16_kernel(const void* __restrict__ x, const float* __restrict__ norm_w, f
     if (lane < B) {
       const long long row = static_cast<long long>(lane) * ldo;
       if (epi == GV_BF16) {
-        reinterpret_cast<__nv_bfloat16*>(out)[row + n0] = __float2bfloat16(v0);
+        reinterpret_cast<uint16_t*>(out)[row + n0] = float_to_h16(v0, out_f16);
       } else if (epi == GV_ACCUM_F32) {
         reinterpret_cast<float*>(out)[row + n0] += v0;
       } else if (epi == GV_SWIGLU) {
-        reinterpret_cast<__nv_bfloat16*>(out)[row + (u >> 6) * 64 + (u & 63)] = __float2bfloat16(silu(v0) * v1);
+        reinterpret_cast<uint16_t*>(out)[row + (u >> 6) * 64 + (u & 63)] = float_to_h16(silu(v0) * v1, out_f16);
       } else {  // GV_ROPE: rotate-half pair (d, d + 64) of a 128-wide head
         float lo = v0, hi = v1;
         if (n0 < rope_cols) {
@@ -262,8 +280,8 @@ gemv_bf16_kernel(const void* __restrict__ x, const float* __restrict__ norm_w, f
           lo = v0 * cc - v1 * sn;
           hi = v1 * cc + v0 * sn;
         }
-        reinterpret_cast<__nv_bfloat16*>(out)[row + n0] = __float2bfloat16(lo);
-        reinterpret_cast<__nv_bfloat16*>(out)[row + n0 + 64] = __float2bfloat16(hi);
+        reinterpret_cast<uint16_t*>(out)[row + n0] = float_to_h16(lo, out_f16);
+        reinterpret_cast<uint16_t*>(out)[row + n0 + 64] = float_to_h16(hi, out_f16);
       }
     }
   }
@@ -287,11 +305,11 @@ int launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t strea
   return B2S_OK;
 }
 
-template <int NB, bool PAIRED>
+template <int NB, bool PAIRED, bool F16>
 int launch_gemv(const void* x, const float* norm_w, float norm_eps, const void* W, int B, int N, int K, int epi,
-                void* out, long long ldo, const float* rope_cs, const int* positions, int rope_cols,
+                void* out, long long ldo, const float* rope_cs, const int* positions, int rope_cols, int out_f16,
                 cudaStream_t stream) {
-  auto kern = gemv_bf16_kernel<NB, PAIRED>;
+  auto kern = gemv_h16_kernel<NB, PAIRED, F16>;
   const int smem = NB * K * 2;
   static int attr_smem = 0;
   if (smem > attr_smem) {
@@ -303,7 +321,7 @@ int launch_gemv(const void* x, const float* norm_w, float norm_eps, const void* 
   const int cap = 4 * num_sms();
   if (blocks > cap) blocks = cap;
   return launch_pdl(kern, dim3(blocks), dim3(kGvWarps * 32), static_cast<size_t>(smem), stream, x, norm_w, norm_eps,
-                    reinterpret_cast<const __nv_bfloat16*>(W), B, N, K, epi, out, ldo, rope_cs, positions, rope_cols);
+                    reinterpret_cast<const __nv_bfloat16*>(W), B, N, K, epi, out, ldo, rope_cs, positions, rope_cols, out_f16);
 }
 
 struct Carve {
@@ -361,24 +379,25 @@ GemmArgs lin(const void* A, const void* W, long long M, int N, int K) {
 
 }  // namespace
 
-// x: bf16 [B <= 4, K] (norm_w == nullptr) or the fp32 residual stream [B, K] with RMSNorm(norm_w, eps) fused into the
-// staging; W bf16 [N, K]; see GemvEpi
-int gemv_bf16(const void* x, const float* norm_w, float norm_eps, const void* W, int B, int N, int K, int epi, void* out,
-              long long ldo, const float* rope_cs, const int* positions, int rope_cols, cudaStream_t stream) {
+// x: 16-bit [B <= 4, K] in format fmt (norm_w == nullptr) or the fp32 residual stream [B, K] with RMSNorm(norm_w, eps)
+// fused into the staging; W 16-bit [N, K] in fmt; 16-bit outputs in out_fmt; see GemvEpi
+int gemv_h16(const void* x, const float* norm_w, float norm_eps, const void* W, int B, int N, int K, int epi, void* out,
+             long long ldo, const float* rope_cs, const int* positions, int rope_cols, int fmt, int out_fmt,
+             cudaStream_t stream) {
   B2S_REQUIRE(x && W && out && B >= 1 && B <= 4, "gemv: needs 1..4 rows");
   B2S_REQUIRE(K % 8 == 0 && K * 2 * 4 <= 200 * 1024, "gemv: K must be a multiple of 8 and fit shared memory");
   const bool paired = epi == GV_SWIGLU || epi == GV_ROPE;
   if (paired) B2S_REQUIRE(N % 128 == 0, "gemv: paired epilogues need N %% 128 == 0");
   if (epi == GV_ROPE) B2S_REQUIRE(rope_cs && positions, "gemv: rope epilogue needs tables");
-#define B2S_GEMV(NB)                                                                                                   \
-  return paired ? launch_gemv<NB, true>(x, norm_w, norm_eps, W, B, N, K, epi, out, ldo, rope_cs, positions, rope_cols, \
-                                        stream)                                                                        \
-                : launch_gemv<NB, false>(x, norm_w, norm_eps, W, B, N, K, epi, out, ldo, rope_cs, positions, rope_cols, \
-                                         stream)
+#define B2S_GEMV_ARGS x, norm_w, norm_eps, W, B, N, K, epi, out, ldo, rope_cs, positions, rope_cols, out_fmt, stream
+#define B2S_GEMV(NB)                                                                                    \
+  if (fmt != 0) return paired ? launch_gemv<NB, true, true>(B2S_GEMV_ARGS) : launch_gemv<NB, false, true>(B2S_GEMV_ARGS); \
+  return paired ? launch_gemv<NB, true, false>(B2S_GEMV_ARGS) : launch_gemv<NB, false, false>(B2S_GEMV_ARGS)
   if (B == 1) { B2S_GEMV(1); }
   if (B == 2) { B2S_GEMV(2); }
   B2S_GEMV(4);
 #undef B2S_GEMV
+#undef B2S_GEMV_ARGS
 }
 
 size_t llama_kv_cache_bytes(const b2s_llama_weights* w, int slots) {
@@ -417,27 +436,28 @@ int llama_decode_step(const b2s_llama_weights* w, const void* embed_table, const
   plan_dec(w, batch, workspace, workspace_bytes, &p);
   B2S_REQUIRE(p.bytes <= workspace_bytes, "llama_decode_step: workspace too small: need %zu bytes, got %zu", p.bytes,
               workspace_bytes);
-  const int B = batch, H = w->hidden, D = w->head_dim, Hq = w->heads, Hkv = w->kv_heads, F = w->ffn;
+  const int B = batch, H = w->hidden, D = w->head_dim, Hq = w->heads, Hkv = w->kv_heads, F = w->ffn, fmt = w->fmt;
   const int qkv_cols = (Hq + 2 * Hkv) * D, width = 2 * Hkv * D;
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(D));
 
-  RC(embed_splice_fwd(embed_table, nullptr, token_ids, p.h, B, H, stream));
+  RC(embed_splice_fwd(embed_table, nullptr, token_ids, p.h, B, H, fmt, stream));
   const bool gv = B <= 4;  // weight-streaming GEMV path (RMSNorm fused into its staging, PDL-chained launches)
   for (int l = 0; l < w->num_layers; ++l) {
     const b2s_llama_layer& L = w->layers[l];
     __nv_bfloat16* cache = reinterpret_cast<__nv_bfloat16*>(kv_cache) + static_cast<size_t>(l) * kv_slots * width;
     if (gv) {
-      RC(gemv_bf16(p.h, L.ln1_w, w->rms_eps, L.wqkv, B, qkv_cols, H, GV_ROPE, p.qkv, qkv_cols, w->rope_cs, seq_len,
-                   (Hq + Hkv) * D, stream));
+      RC(gemv_h16(p.h, L.ln1_w, w->rms_eps, L.wqkv, B, qkv_cols, H, GV_ROPE, p.qkv, qkv_cols, w->rope_cs, seq_len,
+                  (Hq + Hkv) * D, fmt, fmt, stream));
       RC(launch_pdl(decode_attn_kernel, dim3(B, Hq), dim3(kDecWarps * 32), 0, stream,
                     reinterpret_cast<const __nv_bfloat16*>(p.qkv), static_cast<long long>(qkv_cols), cache, seq_start,
-                    seq_len, reinterpret_cast<__nv_bfloat16*>(p.ao), Hq, Hkv, scale_log2));
-      RC(gemv_bf16(p.ao, nullptr, 0.f, L.wo, B, H, Hq * D, GV_ACCUM_F32, p.h, H, nullptr, nullptr, 0, stream));
-      RC(gemv_bf16(p.h, L.ln2_w, w->rms_eps, L.wgu, B, 2 * F, H, GV_SWIGLU, p.act, F, nullptr, nullptr, 0, stream));
-      RC(gemv_bf16(p.act, nullptr, 0.f, L.wd, B, H, F, GV_ACCUM_F32, p.h, H, nullptr, nullptr, 0, stream));
+                    seq_len, reinterpret_cast<__nv_bfloat16*>(p.ao), Hq, Hkv, scale_log2, fmt));
+      RC(gemv_h16(p.ao, nullptr, 0.f, L.wo, B, H, Hq * D, GV_ACCUM_F32, p.h, H, nullptr, nullptr, 0, fmt, fmt, stream));
+      RC(gemv_h16(p.h, L.ln2_w, w->rms_eps, L.wgu, B, 2 * F, H, GV_SWIGLU, p.act, F, nullptr, nullptr, 0, fmt, fmt,
+                  stream));
+      RC(gemv_h16(p.act, nullptr, 0.f, L.wd, B, H, F, GV_ACCUM_F32, p.h, H, nullptr, nullptr, 0, fmt, fmt, stream));
       continue;
     }
-    RC(rmsnorm_fwd(p.h, L.ln1_w, w->rms_eps, p.xn, B, H, stream));
+    RC(rmsnorm_fwd(p.h, L.ln1_w, w->rms_eps, p.xn, B, H, fmt, stream));
     {
       GemmArgs g = lin(p.xn, L.wqkv, B, qkv_cols, H);
       g.epi = EPI_ROPE;
@@ -447,20 +467,20 @@ int llama_decode_step(const b2s_llama_weights* w, const void* embed_table, const
       g.rope_cols = (Hq + Hkv) * D;
       g.block_n = 128;
       g.cta_group = 1;
-      RC(gemm_bf16_launch(g, stream));
+      RC(gemm_launch_fmt(g, fmt, stream));
     }
     decode_attn_kernel<<<dim3(B, Hq), kDecWarps * 32, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(p.qkv), qkv_cols, cache, seq_start, seq_len,
-        reinterpret_cast<__nv_bfloat16*>(p.ao), Hq, Hkv, scale_log2);
+        reinterpret_cast<__nv_bfloat16*>(p.ao), Hq, Hkv, scale_log2, fmt);
     B2S_LAUNCH_CHECK();
     {
       GemmArgs g = lin(p.ao, L.wo, B, H, Hq * D);
       g.epi = EPI_ACCUM_F32;  // h += ao . Wo^T, split-K over the whole chip
       g.out = p.h;
       g.cta_group = 1;
-      RC(gemm_bf16_launch(g, stream));
+      RC(gemm_launch_fmt(g, fmt, stream));
     }
-    RC(rmsnorm_fwd(p.h, L.ln2_w, w->rms_eps, p.xn, B, H, stream));
+    RC(rmsnorm_fwd(p.h, L.ln2_w, w->rms_eps, p.xn, B, H, fmt, stream));
     {
       GemmArgs g = lin(p.xn, L.wgu, B, 2 * F, H);
       g.epi = EPI_SWIGLU;
@@ -468,25 +488,27 @@ int llama_decode_step(const b2s_llama_weights* w, const void* embed_table, const
       g.ldo = F;
       g.block_n = 128;
       g.cta_group = 1;
-      RC(gemm_bf16_launch(g, stream));
+      RC(gemm_launch_fmt(g, fmt, stream));
     }
     {
       GemmArgs g = lin(p.act, L.wd, B, H, F);
       g.epi = EPI_ACCUM_F32;
       g.out = p.h;
       g.cta_group = 1;
-      RC(gemm_bf16_launch(g, stream));
+      RC(gemm_launch_fmt(g, fmt, stream));
     }
   }
   if (gv) {
-    RC(gemv_bf16(p.h, w->final_norm_w, w->rms_eps, w->lm_head, B, w->vocab, H, GV_BF16, logits_bf16, w->vocab, nullptr,
-                 nullptr, 0, stream));
+    RC(gemv_h16(p.h, w->final_norm_w, w->rms_eps, w->lm_head, B, w->vocab, H, GV_BF16, logits_bf16, w->vocab, nullptr,
+                nullptr, 0, fmt, 0 /* logits stay bf16 */, stream));
   } else {
-    RC(rmsnorm_fwd(p.h, w->final_norm_w, w->rms_eps, p.xn, B, H, stream));
+    RC(rmsnorm_fwd(p.h, w->final_norm_w, w->rms_eps, p.xn, B, H, fmt, stream));
     GemmArgs g = lin(p.xn, w->lm_head, B, w->vocab, H);
     g.epi = EPI_BF16;
     g.out = logits_bf16;
     g.cta_group = 1;
+    g.a_fmt = g.w_fmt = fmt;
+    g.out_fmt = 0;  // logits stay bf16
     RC(gemm_bf16_launch(g, stream));
   }
   return B2S_OK;

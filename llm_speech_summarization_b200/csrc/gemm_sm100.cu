@@ -91,6 +91,8 @@ struct KParams {
   uint32_t drop_k1, drop_k2, drop_thresh;  // fused dropout (rng.cuh); thresh 0 = off
   float drop_inv_keep;
   int resid_red;  // in-place residual adds go through red.global.add (B2S_RESID_RED=0 keeps load + add + store, A/B)
+  uint32_t idesc_fmt;  // a_format / b_format bits of the instruction descriptor (bf16 = 1, fp16 = 0; may differ)
+  int out_f16;         // 16-bit outputs (out for the *_BF16-class epilogues, out2) are written as fp16 instead of bf16
 };
 
 struct TileCoord {
@@ -238,17 +240,29 @@ __device__ __forceinline__ void emit_accum_f32(uint32_t stg, const float (&v)[32
   __syncwarp();
 }
 
-__device__ __forceinline__ void emit_bf16(uint32_t stg, const float (&v)[32], int lane, __nv_bfloat16* out0,
-                                          long long ld, int rows_valid, int cols_valid) {
-  // rows are packed to bf16 BEFORE staging (64 B per row, half the shared-memory traffic of the fp32 tile);
+__device__ __forceinline__ void emit_h16(uint32_t stg, const float (&v)[32], int lane, __nv_bfloat16* out0,
+                                         long long ld, int rows_valid, int cols_valid, int f16) {
+  // rows are packed to bf16 / fp16 BEFORE staging (64 B per row, half the shared-memory traffic of the fp32 tile);
   // 16-byte chunk q of row r sits at chunk position q ^ ((r >> 1) & 3): conflict-free both ways.
+  // (f16 is CTA-uniform: one of the two conversion sequences runs, nothing is selected per element)
+  if (f16) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t addr = stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16(v[8 * q], v[8 * q + 1])),
-                 "r"(pack_bf16(v[8 * q + 2], v[8 * q + 3])), "r"(pack_bf16(v[8 * q + 4], v[8 * q + 5])),
-                 "r"(pack_bf16(v[8 * q + 6], v[8 * q + 7]))
-                 : "memory");
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t addr = stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_f16(v[8 * q], v[8 * q + 1])),
+                   "r"(pack_f16(v[8 * q + 2], v[8 * q + 3])), "r"(pack_f16(v[8 * q + 4], v[8 * q + 5])),
+                   "r"(pack_f16(v[8 * q + 6], v[8 * q + 7]))
+                   : "memory");
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t addr = stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16(v[8 * q], v[8 * q + 1])),
+                   "r"(pack_bf16(v[8 * q + 2], v[8 * q + 3])), "r"(pack_bf16(v[8 * q + 4], v[8 * q + 5])),
+                   "r"(pack_bf16(v[8 * q + 6], v[8 * q + 7]))
+                   : "memory");
+    }
   }
   __syncwarp();
   const int j = lane & 3;
@@ -402,8 +416,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else if (warp == 1 && lane == 0 && cta_rank == 0) {
     // ============================== MMA issuer ==============================
     constexpr bool a_mn = kAmn, b_mn = kBmn;
-    constexpr uint32_t idesc =
-        ptx::make_idesc_bf16_f32(128 * CG, BN) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
+    const uint32_t idesc =
+        ptx::make_idesc_f32acc(128 * CG, BN) | p.idesc_fmt | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
     // K step of 16 inside a stage: K-major = 32 bytes along the swizzled row; MN-major = 16 rows of 128 bytes
     constexpr uint32_t a_kstep = a_mn ? (2048u >> 4) : 2u;
     constexpr uint32_t b_kstep = b_mn ? (2048u >> 4) : 2u;
@@ -498,9 +512,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const int valid = min(32, p.N - col);
           if (EXT && out2 != nullptr) {  // training: keep the pre-activation (acc + bias) for the backward
             add_bias_act(v, bias ? bias + col : nullptr, ACT_NONE);
-            emit_bf16(stg, v, lane,
+            emit_h16(stg, v, lane,
                       reinterpret_cast<__nv_bfloat16*>(out2) + orow0 * p.ld2 + static_cast<long long>(tc.g) * og_cols + col,
-                      p.ld2, rows_valid, valid);
+                      p.ld2, rows_valid, valid, p.out_f16);
             add_bias_act(v, nullptr, p.act);
           } else {
             add_bias_act(v, bias ? bias + col : nullptr, p.act);
@@ -513,7 +527,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               v[i] = rng_keep(e0 + i, p.drop_k1, p.drop_k2, p.drop_thresh) ? v[i] * p.drop_inv_keep : 0.f;
           }
           if (p.epi == EPI_BF16) {
-            emit_bf16(stg, v, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, valid);
+            emit_h16(stg, v, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, valid, p.out_f16);
           } else if ((EXT && p.epi == EPI_ACCUM_F32) || resid_inplace) {
             emit_accum_f32(stg, v, lane, reinterpret_cast<float*>(p.out) + off0, p.ldo, rows_valid, valid);
           } else if (has_resid) {
@@ -550,13 +564,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               if (EXT && out2 != nullptr) {  // training: raw gate | up (the GEMM's natural [M, N] layout)
                 __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(out2) + orow0 * p.ld2 +
                                      static_cast<long long>(tc.g) * p.N + bcol + c * 32;
-                emit_bf16(stg, lo, lane, raw, p.ld2, rows_valid, 32);
-                emit_bf16(stg, hi, lane, raw + 64, p.ld2, rows_valid, 32);
+                emit_h16(stg, lo, lane, raw, p.ld2, rows_valid, 32, p.out_f16);
+                emit_h16(stg, hi, lane, raw + 64, p.ld2, rows_valid, 32, p.out_f16);
               }
 #pragma unroll
               for (int i = 0; i < 32; ++i) lo[i] = silu(lo[i]) * hi[i];
               const long long off0 = orow0 * p.ldo + (static_cast<long long>(tc.g) * p.N + bcol) / 2 + c * 32;
-              emit_bf16(stg, lo, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, 32);
+              emit_h16(stg, lo, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, 32, p.out_f16);
             } else {  // EPI_ROPE
               if (bcol < p.rope_cols && row_ok) {
                 const float* cs = p.rope_cs + static_cast<long long>(pos) * 128 + c * 32;
@@ -575,8 +589,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
               }
               const long long off0 = orow0 * p.ldo + static_cast<long long>(tc.g) * p.N + bcol + c * 32;
-              emit_bf16(stg, lo, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, 32);
-              emit_bf16(stg, hi, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0 + 64, p.ldo, rows_valid, 32);
+              emit_h16(stg, lo, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0, p.ldo, rows_valid, 32, p.out_f16);
+              emit_h16(stg, hi, lane, reinterpret_cast<__nv_bfloat16*>(p.out) + off0 + 64, p.ldo, rows_valid, 32, p.out_f16);
             }
           }
         }
@@ -749,6 +763,9 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
                   (reinterpret_cast<uintptr_t>(a.out) & 15) == 0,
               "gemm: pointers must be 16-byte aligned");
   B2S_REQUIRE(a.epi >= EPI_BF16 && a.epi <= EPI_ACCUM_F32, "gemm: bad epilogue id %d", a.epi);
+  // tcgen05 kind::f16 does encode a_format / b_format separately, but a bf16 x fp16 pair traps with an illegal
+  // instruction on B200 (measured, round 2): both operands must share one 16-bit format
+  B2S_REQUIRE((a.a_fmt != 0) == (a.w_fmt != 0), "gemm: A and W must share one 16-bit format (bf16 or fp16)");
   const bool mn = a.a_mn || a.b_mn;
   if (mn) {
     B2S_REQUIRE(a.taps == 1 && (a.epi == EPI_BF16 || a.epi == EPI_F32 || a.epi == EPI_ACCUM_F32 || a.epi == EPI_RESID_F32),
@@ -850,6 +867,8 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   p.rope_cols = a.rope_cols;
   static const int resid_red = getenv("B2S_RESID_RED") ? atoi(getenv("B2S_RESID_RED")) : 1;
   p.resid_red = resid_red;
+  p.idesc_fmt = ptx::idesc_formats(a.a_fmt != 0, a.w_fmt != 0);
+  p.out_f16 = a.out_fmt != 0 ? 1 : 0;
   p.drop_k1 = a.drop_k1;
   p.drop_k2 = a.drop_k2;
   p.drop_thresh = a.drop_thresh;

@@ -77,9 +77,17 @@ struct GemmArgs {
   // Element index = output_row * ldo + output_col. drop_thresh == 0: off. out2 keeps the un-dropped pre-activation.
   unsigned drop_k1, drop_k2, drop_thresh;
   float drop_inv_keep;
+  // ---- 16-bit storage formats (B2S_FMT_BF16 = 0 / B2S_FMT_F16 = 1): A, W and the 16-bit outputs (out, out2).
+  // A and W must agree (a mixed bf16 x fp16 tcgen05.mma traps on B200); the output format is free.
+  int a_fmt, w_fmt, out_fmt;
 };
 
 int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream);
+// the common case: operands and 16-bit outputs all in `fmt`
+inline int gemm_launch_fmt(GemmArgs g, int fmt, cudaStream_t stream) {
+  g.a_fmt = g.w_fmt = g.out_fmt = fmt;
+  return gemm_bf16_launch(g, stream);
+}
 void gemm_timing_enable(int on);
 int gemm_timing_read(double* total_ms, long long* launches);
 int gemm_timing_get(long long index, double* ms, int* shape /* [10] */);

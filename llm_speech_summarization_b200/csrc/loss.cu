@@ -234,11 +234,14 @@ __global__ void __launch_bounds__(kLossThreads)
 kd_ce_bwd_kernel(const __nv_bfloat16* __restrict__ S, const __nv_bfloat16* __restrict__ T, long long lds,
                  long long ldt, int V, const int* __restrict__ labels, const float* __restrict__ lse_s,
                  const float* __restrict__ lse_t, const float* __restrict__ coef_kd,
-                 const float* __restrict__ coef_ce, __nv_bfloat16* __restrict__ dS, long long ldd) {
+                 const float* __restrict__ coef_ce, const float* __restrict__ loss_scale,
+                 __nv_bfloat16* __restrict__ dS, long long ldd, int f16) {
   const int row = blockIdx.y;
   const int c0 = blockIdx.x * kChunkCols;
   const int c1 = min(V, c0 + kChunkCols);
-  const float ck = coef_kd[row], cc = coef_ce[row];
+  // the gradient enters the backward pass here: the dynamic loss scale (GradScaler, REF/trainer.py:374) multiplies it once
+  const float ls = loss_scale != nullptr ? *loss_scale : 1.0f;
+  const float ck = coef_kd[row] * ls, cc = coef_ce[row] * ls;
   const float ls2 = lse_s[row] * kLog2e, lt2 = lse_t[row] * kLog2e;
   const int lab = labels[row];
   const uint4* sv = reinterpret_cast<const uint4*>(S + static_cast<long long>(row) * lds + c0);
@@ -272,12 +275,7 @@ kd_ce_bwd_kernel(const __nv_bfloat16* __restrict__ S, const __nv_bfloat16* __res
           g[j] = cs * ps - ck * pt;
           if (col + j == lab) g[j] -= cc;
         }
-        uint4 o;
-        o.x = pack_bf16(g[0], g[1]);
-        o.y = pack_bf16(g[2], g[3]);
-        o.z = pack_bf16(g[4], g[5]);
-        o.w = pack_bf16(g[6], g[7]);
-        st_stream_u4(dv + i, o);
+        st_stream_u4(dv + i, pack8_h16(g, f16));
       }
     }
   }
@@ -330,8 +328,8 @@ int kd_ce_loss_fwd(const void* S, const void* T, long long lds, long long ldt, i
 }
 
 int kd_ce_loss_bwd(const void* S, const void* T, long long lds, long long ldt, int rows, int V, const int* labels,
-                   const float* lse_s, const float* lse_t, const float* coef_kd, const float* coef_ce, void* dS,
-                   long long ldd, cudaStream_t stream) {
+                   const float* lse_s, const float* lse_t, const float* coef_kd, const float* coef_ce,
+                   const float* loss_scale, void* dS, long long ldd, int fmt, cudaStream_t stream) {
   B2S_REQUIRE(S && T && labels && lse_s && lse_t && coef_kd && coef_ce && dS, "kd_ce_loss_bwd: null pointer");
   B2S_REQUIRE(V > 0 && V % 8 == 0 && lds % 8 == 0 && ldt % 8 == 0 && ldd % 8 == 0,
               "kd_ce_loss_bwd: V/ld must be multiples of 8");
@@ -340,7 +338,7 @@ int kd_ce_loss_bwd(const void* S, const void* T, long long lds, long long ldt, i
   dim3 grid(chunks, rows);
   kd_ce_bwd_kernel<<<grid, kLossThreads, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(S), reinterpret_cast<const __nv_bfloat16*>(T), lds, ldt, V, labels,
-      lse_s, lse_t, coef_kd, coef_ce, reinterpret_cast<__nv_bfloat16*>(dS), ldd);
+      lse_s, lse_t, coef_kd, coef_ce, loss_scale, reinterpret_cast<__nv_bfloat16*>(dS), ldd, fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

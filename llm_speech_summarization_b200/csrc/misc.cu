@@ -22,7 +22,7 @@ constexpr int kConv0TT = 4;  // time steps per warp iteration
 __global__ void __launch_bounds__(256)
 conv0_ln_gelu_kernel(const float* __restrict__ wave, long long wave_stride, int samples, const float* __restrict__ w,
                      const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     float eps, __nv_bfloat16* __restrict__ y, int out_frames) {
+                     float eps, __nv_bfloat16* __restrict__ y, int out_frames, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   __shared__ float ws[kConv0K][kConv0Out];  // transposed taps: ws[j][c]
   for (int i = threadIdx.x; i < kConv0K * kConv0Out; i += blockDim.x) {
@@ -87,7 +87,7 @@ conv0_ln_gelu_kernel(const float* __restrict__ wave, long long wave_stride, int 
         const float2 bt = *reinterpret_cast<const float2*>(beta + 64 * i + 2 * lane);
         const float o0 = gelu_erf((acc[tt][2 * i] - mean) * rstd * gm.x + bt.x);
         const float o1 = gelu_erf((acc[tt][2 * i + 1] - mean) * rstd * gm.y + bt.y);
-        *reinterpret_cast<uint32_t*>(yo + 64 * i + 2 * lane) = pack_bf16(o0, o1);
+        *reinterpret_cast<uint32_t*>(yo + 64 * i + 2 * lane) = pack_h16(o0, o1, f16);
       }
     }
   }
@@ -96,7 +96,7 @@ conv0_ln_gelu_kernel(const float* __restrict__ wave, long long wave_stride, int 
 // one warp per output row; C % 256 == 0
 __global__ void __launch_bounds__(256)
 embed_splice_kernel(const __nv_bfloat16* __restrict__ table, const float* __restrict__ audio,
-                    const int* __restrict__ row_src, float* __restrict__ h0, long long rows, int C) {
+                    const int* __restrict__ row_src, float* __restrict__ h0, long long rows, int C, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -108,11 +108,10 @@ embed_splice_kernel(const __nv_bfloat16* __restrict__ table, const float* __rest
   } else if (src >= 0) {
     const uint4* s = reinterpret_cast<const uint4*>(table + static_cast<long long>(src) * C);
     for (int i = lane; i < C / 8; i += 32) {
-      const uint4 u = __ldg(s + i);
-      float4 a = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
-      float4 b = make_float4(bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w));
-      reinterpret_cast<float4*>(dst)[2 * i] = a;
-      reinterpret_cast<float4*>(dst)[2 * i + 1] = b;
+      float f[8];
+      unpack8_h16(__ldg(s + i), f, f16);
+      reinterpret_cast<float4*>(dst)[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+      reinterpret_cast<float4*>(dst)[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
     }
   } else {
     const float4* s = reinterpret_cast<const float4*>(audio + static_cast<long long>(-(src + 1)) * C);
@@ -140,8 +139,8 @@ rowpair_sqdiff_kernel(const float* __restrict__ h, const int* __restrict__ rows_
 
 // one CTA per tap k: norm over (co, ci) of v[:, :, k], then scaled bf16 write to [co][k][ci]
 __global__ void __launch_bounds__(256)
-posconv_weight_pack_kernel(const float* __restrict__ g, const float* __restrict__ v, __nv_bfloat16* __restrict__ wp,
-                           int cout, int cin_g, int K) {
+posconv_weight_pack_kernel(const float* __restrict__ g, const float* __restrict__ v, uint16_t* __restrict__ wp,
+                           int cout, int cin_g, int K, int f16) {
   const int k = blockIdx.x;
   const long long n = static_cast<long long>(cout) * cin_g;
   float s = 0.f;
@@ -163,14 +162,14 @@ posconv_weight_pack_kernel(const float* __restrict__ g, const float* __restrict_
   const float scale = scale_sh;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
     const long long co = i / cin_g, ci = i - co * cin_g;
-    wp[(co * K + k) * cin_g + ci] = __float2bfloat16(v[i * K + k] * scale);
+    wp[(co * K + k) * cin_g + ci] = float_to_h16(v[i * K + k] * scale, f16);
   }
 }
 
 // log-mel (B, C, T) fp32 -> channels-last bf16 (B, T + 2, C) with a zero row before and after each utterance
 // (the zero padding of Whisper's conv1/conv2, TF/models/whisper/modeling_whisper.py:566-567)
-__global__ void mel_to_padded_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C,
-                                        int T) {
+__global__ void mel_to_padded_cl_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, int B, int C, int T,
+                                        int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * (T + 2) * C;
@@ -181,50 +180,50 @@ __global__ void mel_to_padded_cl_kernel(const float* __restrict__ x, __nv_bfloat
   const int b = static_cast<int>(r / (T + 2));
   float v = 0.f;
   if (tp >= 1 && tp <= T) v = x[(static_cast<long long>(b) * C + c) * T + (tp - 1)];
-  y[i] = __float2bfloat16(v);
+  y[i] = float_to_h16(v, f16);
 }
 
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+__global__ void cast_f32_h16_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, long long n, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(x + i);
     uint2 u;
-    u.x = pack_bf16(v.x, v.y);
-    u.y = pack_bf16(v.z, v.w);
+    u.x = pack_h16(v.x, v.y, f16);
+    u.y = pack_h16(v.z, v.w, f16);
     *reinterpret_cast<uint2*>(y + i) = u;
   } else {
-    for (long long j = i; j < n; ++j) y[j] = __float2bfloat16(x[j]);
+    for (long long j = i; j < n; ++j) y[j] = float_to_h16(x[j], f16);
   }
 }
 
-__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+__global__ void cast_h16_f32_kernel(const uint16_t* __restrict__ x, float* __restrict__ y, long long n, int f16) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = __bfloat162float(x[i]);
+  if (i < n) y[i] = h16_to_float(x[i], f16);
 }
 
 }  // namespace
 
 int conv0_ln_gelu_fwd(const float* wave, long long wave_stride, int batches, int samples, const float* w,
                       const float* bias, const float* gamma, const float* beta, float eps, void* y_bf16, int out_frames,
-                      cudaStream_t stream) {
+                      int fmt, cudaStream_t stream) {
   B2S_REQUIRE(wave && w && bias && gamma && beta && y_bf16, "conv0_ln_gelu_fwd: null pointer");
   B2S_REQUIRE(batches > 0 && samples >= kConv0K, "conv0_ln_gelu_fwd: need at least %d samples", kConv0K);
   B2S_REQUIRE(out_frames == (samples - kConv0K) / kConv0S + 1, "conv0_ln_gelu_fwd: out_frames mismatch");
   dim3 grid((out_frames + 8 * kConv0TT - 1) / (8 * kConv0TT), batches);
   conv0_ln_gelu_kernel<<<grid, 256, 0, stream>>>(wave, wave_stride, samples, w, bias, gamma, beta, eps,
-                                                 reinterpret_cast<__nv_bfloat16*>(y_bf16), out_frames);
+                                                 reinterpret_cast<__nv_bfloat16*>(y_bf16), out_frames, fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 int embed_splice_fwd(const void* embed_table_bf16, const float* audio_embeds, const int* row_src, float* h0,
-                     long long rows, int C, cudaStream_t stream) {
+                     long long rows, int C, int fmt, cudaStream_t stream) {
   B2S_REQUIRE(embed_table_bf16 && row_src && h0, "embed_splice_fwd: null pointer");
   B2S_REQUIRE(C > 0 && C % 8 == 0, "embed_splice_fwd: C must be a multiple of 8");
   if (rows <= 0) return B2S_OK;
   embed_splice_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(embed_table_bf16), audio_embeds, row_src, h0, rows, C);
+      reinterpret_cast<const __nv_bfloat16*>(embed_table_bf16), audio_embeds, row_src, h0, rows, C, fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -239,20 +238,21 @@ int rowpair_sqdiff_fwd(const float* h, const int* rows_a, const int* rows_b, flo
   return B2S_OK;
 }
 
-int posconv_weight_pack(const float* g, const float* v, void* w_packed_bf16, int cout, int cin_g, int k,
+int posconv_weight_pack(const float* g, const float* v, void* w_packed_bf16, int cout, int cin_g, int k, int fmt,
                         cudaStream_t stream) {
   B2S_REQUIRE(g && v && w_packed_bf16 && cout > 0 && cin_g > 0 && k > 0, "posconv_weight_pack: bad arguments");
-  posconv_weight_pack_kernel<<<k, 256, 0, stream>>>(g, v, reinterpret_cast<__nv_bfloat16*>(w_packed_bf16), cout, cin_g,
-                                                    k);
+  posconv_weight_pack_kernel<<<k, 256, 0, stream>>>(g, v, reinterpret_cast<uint16_t*>(w_packed_bf16), cout, cin_g, k,
+                                                    fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
-int mel_to_padded_cl(const float* x, void* y_bf16, int batches, int channels, int frames, cudaStream_t stream) {
+int mel_to_padded_cl(const float* x, void* y_bf16, int batches, int channels, int frames, int fmt,
+                     cudaStream_t stream) {
   B2S_REQUIRE(x && y_bf16 && batches > 0 && channels > 0 && frames > 0, "mel_to_padded_cl: bad arguments");
   const long long total = static_cast<long long>(batches) * (frames + 2) * channels;
   mel_to_padded_cl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(y_bf16), batches, channels, frames);
+      x, reinterpret_cast<uint16_t*>(y_bf16), batches, channels, frames, fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -280,21 +280,21 @@ int gather_rows_bf16(const void* src, const int* index, void* out, long long row
   return B2S_OK;
 }
 
-int cast_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t stream) {
+int cast_f32_to_h16(const float* x, void* y, long long n, int fmt, cudaStream_t stream) {
   if (n <= 0) return B2S_OK;
-  B2S_REQUIRE(x && y, "cast_f32_to_bf16: null pointer");
+  B2S_REQUIRE(x && y, "cast_f32_to_h16: null pointer");
   const long long threads = (n + 3) / 4;
-  cast_f32_bf16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(y), n);
+  cast_f32_h16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(
+      x, reinterpret_cast<uint16_t*>(y), n, fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
-int cast_bf16_to_f32(const void* x, float* y, long long n, cudaStream_t stream) {
+int cast_h16_to_f32(const void* x, float* y, long long n, int fmt, cudaStream_t stream) {
   if (n <= 0) return B2S_OK;
-  B2S_REQUIRE(x && y, "cast_bf16_to_f32: null pointer");
-  cast_bf16_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), y, n);
+  B2S_REQUIRE(x && y, "cast_h16_to_f32: null pointer");
+  cast_h16_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint16_t*>(x), y, n, fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

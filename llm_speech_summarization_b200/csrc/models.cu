@@ -7,8 +7,8 @@
 //                    TF/models/llama/modeling_llama.py:375-425), plus the FD-loss hidden-state taps
 //                    (REF/trainer.py:358-370)
 //
-// Numerics: bf16 GEMM operands, fp32 accumulation, fp32 residual streams, fp32 norm statistics, fp32
-// pre-norm conv activations; everything the reference computes in fp32 on CPU is within bf16 rounding.
+// Numerics: 16-bit GEMM operands in the weights struct's `fmt` (fp16 like the reference's autocast, or bf16), fp32
+// accumulation, fp32 residual streams, fp32 norm statistics, fp32 pre-norm conv activations.
 #include "../../include/b2s.h"
 #include "b2s_common.cuh"
 #include "gemm_sm100.cuh"
@@ -107,26 +107,26 @@ GemmArgs plain_gemm(const void* A, const void* W, long long M, int N, int K) {
 // The pre-LN transformer stack shared by HuBERT (stable-layer-norm variant) and the Whisper encoder:
 //   h += out_proj(attention(qkv(LN1(h))));  h += W2 gelu(W1 LN2(h))      (fp32 residual stream h, bf16 operands)
 int encoder_stack(const b2s_encoder_layer* layers, int num_layers, int H, int F, int heads, float eps, float* h,
-                  void* xn, void* qkv_buf, void* ao, void* ff, const int* cu, int B, int frames,
+                  void* xn, void* qkv_buf, void* ao, void* ff, const int* cu, int B, int frames, int fmt,
                   cudaStream_t stream) {
   const long long rows = static_cast<long long>(B) * frames;
   int rc;
   for (int l = 0; l < num_layers; ++l) {
     const b2s_encoder_layer& L = layers[l];
-    rc = layernorm_fwd(h, 0, L.ln1_g, L.ln1_b, eps, 0, xn, rows, H, stream);
+    rc = layernorm_fwd(h, 0, L.ln1_g, L.ln1_b, eps, 0, xn, rows, H, fmt, stream);
     if (rc != B2S_OK) return rc;
     {
       GemmArgs g = plain_gemm(xn, L.wqkv, rows, 3 * H, H);
       g.epi = EPI_BF16;
       g.bias = L.bqkv;
       g.out = qkv_buf;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
     {
       const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(qkv_buf);
       rc = attention_fwd(qkv, qkv + H, qkv + 2 * H, 3 * H, ao, H, cu, B, frames, rows, heads, heads, 64, 0.125f, 0,
-                         nullptr, stream);
+                         nullptr, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
     {
@@ -135,10 +135,10 @@ int encoder_stack(const b2s_encoder_layer* layers, int num_layers, int H, int F,
       g.bias = L.bo;
       g.out = h;
       g.resid = h;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
-    rc = layernorm_fwd(h, 0, L.ln2_g, L.ln2_b, eps, 0, xn, rows, H, stream);
+    rc = layernorm_fwd(h, 0, L.ln2_g, L.ln2_b, eps, 0, xn, rows, H, fmt, stream);
     if (rc != B2S_OK) return rc;
     {
       GemmArgs g = plain_gemm(xn, L.w1, rows, F, H);
@@ -146,7 +146,7 @@ int encoder_stack(const b2s_encoder_layer* layers, int num_layers, int H, int F,
       g.act = ACT_GELU;
       g.bias = L.b1;
       g.out = ff;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
     {
@@ -155,7 +155,7 @@ int encoder_stack(const b2s_encoder_layer* layers, int num_layers, int H, int F,
       g.bias = L.b2;
       g.out = h;
       g.resid = h;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
   }
@@ -192,13 +192,13 @@ int hubert_forward(const b2s_hubert_weights* w, const float* wave, long long wav
   if (rc != B2S_OK) return rc;
   B2S_REQUIRE(pl.frames > 0 && pl.pooled > 0, "hubert_forward: audio too short (%d samples -> %d frames)", samples,
               pl.frames);
-  const int B = batches, H = w->hidden, F = w->ffn;
+  const int B = batches, H = w->hidden, F = w->ffn, fmt = w->fmt;
   const long long rows = static_cast<long long>(B) * pl.frames;
   const float eps = w->ln_eps;
 
   // ---- conv feature extractor
   rc = conv0_ln_gelu_fwd(wave, wave_stride, B, samples, w->conv0_w, w->conv0_b, w->conv0_ln_g, w->conv0_ln_b, eps,
-                         pl.xa, pl.t[1], stream);
+                         pl.xa, pl.t[1], fmt, stream);
   if (rc != B2S_OK) return rc;
   void* cur = pl.xa;
   void* nxt = pl.xb;
@@ -226,9 +226,10 @@ int hubert_forward(const b2s_hubert_weights* w, const float* wave, long long wav
     g.out = pl.pre;
     g.ldo = 512;
     g.out_batch_rows = tout;
-    rc = gemm_bf16_launch(g, stream);
+    rc = gemm_launch_fmt(g, fmt, stream);
     if (rc != B2S_OK) return rc;
     rc = layernorm_fwd(pl.pre, 0, w->conv_ln_g[i], w->conv_ln_b[i], eps, 1, nxt, static_cast<long long>(B) * tout, 512,
+                       fmt,
                        stream);
     if (rc != B2S_OK) return rc;
     void* tmp = cur;
@@ -238,18 +239,18 @@ int hubert_forward(const b2s_hubert_weights* w, const float* wave, long long wav
   // cur: bf16 [B, frames, 512]
 
   // ---- feature projection: LN(512) -> Linear(512 -> H)
-  rc = layernorm_fwd(cur, 1, w->fp_ln_g, w->fp_ln_b, eps, 0, nxt, rows, 512, stream);
+  rc = layernorm_fwd(cur, 1, w->fp_ln_g, w->fp_ln_b, eps, 0, nxt, rows, 512, fmt, stream);
   if (rc != B2S_OK) return rc;
   {
     GemmArgs g = plain_gemm(nxt, w->fp_w, rows, H, 512);
     g.epi = EPI_F32;
     g.bias = w->fp_b;
     g.out = pl.h;
-    rc = gemm_bf16_launch(g, stream);
+    rc = gemm_launch_fmt(g, fmt, stream);
     if (rc != B2S_OK) return rc;
   }
   // ---- positional conv embedding: h += gelu(grouped_conv(h) + b)
-  rc = cast_f32_to_bf16(pl.h, pl.xn, rows * H, stream);
+  rc = cast_f32_to_h16(pl.h, pl.xn, rows * H, fmt, stream);
   if (rc != B2S_OK) return rc;
   {
     GemmArgs g{};
@@ -277,28 +278,28 @@ int hubert_forward(const b2s_hubert_weights* w, const float* wave, long long wav
     g.resid = pl.h;
     g.ldo = H;
     g.out_batch_rows = pl.frames;
-    rc = gemm_bf16_launch(g, stream);
+    rc = gemm_launch_fmt(g, fmt, stream);
     if (rc != B2S_OK) return rc;
   }
   // ---- transformer layers (stable layer norm = pre-LN)
   iota_scaled_kernel<<<(B + 1 + 255) / 256, 256, 0, stream>>>(pl.cu, B + 1, pl.frames);
   B2S_LAUNCH_CHECK();
   rc = encoder_stack(w->layers, w->num_layers, H, F, w->heads, eps, pl.h, pl.xn, pl.qkv, pl.ao, pl.ff, pl.cu, B,
-                     pl.frames, stream);
+                     pl.frames, fmt, stream);
   if (rc != B2S_OK) return rc;
   if (last_hidden != nullptr) {
     B2S_CUDA_CHECK(cudaMemcpyAsync(last_hidden, pl.h, rows * H * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   }
   // ---- final LN + AvgPool1d + projector
   rc = layernorm_avgpool_fwd(pl.h, w->final_ln_g, w->final_ln_b, eps, pl.pooled_x, B, pl.frames, H, w->pool_kernel,
-                             w->pool_stride, pl.pooled, stream);
+                             w->pool_stride, pl.pooled, fmt, stream);
   if (rc != B2S_OK) return rc;
   {
     GemmArgs g = plain_gemm(pl.pooled_x, w->proj_w, static_cast<long long>(B) * pl.pooled, w->llm_dim, H);
     g.epi = EPI_F32;
     g.bias = w->proj_b;
     g.out = audio_embeds;
-    rc = gemm_bf16_launch(g, stream);
+    rc = gemm_launch_fmt(g, fmt, stream);
     if (rc != B2S_OK) return rc;
   }
   return B2S_OK;
@@ -362,10 +363,10 @@ int whisper_forward(const b2s_whisper_weights* w, const float* mel, int batches,
   int rc = plan_whisper(w, batches, workspace, workspace_bytes, &pl);
   if (rc != B2S_OK) return rc;
   B2S_REQUIRE(pl.pooled > 0, "whisper_forward: too few frames to pool");
-  const int B = batches, H = w->hidden, F = w->ffn, C = w->mel_bins, T = frames_in;
+  const int B = batches, H = w->hidden, F = w->ffn, C = w->mel_bins, T = frames_in, fmt = w->fmt;
   const long long rows = static_cast<long long>(B) * pl.frames;
 
-  rc = mel_to_padded_cl(mel, pl.x0, B, C, T, stream);
+  rc = mel_to_padded_cl(mel, pl.x0, B, C, T, fmt, stream);
   if (rc != B2S_OK) return rc;
   // conv1: Conv1d(mel -> H, k=3, pad=1) + GELU; output row t lands on padded row t+1 of x1, whose first and last
   // rows stay zero (they are conv2's padding)
@@ -392,7 +393,7 @@ int whisper_forward(const b2s_whisper_weights* w, const float* mel, int batches,
     g.out = reinterpret_cast<__nv_bfloat16*>(pl.x1) + H;  // skip the leading zero row
     g.ldo = H;
     g.out_batch_rows = T + 2;
-    rc = gemm_bf16_launch(g, stream);
+    rc = gemm_launch_fmt(g, fmt, stream);
     if (rc != B2S_OK) return rc;
   }
   // conv2: Conv1d(H -> H, k=3, stride=2, pad=1) + GELU, + positional table -> fp32 residual stream
@@ -420,26 +421,26 @@ int whisper_forward(const b2s_whisper_weights* w, const float* mel, int batches,
     g.resid_bcast = 1;
     g.ldo = H;
     g.out_batch_rows = pl.frames;
-    rc = gemm_bf16_launch(g, stream);
+    rc = gemm_launch_fmt(g, fmt, stream);
     if (rc != B2S_OK) return rc;
   }
   iota_scaled_kernel<<<(B + 1 + 255) / 256, 256, 0, stream>>>(pl.cu, B + 1, pl.frames);
   B2S_LAUNCH_CHECK();
   rc = encoder_stack(w->layers, w->num_layers, H, F, w->heads, w->ln_eps, pl.h, pl.xn, pl.qkv, pl.ao, pl.ff, pl.cu, B,
-                     pl.frames, stream);
+                     pl.frames, fmt, stream);
   if (rc != B2S_OK) return rc;
   if (last_hidden != nullptr) {
     B2S_CUDA_CHECK(cudaMemcpyAsync(last_hidden, pl.h, rows * H * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   }
   rc = layernorm_avgpool_fwd(pl.h, w->final_ln_g, w->final_ln_b, w->ln_eps, pl.pooled_x, B, pl.frames, H,
-                             w->pool_kernel, w->pool_stride, pl.pooled, stream);
+                             w->pool_kernel, w->pool_stride, pl.pooled, fmt, stream);
   if (rc != B2S_OK) return rc;
   {
     GemmArgs g = plain_gemm(pl.pooled_x, w->proj_w, static_cast<long long>(B) * pl.pooled, w->llm_dim, H);
     g.epi = EPI_F32;
     g.bias = w->proj_b;
     g.out = audio_embeds;
-    rc = gemm_bf16_launch(g, stream);
+    rc = gemm_launch_fmt(g, fmt, stream);
     if (rc != B2S_OK) return rc;
   }
   return B2S_OK;
@@ -520,7 +521,7 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
   LlamaPlan pl;
   int rc = plan_llama(w, rows, logit_rows, workspace, workspace_bytes, &pl);
   if (rc != B2S_OK) return rc;
-  const int H = w->hidden, D = w->head_dim, Hq = w->heads, Hkv = w->kv_heads, F = w->ffn;
+  const int H = w->hidden, D = w->head_dim, Hq = w->heads, Hkv = w->kv_heads, F = w->ffn, fmt = w->fmt;
   const int qkv_cols = (Hq + 2 * Hkv) * D;
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
 
@@ -542,7 +543,7 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
       }
     }
     const b2s_llama_layer& L = w->layers[l];
-    rc = rmsnorm_fwd(h, L.ln1_w, w->rms_eps, pl.xn, rows, H, stream);
+    rc = rmsnorm_fwd(h, L.ln1_w, w->rms_eps, pl.xn, rows, H, fmt, stream);
     if (rc != B2S_OK) return rc;
     {
       GemmArgs g = plain_gemm(pl.xn, L.wqkv, rows, qkv_cols, H);
@@ -551,7 +552,7 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
       g.rope_cs = w->rope_cs;
       g.positions = positions;
       g.rope_cols = (Hq + Hkv) * D;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
     if (kv_cache != nullptr) {
@@ -561,7 +562,7 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
     {
       const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(pl.qkv);
       rc = attention_fwd(qkv, qkv + Hq * D, qkv + (Hq + Hkv) * D, qkv_cols, pl.ao, Hq * D, cu_seqlens, num_seqs,
-                         max_seqlen, rows, Hq, Hkv, D, scale, 1, nullptr, stream);
+                         max_seqlen, rows, Hq, Hkv, D, scale, 1, nullptr, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
     const bool sel = last_on_selected && l == w->num_layers - 1;
@@ -580,17 +581,17 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
       g.epi = EPI_RESID_F32;
       g.out = hs;
       g.resid = hs;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
-    rc = rmsnorm_fwd(hs, L.ln2_w, w->rms_eps, pl.xn, m, H, stream);
+    rc = rmsnorm_fwd(hs, L.ln2_w, w->rms_eps, pl.xn, m, H, fmt, stream);
     if (rc != B2S_OK) return rc;
     {
       GemmArgs g = plain_gemm(pl.xn, L.wgu, m, 2 * F, H);
       g.epi = EPI_SWIGLU;
       g.out = pl.act;
       g.ldo = F;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
     {
@@ -598,7 +599,7 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
       g.epi = EPI_RESID_F32;
       g.out = hs;
       g.resid = hs;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
   }
@@ -609,19 +610,21 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
     }
   }
   if (all_hidden != nullptr) {  // hidden_states[-1] = output of the final norm (rounded through bf16)
-    rc = rmsnorm_fwd(h, w->final_norm_w, w->rms_eps, pl.xn, rows, H, stream);
+    rc = rmsnorm_fwd(h, w->final_norm_w, w->rms_eps, pl.xn, rows, H, fmt, stream);
     if (rc != B2S_OK) return rc;
-    rc = cast_bf16_to_f32(pl.xn, all_hidden + static_cast<size_t>(w->num_layers) * rows * H,
-                          static_cast<long long>(rows) * H, stream);
+    rc = cast_h16_to_f32(pl.xn, all_hidden + static_cast<size_t>(w->num_layers) * rows * H,
+                          static_cast<long long>(rows) * H, fmt, stream);
     if (rc != B2S_OK) return rc;
   }
   if (logit_rows > 0) {
-    if (last_on_selected) rc = rmsnorm_fwd(pl.hsel, w->final_norm_w, w->rms_eps, pl.xf, logit_rows, H, stream);
-    else rc = rmsnorm_gather_fwd(h, logit_rows_index, w->final_norm_w, w->rms_eps, pl.xf, logit_rows, H, stream);
+    if (last_on_selected) rc = rmsnorm_fwd(pl.hsel, w->final_norm_w, w->rms_eps, pl.xf, logit_rows, H, fmt, stream);
+    else rc = rmsnorm_gather_fwd(h, logit_rows_index, w->final_norm_w, w->rms_eps, pl.xf, logit_rows, H, fmt, stream);
     if (rc != B2S_OK) return rc;
     GemmArgs g = plain_gemm(pl.xf, w->lm_head, logit_rows, w->vocab, H);
     g.epi = EPI_BF16;
     g.out = logits_bf16;
+    g.a_fmt = g.w_fmt = fmt;
+    g.out_fmt = 0;  // logits are bf16 whatever the operand format (what the fused loss kernel reads)
     rc = gemm_bf16_launch(g, stream);
     if (rc != B2S_OK) return rc;
   }

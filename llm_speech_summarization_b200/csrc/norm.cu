@@ -14,11 +14,9 @@ namespace {
 constexpr int kWarpsPerCta = 8;
 
 template <bool IN_BF16>
-__device__ __forceinline__ void load8(const void* base, long long elem_off, float (&f)[8]) {
-  if constexpr (IN_BF16) {
-    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off);
-    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
-    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+__device__ __forceinline__ void load8(const void* base, long long elem_off, float (&f)[8], int f16 = 0) {
+  if constexpr (IN_BF16) {  // 16-bit input in format f16 (0 = bf16, 1 = fp16)
+    ld8h(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off, f, f16);
   } else {
     const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
     const float4 a = p[0], b = p[1];
@@ -26,21 +24,19 @@ __device__ __forceinline__ void load8(const void* base, long long elem_off, floa
   }
 }
 
-__device__ __forceinline__ void store8_bf16(void* base, long long elem_off, const float (&f)[8]) {
-  uint4 u;
-  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
-  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) = u;
+__device__ __forceinline__ void store8_h16(void* base, long long elem_off, const float (&f)[8], int f16) {
+  st8h(reinterpret_cast<__nv_bfloat16*>(base) + elem_off, f, f16);
 }
 
 // row -> registers, returns mean and rstd (two-pass)
 template <int GROUPS, bool IN_BF16>
 __device__ __forceinline__ void load_row_stats(const void* x, long long row_off, int lane, float (&v)[GROUPS][8],
-                                               float eps, float& mean, float& rstd) {
+                                               float eps, float& mean, float& rstd, int f16 = 0) {
   constexpr int C = GROUPS * 256;
   float s = 0.f;
 #pragma unroll
   for (int g = 0; g < GROUPS; ++g) {
-    load8<IN_BF16>(x, row_off + (g * 32 + lane) * 8, v[g]);
+    load8<IN_BF16>(x, row_off + (g * 32 + lane) * 8, v[g], f16);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s += v[g][j];
   }
@@ -60,7 +56,7 @@ __device__ __forceinline__ void load_row_stats(const void* x, long long row_off,
 template <int GROUPS, bool IN_BF16, bool GELU>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 float eps, void* __restrict__ y, long long rows) {
+                 float eps, void* __restrict__ y, long long rows, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   pdl_wait();     // ... and this grid itself may have been launched early: the predecessor's rows are complete from here
   constexpr int C = GROUPS * 256;
@@ -69,7 +65,7 @@ layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma, co
   if (row >= rows) return;
   float v[GROUPS][8];
   float mean, rstd;
-  load_row_stats<GROUPS, IN_BF16>(x, row * C, lane, v, eps, mean, rstd);
+  load_row_stats<GROUPS, IN_BF16>(x, row * C, lane, v, eps, mean, rstd, f16);
 #pragma unroll
   for (int g = 0; g < GROUPS; ++g) {
     float gm[8], bt[8], o[8];
@@ -80,14 +76,14 @@ layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma, co
       float t = (v[g][j] - mean) * rstd * gm[j] + bt[j];
       o[j] = GELU ? gelu_erf(t) : t;
     }
-    store8_bf16(y, row * C + (g * 32 + lane) * 8, o);
+    store8_h16(y, row * C + (g * 32 + lane) * 8, o, f16);
   }
 }
 
 template <int GROUPS, bool GATHER>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 rmsnorm_kernel(const float* __restrict__ x, const int* __restrict__ row_index, const float* __restrict__ w, float eps,
-               void* __restrict__ y, long long rows) {
+               void* __restrict__ y, long long rows, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   pdl_wait();     // ... and this grid itself may have been launched early: the predecessor's rows are complete from here
   constexpr int C = GROUPS * 256;
@@ -111,7 +107,7 @@ rmsnorm_kernel(const float* __restrict__ x, const int* __restrict__ row_index, c
     // LlamaRMSNorm: weight * (x * rstd) with the normalised value rounded to the activation dtype first
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = wt[j] * (v[g][j] * rstd);
-    store8_bf16(y, row * C + (g * 32 + lane) * 8, o);
+    store8_h16(y, row * C + (g * 32 + lane) * 8, o, f16);
   }
 }
 
@@ -119,7 +115,7 @@ template <int GROUPS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 layernorm_avgpool_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                          float eps, void* __restrict__ y, int batches, int frames, int kernel, int stride,
-                         int out_frames) {
+                         int out_frames, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   pdl_wait();     // ... and this grid itself may have been launched early: the predecessor's rows are complete from here
   constexpr int C = GROUPS * 256;
@@ -151,7 +147,7 @@ layernorm_avgpool_kernel(const float* __restrict__ x, const float* __restrict__ 
     load8<false>(beta, (g * 32 + lane) * 8, bt);
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = acc[g][i] * inv * gm[i] + bt[i];  // mean of affine = affine of mean
-    store8_bf16(y, orow * C + (g * 32 + lane) * 8, o);
+    store8_h16(y, orow * C + (g * 32 + lane) * 8, o, f16);
   }
 }
 
@@ -173,7 +169,7 @@ layernorm_avgpool_kernel(const float* __restrict__ x, const float* __restrict__ 
 }  // namespace
 
 int layernorm_fwd(const void* x, int in_bf16, const float* gamma, const float* beta, float eps, int act_gelu,
-                  void* y_bf16, long long rows, int C, cudaStream_t stream) {
+                  void* y_bf16, long long rows, int C, int fmt, cudaStream_t stream) {
   B2S_REQUIRE(x && gamma && beta && y_bf16, "layernorm_fwd: null pointer");
   B2S_REQUIRE(C > 0 && C % 256 == 0, "layernorm_fwd: C must be a multiple of 256");
   if (rows <= 0) return B2S_OK;
@@ -181,11 +177,11 @@ int layernorm_fwd(const void* x, int in_bf16, const float* gamma, const float* b
   int rc_ = B2S_OK;
   B2S_DISPATCH_GROUPS(C, {
     if (in_bf16) {
-      if (act_gelu) rc_ = launch_pdl_kernel(layernorm_kernel<G, true, true>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, gamma, beta, eps, y_bf16, rows);
-      else rc_ = launch_pdl_kernel(layernorm_kernel<G, true, false>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, gamma, beta, eps, y_bf16, rows);
+      if (act_gelu) rc_ = launch_pdl_kernel(layernorm_kernel<G, true, true>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, gamma, beta, eps, y_bf16, rows, fmt);
+      else rc_ = launch_pdl_kernel(layernorm_kernel<G, true, false>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, gamma, beta, eps, y_bf16, rows, fmt);
     } else {
-      if (act_gelu) rc_ = launch_pdl_kernel(layernorm_kernel<G, false, true>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, gamma, beta, eps, y_bf16, rows);
-      else rc_ = launch_pdl_kernel(layernorm_kernel<G, false, false>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, gamma, beta, eps, y_bf16, rows);
+      if (act_gelu) rc_ = launch_pdl_kernel(layernorm_kernel<G, false, true>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, gamma, beta, eps, y_bf16, rows, fmt);
+      else rc_ = launch_pdl_kernel(layernorm_kernel<G, false, false>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, gamma, beta, eps, y_bf16, rows, fmt);
     }
   });
   if (rc_ != B2S_OK) return rc_;
@@ -193,7 +189,8 @@ int layernorm_fwd(const void* x, int in_bf16, const float* gamma, const float* b
   return B2S_OK;
 }
 
-int rmsnorm_fwd(const float* x, const float* w, float eps, void* y_bf16, long long rows, int C, cudaStream_t stream) {
+int rmsnorm_fwd(const float* x, const float* w, float eps, void* y_bf16, long long rows, int C, int fmt,
+                cudaStream_t stream) {
   B2S_REQUIRE(x && w && y_bf16, "rmsnorm_fwd: null pointer");
   B2S_REQUIRE(C > 0 && C % 256 == 0, "rmsnorm_fwd: C must be a multiple of 256");
   if (rows <= 0) return B2S_OK;
@@ -201,28 +198,28 @@ int rmsnorm_fwd(const float* x, const float* w, float eps, void* y_bf16, long lo
   int rc_ = B2S_OK;
   const int* no_index = nullptr;
   B2S_DISPATCH_GROUPS(C, (rc_ = launch_pdl_kernel(rmsnorm_kernel<G, false>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream,
-                                                  x, no_index, w, eps, y_bf16, rows)));
+                                                  x, no_index, w, eps, y_bf16, rows, fmt)));
   if (rc_ != B2S_OK) return rc_;
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 int rmsnorm_gather_fwd(const float* x, const int* row_index, const float* w, float eps, void* y_bf16, long long rows,
-                       int C, cudaStream_t stream) {
+                       int C, int fmt, cudaStream_t stream) {
   B2S_REQUIRE(x && w && y_bf16 && row_index, "rmsnorm_gather_fwd: null pointer");
   B2S_REQUIRE(C > 0 && C % 256 == 0, "rmsnorm_gather_fwd: C must be a multiple of 256");
   if (rows <= 0) return B2S_OK;
   const unsigned grid = static_cast<unsigned>((rows + kWarpsPerCta - 1) / kWarpsPerCta);
   int rc_ = B2S_OK;
   B2S_DISPATCH_GROUPS(C, (rc_ = launch_pdl_kernel(rmsnorm_kernel<G, true>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream,
-                                                  x, row_index, w, eps, y_bf16, rows)));
+                                                  x, row_index, w, eps, y_bf16, rows, fmt)));
   if (rc_ != B2S_OK) return rc_;
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 int layernorm_avgpool_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y_bf16, int batches,
-                          int frames, int C, int kernel, int stride, int out_frames, cudaStream_t stream) {
+                          int frames, int C, int kernel, int stride, int out_frames, int fmt, cudaStream_t stream) {
   B2S_REQUIRE(x && gamma && beta && y_bf16, "layernorm_avgpool_fwd: null pointer");
   B2S_REQUIRE(C > 0 && C % 256 == 0 && kernel > 0 && stride > 0, "layernorm_avgpool_fwd: bad sizes");
   B2S_REQUIRE(out_frames >= 0 && (out_frames == 0 || (out_frames - 1) * stride + kernel <= frames),
@@ -231,7 +228,7 @@ int layernorm_avgpool_fwd(const float* x, const float* gamma, const float* beta,
   if (orows <= 0) return B2S_OK;
   const unsigned grid = static_cast<unsigned>((orows + kWarpsPerCta - 1) / kWarpsPerCta);
   B2S_DISPATCH_GROUPS(C, (layernorm_avgpool_kernel<G><<<grid, kWarpsPerCta * 32, 0, stream>>>(
-                             x, gamma, beta, eps, y_bf16, batches, frames, kernel, stride, out_frames)));
+                             x, gamma, beta, eps, y_bf16, batches, frames, kernel, stride, out_frames, fmt)));
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

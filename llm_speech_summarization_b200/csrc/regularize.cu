@@ -11,7 +11,7 @@ namespace {
 
 // x (fp32 and / or bf16 copy of the same logical tensor) *= keep ? 1/(1-p) : 0, element index = linear index
 __global__ void __launch_bounds__(256)
-dropout_apply_kernel(float* __restrict__ xf, __nv_bfloat16* __restrict__ xb, long long n8, DropSpec d) {
+dropout_apply_kernel(float* __restrict__ xf, __nv_bfloat16* __restrict__ xb, long long n8, DropSpec d, int f16) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
@@ -28,10 +28,10 @@ dropout_apply_kernel(float* __restrict__ xf, __nv_bfloat16* __restrict__ xb, lon
   }
   if (xb != nullptr) {
     float v[8];
-    ld8bf(xb + i * 8, v);
+    ld8h(xb + i * 8, v, f16);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= m[j];
-    st8bf(xb + i * 8, v);
+    st8h(xb + i * 8, v, f16);
   }
 }
 
@@ -89,12 +89,12 @@ drop_mask_dump_kernel(unsigned char* __restrict__ out, long long n, uint32_t e_f
 
 }  // namespace
 
-int dropout_apply(float* x_f32, void* x_bf16, long long n, const DropSpec& d, cudaStream_t stream) {
+int dropout_apply(float* x_f32, void* x_bf16, long long n, const DropSpec& d, int fmt, cudaStream_t stream) {
   B2S_REQUIRE(x_f32 || x_bf16, "dropout_apply: null pointer");
   B2S_REQUIRE(n % 8 == 0 && n < (1LL << 32), "dropout_apply: element count must be a multiple of 8 below 2^32");
   if (n <= 0 || d.thresh == 0u) return B2S_OK;
   dropout_apply_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, stream>>>(
-      x_f32, reinterpret_cast<__nv_bfloat16*>(x_bf16), n / 8, d);
+      x_f32, reinterpret_cast<__nv_bfloat16*>(x_bf16), n / 8, d, fmt);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

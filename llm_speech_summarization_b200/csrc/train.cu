@@ -109,6 +109,7 @@ int llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* sv, i
   B2S_REQUIRE(pl.bytes <= workspace_bytes, "llama_forward_train: workspace too small (%zu < %zu)", workspace_bytes,
               pl.bytes);
   const int H = w->hidden, D = w->head_dim, Hq = w->heads, Hkv = w->kv_heads, F = w->ffn, Lyr = w->num_layers;
+  const int fmt = w->fmt;
   const int qkv_cols = (Hq + 2 * Hkv) * D;
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
   const size_t R = static_cast<size_t>(rows);
@@ -128,7 +129,7 @@ int llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* sv, i
       }
     }
     const b2s_llama_layer& L = w->layers[l];
-    rc = rmsnorm_fwd(h_in, L.ln1_w, w->rms_eps, pl.xn, rows, H, stream);
+    rc = rmsnorm_fwd(h_in, L.ln1_w, w->rms_eps, pl.xn, rows, H, fmt, stream);
     if (rc != B2S_OK) return rc;
     {
       GemmArgs g = lin(pl.xn, L.wqkv, rows, qkv_cols, H);
@@ -137,21 +138,21 @@ int llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* sv, i
       g.rope_cs = w->rope_cs;
       g.positions = positions;
       g.rope_cols = (Hq + Hkv) * D;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
     rc = attention_fwd(qkv, qkv + Hq * D, qkv + (Hq + Hkv) * D, qkv_cols, ao, Hq * D, cu_seqlens, num_seqs, max_seqlen,
-                       rows, Hq, Hkv, D, scale, 1, lse, stream);
+                       rows, Hq, Hkv, D, scale, 1, lse, fmt, stream);
     if (rc != B2S_OK) return rc;
     {
       GemmArgs g = lin(ao, L.wo, rows, H, Hq * D);
       g.epi = EPI_RESID_F32;
       g.out = h_mid;
       g.resid = h_in;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
-    rc = rmsnorm_fwd(h_mid, L.ln2_w, w->rms_eps, pl.xn, rows, H, stream);
+    rc = rmsnorm_fwd(h_mid, L.ln2_w, w->rms_eps, pl.xn, rows, H, fmt, stream);
     if (rc != B2S_OK) return rc;
     {
       GemmArgs g = lin(pl.xn, L.wgu, rows, 2 * F, H);
@@ -160,7 +161,7 @@ int llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* sv, i
       g.ldo = F;
       g.out2 = gu;
       g.ld2 = 2 * F;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
     {
@@ -168,18 +169,21 @@ int llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* sv, i
       g.epi = EPI_RESID_F32;
       g.out = h_out;
       g.resid = h_mid;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
   }
   if (logit_rows > 0) {
     B2S_REQUIRE(logit_rows_index && logits_bf16, "llama_forward_train: logits requested without buffers");
     rc = rmsnorm_gather_fwd(sv->h + Lyr * R * H, logit_rows_index, w->final_norm_w, w->rms_eps, pl.xf, logit_rows, H,
+                            fmt,
                             stream);
     if (rc != B2S_OK) return rc;
     GemmArgs g = lin(pl.xf, w->lm_head, logit_rows, w->vocab, H);
     g.epi = EPI_BF16;
     g.out = logits_bf16;
+    g.a_fmt = g.w_fmt = fmt;
+    g.out_fmt = 0;  // logits stay bf16 (b2s.h)
     rc = gemm_bf16_launch(g, stream);
     if (rc != B2S_OK) return rc;
   }
@@ -189,8 +193,8 @@ int llama_forward_train(const b2s_llama_weights* w, const b2s_llama_saved* sv, i
 int llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt, const b2s_llama_saved* sv, int rows,
                    int rows_bwd, const int* cu_seqlens, int num_seqs_bwd, int max_seqlen, const void* d_logits,
                    const int* dl_rows_index, int n_dl, const int* tap_layers, int num_taps, const int* tap_rows_a,
-                   const int* tap_rows_b, const float* tap_coef, int pairs, float* dh, void* workspace,
-                   size_t workspace_bytes, cudaStream_t stream) {
+                   const int* tap_rows_b, const float* tap_coef, const float* loss_scale, int pairs, float* dh,
+                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   B2S_REQUIRE(w && wt && wt->layers && wt->lm_head_t && sv && cu_seqlens && d_logits && dl_rows_index && dh && workspace,
               "llama_backward: null pointer");
   B2S_REQUIRE(rows_bwd > 0 && rows_bwd <= rows && num_seqs_bwd > 0 && n_dl > 0, "llama_backward: bad sizes");
@@ -198,6 +202,7 @@ int llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt, co
   plan_bwd(w, rows_bwd, n_dl, workspace, workspace_bytes, &pl);
   B2S_REQUIRE(pl.bytes <= workspace_bytes, "llama_backward: workspace too small (%zu < %zu)", workspace_bytes, pl.bytes);
   const int H = w->hidden, D = w->head_dim, Hq = w->heads, Hkv = w->kv_heads, F = w->ffn, Lyr = w->num_layers;
+  const int fmt = w->fmt;
   const int qkv_cols = (Hq + 2 * Hkv) * D;
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
   const size_t R = static_cast<size_t>(rows);
@@ -211,11 +216,11 @@ int llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt, co
     GemmArgs g = lin(d_logits, wt->lm_head_t, n_dl, H, w->vocab);
     g.epi = EPI_ACCUM_F32;
     g.out = pl.dxf;
-    rc = gemm_bf16_launch(g, stream);
+    rc = gemm_launch_fmt(g, fmt, stream);
     if (rc != B2S_OK) return rc;
   }
   rc = rmsnorm_bwd(sv->h + Lyr * R * H, dl_rows_index, w->final_norm_w, w->rms_eps, pl.dxf, dh, dl_rows_index,
-                   pl.dh_bf16, n_dl, H, stream);
+                   pl.dh_bf16, n_dl, H, fmt, stream);
   if (rc != B2S_OK) return rc;
 
   for (int l = Lyr - 1; l >= 0; --l) {
@@ -224,7 +229,8 @@ int llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt, co
     // feature-distillation gradient on hidden_states[l+1] (the input of layer l+1)
     for (int t = 0; t < num_taps; ++t) {
       if (tap_layers[t] == l + 1 && pairs > 0) {
-        rc = add_rowdiff(sv->h + (l + 1) * R * H, tap_rows_a, tap_rows_b, tap_coef, dh, pl.dh_bf16, pairs, H, stream);
+        rc = add_rowdiff(sv->h + (l + 1) * R * H, tap_rows_a, tap_rows_b, tap_coef, loss_scale, dh, pl.dh_bf16, pairs, H,
+                         fmt, stream);
         if (rc != B2S_OK) return rc;
       }
     }
@@ -236,43 +242,43 @@ int llama_backward(const b2s_llama_weights* w, const b2s_llama_weights_t* wt, co
       GemmArgs g = lin(pl.dh_bf16, T.wd_t, Ms, F, H);
       g.epi = EPI_BF16;
       g.out = pl.dact;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
     // (fusing this into the dgrad epilogue was measured: the GEMMs lose more than the 80 us launch saves)
-    rc = swiglu_bwd(gu, pl.dact, pl.dgu, Ms, F, stream);
+    rc = swiglu_bwd(gu, pl.dact, pl.dgu, Ms, F, fmt, stream);
     if (rc != B2S_OK) return rc;
     {  // gate|up dgrad
       GemmArgs g = lin(pl.dgu, T.wgu_t, Ms, H, 2 * F);
       g.epi = EPI_F32;
       g.out = pl.dxn;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
-    rc = rmsnorm_bwd(sv->h_mid + l * R * H, nullptr, L.ln2_w, w->rms_eps, pl.dxn, dh, nullptr, pl.dh_bf16, Ms, H, stream);
+    rc = rmsnorm_bwd(sv->h_mid + l * R * H, nullptr, L.ln2_w, w->rms_eps, pl.dxn, dh, nullptr, pl.dh_bf16, Ms, H, fmt, stream);
     if (rc != B2S_OK) return rc;
     {  // o_proj dgrad
       GemmArgs g = lin(pl.dh_bf16, T.wo_t, Ms, Hq * D, H);
       g.epi = EPI_BF16;
       g.out = pl.dao;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
     {
       __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(pl.dqkv);
       rc = attention_bwd(qkv, qkv + Hq * D, qkv + (Hq + Hkv) * D, qkv_cols, ao, Hq * D, pl.dao, Hq * D, lse, pl.delta,
                          dqkv, dqkv + Hq * D, dqkv + (Hq + Hkv) * D, qkv_cols, cu_seqlens, num_seqs_bwd, max_seqlen, Ms,
-                         Hq, Hkv, D, scale, 1, w->rope_cs, stream);
+                         Hq, Hkv, D, scale, 1, w->rope_cs, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
     {  // fused-QKV dgrad
       GemmArgs g = lin(pl.dqkv, T.wqkv_t, Ms, H, qkv_cols);
       g.epi = EPI_F32;
       g.out = pl.dxn;
-      rc = gemm_bf16_launch(g, stream);
+      rc = gemm_launch_fmt(g, fmt, stream);
       if (rc != B2S_OK) return rc;
     }
-    rc = rmsnorm_bwd(sv->h + l * R * H, nullptr, L.ln1_w, w->rms_eps, pl.dxn, dh, nullptr, pl.dh_bf16, Ms, H, stream);
+    rc = rmsnorm_bwd(sv->h + l * R * H, nullptr, L.ln1_w, w->rms_eps, pl.dxn, dh, nullptr, pl.dh_bf16, Ms, H, fmt, stream);
     if (rc != B2S_OK) return rc;
   }
   return B2S_OK;

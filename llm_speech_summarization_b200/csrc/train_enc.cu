@@ -230,7 +230,7 @@ GemmArgs lin(const void* A, const void* W, long long M, int N, int K) {
 }
 
 // dX[M, K] = dY[M, N] . W[N, K]   (W in its forward layout, read MN-major)
-int dgrad(const void* dy, const void* W, long long M, int N, int K, int epi, void* out, cudaStream_t st) {
+int dgrad(const void* dy, const void* W, long long M, int N, int K, int epi, void* out, int fmt, cudaStream_t st) {
   GemmArgs g{};
   g.A = dy;
   g.a_dim0 = N;
@@ -249,11 +249,11 @@ int dgrad(const void* dy, const void* W, long long M, int N, int K, int epi, voi
   g.epi = epi;
   g.out = out;
   g.ldo = K;
-  return gemm_bf16_launch(g, st);
+  return gemm_launch_fmt(g, fmt, st);
 }
 
 // dW[N, K] += dY[rows, N]^T . X[rows, K]
-int wgrad(const void* dy, const void* x, long long rows, int N, int K, float* dW, cudaStream_t st) {
+int wgrad(const void* dy, const void* x, long long rows, int N, int K, float* dW, int fmt, cudaStream_t st) {
   GemmArgs g{};
   g.A = dy;
   g.a_dim0 = N;
@@ -275,7 +275,7 @@ int wgrad(const void* dy, const void* x, long long rows, int N, int K, float* dW
   g.epi = EPI_ACCUM_F32;
   g.out = dW;
   g.ldo = K;
-  return gemm_bf16_launch(g, st);
+  return gemm_launch_fmt(g, fmt, st);
 }
 
 #define RC(expr)                 \
@@ -318,7 +318,7 @@ bool layer_skipped(const b2s_encoder_regularizers* reg, int l) {
 }
 
 int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, int heads, float eps, const StackBufs& s,
-                        void* xn, const int* cu, int B, int frames, cudaStream_t stream,
+                        void* xn, const int* cu, int B, int frames, int fmt, cudaStream_t stream,
                         const b2s_encoder_regularizers* reg = nullptr, long long rows_packed = -1) {
   // `frames` is the longest sequence (attention grid); rows = all packed rows (B * frames unless the batch is ragged)
   const long long rows = rows_packed >= 0 ? rows_packed : static_cast<long long>(B) * frames;
@@ -337,16 +337,16 @@ int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, in
     __nv_bfloat16* ao = reinterpret_cast<__nv_bfloat16*>(s.ao) + l * rH;
     __nv_bfloat16* ffp = reinterpret_cast<__nv_bfloat16*>(s.ff_pre) + static_cast<size_t>(l) * rows * F;
     __nv_bfloat16* ff = reinterpret_cast<__nv_bfloat16*>(s.ff) + static_cast<size_t>(l) * rows * F;
-    RC(layernorm_fwd(h_in, 0, Ly.ln1_g, Ly.ln1_b, eps, 0, xn, rows, H, stream));
+    RC(layernorm_fwd(h_in, 0, Ly.ln1_g, Ly.ln1_b, eps, 0, xn, rows, H, fmt, stream));
     {
       GemmArgs g = lin(xn, Ly.wqkv, rows, 3 * H, H);
       g.epi = EPI_BF16;
       g.bias = Ly.bqkv;
       g.out = qkv;
-      RC(gemm_bf16_launch(g, stream));
+      RC(gemm_launch_fmt(g, fmt, stream));
     }
     RC(attention_fwd(qkv, qkv + H, qkv + 2 * H, 3 * H, ao, H, cu, B, frames, rows, heads, heads, 64, 0.125f, 0,
-                     s.lse + static_cast<size_t>(l) * rows * heads, stream, reg ? &adrop : nullptr));
+                     s.lse + static_cast<size_t>(l) * rows * heads, fmt, stream, reg ? &adrop : nullptr));
     {
       GemmArgs g = lin(ao, Ly.wo, rows, H, H);
       g.epi = EPI_RESID_F32;
@@ -354,9 +354,9 @@ int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, in
       g.out = h_mid;
       g.resid = h_in;
       if (reg) set_drop(g, make_drop_spec(reg->seed, site_attn_out(l), reg->p_hidden));
-      RC(gemm_bf16_launch(g, stream));
+      RC(gemm_launch_fmt(g, fmt, stream));
     }
-    RC(layernorm_fwd(h_mid, 0, Ly.ln2_g, Ly.ln2_b, eps, 0, xn, rows, H, stream));
+    RC(layernorm_fwd(h_mid, 0, Ly.ln2_g, Ly.ln2_b, eps, 0, xn, rows, H, fmt, stream));
     {
       GemmArgs g = lin(xn, Ly.w1, rows, F, H);
       g.epi = EPI_BF16;
@@ -366,7 +366,7 @@ int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, in
       g.out2 = ffp;
       g.ld2 = F;
       if (reg) set_drop(g, make_drop_spec(reg->seed, site_ff_act(l), reg->p_activation));
-      RC(gemm_bf16_launch(g, stream));
+      RC(gemm_launch_fmt(g, fmt, stream));
     }
     {
       GemmArgs g = lin(ff, Ly.w2, rows, H, F);
@@ -375,7 +375,7 @@ int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, in
       g.out = h_out;
       g.resid = h_mid;
       if (reg) set_drop(g, make_drop_spec(reg->seed, site_ff_out(l), reg->p_hidden));
-      RC(gemm_bf16_launch(g, stream));
+      RC(gemm_launch_fmt(g, fmt, stream));
     }
   }
   return B2S_OK;
@@ -383,13 +383,18 @@ int stack_forward_train(const b2s_encoder_layer* layers, int L, int H, int F, in
 
 // on entry b.dh / b.dyb hold d(loss)/d(h[L]) (fp32 / bf16); on exit d(loss)/d(h[0])
 int stack_backward(const b2s_encoder_layer* layers, const b2s_encoder_layer_grads* grads, int L, int H, int F, int heads,
-                   float eps, const StackBufs& s, const StackScratch& b, const int* cu, int B, int frames,
-                   cudaStream_t stream, const b2s_encoder_regularizers* reg = nullptr, long long rows_packed = -1) {
+                   float eps, const StackBufs& s, const StackScratch& b, const int* cu, int B, int frames, int fmt,
+                   cudaStream_t stream, const b2s_encoder_regularizers* reg = nullptr, long long rows_packed = -1,
+                   void* const* layer_done = nullptr) {
   const long long rows = rows_packed >= 0 ? rows_packed : static_cast<long long>(B) * frames;
   const size_t rH = static_cast<size_t>(rows) * H;
   const bool drop_h = reg != nullptr && reg->p_hidden > 0.f;
   for (int l = L - 1; l >= 0; --l) {
-    if (layer_skipped(reg, l)) continue;  // identity layer: the gradient passes through unchanged
+    if (layer_skipped(reg, l)) {  // identity layer: the gradient passes through unchanged
+      if (layer_done != nullptr && layer_done[l] != nullptr)
+        B2S_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(layer_done[l]), stream));
+      continue;
+    }
     const b2s_encoder_layer& Ly = layers[l];
     const b2s_encoder_layer_grads& G = grads[l];
     const float* h_in = s.h + l * rH;
@@ -400,44 +405,48 @@ int stack_backward(const b2s_encoder_layer* layers, const b2s_encoder_layer_grad
     const __nv_bfloat16* ff = reinterpret_cast<const __nv_bfloat16*>(s.ff) + static_cast<size_t>(l) * rows * F;
     // feed-forward: h_out = h_mid + drop(W2 drop(gelu(W1 LN2(h_mid) + b1)) + b2)
     if (drop_h) {  // the branch gradient is the masked copy; the residual path keeps b.dh
-      RC(dropout_apply(nullptr, b.dyb, rows * H, make_drop_spec(reg->seed, site_ff_out(l), reg->p_hidden), stream));
-      RC(colsum_accum(b.dyb, 1, G.b2, rows, H, stream));
+      RC(dropout_apply(nullptr, b.dyb, rows * H, make_drop_spec(reg->seed, site_ff_out(l), reg->p_hidden), fmt, stream));
+      RC(colsum_accum(b.dyb, 1, G.b2, rows, H, fmt, stream));
     } else {
-      RC(colsum_accum(b.dh, 0, G.b2, rows, H, stream));
+      RC(colsum_accum(b.dh, 0, G.b2, rows, H, fmt, stream));
     }
-    RC(wgrad(b.dyb, ff, rows, H, F, G.w2, stream));
-    RC(dgrad(b.dyb, Ly.w2, rows, H, F, EPI_BF16, b.dbig, stream));
+    RC(wgrad(b.dyb, ff, rows, H, F, G.w2, fmt, stream));
+    RC(dgrad(b.dyb, Ly.w2, rows, H, F, EPI_BF16, b.dbig, fmt, stream));
     {
       const DropSpec dact = reg ? make_drop_spec(reg->seed, site_ff_act(l), reg->p_activation) : DropSpec{};
-      RC(gelu_bwd(ffp, b.dbig, b.dbig, rows * F, stream, dact.thresh != 0u ? &dact : nullptr));
+      RC(gelu_bwd(ffp, b.dbig, b.dbig, rows * F, fmt, stream, dact.thresh != 0u ? &dact : nullptr));
     }
-    RC(colsum_accum(b.dbig, 1, G.b1, rows, F, stream));
-    RC(layernorm_fwd(h_mid, 0, Ly.ln2_g, Ly.ln2_b, eps, 0, b.xn, rows, H, stream));
-    RC(wgrad(b.dbig, b.xn, rows, F, H, G.w1, stream));
-    RC(dgrad(b.dbig, Ly.w1, rows, F, H, EPI_BF16, b.dsm, stream));
+    RC(colsum_accum(b.dbig, 1, G.b1, rows, F, fmt, stream));
+    RC(layernorm_fwd(h_mid, 0, Ly.ln2_g, Ly.ln2_b, eps, 0, b.xn, rows, H, fmt, stream));
+    RC(wgrad(b.dbig, b.xn, rows, F, H, G.w1, fmt, stream));
+    RC(dgrad(b.dbig, Ly.w1, rows, F, H, EPI_BF16, b.dsm, fmt, stream));
     RC(layernorm_bwd_ex(h_mid, 0, Ly.ln2_g, Ly.ln2_b, 0, eps, b.dsm, 1, b.dh, 1, b.dyb, G.ln2_g, G.ln2_b, rows, H,
+                        fmt,
                         stream));
     // attention: h_mid = h_in + drop(Wo attn(Wqkv LN1(h_in) + bqkv) + bo)
     if (drop_h) {
-      RC(dropout_apply(nullptr, b.dyb, rows * H, make_drop_spec(reg->seed, site_attn_out(l), reg->p_hidden), stream));
-      RC(colsum_accum(b.dyb, 1, G.bo, rows, H, stream));
+      RC(dropout_apply(nullptr, b.dyb, rows * H, make_drop_spec(reg->seed, site_attn_out(l), reg->p_hidden), fmt, stream));
+      RC(colsum_accum(b.dyb, 1, G.bo, rows, H, fmt, stream));
     } else {
-      RC(colsum_accum(b.dh, 0, G.bo, rows, H, stream));
+      RC(colsum_accum(b.dh, 0, G.bo, rows, H, fmt, stream));
     }
-    RC(wgrad(b.dyb, ao, rows, H, H, G.wo, stream));
-    RC(dgrad(b.dyb, Ly.wo, rows, H, H, EPI_BF16, b.dsm, stream));
+    RC(wgrad(b.dyb, ao, rows, H, H, G.wo, fmt, stream));
+    RC(dgrad(b.dyb, Ly.wo, rows, H, H, EPI_BF16, b.dsm, fmt, stream));
     {
       __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(b.dbig);
       const AttnDrop adrop = attn_drop(reg, l);
       RC(attention_bwd(qkv, qkv + H, qkv + 2 * H, 3 * H, ao, H, b.dsm, H, s.lse + static_cast<size_t>(l) * rows * heads,
                        b.delta, dqkv, dqkv + H, dqkv + 2 * H, 3 * H, cu, B, frames, rows, heads, heads, 64, 0.125f, 0,
-                       nullptr, stream, reg ? &adrop : nullptr));
+                       nullptr, fmt, stream, reg ? &adrop : nullptr));
     }
-    RC(colsum_accum(b.dbig, 1, G.bqkv, rows, 3 * H, stream));
-    RC(layernorm_fwd(h_in, 0, Ly.ln1_g, Ly.ln1_b, eps, 0, b.xn, rows, H, stream));
-    RC(wgrad(b.dbig, b.xn, rows, 3 * H, H, G.wqkv, stream));
-    RC(dgrad(b.dbig, Ly.wqkv, rows, 3 * H, H, EPI_BF16, b.dsm, stream));
-    RC(layernorm_bwd_ex(h_in, 0, Ly.ln1_g, Ly.ln1_b, 0, eps, b.dsm, 1, b.dh, 1, b.dyb, G.ln1_g, G.ln1_b, rows, H, stream));
+    RC(colsum_accum(b.dbig, 1, G.bqkv, rows, 3 * H, fmt, stream));
+    RC(layernorm_fwd(h_in, 0, Ly.ln1_g, Ly.ln1_b, eps, 0, b.xn, rows, H, fmt, stream));
+    RC(wgrad(b.dbig, b.xn, rows, 3 * H, H, G.wqkv, fmt, stream));
+    RC(dgrad(b.dbig, Ly.wqkv, rows, 3 * H, H, EPI_BF16, b.dsm, fmt, stream));
+    RC(layernorm_bwd_ex(h_in, 0, Ly.ln1_g, Ly.ln1_b, 0, eps, b.dsm, 1, b.dh, 1, b.dyb, G.ln1_g, G.ln1_b, rows, H, fmt, stream));
+    // every gradient of layer l has been enqueued: a communication stream may start exchanging them (training.py)
+    if (layer_done != nullptr && layer_done[l] != nullptr)
+      B2S_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(layer_done[l]), stream));
   }
   return B2S_OK;
 }
@@ -446,15 +455,16 @@ int stack_backward(const b2s_encoder_layer* layers, const b2s_encoder_layer_grad
 int head_backward(const void* proj_w, const float* final_ln_g, const float* final_ln_b, float* g_proj_w, float* g_proj_b,
                   float* g_ln_g, float* g_ln_b, const float* h_last, const void* pooled_x, const float* d_audio_embeds,
                   void* da, float* dpool, float* dxn_f, const StackScratch& b, int B, int frames, int pooled, int H,
-                  int Cl, int pool_kernel, int pool_stride, float eps, cudaStream_t stream) {
+                  int Cl, int pool_kernel, int pool_stride, float eps, int fmt, cudaStream_t stream) {
   const long long rows = static_cast<long long>(B) * frames;
   const long long np = static_cast<long long>(B) * pooled;
-  RC(cast_f32_to_bf16(d_audio_embeds, da, np * Cl, stream));
-  RC(colsum_accum(d_audio_embeds, 0, g_proj_b, np, Cl, stream));
-  RC(wgrad(da, pooled_x, np, Cl, H, g_proj_w, stream));
-  RC(dgrad(da, proj_w, np, Cl, H, EPI_F32, dpool, stream));
+  RC(cast_f32_to_h16(d_audio_embeds, da, np * Cl, fmt, stream));
+  RC(colsum_accum(d_audio_embeds, 0, g_proj_b, np, Cl, fmt, stream));
+  RC(wgrad(da, pooled_x, np, Cl, H, g_proj_w, fmt, stream));
+  RC(dgrad(da, proj_w, np, Cl, H, EPI_F32, dpool, fmt, stream));
   RC(avgpool_bwd(dpool, dxn_f, B, frames, H, pool_kernel, pool_stride, pooled, stream));
   RC(layernorm_bwd_ex(h_last, 0, final_ln_g, final_ln_b, 0, eps, dxn_f, 0, b.dh, 0, b.dyb, g_ln_g, g_ln_b, rows, H,
+                      fmt,
                       stream));
   return B2S_OK;
 }
@@ -501,7 +511,7 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
               saved_bytes);
   B2S_REQUIRE(s.frames > 0 && s.pooled > 0, "hubert_forward_train: audio too short (%d samples -> %d frames)", samples,
               s.frames);
-  const int B = batches, H = w->hidden, F = w->ffn, L = w->num_layers;
+  const int B = batches, H = w->hidden, F = w->ffn, L = w->num_layers, fmt = w->fmt;
   const long long rows = static_cast<long long>(B) * s.frames;
   const float eps = w->ln_eps;
   Ragged rg;
@@ -516,7 +526,7 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
   }
 
   RC(conv0_ln_gelu_fwd(wave, wave_stride, B, samples, w->conv0_w, w->conv0_b, w->conv0_ln_g, w->conv0_ln_b, eps,
-                       s.conv_x[0], s.t[1], stream));
+                       s.conv_x[0], s.t[1], fmt, stream));
   for (int i = 0; i < 6; ++i) {
     const int tin = s.t[i + 1], tout = s.t[i + 2];
     const int k = w->conv_k[i], sd = w->conv_stride[i];
@@ -540,25 +550,25 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
     g.out = s.conv_pre[i];
     g.ldo = 512;
     g.out_batch_rows = tout;
-    RC(gemm_bf16_launch(g, stream));
+    RC(gemm_launch_fmt(g, fmt, stream));
     RC(layernorm_fwd(s.conv_pre[i], 0, w->conv_ln_g[i], w->conv_ln_b[i], eps, 1, s.conv_x[i + 1],
-                     static_cast<long long>(B) * tout, 512, stream));
+                     static_cast<long long>(B) * tout, 512, fmt, stream));
   }
   // feature projection -> h[0]
-  RC(layernorm_fwd(s.conv_x[6], 1, w->fp_ln_g, w->fp_ln_b, eps, 0, s.xn, rows, 512, stream));
+  RC(layernorm_fwd(s.conv_x[6], 1, w->fp_ln_g, w->fp_ln_b, eps, 0, s.xn, rows, 512, fmt, stream));
   {
     GemmArgs g = lin(s.xn, w->fp_w, rows, H, 512);
     g.epi = EPI_F32;
     g.bias = w->fp_b;
     g.out = h0;
     if (reg) set_drop(g, make_drop_spec(reg->seed, SITE_FEAT_PROJ, reg->p_feat_proj));
-    RC(gemm_bf16_launch(g, stream));
+    RC(gemm_launch_fmt(g, fmt, stream));
   }
   if (reg && reg->time_mask)  // SpecAugment: masked frames become masked_spec_embed (after the projection dropout)
     RC(mask_rows_f32(h0, reg->time_mask, reg->masked_spec_embed, rows, H, stream));
   if (rg.on)  // frames past an utterance's end become the zero padding its positional conv must see
     RC(mask_rows_f32(h0, s.tail, s.zeros_h, rows, H, stream));
-  RC(cast_f32_to_bf16(h0, s.hp_bf, rows * H, stream));
+  RC(cast_f32_to_h16(h0, s.hp_bf, rows * H, fmt, stream));
   {
     GemmArgs g{};
     g.A = s.hp_bf;
@@ -587,10 +597,10 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
     g.out_batch_rows = s.frames;
     g.out2 = s.pos_pre;
     g.ld2 = H;
-    RC(gemm_bf16_launch(g, stream));
+    RC(gemm_launch_fmt(g, fmt, stream));
   }
   if (reg)  // dropout(hidden + positional embedding): after the residual add, so not an epilogue of that GEMM
-    RC(dropout_apply(h0, nullptr, rows * H, make_drop_spec(reg->seed, SITE_POS_ADD, reg->p_hidden), stream));
+    RC(dropout_apply(h0, nullptr, rows * H, make_drop_spec(reg->seed, SITE_POS_ADD, reg->p_hidden), fmt, stream));
   const long long srows = rg.on ? rg.rows_packed : rows;  // rows of the transformer stack
   if (rg.on) {
     RC(gather_rows_f32(h0, s.pack_idx, s.h, srows, H, stream));  // padded -> packed valid rows
@@ -602,7 +612,7 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
   {
     StackBufs sb{s.h, s.h_mid, s.lse, s.qkv, s.ao, s.ff_pre, s.ff};
     RC(stack_forward_train(w->layers, L, H, F, w->heads, eps, sb, s.xn, s.cu, B, rg.on ? rg.max_frames : s.frames,
-                           stream, reg, rg.on ? srows : -1));
+                           fmt, stream, reg, rg.on ? srows : -1));
   }
   const float* h_last = s.h + L * rH;
   if (rg.on) {  // packed -> padded (tail rows zero) for the per-utterance pooling windows
@@ -610,13 +620,13 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
     h_last = s.hpad;
   }
   RC(layernorm_avgpool_fwd(h_last, w->final_ln_g, w->final_ln_b, eps, s.pooled_x, B, s.frames, H, w->pool_kernel,
-                           w->pool_stride, s.pooled, stream));
+                           w->pool_stride, s.pooled, fmt, stream));
   {
     GemmArgs g = lin(s.pooled_x, w->proj_w, static_cast<long long>(B) * s.pooled, w->llm_dim, H);
     g.epi = EPI_F32;
     g.bias = w->proj_b;
     g.out = audio_embeds;
-    RC(gemm_bf16_launch(g, stream));
+    RC(gemm_launch_fmt(g, fmt, stream));
   }
   return B2S_OK;
 }
@@ -624,7 +634,7 @@ int hubert_forward_train(const b2s_hubert_weights* w, const float* wave, long lo
 int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const b2s_hubert_grads* gr, const float* wave,
                     long long wave_stride, int batches, int samples, const int* samples_per_utt, void* saved,
                     size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
-                    const b2s_encoder_regularizers* reg, cudaStream_t stream) {
+                    const b2s_encoder_regularizers* reg, void* const* layer_done, cudaStream_t stream) {
   B2S_REQUIRE(w && pos_w_dgrad && gr && gr->layers && wave && saved && d_audio_embeds && workspace,
               "hubert_backward: null pointer");
   RC(check_regularizers(reg));
@@ -635,7 +645,7 @@ int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const 
   plan_bwd(w, batches, s, workspace, workspace_bytes, &b);
   B2S_REQUIRE(b.bytes <= workspace_bytes, "hubert_backward: workspace too small: need %zu bytes, got %zu", b.bytes,
               workspace_bytes);
-  const int B = batches, H = w->hidden, F = w->ffn, L = w->num_layers, Cl = w->llm_dim;
+  const int B = batches, H = w->hidden, F = w->ffn, L = w->num_layers, Cl = w->llm_dim, fmt = w->fmt;
   const long long rows = static_cast<long long>(B) * s.frames;
   const float eps = w->ln_eps;
   Ragged rg;
@@ -651,27 +661,27 @@ int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const 
     StackScratch sc_pad{b.dh_pad, b.delta, b.dyb_pad, b.dbig, b.dsm, b.xn};
     RC(head_backward(w->proj_w, w->final_ln_g, w->final_ln_b, gr->proj_w, gr->proj_b, gr->final_ln_g, gr->final_ln_b,
                      s.hpad, s.pooled_x, d_audio_embeds, b.da, b.dpool, b.dxn_f, sc_pad, B, s.frames, s.pooled, H, Cl,
-                     w->pool_kernel, w->pool_stride, eps, stream));
+                     w->pool_kernel, w->pool_stride, eps, fmt, stream));
     RC(gather_rows_f32(b.dh_pad, s.pack_idx, b.dh, srows, H, stream));
-    RC(cast_f32_to_bf16(b.dh, b.dyb, srows * H, stream));
+    RC(cast_f32_to_h16(b.dh, b.dyb, srows * H, fmt, stream));
   } else {
     RC(head_backward(w->proj_w, w->final_ln_g, w->final_ln_b, gr->proj_w, gr->proj_b, gr->final_ln_g, gr->final_ln_b,
                      s.h + L * rH, s.pooled_x, d_audio_embeds, b.da, b.dpool, b.dxn_f, sc, B, s.frames, s.pooled, H,
-                     Cl, w->pool_kernel, w->pool_stride, eps, stream));
+                     Cl, w->pool_kernel, w->pool_stride, eps, fmt, stream));
   }
   RC(stack_backward(w->layers, gr->layers, L, H, F, w->heads, eps, sb, sc, s.cu, B, rg.on ? rg.max_frames : s.frames,
-                    stream, reg, rg.on ? srows : -1));
+                    fmt, stream, reg, rg.on ? srows : -1, layer_done));
   if (rg.on) {  // packed -> padded gradient of h0 (tail rows zero); the front end's backward runs on the padded layout
     RC(gather_rows_f32(b.dh, s.unpack_idx, b.dh_pad, rows, H, stream));
-    RC(cast_f32_to_bf16(b.dh_pad, b.dyb_pad, rows * H, stream));
+    RC(cast_f32_to_h16(b.dh_pad, b.dyb_pad, rows * H, fmt, stream));
     b.dh = b.dh_pad;
     b.dyb = b.dyb_pad;
   }
 
   // ---- positional conv embedding: h0 = drop(hp + gelu(conv(hp) + b)); dh / dyb = gradient w.r.t. h0
-  if (reg) RC(dropout_apply(b.dh, b.dyb, rows * H, make_drop_spec(reg->seed, SITE_POS_ADD, reg->p_hidden), stream));
-  RC(gelu_bwd(s.pos_pre, b.dyb, b.dsm, rows * H, stream));  // dsm = d(pre-GELU conv output), bf16
-  RC(colsum_accum(b.dsm, 1, gr->pos_b, rows, H, stream));
+  if (reg) RC(dropout_apply(b.dh, b.dyb, rows * H, make_drop_spec(reg->seed, SITE_POS_ADD, reg->p_hidden), fmt, stream));
+  RC(gelu_bwd(s.pos_pre, b.dyb, b.dsm, rows * H, fmt, stream));  // dsm = d(pre-GELU conv output), bf16
+  RC(colsum_accum(b.dsm, 1, gr->pos_b, rows, H, fmt, stream));
   {
     // grouped wgrad: dW[g*64 + o][tap*64 + i] += sum_{b,t} dsm[b, t, g*64 + o] * hp[b, t + tap - pad, g*64 + i]
     GemmArgs g{};
@@ -704,7 +714,7 @@ int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const 
     g.out_group_rows = 64;
     g.out_group_cols = 0;
     g.cta_group = 1;
-    RC(gemm_bf16_launch(g, stream));
+    RC(gemm_launch_fmt(g, fmt, stream));
   }
   {
     // grouped dgrad: dh += conv^T(dsm) -- the forward's tap walk with flipped taps and transposed 64x64 blocks
@@ -731,7 +741,7 @@ int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const 
     g.resid = b.dh;
     g.ldo = H;
     g.out_batch_rows = s.frames;
-    RC(gemm_bf16_launch(g, stream));
+    RC(gemm_launch_fmt(g, fmt, stream));
   }
   // ---- feature projection: hp = specaug(drop(fp_w LN(conv_x[6]) + fp_b)) ; dh = gradient w.r.t. hp
   if (rg.on)  // the forward zeroed the tail rows: they pass no gradient on (the conv transpose wrote into them)
@@ -739,23 +749,23 @@ int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const 
   if (reg)
     RC(featproj_reg_bwd(b.dh, reg->time_mask, reg->g_masked_spec_embed, rows, H,
                         make_drop_spec(reg->seed, SITE_FEAT_PROJ, reg->p_feat_proj), stream));
-  RC(colsum_accum(b.dh, 0, gr->fp_b, rows, H, stream));
-  RC(cast_f32_to_bf16(b.dh, b.dyb, rows * H, stream));
-  RC(layernorm_fwd(s.conv_x[6], 1, w->fp_ln_g, w->fp_ln_b, eps, 0, b.xn, rows, 512, stream));
-  RC(wgrad(b.dyb, b.xn, rows, H, 512, gr->fp_w, stream));
-  RC(dgrad(b.dyb, w->fp_w, rows, H, 512, EPI_BF16, b.dsm, stream));
+  RC(colsum_accum(b.dh, 0, gr->fp_b, rows, H, fmt, stream));
+  RC(cast_f32_to_h16(b.dh, b.dyb, rows * H, fmt, stream));
+  RC(layernorm_fwd(s.conv_x[6], 1, w->fp_ln_g, w->fp_ln_b, eps, 0, b.xn, rows, 512, fmt, stream));
+  RC(wgrad(b.dyb, b.xn, rows, H, 512, gr->fp_w, fmt, stream));
+  RC(dgrad(b.dyb, w->fp_w, rows, H, 512, EPI_BF16, b.dsm, fmt, stream));
   void* dcur = b.dxa;  // gradient w.r.t. conv_x[6], bf16 [B, frames, 512]
   void* dnxt = b.dxb;
   RC(layernorm_bwd_ex(s.conv_x[6], 1, w->fp_ln_g, w->fp_ln_b, 0, eps, b.dsm, 1, nullptr, 0, dcur, gr->fp_ln_g,
-                      gr->fp_ln_b, rows, 512, stream));
+                      gr->fp_ln_b, rows, 512, fmt, stream));
   // ---- conv feature extractor, layers 6..1 (implicit GEMM) then layer 0
   for (int i = 5; i >= 0; --i) {
     const int tin = s.t[i + 1], tout = s.t[i + 2];
     const int k = w->conv_k[i], sd = w->conv_stride[i];
     const long long orows = static_cast<long long>(B) * tout;
     RC(layernorm_bwd_ex(s.conv_pre[i], 0, w->conv_ln_g[i], w->conv_ln_b[i], 1, eps, dcur, 1, nullptr, 0, b.dpre,
-                        gr->conv_ln_g[i], gr->conv_ln_b[i], orows, 512, stream));
-    RC(colsum_accum(b.dpre, 1, gr->conv_b[i], orows, 512, stream));
+                        gr->conv_ln_g[i], gr->conv_ln_b[i], orows, 512, fmt, stream));
+    RC(colsum_accum(b.dpre, 1, gr->conv_b[i], orows, 512, fmt, stream));
     {
       GemmArgs g{};
       g.A = b.dpre;
@@ -780,16 +790,16 @@ int hubert_backward(const b2s_hubert_weights* w, const void* pos_w_dgrad, const 
       g.epi = EPI_ACCUM_F32;
       g.out = gr->conv_w[i];
       g.ldo = static_cast<long long>(k) * 512;
-      RC(gemm_bf16_launch(g, stream));
+      RC(gemm_launch_fmt(g, fmt, stream));
     }
-    RC(dgrad(b.dpre, w->conv_w[i], orows, 512, k * 512, EPI_BF16, b.dcol, stream));
-    RC(col2im_add(b.dcol, dnxt, B, tin, tout, k, sd, 512, stream));
+    RC(dgrad(b.dpre, w->conv_w[i], orows, 512, k * 512, EPI_BF16, b.dcol, fmt, stream));
+    RC(col2im_add(b.dcol, dnxt, B, tin, tout, k, sd, 512, fmt, stream));
     void* tmp = dcur;
     dcur = dnxt;
     dnxt = tmp;
   }
   RC(conv0_bwd(wave, wave_stride, B, samples, w->conv0_w, w->conv0_b, w->conv0_ln_g, w->conv0_ln_b, eps, dcur, s.t[1],
-               gr->conv0_w, gr->conv0_b, gr->conv0_ln_g, gr->conv0_ln_b, stream));
+               gr->conv0_w, gr->conv0_b, gr->conv0_ln_g, gr->conv0_ln_b, fmt, stream));
   return B2S_OK;
 }
 
@@ -894,10 +904,10 @@ int whisper_forward_train(const b2s_whisper_weights* w, const float* mel, int ba
   plan_wsaved(w, batches, saved, saved_bytes, &s);
   B2S_REQUIRE(s.bytes <= saved_bytes && s.pooled > 0, "whisper_forward_train: saved region too small (%zu < %zu)",
               saved_bytes, s.bytes);
-  const int B = batches, H = w->hidden, F = w->ffn, C = w->mel_bins, T = frames_in, L = w->num_layers;
+  const int B = batches, H = w->hidden, F = w->ffn, C = w->mel_bins, T = frames_in, L = w->num_layers, fmt = w->fmt;
   const long long rows = static_cast<long long>(B) * s.frames;
 
-  RC(mel_to_padded_cl(mel, s.x0, B, C, T, stream));
+  RC(mel_to_padded_cl(mel, s.x0, B, C, T, fmt, stream));
   B2S_CUDA_CHECK(cudaMemsetAsync(s.x1, 0, static_cast<size_t>(B) * (T + 2) * H * 2, stream));
   B2S_CUDA_CHECK(cudaMemsetAsync(s.pre1, 0, static_cast<size_t>(B) * (T + 2) * H * 2, stream));
   {
@@ -924,7 +934,7 @@ int whisper_forward_train(const b2s_whisper_weights* w, const float* mel, int ba
     g.out_batch_rows = T + 2;
     g.out2 = reinterpret_cast<__nv_bfloat16*>(s.pre1) + H;
     g.ld2 = H;
-    RC(gemm_bf16_launch(g, stream));
+    RC(gemm_launch_fmt(g, fmt, stream));
   }
   {
     GemmArgs g{};
@@ -952,27 +962,27 @@ int whisper_forward_train(const b2s_whisper_weights* w, const float* mel, int ba
     g.out_batch_rows = s.frames;
     g.out2 = s.pre2;
     g.ld2 = H;
-    RC(gemm_bf16_launch(g, stream));
+    RC(gemm_launch_fmt(g, fmt, stream));
   }
   iota_scaled<<<(B + 1 + 255) / 256, 256, 0, stream>>>(s.cu, B + 1, s.frames);
   B2S_LAUNCH_CHECK();
   StackBufs sb{s.h, s.h_mid, s.lse, s.qkv, s.ao, s.ff_pre, s.ff};
-  RC(stack_forward_train(w->layers, L, H, F, w->heads, w->ln_eps, sb, s.xn, s.cu, B, s.frames, stream));
+  RC(stack_forward_train(w->layers, L, H, F, w->heads, w->ln_eps, sb, s.xn, s.cu, B, s.frames, fmt, stream));
   RC(layernorm_avgpool_fwd(s.h + static_cast<size_t>(L) * rows * H, w->final_ln_g, w->final_ln_b, w->ln_eps, s.pooled_x,
-                           B, s.frames, H, w->pool_kernel, w->pool_stride, s.pooled, stream));
+                           B, s.frames, H, w->pool_kernel, w->pool_stride, s.pooled, fmt, stream));
   {
     GemmArgs g = lin(s.pooled_x, w->proj_w, static_cast<long long>(B) * s.pooled, w->llm_dim, H);
     g.epi = EPI_F32;
     g.bias = w->proj_b;
     g.out = audio_embeds;
-    RC(gemm_bf16_launch(g, stream));
+    RC(gemm_launch_fmt(g, fmt, stream));
   }
   return B2S_OK;
 }
 
 int whisper_backward(const b2s_whisper_weights* w, const b2s_whisper_grads* gr, int batches, void* saved,
                      size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
-                     cudaStream_t stream) {
+                     void* const* layer_done, cudaStream_t stream) {
   B2S_REQUIRE(w && gr && gr->layers && saved && d_audio_embeds && workspace, "whisper_backward: null pointer");
   WSaved s;
   plan_wsaved(w, batches, saved, saved_bytes, &s);
@@ -981,18 +991,19 @@ int whisper_backward(const b2s_whisper_weights* w, const b2s_whisper_grads* gr, 
   plan_wbwd(w, batches, s, workspace, workspace_bytes, &b);
   B2S_REQUIRE(b.bytes <= workspace_bytes, "whisper_backward: workspace too small: need %zu bytes, got %zu", b.bytes,
               workspace_bytes);
-  const int B = batches, H = w->hidden, F = w->ffn, C = w->mel_bins, T = s.frames_in, L = w->num_layers;
+  const int B = batches, H = w->hidden, F = w->ffn, C = w->mel_bins, T = s.frames_in, L = w->num_layers, fmt = w->fmt;
   const long long rows = static_cast<long long>(B) * s.frames;
   const size_t rH = static_cast<size_t>(rows) * H;
   StackBufs sb{s.h, s.h_mid, s.lse, s.qkv, s.ao, s.ff_pre, s.ff};
   StackScratch sc{b.dh, b.delta, b.dyb, b.dbig, b.dsm, b.xn};
   RC(head_backward(w->proj_w, w->final_ln_g, w->final_ln_b, gr->proj_w, gr->proj_b, gr->final_ln_g, gr->final_ln_b,
                    s.h + L * rH, s.pooled_x, d_audio_embeds, b.da, b.dpool, b.dxn_f, sc, B, s.frames, s.pooled, H,
-                   w->llm_dim, w->pool_kernel, w->pool_stride, w->ln_eps, stream));
-  RC(stack_backward(w->layers, gr->layers, L, H, F, w->heads, w->ln_eps, sb, sc, s.cu, B, s.frames, stream));
+                   w->llm_dim, w->pool_kernel, w->pool_stride, w->ln_eps, fmt, stream));
+  RC(stack_backward(w->layers, gr->layers, L, H, F, w->heads, w->ln_eps, sb, sc, s.cu, B, s.frames, fmt, stream, nullptr,
+                    -1, layer_done));
   // ---- conv2: h0 = gelu(conv2(x1) + b2) + pos (pos frozen); dyb = bf16 d(loss)/d(h0)
-  RC(gelu_bwd(s.pre2, b.dyb, b.dpre2, rows * H, stream));
-  RC(colsum_accum(b.dpre2, 1, gr->conv2_b, rows, H, stream));
+  RC(gelu_bwd(s.pre2, b.dyb, b.dpre2, rows * H, fmt, stream));
+  RC(colsum_accum(b.dpre2, 1, gr->conv2_b, rows, H, fmt, stream));
   {
     GemmArgs g{};  // dW2[o, (j, c)] += sum_{b,t} dpre2[b,t,o] * x1p[b, 2t + j, c]
     g.A = b.dpre2;
@@ -1017,16 +1028,16 @@ int whisper_backward(const b2s_whisper_weights* w, const b2s_whisper_grads* gr, 
     g.epi = EPI_ACCUM_F32;
     g.out = gr->conv2_w;
     g.ldo = 3LL * H;
-    RC(gemm_bf16_launch(g, stream));
+    RC(gemm_launch_fmt(g, fmt, stream));
   }
-  RC(dgrad(b.dpre2, w->conv2_w, rows, H, 3 * H, EPI_BF16, b.dcol, stream));
-  RC(col2im_add(b.dcol, b.dx1, B, T + 2, s.frames, 3, 2, H, stream));  // gradient on the PADDED x1 rows
+  RC(dgrad(b.dpre2, w->conv2_w, rows, H, 3 * H, EPI_BF16, b.dcol, fmt, stream));
+  RC(col2im_add(b.dcol, b.dx1, B, T + 2, s.frames, 3, 2, H, fmt, stream));  // gradient on the PADDED x1 rows
   // ---- conv1: x1 = gelu(conv1(x0) + b1); the two padding rows of every utterance carry no gradient
-  RC(gelu_bwd(s.pre1, b.dx1, b.dx1, static_cast<long long>(B) * (T + 2) * H, stream));
+  RC(gelu_bwd(s.pre1, b.dx1, b.dx1, static_cast<long long>(B) * (T + 2) * H, fmt, stream));
   B2S_CUDA_CHECK(cudaMemset2DAsync(b.dx1, static_cast<size_t>(T + 2) * H * 2, 0, static_cast<size_t>(H) * 2, B, stream));
   B2S_CUDA_CHECK(cudaMemset2DAsync(reinterpret_cast<__nv_bfloat16*>(b.dx1) + static_cast<size_t>(T + 1) * H,
                                    static_cast<size_t>(T + 2) * H * 2, 0, static_cast<size_t>(H) * 2, B, stream));
-  RC(colsum_accum(b.dx1, 1, gr->conv1_b, static_cast<long long>(B) * (T + 2), H, stream));
+  RC(colsum_accum(b.dx1, 1, gr->conv1_b, static_cast<long long>(B) * (T + 2), H, fmt, stream));
   {
     GemmArgs g{};  // dW1[o, (j, c)] += sum_{b,t} dpre1[b,t,o] * x0p[b, t + j, c]
     g.A = reinterpret_cast<__nv_bfloat16*>(b.dx1) + H;
@@ -1051,7 +1062,7 @@ int whisper_backward(const b2s_whisper_weights* w, const b2s_whisper_grads* gr, 
     g.epi = EPI_ACCUM_F32;
     g.out = gr->conv1_w;
     g.ldo = 3LL * C;
-    RC(gemm_bf16_launch(g, stream));
+    RC(gemm_launch_fmt(g, fmt, stream));
   }
   return B2S_OK;
 }

@@ -172,10 +172,79 @@ class WhisperBackbone(nn.Module):
         self.layer_norm = _Params(weight=(arch.hidden,), bias=(arch.hidden,))
 
 
+def _random_init_requested(config) -> bool:
+    return bool(getattr(config.model.audio_encoder, "random_init", False))
+
+
+@torch.no_grad()
+def init_hf_default_(backbone: nn.Module, seed: int = 1234) -> nn.Module:
+    """HF's `_init_weights` distributions for a from-scratch backbone (TF/models/hubert/modeling_hubert.py:640-673,
+    TF/models/whisper/modeling_whisper.py `_init_weights`): Linear / Whisper conv N(0, 0.02), HuBERT feature-extractor
+    convs kaiming-normal, LayerNorm 1 / 0, biases 0, positional conv N(0, 2 sqrt(1 / (k C_in))) under weight-norm,
+    masked_spec_embed uniform, Whisper's frozen sinusoid table. Only used when the config says
+    `model.audio_encoder.random_init: true` (benchmarks, tests): the default is the pretrained checkpoint."""
+    import math
+    g = torch.Generator().manual_seed(int(seed))
+    v_param = None
+    for name, p in backbone.named_parameters():
+        if "layer_norm.weight" in name:
+            p.fill_(1.0)
+        elif name.endswith("bias") or name.endswith(".bias"):
+            p.zero_()
+        elif name.endswith("masked_spec_embed"):
+            p.copy_(torch.rand(p.shape, generator=g))
+        elif name.endswith("parametrizations.weight.original1"):
+            cout, cin_g, k = p.shape
+            p.copy_(torch.randn(p.shape, generator=g) * (2.0 * math.sqrt(1.0 / (k * cout))))
+            v_param = p
+        elif name.endswith("parametrizations.weight.original0"):
+            pass  # = ||v|| per tap, set below
+        elif name.endswith("embed_positions.weight"):
+            length, channels = p.shape
+            inc = math.log(10000.0) / (channels // 2 - 1)
+            inv = torch.exp(-inc * torch.arange(channels // 2, dtype=torch.float32))
+            t = torch.arange(length, dtype=torch.float32)[:, None] * inv[None, :]
+            p.copy_(torch.cat([t.sin(), t.cos()], dim=1))
+        elif "feature_extractor.conv_layers" in name and name.endswith("conv.weight"):
+            fan_in = p.shape[1] * p.shape[2]
+            p.copy_(torch.randn(p.shape, generator=g) * math.sqrt(2.0 / fan_in))
+        else:
+            p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    if v_param is not None:
+        for name, p in backbone.named_parameters():
+            if name.endswith("parametrizations.weight.original0"):
+                p.copy_(v_param.pow(2).sum(dim=(0, 1), keepdim=True).sqrt())
+    return backbone
+
+
+def _load_pretrained_into(backbone: nn.Module, hub_id: str, pick=lambda m: m) -> None:
+    """REF/model/audio_encoder.py:6-13: `AutoModel.from_pretrained(config.model.audio_encoder.type)`; the tensors are
+    re-homed in the parameter container (same names as HF's module). Raises when the checkpoint cannot be read -- the
+    module must never be left at its all-zero construction state."""
+    try:
+        from transformers import AutoModel
+        hf = pick(AutoModel.from_pretrained(hub_id))
+    except Exception as e:  # no network / no local cache / transformers missing
+        raise RuntimeError(
+            f"could not load the pretrained audio encoder {hub_id!r} ({type(e).__name__}: {e}). The reference downloads "
+            "it in AudioEncoder.__init__ (REF/model/audio_encoder.py:6-13); offline, point HF_HOME at a local copy, or "
+            "set `model.audio_encoder.random_init: true` in the config to start from HF's default random "
+            "initialisation (benchmarks / tests).") from e
+    sd = dict(hf.state_dict())
+    for k in list(sd):  # torch-2.0 weight-norm spelling
+        for old, new in (("weight_g", "parametrizations.weight.original0"), ("weight_v", "parametrizations.weight.original1")):
+            if k.endswith("pos_conv_embed.conv." + old):
+                sd[k[:-len(old)] + new] = sd.pop(k)
+    own = backbone.state_dict()
+    missing = [k for k in own if k not in sd]
+    if missing:
+        raise RuntimeError(f"pretrained checkpoint {hub_id!r} lacks {len(missing)} tensors, e.g. {missing[:3]}")
+    backbone.load_state_dict({k: sd[k] for k in own}, strict=True)
+
+
 def load_whisper_encoder(config):
-    """REF/model/audio_encoder.py:10-13 downloads openai/whisper-medium and its feature extractor; here the
-    architecture comes from the config (defaults = whisper-medium) and the log-mel extractor is transformers'
-    WhisperFeatureExtractor with its default (= whisper) parameters, which needs no download."""
+    """REF/model/audio_encoder.py:10-13: openai/whisper-medium's encoder + its feature extractor. The log-mel extractor
+    is transformers' WhisperFeatureExtractor with its default (= whisper) parameters, which needs no download."""
     from ..config import whisper_arch_from_config
     feature_extractor = None
     try:
@@ -183,13 +252,24 @@ def load_whisper_encoder(config):
         feature_extractor = WhisperFeatureExtractor()
     except Exception:  # transformers missing: the collate-side extractor is outside the hot path anyway
         pass
-    return WhisperBackbone(whisper_arch_from_config(config)), feature_extractor
+    backbone = WhisperBackbone(whisper_arch_from_config(config))
+    if _random_init_requested(config):
+        init_hf_default_(backbone, getattr(config, "seed_everything", 1234))
+    else:
+        _load_pretrained_into(backbone, config.model.audio_encoder.type, pick=lambda m: m.encoder)
+    return backbone, feature_extractor
 
 
 def load_hubert_encoder(config):
-    """REF/model/audio_encoder.py:6-7 downloads facebook/hubert-large-ls960-ft; here the architecture comes from
-    the config (defaults = HuBERT-large) and the weights from the checkpoint the caller loads."""
-    return HubertBackbone(encoder_arch_from_config(config))
+    """REF/model/audio_encoder.py:6-7: facebook/hubert-large-ls960-ft (`config.model.audio_encoder.type`). The
+    architecture comes from the config (defaults = HuBERT-large); the weights from the hub checkpoint unless the config
+    asks for `model.audio_encoder.random_init: true`."""
+    backbone = HubertBackbone(encoder_arch_from_config(config))
+    if _random_init_requested(config):
+        init_hf_default_(backbone, getattr(config, "seed_everything", 1234))
+    else:
+        _load_pretrained_into(backbone, config.model.audio_encoder.type)
+    return backbone
 
 
 class AudioEncoder(nn.Module):
@@ -220,6 +300,14 @@ class AudioEncoder(nn.Module):
         else:
             raise Exception("Invalid downsampling method for audio encoder.")
 
+        # 16-bit format of the GEMM / attention operands (weights copies, activations, gradients). fp16 is what the
+        # reference computes in (torch.autocast(dtype=torch.float16), REF/trainer.py:270, REF/inference.py:99) and what
+        # keeps the projected embeddings accurate enough for the 2e-2 logit tolerance downstream; the fp32 master
+        # parameters are untouched. `model.audio_encoder.compute_dtype: bfloat16` in the yaml (or assigning
+        # `operand_dtype`) selects bf16.
+        cd = getattr(self.config.model.audio_encoder, "compute_dtype", "float16")
+        self.operand_dtype = {"float16": torch.float16, "fp16": torch.float16, "half": torch.float16,
+                              "bfloat16": torch.bfloat16, "bf16": torch.bfloat16}[str(cd).replace("torch.", "")]
         self._packed = None
         self._packed_key = None
         self._pos_w_packed = None
@@ -243,7 +331,7 @@ class AudioEncoder(nn.Module):
 
     # ---------------------------------------------------------------------------------------------
     def _weights_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (self.operand_dtype,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def pack_weights(self, force: bool = False):
         """bf16 / K-major copies of the parameters in the layouts the kernels consume, rebuilt whenever a
@@ -261,7 +349,7 @@ class AudioEncoder(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("AudioEncoder (B200 path) needs its parameters on a CUDA device; there is no CPU path")
         f32 = lambda t: t.detach().to(torch.float32).contiguous()
-        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        bf = lambda t: t.detach().to(self.operand_dtype).contiguous()
         keep: List[torch.Tensor] = []
 
         def K(t):
@@ -284,7 +372,8 @@ class AudioEncoder(nn.Module):
         w.fp_w, w.fp_b = K(bf(fp.projection.weight)), K(f32(fp.projection.bias))
         pc = enc.encoder.pos_conv_embed.conv
         self._pos_w_packed = ops.posconv_weight_pack(f32(pc.parametrizations.weight.original0).reshape(-1),
-                                                     f32(pc.parametrizations.weight.original1))
+                                                     f32(pc.parametrizations.weight.original1),
+                                                     out_dtype=self.operand_dtype)
         self._pos_w_dgrad = None
         w.pos_w = K(self._pos_w_packed)
         w.pos_b, w.pos_k, w.pos_groups = K(f32(pc.bias)), arch.pos_k, arch.pos_groups
@@ -308,6 +397,7 @@ class AudioEncoder(nn.Module):
         w.pool_kernel, w.pool_stride = self.pool_kernel, self.pool_stride
         w.proj_w, w.proj_b = K(bf(self.embed_projection.weight)), K(f32(self.embed_projection.bias))
         w.llm_dim = self.embed_projection.out_features
+        w.fmt = ops.fmt_of(self.operand_dtype)
         self._packed = (w, layers, keep)
         self._packed_key = key
         return self._packed
@@ -319,7 +409,7 @@ class AudioEncoder(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("AudioEncoder (B200 path) needs its parameters on a CUDA device; there is no CPU path")
         f32 = lambda t: t.detach().to(torch.float32).contiguous()
-        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        bf = lambda t: t.detach().to(self.operand_dtype).contiguous()
         keep: List[torch.Tensor] = []
 
         def K(t):
@@ -350,6 +440,7 @@ class AudioEncoder(nn.Module):
         w.pool_kernel, w.pool_stride = self.pool_kernel, self.pool_stride
         w.proj_w, w.proj_b = K(bf(self.embed_projection.weight)), K(f32(self.embed_projection.bias))
         w.llm_dim = self.embed_projection.out_features
+        w.fmt = ops.fmt_of(self.operand_dtype)
         return (w, layers, keep)
 
     def _whisper_forward_fp32(self, input: torch.Tensor, return_last_hidden: bool = False):
@@ -435,9 +526,14 @@ class AudioEncoder(nn.Module):
         self._packed_key = None
         self._pos_w_dgrad = None
 
+    def transformer_layers(self):
+        return self.encoder.encoder.layers if self.encoder_base == "hubert" else self.encoder.layers
+
     def flat_param_order(self):
-        """Parameter order for a flat optimizer buffer that makes q|k|v weights (and biases) of every layer adjacent,
-        so the fused-QKV gradient [3H, H] the kernels produce IS the concatenation of the three `.grad` views."""
+        """Parameter order for a flat optimizer buffer: the transformer layers first, each layer's parameters in ONE
+        contiguous block (= one all-reduce bucket, exchanged while the layers below it are still in their backward),
+        with q|k|v weights (and biases) adjacent inside it so the fused-QKV gradient [3H, H] the kernels produce IS the
+        concatenation of the three `.grad` views; everything else (conv stack, projections, final norm) follows."""
         order, seen = [], set()
 
         def push(p):
@@ -446,16 +542,22 @@ class AudioEncoder(nn.Module):
                 order.append(p)
 
         hubert = self.encoder_base == "hubert"
-        for lay in (self.encoder.encoder.layers if hubert else self.encoder.layers):
+        for lay in self.transformer_layers():
             a = lay.attention if hubert else lay.self_attn
             for proj in (a.q_proj, a.k_proj, a.v_proj):
                 push(proj.weight)
             if hubert:  # Whisper's k_proj has no bias: its fused bias gradient goes through scratch
                 for proj in (a.q_proj, a.k_proj, a.v_proj):
                     push(proj.bias)
+            for p in lay.parameters():
+                push(p)
         for p in self.parameters():
             push(p)
         return order
+
+    def layer_param_groups(self):
+        """Parameters of each transformer layer (index = layer): the all-reduce buckets of the training step."""
+        return [list(lay.parameters()) for lay in self.transformer_layers()]
 
     def _grad_spec(self):
         """(buffer name, packed shape, parameters that tile the buffer row-wise) for every accumulator whose packed
@@ -654,9 +756,19 @@ class AudioEncoder(nn.Module):
         self._train_ctx = ctx
         return out
 
-    def backward(self, d_audio_embeds: torch.Tensor) -> None:
+    def backward(self, d_audio_embeds: torch.Tensor, layer_events=None) -> None:
         """Accumulate d(loss)/d(parameters) for the last `forward_train` batch given d(loss)/d(audio_embeds)
-        (fp32 (B, A, llm_dim)). Gradients stay in packed accumulators until `flush_grads`."""
+        (fp32 (B, A, llm_dim)). Gradients stay in packed accumulators until `flush_grads`.
+        layer_events (optional list of torch.cuda.Event, one per transformer layer): event l is recorded on the current
+        stream once every gradient of layer l has been enqueued."""
+        ev_arr = None
+        if layer_events is not None:
+            assert len(layer_events) == self.encoder.arch.layers
+            for e in layer_events:  # a torch event only owns a CUDA event once it has been recorded
+                if not getattr(e, "_b2s_primed", False):
+                    e.record()
+                    e._b2s_primed = True
+            ev_arr = (C.c_void_p * len(layer_events))(*[e.cuda_event for e in layer_events])
         ctx = self._train_ctx
         if ctx is None or "wave" not in ctx:
             raise RuntimeError("AudioEncoder.backward called without a preceding forward_train")
@@ -672,7 +784,7 @@ class AudioEncoder(nn.Module):
                 ctx["bws"] = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
             _lib.check(lib.b2s_whisper_backward(C.byref(w), C.byref(g), ctx["B"], ctx["saved"].data_ptr(),
                                                 ctx["saved"].numel(), d.data_ptr(), ctx["bws"].data_ptr(),
-                                                ctx["bws"].numel(), torch.cuda.current_stream().cuda_stream),
+                                                ctx["bws"].numel(), ev_arr, torch.cuda.current_stream().cuda_stream),
                        "whisper_backward")
             del ctx["wave"]
             return
@@ -697,7 +809,7 @@ class AudioEncoder(nn.Module):
                                            wave.stride(0), ctx["B"], ctx["T0"], ctx.get("c_len"),
                                            ctx["saved"].data_ptr(),
                                            ctx["saved"].numel(), d.data_ptr(), ctx["bws"].data_ptr(),
-                                           ctx["bws"].numel(), reg, torch.cuda.current_stream().cuda_stream),
+                                           ctx["bws"].numel(), reg, ev_arr, torch.cuda.current_stream().cuda_stream),
                    "hubert_backward")
         del ctx["wave"]
 
@@ -751,8 +863,8 @@ class AudioEncoder(nn.Module):
 
     def forward(self, input, ctc_pool_ranges=None):
         """Same contract as REF/model/audio_encoder.py:56-88 (`pool` branch): (B, T0) -> (B, A, llm_dim).
-        The result is returned in bf16, the activation dtype of the LLM it is spliced into (the reference returns
-        fp16 under autocast)."""
+        The result is returned in the encoder's 16-bit operand dtype -- fp16 by default, like the reference under
+        autocast."""
         if self.downsample_method != "pool":
             raise Exception("Invalid downsampling method for audio encoder.")
-        return self.forward_fp32(input).to(torch.bfloat16)
+        return self.forward_fp32(input).to(self.operand_dtype)

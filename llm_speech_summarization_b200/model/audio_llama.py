@@ -2,7 +2,9 @@
 object (.loss / .logits / .hidden_states), `.model.embed_tokens` and a greedy `.generate(inputs_embeds=...)`,
 backed by the sm_100a prefill (b2s_llama_prefill) instead of transformers' LlamaModel.
 
-Parameters are held frozen in bf16 under HF's names (`model.embed_tokens.weight`, `model.layers.N.*`,
+Parameters are held frozen in ONE 16-bit dtype -- fp16 by default, what the reference loads (`torch_dtype=torch.float16`,
+REF/trainer.py:57-61, REF/inference.py:46-51) and what meets the 2e-2 logit tolerance at Llama-3.2-3B size; bf16 on
+request (`dtype=torch.bfloat16`) -- under HF's names (`model.embed_tokens.weight`, `model.layers.N.*`,
 `model.norm.weight`, `lm_head.weight`), so an HF Llama-3.2-3B / MiniChat-2-3B state_dict loads unchanged; the
 fused-QKV and gate|up-interleaved copies the kernels consume are built once (the LLM is frozen on this path,
 REF/trainer.py:62-64). No CPU path exists.
@@ -35,57 +37,57 @@ class CausalLMOutputWithPast:
 
 
 class _W(nn.Module):
-    def __init__(self, *shape):
+    def __init__(self, *shape, dtype=torch.float16):
         super().__init__()
-        self.weight = nn.Parameter(torch.zeros(*shape, dtype=torch.bfloat16), requires_grad=False)
+        self.weight = nn.Parameter(torch.zeros(*shape, dtype=dtype), requires_grad=False)
 
 
 class EmbedTokens(nn.Module):
     """`llm.model.embed_tokens(ids)` (REF/utils.py:33-35,61-62,117; REF/inference.py:121): gathers through the
-    splice kernel, returns bf16 (the LLM's activation dtype)."""
+    splice kernel, returns the LLM's 16-bit dtype."""
 
-    def __init__(self, vocab, hidden):
+    def __init__(self, vocab, hidden, dtype=torch.float16):
         super().__init__()
-        self.weight = nn.Parameter(torch.zeros(vocab, hidden, dtype=torch.bfloat16), requires_grad=False)
+        self.weight = nn.Parameter(torch.zeros(vocab, hidden, dtype=dtype), requires_grad=False)
 
     def forward(self, input_ids: torch.Tensor) -> torch.Tensor:
         ids = input_ids.to(device=self.weight.device, dtype=torch.int32).contiguous()
         out = ops.embed_splice(self.weight, None, ids.reshape(-1))
-        return out.to(torch.bfloat16).reshape(*input_ids.shape, self.weight.shape[1])
+        return out.to(self.weight.dtype).reshape(*input_ids.shape, self.weight.shape[1])
 
 
 class _Attn(nn.Module):
-    def __init__(self, a: LlmArch):
+    def __init__(self, a: LlmArch, dt):
         super().__init__()
-        self.q_proj = _W(a.heads * a.head_dim, a.hidden)
-        self.k_proj = _W(a.kv_heads * a.head_dim, a.hidden)
-        self.v_proj = _W(a.kv_heads * a.head_dim, a.hidden)
-        self.o_proj = _W(a.hidden, a.heads * a.head_dim)
+        self.q_proj = _W(a.heads * a.head_dim, a.hidden, dtype=dt)
+        self.k_proj = _W(a.kv_heads * a.head_dim, a.hidden, dtype=dt)
+        self.v_proj = _W(a.kv_heads * a.head_dim, a.hidden, dtype=dt)
+        self.o_proj = _W(a.hidden, a.heads * a.head_dim, dtype=dt)
 
 
 class _Mlp(nn.Module):
-    def __init__(self, a: LlmArch):
+    def __init__(self, a: LlmArch, dt):
         super().__init__()
-        self.gate_proj = _W(a.ffn, a.hidden)
-        self.up_proj = _W(a.ffn, a.hidden)
-        self.down_proj = _W(a.hidden, a.ffn)
+        self.gate_proj = _W(a.ffn, a.hidden, dtype=dt)
+        self.up_proj = _W(a.ffn, a.hidden, dtype=dt)
+        self.down_proj = _W(a.hidden, a.ffn, dtype=dt)
 
 
 class _Layer(nn.Module):
-    def __init__(self, a: LlmArch):
+    def __init__(self, a: LlmArch, dt):
         super().__init__()
-        self.self_attn = _Attn(a)
-        self.mlp = _Mlp(a)
-        self.input_layernorm = _W(a.hidden)
-        self.post_attention_layernorm = _W(a.hidden)
+        self.self_attn = _Attn(a, dt)
+        self.mlp = _Mlp(a, dt)
+        self.input_layernorm = _W(a.hidden, dtype=dt)
+        self.post_attention_layernorm = _W(a.hidden, dtype=dt)
 
 
 class _Model(nn.Module):
-    def __init__(self, a: LlmArch):
+    def __init__(self, a: LlmArch, dt):
         super().__init__()
-        self.embed_tokens = EmbedTokens(a.vocab, a.hidden)
-        self.layers = nn.ModuleList([_Layer(a) for _ in range(a.layers)])
-        self.norm = _W(a.hidden)
+        self.embed_tokens = EmbedTokens(a.vocab, a.hidden, dtype=dt)
+        self.layers = nn.ModuleList([_Layer(a, dt) for _ in range(a.layers)])
+        self.norm = _W(a.hidden, dtype=dt)
 
 
 class _ConfigView:
@@ -102,12 +104,13 @@ class _ConfigView:
 
 
 class AudioLlamaForCausalLM(nn.Module):
-    def __init__(self, config: LlmArch):
+    def __init__(self, config: LlmArch, dtype: torch.dtype = torch.float16):
         super().__init__()
+        ops.fmt_of(dtype)  # fp16 or bf16 only
         self.arch = config
         self.config = _ConfigView(config)
-        self.model = _Model(config)
-        self.lm_head = _W(config.vocab, config.hidden)
+        self.model = _Model(config, dtype)
+        self.lm_head = _W(config.vocab, config.hidden, dtype=dtype)
         if config.tie_embeddings:
             self.lm_head.weight = self.model.embed_tokens.weight
         self._packed = None
@@ -123,8 +126,9 @@ class AudioLlamaForCausalLM(nn.Module):
         if llm_type not in KNOWN_LLMS:
             raise Exception("Unknown LLM type.")
         from transformers import AutoModelForCausalLM  # only to read the checkpoint
-        hf = AutoModelForCausalLM.from_pretrained(llm_type, torch_dtype=torch.bfloat16)
-        self = cls(KNOWN_LLMS[llm_type])
+        dtype = torch_dtype if torch_dtype in (torch.float16, torch.bfloat16) else torch.float16
+        hf = AutoModelForCausalLM.from_pretrained(llm_type, torch_dtype=dtype)
+        self = cls(KNOWN_LLMS[llm_type], dtype=dtype)
         self.load_state_dict(hf.state_dict(), strict=False)
         return self
 
@@ -139,6 +143,11 @@ class AudioLlamaForCausalLM(nn.Module):
     @property
     def device(self):
         return self.model.embed_tokens.weight.device
+
+    @property
+    def dtype(self) -> torch.dtype:
+        """The 16-bit format of the weights and of every 16-bit activation / gradient buffer of the LLM."""
+        return self.model.embed_tokens.weight.dtype
 
     def _apply(self, fn, *a, **k):
         self._packed = self._packed_t = self._pw = None
@@ -161,7 +170,8 @@ class AudioLlamaForCausalLM(nn.Module):
             keep.append(t)
             return t.data_ptr()
 
-        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        dt = self.dtype
+        bf = lambda t: t.detach().to(dt).contiguous()
         f32 = lambda t: t.detach().to(torch.float32).contiguous()
         layers = (_lib.LlamaLayer * a.layers)()
         self._pw = []
@@ -187,6 +197,7 @@ class AudioLlamaForCausalLM(nn.Module):
         w.lm_head = K(bf(self.lm_head.weight))
         w.rope_cs = K(packing.rope_table(a.head_dim, a.max_pos, a.rope_theta, a.rope_scaling, device=dev))
         w.max_pos = a.max_pos
+        w.fmt = ops.fmt_of(dt)
         self._packed = (w, layers, keep)
         return self._packed
 
@@ -212,7 +223,7 @@ class AudioLlamaForCausalLM(nn.Module):
             T.wd_t = K(pw["wd"].t().contiguous())
         wt = _lib.LlamaWeightsT()
         wt.layers = C.cast(layers, C.POINTER(_lib.LlamaLayerT))
-        wt.lm_head_t = K(self.lm_head.weight.detach().to(torch.bfloat16).t().contiguous())
+        wt.lm_head_t = K(self.lm_head.weight.detach().to(self.dtype).t().contiguous())
         self._packed_t = (wt, layers, keep)
         return self._packed_t
 
@@ -223,10 +234,10 @@ class AudioLlamaForCausalLM(nn.Module):
         qkv_cols = (a.heads + 2 * a.kv_heads) * a.head_dim
         t = dict(h=torch.empty(L + 1, rows, H, device=device, dtype=torch.float32),
                  h_mid=torch.empty(L, rows, H, device=device, dtype=torch.float32),
-                 qkv=torch.empty(L, rows, qkv_cols, device=device, dtype=torch.bfloat16),
-                 ao=torch.empty(L, rows, a.heads * a.head_dim, device=device, dtype=torch.bfloat16),
+                 qkv=torch.empty(L, rows, qkv_cols, device=device, dtype=self.dtype),
+                 ao=torch.empty(L, rows, a.heads * a.head_dim, device=device, dtype=self.dtype),
                  lse=torch.empty(L, rows, a.heads, device=device, dtype=torch.float32),
-                 gu=torch.empty(L, rows, 2 * F_, device=device, dtype=torch.bfloat16))
+                 gu=torch.empty(L, rows, 2 * F_, device=device, dtype=self.dtype))
         sv = _lib.LlamaSaved()
         for k, v in t.items():
             setattr(sv, k, v.data_ptr())
@@ -256,8 +267,11 @@ class AudioLlamaForCausalLM(nn.Module):
         return logits, (fd if pairs and taps else None), taps
 
     def backward_packed(self, saved, saved_tensors, rows_bwd: int, cu_seqlens, num_seqs_bwd: int, max_seqlen: int,
-                        d_logits, dl_rows, taps: Sequence[int], tap_rows_a, tap_rows_b, tap_coef):
-        """dL/d(input rows [0, rows_bwd)) given d_logits on rows dl_rows and the FD coefficients."""
+                        d_logits, dl_rows, taps: Sequence[int], tap_rows_a, tap_rows_b, tap_coef,
+                        loss_scale: Optional[torch.Tensor] = None):
+        """dL/d(input rows [0, rows_bwd)) given d_logits (dtype = self.dtype, already carrying the loss scale) on rows
+        dl_rows and the FD coefficients (multiplied by the device scalar loss_scale here)."""
+        assert d_logits.dtype == self.dtype, "gradients travel in the LLM's own 16-bit format"
         w = self.packed()[0]
         wt = self.packed_t()[0]
         lib = _lib.load()
@@ -274,7 +288,8 @@ class AudioLlamaForCausalLM(nn.Module):
             C.byref(w), C.byref(wt), C.byref(saved), rows, rows_bwd, cu_seqlens.data_ptr(), num_seqs_bwd,
             int(max_seqlen), d_logits.data_ptr(), dl_rows.data_ptr(), n_dl, tap_arr, len(taps) if pairs else 0,
             None if not pairs else tap_rows_a.data_ptr(), None if not pairs else tap_rows_b.data_ptr(),
-            None if not pairs else tap_coef.data_ptr(), pairs, dh.data_ptr(), ws.data_ptr(), nbytes,
+            None if not pairs else tap_coef.data_ptr(), None if loss_scale is None else loss_scale.data_ptr(), pairs,
+            dh.data_ptr(), ws.data_ptr(), nbytes,
             torch.cuda.current_stream().cuda_stream), "llama_backward")
         return dh
 
@@ -483,7 +498,7 @@ class AudioLlamaForCausalLM(nn.Module):
         eos = set(int(e) for e in self.arch.eos)
         out: List[int] = []
         if not use_kv_cache:
-            seq = inputs_embeds.to(torch.bfloat16)
+            seq = inputs_embeds.to(self.dtype)
             for _ in range(int(max_new_tokens)):
                 logits = self.forward(inputs_embeds=seq, num_logits_to_keep=1).logits
                 nxt = int(logits[0, -1].float().argmax())

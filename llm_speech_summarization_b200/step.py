@@ -322,11 +322,21 @@ class AudioPromptStep:
 
     @torch.no_grad()
     def llm_forward_backward(self, audio: torch.Tensor, text_ids, resp_ids, loss_scale: float = 1.0,
-                             plan: Optional[StepPlan] = None, n_audio=None) -> Dict[str, torch.Tensor]:
+                             plan: Optional[StepPlan] = None, n_audio=None, scaler=None) -> Dict[str, torch.Tensor]:
         """The LLM half of the TRAINING step for projected audio embeddings `audio` (B, A, C) fp32:
         splice -> training forward (activations kept) -> losses -> backward through the frozen LLM
         (REF/trainer.py:299-374). Returns the per-utterance losses and `d_audio_embeds` (B, A, C) fp32 =
-        d( sum_u loss_scale * total_u ) / d audio  -- loss_scale = 1 / grad_accum_interval in the reference."""
+        d( sum_u loss_scale * total_u ) / d audio  -- loss_scale = 1 / grad_accum_interval in the reference --
+        times the dynamic scale of `scaler` (training.GradScaler, the reference's GradScaler, REF/trainer.py:374) when
+        one is given. An fp16 LLM carries fp16 gradients, which underflow without that scale."""
+        if scaler is None and torch.float16 in (self.llm.dtype, getattr(self.audio_encoder, "operand_dtype", None)):
+            # fp16 gradients underflow without a loss scale: a caller that brings none (tests, one-off gradient checks)
+            # gets a private scaler at GradScaler's initial scale; the gradients it receives carry out["grad_scale"]
+            if getattr(self, "_own_scaler", None) is None:
+                from .training import GradScaler
+                self._own_scaler = GradScaler(audio.device)
+            scaler = self._own_scaler
+        scale_t = None if scaler is None else scaler.scale_tensor
         dev = audio.device
         B, A, Cdim = audio.shape
         if plan is None:  # n_audio: per-utterance counts of a ragged batch (the first n_audio[i] rows of audio[i])
@@ -361,24 +371,26 @@ class AudioPromptStep:
             out["fd_loss"] = fd
             total = total + self.w_fd * fd
         out["total_loss"] = total
-        d_logits = ops.kd_ce_loss_bwd(s_log, t_log, plan.labels, res)
+        d_logits = ops.kd_ce_loss_bwd(s_log, t_log, plan.labels, res, loss_scale=scale_t, out_dtype=self.llm.dtype)
         ns = len(plan.L_audio)
         dh0 = self.llm.backward_packed(saved, st, plan.student_rows_total, plan.cu_seqlens, ns, max(plan.L_audio),
                                        d_logits, s_rows, taps if tap_coef is not None else [],
                                        s_rows if tap_coef is not None else None,
-                                       t_rows if tap_coef is not None else None, tap_coef)
+                                       t_rows if tap_coef is not None else None, tap_coef, loss_scale=scale_t)
         out["d_audio_embeds"] = ops.gather_rows(dh0, plan.audio_rows).view(B, A, Cdim)
+        out["grad_scale"] = scale_t if scale_t is not None else torch.ones(1, device=dev)
         out["plan"] = plan
         return out
 
     @torch.no_grad()
     def forward_backward(self, waves: torch.Tensor, text_ids, resp_ids, loss_scale: float = 1.0,
                          plan: Optional[StepPlan] = None, generator=None, draw=None,
-                         num_audio_embeds: Optional[int] = None, lengths=None) -> Dict[str, torch.Tensor]:
+                         num_audio_embeds: Optional[int] = None, lengths=None, scaler=None,
+                         layer_events=None) -> Dict[str, torch.Tensor]:
         """One training micro-batch (REF/trainer.py:270-374): encoder forward with kept activations -> LLM
-        forward/backward -> encoder backward. Parameter gradients (x loss_scale) accumulate inside the encoder
-        until `audio_encoder.flush_grads()`. `generator` / `draw` feed the encoder's train-mode regularisers
-        (AudioEncoder.forward_train)."""
+        forward/backward -> encoder backward. Parameter gradients (x loss_scale x the scaler's scale) accumulate inside
+        the encoder until `audio_encoder.flush_grads()`. `generator` / `draw` feed the encoder's train-mode
+        regularisers (AudioEncoder.forward_train); `layer_events`: see AudioEncoder.backward."""
         if not waves.is_cuda:
             raise RuntimeError("AudioPromptStep needs CUDA inputs; there is no CPU path")
         kw = {}
@@ -391,11 +403,12 @@ class AudioPromptStep:
         A_full = audio.shape[1]
         if num_audio_embeds is not None and num_audio_embeds < A_full:  # REF/trainer.py:280-291 (see forward_losses)
             audio = audio[:, :num_audio_embeds].contiguous()
-        out = self.llm_forward_backward(audio, text_ids, resp_ids, loss_scale=loss_scale, plan=plan, n_audio=n_valid)
+        out = self.llm_forward_backward(audio, text_ids, resp_ids, loss_scale=loss_scale, plan=plan, n_audio=n_valid,
+                                        scaler=scaler)
         d = out["d_audio_embeds"]
         if d.shape[1] < A_full:  # the cropped embeddings get no gradient
             d = torch.nn.functional.pad(d, (0, 0, 0, A_full - d.shape[1]))
-        self.audio_encoder.backward(d)
+        self.audio_encoder.backward(d, layer_events=layer_events)
         return out
 
     def __call__(self, waves_host: torch.Tensor, text_ids, resp_ids, device) -> Dict[str, float]:

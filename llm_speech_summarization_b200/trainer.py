@@ -7,7 +7,8 @@ optimizer + scheduler step every `grad_accum_interval` batches or at loader end,
 and validation intervals), the checkpoint dictionary and the LogWriter calls.
 
 What is different underneath: the batch goes through `EncoderTrainer.train_step` (one fused forward + backward of the
-hand-written CUDA path, no autograd, no GradScaler: bf16 needs no loss scaling), the optimizer is the flat AdamW with
+hand-written CUDA path, no autograd; fp16 operands and gradients like the reference's autocast, with its GradScaler
+semantics kept on the device by `training.GradScaler`), the optimizer is the flat AdamW with
 `torch.optim.AdamW`'s state layout, the Whisper log-mel features are computed on the GPU instead of inside the collate
 function, and under `torch.distributed` every rank takes its shard of the utterances (DistributedSampler) with one SUM
 all-reduce per optimizer step. A loader batch of utterances of DIFFERENT lengths is one ragged micro-batch (HuBERT:

@@ -29,6 +29,71 @@ import torch.distributed as dist
 from . import _lib
 
 
+class GradScaler:
+    """torch.cuda.amp.GradScaler (REF/trainer.py:252,374,381-382) with its state -- scale, growth tracker, the
+    found-inf flag of the step in flight and the count of optimizer steps actually taken -- in DEVICE memory
+    (include/b2s.h: b2s_grad_scaler_state), so neither the skip-on-overflow decision nor the scale update
+    synchronises the host. fp16 operands mean fp16 gradients (a mixed bf16 x fp16 tcgen05.mma traps), and fp16
+    gradients need the scale exactly as they do in the reference.
+
+        loss gradient  *= scale        where it enters the backward pass (b2s_kd_ce_loss_bwd, the FD taps)
+        optimizer step : check(flat gradient) -> AdamW(..., scaler) [no-op on overflow] -> update()
+
+    enabled=False (bf16 operands): the scale is pinned to 1 and only the step counter is used."""
+
+    def __init__(self, device, init_scale: float = 65536.0, growth_factor: float = 2.0, backoff_factor: float = 0.5,
+                 growth_interval: int = 2000, enabled: bool = True):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("GradScaler (B200 path) keeps its state on a CUDA device; there is no CPU path")
+        self.enabled = bool(enabled)
+        self.growth_factor = float(growth_factor) if enabled else 1.0
+        self.backoff_factor = float(backoff_factor) if enabled else 1.0
+        self.growth_interval = int(growth_interval)
+        self.state = torch.zeros(8, device=device, dtype=torch.int32)
+        self.state[:1].view(torch.float32).fill_(float(init_scale) if enabled else 1.0)
+
+    @property
+    def scale_tensor(self) -> torch.Tensor:
+        """fp32 [1] view of the current scale (what the backward kernels read)."""
+        return self.state[:1].view(torch.float32)
+
+    def data_ptr(self) -> int:
+        return self.state.data_ptr()
+
+    def check(self, flat_grad: torch.Tensor) -> None:
+        """found_inf |= any(non-finite) over the (already all-reduced) flat gradient."""
+        if self.enabled:
+            _lib.check(_lib.load().b2s_nonfinite_check(flat_grad.data_ptr(), flat_grad.numel(), self.state.data_ptr(),
+                                                       torch.cuda.current_stream().cuda_stream), "nonfinite_check")
+
+    def update(self) -> None:
+        _lib.check(_lib.load().b2s_grad_scaler_update(self.state.data_ptr(), self.growth_factor, self.backoff_factor,
+                                                      self.growth_interval, torch.cuda.current_stream().cuda_stream),
+                   "grad_scaler_update")
+
+    def read(self) -> Dict[str, float]:
+        """Host copy of the state (synchronises; logging / checkpoints / tests only)."""
+        host = self.state.cpu()
+        return {"scale": float(host[:1].view(torch.float32)[0]), "growth_tracker": int(host[1]),
+                "found_inf": int(host[2]), "opt_steps": int(host[3]), "skipped_steps": int(host[4])}
+
+    def get_scale(self) -> float:
+        return self.read()["scale"]
+
+    def set_opt_steps(self, n: int) -> None:
+        self.state[3] = int(n)
+
+    def state_dict(self) -> Dict:
+        r = self.read()
+        return {"scale": r["scale"], "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor,
+                "growth_interval": self.growth_interval, "_growth_tracker": r["growth_tracker"]}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        if self.enabled:
+            self.state[:1].view(torch.float32).fill_(float(sd["scale"]))
+            self.state[1] = int(sd.get("_growth_tracker", 0))
+
+
 class FlatAdamW:
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
                  frozen_params=(), exclude=(), order=None):
@@ -62,31 +127,117 @@ class FlatAdamW:
             self.offsets.append(off)
             off += k
         self.step_count = 0
+        self.scaler: Optional[GradScaler] = None  # set by the trainer: device-side step count + loss scale
+        self._comm_stream: Optional[torch.cuda.Stream] = None
+        self.last_allreduce = None  # (events of the last exchange) for `allreduce_ms`
 
     def zero_grad(self, set_to_none: bool = False):
         self.grad.zero_()
 
+    def span_of(self, params) -> Optional[tuple]:
+        """(start, end) element range of the flat buffers covered by `params` if they are contiguous there."""
+        off_of = {id(p): o for p, o in zip(self.trainable, self.offsets)}
+        spans = sorted((off_of[id(p)], off_of[id(p)] + p.numel()) for p in params if id(p) in off_of)
+        if not spans:
+            return None
+        for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+            if a1 != b0:
+                return None
+        return spans[0][0], spans[-1][1]
+
+    @staticmethod
+    def _dist_on() -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
     def all_reduce_grads(self):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        """One SUM all-reduce of the whole flat gradient on the current stream (no overlap)."""
+        if self._dist_on():
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+
+    def all_reduce_buckets(self, buckets, ready_events) -> None:
+        """SUM all-reduce of gradient ranges `buckets` = [(start, end), ...] on a dedicated communication stream, each
+        as soon as `ready_events[i]` (recorded on the compute stream when the range's last gradient kernel was enqueued)
+        has fired: the exchange of layer l's gradients runs under the backward of layers l-1 ... 0 (SURVEY.md 8e:
+        buckets per encoder layer, NVSwitch bandwidth is uniform, so bucket = layer). `finish_all_reduce()` makes the
+        compute stream wait for the communication stream."""
+        if not self._dist_on():
+            return
+        dev = self.grad.device
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(dev)
+        cs = self._comm_stream
+        pend = getattr(self, "_pending_comm", None)  # several calls (layer buckets, then the rest) form ONE exchange
+        t0 = pend[0] if pend is not None else None
+        for (a, b), ev in zip(buckets, ready_events):
+            if b <= a:
+                continue
+            cs.wait_event(ev)
+            with torch.cuda.stream(cs):
+                if t0 is None:
+                    t0 = torch.cuda.Event(enable_timing=True)
+                    t0.record(cs)
+                dist.all_reduce(self.grad[a:b], op=dist.ReduceOp.SUM)
+        if t0 is not None:
+            t1 = torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(cs):
+                t1.record(cs)
+            self._pending_comm = (t0, t1)
+
+    def finish_all_reduce(self) -> None:
+        """Compute stream waits for every bucket launched by `all_reduce_buckets`; records what bench.py reports:
+        comm-stream span of the exchange and how long the compute stream actually stood still for it."""
+        pend = getattr(self, "_pending_comm", None)
+        if pend is None:
+            return
+        t0, t1 = pend
+        main = torch.cuda.current_stream()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record(main)
+        main.wait_stream(self._comm_stream)
+        w1.record(main)
+        self.last_allreduce = (t0, t1, w0, w1)
+        self._pending_comm = None
+
+    def allreduce_ms(self) -> Optional[Dict[str, float]]:
+        """{'span': first bucket start -> last bucket end on the communication stream, 'exposed': time the compute
+        stream waited} of the last exchange (synchronises on its events)."""
+        if self.last_allreduce is None:
+            return None
+        t0, t1, w0, w1 = self.last_allreduce
+        w1.synchronize()
+        t1.synchronize()
+        return {"span": float(t0.elapsed_time(t1)), "exposed": float(w0.elapsed_time(w1))}
 
     @torch.no_grad()
     def step(self):
+        """AdamW on the flat buffers. With a GradScaler attached: inf/nan check -> update (skipped on overflow, gradient
+        divided by the loss scale, bias correction from the device-side count of steps taken) -> scale update."""
         self.step_count += 1
         b1, b2 = self.defaults["betas"]
+        sc = self.scaler
+        if sc is not None:
+            sc.check(self.grad)
         _lib.check(_lib.load().b2s_adamw_step(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
                                               self.exp_avg_sq.data_ptr(), self.flat.numel(), float(self.lr), b1, b2,
                                               self.defaults["eps"], self.defaults["weight_decay"], self.step_count,
-                                              1.0, torch.cuda.current_stream().cuda_stream), "adamw_step")
+                                              1.0, None if sc is None else sc.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream), "adamw_step")
+        if sc is not None:
+            sc.update()
+
+    def steps_taken(self) -> int:
+        """Optimizer steps actually applied (overflow-skipped steps do not count; synchronises with a scaler)."""
+        return self.step_count if self.scaler is None else self.scaler.read()["opt_steps"]
 
     # ---- torch.optim.AdamW-compatible state dict ------------------------------------------------
     def state_dict(self) -> Dict:
         state = {}
         idx_of = {id(p): i for i, p in enumerate(self.params)}
-        if self.step_count > 0:
+        taken = self.steps_taken()
+        if taken > 0:
             for p, off in zip(self.trainable, self.offsets):
                 k = p.numel()
-                state[idx_of[id(p)]] = {"step": torch.tensor(float(self.step_count)),
+                state[idx_of[id(p)]] = {"step": torch.tensor(float(taken)),
                                         "exp_avg": self.exp_avg[off:off + k].view(p.shape).clone(),
                                         "exp_avg_sq": self.exp_avg_sq[off:off + k].view(p.shape).clone()}
         group = dict(lr=self.lr, betas=self.defaults["betas"], eps=self.defaults["eps"],
@@ -110,6 +261,8 @@ class FlatAdamW:
         if len(steps) > 1:
             raise ValueError("FlatAdamW.load_state_dict: parameters with different step counts are not supported")
         self.step_count = steps.pop() if steps else 0
+        if self.scaler is not None:
+            self.scaler.set_opt_steps(self.step_count)
         if sd.get("param_groups"):
             self.lr = sd["param_groups"][0].get("lr", self.lr)
 
@@ -177,6 +330,32 @@ class EncoderTrainer:
         self.step = 0
         self.start_epoch = 0
         self._micro = 0
+        # fp16 operands anywhere on the path -> dynamic loss scaling like the reference's GradScaler (REF/trainer.py:252);
+        # an all-bf16 path keeps the scale at 1 and uses only the device-side step counter
+        llm_dt = getattr(llm, "dtype", None) if llm is not None else getattr(getattr(step_fn, "llm", None), "dtype", None)
+        fp16 = torch.float16 in (llm_dt, getattr(audio_encoder, "operand_dtype", None))
+        dev = self.optimizer.flat.device
+        self.scaler = GradScaler(dev, enabled=fp16)
+        self.optimizer.scaler = self.scaler
+        # gradient exchange: one bucket per transformer layer, launched on a communication stream as soon as the
+        # layer's backward has been enqueued (overlap with the layers below), plus one bucket for everything else
+        self.overlap_allreduce = True
+        self._layer_spans = None
+        groups = getattr(audio_encoder, "layer_param_groups", lambda: [])()
+        spans = [self.optimizer.span_of(g) for g in groups]
+        if groups and all(sp is not None for sp in spans):
+            self._layer_spans = spans
+            self._layer_events = [torch.cuda.Event() for _ in spans]
+            covered = sorted(spans)
+            n = self.optimizer.grad.numel()
+            rest, cur = [], 0
+            for a, b in covered:
+                if a > cur:
+                    rest.append((cur, a))
+                cur = max(cur, b)
+            if cur < n:
+                rest.append((cur, n))
+            self._rest_spans = rest
 
     @classmethod
     def from_config(cls, config, step_fn, audio_encoder, llm=None, batches_per_epoch: int = 1):
@@ -194,16 +373,31 @@ class EncoderTrainer:
         """One micro-batch of B utterances on this rank. The accumulation window counts utterances GLOBALLY:
         an optimizer step happens once world * (micro-batches * B) reaches grad_accum_interval (or at loader end)."""
         B = waves.shape[0]
+        closes_window = self._micro + B * self.world() >= self.grad_accum_interval or last_batch
+        overlap = (closes_window and self.overlap_allreduce and self._layer_spans is not None and self.world() > 1)
         out = self.step_fn.forward_backward(waves, text_ids, resp_ids, loss_scale=1.0 / self.grad_accum_interval,
-                                            plan=plan, generator=self.generator,
+                                            plan=plan, generator=self.generator, scaler=self.scaler,
+                                            layer_events=self._layer_events if overlap else None,
                                             **({} if num_audio_embeds is None else {"num_audio_embeds": num_audio_embeds}),
                                             **({} if lengths is None else {"lengths": lengths}))
         self._micro += B * self.world()
         self.step += 1
         out["optimizer_step"] = False
-        if self._micro >= self.grad_accum_interval or last_batch:
-            self.audio_encoder.flush_grads()
-            self.optimizer.all_reduce_grads()
+        if closes_window:
+            if overlap:
+                # the window's last backward is enqueued: layer L-1's gradients are final first, layer 0's last
+                L = len(self._layer_spans)
+                order = list(range(L - 1, -1, -1))
+                self.optimizer.all_reduce_buckets([self._layer_spans[l] for l in order],
+                                                  [self._layer_events[l] for l in order])
+            self.audio_encoder.flush_grads()  # conv / positional-conv scratch -> .grad (the "rest" ranges)
+            if overlap:
+                ev = torch.cuda.Event()
+                ev.record()
+                self.optimizer.all_reduce_buckets(self._rest_spans, [ev] * len(self._rest_spans))
+                self.optimizer.finish_all_reduce()
+            else:
+                self.optimizer.all_reduce_grads()
             self.optimizer.step()
             self.audio_encoder.mark_weights_changed()
             self.lr_scheduler.step()
@@ -258,7 +452,7 @@ class EncoderTrainer:
                     if seen >= num_generate_samples:
                         break
                     seen += 1
-                    emb = out["audio_embeds"][b:b + 1].to(torch.bfloat16)
+                    emb = out["audio_embeds"][b:b + 1].to(llm.dtype)
                     n_new = 2 * emb.shape[1]
                     llm_type = self.step_fn.llm_type
                     prompts = [merge_prompt_tokens(emb, tokenizer, llm.model.embed_tokens, llm_type, emb.device),

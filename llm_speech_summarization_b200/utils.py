@@ -55,8 +55,8 @@ def prompt_ids(tokenizer, llm_type):
 
 def _table(embed_tokens) -> torch.Tensor:
     w = getattr(embed_tokens, "weight", None)
-    if w is None or w.dtype != torch.bfloat16 or not w.is_cuda:
-        raise RuntimeError("embed_tokens must be the bf16 CUDA embedding table of AudioLlamaForCausalLM "
+    if w is None or w.dtype not in (torch.float16, torch.bfloat16) or not w.is_cuda:
+        raise RuntimeError("embed_tokens must be the 16-bit CUDA embedding table of AudioLlamaForCausalLM "
                            "(llm.model.embed_tokens); there is no CPU path")
     return w
 
@@ -96,7 +96,7 @@ def _splice(embed_tokens, segments_per_sample, audio_list, pad_to: Optional[int]
         flat.extend(src)
     row_src = torch.tensor(flat, dtype=torch.int32, device=dev)
     out = ops.embed_splice(table, audio_cat, row_src)
-    return out.view(len(rows_src), width, table.shape[1]).to(torch.bfloat16), lens
+    return out.view(len(rows_src), width, table.shape[1]).to(table.dtype), lens
 
 
 def merge_prompt_response_tokens(prefix_input_ids, suffix_input_ids, inputs_embeds, response_input_ids, embed_tokens):

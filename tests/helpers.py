@@ -17,7 +17,8 @@ def ns_config(enc_cfg, llm_cfg):
     return NS(
         seed_everything=1234,
         model=NS(
-            audio_encoder=NS(base="hubert", type="facebook/hubert-large-ls960-ft", downsample_method="pool",
+            audio_encoder=NS(base="hubert", type="facebook/hubert-large-ls960-ft", random_init=True,
+                             downsample_method="pool",
                              downsample_factor=4, pooling=NS(kernel_size=enc_cfg.pool_kernel, stride=enc_cfg.pool_stride),
                              arch=NS(hidden=enc_cfg.hidden, layers=enc_cfg.layers, heads=enc_cfg.heads, ffn=enc_cfg.ffn,
                                      pos_k=enc_cfg.pos_k, pos_groups=enc_cfg.pos_groups)),
@@ -32,16 +33,20 @@ def ns_config(enc_cfg, llm_cfg):
     )
 
 
-def build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, device):
-    """AudioEncoder + AudioLlamaForCausalLM of the CUDA path, loaded from reference-layout state dicts."""
+def build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, device, dtype=None):
+    """AudioEncoder + AudioLlamaForCausalLM of the CUDA path, loaded from reference-layout state dicts.
+    dtype: 16-bit operand format of both modules (None = their default, fp16 like the reference's autocast)."""
     from llm_speech_summarization_b200.config import llm_arch_from_config
     from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
     from llm_speech_summarization_b200.model.audio_llama import AudioLlamaForCausalLM
     cfg = ns_config(enc_cfg, llm_cfg)
     enc = AudioEncoder(cfg, device)
+    if dtype is not None:
+        enc.operand_dtype = dtype
     enc.load_state_dict(enc_sd, strict=True)
     enc.eval().to(device)
-    llm = AudioLlamaForCausalLM(llm_arch_from_config(cfg))
+    llm = AudioLlamaForCausalLM(llm_arch_from_config(cfg), **({} if dtype is None else {"dtype": dtype}))
+    # the synthetic weights are bf16-representable (oracle/configs.py); the copy into fp16 parameters is exact
     llm.load_state_dict({k: v.to(torch.bfloat16) for k, v in llm_sd.items()}, strict=True)
     llm.eval().to(device)
     return cfg, enc, llm
@@ -54,7 +59,8 @@ def bf16_round_sd(sd):
 
 
 def ns_config_whisper(cfg, llm_type="meta-llama/Llama-3.2-3B-Instruct"):
-    return NS(model=NS(audio_encoder=NS(base="whisper", type="openai/whisper-medium", downsample_method="pool",
+    return NS(model=NS(audio_encoder=NS(base="whisper", type="openai/whisper-medium", random_init=True,
+                                        downsample_method="pool",
                                         downsample_factor=4, pooling=NS(kernel_size=cfg.pool_kernel, stride=cfg.pool_stride),
                                         arch=NS(hidden=cfg.hidden, layers=cfg.layers, heads=cfg.heads, ffn=cfg.ffn,
                                                 mel_bins=cfg.mel_bins, max_positions=cfg.max_positions)),

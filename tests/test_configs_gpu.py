@@ -7,7 +7,8 @@ covered by tests/test_path_gpu.py::test_full_size_vs_oracle):
                            compute_num_audio_embeds like the trainer does (REF/trainer.py:280-291), prefill.
 
 Random-init weights of the named architectures; the checker is the CPU oracle on this box's host cores.
-Tolerances as in test_path_gpu.py (embeddings 2e-2; last-row logits: see the note there on random-init networks).
+Tolerances are the north star's, as in test_path_gpu.py: embeddings and last-row logits within 2e-2 of the fp32 oracle
+(fp16 operands on the encoder and the LLM, like the reference's autocast; bf16 operands measured 2.7e-2 in round 1).
 """
 import pytest
 import torch
@@ -18,7 +19,7 @@ from helpers import build_product, ns_config_whisper
 pytestmark = [pytest.mark.gpu, pytest.mark.slow]
 
 TOL_EMBED = 2e-2
-TOL_LOGITS_RANDOM_INIT = 3.5e-2
+TOL_LOGITS = 2e-2
 
 
 def test_config3_minichat_hubert_30s_text_plus_speech(cuda):
@@ -46,7 +47,7 @@ def test_config3_minichat_hubert_30s_text_plus_speech(cuda):
     assert rel_l2(prompt.float().cpu(), ref_prompt) < TOL_EMBED
     err = rel_l2(logits, ref_logits[0])
     print(f"config[3] last-row logits rel err {err:.3e}")
-    assert err < TOL_LOGITS_RANDOM_INIT
+    assert err < TOL_LOGITS
 
 
 def test_config4_llama_whisper_30s(cuda):
@@ -85,4 +86,4 @@ def test_config4_llama_whisper_30s(cuda):
     assert rel_l2(emb32.cpu(), ref_emb) < TOL_EMBED
     err = rel_l2(logits, ref_logits[0, -1])
     print(f"config[4] last-row logits rel err {err:.3e}")
-    assert err < TOL_LOGITS_RANDOM_INIT
+    assert err < TOL_LOGITS

@@ -216,3 +216,56 @@ def test_gemm_wgrad_strided_conv_view(cuda, k, s, T):
     (gw,) = torch.autograd.grad(y, w, dy.float().permute(0, 2, 1))
     ref = gw.permute(0, 2, 1).reshape(Cout, k * Cin)
     assert rel_l2(out, ref) < TOL_F32
+
+
+# ---- 16-bit operand formats (b2s.h B2S_FMT_*): fp16 and bf16, never mixed
+_DT = {"bf16": torch.bfloat16, "f16": torch.float16}
+
+
+@pytest.mark.parametrize("cg", [1, 2], ids=["cg1", "cg2"])
+def test_gemm_f16_operands_f32(cuda, cg):
+    """fp16 operands: values exactly representable in both 16-bit formats, so the fp32 result matches to fp32 rounding."""
+    from llm_speech_summarization_b200 import ops
+    a, w, b = _mk(777, 1024, 512, cuda, seed=11)     # bf16-exact values of moderate magnitude: exact in fp16 as well
+    a, w = a.to(torch.float16), w.to(torch.float16)
+    out = ops.gemm(a, w, bias=b, epi=ops.EPI_F32, cta_group=cg)
+    ref = a.float() @ w.float().t() + b
+    assert rel_l2(out, ref) < TOL_F32
+
+
+def test_gemm_rejects_mixed_operand_formats(cuda):
+    """tcgen05 kind::f16 encodes a_format / b_format separately, but a bf16 x fp16 pair traps with an illegal instruction
+    on B200 (measured in round 2): the library refuses it up front -- which is why fp16 activations imply fp16
+    gradients (and a loss scale) on the training path."""
+    from llm_speech_summarization_b200 import ops
+    a, w, _ = _mk(128, 256, 64, cuda, seed=14)
+    with pytest.raises(RuntimeError, match="share one 16-bit format"):
+        ops.gemm(a.to(torch.float16), w, epi=ops.EPI_F32)
+
+
+def test_gemm_f16_needs_the_format_bit(cuda):
+    """fp16 data fed with fp16 mantissa bits that bf16 cannot hold: the result only matches if the MMA really reads
+    the operands as fp16 (guards against a silently ignored format field)."""
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    a = (torch.randn(256, 256, generator=g) * 0.5).to(torch.float16).to(cuda)
+    w = (torch.randn(512, 256, generator=g) * 0.05).to(torch.float16).to(cuda)
+    out = ops.gemm(a, w, epi=ops.EPI_F32)
+    assert rel_l2(out, a.float() @ w.float().t()) < TOL_F32
+    out16 = ops.gemm(a, w, epi=ops.EPI_BF16)           # 16-bit output in a's format (fp16): 2^-12 per element
+    assert out16.dtype == torch.float16
+    assert rel_l2(out16.float(), a.float() @ w.float().t()) < 5e-4
+
+
+@pytest.mark.parametrize("dy_dt,w_dt", [("f16", "f16")])
+def test_gemm_dgrad_wgrad_f16(cuda, dy_dt, w_dt):
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    dy = (torch.randn(640, 768, generator=g) * 0.25).to(torch.bfloat16).to(_DT[dy_dt]).to(cuda)
+    w = (torch.randn(768, 512, generator=g) * 0.05).to(torch.bfloat16).to(_DT[w_dt]).to(cuda)
+    x = (torch.randn(640, 512, generator=g) * 0.5).to(torch.bfloat16).to(_DT[w_dt]).to(cuda)
+    dx = ops.gemm_dgrad(dy, w, out_f32=True)
+    assert rel_l2(dx, dy.float() @ w.float()) < TOL_F32
+    dw = torch.zeros(768, 512, device=cuda)
+    ops.gemm_wgrad(dy, x, dw)
+    assert rel_l2(dw, dy.float().t() @ x.float()) < TOL_F32

@@ -153,20 +153,35 @@ def _attn_ref(qkv, cu, Hq, Hkv, D, scale, causal):
     (2, 1, 128, True, [128, 256, 257, 383]),
     (2, 2, 64, True, [300, 5]),
 ])
-@pytest.mark.parametrize("impl", [1, 0], ids=["tcgen05", "mma_sync"])
-def test_attention(cuda, Hq, Hkv, D, causal, lens, impl):
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_attention(cuda, Hq, Hkv, D, causal, lens, dtype):
+    """tcgen05 flash attention in both operand formats (Q, K, V, P and O all in `dtype`)."""
+    _run_attention_case(cuda, Hq, Hkv, D, causal, lens, dtype)
+
+
+def test_attention_f16_sharp_scores_stay_finite(cuda):
+    """fp16 P tops out at 65504: a later key block whose scores outgrow the running reference by far more than 2^14
+    must be handled by the immediate re-reference, not overflow to inf."""
     from llm_speech_summarization_b200 import ops
-    try:
-        _run_attention_case(cuda, Hq, Hkv, D, causal, lens)
-    finally:
-        ops.attention_set_impl(1)
+    Hq = Hkv = 2
+    D, L = 64, 300
+    g = torch.Generator().manual_seed(1)
+    qkv = torch.randn(L, 3 * Hq * D, generator=g)
+    qkv[:, :Hq * D] *= 3.0
+    qkv[200:, Hq * D:2 * Hq * D] *= 9.0  # keys of the later blocks score much higher
+    qkv = qkv.to(torch.float16).to(cuda)
+    cu = torch.tensor([0, L], dtype=torch.int32, device=cuda)
+    o = ops.attention(qkv, cu, L, Hq, Hkv, D, 0.125, False)
+    ref = _attn_ref(qkv, [0, L], Hq, Hkv, D, 0.125, False)
+    assert bool(torch.isfinite(o.float()).all())
+    assert rel_l2(o.float(), ref) < 6e-3
 
 
-def _run_attention_case(cuda, Hq, Hkv, D, causal, lens):
+def _run_attention_case(cuda, Hq, Hkv, D, causal, lens, dtype=torch.bfloat16):
     from llm_speech_summarization_b200 import ops
     g = torch.Generator().manual_seed(sum(lens) + D)
     rows = sum(lens)
-    qkv = torch.randn(rows, (Hq + 2 * Hkv) * D, generator=g).to(torch.bfloat16).to(cuda)
+    qkv = torch.randn(rows, (Hq + 2 * Hkv) * D, generator=g).to(dtype).to(cuda)
     cu = [0]
     for L in lens:
         cu.append(cu[-1] + L)
@@ -174,7 +189,9 @@ def _run_attention_case(cuda, Hq, Hkv, D, causal, lens):
     scale = 1.0 / math.sqrt(D)
     o = ops.attention(qkv, cu_t, max(lens), Hq, Hkv, D, scale, causal)
     ref = _attn_ref(qkv, cu, Hq, Hkv, D, scale, causal)
-    assert rel_l2(o.float(), ref) < 6e-3  # P is rounded to bf16 before P.V, output rounded to bf16
+    assert o.dtype == dtype
+    # P is rounded to the operand format before P.V and the output is rounded to it: 2^-9 (bf16) / 2^-12 (fp16)
+    assert rel_l2(o.float(), ref) < (6e-3 if dtype == torch.bfloat16 else 1e-3)
 
 
 @pytest.mark.parametrize("Hq,Hkv,D,causal,lens", [
@@ -184,25 +201,23 @@ def _run_attention_case(cuda, Hq, Hkv, D, causal, lens):
     (6, 6, 128, True, [136, 300]),
     (4, 2, 64, True, [77, 200]),
 ])
-@pytest.mark.parametrize("impl", [1, 0], ids=["tcgen05", "mma_sync"])
-def test_attention_backward(cuda, Hq, Hkv, D, causal, lens, impl):
-    """dQ / dK / dV of the packed attention vs autograd through fp32 SDPA on the same bf16 inputs."""
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_attention_backward(cuda, Hq, Hkv, D, causal, lens, dtype):
+    """dQ / dK / dV of the packed attention vs autograd through fp32 SDPA on the same 16-bit inputs (every 16-bit
+    tensor of the call -- q, k, v, o, dout, dq, dk, dv -- shares `dtype`)."""
     from llm_speech_summarization_b200 import ops
     g = torch.Generator().manual_seed(sum(lens) * D + Hq)
     rows = sum(lens)
-    qkv = (torch.randn(rows, (Hq + 2 * Hkv) * D, generator=g) * 0.7).to(torch.bfloat16).to(cuda)
-    dout = torch.randn(rows, Hq * D, generator=g).to(torch.bfloat16).to(cuda)
+    qkv = (torch.randn(rows, (Hq + 2 * Hkv) * D, generator=g) * 0.7).to(dtype).to(cuda)
+    dout = torch.randn(rows, Hq * D, generator=g).to(dtype).to(cuda)
     cu = [0]
     for L in lens:
         cu.append(cu[-1] + L)
     cu_t = torch.tensor(cu, dtype=torch.int32, device=cuda)
     scale = 1.0 / math.sqrt(D)
     o, lse = ops.attention(qkv, cu_t, max(lens), Hq, Hkv, D, scale, causal, return_lse=True)
-    ops.attention_set_impl(impl)  # the forward (and its lse) is always the tcgen05 kernel
-    try:
-        dqkv = ops.attention_bwd(qkv, o, dout, lse, cu_t, max(lens), Hq, Hkv, D, scale, causal)
-    finally:
-        ops.attention_set_impl(1)
+    dqkv = ops.attention_bwd(qkv, o, dout, lse, cu_t, max(lens), Hq, Hkv, D, scale, causal)
+    assert dqkv.dtype == dtype
     x = qkv.float().requires_grad_(True)
     ref = _attn_ref(x, cu, Hq, Hkv, D, scale, causal)
     ref.backward(dout.float())
@@ -215,7 +230,7 @@ def test_attention_backward(cuda, Hq, Hkv, D, causal, lens, impl):
         s = s.masked_fill(~torch.ones(b - a, b - a, dtype=torch.bool, device=cuda).tril(), float("-inf"))
     assert torch.allclose(lse[a:b].t() * math.log(2.0), torch.logsumexp(s, -1), atol=2e-3, rtol=2e-3)
     for name, sl in (("dq", slice(0, Hq * D)), ("dk", slice(Hq * D, (Hq + Hkv) * D)), ("dv", slice((Hq + Hkv) * D, None))):
-        assert rel_l2(dqkv[:, sl].float(), x.grad[:, sl]) < 1.5e-2, name
+        assert rel_l2(dqkv[:, sl].float(), x.grad[:, sl]) < (1.5e-2 if dtype == torch.bfloat16 else 3e-3), name
 
 
 # ------------------------------------------------------------------------------------------------ Whisper log-mel (f2)
@@ -260,3 +275,90 @@ def test_whisper_extract_features_feeds_the_encoder(cuda):
         a = enc.forward_fp32(got)
         b = enc.forward_fp32(want.to(cuda))
     assert rel_l2(a, b) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ fp16 operand format
+def test_memory_bound_ops_in_f16(cuda):
+    """The norm / splice / cast family writes (and reads) fp16 when asked: same math, 2^-12 rounding instead of 2^-9."""
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    x = (torch.randn(333, 1024, generator=g) * 3 + 0.7).to(cuda)
+    gm, bt = torch.randn(1024, generator=g).to(cuda), torch.randn(1024, generator=g).to(cuda)
+    y = ops.layernorm(x, gm, bt, 1e-5, out_dtype=torch.float16)
+    assert y.dtype == torch.float16
+    assert rel_l2(y.float(), F.layer_norm(x, (1024,), gm, bt, 1e-5)) < 4e-4
+    y16 = ops.layernorm(y, gm, bt, 1e-5, gelu=True)  # fp16 in -> fp16 out
+    assert y16.dtype == torch.float16
+    assert rel_l2(y16.float(), F.gelu(F.layer_norm(y.float(), (1024,), gm, bt, 1e-5))) < 4e-4
+    w = (torch.rand(1024, generator=g) + 0.5).to(cuda)
+    ref = w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5))
+    assert rel_l2(ops.rmsnorm(x, w, 1e-5, out_dtype=torch.float16).float(), ref) < 4e-4
+    xp = torch.randn(2, 499, 1024, generator=g).to(cuda)
+    yp = ops.layernorm_avgpool(xp, gm, bt, 1e-5, 8, 4, out_dtype=torch.float16)
+    refp = F.avg_pool1d(F.layer_norm(xp, (1024,), gm, bt, 1e-5).transpose(1, 2), 8, 4).transpose(1, 2)
+    assert yp.dtype == torch.float16 and rel_l2(yp.float(), refp) < 4e-4
+    table = torch.randn(100, 512, generator=g).to(torch.float16).to(cuda)
+    src = torch.tensor([3, 99, 0], dtype=torch.int32, device=cuda)
+    assert torch.equal(ops.embed_splice(table, None, src), table[src.long()].float())
+
+
+def test_kd_ce_loss_bwd_f16_with_loss_scale(cuda):
+    """The gradient enters the backward pass in the model's gradient format, multiplied by the device-resident loss
+    scale (GradScaler, REF/trainer.py:374): fp16 keeps 2^-12 relative precision where an unscaled fp16 store would
+    flush most of these ~1e-6 values to zero."""
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    V, R = 4096, 12
+    s = (torch.randn(R, V, generator=g) * 2.0).to(torch.bfloat16).to(cuda)
+    t = (torch.randn(R, V, generator=g) * 2.0).to(torch.bfloat16).to(cuda)
+    labels = torch.randint(0, V, (R,), generator=g).to(torch.int32)
+    labels[-1] = -1
+    labels = labels.to(cuda)
+    offs = torch.tensor([0, R], dtype=torch.int32, device=cuda)
+    res = ops.kd_ce_loss(s, t, labels, offs, scale_kd=0.5 / 16, scale_ce=0.5 / 16)
+    s32 = s.float().requires_grad_(True)
+    ld_ref, ntp_ref = _loss_ref(s32, t, labels, [0, R])
+    ((0.5 * ld_ref.sum() + 0.5 * ntp_ref.sum()) / 16).backward()
+    scale = torch.tensor([65536.0], device=cuda)
+    ds = ops.kd_ce_loss_bwd(s, t, labels, res, loss_scale=scale, out_dtype=torch.float16)
+    assert ds.dtype == torch.float16
+    assert rel_l2(ds.float() / 65536.0, s32.grad) < 6e-4
+    # why the scale exists: the bulk of this gradient (|g| ~ 1e-7) lands on fp16's subnormal grid (step 6e-8) unscaled
+    small = s32.grad.abs() < 1e-6
+    unscaled = ops.kd_ce_loss_bwd(s, t, labels, res, out_dtype=torch.float16)
+    assert rel_l2(unscaled.float()[small], s32.grad[small]) > 5e-2
+    assert rel_l2((ds.float() / 65536.0)[small], s32.grad[small]) < 1e-3
+
+
+def test_grad_scaler_device_state(cuda):
+    """training.GradScaler == torch.cuda.amp.GradScaler's state machine, without host synchronisation: an overflowing
+    step is skipped (parameters and moments untouched) and halves the scale; clean steps count towards growth; AdamW
+    divides the scale out and takes its bias correction from the number of steps actually applied."""
+    from llm_speech_summarization_b200.training import FlatAdamW, GradScaler
+    p = torch.nn.Parameter(torch.linspace(-1, 1, 1024, device=cuda))
+    ref = torch.nn.Parameter(p.detach().clone())
+    opt = FlatAdamW([p], lr=1e-2)
+    opt.scaler = GradScaler(cuda, init_scale=1024.0, growth_interval=2)
+    topt = torch.optim.AdamW([ref], lr=1e-2)
+    g = torch.Generator().manual_seed(0)
+    for i in range(5):
+        grad = torch.randn(1024, generator=g).to(cuda)
+        scale = opt.scaler.get_scale()
+        opt.grad.copy_(grad * scale)
+        if i == 1:
+            opt.grad[7] = float("inf")  # overflow: this step must be a no-op
+        before = p.detach().clone()
+        opt.step()
+        if i == 1:
+            assert torch.equal(p.detach(), before)
+            assert opt.scaler.get_scale() == scale * 0.5
+        else:
+            ref.grad = grad.clone()
+            topt.step()
+            assert torch.allclose(p.detach(), ref.detach(), rtol=1e-5, atol=1e-6), i
+        opt.zero_grad()
+    st = opt.scaler.read()
+    assert st["opt_steps"] == 4 and st["skipped_steps"] == 1 and st["found_inf"] == 0
+    # 1024 -> (overflow) 512 -> two clean steps -> 1024 -> one more clean step (tracker 1)
+    assert st["scale"] == 1024.0 and st["growth_tracker"] == 1
+    assert opt.steps_taken() == 4 and opt.state_dict()["state"][0]["step"].item() == 4.0

@@ -66,7 +66,7 @@ def test_dropin_modules_match_fused_and_oracle(cuda):
     audio, text_ids, resp_ids = configs.synthetic_utterance(llm_cfg, 0, g["samples"], T=g["T"], R=g["R"])
     R = g["R"]
     with torch.no_grad():
-        embeds = enc(audio[None, :].to(cuda))  # (1, A, C) bf16
+        embeds = enc(audio[None, :].to(cuda))  # (1, A, C) fp16 (the encoder's operand dtype)
         a_seq, a_mask, t_seq, t_mask = U.batch_full_embed_sequence(
             all_audio_embeds=embeds, all_text_input_ids=[text_ids], all_response_input_ids=[resp_ids], tokenizer=tok,
             embed_tokens=llm.model.embed_tokens, llm_type=llm_cfg.llm_type, device=cuda, process_text=True)
@@ -161,17 +161,16 @@ def test_full_size_vs_oracle(cuda):
     assert rel_l2(out["audio_embeds"].cpu(), ref["audio_embeds"]) < TOL_EMBED
     for k in ("ld_loss", "ntp_loss", "fd_loss", "total_loss"):
         assert abs(float(out[k][0]) - float(ref[k])) / abs(float(ref[k])) < TOL_KD, k
-    # Logits of a RANDOM-INIT 28-layer network are a chaotic function of its inputs: the reference's own Llama math
-    # run in bf16 by PyTorch eager on this GPU is ~4.7e-2 away from its fp32 run (measured below), so the 2e-2 target
-    # is below bf16's intrinsic noise floor for these weights (profiles/r01_precision.md). The gate here is: beat the
-    # library bf16 execution of the reference math, and stay within 3.5e-2 (measured: student 2.5e-2, teacher 2.9e-2).
+    # The north star's bound: logits within 2e-2 of the fp32 reference. Met with fp16 operands -- what the reference
+    # itself computes in (REF/trainer.py:57-61,270) -- on BOTH the encoder and the LLM: bf16 operands land at
+    # 2.5e-2 / 2.9e-2 on these random-init 28-layer weights (profiles/r01_precision.md, profiles/r02_precision.md),
+    # and the reference's own Llama math run in bf16 by PyTorch eager on this GPU is ~4.8e-2 away (printed below).
     err_s = rel_l2(out["student_logits"].float().cpu(), ref["student_logits"][0])
     err_t = rel_l2(out["teacher_logits"].float().cpu(), ref["teacher_logits"][0])
     eager = _eager_bf16_teacher_logits(llm_sd, llm_cfg, tok, text_ids, resp_ids, cuda)
     err_eager = rel_l2(eager.float().cpu(), ref["teacher_logits"][0])
     print(f"full-size logits rel err: student {err_s:.3e} teacher {err_t:.3e} torch-eager-bf16 teacher {err_eager:.3e}")
-    assert err_t < err_eager and err_s < err_eager
-    assert err_s < 3.5e-2 and err_t < 3.5e-2
+    assert err_s < TOL_LOGITS and err_t < TOL_LOGITS
 
 
 def _eager_bf16_teacher_logits(llm_sd, llm_cfg, tok, text_ids, resp_ids, dev):
@@ -227,7 +226,7 @@ def test_whisper_encoder_golden(cuda):
     with torch.no_grad():
         out32 = enc.forward_fp32(mel.to(cuda))
         out = enc(mel.to(cuda), None)
-    assert out.shape == g["audio_embeds"].shape and out.dtype == torch.bfloat16
+    assert out.shape == g["audio_embeds"].shape and out.dtype == enc.operand_dtype == torch.float16
     assert rel_l2(out32.cpu(), g["audio_embeds"]) < TOL_EMBED
     n = compute_num_audio_embeds(2 * cfg.max_positions * 160, sr=16000)
     assert n == g["num_audio_embeds"] and out[0, :n].shape[0] == n

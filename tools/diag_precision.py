@@ -29,7 +29,11 @@ def main():
     llm_sd = configs.make_llm_state_dict(llm_cfg, seed=4321, dtype=torch.bfloat16, resid_scale=rs)
     tok = configs.stub_tokenizer(llm_cfg)
     audio, text_ids, resp_ids = configs.synthetic_utterance(llm_cfg, 0, 160000, T=40, R=64)
-    cfg, enc, llm = build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, dev)
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[os.environ.get("DTYPE", "fp16")]
+    enc_dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[os.environ.get("ENC_DTYPE", os.environ.get("DTYPE", "fp16"))]
+    print("operand dtype: llm", dt, "encoder", enc_dt)
+    cfg, enc, llm = build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, dev, dtype=dt)
+    enc.operand_dtype = enc_dt
     llm32 = {k: v.float() for k, v in llm_sd.items()}
     torch.set_num_threads(os.cpu_count())
     with torch.no_grad():
