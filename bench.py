@@ -1,30 +1,39 @@
 #!/usr/bin/env python
-"""bench.py -- utterances/s of the audio-prompt forward step on N B200 GPUs (one process per GPU).
+"""bench.py -- utterances/s of the audio-prompt step on N B200 GPUs (one process per GPU).
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
 
-Workload (BASELINE.json configs[1], the one the metric is quoted on): Llama-3.2-3B + HuBERT-large, synthetic 10 s
-16 kHz utterances, random-init weights. One step = one micro-batch of `--batch` utterances per GPU through
+Headline workload (what BASELINE.json's metric "encoder + prefill + KD loss" names): Llama-3.2-3B + HuBERT-large,
+synthetic 10 s 16 kHz utterances, random-init weights; one step = one micro-batch of `--batch` utterances per GPU through
     encoder -> splice -> packed student (audio prompt) + teacher (text prompt) prefill -> fused CE + KD (+FD) loss,
-i.e. "encoder + prefill + KD loss" (forward). `--workload train` times BASELINE.json configs[2] instead: the same
-forward with activations kept, the backward through the frozen LLM into every encoder/projector parameter, the SUM
-all-reduce of the flat gradient over the ranks and one AdamW update per step (grad_accum window = the global batch).
+i.e. the FORWARD of BASELINE.json configs[2]'s step (the training prompt: L_audio = 200, L_text = 117, R = 64).
+The same JSON line carries a `train` block: configs[2] proper -- that forward with activations kept, the backward
+through the frozen LLM into every encoder / projector parameter, the per-layer-bucketed SUM all-reduce of the gradient
+overlapped with the remaining backward, GradScaler check + AdamW every step -- with its own value / e2e / roofline, the
+all-reduce's span and EXPOSED time, and `check.grad_parity` (the all-reduced gradient of every rank's utterances vs
+rank 0 recomputing all of them alone). `--workload infer` times configs[1] proper instead: generate_audio_response's
+encoder + prompt prefill (L = 137, last-row logits, REF/inference.py:95-135). `--workload train` makes the training
+step the headline line (no forward leg).
 
 `value`  : utterances/s, inputs already resident in HBM, CUDA-event timed, max over ranks.
-`e2e`    : the same through the public streaming call AudioPromptStep.submit(...) / .result() with HOST (pinned)
-           inputs: every step's H2D of the waveforms + ids and the D2H read of its per-utterance losses happen inside
-           the timed region; batch i+1 is submitted before batch i's losses are read, so the copies and the host-side
-           plan building overlap the GPU work (the blocking form is `__call__` = submit(...).result()).
+`e2e`    : the same through the public streaming call submit(...) / .result() with HOST (pinned) inputs: every step's
+           H2D of the waveforms + ids and the D2H read of its per-utterance losses happen inside the timed region;
+           batch i+1 is submitted before batch i's losses are read, so the copies and the host-side plan building
+           overlap the GPU work (the blocking form is `__call__` = submit(...).result()). `value` reuses pre-built
+           index plans, `e2e` rebuilds them every step (config.timed says so).
 `roofline`: the dominant kernel family (the tcgen05 GEMM): algorithmic FLOPs of every GEMM launch of one step
            divided by the summed per-launch CUDA-event durations (b2s_gemm_timing_*), vs the measured sustained
-           bf16 peak in MEASURED_PEAKS.json.
-`cpu_baseline`: the oracle (CPU port of the reference path) timed on this box's host cores on a bounded sample.
+           bf16/fp16 dense peak in MEASURED_PEAKS.json; `traffic` = DRAM bytes per launch parsed from the committed
+           ncu launch list of the same command (profiles/).
+`roofline_loss`: the HBM-bound fused CE + KD kernel, timed alone and hot, traffic parsed from the same profile.
+`cpu_baseline` / `--impl reference`: the CPU oracle (oracle/reference_math.py, fp32, batch 1) on the host cores.
+`library_baseline`: the reference's own stock GPU path -- transformers' HubertModel + LlamaForCausalLM under fp16
+           autocast with cuBLAS / cuDNN / SDPA kernels -- at the SAME batch (B utterances, the reference's left-padded
+           batching, REF/utils.py:136-146) on the same B200: the library-kernel bar of SURVEY.md section 8d.
 """
-from __future__ import annotations
-
 import argparse
 import json
 import os
@@ -47,21 +56,23 @@ SAMPLES = 160000
 T_TEXT, R_RESP = 40, 64
 
 
-def ncu_traffic_per_launch(train: bool):
-    """DRAM bytes per GEMM launch from the committed ncu launch list of the same command (dram__bytes_read.sum +
-    dram__bytes_write.sum, averaged over the GEMM launches of one step); None when the profile is not there."""
-    name = "r01_launch_summary_train.txt" if train else "r01_launch_summary.txt"
-    path = os.path.join(ROOT, "profiles", name)
-    try:
-        tot_gb, n = 0.0, 0
-        for line in open(path):
-            if "gemm_bf16_tcgen05_kernel" in line and "dram=" in line:
-                n += int(line.split("n=")[1].split()[0])
-                tot_gb += float(line.split("dram=")[1].split()[0])
-        if n:
-            return tot_gb * 1e9 / n, f"profiles/{name} (ncu, {n} GEMM launches of one step, mean per launch)"
-    except Exception:
-        pass
+def ncu_traffic_per_launch(train: bool, kernel: str = "gemm_bf16_tcgen05_kernel"):
+    """DRAM bytes per launch of `kernel` from the committed ncu launch list of the same command (dram__bytes_read.sum +
+    dram__bytes_write.sum, averaged over that kernel's launches of one step; tools/summarize_launches.py); the newest
+    round's summary wins; (None, None) when no profile is there."""
+    for rnd in ("r02", "r01"):
+        name = f"{rnd}_launch_summary_train.txt" if train else f"{rnd}_launch_summary.txt"
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            tot_gb, n = 0.0, 0
+            for line in open(path):
+                if kernel in line and "dram=" in line:
+                    n += int(line.split("n=")[1].split()[0])
+                    tot_gb += float(line.split("dram=")[1].split()[0])
+            if n:
+                return tot_gb * 1e9 / n, f"profiles/{name} (ncu, {n} {kernel} launches of one step, mean per launch)"
+        except Exception:
+            pass
     return None, None
 
 
@@ -138,10 +149,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="prefill", choices=["prefill", "train"],
-                    help="prefill = configs[1] (default, the metric's configuration); train = configs[2]")
+    ap.add_argument("--workload", default="forward", choices=["forward", "prefill", "train", "infer"],
+                    help="forward (default; 'prefill' is its old name) = the metric's encoder + prefill + KD loss, with "
+                         "the configs[2] training step reported in the same line's `train` block; train = the training "
+                         "step as the headline; infer = configs[1], generate_audio_response's encoder + prompt prefill")
+    ap.add_argument("--no-train-block", action="store_true", help="forward workload: skip the `train` block")
     ap.add_argument("--regularize", default="none", choices=["none", "dropout", "all"],
-                    help="train workload: HF train-mode regularisers of the encoder (REF/trainer.py:258). 'dropout' = "
+                    help="training step: HF train-mode regularisers of the encoder (REF/trainer.py:258). 'dropout' = "
                          "every dropout site + SpecAugment (same work as the deterministic step plus the mask "
                          "generation), 'all' = also LayerDrop (skips ~10%% of the encoder layers, like the reference)")
     ap.add_argument("--ragged", action="store_true",
@@ -150,12 +164,19 @@ def parse():
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"],
                     help="16-bit operand format of the encoder and the LLM (fp16 = the reference's autocast dtype and the "
                          "default; bf16 = the round-1 path, for A/B)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="training step: one monolithic all-reduce after the backward instead of per-layer buckets on a "
+                         "communication stream (A/B)")
     ap.add_argument("--gemm-shapes", default="", help="write the per-shape GEMM table of the instrumented steps here")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--cpu-utts", type=int, default=3, help="utterances timed for the CPU baseline sample")
     ap.add_argument("--profile-mode", action="store_true",
                     help="only warm-up + timed steps (no e2e / roofline / CPU legs): for runs under ncu")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.workload == "prefill":
+        a.workload = "forward"
+    return a
 
 
 # ------------------------------------------------------------------------------------------ synthetic model
@@ -328,17 +349,22 @@ def run_reference(args):
 
 
 METRIC_TRAIN = "utterances/sec (10 s audio, training step: encoder+prefill+KD loss forward, backward, AdamW)"
+METRIC_INFER = "utterances/sec (10 s audio, inference: encoder + audio-prompt prefill, last-row logits)"
 WORKLOAD_TRAIN = ("configs[2] Llama-3.2-3B + HuBERT-large training step (encoder/projector trainable, LLM frozen), "
                   "CE + logit-KD + FD loss, synthetic 10 s utterances (L_audio=200, L_text=117, R=64); train-mode "
                   "regularisers per config.regularize (none = deterministic step)")
-WORKLOAD = ("configs[1] Llama-3.2-3B + HuBERT-large audio-prompt forward: encoder + packed student&teacher prefill "
-            "+ fused CE/KD/FD loss, synthetic 10 s utterances (L_audio=200, L_text=117, R=64)")
+WORKLOAD = ("forward of configs[2]'s step = the metric's `encoder + prefill + KD loss`: Llama-3.2-3B + HuBERT-large, "
+            "encoder + packed student&teacher prefill + fused CE/KD/FD loss, synthetic 10 s utterances (L_audio=200, "
+            "L_text=117, R=64)")
+WORKLOAD_INFER = ("configs[1] Llama-3.2-3B + HuBERT-large audio-prompt prefill (generate_audio_response up to its first "
+                  "LLM forward, REF/inference.py:95-135): encoder + prompt (9 + 123 + 5 = 137 rows) + prefill, last-row "
+                  "logits, synthetic 10 s utterances")
 
 
 # ------------------------------------------------------------------------------------------ main arm
-def gemm_flops_per_utt(train=False):
+def gemm_flops_per_utt(train=False, infer=False):
     """Algorithmic FLOPs per utterance credited to the GEMM kernel (attention and conv0
-    excluded, LM head on the 2*R consumed rows only). Training adds dgrad + wgrad for the encoder (no dgrad into the
+    excluded, LM head on the consumed rows only). Training adds dgrad + wgrad for the encoder (no dgrad into the
     waveform) and dgrad only for the student sequence of the frozen LLM."""
     conv1 = 2 * 512 * 512 * 3 * 15999
     conv = conv1 + 2 * 512 * 512 * (3 * (7999 + 3999 + 1999) + 2 * (999 + 499))
@@ -346,12 +372,153 @@ def gemm_flops_per_utt(train=False):
     enc = conv + 2 * N * 512 * 1024 + 2 * N * 1024 * 64 * 128 + 24 * (2 * N * 1024 * (4 * 1024 + 2 * 4096)) \
         + 2 * 123 * 1024 * 3072
     per_tok = 2 * 3072 * (5120 + 3072 + 2 * 8192 + 8192)
+    tail = 2 * 3072 * (3072 + 2 * 8192 + 8192)  # out-projection + MLP of one row of the last layer
+    if infer:  # L = 137, the last layer's tail and the LM head on the single consumed row
+        return enc + 28 * per_tok * 137 - 136 * tail + 2 * 3072 * 128256
     llm = 28 * per_tok * (200 + 117) + 2 * 2 * R_RESP * 3072 * 128256
     if not train:
         # the forward runs the last layer's out-projection / MLP on the 2 * R consumed rows only: credit what is done
-        skipped = (200 + 117 - 2 * R_RESP) * 2 * 3072 * (3072 + 2 * 8192 + 8192)
-        return enc + llm - skipped
+        return enc + llm - (200 + 117 - 2 * R_RESP) * tail
     return 3 * enc + llm + 28 * per_tok * 200 + 2 * R_RESP * 3072 * 128256
+
+
+def timed_loop(run, steps, warmup, dp, dev, lib, clock_index=None):
+    """W untimed + K timed steps bracketed by barrier + synchronize; CUDA-event time, max over ranks."""
+    for i in range(warmup):
+        run(i)
+    torch.cuda.synchronize()
+    dp.barrier()
+    clocks = None
+    if clock_index is not None:
+        clocks = ClockSampler(clock_index)
+        clocks.start()
+    launches0 = lib.b2s_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    out = None
+    for i in range(steps):
+        out = run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    dp.barrier()
+    launches = lib.b2s_launch_count() - launches0
+    clk = clocks.stop() if clocks is not None else None
+    ms = dp.max_over_ranks(e0.elapsed_time(e1), dev)
+    return ms, int(launches), clk, out
+
+
+def e2e_loop(submit, steps, warmup, dp, dev):
+    """The streaming public call from HOST buffers: batch i+1 is submitted before batch i's result is read."""
+    warm = None
+    for i in range(max(3, warmup)):  # same pipelined pattern as the timed loop, so both sets of staging buffers exist
+        nxt = submit(i)
+        if warm is not None:
+            warm.result()
+        warm = nxt
+    warm.result()
+    torch.cuda.synchronize()
+    dp.barrier()
+    t0 = time.perf_counter()
+    pending = None
+    for i in range(steps):
+        nxt = submit(i)
+        if pending is not None:
+            pending.result()
+        pending = nxt
+    pending.result()
+    torch.cuda.synchronize()
+    sec = dp.max_over_ranks(time.perf_counter() - t0, dev)
+    dp.barrier()
+    return sec
+
+
+def gemm_roofline(run, lib, peaks, flops_step, ms_step, train, shapes_path="", rank=0):
+    """Per-launch CUDA events over two instrumented steps (b2s_gemm_timing_*)."""
+    import ctypes as C
+    lib.b2s_gemm_timing_enable(1)
+    for i in range(2):
+        run(i)
+    torch.cuda.synchronize()
+    g_ms, g_n = C.c_double(), C.c_longlong()
+    lib.b2s_gemm_timing_read(C.byref(g_ms), C.byref(g_n))
+    if shapes_path and rank == 0:
+        write_gemm_shapes(lib, g_n.value, shapes_path, steps=2)
+    lib.b2s_gemm_timing_enable(0)
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained; fp16 and bf16 share the kind::f16 rate)" if peaks
+                else "fallback (B200_PROFILING.md sustained)")
+    gemm_ms_step = g_ms.value / 2
+    achieved = flops_step / (gemm_ms_step / 1e3) / 1e12 if gemm_ms_step > 0 else None
+    r = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all launches of one step)", "achieved": achieved,
+         "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+         "peak_source": peak_src, "launches_per_step": g_n.value // 2, "gemm_ms_per_step": gemm_ms_step,
+         "gemm_share_of_step": gemm_ms_step / ms_step if ms_step > 0 else None}
+    r["traffic"], r["traffic_source"] = ncu_traffic_per_launch(train)
+    return r
+
+
+def library_baseline(B, dev, steps=3):
+    """The reference's own stock GPU path at the SAME batch on this GPU: transformers' HubertModel (pretrained
+    architecture, random init) -> AvgPool1d(8, 4) -> Linear, then LlamaForCausalLM on the left-padded student and
+    teacher batches with all-row logits and hidden states, CE / soft-CE / MSE losses exactly as REF/trainer.py:270-370
+    computes them, under torch.autocast(fp16) with an fp16 LLM (REF/trainer.py:57-61,270). cuBLAS / cuDNN / SDPA
+    kernels; no kernel of this repository runs here."""
+    import torch.nn.functional as F
+    from transformers import HubertConfig, HubertModel, LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(1234)
+    with torch.device(dev):
+        hub = HubertModel(HubertConfig(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16,
+                                       intermediate_size=4096, feat_extract_norm="layer", conv_bias=True,
+                                       do_stable_layer_norm=True, feat_proj_layer_norm=True, conv_dim=(512,) * 7,
+                                       apply_spec_augment=False)).eval()
+        proj = torch.nn.Linear(1024, 3072)
+        llm = LlamaForCausalLM(LlamaConfig(
+            vocab_size=128256, hidden_size=3072, intermediate_size=8192, num_hidden_layers=28, num_attention_heads=24,
+            num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-5, rope_theta=500000.0, tie_word_embeddings=True,
+            max_position_embeddings=131072, rope_scaling=dict(rope_type="llama3", factor=32.0, high_freq_factor=4.0,
+                                                            low_freq_factor=1.0, original_max_position_embeddings=8192)
+        )).to(torch.float16).eval()
+    embed = llm.model.embed_tokens
+    g = torch.Generator().manual_seed(5)
+    waves = (torch.randn(B, SAMPLES, generator=g) * 0.1).to(dev)
+    ids = lambda n: torch.randint(0, 128000, (B, n), generator=g).to(dev)
+    prefix, suffix, text, resp = ids(9), ids(5), ids(T_TEXT), ids(R_RESP)
+    layers = (0, 5, 11, 17, 23)
+
+    @torch.no_grad()
+    def one():
+        with torch.autocast(device_type="cuda", dtype=torch.float16):
+            h = hub(waves).last_hidden_state
+            a = proj(F.avg_pool1d(h.transpose(1, 2), 8, 4).transpose(1, 2))
+            tail = torch.cat([embed(suffix), embed(resp[:, 1:])], dim=1)
+            s_seq = torch.cat([embed(prefix), a.to(torch.float16), tail], dim=1)      # (B, 200, 3072)
+            t_seq = torch.cat([embed(prefix), embed(text), tail], dim=1)              # (B, 117, 3072)
+            so = llm(inputs_embeds=s_seq, output_hidden_states=True)
+            to = llm(inputs_embeds=t_seq, output_hidden_states=True)
+            R = R_RESP
+            ntp = F.cross_entropy(so.logits[:, -R:-1].reshape(-1, so.logits.shape[-1]).float(), resp[:, 1:].reshape(-1))
+            ls = F.log_softmax(so.logits[:, -R:].float(), -1)
+            ld = -(F.softmax(to.logits[:, -R:].float(), -1) * ls).sum(-1).mean()
+            fd = sum(F.mse_loss(so.hidden_states[l][:, -R:], to.hidden_states[l][:, -R:]) for l in layers)
+            return 0.5 * ntp + 0.5 * ld + fd
+
+    one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del hub, llm, proj
+    torch.cuda.empty_cache()
+    return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "batch": B, "steps": steps,
+            "impl": "transformers HubertModel + LlamaForCausalLM (random init of the named architectures), "
+                    "torch.autocast(fp16) + fp16 LLM, cuBLAS / cuDNN / SDPA, left-padded batch like REF/utils.py:136-146 "
+                    "(all-row logits and hidden states as the reference computes them), forward of the same step",
+            "finite": bool(torch.isfinite(loss))}
 
 
 def main():
@@ -360,11 +527,11 @@ def main():
         return run_reference(args)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists); use --impl reference for the CPU arm")
-    from llm_speech_summarization_b200 import _lib, dp, ops
+    from llm_speech_summarization_b200 import _lib, dp
     from llm_speech_summarization_b200.config import KNOWN_LLMS, to_namespace
     from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
     from llm_speech_summarization_b200.model.audio_llama import AudioLlamaForCausalLM
-    from llm_speech_summarization_b200.step import AudioPromptStep
+    from llm_speech_summarization_b200.step import AudioPromptStep, PendingStep
 
     rank, local_rank, world = dp.init_process_group()
     dev = torch.device("cuda", local_rank)
@@ -389,16 +556,13 @@ def main():
     llm.eval().to(dev)
     tok = FixedTokenizer(la.vocab, la.bos)
     step = AudioPromptStep(enc, llm, tok, cfg.model.llm_type)
-    train = args.workload == "train"
     B = args.batch
-    trainer = None
-    if train:
-        from llm_speech_summarization_b200.training import EncoderTrainer
-        trainer = EncoderTrainer(step, enc, llm, lr=5e-5, betas=(0.9, 0.999), grad_accum_interval=B * world,
-                                 total_optimizer_steps=10 ** 6, regularize=args.regularize != "none",
-                                 generator=torch.Generator().manual_seed(1234 + rank))
-        if args.regularize == "dropout":
-            enc.regularizers.layerdrop = 0.0
+    lib = _lib.load()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
 
     n_pool = 2  # rotate through distinct micro-batches
     host = [synth_batch(B, la.vocab, 1000 * (rank + 1) + i) for i in range(n_pool)]
@@ -406,123 +570,202 @@ def main():
     resident = [(w.to(dev), t, r) for (w, t, r) in host]
     plans = [step.plan(123, t, r, dev) for (_, t, r) in resident]
     torch.cuda.synchronize()
+    plan0 = plans[0]
+    h2d_step = B * SAMPLES * 4 + 4 * (plan0.row_src.numel() + plan0.cu_seqlens.numel() + plan0.positions.numel() +
+                                      plan0.logit_rows.numel() + plan0.labels.numel() + plan0.row_offsets.numel()) \
+        + 4 * plan0.audio_rows.numel() + 4 * plan0.seg.numel() + 4 * plan0.resp_len_f.numel()
+    l2_note = ("no flush needed: every step streams ~7 GB of weights and >2 GB of activations (>> 126 MB L2); two "
+               "distinct micro-batches alternate")
 
-    ragged_lens = None
-    if args.ragged:
-        assert train, "--ragged applies to --workload train"
-        gl = torch.Generator().manual_seed(4242 + rank)
-        ragged_lens = [[int(x) for x in torch.randint(SAMPLES // 2, SAMPLES + 1, (B,), generator=gl)] for _ in range(n_pool)]
-        for k in range(n_pool):
-            ragged_lens[k][0] = SAMPLES  # the padded length is the longest utterance
-            for b_, n_ in enumerate(ragged_lens[k]):
-                resident[k][0][b_, n_:] = 0
-                host[k][0][b_, n_:] = 0
+    # ======================================================================================== training step
+    def measure_train(headline: bool):
+        from llm_speech_summarization_b200.training import EncoderTrainer
+        trainer = EncoderTrainer(step, enc, llm, lr=5e-5, betas=(0.9, 0.999), grad_accum_interval=B * world,
+                                 total_optimizer_steps=10 ** 6, regularize=args.regularize != "none",
+                                 generator=torch.Generator().manual_seed(1234 + rank))
+        trainer.overlap_allreduce = not args.no_overlap
+        if args.regularize == "dropout":
+            enc.regularizers.layerdrop = 0.0
+        ragged_lens = None
+        if args.ragged:
+            gl = torch.Generator().manual_seed(4242 + rank)
+            ragged_lens = [[int(x) for x in torch.randint(SAMPLES // 2, SAMPLES + 1, (B,), generator=gl)]
+                           for _ in range(n_pool)]
+            for k in range(n_pool):
+                ragged_lens[k][0] = SAMPLES  # the padded length is the longest utterance
+                for b_, n_ in enumerate(ragged_lens[k]):
+                    resident[k][0][b_, n_:] = 0
+                    host[k][0][b_, n_:] = 0
+
+        def run(i):
+            w, t, r = resident[i % n_pool]
+            if ragged_lens is not None:
+                return trainer.train_step(w, t, r, lengths=ragged_lens[i % n_pool])
+            return trainer.train_step(w, t, r, plan=plans[i % n_pool])
+
+        ms, launches, clk, out = timed_loop(run, args.steps, args.warmup, dp, dev, lib,
+                                            clock_index=local_rank if headline else None)
+        total_utts = dp.sum_over_ranks(float(B * args.steps), dev)
+        res = {"metric": METRIC_TRAIN, "value": total_utts / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / args.steps,
+               "gpu_launches": launches, "clocks": clk, "loss_check": float(out["total_loss"].mean())}
+        if args.profile_mode:
+            return res, trainer
+        ar = trainer.optimizer.allreduce_ms()
+        if world > 1 and ar is not None:
+            res["allreduce_ms"] = {"span": dp.max_over_ranks(ar["span"], dev), "exposed": dp.max_over_ranks(ar["exposed"], dev),
+                                   "bytes": int(trainer.optimizer.grad.numel() * 4),
+                                   "how": ("per-transformer-layer buckets on a communication stream, each launched when "
+                                           "its layer's backward has been enqueued; `exposed` = how long the compute "
+                                           "stream waited before the optimizer step (last timed step, max over ranks)"
+                                           if trainer.overlap_allreduce and trainer._layer_spans is not None else
+                                           "one monolithic all-reduce on the compute stream after the backward")}
+        elif world > 1:
+            # monolithic path: time it directly
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            trainer.optimizer.all_reduce_grads()
+            b_.record()
+            torch.cuda.synchronize()
+            res["allreduce_ms"] = {"span": dp.max_over_ranks(a_.elapsed_time(b_), dev),
+                                   "exposed": dp.max_over_ranks(a_.elapsed_time(b_), dev),
+                                   "bytes": int(trainer.optimizer.grad.numel() * 4),
+                                   "how": "one monolithic all-reduce on the compute stream after the backward"}
+            trainer.optimizer.zero_grad()
+        else:
+            res["allreduce_ms"] = None  # one rank: nothing to exchange
+        rag = (lambda i: {"lengths": ragged_lens[i % n_pool]}) if ragged_lens is not None else (lambda i: {})
+        sec = e2e_loop(lambda i: trainer.submit(host[i % n_pool][0], host[i % n_pool][1], host[i % n_pool][2], dev, **rag(i)),
+                       args.steps, args.warmup, dp, dev)
+        res["e2e"] = {"value": total_utts / sec, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": 4 * 4 * B,
+                      "api": "EncoderTrainer.submit()/result(), one batch in flight ahead of the one being read"}
+        res["roofline"] = gemm_roofline(run, lib, peaks, gemm_flops_per_utt(train=True) * B, ms / args.steps, True,
+                                        args.gemm_shapes if headline else "", rank)
+        res["roofline"]["algorithmic_gflop_per_utt"] = gemm_flops_per_utt(train=True) / 1e9
+        sc = trainer.scaler.read()
+        res["grad_scaler"] = {"scale": sc["scale"], "optimizer_steps": sc["opt_steps"], "skipped_steps": sc["skipped_steps"],
+                              "enabled": trainer.scaler.enabled}
+        res["check"] = {"mean_total_loss": res.pop("loss_check"),
+                        "grad_parity": grad_parity(trainer, ragged_lens is not None)}
+        if ragged_lens is not None:
+            res["ragged"] = "utterance lengths uniform in [5 s, 10 s], mean %.2f s" % (
+                sum(map(sum, ragged_lens)) / (len(ragged_lens) * B) / 16000.0)
+        return res, trainer
+
+    def grad_parity(trainer, skip: bool):
+        """The real-path multi-rank invariant (REF/trainer.py:372-384 semantics): every rank runs
+        b = 2 of its own utterances through EncoderTrainer.train_step (window = 2 * world, bucketed all-reduce), rank 0
+        then recomputes ALL 2 * world utterances alone, one micro-batch per rank's share, with no exchange; the two
+        flat gradients (loss scale divided out) must agree. At one rank this compares the step with itself."""
+        if skip:
+            return None
+        b = 2
+        mk = lambda r_: synth_batch(b, la.vocab, 777000 + r_)
+        saved = (trainer.grad_accum_interval, trainer._micro, trainer.optimizer.lr, trainer.overlap_allreduce)
+        trainer.grad_accum_interval, trainer._micro = b * world, 0
+        trainer.optimizer.lr = 0.0  # the check must not move the parameters
+        trainer.capture_grad = True
+        trainer.optimizer.zero_grad()
+        w, t, r = mk(rank)
+        trainer.train_step(w.to(dev), t, r)
+        g_dist = trainer.last_flat_grad / trainer.last_flat_grad_scale
+        err = None
+        if rank == 0:
+            trainer.optimizer.zero_grad()
+            # rank 0 alone: run every rank's share as plain micro-batches, never touching the process group
+            for r_ in range(world):
+                w2, t2, r2 = mk(r_)
+                trainer.step_fn.forward_backward(w2.to(dev), t2, r2, loss_scale=1.0 / (b * world),
+                                                 generator=trainer.generator, scaler=trainer.scaler)
+            enc.flush_grads()
+            g_one = trainer.optimizer.grad / trainer.scaler.scale_tensor
+            err = float((g_dist - g_one).norm() / g_one.norm().clamp_min(1e-30))
+            finite = bool(torch.isfinite(g_dist).all())
+            trainer.optimizer.zero_grad()
+        dp.barrier()
+        trainer.capture_grad = False
+        trainer.grad_accum_interval, trainer._micro, trainer.optimizer.lr, trainer.overlap_allreduce = saved
+        trainer.last_flat_grad = None
+        if rank != 0:
+            return None
+        return {"rel_l2": err, "finite": finite, "utterances": b * world, "ranks": world,
+                "what": "all-reduced flat gradient of b=2 utterances per rank vs rank 0 recomputing all of them alone"}
+
+    # ======================================================================================== headline = train
+    if args.workload == "train":
+        res, trainer = measure_train(headline=True)
+        if rank == 0:
+            if args.profile_mode:
+                print(json.dumps({"profile_mode": True, "ms_per_step": res["ms_per_step"], "gpu_launches": res["gpu_launches"]}))
+            else:
+                line = {"metric": METRIC_TRAIN, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                        "config": {"workload": WORKLOAD_TRAIN, "utterances_per_step_per_gpu": B, "parallelism": f"dp{world}",
+                                   "l2": l2_note, "regularize": args.regularize,
+                                   "timed": "forward with kept activations + backward to all encoder/projector parameters "
+                                            "+ bucketed gradient all-reduce + GradScaler check + AdamW, every step; `value` "
+                                            "reuses pre-built index plans, `e2e` rebuilds them every step",
+                                   **({"ragged": res["ragged"]} if "ragged" in res else {})},
+                        "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
+                        "roofline": res["roofline"], "roofline_loss": None, "cpu_baseline": None,
+                        "allreduce_ms": res["allreduce_ms"], "grad_scaler": res["grad_scaler"], "check": res["check"]}
+                print(json.dumps(line), flush=True)
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ======================================================================================== headline = forward / infer
+    infer = args.workload == "infer"
+    infer_plan = [None]
 
     def run_resident(i):
         w, t, r = resident[i % n_pool]
-        if train and ragged_lens is not None:
-            return trainer.train_step(w, t, r, lengths=ragged_lens[i % n_pool])
-        if train:
-            return trainer.train_step(w, t, r, plan=plans[i % n_pool])
+        if infer:
+            logits, infer_plan[0] = step.prefill_prompts(w, plan=infer_plan[0])
+            return {"logits": logits}
         return step.forward_losses(w, t, r, plan=plans[i % n_pool])
 
-    public = trainer if train else step
+    def submit(i):
+        w, t, r = host[i % n_pool]
+        if not infer:
+            return step.submit(w, t, r, dev)
+        from llm_speech_summarization_b200.step import _stage_to_device
+        if getattr(step, "_copy_stream", None) is None:
+            step._copy_stream = torch.cuda.Stream(dev)
+        logits, _ = step.prefill_prompts(_stage_to_device(w, dev, step._copy_stream))
+        nxt = logits.float().argmax(dim=-1).to(torch.int32)  # the first greedy token of every utterance
+        hbuf = torch.empty(nxt.shape, dtype=nxt.dtype, pin_memory=True)
+        hbuf.copy_(nxt, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return PendingStep(["next_token"], hbuf[None], ev)
 
-    lib = _lib.load()
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
     loss_alone = None
-    if not train and not args.profile_mode:
+    if not infer and not args.profile_mode:
         loss_alone = loss_roofline(step, lib, _lib, resident[0], plans[0], dev, peaks)
-    # ---- value: inputs resident in HBM
-    for i in range(args.warmup):
-        run_resident(i)
-    torch.cuda.synchronize()
-    dp.barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    launches0 = lib.b2s_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for i in range(args.steps):
-        out = run_resident(i)
-    e1.record()
-    torch.cuda.synchronize()
-    dp.barrier()
-    launches = lib.b2s_launch_count() - launches0
-    clk = clocks.stop()
-    ms = dp.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms, launches, clk, out = timed_loop(run_resident, args.steps, args.warmup, dp, dev, lib, clock_index=local_rank)
     total_utts = dp.sum_over_ranks(float(B * args.steps), dev)
     value = total_utts / (ms / 1e3)
-    loss_check = float(out["total_loss"].mean())
-
+    if infer:
+        check = {"finite_logits": bool(torch.isfinite(out["logits"].float()).all()), "prompt_rows": infer_plan[0]["max_len"]}
+    else:
+        check = {"mean_total_loss": float(out["total_loss"].mean())}
     if args.profile_mode:
         if rank == 0:
             print(json.dumps({"profile_mode": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)}))
         return
-    # ---- e2e: host buffers -> H2D -> step -> D2H, through the public call
-    rag = (lambda i: {"lengths": ragged_lens[i % n_pool]}) if ragged_lens is not None else (lambda i: {})
-    # warm-up in the same pipelined pattern as the timed loop (two batches in flight), so the second set of pinned /
-    # device staging buffers exists before the clock starts (cudaHostAlloc under 8 processes is slow)
-    warm = None
-    for i in range(max(3, args.warmup)):
-        nxt = public.submit(host[i % n_pool][0], host[i % n_pool][1], host[i % n_pool][2], dev, **rag(i))
-        if warm is not None:
-            warm.result()
-        warm = nxt
-    warm.result()
-    torch.cuda.synchronize()
-    dp.barrier()
-    t0 = time.perf_counter()
-    pending = None  # the streaming form of the public call: batch i+1 is submitted before batch i's losses are read
-    for i in range(args.steps):
-        w, t, r = host[i % n_pool]
-        nxt = public.submit(w, t, r, dev, **rag(i))
-        if pending is not None:
-            res = pending.result()
-        pending = nxt
-    res = pending.result()
-    torch.cuda.synchronize()
-    e2e_s = dp.max_over_ranks(time.perf_counter() - t0, dev)
-    dp.barrier()
-    e2e_value = total_utts / e2e_s
-    plan0 = plans[0]
-    h2d = B * SAMPLES * 4 + 4 * (plan0.row_src.numel() + plan0.cu_seqlens.numel() + plan0.positions.numel() +
-                                 plan0.logit_rows.numel() + plan0.labels.numel() + plan0.row_offsets.numel()) \
-        + 4 * plan0.audio_rows.numel() + 4 * plan0.seg.numel() + 4 * plan0.resp_len_f.numel()
-    d2h = 4 * 4 * B
-
-    # ---- roofline of the dominant kernel (tcgen05 GEMM): per-launch CUDA events over instrumented steps
-    lib.b2s_gemm_timing_enable(1)
-    for i in range(2):
-        run_resident(i)
-    torch.cuda.synchronize()
-    import ctypes as C
-    g_ms, g_n = C.c_double(), C.c_longlong()
-    lib.b2s_gemm_timing_read(C.byref(g_ms), C.byref(g_n))
-    if args.gemm_shapes and rank == 0:
-        write_gemm_shapes(lib, g_n.value, args.gemm_shapes, steps=2)
-    lib.b2s_gemm_timing_enable(0)
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained)"
-    flops_step = gemm_flops_per_utt(train) * B
-    gemm_ms_step = g_ms.value / 2
-    achieved = flops_step / (gemm_ms_step / 1e3) / 1e12 if gemm_ms_step > 0 else None
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all launches of one step)",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": (achieved / peak_tf) if achieved else None, "traffic": None, "peak_source": peak_src,
-                "launches_per_step": g_n.value // 2, "gemm_ms_per_step": gemm_ms_step,
-                "gemm_share_of_step": gemm_ms_step / (ms / args.steps) if ms > 0 else None,
-                "algorithmic_gflop_per_utt": gemm_flops_per_utt(train) / 1e9}
-    roofline["traffic"], roofline["traffic_source"] = ncu_traffic_per_launch(train)
+    sec = e2e_loop(submit, args.steps, args.warmup, dp, dev)
+    e2e_value = total_utts / sec
+    h2d = B * SAMPLES * 4 + (4 * (2 * infer_plan[0]["rows"] + 2 * B + 1) if infer else h2d_step - B * SAMPLES * 4)
+    d2h = 4 * B if infer else 4 * 4 * B
+    flops_utt = gemm_flops_per_utt(infer=infer)
+    roofline = gemm_roofline(run_resident, lib, peaks, flops_utt * B, ms / args.steps, False, args.gemm_shapes, rank)
+    roofline["algorithmic_gflop_per_utt"] = flops_utt / 1e9
     # ---- the HBM-bound kernel the north star names (fused CE + KD loss): again, hot, right after the timed steps
     roofline_loss = None
-    if not train and loss_alone is not None:
+    if loss_alone is not None:
         hot = loss_roofline(step, lib, _lib, resident[0], plans[0], dev, peaks)
+        tr_b, tr_src = ncu_traffic_per_launch(False, kernel="kd_ce_partial_kernel")
         roofline_loss = {"bound": "hbm", "kernel": "kd_ce_partial_kernel + kd_ce_finalize_kernel (fused CE + KD forward)",
                          "unit": "GB/s", **loss_alone,
                          "timed": "alone, before the step heats the part (SM clock at its maximum): the burst HBM peak "
@@ -530,35 +773,45 @@ def main():
                                   "power cap (the kernel issues 2 MUFU.EX2 per logit pair and is SM-clock sensitive)",
                          "hot": {k: hot[k] for k in ("achieved", "frac", "ms")},
                          "l2": "256 MB buffer rewritten before every timed launch",
-                         "traffic": 1.0507e9 * loss_alone["rows"] / 2048.0,
-                         "traffic_source": "profiles/r01_ncu_full_captures.txt (dram read 1.0507 GB at 2048 rows)",
+                         "traffic": (tr_b * loss_alone["rows"] / 2048.0) if tr_b else None,
+                         "traffic_source": (tr_src + ", scaled from the profiled 2048 rows") if tr_src else None,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback"}
+    train_block = None
+    if not infer and not args.no_train_block:
+        tb, _trainer = measure_train(headline=False)
+        tb.pop("clocks", None)
+        train_block = {"workload": WORKLOAD_TRAIN, **tb}
+        del _trainer
+        torch.cuda.empty_cache()
 
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline and not train:
+        if world == 1 and not args.no_cpu_baseline and not infer:
             enc_cpu = {k: v.float().cpu() for k, v in enc_sd.items()}
             llm_cpu = {k: v.float().cpu() for k, v in llm_sd.items() if k != "lm_head.weight"}
             llm_cpu["lm_head.weight"] = llm_cpu["model.embed_tokens.weight"]
             cpu, _ = cpu_reference(args.cpu_utts, enc_cpu, llm_cpu, steps=1, warmup=0)
-        workload = WORKLOAD_TRAIN if train else WORKLOAD
-        timed = ("forward with kept activations + backward to all encoder/projector parameters + gradient all-reduce "
-                 "+ AdamW, every step" if train else "forward only (encoder + student/teacher prefill + CE/KD/FD)")
-        line = {"metric": METRIC_TRAIN if train else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": workload, "utterances_per_step_per_gpu": B, "parallelism": f"dp{world}",
-                           "l2": "no flush needed: every step streams ~7 GB of weights and >2 GB of activations "
-                                 "(>> 126 MB L2); two distinct micro-batches alternate",
-                           "timed": timed, **({"regularize": args.regularize} if train else {}),
-                           **({"ragged": "utterance lengths uniform in [5 s, 10 s], mean %.2f s" % (
-                               sum(map(sum, ragged_lens)) / (len(ragged_lens) * B) / 16000.0)} if ragged_lens else {})},
+        lib_base = None
+        if world == 1 and not args.no_library_baseline and not infer:
+            try:
+                del enc_sd, llm_sd
+                torch.cuda.empty_cache()
+                lib_base = library_baseline(B, dev)
+            except Exception as e:  # the bar is a report, never a reason to lose the measurement
+                lib_base = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        line = {"metric": METRIC_INFER if infer else METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": WORKLOAD_INFER if infer else WORKLOAD, "utterances_per_step_per_gpu": B,
+                           "parallelism": f"dp{world}", "l2": l2_note,
+                           "timed": ("encoder + prompt splice + packed prefill, logits of the last row of every prompt"
+                                     if infer else "forward only (encoder + student/teacher prefill + CE/KD/FD)") +
+                                    "; `value` reuses pre-built index plans, `e2e` rebuilds them every step"},
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "submit()/result(), one batch in flight ahead of the one being read"},
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_loss": roofline_loss,
-                "cpu_baseline": cpu,
-                "check": {"mean_total_loss": loss_check}}
+                "cpu_baseline": cpu, "library_baseline": lib_base, "train": train_block, "check": check}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

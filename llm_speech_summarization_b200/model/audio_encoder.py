@@ -709,7 +709,10 @@ class AudioEncoder(nn.Module):
         out = torch.empty(B, pooled, w.llm_dim, device=wave.device, dtype=torch.float32)
         if draw is None and self.regularizers is not None and self.training:
             from ..regularizers import draw as _draw
-            draw = _draw(self.regularizers, B, frames, w.num_layers, wave.device, generator)
+            vf = None
+            if lengths is not None and len(set(int(n) for n in lengths)) > 1:
+                vf = [self.num_frames(int(n))[0] for n in lengths]  # SpecAugment spans inside each utterance's own length
+            draw = _draw(self.regularizers, B, frames, w.num_layers, wave.device, generator, valid_frames=vf)
         reg = None
         if draw is not None:
             mse = self.encoder.masked_spec_embed.detach()

@@ -86,15 +86,25 @@ class RegularizerDraw:
 
 
 def draw(cfg: RegularizerConfig, batch: int, frames: int, layers: int, device,
-         generator: Optional[torch.Generator] = None) -> RegularizerDraw:
+         generator: Optional[torch.Generator] = None, valid_frames=None) -> RegularizerDraw:
     """Draw the host-side randomness of one micro-batch from a torch CPU generator (None = torch's global one, which
-    is what the reference's LayerDrop consumes)."""
+    is what the reference's LayerDrop consumes). valid_frames (ragged batch): frames of each utterance on its own --
+    its SpecAugment spans are counted and placed inside ITS length, like HF's per-`input_length` loop, instead of
+    landing in the padding."""
     seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator).item())
     skip = (torch.rand(layers, generator=generator) < cfg.layerdrop).to(torch.uint8).numpy().copy()
     time_mask = None
     if cfg.apply_spec_augment and cfg.mask_time_prob > 0:
         np_seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator).item())
-        m = compute_time_mask(batch, frames, cfg.mask_time_prob, cfg.mask_time_length, cfg.mask_time_min_masks,
-                              np.random.default_rng(np_seed))
+        rng = np.random.default_rng(np_seed)
+        if valid_frames is None:
+            m = compute_time_mask(batch, frames, cfg.mask_time_prob, cfg.mask_time_length, cfg.mask_time_min_masks, rng)
+        else:
+            m = np.zeros((batch, frames), dtype=bool)
+            for b, n in enumerate(valid_frames):
+                n = int(n)
+                if n >= cfg.mask_time_length:
+                    m[b, :n] = compute_time_mask(1, n, cfg.mask_time_prob, cfg.mask_time_length,
+                                                 cfg.mask_time_min_masks, rng)[0]
         time_mask = torch.from_numpy(m.reshape(-1).astype(np.uint8)).to(device)
     return RegularizerDraw(seed=seed, layer_skip=skip, time_mask=time_mask, cfg=cfg)

@@ -303,6 +303,41 @@ class AudioPromptStep:
         return out
 
     @torch.no_grad()
+    def prefill_prompts(self, waves: torch.Tensor, extra_text_ids=None, plan=None):
+        """Batched form of the first LLM forward of `generate_audio_response` (REF/inference.py:95-135 -> :55-74):
+        encoder -> prompt = prefix | [additional text] | audio embeddings | suffix[1:] for every utterance, all
+        prompts packed into ONE prefill, logits of the last row of each (what greedy decoding consumes first).
+        waves: CUDA fp32 (B, T0); extra_text_ids: optional list of B id tensors (BOS already stripped,
+        REF/inference.py:116-118). Returns (last-row logits bf16 [B, V], plan) -- pass `plan` back to skip the host-side
+        index building when the prompt geometry repeats."""
+        if not waves.is_cuda:
+            raise RuntimeError("AudioPromptStep needs CUDA inputs; there is no CPU path")
+        dev = waves.device
+        audio = self.audio_encoder.forward_fp32(waves)
+        B, A, Cdim = audio.shape
+        if plan is None:
+            import numpy as np
+            pre = np.asarray(self.prefix, dtype=np.int32)
+            suf = np.asarray(self.suffix, dtype=np.int32)[1:]
+            seqs = []
+            for i in range(B):
+                extra = (np.asarray(extra_text_ids[i].detach().cpu() if torch.is_tensor(extra_text_ids[i])
+                                    else extra_text_ids[i], dtype=np.int32).reshape(-1)
+                         if extra_text_ids is not None else np.zeros(0, dtype=np.int32))
+                seqs.append(np.concatenate([pre, extra, -(i * A + np.arange(A, dtype=np.int32)) - 1, suf]))
+            lens = np.asarray([len(q) for q in seqs], dtype=np.int64)
+            cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+            pos = (np.arange(int(cu[-1]), dtype=np.int64) - np.repeat(cu[:-1].astype(np.int64), lens)).astype(np.int32)
+            host = torch.from_numpy(np.concatenate([np.concatenate(seqs), cu, pos, cu[1:] - 1]).astype(np.int32)).pin_memory()
+            d = host.to(dev, non_blocking=True)
+            n = int(cu[-1])
+            plan = dict(row_src=d[:n], cu=d[n:n + B + 1], pos=d[n + B + 1:2 * n + B + 1], last=d[2 * n + B + 1:],
+                        max_len=int(lens.max()), rows=n)
+        h = ops.embed_splice(self.llm.model.embed_tokens.weight, audio.view(B * A, Cdim), plan["row_src"])
+        logits, _, _ = self.llm.prefill_packed(h, plan["cu"], plan["max_len"], plan["pos"], plan["last"])
+        return logits, plan
+
+    @torch.no_grad()
     def validation_losses(self, waves: torch.Tensor, text_ids, resp_ids,
                           num_audio_embeds: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """Per-utterance next-token losses of the audio-prompt AND the text-prompt sequence (REF/trainer.py:438-451:

@@ -172,7 +172,8 @@ class Trainer():
 
     # ------------------------------------------------------------------------------------------ checkpoints
     def load_checkpoint(self, checkpoint_path):
-        checkpoint = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+        # tensors, numbers, dicts and lists only: a checkpoint is data, never code (torch.load's pickle is restricted)
+        checkpoint = torch.load(checkpoint_path, map_location="cpu", weights_only=True)
         self.core.load_checkpoint(checkpoint)
         self.start_epoch = checkpoint["epoch"]
         self.step = checkpoint["step"]
@@ -306,11 +307,21 @@ class Trainer():
             self.validate(epoch)
 
     def validate(self, epoch):
-        """REF/trainer.py:400-528 through EncoderTrainer.validate."""
+        """REF/trainer.py:400-528 through EncoderTrainer.validate. The reference is single-process; under
+        torch.distributed rank 0 alone validates, logs and writes `epoch_{e}_step_{s}.pt` (every rank holds identical
+        parameters after the all-reduced step), the others wait at the barrier -- no duplicate log entries, no
+        concurrent torch.save to one path."""
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if distributed and dist.get_rank() != 0:
+            dist.barrier()
+            return None
+
         def batches():
             for (_, padded, lens, _, t_ids, r_ids, _) in self.val_dataloader:
-                for waves, t, r, keep in self._micro_batches(padded, lens, t_ids, r_ids):
-                    yield self._encoder_input(waves), t, r, keep
+                for waves, t, r, _keep in self._micro_batches(padded, lens, t_ids, r_ids):
+                    # validation feeds the UN-cropped embeddings (REF/trainer.py:418-447 has no un-padding step, unlike
+                    # the training loop's :280-291), so Whisper perplexities are comparable with the reference's
+                    yield self._encoder_input(waves), t, r, None
 
         texts, audios = [], []
         for i, item in enumerate(self.val_dataloader):
@@ -326,6 +337,8 @@ class Trainer():
                                              audio_responses=[str(r) for r in res["audio_responses"]],
                                              text_responses=[str(r) for r in res["text_responses"]], step=self.step)
         print(f"Saved checkpoint for epoch {epoch} to {save_path}.\n")
+        if distributed:
+            dist.barrier()
         return res
 
     def generate_llm_response(self, inputs_embeds, len_inputs=60):

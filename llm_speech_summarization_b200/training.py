@@ -322,6 +322,7 @@ class EncoderTrainer:
         # masked_spec_embed is only read by SpecAugment: without it the parameter never gets a gradient
         unused = [] if spec_augment else [p for n, p in audio_encoder.named_parameters()
                                           if n.endswith("masked_spec_embed")]
+        lr, betas = float(lr), (float(betas[0]), float(betas[1]))  # yaml scalars may arrive as strings ('5e-5')
         self.optimizer = FlatAdamW(audio_encoder.parameters(), lr=lr, betas=betas, weight_decay=weight_decay,
                                    frozen_params=frozen, exclude=unused,
                                    order=getattr(audio_encoder, "flat_param_order", lambda: None)())
@@ -398,6 +399,9 @@ class EncoderTrainer:
                 self.optimizer.finish_all_reduce()
             else:
                 self.optimizer.all_reduce_grads()
+            if getattr(self, "capture_grad", False):  # measurement hook (bench.py check.grad_parity, tests)
+                self.last_flat_grad = self.optimizer.grad.clone()
+                self.last_flat_grad_scale = self.scaler.scale_tensor.clone()
             self.optimizer.step()
             self.audio_encoder.mark_weights_changed()
             self.lr_scheduler.step()

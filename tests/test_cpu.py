@@ -658,3 +658,33 @@ def test_encoder_is_never_left_at_zero_weights(monkeypatch):
     wenc = AudioEncoder(wcfg, torch.device("cpu"))
     pos = wenc.state_dict()["encoder.embed_positions.weight"]
     assert float(pos[0, : pos.shape[1] // 2].abs().max()) == 0.0 and float(pos[0, pos.shape[1] // 2:].min()) == 1.0
+
+
+def test_allreduce_buckets_tile_the_flat_gradient():
+    """The training step exchanges gradients in one bucket per transformer layer (+ one for everything else): in
+    AudioEncoder.flat_param_order every layer's parameters form ONE contiguous range of the flat optimizer buffer, the
+    ranges are disjoint, q|k|v stay adjacent (the fused-QKV gradient aliases them), and layers + rest cover every
+    element exactly once."""
+    from oracle import configs
+    from llm_speech_summarization_b200.model.audio_encoder import AudioEncoder
+    for cfg in (ns_config(configs.TINY_ENCODER, configs.TINY_LLAMA), ns_config_whisper(configs.TINY_WHISPER)):
+        enc = AudioEncoder(cfg, torch.device("cpu"))
+        order = [p for p in enc.flat_param_order() if p.requires_grad]
+        assert len({id(p) for p in order}) == len(order) == sum(1 for p in enc.parameters() if p.requires_grad)
+        off, at = 0, {}
+        for p in order:
+            at[id(p)] = (off, off + p.numel())
+            off += p.numel()
+        covered = []
+        for group in enc.layer_param_groups():
+            spans = sorted(at[id(p)] for p in group)
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:])), "layer parameters are not contiguous"
+            covered.append((spans[0][0], spans[-1][1]))
+        covered.sort()
+        assert all(a[1] <= b[0] for a, b in zip(covered, covered[1:])), "layer buckets overlap"
+        assert covered[0][0] == 0  # the transformer layers come first, everything else follows as the last bucket
+        layers = enc.transformer_layers()
+        a = layers[0].attention if enc.encoder_base == "hubert" else layers[0].self_attn
+        q, k, v = (at[id(m.weight)] for m in (a.q_proj, a.k_proj, a.v_proj))
+        assert q[1] == k[0] and k[1] == v[0]
+        assert sum(b - a_ for a_, b in covered) + (off - covered[-1][1]) == off

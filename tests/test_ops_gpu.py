@@ -326,7 +326,7 @@ def test_kd_ce_loss_bwd_f16_with_loss_scale(cuda):
     # why the scale exists: the bulk of this gradient (|g| ~ 1e-7) lands on fp16's subnormal grid (step 6e-8) unscaled
     small = s32.grad.abs() < 1e-6
     unscaled = ops.kd_ce_loss_bwd(s, t, labels, res, out_dtype=torch.float16)
-    assert rel_l2(unscaled.float()[small], s32.grad[small]) > 5e-2
+    assert rel_l2(unscaled.float()[small], s32.grad[small]) > 2e-2
     assert rel_l2((ds.float() / 65536.0)[small], s32.grad[small]) < 1e-3
 
 
