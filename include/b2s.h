@@ -43,6 +43,55 @@ const char* b2s_last_error(void);
 int b2s_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long b2s_launch_count(void);
+/* ---------------------------------------------------------------------------------------------
+ * Instance state ("persistent state is owned by an opaque handle created / destroyed explicitly").
+ * A b2s_handle owns everything that is not an argument of an entry point: the A/B options below, the SM budget, the
+ * launch counter, the GEMM timing window and the NCCL communicator of the gradient exchange. Entry points act on the
+ * calling host thread's CURRENT handle (b2s_make_current, like a CUDA context); a process-wide default handle exists, so
+ * callers that never create one keep working. Calls are reentrant across handles; one handle is not thread-safe. */
+typedef struct b2s_handle b2s_handle;
+int b2s_create(b2s_handle** out);
+int b2s_destroy(b2s_handle* h);        /* also tears down its communicator */
+int b2s_make_current(b2s_handle* h);   /* NULL = back to the process default */
+enum {
+  B2S_OPT_PDL = 0,                /* programmatic dependent launch between kernels (default 1; env seed B2S_PDL) */
+  B2S_OPT_RESID_RED = 1,          /* in-place residual epilogues as L2 reductions (default 1; B2S_RESID_RED) */
+  B2S_OPT_TMA_EPILOGUE = 2,       /* forward GEMM outputs through TMA stores / reductions (default 1; B2S_TMA_EPI) */
+  B2S_OPT_ATTN_KEYS_PER_STEP = 3, /* attention forward tile override, 0 = auto (B2S_ATTN_CFG="keys,stages") */
+  B2S_OPT_ATTN_KV_STAGES = 4,
+  B2S_OPT_SM_BUDGET = 5           /* = b2s_set_sm_budget */
+};
+int b2s_set_option(int32_t option, int32_t value); /* on the current handle; measurement A/B only */
+int b2s_get_option(int32_t option, int32_t* value);
+
+/* Gradient exchange of the training step (REF/trainer.py:372-384 accumulation semantics, summed
+ * over ranks): the current handle owns an NCCL communicator and a communication stream.
+ *   b2s_comm_unique_id  rank 0 mints the id (host buffer of B2S_COMM_ID_BYTES), the caller distributes it
+ *                       (torch.distributed broadcast, a file, MPI ...);
+ *   b2s_comm_init       every rank joins (collective: blocks until all `world` ranks have called it);
+ *   b2s_allreduce_grads SUM all-reduce, in place, of the element ranges [starts[i], ends[i]) of the flat fp32 gradient
+ *                       on the communication stream; bucket i is held back until ready_events[i] (a cudaEvent_t the
+ *                       compute stream recorded, e.g. b2s_hubert_backward's layer_done_events; NULL = ready) has fired.
+ *                       span_begin_event / span_end_event (optional timing events) are recorded on the communication
+ *                       stream before the first / after the last bucket;
+ *   b2s_allreduce_join  `compute_stream` waits for every bucket enqueued so far.
+ * NCCL is resolved with dlopen at the first call: the library itself loads without it. */
+#define B2S_COMM_ID_BYTES 128
+int b2s_comm_unique_id(uint8_t* id /* host, B2S_COMM_ID_BYTES */);
+int b2s_comm_init(const uint8_t* id, int32_t rank, int32_t world);
+int b2s_comm_world(int32_t* rank, int32_t* world);
+int b2s_comm_destroy(void);
+int b2s_allreduce_grads(float* flat, const int64_t* starts /* host */, const int64_t* ends /* host */,
+                        void* const* ready_events /* host array of cudaEvent_t, may be NULL */, int32_t n_buckets,
+                        void* span_begin_event, void* span_end_event);
+int b2s_allreduce_join(void* compute_stream);
+
+/* SM budget of the current handle: the persistent kernels (GEMM, attention
+ * forward) size their grids for min(device SMs, budget); 0 = all. Their tile assignment is static, so a grid that counts
+ * on SMs a concurrent NCCL kernel occupies would serialise behind it: the training step lowers the budget by the
+ * communication kernel's CTA count while gradient buckets are being all-reduced under the encoder backward. */
+void b2s_set_sm_budget(int32_t sms);
+int32_t b2s_get_sm_budget(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense contraction: out = epi(A . W^T).  Replaces every nn.Linear / Conv1d(C_in >= 512) on the path

@@ -124,6 +124,20 @@ PROTOTYPES = {
     "b2s_last_error": (C.c_char_p, []),
     "b2s_version": (c_int, []),
     "b2s_launch_count": (C.c_longlong, []),
+    "b2s_set_sm_budget": (None, [c_int]),
+    "b2s_get_sm_budget": (c_int, []),
+    "b2s_create": (c_int, [C.POINTER(c_void_p)]),
+    "b2s_destroy": (c_int, [c_void_p]),
+    "b2s_make_current": (c_int, [c_void_p]),
+    "b2s_set_option": (c_int, [c_int, c_int]),
+    "b2s_get_option": (c_int, [c_int, C.POINTER(c_int)]),
+    "b2s_comm_unique_id": (c_int, [c_void_p]),
+    "b2s_comm_init": (c_int, [c_void_p, c_int, c_int]),
+    "b2s_comm_world": (c_int, [C.POINTER(c_int), C.POINTER(c_int)]),
+    "b2s_comm_destroy": (c_int, []),
+    "b2s_allreduce_grads": (c_int, [P_f32, C.POINTER(c_int64), C.POINTER(c_int64), C.POINTER(c_void_p), c_int,
+                                    c_void_p, c_void_p]),
+    "b2s_allreduce_join": (c_int, [c_void_p]),
     "b2s_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "b2s_gemm_timing_enable": (None, [c_int]),
     "b2s_gemm_timing_read": (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
@@ -212,6 +226,9 @@ PROTOTYPES = {
     "b2s_nonfinite_check": (c_int, [P_f32, c_int64, c_void_p, c_void_p]),
     "b2s_grad_scaler_update": (c_int, [c_void_p, c_float, c_float, c_int, c_void_p]),
 }
+
+OPT_PDL, OPT_RESID_RED, OPT_TMA_EPILOGUE, OPT_ATTN_KEYS_PER_STEP, OPT_ATTN_KV_STAGES, OPT_SM_BUDGET = range(6)
+COMM_ID_BYTES = 128
 
 _lib = None
 

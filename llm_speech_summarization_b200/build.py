@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb2s.so")
 
-SOURCES = ["api.cu", "gemm_sm100.cu", "loss.cu", "norm.cu", "misc.cu", "attention_tc.cu", "attention_bwd_tc.cu", "backward.cu", "train.cu", "backward_enc.cu", "train_enc.cu", "regularize.cu", "decode.cu", "logmel.cu", "models.cu"]
+SOURCES = ["api.cu", "gemm_sm100.cu", "loss.cu", "norm.cu", "misc.cu", "attention_tc.cu", "attention_bwd_tc.cu", "backward.cu", "train.cu", "backward_enc.cu", "train_enc.cu", "regularize.cu", "decode.cu", "logmel.cu", "models.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

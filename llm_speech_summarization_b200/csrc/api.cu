@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" surface declared in include/b2s.h, plus status/error plumbing.
 #include <atomic>
 #include <cstdarg>
+#include <new>
 #include <cstdio>
 #include <cstdlib>
 
@@ -13,8 +14,25 @@ namespace b2s {
 
 namespace {
 thread_local char g_err[1024] = "";
-std::atomic<long long> g_launches{0};
+thread_local Context* g_current = nullptr;
+Context& default_context() {
+  static Context c;
+  return c;
+}
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 }  // namespace
+
+Context::Context() {
+  pdl = env_int("B2S_PDL", 1) != 0;
+  resid_red = env_int("B2S_RESID_RED", 1) != 0;
+  tma_epi = env_int("B2S_TMA_EPI", 1) != 0;
+  if (const char* e = getenv("B2S_ATTN_CFG")) sscanf(e, "%d,%d", &attn_bn, &attn_kvs);
+}
+
+Context& ctx() { return g_current != nullptr ? *g_current : default_context(); }
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -28,14 +46,16 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return B2S_ERR_CUDA;
 }
 
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+void count_launch() { ctx().launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return ctx().launches.load(std::memory_order_relaxed); }
 
-bool pdl_enabled() {
-  static const bool on = !(getenv("B2S_PDL") && atoi(getenv("B2S_PDL")) == 0);
-  return on;
-}
+bool pdl_enabled() { return ctx().pdl != 0; }
 
+void set_sm_budget(int sms) { ctx().sm_budget = sms > 0 ? sms : 0; }
+int sm_budget() { return ctx().sm_budget; }
+
+// SMs the persistent kernels size their grids for: the device's count, or the current context's budget when one is set
+// (a persistent grid with static tile assignment must not count on SMs a concurrent communication kernel occupies)
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -45,8 +65,11 @@ int num_sms() {
       sms = 148;
     }
   }
-  return sms;
+  const int b = ctx().sm_budget;
+  return (b > 0 && b < sms) ? b : sms;
 }
+
+int comm_destroy(Context& c);  // comm.cu
 
 // models.cu
 int hubert_num_frames(const b2s_hubert_weights* w, int samples, int* frames, int* pooled);
@@ -113,6 +136,73 @@ extern "C" {
 const char* b2s_last_error(void) { return g_err; }
 int b2s_version(void) { return 1; }
 long long b2s_launch_count(void) { return launch_count(); }
+void b2s_set_sm_budget(int32_t sms) { set_sm_budget(sms); }
+int32_t b2s_get_sm_budget(void) { return sm_budget(); }
+
+struct b2s_handle {
+  Context c;
+};
+int b2s_create(b2s_handle** out) {
+  if (out == nullptr) {
+    set_last_error("b2s_create: null output pointer");
+    return B2S_ERR_INVALID;
+  }
+  *out = new (std::nothrow) b2s_handle();
+  if (*out == nullptr) {
+    set_last_error("b2s_create: out of memory");
+    return B2S_ERR_INVALID;
+  }
+  return B2S_OK;
+}
+int b2s_destroy(b2s_handle* h) {
+  if (h == nullptr) return B2S_OK;
+  if (g_current == &h->c) g_current = nullptr;
+  const int rc = comm_destroy(h->c);
+  for (auto& e : h->c.events) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  delete h;
+  return rc;
+}
+int b2s_make_current(b2s_handle* h) {
+  g_current = h != nullptr ? &h->c : nullptr;
+  return B2S_OK;
+}
+int b2s_set_option(int32_t option, int32_t value) {
+  Context& c = ctx();
+  switch (option) {
+    case B2S_OPT_PDL: c.pdl = value != 0; break;
+    case B2S_OPT_RESID_RED: c.resid_red = value != 0; break;
+    case B2S_OPT_TMA_EPILOGUE: c.tma_epi = value != 0; break;
+    case B2S_OPT_ATTN_KEYS_PER_STEP: c.attn_bn = value; break;
+    case B2S_OPT_ATTN_KV_STAGES: c.attn_kvs = value; break;
+    case B2S_OPT_SM_BUDGET: c.sm_budget = value > 0 ? value : 0; break;
+    default:
+      set_last_error("b2s_set_option: unknown option %d", option);
+      return B2S_ERR_INVALID;
+  }
+  return B2S_OK;
+}
+int b2s_get_option(int32_t option, int32_t* value) {
+  Context& c = ctx();
+  if (value == nullptr) {
+    set_last_error("b2s_get_option: null output pointer");
+    return B2S_ERR_INVALID;
+  }
+  switch (option) {
+    case B2S_OPT_PDL: *value = c.pdl; break;
+    case B2S_OPT_RESID_RED: *value = c.resid_red; break;
+    case B2S_OPT_TMA_EPILOGUE: *value = c.tma_epi; break;
+    case B2S_OPT_ATTN_KEYS_PER_STEP: *value = c.attn_bn; break;
+    case B2S_OPT_ATTN_KV_STAGES: *value = c.attn_kvs; break;
+    case B2S_OPT_SM_BUDGET: *value = c.sm_budget; break;
+    default:
+      set_last_error("b2s_get_option: unknown option %d", option);
+      return B2S_ERR_INVALID;
+  }
+  return B2S_OK;
+}
 
 int b2s_gemm_bf16(const b2s_gemm_args* a, void* stream) {
   if (a == nullptr) {

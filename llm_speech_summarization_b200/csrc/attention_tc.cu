@@ -488,13 +488,6 @@ int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, vo
 
 }  // namespace
 
-// experiment hook: B2S_ATTN_CFG="<keys per step>,<K/V stages>" overrides the default tile configuration
-static int g_cfg_bn = 0, g_cfg_kvs = 0;
-static const bool g_cfg_read = [] {
-  if (const char* e = getenv("B2S_ATTN_CFG")) sscanf(e, "%d,%d", &g_cfg_bn, &g_cfg_kvs);
-  return true;
-}();
-
 // Packed variable-length attention forward (ops.cuh). q / k / v / o share one 16-bit format (fmt: B2S_FMT_*).
 int attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
                   const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
@@ -517,7 +510,7 @@ int attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv,
     B2S_REQUIRE(D == 64 && max_seqlen < 65536, "attention_fwd: attention dropout supports head_dim 64, seqlen < 65536");
     B2S_ATTN_GO(64, 64, 1, true, drop);
   }
-  int bn = g_cfg_bn, kvs = g_cfg_kvs;
+  int bn = ctx().attn_bn, kvs = ctx().attn_kvs;  // experiment hook (B2S_OPT_ATTN_*, env seed B2S_ATTN_CFG); 0 = auto
   if (bn == 0) {
     // measured on B200 (profiles/r01_attention_configs.md): the kernel is bound by the per-step latency chain, so the
     // configuration that keeps the most CTAs resident wins at these sequence lengths

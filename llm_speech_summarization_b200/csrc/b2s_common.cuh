@@ -1,8 +1,12 @@
 // b2s_common.cuh -- shared device helpers (bf16 packing, warp/block reductions, vector IO) and the
 // host-side status/error plumbing behind the C ABI in include/b2s.h.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <utility>
+#include <vector>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -34,6 +38,33 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     }                                          \
   } while (0)
 
+// ---- per-instance state (the opaque b2s_handle of include/b2s.h) -------------------------------------------------
+// Everything that is not an argument of an entry point lives here: the A/B toggles, the SM budget of the persistent
+// kernels, the launch counter, the GEMM timing window and the NCCL communicator of the gradient exchange. A host thread
+// works against its CURRENT context (b2s_make_current; a process-wide default exists so callers that never create one
+// keep working). Entry points are reentrant across contexts; one context must not be driven by two threads at once.
+struct TimedShape {
+  int M, N, K, batches, groups, epi, act, mode, bn, cg;
+};
+struct Context {
+  int pdl = 1;          // programmatic dependent launch (B2S_PDL seeds the default)
+  int resid_red = 1;    // in-place residual epilogues as L2 reductions (B2S_RESID_RED)
+  int tma_epi = 1;      // MODE 0 GEMM outputs through TMA stores (B2S_TMA_EPI)
+  int attn_bn = 0, attn_kvs = 0;  // attention forward tile override (B2S_ATTN_CFG="keys per step,K/V stages"; 0 = auto)
+  int sm_budget = 0;    // SMs the persistent kernels size their grids for (0 = all)
+  std::atomic<long long> launches{0};
+  bool timing = false;  // GEMM timing window (bench.py roofline leg)
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+  std::vector<TimedShape> shapes;
+  TimedShape pending{};
+  void* comm = nullptr;  // ncclComm_t of the gradient exchange (comm.cu); owned by the context
+  int comm_rank = 0, comm_world = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t comm_done = nullptr;
+  Context();
+};
+Context& ctx();  // the calling thread's current context
+
 void count_launch();
 long long launch_count();
 #define B2S_LAUNCH_CHECK()              \
@@ -42,7 +73,9 @@ long long launch_count();
     B2S_CUDA_CHECK(cudaGetLastError()); \
   } while (0)
 
-int num_sms();
+int num_sms();  // SMs persistent grids are sized for (the device's, or the calling thread's budget)
+void set_sm_budget(int sms);
+int sm_budget();
 
 // Launch `kern` with the programmatic-stream-serialization attribute (PDL, see pdl_trigger / pdl_wait below): the grid
 // may be scheduled while its predecessor drains and must call pdl_wait() before its first global access.

@@ -148,6 +148,33 @@ __device__ __forceinline__ void tma_load_3d_2sm(const void* desc, uint32_t bar, 
       : "memory");
 }
 
+// ---- TMA stores (shared::cta -> global through a tensor map; bulk async-groups are per THREAD: the thread that issues
+// must also commit and wait). Out-of-bounds parts of the box are simply not written, so edge tiles need no predicates.
+__device__ __forceinline__ void tma_store_3d(const void* desc, uint32_t smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// global[box] += smem[box] (fp32 add performed at the L2, one bulk operation per box)
+__device__ __forceinline__ void tma_reduce_add_3d(const void* desc, uint32_t smem, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still have to READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// wait until at most N of this thread's bulk groups are incomplete (their global writes included)
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -34,17 +34,16 @@ namespace b2s {
 
 namespace {
 
-bool g_timing = false;
-std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
-struct TimedShape {
-  int M, N, K, batches, groups, epi, act, mode, bn, cg;
-};
-std::vector<TimedShape> g_shapes;  // one per entry of g_events
-TimedShape g_pending{};            // filled by gemm_bf16_launch just before launch_cfg records the events
-
 constexpr int kBlockK = 64;           // bf16 elements = 128 bytes = one swizzle atom
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 256;
+// warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare; then the epilogue warps, one per TMEM lane quarter.
+// (Eight epilogue warps -- two per quarter, each taking half of the tile's columns -- are supported by the code below and
+// were measured on B200 in round 2 with the TMA-store epilogue: every K = 1024 shape got slower (FFN1 843 -> 818, QKV
+// 980 -> 873 TFLOP/s; 168 registers per thread instead of 255), so four it stays.)
+template <int MODE>
+constexpr int kEpiWarps = 4;
+template <int MODE>
+constexpr int kThreads = 128 + 32 * kEpiWarps<MODE>;
 constexpr int kATileBytes = 128 * kBlockK * 2;  // 16 KiB per CTA per stage
 constexpr int kSmemBudget = 200 * 1024;
 
@@ -56,8 +55,11 @@ struct Cfg {
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;  // power of two for BN in {64,128,256}
   static constexpr int kBarBytes = 256;                  // (2*kStages + 4) mbarriers + the TMEM base slot
-  static constexpr int kStagingBytes = 4 * 4096;         // one 32x128 B transpose tile per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kStagingBytes + 1024;  // +1024 align slack
+  // 32 KiB of epilogue staging, 1024-byte aligned (128B-swizzled TMA store sources): one 32-row x 128-byte tile for
+  // each of MODE 0's eight epilogue warps (the bulk store of chunk c drains while chunk c+1 is read from TMEM and
+  // activated), 8 KiB per warp for the four-warp modes
+  static constexpr int kStagingBytes = 8 * 4096;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // +1024 align slack
   static_assert((2 * kStages + 4) * 8 + 16 <= kBarBytes, "barrier region too small");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -91,6 +93,7 @@ struct KParams {
   uint32_t drop_k1, drop_k2, drop_thresh;  // fused dropout (rng.cuh); thresh 0 = off
   float drop_inv_keep;
   int resid_red;  // in-place residual adds go through red.global.add (B2S_RESID_RED=0 keeps load + add + store, A/B)
+  int tma_out;    // MODE 0 plain epilogues: output leaves through TMA stores / reductions (tmap_o is valid)
   uint32_t idesc_fmt;  // a_format / b_format bits of the instruction descriptor (bf16 = 1, fp16 = 0; may differ)
   int out_f16;         // 16-bit outputs (out for the *_BF16-class epilogues, out2) are written as fp16 instead of bf16
 };
@@ -286,9 +289,9 @@ __device__ __forceinline__ void emit_h16(uint32_t stg, const float (&v)[32], int
 // MODE 2: MODE 1 with an MN-major B operand (dgrad).   MODE 3: both operands MN-major, reduction over batches (wgrad).
 // Operand major-ness is a compile-time property so the single-thread producer / MMA-issue loops stay branch-free.
 template <int BN, int CG, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads<MODE>, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                         const KParams p) {
+                         const __grid_constant__ CUtensorMap tmap_o, const KParams p) {
   using C = Cfg<BN, CG>;
   constexpr int kStages = C::kStages;
   constexpr bool EXT = MODE >= 1;
@@ -297,13 +300,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * C::kStageBytes;
+  const uint32_t stage_base = smem_base + kStages * C::kStageBytes;  // epilogue staging tiles (1024-byte aligned)
+  const uint32_t bar_base = stage_base + C::kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-  const uint32_t stage_base = bar_base + C::kBarBytes;  // epilogue transpose tiles (16-byte aligned)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -326,7 +329,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);        // one tcgen05.commit
-      ptx::mbar_init(tempty_bar(s), 4 * CG);  // one arrive per epilogue warp (both CTAs -> leader)
+      ptx::mbar_init(tempty_bar(s), kEpiWarps<MODE> * CG);  // one arrive per epilogue warp (both CTAs -> leader)
     }
     ptx::fence_mbar_init();
   }
@@ -459,8 +462,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // 32x32 chunk is transposed through a private, XOR-swizzled 4 KiB shared-memory tile and leaves the SM as
     // fully coalesced 128-byte row segments (and the fp32 residual is read the same way).
     const int quarter = warp & 3;
+    constexpr int kHalves = kEpiWarps<MODE> / 4;        // warps sharing one TMEM lane quarter split the tile's columns
+    const int half = (warp - 4) >> 2;                   // 0 .. kHalves-1
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t stg = stage_base + static_cast<uint32_t>(quarter) * 4096u;
+    const uint32_t stg = stage_base + static_cast<uint32_t>(warp - 4) * (kHalves == 2 ? 4096u : 8192u);
+    uint32_t nst = 0;  // staging tiles this warp has handed to the TMA store engine (buffer = nst & 1)
+    if (!EXT && lane == 0) ptx::prefetch_tmap(&tmap_o);
     int it = 0;
     for (int t = cluster_id; t < p.total_tiles; t += num_clusters, ++it) {
       const TileCoord tc = decode_tile<EXT>(p, t);
@@ -481,6 +488,73 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const uint32_t taddr = tmem_base + lane_base + as * BN;
 
       if (p.epi == EPI_BF16 || p.epi == EPI_F32 || p.epi == EPI_RESID_F32 || (EXT && p.epi == EPI_ACCUM_F32)) {
+        if constexpr (!EXT) {
+        // (MODE 0: the host routes every plain epilogue it cannot express as a TMA store to the MODE 1 kernel)
+        // ---- MODE 0 plain epilogues (bf16 / fp16 / fp32 output, fp32 in-place residual): TMEM -> registers ->
+        // bias / activation -> 128B-swizzled staging tile -> ONE bulk tensor store (or fp32 add-reduction at the L2 for
+        // h += proj(...)) per 32-row x 128-byte tile. No per-thread global stores, no read-back of the staging tile, the
+        // write drains asynchronously while the next chunk is computed, and TMA clips the M / N edges.
+        const bool h16 = p.epi == EPI_BF16;
+        const bool red = p.epi == EPI_RESID_F32;
+        const int cw = h16 ? 64 : 32;  // output columns per staging tile
+        const int gcol0 = tc.g * p.N + ncol0;
+        constexpr int kChunksPerWarp = (BN / 32) / kHalves;  // 32-column TMEM chunks this warp drains
+#pragma unroll 1
+        for (int c = half * kChunksPerWarp; c < (half + 1) * kChunksPerWarp; c += (h16 ? 2 : 1)) {
+          const int col = ncol0 + c * 32;
+          if (col >= p.N) break;
+          uint32_t raw[32], raw2[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, raw);
+          if (h16) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, raw2);
+          ptx::tmem_ld_wait();
+          float v[32], v2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          add_bias_act(v, (bias && col < p.N) ? bias + col : nullptr, p.act);
+          if (h16) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v2[i] = __uint_as_float(raw2[i]);
+            add_bias_act(v2, (bias && col + 32 < p.N) ? bias + col + 32 : nullptr, p.act);
+          }
+          // four warps: two staging tiles per warp, the store of chunk c drains while chunk c+1 is staged
+          const uint32_t buf = stg + (kHalves == 1 ? (nst & 1u) * 4096u : 0u);
+          if (lane == 0) ptx::bulk_wait_read<(kHalves == 1 ? 1 : 0)>();  // the store that last used this tile has read it
+          __syncwarp();
+          if (h16) {
+            // row = lane: 64 values = 128 bytes = eight 16-byte chunks at chunk position q ^ (lane & 7)
+            if (p.out_f16) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float* s = q < 4 ? &v[8 * q] : &v2[8 * (q - 4)];
+                const uint32_t addr = buf + lane * 128 + ((q ^ (lane & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_f16(s[0], s[1])),
+                             "r"(pack_f16(s[2], s[3])), "r"(pack_f16(s[4], s[5])), "r"(pack_f16(s[6], s[7]))
+                             : "memory");
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float* s = q < 4 ? &v[8 * q] : &v2[8 * (q - 4)];
+                const uint32_t addr = buf + lane * 128 + ((q ^ (lane & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16(s[0], s[1])),
+                             "r"(pack_bf16(s[2], s[3])), "r"(pack_bf16(s[4], s[5])), "r"(pack_bf16(s[6], s[7]))
+                             : "memory");
+              }
+            }
+          } else {
+            stage_write(buf, v, lane);
+          }
+          ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA (async proxy) read
+          __syncwarp();
+          if (lane == 0 && rows_valid > 0) {
+            if (red) ptx::tma_reduce_add_3d(&tmap_o, buf, gcol0 + c * 32, m0w, tc.b);
+            else ptx::tma_store_3d(&tmap_o, buf, gcol0 + c * 32, m0w, tc.b);
+            ptx::bulk_commit();
+          }
+          ++nst;
+          (void)cw;
+        }
+        } else {
         // In-place residual (out aliases resid: the inference forward's h += proj(...)): the add is done by the L2 as
         // an fp32 reduction (red.global.add.v4.f32, one per element, so still deterministic) and the residual never
         // travels to the SM -- the load -> add -> store chain with one 4 KiB chunk per warp in flight was what bound
@@ -537,13 +611,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             emit_f32(stg, v, lane, reinterpret_cast<float*>(p.out) + off0, nullptr, p.ldo, rows_valid, valid);
           }
         }
+        }
       } else {
         // paired-chunk epilogues over 128-column blocks: chunk c pairs with chunk c+2
         // (SwiGLU: 64 gate | 64 up ; RoPE: head_dim 128 = first half | second half)
         int pos = 0;
         if (p.epi == EPI_ROPE && row_ok) pos = __ldg(p.positions + orow0 + lane);
+        constexpr int kBlocks = BN / 128;
+        constexpr int kBlkPerWarp = (kBlocks >= kHalves) ? kBlocks / kHalves : 1;
+        const int blk_lo = (kBlocks >= kHalves) ? half * kBlkPerWarp : (half == 0 ? 0 : kBlocks);
 #pragma unroll 1
-        for (int blk = 0; blk < BN / 128; ++blk) {
+        for (int blk = blk_lo; blk < min(kBlocks, blk_lo + kBlkPerWarp); ++blk) {
           const int bcol = ncol0 + blk * 128;
           if (bcol >= p.N) break;
 #pragma unroll 1
@@ -606,6 +684,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
       }
     }
+    if (!EXT && lane == 0) ptx::bulk_wait<0>();  // every bulk store of this warp has landed before the CTA retires
   }
 
   ptx::tc_fence_before();
@@ -640,14 +719,14 @@ EncodeFn get_encode_fn() {
 }
 
 int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box) {
+               const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   EncodeFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return B2S_ERR_CUDA;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+  CUresult r = fn(map, dtype, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -661,7 +740,8 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
 }
 
 template <int BN, int CG, int MODE>
-int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const KParams& p, cudaStream_t stream) {
+int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const KParams& p,
+               cudaStream_t stream) {
   using C = Cfg<BN, CG>;
   auto kern = gemm_bf16_tcgen05_kernel<BN, CG, MODE>;
   static bool attr_set = false;
@@ -674,7 +754,7 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const KParams& p, c
   if (clusters > p.total_tiles) clusters = p.total_tiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CG);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kThreads<MODE>);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -688,16 +768,17 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const KParams& p, c
   cfg.numAttrs = pdl_enabled() ? 2 : 1;  // B2S_PDL=0: plain stream serialisation (A/B runs)
   count_launch();
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (g_timing) {
+  Context& cx = ctx();
+  if (cx.timing) {
     B2S_CUDA_CHECK(cudaEventCreate(&ev0));
     B2S_CUDA_CHECK(cudaEventCreate(&ev1));
     B2S_CUDA_CHECK(cudaEventRecord(ev0, stream));
   }
-  B2S_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, p));
-  if (g_timing) {
+  B2S_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, to, p));
+  if (cx.timing) {
     B2S_CUDA_CHECK(cudaEventRecord(ev1, stream));
-    g_events.emplace_back(ev0, ev1);
-    g_shapes.push_back(g_pending);
+    cx.events.emplace_back(ev0, ev1);
+    cx.shapes.push_back(cx.pending);
   }
   return B2S_OK;
 }
@@ -716,39 +797,42 @@ int encode_map_2d_bf16(CUtensorMap* map, const void* base, unsigned long long co
 // Optional per-launch timing of this kernel (bench.py's roofline leg): CUDA events on the launching stream
 // around every GEMM launch while enabled.
 void gemm_timing_enable(int on) {
-  for (auto& e : g_events) {
+  Context& cx = ctx();
+  for (auto& e : cx.events) {
     cudaEventDestroy(e.first);
     cudaEventDestroy(e.second);
   }
-  g_events.clear();
-  g_shapes.clear();
-  g_timing = on != 0;
+  cx.events.clear();
+  cx.shapes.clear();
+  cx.timing = on != 0;
 }
 
 // per-launch record: shape[10] = M, N, K (whole reduction), batches, groups, epilogue, activation, mode, block_n, cta_group
 int gemm_timing_get(long long index, double* ms, int* shape) {
-  B2S_REQUIRE(index >= 0 && index < static_cast<long long>(g_events.size()) && ms && shape, "gemm_timing_get: bad index");
-  auto& e = g_events[static_cast<size_t>(index)];
+  Context& cx = ctx();
+  B2S_REQUIRE(index >= 0 && index < static_cast<long long>(cx.events.size()) && ms && shape, "gemm_timing_get: bad index");
+  auto& e = cx.events[static_cast<size_t>(index)];
   B2S_CUDA_CHECK(cudaEventSynchronize(e.second));
   float t = 0.f;
   B2S_CUDA_CHECK(cudaEventElapsedTime(&t, e.first, e.second));
   *ms = t;
-  const TimedShape& d = g_shapes[static_cast<size_t>(index)];
+  const TimedShape& d = cx.shapes[static_cast<size_t>(index)];
   const int v[10] = {d.M, d.N, d.K, d.batches, d.groups, d.epi, d.act, d.mode, d.bn, d.cg};
   for (int i = 0; i < 10; ++i) shape[i] = v[i];
   return B2S_OK;
 }
 
 int gemm_timing_read(double* total_ms, long long* launches) {
+  Context& cx = ctx();
   double ms = 0.0;
-  for (auto& e : g_events) {
+  for (auto& e : cx.events) {
     B2S_CUDA_CHECK(cudaEventSynchronize(e.second));
     float t = 0.f;
     B2S_CUDA_CHECK(cudaEventElapsedTime(&t, e.first, e.second));
     ms += t;
   }
   if (total_ms) *total_ms = ms;
-  if (launches) *launches = static_cast<long long>(g_events.size());
+  if (launches) *launches = static_cast<long long>(cx.events.size());
   return B2S_OK;
 }
 
@@ -865,7 +949,7 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   p.rope_cs = a.rope_cs;
   p.positions = a.positions;
   p.rope_cols = a.rope_cols;
-  static const int resid_red = getenv("B2S_RESID_RED") ? atoi(getenv("B2S_RESID_RED")) : 1;
+  const int resid_red = ctx().resid_red;
   p.resid_red = resid_red;
   p.idesc_fmt = ptx::idesc_formats(a.a_fmt != 0, a.w_fmt != 0);
   p.out_f16 = a.out_fmt != 0 ? 1 : 0;
@@ -911,18 +995,43 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
     if (rc != B2S_OK) return rc;
   }
 
-  const bool ext = mn || a.epi == EPI_ACCUM_F32 || p.k_splits > 1 || a.out2 != nullptr || a.out_group_rows != 0 ||
-                   (a.out_group_cols > 0 && a.out_group_cols != a.N) || a.drop_thresh != 0u;
+  bool ext = mn || a.epi == EPI_ACCUM_F32 || p.k_splits > 1 || a.out2 != nullptr || a.out_group_rows != 0 ||
+             (a.out_group_cols > 0 && a.out_group_cols != a.N) || a.drop_thresh != 0u;
+  // MODE 0 writes its plain outputs through TMA (stores, or fp32 add-reductions for the in-place residual); whatever
+  // that cannot express -- a residual read from another tensor, a broadcast residual -- takes the MODE 1 kernel, which
+  // keeps the per-thread epilogue. B2S_OPT_TMA_EPILOGUE = 0 (env seed B2S_TMA_EPI) forces the per-thread path everywhere (A/B).
+  const int tma_epi = ctx().tma_epi;
+  CUtensorMap to = ta;
+  p.tma_out = 0;
+  if (!ext && (a.epi == EPI_BF16 || a.epi == EPI_F32 || a.epi == EPI_RESID_F32)) {
+    const bool inplace = a.epi == EPI_RESID_F32 && static_cast<const void*>(a.resid) == a.out && !a.resid_bcast &&
+                         resid_red != 0;
+    const bool ok = tma_epi != 0 && (a.epi != EPI_RESID_F32 || inplace);
+    if (ok) {
+      const bool h16 = a.epi == EPI_BF16;
+      const cuuint64_t elt = h16 ? 2 : 4;
+      const cuuint64_t cols = a.groups > 1 ? static_cast<cuuint64_t>(a.groups) * a.N : static_cast<cuuint64_t>(a.N);
+      const cuuint64_t row_bytes = static_cast<cuuint64_t>(a.ldo) * elt;
+      const cuuint64_t batch_rows = a.out_batch_rows > 0 ? a.out_batch_rows : a.M;
+      cuuint64_t dims[3] = {cols, static_cast<cuuint64_t>(a.M), static_cast<cuuint64_t>(a.batches)};
+      cuuint64_t strides[2] = {row_bytes, row_bytes * batch_rows};
+      cuuint32_t box[3] = {h16 ? 64u : 32u, 32u, 1u};
+      const CUtensorMapDataType dt = h16 ? (a.out_fmt != 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)
+                                         : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+      if (row_bytes % 16 == 0 && encode_map(&to, a.out, 3, dims, strides, box, dt) == B2S_OK) p.tma_out = 1;
+    }
+    if (!p.tma_out) ext = true;
+  }
   const int mode = a.a_mn ? 3 : (a.b_mn ? 2 : (ext ? 1 : 0));
-  if (g_timing)
-    g_pending = TimedShape{a.M, a.N, a.k_per_tap * a.taps * k_batches, a.batches, a.groups, a.epi, a.act, mode, bn, cg};
+  if (ctx().timing)
+    ctx().pending = TimedShape{a.M, a.N, a.k_per_tap * a.taps * k_batches, a.batches, a.groups, a.epi, a.act, mode, bn, cg};
 #define B2S_GEMM_CASE(BN_, CG_)                                          \
   if (bn == BN_ && cg == CG_) {                                          \
     switch (mode) {                                                      \
-      case 0: return launch_cfg<BN_, CG_, 0>(ta, tw, p, stream);         \
-      case 1: return launch_cfg<BN_, CG_, 1>(ta, tw, p, stream);         \
-      case 2: return launch_cfg<BN_, CG_, 2>(ta, tw, p, stream);         \
-      default: return launch_cfg<BN_, CG_, 3>(ta, tw, p, stream);        \
+      case 0: return launch_cfg<BN_, CG_, 0>(ta, tw, to, p, stream);     \
+      case 1: return launch_cfg<BN_, CG_, 1>(ta, tw, to, p, stream);     \
+      case 2: return launch_cfg<BN_, CG_, 2>(ta, tw, to, p, stream);     \
+      default: return launch_cfg<BN_, CG_, 3>(ta, tw, to, p, stream);    \
     }                                                                    \
   }
   B2S_GEMM_CASE(256, 1);

@@ -27,11 +27,43 @@ def init_process_group(backend: str | None = None) -> tuple[int, int, int]:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
         if backend == "nccl":
+            # The only collective of this path is the gradient all-reduce, hidden under the encoder backward: it needs
+            # ~20 GB/s, not the whole chip. Few NCCL CTAs = few SMs taken from the persistent GEMMs it overlaps with
+            # (EncoderTrainer.comm_sms reads the same variable). An explicit setting in the environment wins.
+            os.environ.setdefault("NCCL_MAX_CTAS", "4")
             torch.cuda.set_device(local_rank)
             dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
         else:
             dist.init_process_group(backend)
     return rank, local_rank, world
+
+
+_NATIVE_COMM = {"world": 1}
+
+
+def ensure_native_comm() -> int:
+    """Give the library's current handle its own NCCL communicator over the ranks of the default process group
+    (include/b2s.h: b2s_comm_unique_id / b2s_comm_init): rank 0 mints the id, torch.distributed carries it to the others.
+    The gradient all-reduce of the training step then runs through the C ABI (b2s_allreduce_grads) on the library's
+    communication stream; torch.distributed stays the plumbing (rendezvous, barriers, scalar reductions).
+    Returns the communicator's world size (1 = not distributed)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 1
+    if _NATIVE_COMM["world"] == dist.get_world_size():
+        return _NATIVE_COMM["world"]
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    buf = (C.c_uint8 * _lib.COMM_ID_BYTES)()
+    if rank == 0:
+        _lib.check(lib.b2s_comm_unique_id(buf), "comm_unique_id")
+    box = [bytes(buf)]
+    dist.broadcast_object_list(box, src=0)
+    buf = (C.c_uint8 * _lib.COMM_ID_BYTES).from_buffer_copy(box[0])
+    _lib.check(lib.b2s_comm_init(buf, rank, world), "comm_init")
+    _NATIVE_COMM["world"] = world
+    return world
 
 
 def shard_indices(n_items: int, rank: int, world: int) -> List[int]:

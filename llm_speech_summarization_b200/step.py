@@ -421,7 +421,7 @@ class AudioPromptStep:
     def forward_backward(self, waves: torch.Tensor, text_ids, resp_ids, loss_scale: float = 1.0,
                          plan: Optional[StepPlan] = None, generator=None, draw=None,
                          num_audio_embeds: Optional[int] = None, lengths=None, scaler=None,
-                         layer_events=None) -> Dict[str, torch.Tensor]:
+                         layer_events=None, comm_sms: int = 0) -> Dict[str, torch.Tensor]:
         """One training micro-batch (REF/trainer.py:270-374): encoder forward with kept activations -> LLM
         forward/backward -> encoder backward. Parameter gradients (x loss_scale x the scaler's scale) accumulate inside
         the encoder until `audio_encoder.flush_grads()`. `generator` / `draw` feed the encoder's train-mode
@@ -443,7 +443,19 @@ class AudioPromptStep:
         d = out["d_audio_embeds"]
         if d.shape[1] < A_full:  # the cropped embeddings get no gradient
             d = torch.nn.functional.pad(d, (0, 0, 0, A_full - d.shape[1]))
-        self.audio_encoder.backward(d, layer_events=layer_events)
+        if layer_events is not None and comm_sms > 0:
+            # gradient buckets are all-reduced on a communication stream WHILE this backward runs: the persistent GEMMs
+            # must not count on the SMs the NCCL kernel occupies (b2s_set_sm_budget)
+            from . import _lib
+            lib = _lib.load()
+            prop = torch.cuda.get_device_properties(waves.device)
+            lib.b2s_set_sm_budget(max(2, prop.multi_processor_count - int(comm_sms)))
+            try:
+                self.audio_encoder.backward(d, layer_events=layer_events)
+            finally:
+                lib.b2s_set_sm_budget(0)
+        else:
+            self.audio_encoder.backward(d, layer_events=layer_events)
         return out
 
     def __call__(self, waves_host: torch.Tensor, text_ids, resp_ids, device) -> Dict[str, float]:

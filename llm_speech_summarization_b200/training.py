@@ -128,7 +128,6 @@ class FlatAdamW:
             off += k
         self.step_count = 0
         self.scaler: Optional[GradScaler] = None  # set by the trainer: device-side step count + loss scale
-        self._comm_stream: Optional[torch.cuda.Stream] = None
         self.last_allreduce = None  # (events of the last exchange) for `allreduce_ms`
 
     def zero_grad(self, set_to_none: bool = False):
@@ -147,45 +146,57 @@ class FlatAdamW:
 
     @staticmethod
     def _dist_on() -> bool:
-        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        """True when the gradient has to be exchanged; makes sure the library's own communicator exists."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return False
+        from . import dp
+        return dp.ensure_native_comm() > 1
+
+    @staticmethod
+    def _raw_event(ev: torch.cuda.Event) -> int:
+        if not getattr(ev, "_b2s_primed", False):  # a torch event owns a CUDA event only once it has been recorded
+            ev.record()
+            ev._b2s_primed = True
+        return ev.cuda_event
 
     def all_reduce_grads(self):
-        """One SUM all-reduce of the whole flat gradient on the current stream (no overlap)."""
+        """One SUM all-reduce of the whole flat gradient, joined at once (no overlap)."""
         if self._dist_on():
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+            ev = torch.cuda.Event()
+            ev.record()
+            ev._b2s_primed = True
+            self.all_reduce_buckets([(0, self.grad.numel())], [ev])
+            self.finish_all_reduce()
 
     def all_reduce_buckets(self, buckets, ready_events) -> None:
-        """SUM all-reduce of gradient ranges `buckets` = [(start, end), ...] on a dedicated communication stream, each
-        as soon as `ready_events[i]` (recorded on the compute stream when the range's last gradient kernel was enqueued)
-        has fired: the exchange of layer l's gradients runs under the backward of layers l-1 ... 0 (SURVEY.md 8e:
-        buckets per encoder layer, NVSwitch bandwidth is uniform, so bucket = layer). `finish_all_reduce()` makes the
-        compute stream wait for the communication stream."""
+        """SUM all-reduce of gradient ranges `buckets` = [(start, end), ...] through the C ABI (b2s_allreduce_grads) on
+        the library's communication stream, each bucket as soon as `ready_events[i]` (recorded on the compute stream
+        when the range's last gradient kernel was enqueued) has fired: the exchange of layer l's gradients runs under
+        the backward of layers l-1 ... 0 (buckets per encoder layer; NVSwitch bandwidth is uniform, so
+        bucket = layer). Several calls form one exchange; `finish_all_reduce()` makes the compute stream join."""
         if not self._dist_on():
             return
-        dev = self.grad.device
-        if self._comm_stream is None:
-            self._comm_stream = torch.cuda.Stream(dev)
-        cs = self._comm_stream
-        pend = getattr(self, "_pending_comm", None)  # several calls (layer buckets, then the rest) form ONE exchange
-        t0 = pend[0] if pend is not None else None
-        for (a, b), ev in zip(buckets, ready_events):
-            if b <= a:
-                continue
-            cs.wait_event(ev)
-            with torch.cuda.stream(cs):
-                if t0 is None:
-                    t0 = torch.cuda.Event(enable_timing=True)
-                    t0.record(cs)
-                dist.all_reduce(self.grad[a:b], op=dist.ReduceOp.SUM)
-        if t0 is not None:
-            t1 = torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(cs):
-                t1.record(cs)
-            self._pending_comm = (t0, t1)
+        import ctypes as C
+        keep = [(a, b, ev) for (a, b), ev in zip(buckets, ready_events) if b > a]
+        if not keep:
+            return
+        n = len(keep)
+        starts = (C.c_int64 * n)(*[a for a, _, _ in keep])
+        ends = (C.c_int64 * n)(*[b for _, b, _ in keep])
+        evs = (C.c_void_p * n)(*[self._raw_event(ev) for _, _, ev in keep])
+        pend = getattr(self, "_pending_comm", None)
+        t0 = None
+        if pend is None:
+            t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        _lib.check(_lib.load().b2s_allreduce_grads(self.grad.data_ptr(), starts, ends, evs, n,
+                                                   None if t0 is None else self._raw_event(t0), self._raw_event(t1)),
+                   "allreduce_grads")
+        self._pending_comm = (pend[0] if pend is not None else t0, t1)
 
     def finish_all_reduce(self) -> None:
-        """Compute stream waits for every bucket launched by `all_reduce_buckets`; records what bench.py reports:
-        comm-stream span of the exchange and how long the compute stream actually stood still for it."""
+        """Compute stream waits for every bucket launched by `all_reduce_buckets` (b2s_allreduce_join); records what
+        bench.py reports: the communication-stream span of the exchange and how long the compute stream stood still."""
         pend = getattr(self, "_pending_comm", None)
         if pend is None:
             return
@@ -193,7 +204,7 @@ class FlatAdamW:
         main = torch.cuda.current_stream()
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0.record(main)
-        main.wait_stream(self._comm_stream)
+        _lib.check(_lib.load().b2s_allreduce_join(main.cuda_stream), "allreduce_join")
         w1.record(main)
         self.last_allreduce = (t0, t1, w0, w1)
         self._pending_comm = None
@@ -341,6 +352,10 @@ class EncoderTrainer:
         # gradient exchange: one bucket per transformer layer, launched on a communication stream as soon as the
         # layer's backward has been enqueued (overlap with the layers below), plus one bucket for everything else
         self.overlap_allreduce = True
+        # SMs left to the NCCL kernels while buckets are exchanged under the encoder backward (= NCCL_MAX_CTAS set by
+        # dp.init_process_group); the persistent GEMMs of that backward size their grids for the rest
+        import os
+        self.comm_sms = int(os.environ.get("NCCL_MAX_CTAS", "0") or 0)
         self._layer_spans = None
         groups = getattr(audio_encoder, "layer_param_groups", lambda: [])()
         spans = [self.optimizer.span_of(g) for g in groups]
@@ -379,6 +394,7 @@ class EncoderTrainer:
         out = self.step_fn.forward_backward(waves, text_ids, resp_ids, loss_scale=1.0 / self.grad_accum_interval,
                                             plan=plan, generator=self.generator, scaler=self.scaler,
                                             layer_events=self._layer_events if overlap else None,
+                                            comm_sms=self.comm_sms if overlap else 0,
                                             **({} if num_audio_embeds is None else {"num_audio_embeds": num_audio_embeds}),
                                             **({} if lengths is None else {"lengths": lengths}))
         self._micro += B * self.world()

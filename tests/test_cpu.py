@@ -688,3 +688,33 @@ def test_allreduce_buckets_tile_the_flat_gradient():
         q, k, v = (at[id(m.weight)] for m in (a.q_proj, a.k_proj, a.v_proj))
         assert q[1] == k[0] and k[1] == v[0]
         assert sum(b - a_ for a_, b in covered) + (off - covered[-1][1]) == off
+
+
+def test_handles_own_their_state():
+    """include/b2s.h: options, SM budget and the launch counter belong to a b2s_handle, not to the process: two handles
+    do not see each other's settings, the process default is untouched, destroy() falls back to the default."""
+    import ctypes as C
+    from llm_speech_summarization_b200 import _lib
+    lib = _lib.load()
+    get = lambda opt: (lambda v: (lib.b2s_get_option(opt, C.byref(v)), v.value)[1])(C.c_int32())
+    base_pdl, base_budget = get(_lib.OPT_PDL), get(_lib.OPT_SM_BUDGET)
+    h1, h2 = C.c_void_p(), C.c_void_p()
+    assert lib.b2s_create(C.byref(h1)) == 0 and lib.b2s_create(C.byref(h2)) == 0
+    try:
+        assert lib.b2s_make_current(h1) == 0
+        assert lib.b2s_set_option(_lib.OPT_PDL, 0) == 0 and lib.b2s_set_option(_lib.OPT_TMA_EPILOGUE, 0) == 0
+        lib.b2s_set_sm_budget(140)
+        assert (get(_lib.OPT_PDL), get(_lib.OPT_TMA_EPILOGUE), lib.b2s_get_sm_budget()) == (0, 0, 140)
+        assert lib.b2s_make_current(h2) == 0
+        assert (get(_lib.OPT_PDL), get(_lib.OPT_TMA_EPILOGUE), lib.b2s_get_sm_budget()) == (base_pdl, 1, 0)
+        assert lib.b2s_set_option(99, 1) != 0 and b"unknown option" in lib.b2s_last_error()
+        assert lib.b2s_make_current(None) == 0
+        assert (get(_lib.OPT_PDL), get(_lib.OPT_SM_BUDGET)) == (base_pdl, base_budget)
+        assert lib.b2s_make_current(h1) == 0 and get(_lib.OPT_PDL) == 0
+    finally:
+        assert lib.b2s_destroy(h1) == 0 and lib.b2s_destroy(h2) == 0
+    assert get(_lib.OPT_PDL) == base_pdl  # destroying the current handle falls back to the process default
+    rank, world = C.c_int32(-1), C.c_int32(-1)
+    assert lib.b2s_comm_world(C.byref(rank), C.byref(world)) == 0 and (rank.value, world.value) == (0, 1)
+    flat = (C.c_float * 4)()
+    assert lib.b2s_allreduce_join(None) != 0 and b"no communicator" in lib.b2s_last_error()
