@@ -128,11 +128,13 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
 }
 
 // ---- epilogue helpers ------------------------------------------------------------------------
-__device__ __forceinline__ void add_bias_act(float (&v)[32], const float* bias, int act) {
+// nvalid: columns of this 32-wide chunk that exist (N is a multiple of 8, so whole float4 groups; the bias array ends at N)
+__device__ __forceinline__ void add_bias_act(float (&v)[32], const float* bias, int act, int nvalid = 32) {
   if (bias != nullptr) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + q);
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * q < nvalid) b4 = __ldg(reinterpret_cast<const float4*>(bias) + q);
       v[4 * q + 0] += b4.x;
       v[4 * q + 1] += b4.y;
       v[4 * q + 2] += b4.z;
@@ -510,11 +512,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           float v[32], v2[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          add_bias_act(v, (bias && col < p.N) ? bias + col : nullptr, p.act);
+          add_bias_act(v, (bias && col < p.N) ? bias + col : nullptr, p.act, p.N - col);
           if (h16) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v2[i] = __uint_as_float(raw2[i]);
-            add_bias_act(v2, (bias && col + 32 < p.N) ? bias + col + 32 : nullptr, p.act);
+            add_bias_act(v2, (bias && col + 32 < p.N) ? bias + col + 32 : nullptr, p.act, p.N - col - 32);
           }
           // four warps: two staging tiles per warp, the store of chunk c drains while chunk c+1 is staged
           const uint32_t buf = stg + (kHalves == 1 ? (nst & 1u) * 4096u : 0u);

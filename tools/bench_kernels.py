@@ -80,12 +80,11 @@ def bench_attn(label, lens, Hq, Hkv, D, causal):
     qkv = torch.randn(rows, (Hq + 2 * Hkv) * D, device=dev).to(torch.bfloat16)
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
     flops = sum(4 * L * L * Hq * D * (0.5 if causal else 1.0) for L in lens)
-    for impl, name in ((1, "tcgen05"), (0, "mma_sync")):
-        ops.attention_set_impl(impl)
-        ms = time_fn(lambda: ops.attention(qkv, cu, max(lens), Hq, Hkv, D, 1.0 / math.sqrt(D), causal), iters=20)
-        print(json.dumps({"kernel": "attention", "label": label, "impl": name, "ms": round(ms, 4),
+    for dt, name in ((torch.float16, "fp16"), (torch.bfloat16, "bf16")):
+        x = qkv.to(dt)
+        ms = time_fn(lambda: ops.attention(x, cu, max(lens), Hq, Hkv, D, 1.0 / math.sqrt(D), causal), iters=20)
+        print(json.dumps({"kernel": "attention", "label": label, "operands": name, "ms": round(ms, 4),
                           "tflops": round(flops / ms / 1e9, 1)}), flush=True)
-    ops.attention_set_impl(1)
 
 
 if __name__ == "__main__":
