@@ -30,7 +30,7 @@ def init_process_group(backend: str | None = None) -> tuple[int, int, int]:
             # The only collective of this path is the gradient all-reduce, hidden under the encoder backward: it needs
             # ~20 GB/s, not the whole chip. Few NCCL CTAs = few SMs taken from the persistent GEMMs it overlaps with
             # (EncoderTrainer.comm_sms reads the same variable). An explicit setting in the environment wins.
-            os.environ.setdefault("NCCL_MAX_CTAS", "4")
+            os.environ.setdefault("NCCL_MAX_CTAS", "8")
             torch.cuda.set_device(local_rank)
             dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
         else:
