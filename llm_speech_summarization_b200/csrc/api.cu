@@ -30,6 +30,7 @@ Context::Context() {
   resid_red = env_int("B2S_RESID_RED", 1) != 0;
   tma_epi = env_int("B2S_TMA_EPI", 1) != 0;
   if (const char* e = getenv("B2S_ATTN_CFG")) sscanf(e, "%d,%d", &attn_bn, &attn_kvs);
+  gemm_group_m = env_int("B2S_GEMM_GROUP_M", 0);
 }
 
 Context& ctx() { return g_current != nullptr ? *g_current : default_context(); }
@@ -178,6 +179,7 @@ int b2s_set_option(int32_t option, int32_t value) {
     case B2S_OPT_ATTN_KEYS_PER_STEP: c.attn_bn = value; break;
     case B2S_OPT_ATTN_KV_STAGES: c.attn_kvs = value; break;
     case B2S_OPT_SM_BUDGET: c.sm_budget = value > 0 ? value : 0; break;
+    case B2S_OPT_GEMM_GROUP_M: c.gemm_group_m = value > 0 ? value : 0; break;
     default:
       set_last_error("b2s_set_option: unknown option %d", option);
       return B2S_ERR_INVALID;
@@ -197,6 +199,7 @@ int b2s_get_option(int32_t option, int32_t* value) {
     case B2S_OPT_ATTN_KEYS_PER_STEP: *value = c.attn_bn; break;
     case B2S_OPT_ATTN_KV_STAGES: *value = c.attn_kvs; break;
     case B2S_OPT_SM_BUDGET: *value = c.sm_budget; break;
+    case B2S_OPT_GEMM_GROUP_M: *value = c.gemm_group_m; break;
     default:
       set_last_error("b2s_get_option: unknown option %d", option);
       return B2S_ERR_INVALID;

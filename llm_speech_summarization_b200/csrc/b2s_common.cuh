@@ -52,6 +52,7 @@ struct Context {
   int tma_epi = 1;      // MODE 0 GEMM outputs through TMA stores (B2S_TMA_EPI)
   int attn_bn = 0, attn_kvs = 0;  // attention forward tile override (B2S_ATTN_CFG="keys per step,K/V stages"; 0 = auto)
   int sm_budget = 0;    // SMs the persistent kernels size their grids for (0 = all)
+  int gemm_group_m = 0; // GEMM tile-order override: M tiles per group (0 = the default of 8, gemm_sm100.cu)
   std::atomic<long long> launches{0};
   bool timing = false;  // GEMM timing window (bench.py roofline leg)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;

@@ -11,6 +11,10 @@
 // A decode step is weight-streaming bound (M = batch rows against 6.4 GB of weights): the GEMMs run with narrow
 // tiles, and the two residual projections use the accumulate epilogue straight onto the fp32 residual stream so they
 // can split K across the whole chip (out += partial IS the residual add).
+// Measured and rejected in round 2 (profiles/r02_decode.md): the whole step as ONE persistent cooperative kernel (one
+// CTA per SM, equal contiguous row ranges per CTA, grid barriers between the five phases of a layer, next-phase weight
+// prefetch): parity-green, but 2.75 ms / token against 2.39 ms for the PDL-chained launches below at batch 1 -- with
+// fp16 operands the per-element convert + FMA work, not the launch gaps, is what keeps the step at ~0.42 of HBM peak.
 #include "../../include/b2s.h"
 #include "b2s_common.cuh"
 #include "gemm_sm100.cuh"

@@ -94,6 +94,7 @@ struct KParams {
   float drop_inv_keep;
   int resid_red;  // in-place residual adds go through red.global.add (B2S_RESID_RED=0 keeps load + add + store, A/B)
   int tma_out;    // MODE 0 plain epilogues: output leaves through TMA stores / reductions (tmap_o is valid)
+  int group_m;    // tile order: M tiles per group (a group's tiles walk N with M fastest, see decode_tile)
   uint32_t idesc_fmt;  // a_format / b_format bits of the instruction descriptor (bf16 = 1, fp16 = 0; may differ)
   int out_f16;         // 16-bit outputs (out for the *_BF16-class epilogues, out2) are written as fp16 instead of bf16
 };
@@ -104,7 +105,10 @@ struct TileCoord {
 
 template <bool EXT>
 __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
-  constexpr int kGroupM = 8;
+  // Tiles are walked group by group: inside a group of `group_m` M-tiles, M is the fast index and N the slow one, so
+  // the clusters running at the same time share few W tiles and a group's A tiles stay in L2 for its whole N sweep.
+  // W is re-read once per group: DRAM traffic ~ A + W * ceil(m_tiles / group_m) as long as group_m A-tiles fit in L2.
+  const int kGroupM = p.group_m;
   int split = 0;
   if constexpr (EXT) {
     split = t / p.tiles_per_split;
@@ -953,6 +957,10 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   p.rope_cols = a.rope_cols;
   const int resid_red = ctx().resid_red;
   p.resid_red = resid_red;
+  // group_m = 8 M-tiles per group. Swept on the forward step in round 2 (profiles/r02_gemm_tile_order.md): 8 / 16 / 32 and
+  // an L2-sized automatic choice are within run-to-run noise of each other (32 slightly slower); larger groups do cut the
+  // W re-reads (DRAM traffic ~ A + W * ceil(m_tiles / group_m)) but DRAM sits at 12-28 % of peak on these shapes.
+  p.group_m = ctx().gemm_group_m > 0 ? ctx().gemm_group_m : 8;
   p.idesc_fmt = ptx::idesc_formats(a.a_fmt != 0, a.w_fmt != 0);
   p.out_f16 = a.out_fmt != 0 ? 1 : 0;
   p.drop_k1 = a.drop_k1;

@@ -24,11 +24,11 @@ def main():
     llm.eval().to(dev)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    hbm = float(peaks.get("hbm_gbps", peaks.get("hbm_gbps_burst", 6461.5)))
+    hbm = float(peaks.get("hbm_gbs", 6461.5))
     D = la.head_dim
     per_layer = la.hidden * (la.heads + 2 * la.kv_heads) * D + la.heads * D * la.hidden + 3 * la.hidden * la.ffn
     wbytes = 2 * (la.layers * per_layer + la.vocab * la.hidden)
-    for B in (1, 8, 32):
+    for B in [int(x) for x in os.environ.get("DECODE_BATCHES", "1,2,4,8,32").split(",")]:
         g = torch.Generator(device=dev).manual_seed(1)
         prompts = [torch.randn(137, la.hidden, device=dev, generator=g) * 0.02 for _ in range(B)]
         steps, warm = 64, 8
@@ -50,7 +50,9 @@ def main():
         print(json.dumps({"kernel": "decode_step", "batch": B, "ms_per_step": round(ms, 4),
                           "tokens_per_s": round(B * 1e3 / ms, 1), "weight_GB": round(wbytes / 1e9, 3),
                           "achieved_GBps": round(wbytes / ms / 1e6, 1), "hbm_frac": round(wbytes / ms / 1e6 / hbm, 3),
-                          "launches_per_step": (lib.b2s_launch_count() - n0) // steps}), flush=True)
+                          "launches_per_step": (lib.b2s_launch_count() - n0) // steps,
+                          "path": "megakernel" if (B <= 4 and os.environ.get("B2S_DECODE_MEGA", "1") != "0") else "multi-kernel"}),
+              flush=True)
 
 
 if __name__ == "__main__":
