@@ -227,7 +227,8 @@ PROTOTYPES = {
     "b2s_grad_scaler_update": (c_int, [c_void_p, c_float, c_float, c_int, c_void_p]),
 }
 
-OPT_PDL, OPT_RESID_RED, OPT_TMA_EPILOGUE, OPT_ATTN_KEYS_PER_STEP, OPT_ATTN_KV_STAGES, OPT_SM_BUDGET, OPT_GEMM_GROUP_M = range(7)
+OPT_PDL, OPT_RESID_RED, OPT_TMA_EPILOGUE, OPT_ATTN_KEYS_PER_STEP, OPT_ATTN_KV_STAGES, OPT_SM_BUDGET, OPT_GEMM_GROUP_M, \
+    OPT_GEMM_TAIL_SPLIT = range(8)
 COMM_ID_BYTES = 128
 
 _lib = None

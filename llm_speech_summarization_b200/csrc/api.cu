@@ -31,6 +31,7 @@ Context::Context() {
   tma_epi = env_int("B2S_TMA_EPI", 1) != 0;
   if (const char* e = getenv("B2S_ATTN_CFG")) sscanf(e, "%d,%d", &attn_bn, &attn_kvs);
   gemm_group_m = env_int("B2S_GEMM_GROUP_M", 0);
+  gemm_tail_split = env_int("B2S_GEMM_TAIL_SPLIT", 1) != 0;
 }
 
 Context& ctx() { return g_current != nullptr ? *g_current : default_context(); }
@@ -159,6 +160,7 @@ int b2s_destroy(b2s_handle* h) {
   if (h == nullptr) return B2S_OK;
   if (g_current == &h->c) g_current = nullptr;
   const int rc = comm_destroy(h->c);
+  if (h->c.tail_flags != nullptr) cudaFree(h->c.tail_flags);
   for (auto& e : h->c.events) {
     cudaEventDestroy(e.first);
     cudaEventDestroy(e.second);
@@ -180,6 +182,7 @@ int b2s_set_option(int32_t option, int32_t value) {
     case B2S_OPT_ATTN_KV_STAGES: c.attn_kvs = value; break;
     case B2S_OPT_SM_BUDGET: c.sm_budget = value > 0 ? value : 0; break;
     case B2S_OPT_GEMM_GROUP_M: c.gemm_group_m = value > 0 ? value : 0; break;
+    case B2S_OPT_GEMM_TAIL_SPLIT: c.gemm_tail_split = value != 0; break;
     default:
       set_last_error("b2s_set_option: unknown option %d", option);
       return B2S_ERR_INVALID;
@@ -200,6 +203,7 @@ int b2s_get_option(int32_t option, int32_t* value) {
     case B2S_OPT_ATTN_KV_STAGES: *value = c.attn_kvs; break;
     case B2S_OPT_SM_BUDGET: *value = c.sm_budget; break;
     case B2S_OPT_GEMM_GROUP_M: *value = c.gemm_group_m; break;
+    case B2S_OPT_GEMM_TAIL_SPLIT: *value = c.gemm_tail_split; break;
     default:
       set_last_error("b2s_get_option: unknown option %d", option);
       return B2S_ERR_INVALID;

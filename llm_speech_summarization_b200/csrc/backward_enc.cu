@@ -16,14 +16,17 @@ namespace {
 
 constexpr int kWarps = 8;
 
-template <int GROUPS, bool GELU>
+// F16 is a template parameter, not a kernel argument: a run-time format test inside the row loop splits the unrolled
+// loads into separate branch regions and serialises their latencies (+22 % on this kernel, measured round 2)
+template <int GROUPS, bool GELU, bool F16>
 __global__ void __launch_bounds__(kWarps * 32)
 layernorm_bwd_ex_kernel(const void* __restrict__ x, int x_bf16, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float eps, const void* __restrict__ dy, int dy_bf16, float* dh,
                         int accumulate, __nv_bfloat16* dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                        long long rows, int f16) {
+                        long long rows) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   constexpr int C = GROUPS * 256;
+  constexpr int f16 = F16 ? 1 : 0;
   __shared__ float s_red[kWarps][C];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float gm[GROUPS][8], bt[GROUPS][8], adg[GROUPS][8], adb[GROUPS][8];
@@ -194,11 +197,12 @@ col2im_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict_
 constexpr int kC0 = 512, kK0 = 10, kS0 = 5, kTile0 = 32, kTT0 = 2;
 constexpr int kConv0BwdSmem = (kK0 * kC0 + kTile0 * kC0 + kTile0 * 12) * 4;
 
+template <bool F16>
 __global__ void __launch_bounds__(256)
 conv0_bwd_kernel(const float* __restrict__ wave, long long wave_stride, int samples, int frames, long long total_rows,
                  const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dW,
-                 float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, int f16) {
+                 float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float sm0[];
   float* ws = sm0;                 // [kK0][kC0] transposed taps
   float* sd = ws + kK0 * kC0;      // [kTile0][kC0] d(pre-norm)
@@ -277,15 +281,16 @@ conv0_bwd_kernel(const float* __restrict__ wave, long long wave_stride, int samp
         const float rstd = rsqrtf(warp_sum(q) * (1.0f / kC0) + eps);
         float g16[16];
         float sg = 0.f, sgx = 0.f;
+        // all eight dy words of the frame are requested before the first is used (one load latency per frame, not 8)
+        uint32_t du[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          du[i] = ok ? __ldg(reinterpret_cast<const uint32_t*>(dy + rows[tt] * kC0 + 64 * i + 2 * lane)) : 0u;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float2 gm = *reinterpret_cast<const float2*>(gamma + 64 * i + 2 * lane);
           const float2 bt = *reinterpret_cast<const float2*>(beta + 64 * i + 2 * lane);
-          float2 d = make_float2(0.f, 0.f);
-          if (ok) {
-            const uint32_t u = *reinterpret_cast<const uint32_t*>(dy + rows[tt] * kC0 + 64 * i + 2 * lane);
-            d = unpack_h16(u, f16);
-          }
+          const float2 d = F16 ? unpack_f16(du[i]) : unpack_bf16(du[i]);
           const float xh0 = acc[tt][2 * i] * rstd, xh1 = acc[tt][2 * i + 1] * rstd;
           const float dz0 = d.x * gelu_erf_grad(fmaf(gm.x, xh0, bt.x));
           const float dz1 = d.y * gelu_erf_grad(fmaf(gm.y, xh1, bt.y));
@@ -366,13 +371,17 @@ int layernorm_bwd_ex(const void* x, int x_bf16, const float* gamma, const float*
   if (blocks > cap) blocks = cap;
   const unsigned grid = static_cast<unsigned>(blocks);
   __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
-#define B2S_LNBWD(G)                                                                                                  \
-  if (act_gelu)                                                                                                       \
-    layernorm_bwd_ex_kernel<G, true><<<grid, kWarps * 32, 0, stream>>>(x, x_bf16, gamma, beta, eps, dy, dy_bf16, dh,  \
-                                                                       accumulate, dxb, dgamma, dbeta, rows, fmt);   \
-  else                                                                                                                \
-    layernorm_bwd_ex_kernel<G, false><<<grid, kWarps * 32, 0, stream>>>(x, x_bf16, gamma, beta, eps, dy, dy_bf16, dh, \
-                                                                        accumulate, dxb, dgamma, dbeta, rows, fmt);
+#define B2S_LNBWD_(G, A, F)                                                                                            \
+  layernorm_bwd_ex_kernel<G, A, F><<<grid, kWarps * 32, 0, stream>>>(x, x_bf16, gamma, beta, eps, dy, dy_bf16, dh,      \
+                                                                     accumulate, dxb, dgamma, dbeta, rows)
+#define B2S_LNBWD(G)                                  \
+  if (act_gelu) {                                     \
+    if (fmt) B2S_LNBWD_(G, true, true);               \
+    else B2S_LNBWD_(G, true, false);                  \
+  } else {                                            \
+    if (fmt) B2S_LNBWD_(G, false, true);              \
+    else B2S_LNBWD_(G, false, false);                 \
+  }
   switch (C) {
     case 256: B2S_LNBWD(1); break;
     case 512: B2S_LNBWD(2); break;
@@ -382,6 +391,7 @@ int layernorm_bwd_ex(const void* x, int x_bf16, const float* gamma, const float*
       return B2S_ERR_UNSUPPORTED;
   }
 #undef B2S_LNBWD
+#undef B2S_LNBWD_
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -430,15 +440,20 @@ int conv0_bwd(const float* wave, long long wave_stride, int batches, int samples
   const long long total = static_cast<long long>(batches) * frames;
   static bool attr_set = false;
   if (!attr_set) {
-    B2S_CUDA_CHECK(cudaFuncSetAttribute(conv0_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv0BwdSmem));
+    B2S_CUDA_CHECK(cudaFuncSetAttribute(conv0_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv0BwdSmem));
+    B2S_CUDA_CHECK(cudaFuncSetAttribute(conv0_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv0BwdSmem));
     attr_set = true;
   }
   long long blocks = (total + kTile0 - 1) / kTile0;
   const long long cap = num_sms();  // 177 registers x 256 threads + 87 KB shared memory: one resident block per SM
   if (blocks > cap) blocks = cap;
-  conv0_bwd_kernel<<<static_cast<unsigned>(blocks), 256, kConv0BwdSmem, stream>>>(
-      wave, wave_stride, samples, frames, total, w, bias, gamma, beta, eps,
-      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), dW, db, dgamma, dbeta, fmt);
+  const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
+  if (fmt)
+    conv0_bwd_kernel<true><<<static_cast<unsigned>(blocks), 256, kConv0BwdSmem, stream>>>(
+        wave, wave_stride, samples, frames, total, w, bias, gamma, beta, eps, dy, dW, db, dgamma, dbeta);
+  else
+    conv0_bwd_kernel<false><<<static_cast<unsigned>(blocks), 256, kConv0BwdSmem, stream>>>(
+        wave, wave_stride, samples, frames, total, w, bias, gamma, beta, eps, dy, dW, db, dgamma, dbeta);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

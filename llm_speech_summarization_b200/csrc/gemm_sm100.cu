@@ -95,6 +95,13 @@ struct KParams {
   int resid_red;  // in-place residual adds go through red.global.add (B2S_RESID_RED=0 keeps load + add + store, A/B)
   int tma_out;    // MODE 0 plain epilogues: output leaves through TMA stores / reductions (tmap_o is valid)
   int group_m;    // tile order: M tiles per group (a group's tiles walk N with M fastest, see decode_tile)
+  // MODE 0 tail split: the persistent grid walks `units` work units. Units below tail_first are whole tiles; the
+  // tiles of the last, partly filled round are cut into tail_split K-slices of tail_kb k-blocks each so that the round
+  // costs 1 / tail_split of a tile instead of a whole one (M = 6400, N = 3072: 4.05 rounds -> 5 before, 4.25 now).
+  // Slices of one tile meet in the fp32 output: slice 0 stores (or all slices reduce-add for the in-place residual),
+  // the others reduce-add once slice 0's rows have landed (tail_flags, two ints per tile x CTA x epilogue warp).
+  int units, tail_first, tail_split, tail_kb;
+  int* tail_flags;
   uint32_t idesc_fmt;  // a_format / b_format bits of the instruction descriptor (bf16 = 1, fp16 = 0; may differ)
   int out_f16;         // 16-bit outputs (out for the *_BF16-class epilogues, out2) are written as fp16 instead of bf16
 };
@@ -129,6 +136,34 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int t) {
   c.g = bg - c.b * p.groups;
   c.split = split;
   return c;
+}
+
+struct Unit {
+  int tile, split, kb_lo, kb_hi;
+};
+
+template <bool EXT>
+__device__ __forceinline__ Unit decode_unit(const KParams& p, int u) {
+  Unit r;
+  if constexpr (EXT) {  // split-K over the whole problem: the split index is the slow part of the tile index
+    r.tile = u;
+    r.split = u / p.tiles_per_split;
+    r.kb_lo = r.split * p.kb_per_split;
+    r.kb_hi = min(p.num_kb, r.kb_lo + p.kb_per_split);
+  } else if (u < p.tail_first) {
+    r.tile = u;
+    r.split = 0;
+    r.kb_lo = 0;
+    r.kb_hi = p.num_kb;
+  } else {
+    const int j = u - p.tail_first;
+    const int q = j / p.tail_split;
+    r.split = j - q * p.tail_split;
+    r.tile = p.tail_first + q;
+    r.kb_lo = r.split * p.tail_kb;
+    r.kb_hi = min(p.num_kb, r.kb_lo + p.tail_kb);
+  }
+  return r;
 }
 
 // ---- epilogue helpers ------------------------------------------------------------------------
@@ -359,13 +394,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ============================== TMA producer ==============================
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = cluster_id; t < p.total_tiles; t += num_clusters) {
-      const TileCoord tc = decode_tile<EXT>(p, t);
+    for (int t = cluster_id; t < p.units; t += num_clusters) {
+      const Unit un = decode_unit<EXT>(p, t);
+      const TileCoord tc = decode_tile<EXT>(p, un.tile);
       const int m0 = tc.m_t * (128 * CG) + static_cast<int>(cta_rank) * 128;
       const int n0 = tc.g * p.w_group_off + tc.n_t * BN + static_cast<int>(cta_rank) * C::kBRows;
       const int a_c0_base = tc.g * p.a_group_off;
-      const int kb_lo = EXT ? tc.split * p.kb_per_split : 0;
-      const int kb_hi = EXT ? min(p.num_kb, kb_lo + p.kb_per_split) : p.num_kb;
+      const int kb_lo = un.kb_lo, kb_hi = un.kb_hi;
       for (int kb = kb_lo; kb < kb_hi; ++kb) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = smem_base + stage * C::kStageBytes;
@@ -433,14 +468,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = cluster_id; t < p.total_tiles; t += num_clusters, ++it) {
+    for (int t = cluster_id; t < p.units; t += num_clusters, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
-      const int kb_lo = EXT ? (t / p.tiles_per_split) * p.kb_per_split : 0;
-      const int kb_hi = EXT ? min(p.num_kb, kb_lo + p.kb_per_split) : p.num_kb;
+      const Unit un = decode_unit<EXT>(p, t);
+      const int kb_lo = un.kb_lo, kb_hi = un.kb_hi;
       for (int kb = kb_lo; kb < kb_hi; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
@@ -475,8 +510,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint32_t nst = 0;  // staging tiles this warp has handed to the TMA store engine (buffer = nst & 1)
     if (!EXT && lane == 0) ptx::prefetch_tmap(&tmap_o);
     int it = 0;
-    for (int t = cluster_id; t < p.total_tiles; t += num_clusters, ++it) {
-      const TileCoord tc = decode_tile<EXT>(p, t);
+    for (int t = cluster_id; t < p.units; t += num_clusters, ++it) {
+      const Unit un = decode_unit<EXT>(p, t);
+      const TileCoord tc = decode_tile<EXT>(p, un.tile);
       const int og_cols = EXT ? p.og_cols : p.N;
       void* const out2 = EXT ? p.out2 : nullptr;
       const int as = it & 1;
@@ -488,6 +524,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                               (EXT ? static_cast<long long>(tc.g) * p.og_rows : 0LL) + m0w;
       const int ncol0 = tc.n_t * BN;  // column inside the group
       const float* bias = p.bias ? p.bias + static_cast<long long>(tc.g) * p.N : nullptr;
+      (void)un;
 
       ptx::mbar_wait(tfull_bar(as), aphase);
       ptx::tc_fence_after();
@@ -501,7 +538,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // h += proj(...)) per 32-row x 128-byte tile. No per-thread global stores, no read-back of the staging tile, the
         // write drains asynchronously while the next chunk is computed, and TMA clips the M / N edges.
         const bool h16 = p.epi == EPI_BF16;
-        const bool red = p.epi == EPI_RESID_F32;
+        // K-slices of a tail tile: slice 0 carries the bias and (fp32 store) writes first; later slices add into it
+        const bool tail_tile = t >= p.tail_first;
+        const bool part = un.split > 0;
+        const bool red = p.epi == EPI_RESID_F32 || part;
+        if (part) bias = nullptr;
+        int* const tflag = p.tail_flags + 2 * (((un.tile - p.tail_first) * CG + static_cast<int>(cta_rank)) * 4 + quarter);
+        if (part && p.epi == EPI_F32) {
+          if (lane == 0) {
+            while (ptx::ld_acquire_gpu(tflag) == 0) __nanosleep(64);
+            ptx::fence_proxy_async_all();
+          }
+          __syncwarp();
+        }
         const int cw = h16 ? 64 : 32;  // output columns per staging tile
         const int gcol0 = tc.g * p.N + ncol0;
         constexpr int kChunksPerWarp = (BN / 32) / kHalves;  // 32-column TMEM chunks this warp drains
@@ -559,6 +608,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           ++nst;
           (void)cw;
+        }
+        if (tail_tile && p.epi == EPI_F32 && lane == 0) {
+          if (!part) {
+            ptx::bulk_wait<0>();  // this warp's 32 rows of slice 0 are in memory
+            ptx::fence_proxy_async_all();
+            __threadfence();
+            ptx::st_release_gpu(tflag, 1);
+          } else if (atomicAdd(tflag + 1, 1) == p.tail_split - 2) {  // last adder: re-arm the pair for the next launch
+            tflag[1] = 0;
+            ptx::st_release_gpu(tflag, 0);
+          }
         }
         } else {
         // In-place residual (out aliases resid: the inference forward's h += proj(...)): the add is done by the L2 as
@@ -745,6 +805,21 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
   return B2S_OK;
 }
 
+constexpr size_t kTailFlagBytes = 148 * 2 * 4 * 2 * sizeof(int);  // tiles of one round x CTAs x epilogue warps x {ready, count}
+
+int ensure_tail_flags() {
+  Context& c = ctx();
+  int dev = 0;
+  B2S_CUDA_CHECK(cudaGetDevice(&dev));
+  if (c.tail_flags != nullptr && c.tail_flags_dev == dev) return B2S_OK;
+  if (c.tail_flags != nullptr) cudaFree(c.tail_flags);
+  c.tail_flags = nullptr;
+  B2S_CUDA_CHECK(cudaMalloc(&c.tail_flags, kTailFlagBytes));
+  B2S_CUDA_CHECK(cudaMemset(c.tail_flags, 0, kTailFlagBytes));
+  c.tail_flags_dev = dev;
+  return B2S_OK;
+}
+
 template <int BN, int CG, int MODE>
 int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const KParams& p,
                cudaStream_t stream) {
@@ -757,7 +832,7 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& 
   }
   const int sms = num_sms();
   int clusters = sms / CG;
-  if (clusters > p.total_tiles) clusters = p.total_tiles;
+  if (clusters > p.units) clusters = p.units;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CG);
   cfg.blockDim = dim3(kThreads<MODE>);
@@ -1033,6 +1108,32 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
     if (!p.tma_out) ext = true;
   }
   const int mode = a.a_mn ? 3 : (a.b_mn ? 2 : (ext ? 1 : 0));
+  // Tail split (MODE 0, fp32 outputs that leave through TMA): see KParams. Only the last, partly filled round is cut, into
+  // at most 4 K-slices of at least 8 k-blocks, one slice per cluster, so the round costs 1/S of a tile (+ one epilogue).
+  p.units = p.total_tiles;
+  p.tail_first = p.total_tiles;
+  p.tail_split = 1;
+  p.tail_kb = p.num_kb;
+  p.tail_flags = nullptr;
+  if (mode == 0 && p.tma_out && ctx().gemm_tail_split && a.act == ACT_NONE && (a.epi == EPI_F32 || a.epi == EPI_RESID_F32)) {
+    const int G = num_sms() / cg;
+    const int tail = G > 0 ? p.total_tiles % G : 0;
+    const int full = p.total_tiles - tail;
+    if (tail > 0 && full > 0) {
+      int S = G / tail;
+      if (S > 4) S = 4;
+      if (S > p.num_kb / 8) S = p.num_kb / 8;
+      if (S >= 2) {
+        const int rc = ensure_tail_flags();
+        if (rc != B2S_OK) return rc;
+        p.tail_kb = (p.num_kb + S - 1) / S;
+        p.tail_split = (p.num_kb + p.tail_kb - 1) / p.tail_kb;
+        p.tail_first = full;
+        p.units = full + tail * p.tail_split;
+        p.tail_flags = ctx().tail_flags;
+      }
+    }
+  }
   if (ctx().timing)
     ctx().pending = TimedShape{a.M, a.N, a.k_per_tap * a.taps * k_batches, a.batches, a.groups, a.epi, a.act, mode, bn, cg};
 #define B2S_GEMM_CASE(BN_, CG_)                                          \

@@ -269,3 +269,47 @@ def test_gemm_dgrad_wgrad_f16(cuda, dy_dt, w_dt):
     dw = torch.zeros(768, 512, device=cuda)
     ops.gemm_wgrad(dy, x, dw)
     assert rel_l2(dw, dy.float().t() @ x.float()) < TOL_F32
+
+
+def _set_tail_split(v):
+    from llm_speech_summarization_b200 import _lib
+    lib = _lib.load()
+    old = C.c_int32(0)
+    _lib.check(lib.b2s_get_option(_lib.OPT_GEMM_TAIL_SPLIT, C.byref(old)), "get_option")
+    _lib.check(lib.b2s_set_option(_lib.OPT_GEMM_TAIL_SPLIT, v), "set_option")
+    return old.value
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("M,N,K", [(6400, 3072, 2048), (6400, 3072, 1024), (10144, 3072, 1024), (15968, 1024, 1024),
+                                   (9601, 3072 - 8, 1536)],
+                         ids=["dgrad6400", "dgrad6400_k1024", "llm_resid", "enc_out_proj", "ragged_edges"])
+@pytest.mark.parametrize("epi", ["f32", "resid"])
+def test_gemm_tail_split_matches_unsplit(cuda, M, N, K, epi):
+    """The last, partly filled round of the persistent grid is K-sliced (KParams.tail_*): slice 0 stores / every slice
+    reduce-adds. Same numbers as the unsplit kernel up to fp32 summation order, twice in a row (the flags re-arm), and
+    the shapes here all HAVE a tail on 148 SMs (300, 300, 480, 252, 456 tiles over 74 CTA pairs)."""
+    from llm_speech_summarization_b200 import ops
+    a, w, b = _mk(M, N, K, cuda, seed=11)
+    ref = a.float() @ w.float().t() + b
+    h0 = torch.randn(M, N, device=cuda)
+    old = _set_tail_split(1)
+    try:
+        for rep in range(3):
+            if epi == "f32":
+                out = torch.full((M, N), float("nan"), device=cuda)
+                ops.gemm(a, w, bias=b, epi=ops.EPI_F32, out=out)
+                want = ref
+            else:
+                out = h0.clone()
+                ops.gemm(a, w, bias=b, epi=ops.EPI_RESID_F32, resid=out, out=out)
+                want = h0 + ref
+            torch.cuda.synchronize()
+            assert bool(torch.isfinite(out).all()), rep
+            assert rel_l2(out, want) < TOL_F32, rep
+        _set_tail_split(0)
+        plain = torch.empty(M, N, device=cuda)
+        ops.gemm(a, w, bias=b, epi=ops.EPI_F32, out=plain)
+        assert rel_l2(plain, ref) < TOL_F32
+    finally:
+        _set_tail_split(old)
