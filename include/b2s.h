@@ -488,10 +488,14 @@ int b2s_whisper_forward_train(const b2s_whisper_weights* w, const float* mel, in
 int b2s_whisper_backward(const b2s_whisper_weights* w, const b2s_whisper_grads* grads, int32_t batches, void* saved,
                          size_t saved_bytes, const float* d_audio_embeds, void* workspace, size_t workspace_bytes,
                          void* const* layer_done_events, void* stream);
-/* memory-bound backward kernels of the encoder (see csrc/backward_enc.cu) */
+/* memory-bound backward kernels of the encoder (see csrc/backward_enc.cu).
+ * layernorm_bwd_ex: dh (+)= LN'(x) dy [optionally through an erf-GELU], dgamma / dbeta += ...; dh_colsum (optional, [C])
+ * += the column sums of the dh it writes -- the bias gradient of the linear layer underneath, so that the transformer
+ * backward does not re-read dh for it (REF: torch autograd of nn.LayerNorm / nn.Linear.bias in HubertEncoderLayer). */
 int b2s_layernorm_bwd_ex(const void* x, int32_t x_bf16, const float* gamma, const float* beta, int32_t act_gelu,
                          float eps, const void* dy, int32_t dy_bf16, float* dh, int32_t accumulate, void* dx_bf16,
-                         float* dgamma, float* dbeta, int64_t rows, int32_t C, int32_t fmt, void* stream);
+                         float* dgamma, float* dbeta, int64_t rows, int32_t C, int32_t fmt, float* dh_colsum,
+                         void* stream);
 int b2s_colsum_accum(const void* x, int32_t x_bf16, float* out, int64_t rows, int32_t C, int32_t fmt, void* stream);
 int b2s_avgpool_bwd(const float* dpooled, float* dx, int32_t batches, int32_t frames, int32_t C, int32_t kernel,
                     int32_t stride, int32_t pooled, void* stream);

@@ -215,7 +215,8 @@ PROTOTYPES = {
     "b2s_whisper_backward": (c_int, [C.POINTER(WhisperWeights), C.POINTER(WhisperGrads), c_int, c_void_p, C.c_size_t,
                                      c_void_p, c_void_p, C.c_size_t, C.POINTER(c_void_p), c_void_p]),
     "b2s_layernorm_bwd_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p,
-                                     c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+                                     c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
+                                     c_void_p]),
     "b2s_colsum_accum": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "b2s_avgpool_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b2s_col2im_add": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -461,9 +461,10 @@ int b2s_drop_mask_dump(uint8_t* out, int64_t n, uint64_t seed, uint32_t site, ui
 }
 int b2s_layernorm_bwd_ex(const void* x, int32_t x_bf16, const float* gamma, const float* beta, int32_t act_gelu,
                          float eps, const void* dy, int32_t dy_bf16, float* dh, int32_t accumulate, void* dx_bf16,
-                         float* dgamma, float* dbeta, int64_t rows, int32_t C, int32_t fmt, void* stream) {
+                         float* dgamma, float* dbeta, int64_t rows, int32_t C, int32_t fmt, float* dh_colsum,
+                         void* stream) {
   return layernorm_bwd_ex(x, x_bf16, gamma, beta, act_gelu, eps, dy, dy_bf16, dh, accumulate, dx_bf16, dgamma, dbeta,
-                          rows, C, fmt, S(stream));
+                          rows, C, fmt, S(stream), dh_colsum);
 }
 int b2s_colsum_accum(const void* x, int32_t x_bf16, float* out, int64_t rows, int32_t C, int32_t fmt, void* stream) {
   return colsum_accum(x, x_bf16, out, rows, C, fmt, S(stream));

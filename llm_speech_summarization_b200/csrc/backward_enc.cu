@@ -17,22 +17,31 @@ namespace {
 constexpr int kWarps = 8;
 
 // F16 is a template parameter, not a kernel argument: a run-time format test inside the row loop splits the unrolled
-// loads into separate branch regions and serialises their latencies (+22 % on this kernel, measured round 2)
+// loads into separate branch regions and serialises their latencies (+22 % on this kernel, measured round 2).
+// One warp per row, 8 * GROUPS columns per lane, dgamma / dbeta sums in registers. Measured and rejected in round 2
+// (tools/bench_ln_bwd.py): one block per row with 8 columns per thread (72-96 registers, 20-32 resident warps, three
+// block reductions per row) ran at 110-140 us on the 15968 x 1024 case against 73 us for this form.
+// dh_colsum (optional): column sums of the dh written here, accumulated in the warp's shared-memory slice (each cell is
+// owned by one lane, so no synchronisation) -- the registers are all taken.
 template <int GROUPS, bool GELU, bool F16>
 __global__ void __launch_bounds__(kWarps * 32)
 layernorm_bwd_ex_kernel(const void* __restrict__ x, int x_bf16, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float eps, const void* __restrict__ dy, int dy_bf16, float* dh,
                         int accumulate, __nv_bfloat16* dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                        long long rows) {
+                        float* __restrict__ dh_colsum, long long rows) {
   pdl_trigger();  // PDL: let a dependent GEMM take the SMs this grid frees (b2s_common.cuh)
   constexpr int C = GROUPS * 256;
   constexpr int f16 = F16 ? 1 : 0;
-  __shared__ float s_red[kWarps][C];
+  __shared__ __align__(16) float s_red[kWarps][C];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float gm[GROUPS][8], bt[GROUPS][8], adg[GROUPS][8], adb[GROUPS][8];
 #pragma unroll
   for (int g = 0; g < GROUPS; ++g) {
     const int c = (g * 32 + lane) * 8;
+    if (dh_colsum != nullptr) {
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      st8f(&s_red[warp][c], z);
+    }
     ld8f(gamma + c, gm[g]);
     if constexpr (GELU) ld8f(beta + c, bt[g]);
 #pragma unroll
@@ -93,7 +102,24 @@ layernorm_bwd_ex_kernel(const void* __restrict__ x, int x_bf16, const float* __r
       for (int j = 0; j < 8; ++j) acc[j] += rstd * (dv[g][j] - sg - xv[g][j] * sgx);
       if (dh != nullptr) st8f(dh + row * C + c, acc);
       if (dx_bf16 != nullptr) st8h(dx_bf16 + row * C + c, acc, f16);
+      if (dh_colsum != nullptr) {
+        float cs[8];
+        ld8f(&s_red[warp][c], cs);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[j] += acc[j];
+        st8f(&s_red[warp][c], cs);
+      }
     }
+  }
+  if (dh_colsum != nullptr) {  // flush the column sums before the slices are reused for dgamma / dbeta
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) t += s_red[w][i];
+      atomicAdd(dh_colsum + i, t);
+    }
+    __syncthreads();
   }
   // parameter gradients: registers -> shared (per warp) -> one atomic per column per block
 #pragma unroll
@@ -362,7 +388,7 @@ conv0_bwd_kernel(const float* __restrict__ wave, long long wave_stride, int samp
 
 int layernorm_bwd_ex(const void* x, int x_bf16, const float* gamma, const float* beta, int act_gelu, float eps,
                      const void* dy, int dy_bf16, float* dh, int accumulate, void* dx_bf16, float* dgamma, float* dbeta,
-                     long long rows, int C, int fmt, cudaStream_t stream) {
+                     long long rows, int C, int fmt, cudaStream_t stream, float* dh_colsum) {
   B2S_REQUIRE(x && gamma && dy && dgamma && dbeta && (dh || dx_bf16), "layernorm_bwd_ex: null pointer");
   B2S_REQUIRE(!act_gelu || beta != nullptr, "layernorm_bwd_ex: the GELU variant needs beta");
   if (rows <= 0) return B2S_OK;
@@ -373,7 +399,7 @@ int layernorm_bwd_ex(const void* x, int x_bf16, const float* gamma, const float*
   __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
 #define B2S_LNBWD_(G, A, F)                                                                                            \
   layernorm_bwd_ex_kernel<G, A, F><<<grid, kWarps * 32, 0, stream>>>(x, x_bf16, gamma, beta, eps, dy, dy_bf16, dh,      \
-                                                                     accumulate, dxb, dgamma, dbeta, rows)
+                                                                     accumulate, dxb, dgamma, dbeta, dh_colsum, rows)
 #define B2S_LNBWD(G)                                  \
   if (act_gelu) {                                     \
     if (fmt) B2S_LNBWD_(G, true, true);               \

@@ -99,7 +99,7 @@ int grad_scaler_update(GradScalerState* scaler, float growth, float backoff, int
 // LayerNorm (+ optional erf-GELU on its output) backward; x / dy fp32 or bf16; dh fp32 (+=) and/or bf16 dx outputs
 int layernorm_bwd_ex(const void* x, int x_bf16, const float* gamma, const float* beta, int act_gelu, float eps,
                      const void* dy, int dy_bf16, float* dh, int accumulate, void* dx_bf16, float* dgamma, float* dbeta,
-                     long long rows, int C, int fmt, cudaStream_t stream);
+                     long long rows, int C, int fmt, cudaStream_t stream, float* dh_colsum = nullptr);
 int colsum_accum(const void* x, int x_bf16, float* out, long long rows, int C, int fmt, cudaStream_t stream);
 int avgpool_bwd(const float* dpooled, float* dx, int batches, int frames, int C, int kernel, int stride, int pooled,
                 cudaStream_t stream);

@@ -389,6 +389,9 @@ int stack_backward(const b2s_encoder_layer* layers, const b2s_encoder_layer_grad
   const long long rows = rows_packed >= 0 ? rows_packed : static_cast<long long>(B) * frames;
   const size_t rH = static_cast<size_t>(rows) * H;
   const bool drop_h = reg != nullptr && reg->p_hidden > 0.f;
+  // Without hidden dropout the bias gradients of W2 / Wo are column sums of dh itself; the LayerNorm backward that
+  // writes dh accumulates them on the way (layernorm_bwd_ex's dh_colsum) instead of a colsum pass re-reading dh.
+  bool b2_done = false;  // layer l's b2 gradient was produced by the layer above
   for (int l = L - 1; l >= 0; --l) {
     if (layer_skipped(reg, l)) {  // identity layer: the gradient passes through unchanged
       if (layer_done != nullptr && layer_done[l] != nullptr)
@@ -407,9 +410,10 @@ int stack_backward(const b2s_encoder_layer* layers, const b2s_encoder_layer_grad
     if (drop_h) {  // the branch gradient is the masked copy; the residual path keeps b.dh
       RC(dropout_apply(nullptr, b.dyb, rows * H, make_drop_spec(reg->seed, site_ff_out(l), reg->p_hidden), fmt, stream));
       RC(colsum_accum(b.dyb, 1, G.b2, rows, H, fmt, stream));
-    } else {
+    } else if (!b2_done) {
       RC(colsum_accum(b.dh, 0, G.b2, rows, H, fmt, stream));
     }
+    b2_done = false;
     RC(wgrad(b.dyb, ff, rows, H, F, G.w2, fmt, stream));
     RC(dgrad(b.dyb, Ly.w2, rows, H, F, EPI_BF16, b.dbig, fmt, stream));
     {
@@ -421,14 +425,11 @@ int stack_backward(const b2s_encoder_layer* layers, const b2s_encoder_layer_grad
     RC(wgrad(b.dbig, b.xn, rows, F, H, G.w1, fmt, stream));
     RC(dgrad(b.dbig, Ly.w1, rows, F, H, EPI_BF16, b.dsm, fmt, stream));
     RC(layernorm_bwd_ex(h_mid, 0, Ly.ln2_g, Ly.ln2_b, 0, eps, b.dsm, 1, b.dh, 1, b.dyb, G.ln2_g, G.ln2_b, rows, H,
-                        fmt,
-                        stream));
+                        fmt, stream, drop_h ? nullptr : G.bo));
     // attention: h_mid = h_in + drop(Wo attn(Wqkv LN1(h_in) + bqkv) + bo)
     if (drop_h) {
       RC(dropout_apply(nullptr, b.dyb, rows * H, make_drop_spec(reg->seed, site_attn_out(l), reg->p_hidden), fmt, stream));
       RC(colsum_accum(b.dyb, 1, G.bo, rows, H, fmt, stream));
-    } else {
-      RC(colsum_accum(b.dh, 0, G.bo, rows, H, fmt, stream));
     }
     RC(wgrad(b.dyb, ao, rows, H, H, G.wo, fmt, stream));
     RC(dgrad(b.dyb, Ly.wo, rows, H, H, EPI_BF16, b.dsm, fmt, stream));
@@ -443,7 +444,14 @@ int stack_backward(const b2s_encoder_layer* layers, const b2s_encoder_layer_grad
     RC(layernorm_fwd(h_in, 0, Ly.ln1_g, Ly.ln1_b, eps, 0, b.xn, rows, H, fmt, stream));
     RC(wgrad(b.dbig, b.xn, rows, 3 * H, H, G.wqkv, fmt, stream));
     RC(dgrad(b.dbig, Ly.wqkv, rows, 3 * H, H, EPI_BF16, b.dsm, fmt, stream));
-    RC(layernorm_bwd_ex(h_in, 0, Ly.ln1_g, Ly.ln1_b, 0, eps, b.dsm, 1, b.dh, 1, b.dyb, G.ln1_g, G.ln1_b, rows, H, fmt, stream));
+    {
+      int below = l - 1;  // the next layer down that runs: its W2 bias gradient is the column sum of the dh written here
+      while (below >= 0 && layer_skipped(reg, below)) --below;
+      float* b2_below = (!drop_h && below >= 0) ? grads[below].b2 : nullptr;
+      RC(layernorm_bwd_ex(h_in, 0, Ly.ln1_g, Ly.ln1_b, 0, eps, b.dsm, 1, b.dh, 1, b.dyb, G.ln1_g, G.ln1_b, rows, H, fmt,
+                          stream, b2_below));
+      b2_done = b2_below != nullptr;
+    }
     // every gradient of layer l has been enqueued: a communication stream may start exchanging them (training.py)
     if (layer_done != nullptr && layer_done[l] != nullptr)
       B2S_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(layer_done[l]), stream));

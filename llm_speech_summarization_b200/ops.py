@@ -336,3 +336,42 @@ def whisper_log_mel(waves: torch.Tensor, mel_filters: torch.Tensor) -> torch.Ten
 
 def launch_count() -> int:
     return int(_lib.load().b2s_launch_count())
+
+
+def layernorm_bwd_ex(x: torch.Tensor, gamma: torch.Tensor, beta: Optional[torch.Tensor], dy: torch.Tensor, eps: float,
+                     *, gelu: bool = False, dh: Optional[torch.Tensor] = None, accumulate: bool = False,
+                     dx_dtype: Optional[torch.dtype] = None, dgamma: Optional[torch.Tensor] = None,
+                     dbeta: Optional[torch.Tensor] = None, dh_colsum: Optional[torch.Tensor] = None):
+    """Backward of y = [gelu](LayerNorm(x)): returns (dh fp32 or None, dx 16-bit or None, dgamma, dbeta); dgamma / dbeta /
+    dh_colsum are ACCUMULATED into when given. x, dy: fp32 or one 16-bit format; C in {256, 512, 1024}."""
+    _need_cuda(x, gamma, beta, dy, dh, dgamma, dbeta, dh_colsum)
+    C_ = x.shape[-1]
+    rows = x.numel() // C_
+    h16 = [t.dtype for t in (x, dy) if t.dtype in _H16] + ([dx_dtype] if dx_dtype is not None else [])
+    assert len(set(h16)) <= 1, "one 16-bit format per call"
+    fmt = fmt_of(h16[0]) if h16 else FMT_BF16
+    if dh is None and (dx_dtype is None or accumulate):
+        dh = torch.zeros(x.shape, device=x.device, dtype=torch.float32)
+    dx = torch.empty(x.shape, device=x.device, dtype=dx_dtype) if dx_dtype is not None else None
+    dgamma = torch.zeros(C_, device=x.device) if dgamma is None else dgamma
+    dbeta = torch.zeros(C_, device=x.device) if dbeta is None else dbeta
+    _lib.check(_lib.load().b2s_layernorm_bwd_ex(x.data_ptr(), int(x.dtype in _H16), gamma.data_ptr(), _ptr(beta),
+                                                int(gelu), eps, dy.data_ptr(), int(dy.dtype in _H16), _ptr(dh),
+                                                int(accumulate), _ptr(dx), dgamma.data_ptr(), dbeta.data_ptr(), rows, C_,
+                                                fmt, _ptr(dh_colsum), _stream()), "layernorm_bwd_ex")
+    return dh, dx, dgamma, dbeta
+
+
+def conv0_bwd(wave: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+              eps: float, dy: torch.Tensor):
+    """Parameter gradients of y = gelu(LayerNorm(conv1d(wave, w, b, stride 5))) (HuBERT-large layer 0: 512 x 1 x 10):
+    returns (dW [512, 10], db, dgamma, dbeta), fp32. dy: [B, frames, 512] in one 16-bit format."""
+    _need_cuda(wave, w, b, gamma, beta, dy)
+    assert wave.dtype == torch.float32 and wave.is_contiguous() and dy.dtype in _H16 and dy.is_contiguous()
+    B, S = wave.shape
+    frames = dy.shape[1]
+    outs = [torch.zeros(n, device=wave.device) for n in (w.numel(), 512, 512, 512)]
+    _lib.check(_lib.load().b2s_conv0_bwd(wave.data_ptr(), S, B, S, w.data_ptr(), b.data_ptr(), gamma.data_ptr(),
+                                         beta.data_ptr(), eps, dy.data_ptr(), frames, *[o.data_ptr() for o in outs],
+                                         fmt_of(dy.dtype), _stream()), "conv0_bwd")
+    return outs[0].view_as(w), outs[1], outs[2], outs[3]

@@ -362,3 +362,61 @@ def test_grad_scaler_device_state(cuda):
     # 1024 -> (overflow) 512 -> two clean steps -> 1024 -> one more clean step (tracker 1)
     assert st["scale"] == 1024.0 and st["growth_tracker"] == 1
     assert opt.steps_taken() == 4 and opt.state_dict()["state"][0]["step"].item() == 4.0
+
+
+# ------------------------------------------------------------------- encoder backward: the memory-bound kernels, directly
+@pytest.mark.parametrize("C", [256, 512, 1024])
+@pytest.mark.parametrize("gelu", [False, True], ids=["ln", "ln_gelu"])
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16], ids=["f32", "f16", "bf16"])
+def test_layernorm_bwd_ex_vs_autograd(cuda, C, gelu, dt):
+    """dh (+)= d/dx [gelu](LN(x)) . dy, dgamma / dbeta, the 16-bit copy of dh, and the fused column sum of dh (the bias
+    gradient of the linear layer underneath) against torch autograd on the same (rounded) inputs."""
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(5 + C)
+    rows = 1237  # not a multiple of anything the kernel strides by
+    x = (torch.randn(rows, C, generator=g) * 2 + 0.3).to(dt).to(cuda)
+    dy = torch.randn(rows, C, generator=g).to(dt).to(cuda)
+    gm = (1 + 0.2 * torch.randn(C, generator=g)).to(cuda)
+    bt = (0.3 * torch.randn(C, generator=g)).to(cuda)
+    prev = torch.randn(rows, C, generator=g).to(cuda)
+    xr = x.float().requires_grad_(True)
+    gr, br = gm.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+    y = F.layer_norm(xr, (C,), gr, br, 1e-5)
+    if gelu:
+        y = F.gelu(y)
+    y.backward(dy.float())
+    dh = prev.clone()
+    cs = torch.full((C,), 2.0, device=cuda)
+    h16 = dt if dt != torch.float32 else torch.float16
+    dh, dx, dg, db = ops.layernorm_bwd_ex(x, gm, bt, dy, 1e-5, gelu=gelu, dh=dh, accumulate=True, dx_dtype=h16,
+                                          dh_colsum=cs)
+    want = prev + xr.grad
+    assert rel_l2(dh, want) < 2e-5
+    assert rel_l2(dx.float(), want) < (6e-4 if h16 == torch.float16 else 4e-3)
+    assert rel_l2(dg, gr.grad) < 2e-5 and rel_l2(db, br.grad) < 2e-5
+    assert rel_l2(cs - 2.0, want.sum(0)) < 2e-5
+    # 16-bit output only, no accumulation (the conv front end's use)
+    _, dx2, _, _ = ops.layernorm_bwd_ex(x, gm, bt, dy, 1e-5, gelu=gelu, dx_dtype=h16)
+    assert rel_l2(dx2.float(), xr.grad) < (6e-4 if h16 == torch.float16 else 4e-3)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_conv0_bwd_vs_autograd(cuda, dt):
+    """Layer 0 of the conv front end (REF: HubertLayerNormConvLayer via transformers): parameter gradients of
+    gelu(LN(conv1d(wave))) recomputed from the waveform, against autograd."""
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    B, S = 3, 4000
+    frames = (S - 10) // 5 + 1
+    wave = torch.randn(B, S, generator=g).to(cuda)
+    w = (0.3 * torch.randn(512, 1, 10, generator=g)).to(cuda).requires_grad_(True)
+    b = (0.1 * torch.randn(512, generator=g)).to(cuda).requires_grad_(True)
+    gm = (1 + 0.1 * torch.randn(512, generator=g)).to(cuda).requires_grad_(True)
+    bt = (0.1 * torch.randn(512, generator=g)).to(cuda).requires_grad_(True)
+    dy = torch.randn(B, frames, 512, generator=g).to(dt).to(cuda)
+    y = F.gelu(F.layer_norm(F.conv1d(wave[:, None], w, b, stride=5).transpose(1, 2), (512,), gm, bt, 1e-5))
+    y.backward(dy.float())
+    dW, db, dg, dbt = ops.conv0_bwd(wave, w.detach().view(512, 10).contiguous(), b.detach(), gm.detach(), bt.detach(),
+                                    1e-5, dy)
+    for got, ref in ((dW, w.grad.view(512, 10)), (db, b.grad), (dg, gm.grad), (dbt, bt.grad)):
+        assert rel_l2(got, ref) < 5e-5
