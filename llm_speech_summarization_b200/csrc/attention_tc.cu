@@ -39,19 +39,24 @@ constexpr int kBM = 128;   // queries per CTA
 constexpr int kThreadsTc = 160;
 
 // BN = keys per step (128, or 64 for short sequences at D = 128 so that two CTAs fit on an SM)
+// KVS = 3 selects the PIPELINED form: S double-buffered in TMEM (the issuer runs two key blocks ahead of the softmax
+// warps, so QK^T of block g+1 / g+2 overlaps the softmax of block g), K and V in two stages each with their own
+// barriers, P single-buffered (rewritten once P.V of the previous block has retired).
 template <int D, int BN, int KVS>
 struct AttnCfg {
+  static constexpr bool kPipe = KVS == 3;
   static constexpr int kQBytes = kBM * D * 2;
   static constexpr int kKBytes = BN * D * 2;
   static constexpr int kVBytes = BN * D * 2;
   static constexpr int kPBytes = kBM * BN * 2;
   // D = 64: single-buffered K/V keeps the CTA at ~81 KiB so two CTAs (2 x 256 TMEM columns) share an SM and overlap
   // each other's TMA / MMA / softmax phases; D = 128: one CTA per SM, K/V double-buffered inside it.
-  static constexpr int kKvStages = KVS;  // K/V tiles in flight: 1 keeps the CTA small (more CTAs per SM), 2 prefetches
+  static constexpr int kKvStages = kPipe ? 2 : KVS;  // K/V tiles in flight: 1 keeps the CTA small (more CTAs per SM), 2 prefetches
   // the dynamic shared-memory window is declared 1024-byte aligned (128B-swizzle atoms), so no alignment slack
   static constexpr int kSmemBytes = kQBytes + kKvStages * (kKBytes + kVBytes) + kPBytes + 256;
-  static constexpr int kOCol = BN;                                // S: [0, BN), O: [BN, BN + D)
-  static constexpr int kTmemCols = (BN + D) <= 128 ? 128 : 256;  // power of two >= BN + D
+  static constexpr int kOCol = kPipe ? 2 * BN : BN;               // S: [0, BN) (+ [BN, 2 BN) pipelined), then O: D columns
+  static constexpr int kTmemCols = (kOCol + D) <= 128 ? 128 : 256;  // power of two >= kOCol + D
+  static_assert(kOCol + D <= 256, "TMEM budget: two CTAs per SM");
 };
 
 struct AttnParams {
@@ -142,6 +147,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const uint32_t bar_q = bars, bar_kv0 = bars + 8, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40;
   const uint32_t bar_oe = bars + 48;  // softmax warps -> issuer: the item's O accumulator has been read out
   const uint32_t tmem_slot = bars + 56;
+  // pipelined form: K / V stages have separate barriers (bar_kv0 + 8 s = K stage s, bar_v0 + 8 s = V stage s) and there
+  // is one S barrier per TMEM buffer (bar_s, bar_s1)
+  constexpr bool kPipe = C::kPipe;
+  const uint32_t bar_v0 = bars + 64, bar_s1 = bars + 80;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -152,6 +161,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     ptx::mbar_init(bar_p, kBM);
     ptx::mbar_init(bar_o, 1);
     ptx::mbar_init(bar_oe, kBM);
+    ptx::mbar_init(bar_v0, 1);
+    ptx::mbar_init(bar_v0 + 8, 1);
+    ptx::mbar_init(bar_s1, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 4) ptx::tmem_alloc<1>(tmem_slot, C::kTmemCols);
@@ -188,62 +200,162 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       constexpr uint32_t idesc_s = ptx::make_idesc_f32acc(kBM, kBN) | ptx::idesc_formats(F16, F16);
       constexpr uint32_t idesc_o =
           ptx::make_idesc_f32acc(kBM, D) | ptx::idesc_formats(F16, F16) | (1u << 16);  // B (= V) is MN-major
-      AttnItem cur, nxt;
-      int item = attn_next_item<BN>(p, blockIdx.x, &cur);
-      uint32_t g = 0, items_done = 0;
-      if (item < p.total_items) {
-        load_q(cur);
-        load_kv(cur, 0, 0);
-      }
-      while (item < p.total_items) {
-        const int item_nxt = attn_next_item<BN>(p, item + gridDim.x, &nxt);
-        const bool have_nxt = item_nxt < p.total_items;
-        ptx::mbar_wait(bar_q, items_done & 1);
-        for (int j = 0; j < cur.nblk; ++j, ++g) {
-          const int st = g % kKvStages;
-          const bool last = j + 1 == cur.nblk;
-          const bool has_next = !last || have_nxt;
-          if (kKvStages == 2 && has_next) {
-            // stage st^1 was last read by PV(g-1): refill it only after that MMA has retired
-            if (g >= 1) ptx::mbar_wait(bar_o, (g - 1) & 1);
-            if (!last) load_kv(cur, j + 1, g + 1);
-            else load_kv(nxt, 0, g + 1);
+      if constexpr (kPipe) {
+        // ---- pipelined issue order. Blocks are numbered CTA-wide (g = 0, 1, ...) across item boundaries; block g uses
+        // S buffer g & 1 and K / V stage g & 1. Iteration i: K(i+2) is requested as soon as S(i) has retired, P.V(i) is
+        // issued when the softmax warps publish P(i), then S(i+2) (its buffer was read out for P(i)), then V(i+2) once
+        // P.V(i) has retired. The softmax warps therefore always find S(i+1) waiting when they finish block i.
+        struct Cur {
+          AttnItem it;
+          int item, j;
+        };
+        auto cur_valid = [&](const Cur& c) { return c.item < p.total_items; };
+        auto cur_next = [&](Cur& c) {
+          if (++c.j >= c.it.nblk) {
+            c.item = attn_next_item<BN>(p, c.item + gridDim.x, &c.it);
+            c.j = 0;
           }
-          ptx::mbar_wait(bar_kv0 + 8 * st, (g / kKvStages) & 1);
+        };
+        auto load_k = [&](const Cur& c, uint32_t g) {
+          const int st = g & 1;
+          ptx::mbar_arrive_expect_tx(bar_kv0 + 8 * st, C::kKBytes);
+#pragma unroll
+          for (int a = 0; a < kAtoms; ++a)
+            ptx::tma_load_2d(&tmap_k, bar_kv0 + 8 * st, sK + st * C::kKBytes + a * (kBN * 128),
+                             p.k_col0 + c.it.hk * D + a * 64, c.it.s0 + c.j * kBN);
+        };
+        auto load_v = [&](const Cur& c, uint32_t g) {
+          const int st = g & 1;
+          ptx::mbar_arrive_expect_tx(bar_v0 + 8 * st, C::kVBytes);
+#pragma unroll
+          for (int a = 0; a < kAtoms; ++a)
+            ptx::tma_load_2d(&tmap_v, bar_v0 + 8 * st, sV + st * C::kVBytes + a * (kBN * 128),
+                             p.v_col0 + c.it.hk * D + a * 64, c.it.s0 + c.j * kBN);
+        };
+        uint32_t q_loads = 0;
+        auto issue_s = [&](const Cur& c, uint32_t g) {
+          const int st = g & 1;
+          if (c.j == 0) {  // first block of an item: its Q rows may replace the previous item's once that item's last
+                           // S = S(g-1) has retired
+            if (g > 0) ptx::mbar_wait(((g - 1) & 1) ? bar_s1 : bar_s, ((g - 1) >> 1) & 1);
+            load_q(c.it);
+            ptx::mbar_wait(bar_q, q_loads & 1);
+            ++q_loads;
+          }
+          ptx::mbar_wait(bar_kv0 + 8 * st, (g >> 1) & 1);
           ptx::tc_fence_after();
-          // S = Q K^T
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
-            const uint32_t q_off = (k >> 2) * (kBM * 128) + (k & 3) * 32;  // 64-column atoms are kBM rows tall
-            const uint32_t k_off = (k >> 2) * (kBN * 128) + (k & 3) * 32;  // ... and kBN rows tall for K
-            ptx::umma_bf16<1>(tmem_base, ptx::make_kmajor_sw128_desc(sQ + q_off),
+            const uint32_t q_off = (k >> 2) * (kBM * 128) + (k & 3) * 32;
+            const uint32_t k_off = (k >> 2) * (kBN * 128) + (k & 3) * 32;
+            ptx::umma_bf16<1>(tmem_base + st * kBN, ptx::make_kmajor_sw128_desc(sQ + q_off),
                               ptx::make_kmajor_sw128_desc(sK + st * C::kKBytes + k_off), idesc_s, k > 0 ? 1u : 0u);
           }
-          ptx::umma_commit<1>(bar_s);
-          // O += P V once the softmax warps have published P (and finished reading S / rescaling O)
-          ptx::mbar_wait(bar_p, g & 1);
-          if (j == 0 && items_done > 0) ptx::mbar_wait(bar_oe, (items_done - 1) & 1);  // previous O read out
-          ptx::tc_fence_after();
+          ptx::umma_commit<1>(st ? bar_s1 : bar_s);
+        };
+        Cur c0, c2;
+        c0.item = attn_next_item<BN>(p, blockIdx.x, &c0.it);
+        c0.j = 0;
+        if (cur_valid(c0)) {
+          c2 = c0;
+          load_k(c2, 0);
+          load_v(c2, 0);
+          issue_s(c2, 0);
+          cur_next(c2);
+          if (cur_valid(c2)) {
+            load_k(c2, 1);
+            load_v(c2, 1);
+            issue_s(c2, 1);
+            cur_next(c2);
+          }
+          uint32_t i = 0, items_done = 0;
+          while (cur_valid(c0)) {
+            const int st = i & 1;
+            const bool have2 = cur_valid(c2);
+            if (have2) {
+              ptx::mbar_wait(st ? bar_s1 : bar_s, (i >> 1) & 1);  // S(i) has retired: its K stage is free
+              load_k(c2, i + 2);
+            }
+            ptx::mbar_wait(bar_p, i & 1);  // P(i) published, S(i) read out
+            if (c0.j == 0 && items_done > 0) ptx::mbar_wait(bar_oe, (items_done - 1) & 1);  // previous O read out
+            ptx::mbar_wait(bar_v0 + 8 * st, (i >> 1) & 1);
+            ptx::tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < kBN / 16; ++k) {
-            const uint64_t pdesc = ptx::make_kmajor_sw128_desc(sP + (k >> 2) * (kBM * 128) + (k & 3) * 32);
-            const uint64_t vdesc = ptx::make_mnmajor_sw128_desc(sV + st * C::kVBytes + k * 2048, kBN * 128);
-            ptx::umma_bf16<1>(tmem_base + C::kOCol, pdesc, vdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBN / 16; ++k) {
+              const uint64_t pdesc = ptx::make_kmajor_sw128_desc(sP + (k >> 2) * (kBM * 128) + (k & 3) * 32);
+              const uint64_t vdesc = ptx::make_mnmajor_sw128_desc(sV + st * C::kVBytes + k * 2048, kBN * 128);
+              ptx::umma_bf16<1>(tmem_base + C::kOCol, pdesc, vdesc, idesc_o, (c0.j > 0 || k > 0) ? 1u : 0u);
+            }
+            ptx::umma_commit<1>(bar_o);
+            if (have2) {
+              issue_s(c2, i + 2);
+              ptx::mbar_wait(bar_o, i & 1);  // P.V(i) has retired: its V stage is free
+              load_v(c2, i + 2);
+              cur_next(c2);
+            }
+            if (c0.j + 1 == c0.it.nblk) ++items_done;
+            cur_next(c0);
+            ++i;
           }
-          ptx::umma_commit<1>(bar_o);
-          // bar_p(g) has fired, so every S MMA of this item has retired: Q's tile can take the next item's rows
-          if (last && have_nxt) load_q(nxt);
-          if (kKvStages == 1 && has_next) {  // single buffer: refill once PV(g) has retired
-            ptx::mbar_wait(bar_o, g & 1);
-            if (!last) load_kv(cur, j + 1, g + 1);
-            else load_kv(nxt, 0, g + 1);
-          }
-          // S(g+1) may now overwrite S (the softmax warps are done with it); P's smem and O are protected because
-          // bar_s(g+1) -- a tcgen05.commit -- only fires after every earlier MMA of this thread, PV(g) included.
         }
-        cur = nxt;
-        item = item_nxt;
-        ++items_done;
+      } else {
+        AttnItem cur, nxt;
+        int item = attn_next_item<BN>(p, blockIdx.x, &cur);
+        uint32_t g = 0, items_done = 0;
+        if (item < p.total_items) {
+          load_q(cur);
+          load_kv(cur, 0, 0);
+        }
+        while (item < p.total_items) {
+          const int item_nxt = attn_next_item<BN>(p, item + gridDim.x, &nxt);
+          const bool have_nxt = item_nxt < p.total_items;
+          ptx::mbar_wait(bar_q, items_done & 1);
+          for (int j = 0; j < cur.nblk; ++j, ++g) {
+            const int st = g % kKvStages;
+            const bool last = j + 1 == cur.nblk;
+            const bool has_next = !last || have_nxt;
+            if (kKvStages == 2 && has_next) {
+              // stage st^1 was last read by PV(g-1): refill it only after that MMA has retired
+              if (g >= 1) ptx::mbar_wait(bar_o, (g - 1) & 1);
+              if (!last) load_kv(cur, j + 1, g + 1);
+              else load_kv(nxt, 0, g + 1);
+            }
+            ptx::mbar_wait(bar_kv0 + 8 * st, (g / kKvStages) & 1);
+            ptx::tc_fence_after();
+            // S = Q K^T
+  #pragma unroll
+            for (int k = 0; k < D / 16; ++k) {
+              const uint32_t q_off = (k >> 2) * (kBM * 128) + (k & 3) * 32;  // 64-column atoms are kBM rows tall
+              const uint32_t k_off = (k >> 2) * (kBN * 128) + (k & 3) * 32;  // ... and kBN rows tall for K
+              ptx::umma_bf16<1>(tmem_base, ptx::make_kmajor_sw128_desc(sQ + q_off),
+                                ptx::make_kmajor_sw128_desc(sK + st * C::kKBytes + k_off), idesc_s, k > 0 ? 1u : 0u);
+            }
+            ptx::umma_commit<1>(bar_s);
+            // O += P V once the softmax warps have published P (and finished reading S / rescaling O)
+            ptx::mbar_wait(bar_p, g & 1);
+            if (j == 0 && items_done > 0) ptx::mbar_wait(bar_oe, (items_done - 1) & 1);  // previous O read out
+            ptx::tc_fence_after();
+  #pragma unroll
+            for (int k = 0; k < kBN / 16; ++k) {
+              const uint64_t pdesc = ptx::make_kmajor_sw128_desc(sP + (k >> 2) * (kBM * 128) + (k & 3) * 32);
+              const uint64_t vdesc = ptx::make_mnmajor_sw128_desc(sV + st * C::kVBytes + k * 2048, kBN * 128);
+              ptx::umma_bf16<1>(tmem_base + C::kOCol, pdesc, vdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+            }
+            ptx::umma_commit<1>(bar_o);
+            // bar_p(g) has fired, so every S MMA of this item has retired: Q's tile can take the next item's rows
+            if (last && have_nxt) load_q(nxt);
+            if (kKvStages == 1 && has_next) {  // single buffer: refill once PV(g) has retired
+              ptx::mbar_wait(bar_o, g & 1);
+              if (!last) load_kv(cur, j + 1, g + 1);
+              else load_kv(nxt, 0, g + 1);
+            }
+            // S(g+1) may now overwrite S (the softmax warps are done with it); P's smem and O are protected because
+            // bar_s(g+1) -- a tcgen05.commit -- only fires after every earlier MMA of this thread, PV(g) included.
+          }
+          cur = nxt;
+          item = item_nxt;
+          ++items_done;
+        }
       }
     }
   } else {
@@ -292,32 +404,51 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     };
 
     for (int j = 0; j < nblk; ++j, ++g) {
-      ptx::mbar_wait(bar_s, g & 1);  // S(g) is in TMEM; every earlier MMA (PV(g-1) included) has retired
+      // S(g) is in TMEM. Unpipelined: every earlier MMA (PV(g-1) included) has retired with it. Pipelined: S(g) was
+      // issued two blocks ahead, so P.V(g-1) may still be running -- it is waited for (once per block, prev_pv) before
+      // P's shared-memory tile is rewritten and before O is rescaled.
+      if (kPipe) ptx::mbar_wait((g & 1) ? bar_s1 : bar_s, (g >> 1) & 1);
+      else ptx::mbar_wait(bar_s, g & 1);
       ptx::tc_fence_after();
+      const uint32_t tSg = tS + (kPipe ? (g & 1u) * kBN : 0u);
+      bool pv_synced = !kPipe || g == 0;
+      auto prev_pv = [&]() {
+        if (!pv_synced) {
+          ptx::mbar_wait(bar_o, (g - 1) & 1);
+          ptx::tc_fence_after();
+          pv_synced = true;
+        }
+      };
       const int nvis = row_limit - j * kBN;  // visible keys of this row inside this block (<= 0 .. >= 128)
       const bool full_blk = __all_sync(0xffffffffu, nvis >= kBN);
       // D = 128 with 64-key steps (two CTAs per SM, registers to spare): the thread's whole row of S (64 fp32) is read
       // from TMEM ONCE, both 32-column loads in flight before the single wait, and stays in registers for the
       // first-block max pass, the main pass and a retry. Elsewhere the row is re-read chunk by chunk: at D = 64 the
       // four-CTAs-per-SM residency needs <= 102 registers per thread.
-      constexpr bool kHold = (kBN == 64 && D == 128);
+      constexpr bool kHold = (kBN == 64 && (D == 128 || kPipe));  // (pipelined: two CTAs per SM at either D)
       uint32_t held[kHold ? kBN : 1];
       if (kHold) {
-        ptx::tmem_ld_32x32(tS, *reinterpret_cast<uint32_t(*)[32]>(&held[0]));
-        ptx::tmem_ld_32x32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&held[kHold ? 32 : 0]));
+        ptx::tmem_ld_32x32(tSg, *reinterpret_cast<uint32_t(*)[32]>(&held[0]));
+        ptx::tmem_ld_32x32(tSg + 32, *reinterpret_cast<uint32_t(*)[32]>(&held[kHold ? 32 : 0]));
         ptx::tmem_ld_wait();
+        if (!full_blk) {  // (register-held row) invisible scores become -inf once per block, in place
+#pragma unroll
+          for (int i = 0; i < kBN; ++i) held[kHold ? i : 0] = (i < nvis) ? held[kHold ? i : 0] : 0xff800000u;
+        }
       }
-      if (j == 0) {
-        // first block: exact masked row max as the initial reference (nothing accumulated yet)
+      if (__builtin_expect(j == 0, 0)) {
+        // first block: exact masked row max as the initial reference (nothing accumulated yet). (Kept behind a real
+        // branch: if-converted, ptxas ran these 64 compare + select + max per row in EVERY block -- ncu, round 2.)
         float bm = -INFINITY;
         if (kHold) {
+          asm volatile("" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < kBN; ++i) bm = fmaxf(bm, (i < nvis) ? __uint_as_float(held[kHold ? i : 0]) : -INFINITY);
+          for (int i = 0; i < kBN; ++i) bm = fmaxf(bm, __uint_as_float(held[kHold ? i : 0]));
         } else {
 #pragma unroll 1
           for (int c = 0; c < kBN / 32; ++c) {
             uint32_t raw[32];
-            ptx::tmem_ld_32x32(tS + c * 32, raw);
+            ptx::tmem_ld_32x32(tSg + c * 32, raw);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) bm = fmaxf(bm, (c * 32 + i < nvis) ? __uint_as_float(raw[i]) : -INFINITY);
@@ -329,6 +460,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       // fp32 / bf16 absorb; the reference is only moved when the block max outgrew it by 2^16 (deferred to the
       // next block, when no PV is in flight) or, to rule out overflow, immediately by re-running the block (> 2^60).
       for (int attempt = 0; attempt < 2; ++attempt) {
+        if (kPipe && j > 0 && __any_sync(0xffffffffu, pend > m_ref)) prev_pv();  // O is about to be rescaled
         adopt(j > 0);
         const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;
         float rs = 0.f, bmax = -INFINITY;
@@ -336,44 +468,34 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         for (int c = 0; c < kBN / 32; ++c) {
           uint32_t raw_c[kHold ? 1 : 32];
           if (!kHold) {
-            ptx::tmem_ld_32x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&raw_c[0]));
+            ptx::tmem_ld_32x32(tSg + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&raw_c[0]));
             ptx::tmem_ld_wait();
           }
           const uint32_t* raw = kHold ? &held[kHold ? c * 32 : 0] : &raw_c[0];
           uint32_t pk[16];
-          if (full_blk) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float x0 = __uint_as_float(raw[i]), x1 = __uint_as_float(raw[i + 1]);
-              bmax = fmaxf(bmax, fmaxf(x0, x1));
-              float p0 = ex2f(fmaf(x0, sc, -mr)), p1 = ex2f(fmaf(x1, sc, -mr));
-              rs += p0 + p1;
-              if (DROP) {  // the row sum keeps every key; only the P fed to P.V is thinned (1/(1-p) folded into 1/l)
-                const uint32_t e = drow | static_cast<uint32_t>(j * kBN + c * 32 + i);
-                p0 = rng_keep(e, dk1, dk2, p.drop.thresh) ? p0 : 0.f;
-                p1 = rng_keep(e + 1u, dk1, dk2, p.drop.thresh) ? p1 : 0.f;
-              }
-              pk[i >> 1] = F16 ? pack_f16(p0, p1) : pack_bf16(p0, p1);
-            }
-          } else {
+          // ONE code path for full and partial blocks: a partial block first overwrites its invisible scores with -inf
+          // (exp2 -> 0, ignored by the max) behind a warp-uniform branch. (Two separate loops were merged by the compiler
+          // into one that evaluated the 64 compare + select + max of the masked form in EVERY block -- ncu, round 2.)
+          if (!kHold && !full_blk) {
             const int nv = nvis - c * 32;
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float x0 = __uint_as_float(raw[i]), x1 = __uint_as_float(raw[i + 1]);
-              const bool ok0 = i < nv, ok1 = i + 1 < nv;
-              bmax = fmaxf(bmax, fmaxf(ok0 ? x0 : -INFINITY, ok1 ? x1 : -INFINITY));
-              float p0 = ok0 ? ex2f(fmaf(x0, sc, -mr)) : 0.f;
-              float p1 = ok1 ? ex2f(fmaf(x1, sc, -mr)) : 0.f;
-              rs += p0 + p1;
-              if (DROP) {
-                const uint32_t e = drow | static_cast<uint32_t>(j * kBN + c * 32 + i);
-                p0 = rng_keep(e, dk1, dk2, p.drop.thresh) ? p0 : 0.f;
-                p1 = rng_keep(e + 1u, dk1, dk2, p.drop.thresh) ? p1 : 0.f;
-              }
-              pk[i >> 1] = F16 ? pack_f16(p0, p1) : pack_bf16(p0, p1);
+            for (int i = 0; i < 32; ++i) raw_c[kHold ? 0 : i] = (i < nv) ? raw_c[kHold ? 0 : i] : 0xff800000u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float x0 = __uint_as_float(raw[i]), x1 = __uint_as_float(raw[i + 1]);
+            bmax = fmaxf(bmax, fmaxf(x0, x1));
+            float p0 = ex2f(fmaf(x0, sc, -mr)), p1 = ex2f(fmaf(x1, sc, -mr));
+            rs += p0 + p1;
+            if (DROP) {  // the row sum keeps every key; only the P fed to P.V is thinned (1/(1-p) folded into 1/l)
+              const uint32_t e = drow | static_cast<uint32_t>(j * kBN + c * 32 + i);
+              p0 = rng_keep(e, dk1, dk2, p.drop.thresh) ? p0 : 0.f;
+              p1 = rng_keep(e + 1u, dk1, dk2, p.drop.thresh) ? p1 : 0.f;
             }
+            pk[i >> 1] = F16 ? pack_f16(p0, p1) : pack_bf16(p0, p1);
           }
           // chunk c covers keys [32c, 32c+32) = 64 bytes = four 16-byte chunks of atom (c >> 1)
+          prev_pv();  // (pipelined) P.V(g-1) still reads this tile until it retires
           const uint32_t atom = sP + (c >> 1) * (kBM * 128) + r * 128;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -525,6 +647,8 @@ int attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv,
   if (D == 128 && bn == 64 && kvs == 1) { B2S_ATTN_GO(128, 64, 1, false, nullptr); }
   if (D == 128 && bn == 64 && kvs == 2) { B2S_ATTN_GO(128, 64, 2, false, nullptr); }
   if (D == 128 && bn == 128 && kvs == 2) { B2S_ATTN_GO(128, 128, 2, false, nullptr); }
+  if (D == 64 && bn == 64 && kvs == 3) { B2S_ATTN_GO(64, 64, 3, false, nullptr); }    // pipelined (S double-buffered)
+  if (D == 128 && bn == 64 && kvs == 3) { B2S_ATTN_GO(128, 64, 3, false, nullptr); }
 #undef B2S_ATTN_GO
 #undef B2S_ATTN_ARGS
   set_last_error("attention_fwd: tile configuration %d,%d unsupported for head_dim %d", bn, kvs, D);

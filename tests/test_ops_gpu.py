@@ -159,6 +159,58 @@ def test_attention(cuda, Hq, Hkv, D, causal, lens, dtype):
     _run_attention_case(cuda, Hq, Hkv, D, causal, lens, dtype)
 
 
+@pytest.fixture
+def attn_pipelined():
+    """Selects the pipelined attention forward (S double-buffered in TMEM: 64 keys per step, 'K/V stages' = 3) for the
+    duration of a test, through the handle options a caller would use."""
+    from llm_speech_summarization_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    old = [C.c_int32(0), C.c_int32(0)]
+    for o, opt in zip(old, (_lib.OPT_ATTN_KEYS_PER_STEP, _lib.OPT_ATTN_KV_STAGES)):
+        _lib.check(lib.b2s_get_option(opt, C.byref(o)), "get_option")
+    _lib.check(lib.b2s_set_option(_lib.OPT_ATTN_KEYS_PER_STEP, 64), "set_option")
+    _lib.check(lib.b2s_set_option(_lib.OPT_ATTN_KV_STAGES, 3), "set_option")
+    yield
+    _lib.check(lib.b2s_set_option(_lib.OPT_ATTN_KEYS_PER_STEP, old[0].value), "set_option")
+    _lib.check(lib.b2s_set_option(_lib.OPT_ATTN_KV_STAGES, old[1].value), "set_option")
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("Hq,Hkv,D,causal,lens", [
+    (16, 16, 64, False, [499] * 4),
+    (16, 16, 64, False, [1, 63, 64, 65, 130]),
+    (24, 8, 128, True, [200, 117, 1, 64, 129] * 3),
+    (24, 24, 128, True, [136, 400]),
+    (16, 16, 64, False, [1500]),
+    (2, 1, 128, True, [128, 256, 257, 383]),
+    (2, 2, 64, True, [300, 5]),
+    (16, 16, 64, False, [499] * 32),
+    (24, 8, 128, True, [200] * 32 + [117] * 32),
+])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_attention_pipelined(cuda, attn_pipelined, Hq, Hkv, D, causal, lens, dtype):
+    """The same cases (plus the two full bench shapes, where every persistent CTA crosses many item boundaries) through
+    the pipelined forward: the issuer runs two key blocks ahead across (sequence, head, query-block) items."""
+    _run_attention_case(cuda, Hq, Hkv, D, causal, lens, dtype)
+
+
+def test_attention_pipelined_lse_feeds_backward(cuda, attn_pipelined):
+    from llm_speech_summarization_b200 import ops
+    Hq, Hkv, D, lens = 4, 2, 128, [200, 117, 77]
+    g = torch.Generator().manual_seed(12)
+    rows = sum(lens)
+    qkv = (torch.randn(rows, (Hq + 2 * Hkv) * D, generator=g) * 0.7).to(torch.float16).to(cuda)
+    dout = torch.randn(rows, Hq * D, generator=g).to(torch.float16).to(cuda)
+    cu = [0, 200, 317, 394]
+    cu_t = torch.tensor(cu, dtype=torch.int32, device=cuda)
+    o, lse = ops.attention(qkv, cu_t, max(lens), Hq, Hkv, D, 1.0 / math.sqrt(D), True, return_lse=True)
+    dqkv = ops.attention_bwd(qkv, o, dout, lse, cu_t, max(lens), Hq, Hkv, D, 1.0 / math.sqrt(D), True)
+    x = qkv.float().requires_grad_(True)
+    _attn_ref(x, cu, Hq, Hkv, D, 1.0 / math.sqrt(D), True).backward(dout.float())
+    assert rel_l2(dqkv.float(), x.grad) < 3e-3
+
+
 def test_attention_f16_sharp_scores_stay_finite(cuda):
     """fp16 P tops out at 65504: a later key block whose scores outgrow the running reference by far more than 2^14
     must be handled by the immediate re-reference, not overflow to inf."""

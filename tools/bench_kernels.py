@@ -80,11 +80,20 @@ def bench_attn(label, lens, Hq, Hkv, D, causal):
     qkv = torch.randn(rows, (Hq + 2 * Hkv) * D, device=dev).to(torch.bfloat16)
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
     flops = sum(4 * L * L * Hq * D * (0.5 if causal else 1.0) for L in lens)
-    for dt, name in ((torch.float16, "fp16"), (torch.bfloat16, "bf16")):
-        x = qkv.to(dt)
-        ms = time_fn(lambda: ops.attention(x, cu, max(lens), Hq, Hkv, D, 1.0 / math.sqrt(D), causal), iters=20)
-        print(json.dumps({"kernel": "attention", "label": label, "operands": name, "ms": round(ms, 4),
-                          "tflops": round(flops / ms / 1e9, 1)}), flush=True)
+    from llm_speech_summarization_b200 import _lib
+    lib = _lib.load()
+    for cfg, cname in (((0, 0), "default"), ((64, 3), "pipelined")):
+        if cfg[1] == 3 and max(lens) > 1024 and D == 128:
+            continue
+        lib.b2s_set_option(_lib.OPT_ATTN_KEYS_PER_STEP, cfg[0])
+        lib.b2s_set_option(_lib.OPT_ATTN_KV_STAGES, cfg[1])
+        for dt, name in ((torch.float16, "fp16"), (torch.bfloat16, "bf16")):
+            x = qkv.to(dt)
+            ms = time_fn(lambda: ops.attention(x, cu, max(lens), Hq, Hkv, D, 1.0 / math.sqrt(D), causal), iters=20)
+            print(json.dumps({"kernel": "attention", "label": label, "config": cname, "operands": name,
+                              "ms": round(ms, 4), "tflops": round(flops / ms / 1e9, 1)}), flush=True)
+    lib.b2s_set_option(_lib.OPT_ATTN_KEYS_PER_STEP, 0)
+    lib.b2s_set_option(_lib.OPT_ATTN_KV_STAGES, 0)
 
 
 if __name__ == "__main__":
@@ -94,6 +103,9 @@ if __name__ == "__main__":
         bench_attn("whisper_b8", [1500] * 8, 16, 16, 64, False)
         bench_attn("llama_b32_student+teacher", [200] * 32 + [117] * 32, 24, 8, 128, True)
         bench_attn("minichat_b8_L400", [400] * 8, 24, 24, 128, True)
+        bench_attn("llama_b1_prompt137 (configs[1] inference prefill)", [137], 24, 8, 128, True)
+        bench_attn("hubert_b1", [499], 16, 16, 64, False)
+        bench_attn("llama_b4_prompt137", [137] * 4, 24, 8, 128, True)
     if which in ("all", "loss"):  # before the GEMMs heat the part up (the loss kernel is SM-clock sensitive)
         for rows in (64, 2048):
             bench_loss(rows, 128256)
