@@ -283,22 +283,19 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             rd[i] = rng_keep(e, dk1, dk2, p.drop.thresh) ? __float_as_uint(__uint_as_float(rd[i]) * p.drop.inv_keep) : 0u;
           }
         }
-        if (full_blk) {  // every row of the warp sees the whole block: no per-element predicates
+        // one code path: a partial block first turns its invisible scores into -inf (P = 0, dS = 0) behind a
+        // warp-uniform branch (two loops get merged by the compiler into the masked form for EVERY block, see
+        // profiles/r02_attention_pipelined.md)
+        if (!full_blk) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2b(fmaf(__uint_as_float(rs[i]), sc2, -lse));
-            const float p1 = ex2b(fmaf(__uint_as_float(rs[i + 1]), sc2, -lse));
-            pk[i >> 1] = pack_op<F16>(p0 * fmaf(__uint_as_float(rd[i]), sc, -dls),
-                                   p1 * fmaf(__uint_as_float(rd[i + 1]), sc, -dls));
-          }
-        } else {
+          for (int i = 0; i < 32; ++i) rs[i] = (i < nv) ? rs[i] : 0xff800000u;
+        }
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = (i < nv) ? ex2b(fmaf(__uint_as_float(rs[i]), sc2, -lse)) : 0.f;
-            const float p1 = (i + 1 < nv) ? ex2b(fmaf(__uint_as_float(rs[i + 1]), sc2, -lse)) : 0.f;
-            pk[i >> 1] = pack_op<F16>(p0 * fmaf(__uint_as_float(rd[i]), sc, -dls),
-                                   p1 * fmaf(__uint_as_float(rd[i + 1]), sc, -dls));
-          }
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2b(fmaf(__uint_as_float(rs[i]), sc2, -lse));
+          const float p1 = ex2b(fmaf(__uint_as_float(rs[i + 1]), sc2, -lse));
+          pk[i >> 1] = pack_op<F16>(p0 * fmaf(__uint_as_float(rd[i]), sc, -dls),
+                                 p1 * fmaf(__uint_as_float(rd[i + 1]), sc, -dls));
         }
         st_row_chunk(sDS, r, c, pk);
       }
@@ -493,31 +490,23 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             rd[i] = __float_as_uint(__uint_as_float(rd[i]) * mk[i]);
           }
         }
-        if (full_blk) {
+        if (!full_blk) {  // one code path (see the dQ kernel): masked (query, key) pairs get a score of -inf
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float2 nl = *reinterpret_cast<const float2*>(st_lse + c * 32 + i);  // lse (log2 domain)
-            const float2 ds = *reinterpret_cast<const float2*>(st_dl + c * 32 + i);   // delta * scale
-            const float p0 = ex2b(fmaf(__uint_as_float(rs[i]), sc2, -nl.x));
-            const float p1 = ex2b(fmaf(__uint_as_float(rs[i + 1]), sc2, -nl.y));
-            pp[i >> 1] = DROP ? pack_op<F16>(p0 * mk[i], p1 * mk[i + 1]) : pack_op<F16>(p0, p1);
-            pd[i >> 1] = pack_op<F16>(p0 * fmaf(__uint_as_float(rd[i]), sc, -ds.x),
-                                   p1 * fmaf(__uint_as_float(rd[i + 1]), sc, -ds.y));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
+          for (int i = 0; i < 32; ++i) {
             const int qa = q0 + c * 32 + i;
-            const bool ok0 = kvalid && qa < L && (!p.causal || key <= qa);
-            const bool ok1 = kvalid && qa + 1 < L && (!p.causal || key <= qa + 1);
-            const float2 nl = *reinterpret_cast<const float2*>(st_lse + c * 32 + i);
-            const float2 ds = *reinterpret_cast<const float2*>(st_dl + c * 32 + i);
-            const float p0 = ok0 ? ex2b(fmaf(__uint_as_float(rs[i]), sc2, -nl.x)) : 0.f;
-            const float p1 = ok1 ? ex2b(fmaf(__uint_as_float(rs[i + 1]), sc2, -nl.y)) : 0.f;
-            pp[i >> 1] = DROP ? pack_op<F16>(p0 * mk[i], p1 * mk[i + 1]) : pack_op<F16>(p0, p1);
-            pd[i >> 1] = pack_op<F16>(p0 * fmaf(__uint_as_float(rd[i]), sc, -ds.x),
-                                   p1 * fmaf(__uint_as_float(rd[i + 1]), sc, -ds.y));
+            const bool ok = kvalid && qa < L && (!p.causal || key <= qa);
+            rs[i] = ok ? rs[i] : 0xff800000u;
           }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 nl = *reinterpret_cast<const float2*>(st_lse + c * 32 + i);  // lse (log2 domain)
+          const float2 ds = *reinterpret_cast<const float2*>(st_dl + c * 32 + i);   // delta * scale
+          const float p0 = ex2b(fmaf(__uint_as_float(rs[i]), sc2, -nl.x));
+          const float p1 = ex2b(fmaf(__uint_as_float(rs[i + 1]), sc2, -nl.y));
+          pp[i >> 1] = DROP ? pack_op<F16>(p0 * mk[i], p1 * mk[i + 1]) : pack_op<F16>(p0, p1);
+          pd[i >> 1] = pack_op<F16>(p0 * fmaf(__uint_as_float(rd[i]), sc, -ds.x),
+                                 p1 * fmaf(__uint_as_float(rd[i + 1]), sc, -ds.y));
         }
         st_row_chunk(sPT, r, c, pp);
         st_row_chunk(sDST, r, c, pd);
