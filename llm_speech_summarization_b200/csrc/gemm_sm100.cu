@@ -328,6 +328,7 @@ __device__ __forceinline__ void emit_h16(uint32_t stg, const float (&v)[32], int
 // MODE 1: K-major operands + split-K, the accumulate epilogue, per-group output offsets and the pre-activation copy
 //         (training forward, decode).
 // MODE 2: MODE 1 with an MN-major B operand (dgrad).   MODE 3: both operands MN-major, reduction over batches (wgrad).
+// MODE 4: MODE 2 whose plain 16-bit / fp32 output leaves through TMA like MODE 0's (the encoder's dgrad GEMMs).
 // Operand major-ness is a compile-time property so the single-thread producer / MMA-issue loops stay branch-free.
 template <int BN, int CG, int MODE>
 __global__ void __launch_bounds__(kThreads<MODE>, 1)
@@ -337,6 +338,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   constexpr int kStages = C::kStages;
   constexpr bool EXT = MODE >= 1;
   constexpr bool kAmn = MODE == 3, kBmn = MODE >= 2;
+  constexpr bool kTma = MODE == 0 || MODE == 4;  // plain outputs leave through TMA stores / reductions
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
@@ -508,7 +510,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t stg = stage_base + static_cast<uint32_t>(warp - 4) * (kHalves == 2 ? 4096u : 8192u);
     uint32_t nst = 0;  // staging tiles this warp has handed to the TMA store engine (buffer = nst & 1)
-    if (!EXT && lane == 0) ptx::prefetch_tmap(&tmap_o);
+    if (kTma && lane == 0) ptx::prefetch_tmap(&tmap_o);
     int it = 0;
     for (int t = cluster_id; t < p.units; t += num_clusters, ++it) {
       const Unit un = decode_unit<EXT>(p, t);
@@ -531,8 +533,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const uint32_t taddr = tmem_base + lane_base + as * BN;
 
       if (p.epi == EPI_BF16 || p.epi == EPI_F32 || p.epi == EPI_RESID_F32 || (EXT && p.epi == EPI_ACCUM_F32)) {
-        if constexpr (!EXT) {
-        // (MODE 0: the host routes every plain epilogue it cannot express as a TMA store to the MODE 1 kernel)
+        if constexpr (kTma) {
+        // (MODE 0: the host routes every plain epilogue it cannot express as a TMA store to the MODE 1 kernel; MODE 4 is
+        // the dgrad kernel with this epilogue. Compiling both epilogues into one kernel cost the per-thread one 7-8 %
+        // through register pressure, so a kernel has exactly one of them.)
         // ---- MODE 0 plain epilogues (bf16 / fp16 / fp32 output, fp32 in-place residual): TMEM -> registers ->
         // bias / activation -> 128B-swizzled staging tile -> ONE bulk tensor store (or fp32 add-reduction at the L2 for
         // h += proj(...)) per 32-row x 128-byte tile. No per-thread global stores, no read-back of the staging tile, the
@@ -541,7 +545,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // K-slices of a tail tile: slice 0 carries the bias and (fp32 store) writes first; later slices add into it
         const bool tail_tile = t >= p.tail_first;
         const bool part = un.split > 0;
-        const bool red = p.epi == EPI_RESID_F32 || part;
+        const bool red = p.epi == EPI_RESID_F32 || p.epi == EPI_ACCUM_F32 || part;
         if (part) bias = nullptr;
         int* const tflag = p.tail_flags + 2 * (((un.tile - p.tail_first) * CG + static_cast<int>(cta_rank)) * 4 + quarter);
         if (part && p.epi == EPI_F32) {
@@ -601,10 +605,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA (async proxy) read
           __syncwarp();
-          if (lane == 0 && rows_valid > 0) {
-            if (red) ptx::tma_reduce_add_3d(&tmap_o, buf, gcol0 + c * 32, m0w, tc.b);
-            else ptx::tma_store_3d(&tmap_o, buf, gcol0 + c * 32, m0w, tc.b);
-            ptx::bulk_commit();
+          if (lane == 0) {
+            if (rows_valid > 0) {
+              if (red) ptx::tma_reduce_add_3d(&tmap_o, buf, gcol0 + c * 32, m0w, tc.b);
+              else ptx::tma_store_3d(&tmap_o, buf, gcol0 + c * 32, m0w, tc.b);
+            }
+            ptx::bulk_commit();  // (an empty group when the warp's rows lie beyond M: the two staging tiles' wait_group
+                                 // accounting must advance with every chunk, stored or not)
           }
           ++nst;
           (void)cw;
@@ -750,7 +757,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
       }
     }
-    if (!EXT && lane == 0) ptx::bulk_wait<0>();  // every bulk store of this warp has landed before the CTA retires
+    if (kTma && lane == 0) ptx::bulk_wait<0>();  // every bulk store of this warp has landed before the CTA retires
   }
 
   ptx::tc_fence_before();
@@ -1088,11 +1095,19 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   const int tma_epi = ctx().tma_epi;
   CUtensorMap to = ta;
   p.tma_out = 0;
-  if (!ext && (a.epi == EPI_BF16 || a.epi == EPI_F32 || a.epi == EPI_RESID_F32)) {
+  {
+    // what a tensor-map store / reduction can express: one [batches][M][groups * N] view of the output, no second
+    // output, no per-group row offsets, no dropout; the residual only in place (a reduction cannot read another tensor)
+    const bool plain = a.epi == EPI_BF16 || a.epi == EPI_F32 || a.epi == EPI_RESID_F32 || a.epi == EPI_ACCUM_F32;
     const bool inplace = a.epi == EPI_RESID_F32 && static_cast<const void*>(a.resid) == a.out && !a.resid_bcast &&
                          resid_red != 0;
-    const bool ok = tma_epi != 0 && (a.epi != EPI_RESID_F32 || inplace);
-    if (ok) {
+    // MODE 0 (K-major, unsplit) and the dgrad form (MN-major B, plain store). The fp32 accumulation of wgrad / split-K
+    // stays on red.global: as a TMA reduction it measured 4 % slower on the 15968-row wgrads (round 2).
+    const bool kernel_ok = !ext || (a.b_mn && !a.a_mn && p.k_splits == 1 && (a.epi == EPI_BF16 || a.epi == EPI_F32));
+    const bool view_ok = a.out2 == nullptr && a.out_group_rows == 0 &&
+                         (a.out_group_cols == 0 || a.out_group_cols == a.N) && a.drop_thresh == 0u &&
+                         a.epi != EPI_ACCUM_F32;
+    if (plain && kernel_ok && view_ok && tma_epi != 0 && (a.epi != EPI_RESID_F32 || inplace)) {
       const bool h16 = a.epi == EPI_BF16;
       const cuuint64_t elt = h16 ? 2 : 4;
       const cuuint64_t cols = a.groups > 1 ? static_cast<cuuint64_t>(a.groups) * a.N : static_cast<cuuint64_t>(a.N);
@@ -1105,9 +1120,10 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
                                          : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
       if (row_bytes % 16 == 0 && encode_map(&to, a.out, 3, dims, strides, box, dt) == B2S_OK) p.tma_out = 1;
     }
-    if (!p.tma_out) ext = true;
+    // MODE 0 has no per-thread plain epilogue: a K-major, unsplit problem that cannot use TMA runs as MODE 1
+    if (!ext && !p.tma_out && plain) ext = true;
   }
-  const int mode = a.a_mn ? 3 : (a.b_mn ? 2 : (ext ? 1 : 0));
+  const int mode = a.a_mn ? 3 : (a.b_mn ? (p.tma_out ? 4 : 2) : (ext ? 1 : 0));
   // Tail split (MODE 0, fp32 outputs that leave through TMA): see KParams. Only the last, partly filled round is cut, into
   // at most 4 K-slices of at least 8 k-blocks, one slice per cluster, so the round costs 1/S of a tile (+ one epilogue).
   p.units = p.total_tiles;
@@ -1142,6 +1158,7 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
       case 0: return launch_cfg<BN_, CG_, 0>(ta, tw, to, p, stream);     \
       case 1: return launch_cfg<BN_, CG_, 1>(ta, tw, to, p, stream);     \
       case 2: return launch_cfg<BN_, CG_, 2>(ta, tw, to, p, stream);     \
+      case 4: return launch_cfg<BN_, CG_, 4>(ta, tw, to, p, stream);     \
       default: return launch_cfg<BN_, CG_, 3>(ta, tw, to, p, stream);    \
     }                                                                    \
   }
