@@ -106,8 +106,11 @@ def write_gemm_shapes(lib, n, path, steps):
 
 def loss_roofline(step, lib, _lib, resident0, plan0, dev, peaks):
     """The HBM-bound kernel the north star names: the fused CE + KD forward (kd_ce_partial + kd_ce_finalize) timed alone
-    on the step's own logits; 256 MB rewritten before every launch (> 126 MB L2); straight through the C ABI with
-    pre-allocated outputs so no allocator work sits between the event pair."""
+    on the step's own logits, straight through the C ABI with pre-allocated outputs so no allocator work sits between the
+    event pair. L2: the launch streams 1.05 GB of logits once, front to back (8x the 126 MB L2), so a launch finds none of
+    its input cached by the previous one; the 256 MB rewrite used in round 1 is kept for the first launch only -- done
+    before EVERY launch it left ~100 MB of dirty lines whose write-back competed with the kernel's reads (0.74-0.77 of
+    peak against 0.93 for the same kernel under ncu's cache control)."""
     import ctypes as C
     kept = step.forward_losses(*resident0, plan=plan0, keep=True)
     s_log, t_log, pl = kept["student_logits"], kept["teacher_logits"], kept["plan"]
@@ -119,8 +122,9 @@ def loss_roofline(step, lib, _lib, resident0, plan0, dev, peaks):
     lse_s, lse_t, ck, cc, ld_o, ntp_o = f32(rows_l), f32(rows_l), f32(rows_l), f32(rows_l), f32(n_utt), f32(n_utt)
     st_l = torch.cuda.current_stream().cuda_stream
     evs, loss_launches = [], 0
+    flush.zero_()
+    torch.cuda.synchronize()
     for _ in range(3 + 10):
-        flush.zero_()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches_l0 = lib.b2s_launch_count()
         a.record()
@@ -275,7 +279,13 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_mark = index, [], None, None
+
+    def mark(self):
+        """The timed region starts now: rows that arrive later are the ones reported. (nvidia-smi takes a few hundred ms to
+        produce its first row on an 8-GPU box, so the sampler is started before the warm-up steps -- same load -- and a
+        short timed region that caught no row of its own falls back to the warm-up rows and says so.)"""
+        self.t_mark = time.time()
 
     def start(self):
         try:
@@ -288,20 +298,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        timed = [r for t, r in self.rows if self.t_mark is None or t >= self.t_mark]
+        window = "timed region"
+        if len(timed) < 2 and self.rows:
+            timed, window = [r for _, r in self.rows], "warm-up + timed region (the timed region is shorter than the sampler's period)"
+        sm = [float(r[0]) for r in timed if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in timed if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in timed)]
         busy = sorted(sm)[len(sm) // 2:] if sm else []
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
@@ -384,14 +398,16 @@ def gemm_flops_per_utt(train=False, infer=False):
 
 def timed_loop(run, steps, warmup, dp, dev, lib, clock_index=None):
     """W untimed + K timed steps bracketed by barrier + synchronize; CUDA-event time, max over ranks."""
-    for i in range(warmup):
-        run(i)
-    torch.cuda.synchronize()
-    dp.barrier()
     clocks = None
     if clock_index is not None:
         clocks = ClockSampler(clock_index)
         clocks.start()
+    for i in range(warmup):
+        run(i)
+    torch.cuda.synchronize()
+    dp.barrier()
+    if clocks is not None:
+        clocks.mark()
     launches0 = lib.b2s_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -772,7 +788,7 @@ def main():
                                   "applies; `hot` is the same measurement right after the timed steps, under the "
                                   "power cap (the kernel issues 2 MUFU.EX2 per logit pair and is SM-clock sensitive)",
                          "hot": {k: hot[k] for k in ("achieved", "frac", "ms")},
-                         "l2": "256 MB buffer rewritten before every timed launch",
+                         "l2": "inputs larger than L2: every launch streams 1.05 GB of logits once (8x the 126 MB L2); no flush between launches",
                          "traffic": (tr_b * loss_alone["rows"] / 2048.0) if tr_b else None,
                          "traffic_source": (tr_src + ", scaled from the profiled 2048 rows") if tr_src else None,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback"}
