@@ -108,7 +108,13 @@ int b2s_comm_init(const uint8_t* id, int32_t rank, int32_t world) {
   c.comm = comm;
   c.comm_rank = rank;
   c.comm_world = world;
-  B2S_CUDA_CHECK(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+  {
+    // highest priority: when an SM frees a slot, a waiting NCCL CTA is placed before the next compute block, so the
+    // exchange keeps pace with the backward it hides behind instead of queueing behind whole compute grids
+    int prio_lo = 0, prio_hi = 0;
+    B2S_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    B2S_CUDA_CHECK(cudaStreamCreateWithPriority(&c.comm_stream, cudaStreamNonBlocking, prio_hi));
+  }
   B2S_CUDA_CHECK(cudaEventCreateWithFlags(&c.comm_done, cudaEventDisableTiming));
   return B2S_OK;
 }
