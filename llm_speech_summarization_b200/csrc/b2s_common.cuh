@@ -207,6 +207,7 @@ __device__ __forceinline__ void ld8h(const __nv_bfloat16* p, float (&f)[8], int 
 __device__ __forceinline__ void st8h(__nv_bfloat16* p, const float (&f)[8], int f16) {
   *reinterpret_cast<uint4*>(p) = pack8_h16(f, f16);
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float h16_to_float(uint16_t bits, int f16) {
   return f16 ? __half2float(__ushort_as_half(bits)) : __uint_as_float(static_cast<uint32_t>(bits) << 16);
 }

@@ -51,6 +51,21 @@ layernorm_bwd_ex_kernel(const void* __restrict__ x, int x_bf16, const float* __r
        row += static_cast<long long>(gridDim.x) * kWarps) {
     float xv[GROUPS][8], dv[GROUPS][8];
     float s = 0.f;
+    if constexpr (GROUPS >= 4) {
+      // the warp's NEXT row is requested into L2 now: with 8 resident warps per SM (the registers are all taken) nothing
+      // else overlaps DRAM latency with this row's three reductions (15968 x 1024: 84 -> 74 us; at 512 columns, where
+      // twice the warps are resident, the same prefetch cost 30 %)
+      const long long nrow = row + static_cast<long long>(gridDim.x) * kWarps;
+      if (nrow < rows) {
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g) {
+          const long long e = nrow * C + (g * 32 + lane) * 8;
+          prefetch_l2(reinterpret_cast<const char*>(x) + e * (x_bf16 ? 2 : 4));
+          prefetch_l2(reinterpret_cast<const char*>(dy) + e * (dy_bf16 ? 2 : 4));
+          if (dh != nullptr && accumulate) prefetch_l2(dh + e);
+        }
+      }
+    }
 #pragma unroll
     for (int g = 0; g < GROUPS; ++g) {
       const int c = (g * 32 + lane) * 8;
