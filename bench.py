@@ -88,7 +88,7 @@ def write_gemm_shapes(lib, n, path, steps):
         a[0] += 1
         a[1] += ms.value
     epi = {0: "bf16", 1: "resid_f32", 2: "swiglu", 3: "rope", 4: "f32", 5: "accum_f32"}
-    mode = {0: "fwd", 1: "fwd+", 2: "dgrad", 3: "wgrad", 4: "dgrad"}  # 4 = dgrad with the TMA-store epilogue
+    mode = {0: "fwd", 1: "fwd+", 2: "dgrad", 3: "wgrad", 4: "dgrad", 5: "fwd8"}  # 4 = dgrad with the TMA-store epilogue
     rows = []
     for (M, N, K, b, g, e, act, md, bn, cg), (cnt, t) in agg.items():
         fl = 2.0 * M * N * K * b * g * cnt

@@ -61,9 +61,11 @@ enum {
   B2S_OPT_ATTN_KV_STAGES = 4,
   B2S_OPT_SM_BUDGET = 5,          /* = b2s_set_sm_budget */
   B2S_OPT_GEMM_GROUP_M = 6,       /* GEMM tile order: M tiles per group, 0 = default 8 (B2S_GEMM_GROUP_M) */
-  B2S_OPT_GEMM_TAIL_SPLIT = 7     /* K-slice the tiles of a partly filled last round of the persistent GEMM grid (fp32
+  B2S_OPT_GEMM_TAIL_SPLIT = 7,    /* K-slice the tiles of a partly filled last round of the persistent GEMM grid (fp32
                                      outputs; B2S_GEMM_TAIL_SPLIT). GEMMs of ONE handle must be stream-ordered: the
                                      slices of a tile hand over through flags the handle owns. Default 1 */
+  B2S_OPT_GEMM_EPI8 = 8           /* eight epilogue warps in the forward GEMM kernel: 0 never, 1 for epilogues with an
+                                     activation and a reduction of at most 2048 (default), 2 always (B2S_GEMM_EPI8) */
 };
 int b2s_set_option(int32_t option, int32_t value); /* on the current handle; measurement A/B only */
 int b2s_get_option(int32_t option, int32_t* value);

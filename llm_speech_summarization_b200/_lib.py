@@ -229,7 +229,7 @@ PROTOTYPES = {
 }
 
 OPT_PDL, OPT_RESID_RED, OPT_TMA_EPILOGUE, OPT_ATTN_KEYS_PER_STEP, OPT_ATTN_KV_STAGES, OPT_SM_BUDGET, OPT_GEMM_GROUP_M, \
-    OPT_GEMM_TAIL_SPLIT = range(8)
+    OPT_GEMM_TAIL_SPLIT, OPT_GEMM_EPI8 = range(9)
 COMM_ID_BYTES = 128
 
 _lib = None

@@ -32,6 +32,7 @@ Context::Context() {
   if (const char* e = getenv("B2S_ATTN_CFG")) sscanf(e, "%d,%d", &attn_bn, &attn_kvs);
   gemm_group_m = env_int("B2S_GEMM_GROUP_M", 0);
   gemm_tail_split = env_int("B2S_GEMM_TAIL_SPLIT", 1) != 0;
+  gemm_epi8 = env_int("B2S_GEMM_EPI8", 1);
 }
 
 Context& ctx() { return g_current != nullptr ? *g_current : default_context(); }
@@ -183,6 +184,7 @@ int b2s_set_option(int32_t option, int32_t value) {
     case B2S_OPT_SM_BUDGET: c.sm_budget = value > 0 ? value : 0; break;
     case B2S_OPT_GEMM_GROUP_M: c.gemm_group_m = value > 0 ? value : 0; break;
     case B2S_OPT_GEMM_TAIL_SPLIT: c.gemm_tail_split = value != 0; break;
+    case B2S_OPT_GEMM_EPI8: c.gemm_epi8 = value < 0 ? 0 : (value > 2 ? 2 : value); break;
     default:
       set_last_error("b2s_set_option: unknown option %d", option);
       return B2S_ERR_INVALID;
@@ -204,6 +206,7 @@ int b2s_get_option(int32_t option, int32_t* value) {
     case B2S_OPT_SM_BUDGET: *value = c.sm_budget; break;
     case B2S_OPT_GEMM_GROUP_M: *value = c.gemm_group_m; break;
     case B2S_OPT_GEMM_TAIL_SPLIT: *value = c.gemm_tail_split; break;
+    case B2S_OPT_GEMM_EPI8: *value = c.gemm_epi8; break;
     default:
       set_last_error("b2s_get_option: unknown option %d", option);
       return B2S_ERR_INVALID;

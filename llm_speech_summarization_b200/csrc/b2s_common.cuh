@@ -53,6 +53,7 @@ struct Context {
   int attn_bn = 0, attn_kvs = 0;  // attention forward tile override (B2S_ATTN_CFG="keys per step,K/V stages"; 0 = auto)
   int sm_budget = 0;    // SMs the persistent kernels size their grids for (0 = all)
   int gemm_group_m = 0; // GEMM tile-order override: M tiles per group (0 = the default of 8, gemm_sm100.cu)
+  int gemm_epi8 = 1;        // eight epilogue warps for short reductions (B2S_GEMM_EPI8: 0 never, 1 activation + K <= 2048, 2 always)
   int gemm_tail_split = 1;  // K-slice the tiles of a partly filled last round (B2S_GEMM_TAIL_SPLIT; gemm_sm100.cu)
   int* tail_flags = nullptr;  // device flags of the tail split (slice 0 stored -> later slices may add); owned
   int tail_flags_dev = -1;

@@ -37,11 +37,12 @@ namespace {
 constexpr int kBlockK = 64;           // bf16 elements = 128 bytes = one swizzle atom
 constexpr int kUmmaK = 16;
 // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare; then the epilogue warps, one per TMEM lane quarter.
-// (Eight epilogue warps -- two per quarter, each taking half of the tile's columns -- are supported by the code below and
-// were measured on B200 in round 2 with the TMA-store epilogue: every K = 1024 shape got slower (FFN1 843 -> 818, QKV
-// 980 -> 873 TFLOP/s; 168 registers per thread instead of 255), so four it stays.)
+// Eight epilogue warps -- two per TMEM lane quarter, each taking half of the tile's columns -- are MODE 5 (= MODE 0
+// otherwise), chosen by the host for short reductions where the epilogue, not the mainloop, is the critical path. Their
+// first form (round 2, both 32-column chunks of a 16-bit staging tile in registers at once) spilled at the 168 registers
+// 384 threads leave and was slower on every shape; MODE 5 stages one chunk at a time.
 template <int MODE>
-constexpr int kEpiWarps = 4;
+constexpr int kEpiWarps = (MODE == 5) ? 8 : 4;
 template <int MODE>
 constexpr int kThreads = 128 + 32 * kEpiWarps<MODE>;
 constexpr int kATileBytes = 128 * kBlockK * 2;  // 16 KiB per CTA per stage
@@ -336,9 +337,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                          const __grid_constant__ CUtensorMap tmap_o, const KParams p) {
   using C = Cfg<BN, CG>;
   constexpr int kStages = C::kStages;
-  constexpr bool EXT = MODE >= 1;
-  constexpr bool kAmn = MODE == 3, kBmn = MODE >= 2;
-  constexpr bool kTma = MODE == 0 || MODE == 4;  // plain outputs leave through TMA stores / reductions
+  constexpr bool EXT = MODE >= 1 && MODE <= 4;
+  constexpr bool kAmn = MODE == 3, kBmn = MODE >= 2 && MODE <= 4;
+  constexpr bool kTma = MODE == 0 || MODE == 4 || MODE == 5;  // plain outputs leave through TMA stores / reductions
 
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
@@ -547,7 +548,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const bool part = un.split > 0;
         const bool red = p.epi == EPI_RESID_F32 || p.epi == EPI_ACCUM_F32 || part;
         if (part) bias = nullptr;
-        int* const tflag = p.tail_flags + 2 * (((un.tile - p.tail_first) * CG + static_cast<int>(cta_rank)) * 4 + quarter);
+        int* const tflag = p.tail_flags +
+                           2 * ((((un.tile - p.tail_first) * CG + static_cast<int>(cta_rank)) * 4 + quarter) * 2 + half);
         if (part && p.epi == EPI_F32) {
           if (lane == 0) {
             while (ptx::ld_acquire_gpu(tflag) == 0) __nanosleep(64);
@@ -558,6 +560,52 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int cw = h16 ? 64 : 32;  // output columns per staging tile
         const int gcol0 = tc.g * p.N + ncol0;
         constexpr int kChunksPerWarp = (BN / 32) / kHalves;  // 32-column TMEM chunks this warp drains
+        if constexpr (kHalves == 2) {
+          // eight warps: one staging tile per warp, ONE 32-column chunk in registers at a time (a 16-bit tile is filled by
+          // two consecutive chunks, left then right half of its 128-byte rows)
+#pragma unroll 1
+          for (int c = half * kChunksPerWarp; c < (half + 1) * kChunksPerWarp; c += (h16 ? 2 : 1)) {
+            const int col = ncol0 + c * 32;
+            if (col >= p.N) break;
+            if (lane == 0) ptx::bulk_wait_read<0>();  // the store that last used this tile has read it
+            __syncwarp();
+#pragma unroll 1
+            for (int hc = 0; hc < (h16 ? 2 : 1); ++hc) {
+              uint32_t raw[32];
+              ptx::tmem_ld_32x32(taddr + (c + hc) * 32, raw);
+              ptx::tmem_ld_wait();
+              float v[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+              const int cc = col + 32 * hc;
+              add_bias_act(v, (bias && cc < p.N) ? bias + cc : nullptr, p.act, p.N - cc);
+              if (h16) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float* s8 = &v[8 * q];
+                  const uint32_t addr = stg + lane * 128 + (((4 * hc + q) ^ (lane & 7)) << 4);
+                  const uint32_t w0 = p.out_f16 ? pack_f16(s8[0], s8[1]) : pack_bf16(s8[0], s8[1]);
+                  const uint32_t w1 = p.out_f16 ? pack_f16(s8[2], s8[3]) : pack_bf16(s8[2], s8[3]);
+                  const uint32_t w2 = p.out_f16 ? pack_f16(s8[4], s8[5]) : pack_bf16(s8[4], s8[5]);
+                  const uint32_t w3 = p.out_f16 ? pack_f16(s8[6], s8[7]) : pack_bf16(s8[6], s8[7]);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                               : "memory");
+                }
+              } else {
+                stage_write(stg, v, lane);
+              }
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (rows_valid > 0) {
+                if (red) ptx::tma_reduce_add_3d(&tmap_o, stg, gcol0 + c * 32, m0w, tc.b);
+                else ptx::tma_store_3d(&tmap_o, stg, gcol0 + c * 32, m0w, tc.b);
+              }
+              ptx::bulk_commit();
+            }
+          }
+        } else {
 #pragma unroll 1
         for (int c = half * kChunksPerWarp; c < (half + 1) * kChunksPerWarp; c += (h16 ? 2 : 1)) {
           const int col = ncol0 + c * 32;
@@ -615,6 +663,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           ++nst;
           (void)cw;
+        }
         }
         if (tail_tile && p.epi == EPI_F32 && lane == 0) {
           if (!part) {
@@ -812,7 +861,7 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
   return B2S_OK;
 }
 
-constexpr size_t kTailFlagBytes = 148 * 2 * 4 * 2 * sizeof(int);  // tiles of one round x CTAs x epilogue warps x {ready, count}
+constexpr size_t kTailFlagBytes = 148 * 2 * 8 * 2 * sizeof(int);  // tiles of one round x CTAs x epilogue warps (<= 8) x {ready, count}
 
 int ensure_tail_flags() {
   Context& c = ctx();
@@ -1123,7 +1172,16 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
     // MODE 0 has no per-thread plain epilogue: a K-major, unsplit problem that cannot use TMA runs as MODE 1
     if (!ext && !p.tma_out && plain) ext = true;
   }
-  const int mode = a.a_mn ? 3 : (a.b_mn ? (p.tma_out ? 4 : 2) : (ext ? 1 : 0));
+  int mode = a.a_mn ? 3 : (a.b_mn ? (p.tma_out ? 4 : 2) : (ext ? 1 : 0));
+  // short reductions with an ACTIVATION in a plain epilogue are bound by the epilogue's arithmetic (16 k-blocks of MMA
+  // against 256 erf-GELUs per epilogue thread): eight epilogue warps (MODE 5) hide its latencies better -- FFN1 + GELU
+  // 756 -> 805 TFLOP/s inside the step. Without an activation the same eight warps LOSE 2-9 % (QKV 928 -> 909, out-proj
+  // 599 -> 574, conv 1150 -> 1046: more barrier traffic, one staging tile per warp), so they stay on four.
+  // B2S_OPT_GEMM_EPI8: 0 = never, 1 = activation and K <= 2048 (default), 2 = every plain MODE 0 launch (tests)
+  if (mode == 0 && (a.epi == EPI_BF16 || a.epi == EPI_F32 || a.epi == EPI_RESID_F32)) {
+    const int e8 = ctx().gemm_epi8;
+    if (e8 == 2 || (e8 == 1 && p.num_kb <= 32 && a.act != ACT_NONE)) mode = 5;
+  }
   // Tail split (MODE 0, fp32 outputs that leave through TMA): see KParams. Only the last, partly filled round is cut, into
   // at most 4 K-slices of at least 8 k-blocks, one slice per cluster, so the round costs 1/S of a tile (+ one epilogue).
   p.units = p.total_tiles;
@@ -1131,7 +1189,7 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
   p.tail_split = 1;
   p.tail_kb = p.num_kb;
   p.tail_flags = nullptr;
-  if (mode == 0 && p.tma_out && ctx().gemm_tail_split && a.act == ACT_NONE && (a.epi == EPI_F32 || a.epi == EPI_RESID_F32)) {
+  if ((mode == 0 || mode == 5) && p.tma_out && ctx().gemm_tail_split && a.act == ACT_NONE && (a.epi == EPI_F32 || a.epi == EPI_RESID_F32)) {
     const int G = num_sms() / cg;
     const int tail = G > 0 ? p.total_tiles % G : 0;
     const int full = p.total_tiles - tail;
@@ -1159,6 +1217,7 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
       case 1: return launch_cfg<BN_, CG_, 1>(ta, tw, to, p, stream);     \
       case 2: return launch_cfg<BN_, CG_, 2>(ta, tw, to, p, stream);     \
       case 4: return launch_cfg<BN_, CG_, 4>(ta, tw, to, p, stream);     \
+      case 5: return launch_cfg<BN_, CG_, 5>(ta, tw, to, p, stream);     \
       default: return launch_cfg<BN_, CG_, 3>(ta, tw, to, p, stream);    \
     }                                                                    \
   }

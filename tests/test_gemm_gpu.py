@@ -335,3 +335,37 @@ def test_gemm_store_epilogue_is_repeatable_with_rows_beyond_m(cuda, epi):
             assert torch.equal(out, first)
     finally:
         _set_tail_split(old)
+
+
+@pytest.mark.parametrize("epi,act", [("h16", "gelu"), ("h16", "none"), ("f32", "none"), ("resid", "none")])
+def test_gemm_eight_epilogue_warps_match_four(cuda, epi, act):
+    """MODE 5 (two epilogue warps per TMEM lane quarter, one 32-column chunk staged at a time) against the four-warp
+    kernel and the torch reference, on an encoder-shaped problem with ragged M / N edges."""
+    from llm_speech_summarization_b200 import _lib, ops
+    lib = _lib.load()
+    M, N, K = 1497, 4096 - 24, 1024
+    a, w, b = _mk(M, N, K, cuda, seed=5)
+    ref = a.float() @ w.float().t() + b
+    if act == "gelu":
+        ref = F.gelu(ref)
+    h0 = torch.randn(M, N, device=cuda)
+    outs = []
+    for force in (2, 0):
+        _lib.check(lib.b2s_set_option(_lib.OPT_GEMM_EPI8, force), "set_option")
+        try:
+            kw = dict(bias=b, act=ops.ACT_GELU if act == "gelu" else ops.ACT_NONE)
+            if epi == "h16":
+                out = ops.gemm(a, w, epi=ops.EPI_BF16, **kw).float()
+            elif epi == "f32":
+                out = ops.gemm(a, w, epi=ops.EPI_F32, **kw)
+            else:
+                out = h0.clone()
+                ops.gemm(a, w, epi=ops.EPI_RESID_F32, resid=out, out=out, **kw)
+                out = out - h0
+            outs.append(out)
+        finally:
+            _lib.check(lib.b2s_set_option(_lib.OPT_GEMM_EPI8, 1), "set_option")
+    tol = TOL_BF16 if epi == "h16" else (TOL_F32 if epi == "f32" else 2e-4)
+    assert rel_l2(outs[0], ref) < tol and rel_l2(outs[1], ref) < tol
+    if epi != "resid":
+        assert torch.equal(outs[0], outs[1])  # same arithmetic, only the warp that stores a column differs
