@@ -512,7 +512,10 @@ int b2s_layernorm_bwd(const float* x, const float* gamma, float eps, const void*
                       int32_t accumulate, void* dh_bf16, float* dgamma, float* dbeta, int64_t rows, int32_t C,
                       int32_t fmt, void* stream);
 int b2s_swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t rows, int32_t F, int32_t fmt, void* stream);
-int b2s_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, int32_t fmt, void* stream);
+/* dpre = dy * gelu'(pre) (erf form). colsum (optional, with the row width F, F % 2048 == 0): += column sums of dpre, the
+ * bias gradient of the Linear that produced `pre`, accumulated by the same pass. */
+int b2s_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, int32_t fmt, float* colsum, int32_t F,
+                 void* stream);
 int b2s_gather_rows_f32(const float* src, const int32_t* index, float* out, int64_t rows, int32_t C, void* stream);
 /* Dynamic loss scaling, torch.cuda.amp.GradScaler semantics (REF/trainer.py:252,374,381-382), with its state in DEVICE
  * memory so that neither the skip-on-overflow decision nor the scale update synchronises the host:

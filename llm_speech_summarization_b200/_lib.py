@@ -188,7 +188,7 @@ PROTOTYPES = {
     "b2s_layernorm_bwd": (c_int, [P_f32, P_f32, c_float, c_void_p, c_int, P_f32, c_int, c_void_p, P_f32, P_f32,
                                   c_int64, c_int, c_int, c_void_p]),
     "b2s_swiglu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
-    "b2s_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "b2s_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
     "b2s_gather_rows_f32": (c_int, [P_f32, P_int, P_f32, c_int64, c_int, c_void_p]),
     "b2s_whisper_log_mel": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b2s_llama_kv_cache_bytes": (C.c_size_t, [C.POINTER(LlamaWeights), c_int]),

@@ -416,8 +416,9 @@ int b2s_layernorm_bwd(const float* x, const float* gamma, float eps, const void*
 int b2s_swiglu_bwd(const void* gu, const void* dact, void* dgu, int64_t rows, int32_t F, int32_t fmt, void* stream) {
   return swiglu_bwd(gu, dact, dgu, rows, F, fmt, S(stream));
 }
-int b2s_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, int32_t fmt, void* stream) {
-  return gelu_bwd(pre, dy, dpre, n, fmt, S(stream));
+int b2s_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, int32_t fmt, float* colsum, int32_t F,
+                 void* stream) {
+  return gelu_bwd(pre, dy, dpre, n, fmt, S(stream), nullptr, colsum, F);
 }
 int b2s_gather_rows_f32(const float* src, const int32_t* index, float* out, int64_t rows, int32_t C, void* stream) {
   return gather_rows_f32(src, index, out, rows, C, S(stream));

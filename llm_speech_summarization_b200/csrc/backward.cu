@@ -184,6 +184,40 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __re
   st8h(dpre + i * 8, d, f16);
 }
 
+// The same with the column sums of dpre (the bias gradient) accumulated on the way: a thread keeps the SAME 8 columns for
+// every row it visits (256 threads = 2048 columns, F / 2048 blocks side by side, the rest of the grid strides over rows),
+// so the sums are 8 registers and one atomic per column per block.
+__global__ void __launch_bounds__(256)
+gelu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dy,
+                       __nv_bfloat16* __restrict__ dpre, long long rows, int F, float* __restrict__ colsum,
+                       DropSpec drop, int f16) {
+  pdl_trigger();
+  const int tpr = F / 8, bpr = tpr / 256;
+  const int cg = (blockIdx.x % bpr) * 256 + threadIdx.x;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (long long row = blockIdx.x / bpr; row < rows; row += gridDim.x / bpr) {
+    const long long i = row * tpr + cg;
+    float x[8], d[8];
+    ld8h(pre + i * 8, x, f16);
+    ld8h(dy + i * 8, d, f16);
+    if (drop.thresh != 0u) {
+      const uint32_t e0 = static_cast<uint32_t>(i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = rng_keep(e0 + j, drop.k1, drop.k2, drop.thresh) ? d[j] * drop.inv_keep : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      d[j] *= gelu_erf_grad(x[j]);
+      acc[j] += d[j];
+    }
+    st8h(dpre + i * 8, d, f16);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(colsum + cg * 8 + j, acc[j]);
+}
+
 // dh[rows_a[i]] += c * (h[rows_a[i]] - h[rows_b[i]])  (feature-distillation MSE backward, REF/trainer.py:358-370)
 __global__ void __launch_bounds__(256)
 add_rowdiff_kernel(const float* __restrict__ h, const int* __restrict__ rows_a, const int* __restrict__ rows_b,
@@ -233,7 +267,7 @@ gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ index,
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2,
-             float grad_scale, const GradScalerState* __restrict__ scaler) {
+             float grad_scale, const GradScalerState* __restrict__ scaler, int vec) {
   if (scaler != nullptr) {  // block-uniform: one thread evaluates the state, everybody reads it from shared memory
     __shared__ float s_par[3];
     __shared__ int s_skip;
@@ -250,16 +284,36 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     bc1 = s_par[1];
     bc2 = s_par[2];
   }
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float gr = g[i] * grad_scale;
-  float pv = p[i] * (1.0f - lr * wd);
-  const float mv = beta1 * m[i] + (1.0f - beta1) * gr;
-  const float vv = beta2 * v[i] + (1.0f - beta2) * gr * gr;
-  m[i] = mv;
-  v[i] = vv;
-  pv -= lr * (mv / bc1) / (sqrtf(vv / bc2) + eps);
-  p[i] = pv;
+  // grid-stride over float4 groups (the scaler prologue above is paid once per block, not once per 256 elements), then
+  // the scalar tail; `vec` = all four buffers 16-byte aligned
+  auto upd = [&](float& pv, float gr, float& mv, float& vv) {
+    gr *= grad_scale;
+    pv *= (1.0f - lr * wd);
+    mv = beta1 * mv + (1.0f - beta1) * gr;
+    vv = beta2 * vv + (1.0f - beta2) * gr * gr;
+    pv -= lr * (mv / bc1) / (sqrtf(vv / bc2) + eps);
+  };
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = gid; i < n4; i += stride) {
+    float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    const float4 G = __ldg(reinterpret_cast<const float4*>(g) + i);
+    upd(P.x, G.x, M.x, V.x);
+    upd(P.y, G.y, M.y, V.y);
+    upd(P.z, G.z, M.z, V.z);
+    upd(P.w, G.w, M.w, V.w);
+    reinterpret_cast<float4*>(m)[i] = M;
+    reinterpret_cast<float4*>(v)[i] = V;
+    reinterpret_cast<float4*>(p)[i] = P;
+  }
+  for (long long i = n4 * 4 + gid; i < n; i += stride) {
+    float pv = p[i], mv = m[i], vv = v[i];
+    upd(pv, g[i], mv, vv);
+    m[i] = mv;
+    v[i] = vv;
+    p[i] = pv;
+  }
 }
 
 // found_inf |= any non-finite element of g (the unscale_ + inf check of GradScaler, fused: nothing is rewritten)
@@ -348,11 +402,24 @@ int swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows, int 
 }
 
 int gelu_bwd(const void* pre, const void* dy, void* dpre, long long n, int fmt, cudaStream_t stream,
-             const DropSpec* drop) {
+             const DropSpec* drop, float* colsum, int F) {
   B2S_REQUIRE(pre && dy && dpre, "gelu_bwd: null pointer");
   B2S_REQUIRE(n % 8 == 0, "gelu_bwd: element count must be a multiple of 8");
   B2S_REQUIRE(drop == nullptr || n < (1LL << 32), "gelu_bwd: dropout element index exceeds 32 bits");
   if (n <= 0) return B2S_OK;
+  if (colsum != nullptr) {
+    B2S_REQUIRE(F > 0 && F % 2048 == 0 && n % F == 0, "gelu_bwd: the fused column sum needs a row width that is a multiple of 2048");
+    const int bpr = F / 2048;
+    const long long rows = n / F;
+    long long per_col = 4LL * num_sms() / bpr;  // four 256-thread blocks per SM
+    if (per_col > rows) per_col = rows;
+    if (per_col < 1) per_col = 1;
+    gelu_bwd_colsum_kernel<<<static_cast<unsigned>(per_col * bpr), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<const __nv_bfloat16*>(dy),
+        reinterpret_cast<__nv_bfloat16*>(dpre), rows, F, colsum, drop ? *drop : DropSpec{}, fmt);
+    B2S_LAUNCH_CHECK();
+    return B2S_OK;
+  }
   gelu_bwd_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<const __nv_bfloat16*>(dy),
       reinterpret_cast<__nv_bfloat16*>(dpre), n / 8, drop ? *drop : DropSpec{}, fmt);
@@ -386,8 +453,14 @@ int adamw_step(float* p, const float* g, float* m, float* v, long long n, float 
   if (n <= 0) return B2S_OK;
   const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
-  adamw_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps,
-                                                                           weight_decay, bc1, bc2, grad_scale, scaler);
+  const int vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                    reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  long long blocks = ((vec ? n / 4 : n) + 255) / 256;
+  const long long cap = 16LL * num_sms();
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  adamw_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1,
+                                                                  bc2, grad_scale, scaler, vec);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

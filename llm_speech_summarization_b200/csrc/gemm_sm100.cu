@@ -863,7 +863,9 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
 
 constexpr size_t kTailFlagBytes = 148 * 2 * 8 * 2 * sizeof(int);  // tiles of one round x CTAs x epilogue warps (<= 8) x {ready, count}
 
-int ensure_tail_flags() {
+// (zeroed on the launching stream, not with a synchronous memset: the first tail-split GEMM of a process may be issued
+// inside a stream capture, where a legacy-stream memset is an error)
+int ensure_tail_flags(cudaStream_t stream) {
   Context& c = ctx();
   int dev = 0;
   B2S_CUDA_CHECK(cudaGetDevice(&dev));
@@ -871,7 +873,7 @@ int ensure_tail_flags() {
   if (c.tail_flags != nullptr) cudaFree(c.tail_flags);
   c.tail_flags = nullptr;
   B2S_CUDA_CHECK(cudaMalloc(&c.tail_flags, kTailFlagBytes));
-  B2S_CUDA_CHECK(cudaMemset(c.tail_flags, 0, kTailFlagBytes));
+  B2S_CUDA_CHECK(cudaMemsetAsync(c.tail_flags, 0, kTailFlagBytes, stream));
   c.tail_flags_dev = dev;
   return B2S_OK;
 }
@@ -1198,7 +1200,7 @@ int gemm_bf16_launch(const GemmArgs& a, cudaStream_t stream) {
       if (S > 4) S = 4;
       if (S > p.num_kb / 8) S = p.num_kb / 8;
       if (S >= 2) {
-        const int rc = ensure_tail_flags();
+        const int rc = ensure_tail_flags(stream);
         if (rc != B2S_OK) return rc;
         p.tail_kb = (p.num_kb + S - 1) / S;
         p.tail_split = (p.num_kb + p.tail_kb - 1) / p.tail_kb;

@@ -72,8 +72,10 @@ int layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy,
                   void* dh_bf16, float* dgamma, float* dbeta, long long rows, int C, int fmt, cudaStream_t stream);
 int swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows, int F, int fmt, cudaStream_t stream);
 // drop (optional): dy is the gradient w.r.t. dropout(gelu(pre)) of that site (element index = linear index)
+// colsum (optional, with the row width F, F % 2048 == 0): colsum[c] += sum over rows of dpre[., c] -- the bias gradient of
+// the Linear that produced `pre`, accumulated on the way instead of by a second pass over dpre
 int gelu_bwd(const void* pre, const void* dy, void* dpre, long long n, int fmt, cudaStream_t stream,
-             const DropSpec* drop = nullptr);
+             const DropSpec* drop = nullptr, float* colsum = nullptr, int F = 0);
 // dh[rows_a[i]] += coef[i] * (*loss_scale) * (h[rows_a[i]] - h[rows_b[i]]); loss_scale: optional device scalar
 int add_rowdiff(const float* h, const int* rows_a, const int* rows_b, const float* coef, const float* loss_scale,
                 float* dh, void* dh_bf16, int pairs, int C, int fmt, cudaStream_t stream);

@@ -418,9 +418,13 @@ int stack_backward(const b2s_encoder_layer* layers, const b2s_encoder_layer_grad
     RC(dgrad(b.dyb, Ly.w2, rows, H, F, EPI_BF16, b.dbig, fmt, stream));
     {
       const DropSpec dact = reg ? make_drop_spec(reg->seed, site_ff_act(l), reg->p_activation) : DropSpec{};
-      RC(gelu_bwd(ffp, b.dbig, b.dbig, rows * F, fmt, stream, dact.thresh != 0u ? &dact : nullptr));
+      if (F % 2048 == 0) {  // the bias gradient of W1 is accumulated by the same pass
+        RC(gelu_bwd(ffp, b.dbig, b.dbig, rows * F, fmt, stream, dact.thresh != 0u ? &dact : nullptr, G.b1, F));
+      } else {
+        RC(gelu_bwd(ffp, b.dbig, b.dbig, rows * F, fmt, stream, dact.thresh != 0u ? &dact : nullptr));
+        RC(colsum_accum(b.dbig, 1, G.b1, rows, F, fmt, stream));
+      }
     }
-    RC(colsum_accum(b.dbig, 1, G.b1, rows, F, fmt, stream));
     RC(layernorm_fwd(h_mid, 0, Ly.ln2_g, Ly.ln2_b, eps, 0, b.xn, rows, H, fmt, stream));
     RC(wgrad(b.dbig, b.xn, rows, F, H, G.w1, fmt, stream));
     RC(dgrad(b.dbig, Ly.w1, rows, F, H, EPI_BF16, b.dsm, fmt, stream));

@@ -375,3 +375,15 @@ def conv0_bwd(wave: torch.Tensor, w: torch.Tensor, b: torch.Tensor, gamma: torch
                                          beta.data_ptr(), eps, dy.data_ptr(), frames, *[o.data_ptr() for o in outs],
                                          fmt_of(dy.dtype), _stream()), "conv0_bwd")
     return outs[0].view_as(w), outs[1], outs[2], outs[3]
+
+
+def gelu_bwd(pre: torch.Tensor, dy: torch.Tensor, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dpre = dy * gelu'(pre) (erf form) for 16-bit [rows, F] tensors of one format; `colsum` ([F] fp32, F % 2048 == 0)
+    additionally receives += the column sums of dpre (the bias gradient of the Linear that produced `pre`)."""
+    _need_cuda(pre, dy, colsum)
+    assert pre.dtype in _H16 and dy.dtype == pre.dtype and pre.is_contiguous() and dy.is_contiguous()
+    out = torch.empty_like(pre)
+    F_ = pre.shape[-1]
+    _lib.check(_lib.load().b2s_gelu_bwd(pre.data_ptr(), dy.data_ptr(), out.data_ptr(), pre.numel(), fmt_of(pre.dtype),
+                                        _ptr(colsum), F_ if colsum is not None else 0, _stream()), "gelu_bwd")
+    return out

@@ -472,3 +472,23 @@ def test_conv0_bwd_vs_autograd(cuda, dt):
                                     1e-5, dy)
     for got, ref in ((dW, w.grad.view(512, 10)), (db, b.grad), (dg, gm.grad), (dbt, bt.grad)):
         assert rel_l2(got, ref) < 5e-5
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_gelu_bwd_with_fused_bias_gradient(cuda, dt):
+    """dpre = dy * gelu'(pre) against autograd, plain and with the column sums (the W1 bias gradient) accumulated by the
+    same pass; 1237 rows so that the row-striding blocks of the fused form see uneven trip counts."""
+    from llm_speech_summarization_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    rows, Fd = 1237, 4096
+    pre = (torch.randn(rows, Fd, generator=g) * 1.5).to(dt).to(cuda)
+    dy = torch.randn(rows, Fd, generator=g).to(dt).to(cuda)
+    x = pre.float().requires_grad_(True)
+    F.gelu(x).backward(dy.float())
+    tol = 6e-4 if dt == torch.float16 else 4e-3
+    plain = ops.gelu_bwd(pre, dy)
+    assert rel_l2(plain.float(), x.grad) < tol
+    cs = torch.full((Fd,), 3.0, device=cuda)
+    fused = ops.gelu_bwd(pre, dy, colsum=cs)
+    assert torch.equal(fused, plain)
+    assert rel_l2(cs - 3.0, x.grad.sum(0)) < 1e-4
