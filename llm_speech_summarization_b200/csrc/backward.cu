@@ -197,22 +197,41 @@ gelu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat1
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (long long row = blockIdx.x / bpr; row < rows; row += gridDim.x / bpr) {
-    const long long i = row * tpr + cg;
-    float x[8], d[8];
-    ld8h(pre + i * 8, x, f16);
-    ld8h(dy + i * 8, d, f16);
-    if (drop.thresh != 0u) {
-      const uint32_t e0 = static_cast<uint32_t>(i * 8);
+  // four rows per iteration: eight 16-byte loads in flight per thread (one row at a time ran at 2/3 of the plain kernel)
+  const long long rstep = gridDim.x / bpr;
+  for (long long row0 = blockIdx.x / bpr; row0 < rows; row0 += 4 * rstep) {
+    uint4 xr[4], dr[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = rng_keep(e0 + j, drop.k1, drop.k2, drop.thresh) ? d[j] * drop.inv_keep : 0.f;
+    for (int u = 0; u < 4; ++u) {
+      const long long row = row0 + u * rstep;
+      if (row < rows) {
+        const long long i = row * tpr + cg;
+        xr[u] = *reinterpret_cast<const uint4*>(pre + i * 8);
+        dr[u] = *reinterpret_cast<const uint4*>(dy + i * 8);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      d[j] *= gelu_erf_grad(x[j]);
-      acc[j] += d[j];
+    for (int u = 0; u < 4; ++u) {
+      const long long row = row0 + u * rstep;
+      if (row < rows) {
+        const long long i = row * tpr + cg;
+        float x[8], d[8];
+        unpack8_h16(xr[u], x, f16);
+        unpack8_h16(dr[u], d, f16);
+        if (drop.thresh != 0u) {
+          const uint32_t e0 = static_cast<uint32_t>(i * 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            d[j] = rng_keep(e0 + j, drop.k1, drop.k2, drop.thresh) ? d[j] * drop.inv_keep : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          d[j] *= gelu_erf_grad(x[j]);
+          acc[j] += d[j];
+        }
+        st8h(dpre + i * 8, d, f16);
+      }
     }
-    st8h(dpre + i * 8, d, f16);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) atomicAdd(colsum + cg * 8 + j, acc[j]);
