@@ -718,3 +718,17 @@ def test_handles_own_their_state():
     assert lib.b2s_comm_world(C.byref(rank), C.byref(world)) == 0 and (rank.value, world.value) == (0, 1)
     flat = (C.c_float * 4)()
     assert lib.b2s_allreduce_join(None) != 0 and b"no communicator" in lib.b2s_last_error()
+
+
+def test_option_ids_match_the_header():
+    """_lib.OPT_* are positional mirrors of the B2S_OPT_* enum in include/b2s.h: a new option added on one side only would
+    silently set a different knob."""
+    import re
+    from llm_speech_summarization_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "b2s.h")).read()
+    enum = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"B2S_OPT_([A-Z0-9_]+)\s*=\s*(\d+)", hdr))
+    mirror = {"PDL": _lib.OPT_PDL, "RESID_RED": _lib.OPT_RESID_RED, "TMA_EPILOGUE": _lib.OPT_TMA_EPILOGUE,
+              "ATTN_KEYS_PER_STEP": _lib.OPT_ATTN_KEYS_PER_STEP, "ATTN_KV_STAGES": _lib.OPT_ATTN_KV_STAGES,
+              "SM_BUDGET": _lib.OPT_SM_BUDGET, "GEMM_GROUP_M": _lib.OPT_GEMM_GROUP_M,
+              "GEMM_TAIL_SPLIT": _lib.OPT_GEMM_TAIL_SPLIT, "GEMM_EPI8": _lib.OPT_GEMM_EPI8}
+    assert enum == mirror
