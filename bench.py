@@ -369,17 +369,20 @@ WORKLOAD_TRAIN = ("configs[2] Llama-3.2-3B + HuBERT-large training step (encoder
                   "regularisers per config.regularize (none = deterministic step)")
 WORKLOAD = ("forward of configs[2]'s step = the metric's `encoder + prefill + KD loss`: Llama-3.2-3B + HuBERT-large, "
             "encoder + packed student&teacher prefill + fused CE/KD/FD loss, synthetic 10 s utterances (L_audio=200, "
-            "L_text=117, R=64)")
+            "L_text=117, R=64); the 9 prompt-prefix rows every sequence starts with are computed once per step "
+            "(config.shared_prefix_rows), which changes no consumed value")
 WORKLOAD_INFER = ("configs[1] Llama-3.2-3B + HuBERT-large audio-prompt prefill (generate_audio_response up to its first "
                   "LLM forward, REF/inference.py:95-135): encoder + prompt (9 + 123 + 5 = 137 rows) + prefill, last-row "
                   "logits, synthetic 10 s utterances")
 
 
 # ------------------------------------------------------------------------------------------ main arm
-def gemm_flops_per_utt(train=False, infer=False):
+def gemm_flops_per_utt(train=False, infer=False, shared_prefix=0, batch=32):
     """Algorithmic FLOPs per utterance credited to the GEMM kernel (attention and conv0
     excluded, LM head on the consumed rows only). Training adds dgrad + wgrad for the encoder (no dgrad into the
-    waveform) and dgrad only for the student sequence of the frozen LLM."""
+    waveform) and dgrad only for the student sequence of the frozen LLM. shared_prefix = P > 0 (forward / infer): the P
+    prompt-prefix rows are computed once per step of `batch` utterances instead of once per sequence -- the rows that
+    are not computed are not credited."""
     conv1 = 2 * 512 * 512 * 3 * 15999
     conv = conv1 + 2 * 512 * 512 * (3 * (7999 + 3999 + 1999) + 2 * (999 + 499))
     N = 499
@@ -387,12 +390,15 @@ def gemm_flops_per_utt(train=False, infer=False):
         + 2 * 123 * 1024 * 3072
     per_tok = 2 * 3072 * (5120 + 3072 + 2 * 8192 + 8192)
     tail = 2 * 3072 * (3072 + 2 * 8192 + 8192)  # out-projection + MLP of one row of the last layer
+    P = float(shared_prefix)
     if infer:  # L = 137, the last layer's tail and the LM head on the single consumed row
-        return enc + 28 * per_tok * 137 - 136 * tail + 2 * 3072 * 128256
-    llm = 28 * per_tok * (200 + 117) + 2 * 2 * R_RESP * 3072 * 128256
+        rows = 137 - P + P / batch
+        return enc + 28 * per_tok * rows - (rows - 1) * tail + 2 * 3072 * 128256
     if not train:
         # the forward runs the last layer's out-projection / MLP on the 2 * R consumed rows only: credit what is done
-        return enc + llm - (200 + 117 - 2 * R_RESP) * tail
+        rows = (200 + 117) - 2 * P + P / batch
+        return enc + 28 * per_tok * rows + 2 * 2 * R_RESP * 3072 * 128256 - (rows - 2 * R_RESP) * tail
+    llm = 28 * per_tok * (200 + 117) + 2 * 2 * R_RESP * 3072 * 128256
     return 3 * enc + llm + 28 * per_tok * 200 + 2 * R_RESP * 3072 * 128256
 
 
@@ -584,12 +590,16 @@ def main():
     host = [synth_batch(B, la.vocab, 1000 * (rank + 1) + i) for i in range(n_pool)]
     host = [(w.pin_memory(), t, r) for (w, t, r) in host]
     resident = [(w.to(dev), t, r) for (w, t, r) in host]
-    plans = [step.plan(123, t, r, dev) for (_, t, r) in resident]
+    plans = [step.plan(123, t, r, dev) for (_, t, r) in resident]  # the training step's (reference layout)
+    plans_fwd = [step.plan(123, t, r, dev, shared_prefix=step.share_prefix) for (_, t, r) in resident]
     torch.cuda.synchronize()
-    plan0 = plans[0]
-    h2d_step = B * SAMPLES * 4 + 4 * (plan0.row_src.numel() + plan0.cu_seqlens.numel() + plan0.positions.numel() +
-                                      plan0.logit_rows.numel() + plan0.labels.numel() + plan0.row_offsets.numel()) \
-        + 4 * plan0.audio_rows.numel() + 4 * plan0.seg.numel() + 4 * plan0.resp_len_f.numel()
+    plan0 = plans_fwd[0]
+
+    def h2d_of(pl):
+        return B * SAMPLES * 4 + 4 * (pl.row_src.numel() + pl.cu_seqlens.numel() + pl.positions.numel() +
+                                      pl.logit_rows.numel() + pl.labels.numel() + pl.row_offsets.numel()) \
+            + 4 * pl.audio_rows.numel() + 4 * pl.seg.numel() + 4 * pl.resp_len_f.numel()
+    h2d_step = h2d_of(plan0)
     l2_note = ("no flush needed: every step streams ~7 GB of weights and >2 GB of activations (>> 126 MB L2); two "
                "distinct micro-batches alternate")
 
@@ -652,7 +662,7 @@ def main():
         rag = (lambda i: {"lengths": ragged_lens[i % n_pool]}) if ragged_lens is not None else (lambda i: {})
         sec = e2e_loop(lambda i: trainer.submit(host[i % n_pool][0], host[i % n_pool][1], host[i % n_pool][2], dev, **rag(i)),
                        args.steps, args.warmup, dp, dev)
-        res["e2e"] = {"value": total_utts / sec, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": 4 * 4 * B,
+        res["e2e"] = {"value": total_utts / sec, "unit": UNIT, "h2d_bytes_per_step": h2d_of(plans[0]), "d2h_bytes_per_step": 4 * 4 * B,
                       "api": "EncoderTrainer.submit()/result(), one batch in flight ahead of the one being read"}
         res["roofline"] = gemm_roofline(run, lib, peaks, gemm_flops_per_utt(train=True) * B, ms / args.steps, True,
                                         args.gemm_shapes if headline else "", rank)
@@ -739,7 +749,7 @@ def main():
         if infer:
             logits, infer_plan[0] = step.prefill_prompts(w, plan=infer_plan[0])
             return {"logits": logits}
-        return step.forward_losses(w, t, r, plan=plans[i % n_pool])
+        return step.forward_losses(w, t, r, plan=plans_fwd[i % n_pool])
 
     def submit(i):
         w, t, r = host[i % n_pool]
@@ -774,7 +784,7 @@ def main():
     e2e_value = total_utts / sec
     h2d = B * SAMPLES * 4 + (4 * (2 * infer_plan[0]["rows"] + 2 * B + 1) if infer else h2d_step - B * SAMPLES * 4)
     d2h = 4 * B if infer else 4 * 4 * B
-    flops_utt = gemm_flops_per_utt(infer=infer)
+    flops_utt = gemm_flops_per_utt(infer=infer, shared_prefix=plan0.shared_prefix_len, batch=B)
     roofline = gemm_roofline(run_resident, lib, peaks, flops_utt * B, ms / args.steps, False, args.gemm_shapes, rank)
     roofline["algorithmic_gflop_per_utt"] = flops_utt / 1e9
     # ---- the HBM-bound kernel the north star names (fused CE + KD loss): again, hot, right after the timed steps
@@ -820,6 +830,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": WORKLOAD_INFER if infer else WORKLOAD, "utterances_per_step_per_gpu": B,
                            "parallelism": f"dp{world}", "l2": l2_note,
+                           "shared_prefix_rows": int(step.share_prefix) * len(step.prefix),
                            "timed": ("encoder + prompt splice + packed prefill, logits of the last row of every prompt"
                                      if infer else "forward only (encoder + student/teacher prefill + CE/KD/FD)") +
                                     "; `value` reuses pre-built index plans, `e2e` rebuilds them every step"},

@@ -161,6 +161,8 @@ PROTOTYPES = {
     "b2s_cast_h16_to_f32": (c_int, [c_void_p, P_f32, c_int64, c_int, c_void_p]),
     "b2s_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, P_int, c_int, c_int,
                                   c_int64, c_int, c_int, c_int, c_float, c_int, P_f32, c_int, c_void_p]),
+    "b2s_attention_fwd_prefix": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, P_int, c_int, c_int,
+                                         c_int64, c_int, c_int, c_int, c_float, P_f32, c_int, c_int, c_void_p]),
     "b2s_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, P_f32,
                                   P_f32, c_void_p, c_void_p, c_void_p, c_int64, P_int, c_int, c_int, c_int64, c_int,
                                   c_int, c_int, c_float, c_int, P_f32, c_int, c_void_p]),
@@ -175,6 +177,9 @@ PROTOTYPES = {
     "b2s_llama_prefill": (c_int, [C.POINTER(LlamaWeights), P_f32, c_int, P_int, c_int, c_int, P_int, P_int, c_int,
                                   c_void_p, C.POINTER(c_int), c_int, P_int, P_int, c_int, P_f32, P_f32, c_void_p,
                                   c_size_t, c_void_p]),
+    "b2s_llama_prefill_prefix": (c_int, [C.POINTER(LlamaWeights), P_f32, c_int, P_int, c_int, c_int, P_int, P_int, c_int,
+                                         c_void_p, C.POINTER(c_int), c_int, P_int, P_int, c_int, P_f32, P_f32, c_void_p,
+                                         c_size_t, c_int, c_void_p]),
     "b2s_llama_train_workspace_bytes": (c_size_t, [C.POINTER(LlamaWeights), c_int, c_int]),
     "b2s_llama_backward_workspace_bytes": (c_size_t, [C.POINTER(LlamaWeights), c_int, c_int]),
     "b2s_llama_forward_train": (c_int, [C.POINTER(LlamaWeights), C.POINTER(LlamaSaved), c_int, P_int, c_int, c_int,

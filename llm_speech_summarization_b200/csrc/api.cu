@@ -87,7 +87,8 @@ size_t llama_workspace_bytes(const b2s_llama_weights* w, int rows, int logit_row
 int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_seqlens, int num_seqs, int max_seqlen,
                   const int* positions, const int* logit_rows_index, int logit_rows, void* logits_bf16,
                   const int* tap_layers, int num_taps, const int* tap_rows_a, const int* tap_rows_b, int pairs,
-                  float* fd_sq, float* all_hidden, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                  float* fd_sq, float* all_hidden, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                  int shared_prefix_len = 0);
 
 size_t llama_train_workspace_bytes(const b2s_llama_weights* w, int rows, int logit_rows);
 size_t whisper_saved_bytes(const b2s_whisper_weights* w, int batches);
@@ -102,7 +103,8 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
                      int max_seqlen, const int* positions, const int* logit_rows_index, int logit_rows,
                      void* logits_bf16, const int* tap_layers, int num_taps, const int* tap_rows_a,
                      const int* tap_rows_b, int pairs, float* fd_sq, float* all_hidden, void* kv_cache, int kv_slots,
-                     const int* kv_slot_of_row, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                     const int* kv_slot_of_row, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                     int shared_prefix_len = 0);
 size_t llama_decode_workspace_bytes(const b2s_llama_weights* w, int batch);
 int llama_decode_step(const b2s_llama_weights* w, const void* embed_table, const int* token_ids, int batch,
                       void* kv_cache, int kv_slots, const int* seq_start, const int* seq_len, void* logits_bf16,
@@ -335,6 +337,13 @@ int b2s_attention_fwd(const void* q, const void* k, const void* v, int64_t ld_qk
   return attention_fwd(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, D, scale,
                        causal, lse, fmt, S(stream));
 }
+int b2s_attention_fwd_prefix(const void* q, const void* k, const void* v, int64_t ld_qkv, void* o, int64_t ld_o,
+                             const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int64_t total_rows,
+                             int32_t Hq, int32_t Hkv, int32_t D, float scale, float* lse, int32_t fmt,
+                             int32_t shared_prefix_len, void* stream) {
+  return attention_fwd(q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, D, scale, 1, lse,
+                       fmt, S(stream), nullptr, shared_prefix_len);
+}
 int b2s_attention_bwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const void* o, int64_t ld_o,
                       const void* dout, int64_t ld_do, const float* lse, float* delta_ws, void* dq, void* dk, void* dv,
                       int64_t ld_dqkv, const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen,
@@ -376,6 +385,17 @@ int b2s_llama_prefill(const b2s_llama_weights* w, float* h, int32_t rows, const 
   return llama_prefill(w, h, rows, cu_seqlens, num_seqs, max_seqlen, positions, logit_rows_index, logit_rows,
                        logits_bf16, tap_layers, num_taps, tap_rows_a, tap_rows_b, pairs, fd_sq, all_hidden, workspace,
                        workspace_bytes, S(stream));
+}
+
+int b2s_llama_prefill_prefix(const b2s_llama_weights* w, float* h, int32_t rows, const int32_t* cu_seqlens,
+                             int32_t num_seqs, int32_t max_seqlen, const int32_t* positions,
+                             const int32_t* logit_rows_index, int32_t logit_rows, void* logits_bf16,
+                             const int32_t* tap_layers, int32_t num_taps, const int32_t* tap_rows_a,
+                             const int32_t* tap_rows_b, int32_t pairs, float* fd_sq, float* all_hidden, void* workspace,
+                             size_t workspace_bytes, int32_t shared_prefix_len, void* stream) {
+  return llama_prefill(w, h, rows, cu_seqlens, num_seqs, max_seqlen, positions, logit_rows_index, logit_rows,
+                       logits_bf16, tap_layers, num_taps, tap_rows_a, tap_rows_b, pairs, fd_sq, all_hidden, workspace,
+                       workspace_bytes, S(stream), shared_prefix_len);
 }
 
 size_t b2s_llama_train_workspace_bytes(const b2s_llama_weights* w, int32_t rows, int32_t logit_rows) {

@@ -71,6 +71,10 @@ struct AttnParams {
   AttnDrop drop;  // attention-probability dropout (thresh 0 = off): softmax statistics stay those of the un-dropped row
   int n_qblk;       // 128-query blocks per (sequence, head) = ceil(max_seqlen / 128)
   int total_items;  // num_seqs * Hq * n_qblk
+  // Shared prefix (the prompt prefix is the same token run in every sequence of a step, so under a causal mask its hidden
+  // states are identical everywhere): sequence 0 holds the prefix rows ONCE; every other sequence holds only its own
+  // rows and sees the prefix_len keys / values of sequence 0 as one extra, leading key block. 0 = off.
+  int prefix_len;
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -100,6 +104,7 @@ __device__ __forceinline__ float ex2f(float x) {
 // counters (g = blocks processed by this CTA so far, items done so far).
 struct AttnItem {
   int seq, h, hk, s0, L, q0, nblk;
+  int pre;  // 1 = key block 0 of this item is the shared prefix (rows [cu[0], cu[0] + prefix_len)), own keys follow
 };
 
 template <int BN>
@@ -114,7 +119,8 @@ __device__ __forceinline__ bool attn_decode_item(const AttnParams& p, int item, 
   if (it->q0 >= it->L) return false;
   it->hk = it->h / (p.Hq / p.Hkv);
   const int kv_len = p.causal ? min(it->L, it->q0 + kBM) : it->L;
-  it->nblk = (kv_len + BN - 1) / BN;
+  it->pre = (p.prefix_len > 0 && it->seq > 0) ? 1 : 0;
+  it->nblk = it->pre + (kv_len + BN - 1) / BN;
   return true;
 }
 
@@ -180,6 +186,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       ptx::prefetch_tmap(&tmap_q);
       ptx::prefetch_tmap(&tmap_k);
       ptx::prefetch_tmap(&tmap_v);
+      // first row of key block j of an item (block 0 of a prefixed item = the shared prefix rows of sequence 0)
+      auto kv_row = [&](const AttnItem& it, int j) { return j < it.pre ? p.cu[0] : it.s0 + (j - it.pre) * kBN; };
       auto load_q = [&](const AttnItem& it) {
         ptx::mbar_arrive_expect_tx(bar_q, C::kQBytes);
 #pragma unroll
@@ -192,9 +200,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
         for (int a = 0; a < kAtoms; ++a) {
           ptx::tma_load_2d(&tmap_k, bar_kv0 + 8 * st, sK + st * C::kKBytes + a * (kBN * 128),
-                           p.k_col0 + it.hk * D + a * 64, it.s0 + j * kBN);
+                           p.k_col0 + it.hk * D + a * 64, kv_row(it, j));
           ptx::tma_load_2d(&tmap_v, bar_kv0 + 8 * st, sV + st * C::kVBytes + a * (kBN * 128),
-                           p.v_col0 + it.hk * D + a * 64, it.s0 + j * kBN);
+                           p.v_col0 + it.hk * D + a * 64, kv_row(it, j));
         }
       };
       constexpr uint32_t idesc_s = ptx::make_idesc_f32acc(kBM, kBN) | ptx::idesc_formats(F16, F16);
@@ -222,7 +230,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
           for (int a = 0; a < kAtoms; ++a)
             ptx::tma_load_2d(&tmap_k, bar_kv0 + 8 * st, sK + st * C::kKBytes + a * (kBN * 128),
-                             p.k_col0 + c.it.hk * D + a * 64, c.it.s0 + c.j * kBN);
+                             p.k_col0 + c.it.hk * D + a * 64, kv_row(c.it, c.j));
         };
         auto load_v = [&](const Cur& c, uint32_t g) {
           const int st = g & 1;
@@ -230,7 +238,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
           for (int a = 0; a < kAtoms; ++a)
             ptx::tma_load_2d(&tmap_v, bar_v0 + 8 * st, sV + st * C::kVBytes + a * (kBN * 128),
-                             p.v_col0 + c.it.hk * D + a * 64, c.it.s0 + c.j * kBN);
+                             p.v_col0 + c.it.hk * D + a * 64, kv_row(c.it, c.j));
         };
         uint32_t q_loads = 0;
         auto issue_s = [&](const Cur& c, uint32_t g) {
@@ -419,7 +427,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           pv_synced = true;
         }
       };
-      const int nvis = row_limit - j * kBN;  // visible keys of this row inside this block (<= 0 .. >= 128)
+      // visible keys of this row inside this block (<= 0 .. >= 128); the shared-prefix block shows all its keys to every row
+      const int nvis = (j < cur.pre) ? p.prefix_len : row_limit - (j - cur.pre) * kBN;
       const bool full_blk = __all_sync(0xffffffffu, nvis >= kBN);
       // D = 128 with 64-key steps (two CTAs per SM, registers to spare): the thread's whole row of S (64 fp32) is read
       // from TMEM ONCE, both 32-column loads in flight before the single wait, and stays in registers for the
@@ -565,7 +574,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 template <int D, int BN, int KVS, bool DROP, bool F16>
 int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, void* o, long long ldo, const int* cu,
                    int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, float scale, int causal,
-                   float* lse, cudaStream_t stream, const AttnDrop* drop) {
+                   float* lse, cudaStream_t stream, const AttnDrop* drop, int prefix_len) {
   using C = AttnCfg<D, BN, KVS>;
   constexpr int kBN = BN;
   auto kern = attn_fwd_tc_kernel<D, BN, KVS, DROP, F16>;
@@ -592,6 +601,7 @@ int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, vo
   p.causal = causal;
   p.lse = lse;
   if (DROP) p.drop = *drop;
+  p.prefix_len = prefix_len;
   p.n_qblk = (max_seqlen + kBM - 1) / kBM;
   const long long total = static_cast<long long>(p.n_qblk) * Hq * num_seqs;
   B2S_REQUIRE(total < (1LL << 31), "attention_fwd_tc: too many work items");
@@ -613,8 +623,11 @@ int launch_attn_tc(const void* q, const void* k, const void* v, long long ld, vo
 // Packed variable-length attention forward (ops.cuh). q / k / v / o share one 16-bit format (fmt: B2S_FMT_*).
 int attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
                   const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
-                  float scale, int causal, float* lse, int fmt, cudaStream_t stream, const AttnDrop* drop) {
+                  float scale, int causal, float* lse, int fmt, cudaStream_t stream, const AttnDrop* drop,
+                  int shared_prefix_len) {
   B2S_REQUIRE(q && k && v && o && cu_seqlens, "attention_fwd: null pointer");
+  B2S_REQUIRE(shared_prefix_len >= 0 && shared_prefix_len <= 64 && (shared_prefix_len == 0 || (causal && drop == nullptr)),
+              "attention_fwd: a shared prefix needs a causal mask, no dropout and at most 64 rows");
   if (drop != nullptr && drop->thresh == 0u) drop = nullptr;
   B2S_REQUIRE(total_rows > 0, "attention_fwd: total_rows must be the row count of the packed q/k/v buffers");
   B2S_REQUIRE(num_seqs > 0 && max_seqlen > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "attention_fwd: bad head counts");
@@ -626,8 +639,8 @@ int attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv,
   const bool f16 = fmt != 0;
 #define B2S_ATTN_ARGS q, k, v, ld_qkv, o, ld_o, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, scale, causal, lse, stream
 #define B2S_ATTN_GO(D_, BN_, KVS_, DROP_, DP_)                                     \
-  return f16 ? launch_attn_tc<D_, BN_, KVS_, DROP_, true>(B2S_ATTN_ARGS, DP_)      \
-             : launch_attn_tc<D_, BN_, KVS_, DROP_, false>(B2S_ATTN_ARGS, DP_)
+  return f16 ? launch_attn_tc<D_, BN_, KVS_, DROP_, true>(B2S_ATTN_ARGS, DP_, shared_prefix_len)      \
+             : launch_attn_tc<D_, BN_, KVS_, DROP_, false>(B2S_ATTN_ARGS, DP_, shared_prefix_len)
   if (drop != nullptr) {  // train-mode HuBERT attention only (TF/.../modeling_hubert.py:254)
     B2S_REQUIRE(D == 64 && max_seqlen < 65536, "attention_fwd: attention dropout supports head_dim 64, seqlen < 65536");
     B2S_ATTN_GO(64, 64, 1, true, drop);

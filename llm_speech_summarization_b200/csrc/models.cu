@@ -493,15 +493,17 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
                      int max_seqlen, const int* positions, const int* logit_rows_index, int logit_rows,
                      void* logits_bf16, const int* tap_layers, int num_taps, const int* tap_rows_a,
                      const int* tap_rows_b, int pairs, float* fd_sq, float* all_hidden, void* kv_cache, int kv_slots,
-                     const int* kv_slot_of_row, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                     const int* kv_slot_of_row, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                     int shared_prefix_len = 0);
 
 int llama_prefill(const b2s_llama_weights* w, float* h, int rows, const int* cu_seqlens, int num_seqs, int max_seqlen,
                   const int* positions, const int* logit_rows_index, int logit_rows, void* logits_bf16,
                   const int* tap_layers, int num_taps, const int* tap_rows_a, const int* tap_rows_b, int pairs,
-                  float* fd_sq, float* all_hidden, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                  float* fd_sq, float* all_hidden, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                  int shared_prefix_len) {
   return llama_prefill_kv(w, h, rows, cu_seqlens, num_seqs, max_seqlen, positions, logit_rows_index, logit_rows,
                           logits_bf16, tap_layers, num_taps, tap_rows_a, tap_rows_b, pairs, fd_sq, all_hidden, nullptr, 0,
-                          nullptr, workspace, workspace_bytes, stream);
+                          nullptr, workspace, workspace_bytes, stream, shared_prefix_len);
 }
 
 // llama_prefill that additionally leaves every layer's post-RoPE k | v rows in a KV cache (decode.cu) so a greedy
@@ -510,8 +512,10 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
                      int max_seqlen, const int* positions, const int* logit_rows_index, int logit_rows,
                      void* logits_bf16, const int* tap_layers, int num_taps, const int* tap_rows_a,
                      const int* tap_rows_b, int pairs, float* fd_sq, float* all_hidden, void* kv_cache, int kv_slots,
-                     const int* kv_slot_of_row, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                     const int* kv_slot_of_row, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                     int shared_prefix_len) {
   B2S_REQUIRE(kv_cache == nullptr || (kv_slots > 0 && kv_slot_of_row != nullptr), "llama_prefill: bad KV cache arguments");
+  B2S_REQUIRE(shared_prefix_len == 0 || kv_cache == nullptr, "llama_prefill: the shared prefix is not combined with a KV cache");
   B2S_REQUIRE(w && h && cu_seqlens && positions && workspace, "llama_prefill: null pointer");
   B2S_REQUIRE(rows > 0 && num_seqs > 0 && max_seqlen > 0, "llama_prefill: empty batch");
   B2S_REQUIRE(w->head_dim == 128, "llama_prefill: head_dim must be 128 (got %d)", w->head_dim);
@@ -562,7 +566,7 @@ int llama_prefill_kv(const b2s_llama_weights* w, float* h, int rows, const int* 
     {
       const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(pl.qkv);
       rc = attention_fwd(qkv, qkv + Hq * D, qkv + (Hq + Hkv) * D, qkv_cols, pl.ao, Hq * D, cu_seqlens, num_seqs,
-                         max_seqlen, rows, Hq, Hkv, D, scale, 1, nullptr, fmt, stream);
+                         max_seqlen, rows, Hq, Hkv, D, scale, 1, nullptr, fmt, stream, nullptr, shared_prefix_len);
       if (rc != B2S_OK) return rc;
     }
     const bool sel = last_on_selected && l == w->num_layers - 1;

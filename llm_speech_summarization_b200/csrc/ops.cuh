@@ -132,7 +132,8 @@ int drop_mask_dump(unsigned char* out, long long n, unsigned long long seed, uin
 int attention_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* o, long long ld_o,
                   const int* cu_seqlens, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv, int D,
                   float scale, int causal, float* lse /* optional [rows, Hq] */, int fmt, cudaStream_t stream,
-                  const AttnDrop* drop = nullptr /* attention-probability dropout */);
+                  const AttnDrop* drop = nullptr /* attention-probability dropout */,
+                  int shared_prefix_len = 0 /* > 0: sequence 0 is a prefix every other sequence also attends to */);
 // Backward of attention_fwd. lse = the forward's saved log-sum-exp; delta_ws = fp32 [rows, Hq] scratch.
 // dq / dk / dv are 16-bit views with row stride ld_dqkv (head h at column h*D). rope_cs (optional, [npos, D]) fuses
 // the inverse rotary rotation into the dq / dk stores (positions = row index inside its sequence).

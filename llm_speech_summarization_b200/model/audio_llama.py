@@ -297,9 +297,12 @@ class AudioLlamaForCausalLM(nn.Module):
     def prefill_packed(self, h: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, positions: torch.Tensor,
                        logit_rows: Optional[torch.Tensor], *, tap_layers: Sequence[int] = (),
                        tap_rows_a: Optional[torch.Tensor] = None, tap_rows_b: Optional[torch.Tensor] = None,
-                       all_hidden: bool = False, logits_out: Optional[torch.Tensor] = None):
+                       all_hidden: bool = False, logits_out: Optional[torch.Tensor] = None,
+                       shared_prefix_len: int = 0):
         """Run the LLM over packed sequences. h: fp32 [rows, H] (overwritten with the last residual stream).
-        Returns (logits bf16 [n_logit_rows, V] | None, fd_sq fp32 [taps, pairs] | None, all_hidden | None)."""
+        Returns (logits bf16 [n_logit_rows, V] | None, fd_sq fp32 [taps, pairs] | None, all_hidden | None).
+        shared_prefix_len > 0: sequence 0 is the prompt prefix every other sequence also attends to (step.build_plan's
+        shared-prefix layout)."""
         w = self.packed()[0]
         a = self.arch
         lib = _lib.load()
@@ -319,13 +322,16 @@ class AudioLlamaForCausalLM(nn.Module):
         hid = torch.empty(a.layers + 1, rows, a.hidden, device=h.device, dtype=torch.float32) if all_hidden else None
         nbytes = lib.b2s_llama_workspace_bytes(C.byref(w), rows, n_log)
         ws = torch.empty(nbytes, device=h.device, dtype=torch.uint8)
-        _lib.check(lib.b2s_llama_prefill(
-            C.byref(w), h.data_ptr(), rows, cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, int(max_seqlen),
-            positions.data_ptr(), None if not n_log else logit_rows.data_ptr(), n_log,
-            None if logits is None else logits.data_ptr(), tap_arr, len(taps) if pairs else 0,
-            None if not pairs else tap_rows_a.data_ptr(), None if not pairs else tap_rows_b.data_ptr(), pairs,
-            fd.data_ptr(), None if hid is None else hid.data_ptr(), ws.data_ptr(), nbytes,
-            torch.cuda.current_stream().cuda_stream), "llama_prefill")
+        args = (C.byref(w), h.data_ptr(), rows, cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, int(max_seqlen),
+                positions.data_ptr(), None if not n_log else logit_rows.data_ptr(), n_log,
+                None if logits is None else logits.data_ptr(), tap_arr, len(taps) if pairs else 0,
+                None if not pairs else tap_rows_a.data_ptr(), None if not pairs else tap_rows_b.data_ptr(), pairs,
+                fd.data_ptr(), None if hid is None else hid.data_ptr(), ws.data_ptr(), nbytes)
+        stream = torch.cuda.current_stream().cuda_stream
+        if shared_prefix_len > 0:
+            _lib.check(lib.b2s_llama_prefill_prefix(*args, int(shared_prefix_len), stream), "llama_prefill (shared prefix)")
+        else:
+            _lib.check(lib.b2s_llama_prefill(*args, stream), "llama_prefill")
         return logits, (fd if pairs and taps else None), hid
 
     # ------------------------------------------------------------------------------------------ reference API

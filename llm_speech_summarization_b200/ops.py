@@ -225,15 +225,24 @@ def posconv_weight_pack(g: torch.Tensor, v: torch.Tensor, out_dtype: torch.dtype
 
 
 def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, Hq: int, Hkv: int, D: int, scale: float,
-              causal: bool, return_lse: bool = False):
+              causal: bool, return_lse: bool = False, shared_prefix_len: int = 0):
     """qkv 16-bit [rows, (Hq+2Hkv)*D] (q | k | v) -> o [rows, Hq*D] in the same dtype (and the fp32 [rows, Hq]
-    log2-domain lse)."""
+    log2-domain lse). shared_prefix_len > 0 (causal only): sequence 0 is a prefix of that many rows which every other
+    sequence attends to in front of its own rows."""
     _need_cuda(qkv, cu_seqlens)
     assert qkv.dtype in _H16 and qkv.is_contiguous() and cu_seqlens.dtype == torch.int32
     rows, ld = qkv.shape
     o = torch.empty(rows, Hq * D, device=qkv.device, dtype=qkv.dtype)
     lse = torch.empty(rows, Hq, device=qkv.device, dtype=torch.float32) if return_lse else None
     base = qkv.data_ptr()
+    if shared_prefix_len > 0:
+        assert causal
+        _lib.check(_lib.load().b2s_attention_fwd_prefix(base, base + 2 * Hq * D, base + 2 * (Hq + Hkv) * D, ld,
+                                                        o.data_ptr(), Hq * D, cu_seqlens.data_ptr(),
+                                                        cu_seqlens.numel() - 1, max_seqlen, rows, Hq, Hkv, D, scale,
+                                                        _ptr(lse), fmt_of(qkv.dtype), int(shared_prefix_len), _stream()),
+                   "attention (shared prefix)")
+        return (o, lse) if return_lse else o
     _lib.check(_lib.load().b2s_attention_fwd(base, base + 2 * Hq * D, base + 2 * (Hq + Hkv) * D, ld, o.data_ptr(),
                                              Hq * D, cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, max_seqlen, rows,
                                              Hq, Hkv, D, scale, int(causal), _ptr(lse), fmt_of(qkv.dtype), _stream()),

@@ -40,6 +40,7 @@ class StepPlan:
     resp_len_f: Optional[torch.Tensor] = None  # fp32 [B]
     audio_rows: Optional[torch.Tensor] = None  # int32 [B*A] packed row of every audio embedding (student sequences)
     student_rows_total: int = 0                # rows of all student sequences (they are packed first)
+    shared_prefix_len: int = 0                 # > 0: sequence 0 is the prompt prefix, stored once (forward-only layout)
 
 
 def build_plan(prefix: Sequence[int], suffix: Sequence[int], n_audio, text_ids: Sequence[Sequence[int]],
@@ -102,10 +103,17 @@ def build_plan(prefix: Sequence[int], suffix: Sequence[int], n_audio, text_ids: 
 
 
 def build_plan_arrays(prefix: Sequence[int], suffix: Sequence[int], n_audio, text_ids, resp_ids,
-                      with_teacher: bool = True, audio_stride: Optional[int] = None) -> Dict[str, object]:
+                      with_teacher: bool = True, audio_stride: Optional[int] = None,
+                      shared_prefix: bool = False) -> Dict[str, object]:
     """`build_plan` with numpy (same keys, int32 arrays instead of lists): what the step calls per micro-batch -- the
     list version costs ~7 ms of Python per 32 utterances, this one well under 1 ms. Equality with `build_plan` is a
-    CPU unit test."""
+    CPU unit test.
+
+    shared_prefix=True is the forward-only SHARED-PREFIX layout: every sequence the reference builds starts with the same
+    prompt-prefix tokens, and under a causal mask those rows are identical in all of them at every layer. They are packed
+    ONCE, as sequence 0; sequences 1 .. 2B hold only their own rows (positions continue after the prefix) and the
+    attention kernel lets them see sequence 0's keys (b2s_llama_prefill_prefix). Every row the losses consume has the
+    value it has in the reference's layout; (2B - 1) * len(prefix) rows are not computed."""
     import numpy as np
     B = len(resp_ids)
     n_each = [int(n_audio)] * B if isinstance(n_audio, int) else [int(n) for n in n_audio]
@@ -115,37 +123,47 @@ def build_plan_arrays(prefix: Sequence[int], suffix: Sequence[int], n_audio, tex
     pre, suf = i32(prefix), i32(suffix)[1:]
     resp = [i32(r) for r in resp_ids]
     text = [i32(t) for t in text_ids] if with_teacher else []
-    seqs = [np.concatenate([pre, -(i * A + np.arange(n_each[i], dtype=np.int32)) - 1, suf, resp[i][1:]]) for i in range(B)]
-    L_audio = [len(q) for q in seqs]
+    P = len(pre)
+    head = np.zeros(0, dtype=np.int32) if shared_prefix else pre  # what every sequence starts with in the packed layout
+    seqs = [np.concatenate([head, -(i * A + np.arange(n_each[i], dtype=np.int32)) - 1, suf, resp[i][1:]]) for i in range(B)]
+    extra = P if shared_prefix else 0  # rows of each sequence that live in sequence 0
+    L_audio = [len(q) + extra for q in seqs]
     L_text = []
     if with_teacher:
-        t_seqs = [np.concatenate([pre, text[i], suf, resp[i][1:]]) for i in range(B)]
-        L_text = [len(q) for q in t_seqs]
+        t_seqs = [np.concatenate([head, text[i], suf, resp[i][1:]]) for i in range(B)]
+        L_text = [len(q) + extra for q in t_seqs]
         seqs = seqs + t_seqs
+    if shared_prefix:
+        seqs = [pre] + seqs
+    s0 = 1 if shared_prefix else 0  # index of the first student sequence
     lens = np.asarray([len(q) for q in seqs], dtype=np.int64)
     cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
     row_src = np.concatenate(seqs).astype(np.int32)
-    positions = (np.arange(int(cu[-1]), dtype=np.int64) - np.repeat(cu[:-1].astype(np.int64), lens)).astype(np.int32)
+    first_pos = np.full(len(seqs), extra, dtype=np.int64)
+    if shared_prefix:
+        first_pos[0] = 0
+    positions = (np.arange(int(cu[-1]), dtype=np.int64) - np.repeat(cu[:-1].astype(np.int64), lens) +
+                 np.repeat(first_pos, lens)).astype(np.int32)
     resp_lens = [len(r) for r in resp]
     for i in range(B):
         if resp_lens[i] > L_audio[i]:
             raise ValueError("response longer than its sequence")
     R = np.asarray(resp_lens, dtype=np.int64)
     within = np.arange(int(R.sum()), dtype=np.int64) - np.repeat(np.concatenate([[0], np.cumsum(R)[:-1]]), R)
-    s_rows = (np.repeat(cu[1:B + 1].astype(np.int64) - R, R) + within).astype(np.int32)
-    t_rows = ((np.repeat(cu[B + 1:2 * B + 1].astype(np.int64) - R, R) + within).astype(np.int32) if with_teacher
+    s_rows = (np.repeat(cu[s0 + 1:s0 + B + 1].astype(np.int64) - R, R) + within).astype(np.int32)
+    t_rows = ((np.repeat(cu[s0 + B + 1:s0 + 2 * B + 1].astype(np.int64) - R, R) + within).astype(np.int32) if with_teacher
               else np.zeros(0, dtype=np.int32))
     labels = np.concatenate([np.concatenate([resp[i][1:], [-1]]) for i in range(B)]).astype(np.int32) if B else i32([])
     offs = np.concatenate([[0], np.cumsum(R)]).astype(np.int32)
-    P = len(pre)
     r_idx = np.arange(A, dtype=np.int64)[None, :]
     audio_rows = np.where(r_idx < np.asarray(n_each, dtype=np.int64)[:, None],
-                          cu[:B].astype(np.int64)[:, None] + P + r_idx, -1).astype(np.int32).reshape(-1)
+                          cu[s0:s0 + B].astype(np.int64)[:, None] + (P - extra) + r_idx, -1).astype(np.int32).reshape(-1)
     seg = np.repeat(np.arange(B, dtype=np.int32), R)
+    # max_seqlen bounds both the query blocks of the longest sequence and the largest position + 1 (RoPE table check)
     return dict(row_src=row_src, cu_seqlens=cu, positions=positions, student_rows=s_rows, teacher_rows=t_rows,
-                labels=labels, row_offsets=offs, max_seqlen=int(lens.max()), rows=int(cu[-1]), sum_r=int(R.sum()),
+                labels=labels, row_offsets=offs, max_seqlen=int(lens.max()) + extra, rows=int(cu[-1]), sum_r=int(R.sum()),
                 resp_lens=resp_lens, L_audio=L_audio, L_text=L_text, audio_rows=audio_rows,
-                student_rows_total=int(cu[B]), seg=seg)
+                student_rows_total=int(cu[s0 + B]), seg=seg, shared_prefix_len=extra)
 
 
 class PendingStep:
@@ -188,7 +206,12 @@ def _losses_to_host(out: Dict[str, torch.Tensor]) -> PendingStep:
 class AudioPromptStep:
     def __init__(self, audio_encoder, llm, tokenizer, llm_type: str, *, use_ld_loss: bool = True,
                  use_fd_loss: bool = True, ntp_loss_weight: float = 0.5, ld_loss_weight: float = 0.5,
-                 fd_loss_weight: float = 1.0, fd_loss_connector_layers: Sequence[int] = (0, 5, 11, 17, 23)):
+                 fd_loss_weight: float = 1.0, fd_loss_connector_layers: Sequence[int] = (0, 5, 11, 17, 23),
+                 share_prefix: bool = True):
+        # share_prefix: the forward-only paths (forward_losses, prefill_prompts) compute the prompt-prefix rows once per
+        # step instead of once per sequence (build_plan_arrays). The training step keeps the reference's layout: its
+        # backward kernels have no shared-prefix form.
+        self.share_prefix = bool(share_prefix)
         self.audio_encoder = audio_encoder
         self.llm = llm
         self.llm_type = llm_type
@@ -207,11 +230,13 @@ class AudioPromptStep:
                    use_fd_loss=t.use_fd_loss, ntp_loss_weight=t.ntp_loss_weight, ld_loss_weight=t.ld_loss_weight,
                    fd_loss_weight=t.fd_loss_weight, fd_loss_connector_layers=t.fd_loss_connector_layers)
 
-    def plan(self, n_audio, text_ids, resp_ids, device, audio_stride: Optional[int] = None) -> StepPlan:
+    def plan(self, n_audio, text_ids, resp_ids, device, audio_stride: Optional[int] = None,
+             shared_prefix: bool = False) -> StepPlan:
         import numpy as np
         as_np = lambda xs: [x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x) for x in xs]
         d = build_plan_arrays(self.prefix, self.suffix, n_audio, as_np(text_ids), as_np(resp_ids),
-                              with_teacher=(self.use_ld or self.use_fd), audio_stride=audio_stride)
+                              with_teacher=(self.use_ld or self.use_fd), audio_stride=audio_stride,
+                              shared_prefix=shared_prefix and len(self.prefix) > 0 and len(self.prefix) <= 64)
         # every index array of the plan travels in ONE pinned staging buffer and one H2D copy (each array starts on a
         # 16-byte boundary); the fp32 response lengths ride along as raw bits
         parts = {"row_src": d["row_src"], "cu_seqlens": d["cu_seqlens"], "positions": d["positions"],
@@ -236,7 +261,8 @@ class AudioPromptStep:
                         max_seqlen=d["max_seqlen"], rows=d["rows"], sum_r=d["sum_r"], resp_lens=d["resp_lens"],
                         L_audio=d["L_audio"], L_text=d["L_text"], seg=i32("seg").to(torch.int64),
                         resp_len_f=dev_buf[offs["resp_len_f"]:offs["resp_len_f"] + nB].view(torch.float32),
-                        audio_rows=i32("audio_rows"), student_rows_total=d["student_rows_total"])
+                        audio_rows=i32("audio_rows"), student_rows_total=d["student_rows_total"],
+                        shared_prefix_len=d["shared_prefix_len"])
 
     @torch.no_grad()
     def forward_losses(self, waves: torch.Tensor, text_ids, resp_ids, plan: Optional[StepPlan] = None,
@@ -266,7 +292,8 @@ class AudioPromptStep:
             audio = audio[:, :num_audio_embeds].contiguous()
         A, Cdim = audio.shape[1], audio.shape[2]
         if plan is None:
-            plan = self.plan(A if n_valid is None else n_valid, text_ids, resp_ids, dev, audio_stride=A)
+            plan = self.plan(A if n_valid is None else n_valid, text_ids, resp_ids, dev, audio_stride=A,
+                             shared_prefix=self.share_prefix)
         h = ops.embed_splice(self.llm.model.embed_tokens.weight, audio.view(B * A, Cdim), plan.row_src)
         with_teacher = self.use_ld or self.use_fd
         taps = [l for l in self.fd_layers if l > 0] if self.use_fd else []
@@ -274,7 +301,8 @@ class AudioPromptStep:
         t_rows = plan.logit_rows[plan.sum_r:] if with_teacher else None
         logits, fd_sq, _ = self.llm.prefill_packed(
             h, plan.cu_seqlens, plan.max_seqlen, plan.positions, plan.logit_rows, tap_layers=taps,
-            tap_rows_a=s_rows if taps else None, tap_rows_b=t_rows if taps else None)
+            tap_rows_a=s_rows if taps else None, tap_rows_b=t_rows if taps else None,
+            shared_prefix_len=plan.shared_prefix_len)
         s_log = logits[:plan.sum_r]
         t_log = logits[plan.sum_r:] if with_teacher else s_log
         res = ops.kd_ce_loss(s_log, t_log, plan.labels, plan.row_offsets, scale_kd=self.w_ld, scale_ce=self.w_ntp)
@@ -319,22 +347,34 @@ class AudioPromptStep:
             import numpy as np
             pre = np.asarray(self.prefix, dtype=np.int32)
             suf = np.asarray(self.suffix, dtype=np.int32)[1:]
+            share = self.share_prefix and 0 < len(pre) <= 64
+            head = np.zeros(0, dtype=np.int32) if share else pre
             seqs = []
             for i in range(B):
                 extra = (np.asarray(extra_text_ids[i].detach().cpu() if torch.is_tensor(extra_text_ids[i])
                                     else extra_text_ids[i], dtype=np.int32).reshape(-1)
                          if extra_text_ids is not None else np.zeros(0, dtype=np.int32))
-                seqs.append(np.concatenate([pre, extra, -(i * A + np.arange(A, dtype=np.int32)) - 1, suf]))
+                seqs.append(np.concatenate([head, extra, -(i * A + np.arange(A, dtype=np.int32)) - 1, suf]))
+            if share:  # the prefix rows once, as sequence 0 (build_plan_arrays' shared-prefix layout)
+                seqs = [pre] + seqs
             lens = np.asarray([len(q) for q in seqs], dtype=np.int64)
             cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
-            pos = (np.arange(int(cu[-1]), dtype=np.int64) - np.repeat(cu[:-1].astype(np.int64), lens)).astype(np.int32)
-            host = torch.from_numpy(np.concatenate([np.concatenate(seqs), cu, pos, cu[1:] - 1]).astype(np.int32)).pin_memory()
+            first = np.full(len(seqs), len(pre) if share else 0, dtype=np.int64)
+            if share:
+                first[0] = 0
+            pos = (np.arange(int(cu[-1]), dtype=np.int64) - np.repeat(cu[:-1].astype(np.int64), lens) +
+                   np.repeat(first, lens)).astype(np.int32)
+            last = cu[2:] - 1 if share else cu[1:] - 1
+            nseq = len(seqs)
+            host = torch.from_numpy(np.concatenate([np.concatenate(seqs), cu, pos, last]).astype(np.int32)).pin_memory()
             d = host.to(dev, non_blocking=True)
             n = int(cu[-1])
-            plan = dict(row_src=d[:n], cu=d[n:n + B + 1], pos=d[n + B + 1:2 * n + B + 1], last=d[2 * n + B + 1:],
-                        max_len=int(lens.max()), rows=n)
+            plan = dict(row_src=d[:n], cu=d[n:n + nseq + 1], pos=d[n + nseq + 1:2 * n + nseq + 1],
+                        last=d[2 * n + nseq + 1:], max_len=int(lens.max()) + (len(pre) if share else 0), rows=n,
+                        shared_prefix_len=len(pre) if share else 0)
         h = ops.embed_splice(self.llm.model.embed_tokens.weight, audio.view(B * A, Cdim), plan["row_src"])
-        logits, _, _ = self.llm.prefill_packed(h, plan["cu"], plan["max_len"], plan["pos"], plan["last"])
+        logits, _, _ = self.llm.prefill_packed(h, plan["cu"], plan["max_len"], plan["pos"], plan["last"],
+                                               shared_prefix_len=plan.get("shared_prefix_len", 0))
         return logits, plan
 
     @torch.no_grad()
@@ -376,6 +416,8 @@ class AudioPromptStep:
         B, A, Cdim = audio.shape
         if plan is None:  # n_audio: per-utterance counts of a ragged batch (the first n_audio[i] rows of audio[i])
             plan = self.plan(A if n_audio is None else n_audio, text_ids, resp_ids, dev, audio_stride=A)
+        if plan.shared_prefix_len:
+            raise ValueError("the training step needs the reference's layout: build its plan with shared_prefix=False")
         with_teacher = self.use_ld or self.use_fd
         saved, st = self.llm.alloc_saved(plan.rows, dev)
         ops.embed_splice(self.llm.model.embed_tokens.weight, audio.reshape(B * A, Cdim).contiguous(), plan.row_src,

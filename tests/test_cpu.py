@@ -732,3 +732,35 @@ def test_option_ids_match_the_header():
               "SM_BUDGET": _lib.OPT_SM_BUDGET, "GEMM_GROUP_M": _lib.OPT_GEMM_GROUP_M,
               "GEMM_TAIL_SPLIT": _lib.OPT_GEMM_TAIL_SPLIT, "GEMM_EPI8": _lib.OPT_GEMM_EPI8}
     assert enum == mirror
+
+
+def test_shared_prefix_plan_expands_to_the_reference_layout():
+    """build_plan_arrays(shared_prefix=True): the prefix is sequence 0, every other sequence is the reference's sequence
+    minus its prefix, positions continue after the prefix, and every index the losses / the splice use points at the
+    same token with the same position as in the reference layout."""
+    import numpy as np
+    from llm_speech_summarization_b200.step import build_plan_arrays
+    rng = np.random.default_rng(0)
+    pre, suf = [1, 2, 3, 4], [9, 8, 7]
+    B, A = 5, 6
+    n_audio = [6, 3, 6, 1, 4]
+    text = [rng.integers(10, 99, size=rng.integers(1, 9)).astype(np.int32) for _ in range(B)]
+    resp = [np.concatenate([[5], rng.integers(10, 99, size=rng.integers(1, 5))]).astype(np.int32) for _ in range(B)]
+    a = build_plan_arrays(pre, suf, n_audio, text, resp, audio_stride=A)
+    b = build_plan_arrays(pre, suf, n_audio, text, resp, audio_stride=A, shared_prefix=True)
+    seqs = lambda d: [d["row_src"][d["cu_seqlens"][i]:d["cu_seqlens"][i + 1]] for i in range(len(d["cu_seqlens"]) - 1)]
+    poss = lambda d: [d["positions"][d["cu_seqlens"][i]:d["cu_seqlens"][i + 1]] for i in range(len(d["cu_seqlens"]) - 1)]
+    sa, sb, pa, pb = seqs(a), seqs(b), poss(a), poss(b)
+    assert b["shared_prefix_len"] == 4 and a.get("shared_prefix_len", 0) == 0
+    assert len(sb) == 2 * B + 1 and np.array_equal(sb[0], pre) and np.array_equal(pb[0], np.arange(4))
+    for i in range(2 * B):
+        assert np.array_equal(np.concatenate([sb[0], sb[i + 1]]), sa[i])
+        assert np.array_equal(np.concatenate([pb[0], pb[i + 1]]), pa[i])
+    for key in ("student_rows", "teacher_rows"):
+        assert np.array_equal(a["row_src"][a[key]], b["row_src"][b[key]])
+        assert np.array_equal(a["positions"][a[key]], b["positions"][b[key]])
+    for x, y in zip(a["audio_rows"], b["audio_rows"]):
+        assert (x < 0) == (y < 0) and (x < 0 or a["row_src"][x] == b["row_src"][y])
+    for key in ("labels", "row_offsets", "seg", "resp_lens", "L_audio", "L_text", "sum_r"):
+        assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), key
+    assert b["rows"] == a["rows"] - (2 * B - 1) * 4 and b["max_seqlen"] == a["max_seqlen"]

@@ -114,7 +114,8 @@ def test_bench_batch32_packed_forward_equals_per_utterance_oracle(cuda, full):
     step = AudioPromptStep(enc, llm, tok, llm_cfg.llm_type)
     out = step.forward_losses(waves, [u[1] for u in utts], [u[2] for u in utts], keep=True)
     torch.cuda.synchronize()
-    assert out["plan"].rows == B * (200 + 117)
+    P = out["plan"].shared_prefix_len  # 9 prompt-prefix rows, stored once instead of 2 B times
+    assert P == 9 and out["plan"].rows == B * (200 + 117) - (2 * B - 1) * P
     s_log = out["student_logits"].view(B, R_RESP, -1)
     t_log = out["teacher_logits"].view(B, R_RESP, -1)
     for i in (0, 11, 21, 31):

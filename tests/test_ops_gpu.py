@@ -492,3 +492,36 @@ def test_gelu_bwd_with_fused_bias_gradient(cuda, dt):
     fused = ops.gelu_bwd(pre, dy, colsum=cs)
     assert torch.equal(fused, plain)
     assert rel_l2(cs - 3.0, x.grad.sum(0)) < 1e-4
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("P,Hq,Hkv,own", [(9, 24, 8, [191, 108, 191, 108]), (9, 4, 2, [1, 55, 56, 64, 65, 130]),
+                                         (64, 2, 2, [100, 7]), (1, 2, 1, [300])])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_attention_shared_prefix_equals_per_sequence_copies(cuda, P, Hq, Hkv, own, dtype):
+    """Sequence 0 = the P prefix rows, stored once; sequences 1.. hold only their own rows and attend to the prefix keys in
+    front of them. Must equal plain causal attention over sequences that each carry their own copy of the prefix."""
+    from llm_speech_summarization_b200 import ops
+    D = 128
+    g = torch.Generator().manual_seed(P * 1000 + sum(own))
+    width = (Hq + 2 * Hkv) * D
+    pre = torch.randn(P, width, generator=g)
+    owns = [torch.randn(n, width, generator=g) for n in own]
+    packed = torch.cat([pre] + owns).to(dtype).to(cuda)
+    cu_p = [0, P]
+    for n in own:
+        cu_p.append(cu_p[-1] + n)
+    o = ops.attention(packed, torch.tensor(cu_p, dtype=torch.int32, device=cuda), max(own + [P]), Hq, Hkv, D,
+                      1.0 / math.sqrt(D), True, shared_prefix_len=P)
+    # reference: every sequence with its own copy of the prefix
+    full = torch.cat([torch.cat([pre, x]) for x in owns]).to(dtype).to(cuda)
+    cu_f = [0]
+    for n in own:
+        cu_f.append(cu_f[-1] + P + n)
+    ref = _attn_ref(full, cu_f, Hq, Hkv, D, 1.0 / math.sqrt(D), True)
+    tol = 2e-3 if dtype == torch.float16 else 1.2e-2
+    assert rel_l2(o[:P].float(), ref[:P]) < tol  # the prefix rows themselves (= the first copy's)
+    for i, n in enumerate(own):
+        got = o[cu_p[i + 1]:cu_p[i + 2]].float()
+        want = ref[cu_f[i] + P:cu_f[i + 1]]
+        assert rel_l2(got, want) < tol, (i, n)

@@ -275,3 +275,35 @@ def test_streaming_submit_equals_blocking_call(cuda):
         assert set(got) == set(ref)
         for k in ref:
             assert torch.equal(got[k], ref[k]), k
+
+
+def test_shared_prefix_forward_equals_reference_layout(cuda):
+    """forward_losses with the prompt prefix computed once per step (share_prefix=True, the default) against the same
+    step in the reference's layout (every sequence carries its own prefix rows): same losses, same logits on the consumed
+    rows, up to the rounding of a different attention tiling."""
+    from oracle import configs
+    from llm_speech_summarization_b200.step import AudioPromptStep
+    enc_cfg, llm_cfg = configs.TINY_ENCODER, configs.TINY_LLAMA
+    enc_sd = configs.make_encoder_state_dict(enc_cfg, seed=3)
+    llm_sd = configs.make_llm_state_dict(llm_cfg, seed=4, dtype=torch.bfloat16)
+    cfg, enc, llm = build_product(enc_cfg, llm_cfg, enc_sd, llm_sd, cuda)
+    tok = configs.stub_tokenizer(llm_cfg)
+    utts = [configs.synthetic_utterance(llm_cfg, 40 + i, 16000, T=7 + i, R=5 + i) for i in range(3)]
+    waves = torch.stack([u[0] for u in utts]).to(cuda)
+    outs = {}
+    for share in (True, False):
+        step = AudioPromptStep(enc, llm, tok, llm_cfg.llm_type, share_prefix=share, fd_loss_connector_layers=(0, 1, 2))
+        outs[share] = step.forward_losses(waves, [u[1] for u in utts], [u[2] for u in utts], keep=True)
+    a, b = outs[True], outs[False]
+    assert a["plan"].shared_prefix_len == len(step.prefix) > 0 and b["plan"].shared_prefix_len == 0
+    assert a["plan"].rows == b["plan"].rows - (2 * 3 - 1) * len(step.prefix)
+    for k in ("ntp_loss", "ld_loss", "fd_loss", "total_loss"):
+        assert torch.allclose(a[k], b[k], rtol=2e-3, atol=1e-5), k
+    assert rel_l2(a["student_logits"].float(), b["student_logits"].float()) < 4e-3
+    assert rel_l2(a["teacher_logits"].float(), b["teacher_logits"].float()) < 4e-3
+    # the batched inference prefill shares the prefix the same way
+    la, _ = AudioPromptStep(enc, llm, tok, llm_cfg.llm_type, share_prefix=True,
+                            fd_loss_connector_layers=(0, 1)).prefill_prompts(waves)
+    lb, _ = AudioPromptStep(enc, llm, tok, llm_cfg.llm_type, share_prefix=False,
+                            fd_loss_connector_layers=(0, 1)).prefill_prompts(waves)
+    assert rel_l2(la.float(), lb.float()) < 4e-3
