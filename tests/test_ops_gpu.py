@@ -525,3 +525,10 @@ def test_attention_shared_prefix_equals_per_sequence_copies(cuda, P, Hq, Hkv, ow
         got = o[cu_p[i + 1]:cu_p[i + 2]].float()
         want = ref[cu_f[i] + P:cu_f[i + 1]]
         assert rel_l2(got, want) < tol, (i, n)
+
+
+@pytest.mark.timeout(120)
+def test_attention_shared_prefix_pipelined(cuda, attn_pipelined):
+    """The shared-prefix key block through the pipelined issuer (two-block look-ahead cursor across items)."""
+    test_attention_shared_prefix_equals_per_sequence_copies(cuda, 9, 24, 8, [191, 108, 191, 108], torch.float16)
+    test_attention_shared_prefix_equals_per_sequence_copies(cuda, 9, 4, 2, [1, 55, 56, 64, 65, 130], torch.bfloat16)
