@@ -552,7 +552,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                            2 * ((((un.tile - p.tail_first) * CG + static_cast<int>(cta_rank)) * 4 + quarter) * 2 + half);
         if (part && p.epi == EPI_F32) {
           if (lane == 0) {
-            while (ptx::ld_acquire_gpu(tflag) == 0) __nanosleep(64);
+            // bounded like every other wait of this kernel: slice 0 runs on a lower-numbered, co-resident CTA pair and
+            // publishes within microseconds; ~4 s without the flag means a broken launch, and a trap beats a hang
+            unsigned spins = 0;
+            while (ptx::ld_acquire_gpu(tflag) == 0) {
+              __nanosleep(64);
+              if (++spins > (1u << 26)) __trap();
+            }
             ptx::fence_proxy_async_all();
           }
           __syncwarp();
